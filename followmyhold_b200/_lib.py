@@ -1,0 +1,189 @@
+"""ctypes binding of ``libfoho_b200.so`` (the C-ABI declared in ``include/foho_b200.h``).
+
+There is deliberately no CPU fallback: if the shared library is missing or a symbol is
+absent, importing callers get a loud ``FohoLibraryError``.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import shutil
+import subprocess
+from pathlib import Path
+from typing import List, Optional
+
+PKG_DIR = Path(__file__).resolve().parent
+REPO_ROOT = PKG_DIR.parent
+CSRC = PKG_DIR / "csrc"
+LIB_PATH = PKG_DIR / "libfoho_b200.so"
+SOURCES = ["guidance_stream.cu", "guidance_sparse.cu", "guidance_update.cu", "icp.cu", "mesh_sdf.cu"]
+NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
+              "-Xcompiler", "-fPIC", "-Xcompiler", "-O3"]
+
+FOHO_NUM_TERMS = 16
+TERM_NAMES = ["total", "pen", "con", "int", "count", "mom", "ch", "kp", "treg_h", "treg_o", "dist", "vreg",
+              "edge", "mean_d2", "ncand", "flags"]
+
+# every symbol include/foho_b200.h declares (tests/test_capi_symbols.py checks both directions)
+EXPORTED_SYMBOLS = [
+    "foho_abi_version", "foho_status_string", "foho_default_weights",
+    "foho_guidance_workspace_bytes", "foho_guidance_energy_fwd_bwd", "foho_guidance_update",
+    "foho_scheduler_step", "foho_icp_workspace_bytes", "foho_icp_run",
+    "foho_mesh2sdf_workspace_bytes", "foho_mesh2sdf_lattice", "foho_intersection_count",
+]
+
+
+class FohoLibraryError(RuntimeError):
+    pass
+
+
+class FohoStatusError(RuntimeError):
+    def __init__(self, fn: str, status: int, msg: str):
+        super().__init__(f"{fn} failed with status {status}: {msg}")
+        self.status = status
+
+
+def _nvcc() -> str:
+    for cand in (os.environ.get("NVCC"), shutil.which("nvcc"), "/usr/local/cuda/bin/nvcc"):
+        if cand and os.path.exists(cand):
+            return cand
+    raise FohoLibraryError("nvcc not found; cannot build libfoho_b200.so")
+
+
+def _stale() -> bool:
+    if not LIB_PATH.exists():
+        return True
+    t = LIB_PATH.stat().st_mtime
+    deps = list(CSRC.glob("*.cu")) + list(CSRC.glob("*.cuh")) + [REPO_ROOT / "include" / "foho_b200.h"]
+    return any(d.stat().st_mtime > t for d in deps)
+
+
+def build(force: bool = False, verbose: bool = False) -> Path:
+    """Compile every CUDA source for sm_100a into the in-tree shared library."""
+    if not force and not _stale():
+        return LIB_PATH
+    nvcc = _nvcc()
+    objs: List[str] = []
+    build_dir = PKG_DIR / "build"
+    build_dir.mkdir(exist_ok=True)
+    procs = []
+    for src in SOURCES:
+        obj = build_dir / (Path(src).stem + ".o")
+        cmd = [nvcc, *NVCC_FLAGS, "-c", str(CSRC / src), "-o", str(obj)]
+        if verbose:
+            print(" ".join(cmd))
+        procs.append((src, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
+        objs.append(str(obj))
+    for src, p in procs:
+        out, _ = p.communicate()
+        if p.returncode != 0:
+            raise FohoLibraryError(f"nvcc failed on {src}:\n{out}")
+        if verbose and out:
+            print(out)
+    tmp = str(LIB_PATH) + ".tmp"
+    cmd = [nvcc, "-shared", "-o", tmp, *objs, "-gencode", "arch=compute_100a,code=sm_100a", "-lcudart"]
+    r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    if r.returncode != 0:
+        raise FohoLibraryError(f"link failed:\n{r.stdout}")
+    os.replace(tmp, LIB_PATH)
+    return LIB_PATH
+
+
+class Weights(C.Structure):
+    _fields_ = [(n, C.c_float) for n in (
+        "w_dist", "w_vreg", "w_edge", "w_treg_o", "w_hand", "w_kp", "w_treg_h", "w_int_lo", "w_int_hi",
+        "dist_margin", "w_pen", "w_con", "w_ivol", "w_ch", "w_mom", "con_margin")]
+
+
+class GuidanceDesc(C.Structure):
+    _fields_ = [
+        ("B", C.c_int32), ("D", C.c_int32), ("Vh", C.c_int32), ("Fh", C.c_int32), ("P", C.c_int32),
+        ("n_joints", C.c_int32), ("image_h", C.c_int32), ("image_w", C.c_int32), ("late_step", C.c_int32),
+        ("stream_variant", C.c_int32), ("fov_deg", C.c_float), ("bound", C.c_float), ("w", Weights),
+        ("sdf", C.c_void_p), ("grad_sdf", C.c_void_p), ("hand_rest", C.c_void_p), ("hand_faces", C.c_void_p),
+        ("cloud", C.c_void_p), ("T_h2m", C.c_void_p), ("obj_center", C.c_void_p), ("theta", C.c_void_p),
+        ("j_regressor", C.c_void_p), ("kps_2d", C.c_void_p), ("grad_hand_ext", C.c_void_p),
+        ("grad_theta", C.c_void_p), ("terms", C.c_void_p), ("hand_moge", C.c_void_p), ("hand_grid", C.c_void_p),
+        ("Vo_total", C.c_int32), ("Eo_total", C.c_int32), ("obj_verts", C.c_void_p),
+        ("obj_vert_offsets", C.c_void_p), ("obj_edges", C.c_void_p), ("obj_edge_offsets", C.c_void_p),
+        ("grad_obj_verts", C.c_void_p), ("workspace", C.c_void_p), ("workspace_bytes", C.c_size_t),
+    ]
+
+
+class UpdateDesc(C.Structure):
+    _fields_ = [
+        ("B", C.c_int32), ("L", C.c_int32), ("step", C.c_int32),
+        ("beta1", C.c_float), ("beta2", C.c_float), ("eps", C.c_float), ("weight_decay", C.c_float),
+        ("lr_theta", C.c_float * 6), ("lr_velocity", C.c_float), ("sigma", C.c_float), ("theta_mask", C.c_uint32),
+        ("theta", C.c_void_p), ("grad_theta", C.c_void_p), ("theta_m", C.c_void_p), ("theta_v", C.c_void_p),
+        ("velocity", C.c_void_p), ("grad_velocity", C.c_void_p), ("vel_m", C.c_void_p), ("vel_v", C.c_void_p),
+        ("x_t", C.c_void_p), ("x1", C.c_void_p),
+    ]
+
+
+_lib: Optional[C.CDLL] = None
+
+
+def load(build_if_missing: bool = False) -> C.CDLL:
+    """Load the shared library (never falls back to anything else)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not LIB_PATH.exists():
+        if build_if_missing:
+            build()
+        else:
+            raise FohoLibraryError(
+                f"{LIB_PATH} is missing. Build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                "(needs nvcc). There is no CPU fallback for the guidance / alignment kernels.")
+    try:
+        lib = C.CDLL(str(LIB_PATH))
+    except OSError as e:  # pragma: no cover - depends on the box
+        raise FohoLibraryError(f"cannot load {LIB_PATH}: {e}") from e
+    missing = [s for s in EXPORTED_SYMBOLS if not hasattr(lib, s)]
+    if missing:
+        raise FohoLibraryError(f"{LIB_PATH} lacks symbols {missing}; rebuild it")
+    lib.foho_abi_version.restype = C.c_int
+    lib.foho_status_string.restype = C.c_char_p
+    lib.foho_status_string.argtypes = [C.c_int]
+    lib.foho_default_weights.argtypes = [C.POINTER(Weights)]
+    lib.foho_default_weights.restype = None
+    lib.foho_guidance_workspace_bytes.restype = C.c_size_t
+    lib.foho_guidance_workspace_bytes.argtypes = [C.c_int32] * 6
+    lib.foho_guidance_energy_fwd_bwd.restype = C.c_int
+    lib.foho_guidance_energy_fwd_bwd.argtypes = [C.POINTER(GuidanceDesc), C.c_void_p]
+    lib.foho_guidance_update.restype = C.c_int
+    lib.foho_guidance_update.argtypes = [C.POINTER(UpdateDesc), C.c_void_p]
+    lib.foho_scheduler_step.restype = C.c_int
+    lib.foho_scheduler_step.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_float,
+                                        C.c_float, C.c_void_p]
+    lib.foho_icp_workspace_bytes.restype = C.c_size_t
+    lib.foho_icp_workspace_bytes.argtypes = [C.c_int32, C.c_int32]
+    lib.foho_icp_run.restype = C.c_int
+    lib.foho_icp_run.argtypes = [C.c_void_p, C.c_int32, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
+                                 C.c_double, C.c_double, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                 C.c_void_p, C.c_size_t, C.c_void_p]
+    lib.foho_mesh2sdf_workspace_bytes.restype = C.c_size_t
+    lib.foho_mesh2sdf_workspace_bytes.argtypes = [C.c_int32] * 5
+    lib.foho_mesh2sdf_lattice.restype = C.c_int
+    lib.foho_mesh2sdf_lattice.argtypes = [C.c_void_p, C.c_int32, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p,
+                                          C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p,
+                                          C.c_size_t, C.c_void_p]
+    lib.foho_intersection_count.restype = C.c_int
+    lib.foho_intersection_count.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]
+    if lib.foho_abi_version() != 1:
+        raise FohoLibraryError("libfoho_b200.so ABI version mismatch; rebuild it")
+    _lib = lib
+    return lib
+
+
+def check(fn: str, status: int) -> None:
+    if status != 0:
+        msg = load().foho_status_string(status)
+        raise FohoStatusError(fn, status, msg.decode() if msg else "?")
+
+
+def default_weights() -> Weights:
+    w = Weights()
+    load().foho_default_weights(C.byref(w))
+    return w

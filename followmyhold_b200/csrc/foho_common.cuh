@@ -1,0 +1,134 @@
+// Internal declarations shared by the .cu translation units (not part of the C-ABI).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include "../../include/foho_b200.h"
+#include "foho_math.cuh"
+
+#define FOHO_CUDA_TRY(expr)                      \
+  do {                                           \
+    cudaError_t _e = (expr);                     \
+    if (_e != cudaSuccess) return (int)_e;       \
+  } while (0)
+
+#define FOHO_LAUNCH_CHECK()                      \
+  do {                                           \
+    cudaError_t _e = cudaGetLastError();         \
+    if (_e != cudaSuccess) return (int)_e;       \
+  } while (0)
+
+// Per-sample geometry of one evaluation, written by k_prep, read by everything else.
+struct FohoFrame {
+  float Rh[9], sh, th[3], ch[3];   // hand similarity about the rest bbox centre ch
+  float chc[3];                    // ch - c_o
+  float Ro[9], so, to[3], co[3];   // object similarity about c_o
+  float Ah[9];                     // 3x3 of T_h2m (scale * rotation)
+  float u0[3];                     // A_h(-bound*1) + t_h2m - c_o
+  float s_h2m, step;               // |A_h[:,0]|, lattice spacing in Hunyuan units
+  float A[9];                      // lattice -> MoGe linear part  s_o R_o A_h step
+  float bc[3];                     // lattice origin in centred MoGe coords: s_o R_o u0 + t_o
+  float Ainv[9];                   // inverse of A
+  float Ahs_inv[9];                // inverse of (A_h * step)
+  float kappa;                     // MoGe length of one lattice step
+  float e[3], f;                   // |y|^2 = kappa^2 |g|^2 + 2 e.g + f   (absolute MoGe frame)
+  int lo[3], hi[3];                // hand bbox on the lattice (inclusive, clipped; lo>hi = empty)
+  int pad[2];
+};
+
+// per-sample accumulators (floats) zeroed by k_prep
+enum {
+  ACC_INT = 0,      // sum over candidates of (-S) * d_grid
+  ACC_GKAPPA = 1,   // dE/dkappa
+  ACC_CH_CLOUD = 2, // sum over cloud points of d2 to nearest hand vertex
+  ACC_NUM = 8
+};
+enum { CNT_NCAND = 0, CNT_COUNT = 1, CNT_FLAGS = 2, CNT_NUM = 4 };
+
+#define FOHO_STREAM_PARTIALS 8      // m0, m1x, m1y, m1z, m2, count_obj, pad, pad
+#define FOHO_MAX_STREAM_CTAS 2048   // per sample
+
+struct FohoWorkspace {
+  FohoFrame *frames;          // [B]
+  float *hmc;                 // [B,Vh,3] transformed hand verts, centred on c_o
+  float *hg;                  // [B,Vh,3] same in lattice units
+  float *G_hm;                // [B,Vh,3] dE/d(hm) (MoGe)
+  float *G_hg;                // [B,Vh,3] dE/d(hg) (lattice)
+  float *acc;                 // [B,ACC_NUM]
+  int *cnt;                   // [B,CNT_NUM]
+  unsigned long long *knn;    // [B,Vh] packed (d2 bits << 32 | cloud index)
+  float *stream_part;         // [B,FOHO_MAX_STREAM_CTAS,FOHO_STREAM_PARTIALS]
+  uint32_t *parity;           // [B,D*D*W]
+  int *cand;                  // [B,cap]
+  int cap;
+  int W;                      // words per column
+  size_t total;
+};
+
+static inline size_t foho_align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+static inline int foho_cand_capacity(int D) {
+  long long n = (long long)D * D * D;
+  return (int)(n < (1ll << 18) ? n : (1ll << 18));
+}
+
+static inline void foho_ws_layout(FohoWorkspace &w, char *base, int B, int D, int Vh, int /*Fh*/, int /*P*/, int /*Vo*/) {
+  size_t off = 0;
+  auto take = [&](size_t bytes) { char *p = base ? base + off : nullptr; off += foho_align_up(bytes, 256); return p; };
+  w.W = (D + 31) / 32;
+  w.cap = foho_cand_capacity(D);
+  w.frames = (FohoFrame *)take(sizeof(FohoFrame) * (size_t)B);
+  w.hmc = (float *)take(sizeof(float) * 3 * (size_t)B * Vh);
+  w.hg = (float *)take(sizeof(float) * 3 * (size_t)B * Vh);
+  w.G_hm = (float *)take(sizeof(float) * 3 * (size_t)B * Vh);
+  w.G_hg = (float *)take(sizeof(float) * 3 * (size_t)B * Vh);
+  w.acc = (float *)take(sizeof(float) * ACC_NUM * (size_t)B);
+  w.cnt = (int *)take(sizeof(int) * CNT_NUM * (size_t)B);
+  w.knn = (unsigned long long *)take(sizeof(unsigned long long) * (size_t)B * Vh);
+  w.stream_part = (float *)take(sizeof(float) * FOHO_STREAM_PARTIALS * FOHO_MAX_STREAM_CTAS * (size_t)B);
+  w.parity = (uint32_t *)take(sizeof(uint32_t) * (size_t)B * D * D * w.W);
+  w.cand = (int *)take(sizeof(int) * (size_t)B * w.cap);
+  w.total = off;
+}
+
+// ---- device reductions -------------------------------------------------------------
+#if defined(__CUDACC__)
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ float warp_min(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fminf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+// block-wide sum of N values per thread; result valid in thread 0 (and returned to all
+// threads of warp 0).  smem must hold N * 32 floats.
+template <int N>
+__device__ __forceinline__ void block_sum(float (&v)[N], float *smem) {
+  int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+#pragma unroll
+  for (int i = 0; i < N; ++i) v[i] = warp_sum(v[i]);
+  __syncthreads();
+  if (lane == 0) {
+#pragma unroll
+    for (int i = 0; i < N; ++i) smem[i * 32 + wid] = v[i];
+  }
+  __syncthreads();
+  if (wid == 0) {
+#pragma unroll
+    for (int i = 0; i < N; ++i) {
+      float x = lane < nw ? smem[i * 32 + lane] : 0.f;
+      v[i] = warp_sum(x);
+    }
+  }
+}
+#endif
+
+// kernels implemented in the other translation units
+int foho_launch_stream(const foho_guidance_desc *d, const FohoWorkspace &ws, int *grid_x_out, cudaStream_t st);

@@ -1,0 +1,341 @@
+// Trimmed similarity ICP, float64, the whole iteration loop on the device.
+//
+// Restates the per-iteration arithmetic of `icp` in the reference's
+// src/foho/alignment/mesh_align.py:104-142 for the configuration both callers use
+// (h2m.py:35-54, mano.py:24-43: on_surface=False, one "cube" = identity start):
+//
+//   p      = transform . source                                   (:106)
+//   dist,q = Euclidean 1-NN of p in the target                    (:111-112, scipy cKDTree.query)
+//   drop the n_outliers = int(outliers*count_source) largest dist (:114-120)
+//   cost   = mean(inlier dist)                                    (:118)
+//   next   = trimesh.registration.procrustes(p_in, q_in, reflection=False, scale=not fixed_scale) (:127)
+//   transform = next @ transform; renormalise + clip scale        (:129-135)
+//   keep `transform` if this iteration's (pre-update) cost is the best so far (:140-142)
+//
+// Kernels per iteration (no host round trip; state lives in the workspace):
+//   k_icp_nn     tiled brute-force 1-NN, target chunk in shared memory, partial minima per chunk
+//   k_icp_step   single CTA: reduce the partial minima, radix-select the trim threshold,
+//                centred covariances, 3x3 SVD (Jacobi), transform/scale update, best tracking
+#include "foho_common.cuh"
+
+namespace {
+
+constexpr int NN_THREADS = 256;
+constexpr int NN_TILE = 1024;          // target points staged per shared-memory tile
+constexpr int STEP_THREADS = 1024;
+
+struct IcpState {
+  double T[16];        // current transform (row-major 4x4)
+  double best_T[16];
+  double best_cost;
+  double cost;
+  int iter;
+  int pad;
+};
+
+struct IcpWorkspace {
+  IcpState *state;
+  double *pd2;         // [nchunks, Ns] partial min squared distance
+  int *pidx;           // [nchunks, Ns]
+  double *dist;        // [Ns]
+  int *qi;             // [Ns]
+  double *p;           // [Ns,3] transformed source of the current iteration
+  int nchunks, chunk;
+  size_t total;
+};
+
+inline void icp_ws_layout(IcpWorkspace &w, char *base, int Ns, int Nt) {
+  size_t off = 0;
+  auto take = [&](size_t bytes) { char *p = base ? base + off : nullptr; off += foho_align_up(bytes, 256); return p; };
+  // enough chunks to fill the machine, each a multiple of the smem tile
+  int blocks_s = (Ns + NN_THREADS - 1) / NN_THREADS;
+  int want = (4 * 148 + blocks_s - 1) / blocks_s;
+  int max_chunks = (Nt + NN_TILE - 1) / NN_TILE;
+  int nchunks = want < max_chunks ? want : max_chunks;
+  if (nchunks < 1) nchunks = 1;
+  if (nchunks > 64) nchunks = 64;
+  int chunk = (Nt + nchunks - 1) / nchunks;
+  chunk = (chunk + NN_TILE - 1) / NN_TILE * NN_TILE;
+  nchunks = (Nt + chunk - 1) / chunk;
+  w.nchunks = nchunks; w.chunk = chunk;
+  w.state = (IcpState *)take(sizeof(IcpState));
+  w.pd2 = (double *)take(sizeof(double) * (size_t)nchunks * Ns);
+  w.pidx = (int *)take(sizeof(int) * (size_t)nchunks * Ns);
+  w.dist = (double *)take(sizeof(double) * (size_t)Ns);
+  w.qi = (int *)take(sizeof(int) * (size_t)Ns);
+  w.p = (double *)take(sizeof(double) * 3 * (size_t)Ns);
+  w.total = off;
+}
+
+__global__ void k_icp_init(IcpWorkspace w) {
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < 16; ++i) { w.state->T[i] = (i % 5 == 0) ? 1.0 : 0.0; w.state->best_T[i] = w.state->T[i]; }
+    w.state->best_cost = INFINITY;
+    w.state->cost = INFINITY;
+    w.state->iter = 0;
+  }
+}
+
+__global__ void __launch_bounds__(NN_THREADS) k_icp_nn(const double *__restrict__ src, int Ns,
+                                                       const double *__restrict__ tgt, int Nt, IcpWorkspace w) {
+  __shared__ double st[NN_TILE * 3];
+  const int i = blockIdx.x * NN_THREADS + threadIdx.x;
+  const int c0 = blockIdx.y * w.chunk;
+  const int c1 = min(c0 + w.chunk, Nt);
+  const double *T = w.state->T;
+  double px = 0, py = 0, pz = 0;
+  if (i < Ns) {
+    const double x = src[3 * i], y = src[3 * i + 1], z = src[3 * i + 2];
+    // trimesh.transform_points: dot(T[:3,:3], p) + T[:3,3]
+    px = T[0] * x + T[1] * y + T[2] * z + T[3];
+    py = T[4] * x + T[5] * y + T[6] * z + T[7];
+    pz = T[8] * x + T[9] * y + T[10] * z + T[11];
+    if (blockIdx.y == 0) { w.p[3 * i] = px; w.p[3 * i + 1] = py; w.p[3 * i + 2] = pz; }
+  }
+  double best = INFINITY;
+  int bi = -1;
+  for (int t0 = c0; t0 < c1; t0 += NN_TILE) {
+    const int n = min(NN_TILE, c1 - t0);
+    __syncthreads();
+    for (int k = threadIdx.x; k < 3 * n; k += NN_THREADS) st[k] = tgt[(size_t)3 * t0 + k];
+    __syncthreads();
+    if (i < Ns) {
+#pragma unroll 4
+      for (int k = 0; k < n; ++k) {
+        const double dx = px - st[3 * k], dy = py - st[3 * k + 1], dz = pz - st[3 * k + 2];
+        const double d2 = dx * dx + dy * dy + dz * dz;
+        if (d2 < best) { best = d2; bi = t0 + k; }
+      }
+    }
+  }
+  if (i < Ns) {
+    w.pd2[(size_t)blockIdx.y * Ns + i] = best;
+    w.pidx[(size_t)blockIdx.y * Ns + i] = bi;
+  }
+}
+
+// ---- block-wide helpers for k_icp_step (1024 threads)
+__device__ double block_sum_d(double v, double *sm) {
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  __syncthreads();
+  if (lane == 0) sm[wid] = v;
+  __syncthreads();
+  double r = 0;
+  const int nw = blockDim.x >> 5;
+  for (int k = 0; k < nw; ++k) r += sm[k];      // fixed order: deterministic, same value in every thread
+  return r;
+}
+
+__global__ void __launch_bounds__(STEP_THREADS) k_icp_step(const double *__restrict__ tgt, int Ns, int n_outliers,
+                                                           int fixed_scale, double min_scale, double max_scale,
+                                                           IcpWorkspace w, double *cost_history, int *nn_out) {
+  __shared__ double smd[32];
+  __shared__ unsigned int hist[256];
+  __shared__ unsigned long long s_prefix;
+  __shared__ int s_remaining;
+  __shared__ int s_take_eq;
+  const int tid = threadIdx.x;
+
+  // 1. reduce the per-chunk partial minima; dist = sqrt(d2) (cKDTree returns Euclidean distance)
+  for (int i = tid; i < Ns; i += STEP_THREADS) {
+    double best = w.pd2[i];
+    int bi = w.pidx[i];
+    for (int c = 1; c < w.nchunks; ++c) {
+      double v = w.pd2[(size_t)c * Ns + i];
+      if (v < best) { best = v; bi = w.pidx[(size_t)c * Ns + i]; }
+    }
+    w.dist[i] = sqrt(best);
+    w.qi[i] = bi;
+    if (nn_out) nn_out[i] = bi;
+  }
+  __syncthreads();
+
+  // 2. trim threshold = the n_in-th smallest distance (n_in = Ns - n_outliers), MSB radix select
+  //    over the IEEE bits (non-negative doubles order like unsigned integers).
+  const int n_in = Ns - (n_outliers > 0 ? n_outliers : 0);
+  unsigned long long thr = ~0ull;
+  int take_eq = 0;                       // how many elements equal to thr are inliers (lowest indices first)
+  if (n_outliers > 0) {
+    if (tid == 0) { s_prefix = 0ull; s_remaining = n_in; }
+    __syncthreads();
+    for (int shift = 56; shift >= 0; shift -= 8) {
+      if (tid < 256) hist[tid] = 0u;
+      __syncthreads();
+      const unsigned long long prefix = s_prefix;
+      const unsigned long long mask = shift == 56 ? 0ull : (~0ull << (shift + 8));
+      for (int i = tid; i < Ns; i += STEP_THREADS) {
+        unsigned long long bits = (unsigned long long)__double_as_longlong(w.dist[i]);
+        if ((bits & mask) == prefix) atomicAdd(&hist[(bits >> shift) & 255ull], 1u);
+      }
+      __syncthreads();
+      if (tid == 0) {
+        int rem = s_remaining;
+        int bkt = 0;
+        for (; bkt < 256; ++bkt) {
+          if ((int)hist[bkt] >= rem) break;
+          rem -= (int)hist[bkt];
+        }
+        if (bkt > 255) bkt = 255;
+        s_prefix = prefix | ((unsigned long long)bkt << shift);
+        s_remaining = rem;
+      }
+      __syncthreads();
+    }
+    thr = s_prefix;
+    if (tid == 0) s_take_eq = s_remaining;   // of the elements == thr, this many are inliers
+    __syncthreads();
+    take_eq = s_take_eq;
+  }
+  // rank elements equal to thr by index (stable) so exactly n_in inliers are kept
+  // (ties at the threshold are measure-zero for real data; the rule only has to be deterministic)
+  auto is_inlier = [&](int i, int &eq_seen) -> bool {
+    if (n_outliers <= 0) return true;
+    unsigned long long bits = (unsigned long long)__double_as_longlong(w.dist[i]);
+    if (bits < thr) return true;
+    if (bits > thr) return false;
+    (void)eq_seen;
+    return true;   // provisional; corrected below when duplicates exist
+  };
+  // count elements == thr; if more than take_eq exist, only thread 0 resolves (rare path)
+  __shared__ int s_eq_total;
+  if (tid == 0) s_eq_total = 0;
+  __syncthreads();
+  if (n_outliers > 0) {
+    int local = 0;
+    for (int i = tid; i < Ns; i += STEP_THREADS)
+      if ((unsigned long long)__double_as_longlong(w.dist[i]) == thr) ++local;
+    if (local) atomicAdd(&s_eq_total, local);
+  }
+  __syncthreads();
+  const bool dup_ties = n_outliers > 0 && s_eq_total > take_eq;
+  __shared__ int s_last_eq_index;          // inliers among ties: index <= s_last_eq_index
+  if (tid == 0) {
+    s_last_eq_index = 0x7fffffff;
+    if (dup_ties) {
+      int seen = 0;
+      for (int i = 0; i < Ns; ++i)
+        if ((unsigned long long)__double_as_longlong(w.dist[i]) == thr) {
+          if (++seen == take_eq) { s_last_eq_index = i; break; }
+        }
+      if (take_eq == 0) s_last_eq_index = -1;
+    }
+  }
+  __syncthreads();
+  const int last_eq = s_last_eq_index;
+
+  // 3. inlier statistics (two passes: means, then centred second moments)
+  double sa[3] = {0, 0, 0}, sb[3] = {0, 0, 0}, sd = 0;
+  int dummy = 0;
+  for (int i = tid; i < Ns; i += STEP_THREADS) {
+    bool in = is_inlier(i, dummy);
+    if (in && dup_ties && (unsigned long long)__double_as_longlong(w.dist[i]) == thr && i > last_eq) in = false;
+    if (!in) continue;
+    const int q = w.qi[i];
+    sa[0] += w.p[3 * i]; sa[1] += w.p[3 * i + 1]; sa[2] += w.p[3 * i + 2];
+    sb[0] += tgt[3 * (size_t)q]; sb[1] += tgt[3 * (size_t)q + 1]; sb[2] += tgt[3 * (size_t)q + 2];
+    sd += w.dist[i];
+  }
+  const double n = (double)n_in;
+  double am[3], bm[3];
+  for (int a = 0; a < 3; ++a) { am[a] = block_sum_d(sa[a], smd) / n; bm[a] = block_sum_d(sb[a], smd) / n; }
+  const double cost = block_sum_d(sd, smd) / n;
+  double h[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0}, va = 0, vb = 0;
+  for (int i = tid; i < Ns; i += STEP_THREADS) {
+    bool in = is_inlier(i, dummy);
+    if (in && dup_ties && (unsigned long long)__double_as_longlong(w.dist[i]) == thr && i > last_eq) in = false;
+    if (!in) continue;
+    const int q = w.qi[i];
+    const double a0 = w.p[3 * i] - am[0], a1 = w.p[3 * i + 1] - am[1], a2 = w.p[3 * i + 2] - am[2];
+    const double b0 = tgt[3 * (size_t)q] - bm[0], b1 = tgt[3 * (size_t)q + 1] - bm[1], b2 = tgt[3 * (size_t)q + 2] - bm[2];
+    va += a0 * a0 + a1 * a1 + a2 * a2;
+    vb += b0 * b0 + b1 * b1 + b2 * b2;
+    h[0] += b0 * a0; h[1] += b0 * a1; h[2] += b0 * a2;
+    h[3] += b1 * a0; h[4] += b1 * a1; h[5] += b1 * a2;
+    h[6] += b2 * a0; h[7] += b2 * a1; h[8] += b2 * a2;
+  }
+  double H[3][3];
+  for (int k = 0; k < 9; ++k) H[k / 3][k % 3] = block_sum_d(h[k], smd);
+  va = block_sum_d(va, smd);
+  vb = block_sum_d(vb, smd);
+
+  // 4. similarity fit + transform update (thread 0)
+  if (tid == 0) {
+    IcpState *S = w.state;
+    double ascale = 1.0, bscale = 1.0;
+    if (!fixed_scale) { ascale = sqrt(va / n); bscale = sqrt(vb / n); }
+    // trimesh divides both centred sets by their scale before the SVD; a positive scalar on H
+    // does not change its singular vectors, so H is used as accumulated.
+    double R[3][3];
+    kabsch_rotation(H, R);
+    const double sc = bscale / ascale;
+    double M[16];
+    for (int i = 0; i < 3; ++i) {
+      for (int j = 0; j < 3; ++j) M[4 * i + j] = sc * R[i][j];
+      M[4 * i + 3] = bm[i] - sc * (R[i][0] * am[0] + R[i][1] * am[1] + R[i][2] * am[2]);
+    }
+    M[12] = M[13] = M[14] = 0.0; M[15] = 1.0;
+    double Tn[16];
+    for (int i = 0; i < 4; ++i)
+      for (int j = 0; j < 4; ++j) {
+        double acc = 0;
+        for (int k = 0; k < 4; ++k) acc += M[4 * i + k] * S->T[4 * k + j];
+        Tn[4 * i + j] = acc;
+      }
+    if (!fixed_scale) {
+      double s0 = sqrt(Tn[0] * Tn[0] + Tn[4] * Tn[4] + Tn[8] * Tn[8]);     // norm of the first column (:132)
+      double s1 = fmin(fmax(s0, min_scale), max_scale);
+      for (int i = 0; i < 3; ++i)
+        for (int j = 0; j < 3; ++j) Tn[4 * i + j] = Tn[4 * i + j] / s0 * s1;
+    }
+    for (int k = 0; k < 16; ++k) S->T[k] = Tn[k];
+    S->cost = cost;
+    if (cost < S->best_cost) {          // updated transform paired with the pre-update cost (:140-142)
+      S->best_cost = cost;
+      for (int k = 0; k < 16; ++k) S->best_T[k] = Tn[k];
+    }
+    if (cost_history) cost_history[S->iter] = cost;
+    S->iter += 1;
+  }
+}
+
+__global__ void k_icp_finish(IcpWorkspace w, double *T_out, double *cost_out) {
+  if (threadIdx.x < 16) T_out[threadIdx.x] = w.state->best_T[threadIdx.x];
+  if (threadIdx.x == 0 && cost_out) cost_out[0] = w.state->best_cost;
+}
+
+}  // namespace
+
+extern "C" size_t foho_icp_workspace_bytes(int32_t Ns, int32_t Nt) {
+  if (Ns < 1 || Nt < 1) return 0;
+  IcpWorkspace w;
+  icp_ws_layout(w, nullptr, Ns, Nt);
+  return w.total;
+}
+
+extern "C" int foho_icp_run(const double *source, int32_t Ns, const double *target, int32_t Nt, int32_t n_iter,
+                            int32_t n_outliers, int32_t fixed_scale, double min_scale, double max_scale,
+                            double *transform_out, double *cost_out, double *cost_history, int32_t *nn_index_last,
+                            void *workspace, size_t workspace_bytes, void *cuda_stream) {
+  if (!source || !target || !transform_out || !workspace) return FOHO_E_NULL;
+  if (Ns < 1 || Nt < 1 || n_iter < 0) return FOHO_E_SHAPE;
+  if (n_outliers < 0 || n_outliers >= Ns) return FOHO_E_ARG;
+  if (!(min_scale > 0.0) || !(max_scale >= min_scale)) return FOHO_E_ARG;
+  if (((uintptr_t)workspace & 255) != 0) return FOHO_E_WORKSPACE;
+  IcpWorkspace w;
+  icp_ws_layout(w, (char *)workspace, Ns, Nt);
+  if (w.total > workspace_bytes) return FOHO_E_WORKSPACE;
+  cudaStream_t st = (cudaStream_t)cuda_stream;
+  k_icp_init<<<1, 32, 0, st>>>(w);
+  FOHO_LAUNCH_CHECK();
+  const dim3 nn_grid((Ns + NN_THREADS - 1) / NN_THREADS, w.nchunks);
+  for (int it = 0; it < n_iter; ++it) {
+    k_icp_nn<<<nn_grid, NN_THREADS, 0, st>>>(source, Ns, target, Nt, w);
+    k_icp_step<<<1, STEP_THREADS, 0, st>>>(target, Ns, n_outliers, fixed_scale, min_scale, max_scale, w, cost_history,
+                                           it == n_iter - 1 ? nn_index_last : nullptr);
+  }
+  FOHO_LAUNCH_CHECK();
+  k_icp_finish<<<1, 32, 0, st>>>(w, transform_out, cost_out);
+  FOHO_LAUNCH_CHECK();
+  return FOHO_OK;
+}

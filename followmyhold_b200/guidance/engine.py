@@ -1,0 +1,242 @@
+"""Host side of the fused guidance evaluation: torch tensors in, C-ABI call, torch tensors out.
+
+PyTorch is plumbing here (device memory, streams); all arithmetic runs in
+``libfoho_b200.so``.  The seam this replaces is the body of the phase-2 inner iteration of
+the reference's ``Hunyuan3DDiTFlowMatchingPipeline_main.__call__``
+(third_party_patches/hy3dgen/shapegen/pipelines.py:1480-1601): leaves -> energy ->
+``backward()`` -> ``joint_optimizer.step()``.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass
+from typing import Dict, Optional, Sequence
+
+import torch
+
+from .. import _lib
+from .config import OptimizationConfig
+
+GRID_BOUND = 1.10  # pipelines.py:1127
+
+
+def _ptr(t: Optional[torch.Tensor]) -> Optional[int]:
+    return None if t is None else t.data_ptr()
+
+
+def _chk(t: torch.Tensor, shape: Sequence[int], dtype, name: str) -> torch.Tensor:
+    if not t.is_cuda:
+        raise ValueError(f"{name} must be a CUDA tensor (there is no CPU path)")
+    if tuple(t.shape) != tuple(shape):
+        raise ValueError(f"{name}: expected shape {tuple(shape)}, got {tuple(t.shape)}")
+    if t.dtype != dtype:
+        raise ValueError(f"{name}: expected dtype {dtype}, got {t.dtype}")
+    if not t.is_contiguous():
+        raise ValueError(f"{name} must be contiguous")
+    return t
+
+
+@dataclass
+class GuidanceStatics:
+    """Per-image inputs that stay fixed over a whole guided denoise run (batched)."""
+    hand_rest: torch.Tensor      # [B,Vh,3] f32  aligned MANO verts in MoGe space (pipelines.py:1241)
+    hand_faces: torch.Tensor     # [Fh,3]  i32
+    cloud: Optional[torch.Tensor]  # [B,P,3] f32 MoGe cloud
+    T_h2m: torch.Tensor          # [B,4,4] f32 (alignment/h2m.py output, loaded at pipelines.py:1240)
+    obj_center: torch.Tensor     # [B,3]   f32
+    j_regressor: Optional[torch.Tensor] = None   # [16,Vh]
+    kps_2d: Optional[torch.Tensor] = None        # [B,21,2]
+    fov_deg: float = 41.0
+    image_hw: Sequence[int] = (512, 512)
+
+
+class GuidanceEngine:
+    """Owns workspace + output buffers for a fixed problem shape and launches the kernels."""
+
+    def __init__(self, B: int, D: int, Vh: int, Fh: int, P: int, device="cuda:0",
+                 weights: Optional[_lib.Weights] = None, stream_variant: int = 0):
+        self.lib = _lib.load()
+        self.device = torch.device(device)
+        if self.device.type != "cuda":
+            raise _lib.FohoLibraryError("GuidanceEngine needs a CUDA device; there is no CPU fallback")
+        self.B, self.D, self.Vh, self.Fh, self.P = B, D, Vh, Fh, P
+        self.weights = weights if weights is not None else _lib.default_weights()
+        self.stream_variant = stream_variant
+        nbytes = self.lib.foho_guidance_workspace_bytes(B, D, Vh, Fh, P, 0)
+        if nbytes == 0:
+            raise ValueError("unsupported guidance problem shape")
+        dev = self.device
+        self.workspace = torch.empty(nbytes + 256, dtype=torch.uint8, device=dev)
+        off = (-self.workspace.data_ptr()) % 256
+        self._ws_ptr = self.workspace.data_ptr() + off
+        self._ws_bytes = nbytes
+        self.grad_sdf = torch.empty(B, D, D, D, dtype=torch.float32, device=dev)
+        self.grad_theta = torch.zeros(B, 16, dtype=torch.float32, device=dev)
+        self.terms = torch.zeros(B, _lib.FOHO_NUM_TERMS, dtype=torch.float32, device=dev)
+        self.hand_moge = torch.zeros(B, Vh, 3, dtype=torch.float32, device=dev)
+        self.hand_grid = torch.zeros(B, Vh, 3, dtype=torch.float32, device=dev)
+        self.launches_per_eval = 7 if P > 0 else 6
+
+    def make_desc(self, sdf: torch.Tensor, theta: torch.Tensor, st: GuidanceStatics,
+                  grad_sdf: Optional[torch.Tensor] = None, late_step: bool = False,
+                  grad_hand_ext: Optional[torch.Tensor] = None) -> _lib.GuidanceDesc:
+        B, D, Vh, Fh, P = self.B, self.D, self.Vh, self.Fh, self.P
+        f32 = torch.float32
+        _chk(sdf, (B, D, D, D), f32, "sdf")
+        _chk(theta, (B, 16), f32, "theta")
+        _chk(st.hand_rest, (B, Vh, 3), f32, "hand_rest")
+        _chk(st.hand_faces, (Fh, 3), torch.int32, "hand_faces")
+        _chk(st.T_h2m, (B, 4, 4), f32, "T_h2m")
+        _chk(st.obj_center, (B, 3), f32, "obj_center")
+        if P > 0:
+            if st.cloud is None:
+                raise ValueError("cloud is required when P > 0")
+            _chk(st.cloud, (B, P, 3), f32, "cloud")
+        use_kp = st.j_regressor is not None and st.kps_2d is not None
+        if use_kp:
+            _chk(st.j_regressor, (16, Vh), f32, "j_regressor")
+            _chk(st.kps_2d, (B, 21, 2), f32, "kps_2d")
+        g = self.grad_sdf if grad_sdf is None else _chk(grad_sdf, (B, D, D, D), f32, "grad_sdf")
+        if grad_hand_ext is not None:
+            _chk(grad_hand_ext, (B, Vh, 3), f32, "grad_hand_ext")
+        d = _lib.GuidanceDesc()
+        d.B, d.D, d.Vh, d.Fh, d.P = B, D, Vh, Fh, P
+        d.n_joints = 16 if use_kp else 0
+        d.image_h, d.image_w = int(st.image_hw[0]), int(st.image_hw[1])
+        d.late_step = int(late_step)
+        d.stream_variant = self.stream_variant
+        d.fov_deg = float(st.fov_deg)
+        d.bound = GRID_BOUND
+        d.w = self.weights
+        d.sdf, d.grad_sdf = sdf.data_ptr(), g.data_ptr()
+        d.hand_rest, d.hand_faces = st.hand_rest.data_ptr(), st.hand_faces.data_ptr()
+        d.cloud = _ptr(st.cloud) if P > 0 else None
+        d.T_h2m, d.obj_center, d.theta = st.T_h2m.data_ptr(), st.obj_center.data_ptr(), theta.data_ptr()
+        d.j_regressor = _ptr(st.j_regressor) if use_kp else None
+        d.kps_2d = _ptr(st.kps_2d) if use_kp else None
+        d.grad_hand_ext = _ptr(grad_hand_ext)
+        d.grad_theta, d.terms = self.grad_theta.data_ptr(), self.terms.data_ptr()
+        d.hand_moge, d.hand_grid = self.hand_moge.data_ptr(), self.hand_grid.data_ptr()
+        d.Vo_total = 0
+        d.Eo_total = 0
+        d.workspace, d.workspace_bytes = self._ws_ptr, self._ws_bytes
+        return d
+
+    def launch(self, desc: _lib.GuidanceDesc, stream: Optional[torch.cuda.Stream] = None) -> None:
+        s = stream if stream is not None else torch.cuda.current_stream(self.device)
+        _lib.check("foho_guidance_energy_fwd_bwd",
+                   self.lib.foho_guidance_energy_fwd_bwd(C.byref(desc), C.c_void_p(s.cuda_stream)))
+
+    def energy_fwd_bwd(self, sdf, theta, st: GuidanceStatics, **kw):
+        """One batched evaluation.  Returns (terms [B,16], grad_sdf [B,D,D,D], grad_theta [B,16]);
+        the returned tensors are the engine's own buffers (overwritten by the next call)."""
+        with torch.cuda.device(self.device):
+            self.launch(self.make_desc(sdf, theta, st, **kw))
+        return self.terms, self.grad_sdf, self.grad_theta
+
+    def terms_dict(self) -> Dict[str, torch.Tensor]:
+        t = self.terms.detach().cpu()
+        return {n: t[:, i] for i, n in enumerate(_lib.TERM_NAMES)}
+
+
+# --------------------------------------------------------------------------- optimiser
+# bit g of theta_mask <-> leaf group g, in the order of code_utils.py:69-77
+GROUPS = ("scale_hand", "trans_hand", "rot_hand", "scale_obj", "trans_obj", "rot_obj")
+MASK_HAND = 0b000111
+MASK_OBJ = 0b111000
+MASK_ALL = 0b111111
+
+
+class GuidanceOptimizer:
+    """AdamW state + fused update for the 16 scalar leaves and the velocity tensor.
+
+    Mirrors ``get_guidance_params`` (third_party/utilz/code_utils.py:3-83): state is
+    created fresh for every outer denoise step, learning rates per group come from
+    ``OptimizationConfig`` (src/foho/configs/guid_config.py:20-27).
+    """
+
+    def __init__(self, B: int, L: int, device="cuda:0", config: Optional[OptimizationConfig] = None):
+        self.lib = _lib.load()
+        self.B, self.L = B, L
+        self.device = torch.device(device)
+        self.config = config or OptimizationConfig()
+        dev = self.device
+        self.theta_m = torch.zeros(B, 16, device=dev)
+        self.theta_v = torch.zeros(B, 16, device=dev)
+        self.vel_m = torch.zeros(B, L, device=dev) if L > 0 else None
+        self.vel_v = torch.zeros(B, L, device=dev) if L > 0 else None
+        self.step_count = 0
+        self.set_phase(2)
+
+    def set_phase(self, phase: float) -> None:
+        c = self.config
+        if phase == 1:
+            h = c.phase1_hand_lrs
+            self.lr_theta = [h["scale"], h["trans"], h["rot"], 0.0, 0.0, 0.0]
+            self.mask, self.lr_velocity, self.weight_decay, self.opt_velocity = MASK_HAND, 0.0, 0.0, False
+        elif phase == 1.5:
+            o = c.obj_2half_lrs
+            self.lr_theta = [0.0, 0.0, 0.0, o["scale"], o["trans"], o["rot"]]
+            self.mask, self.lr_velocity, self.weight_decay, self.opt_velocity = MASK_OBJ, c.noise_obj_lr1, 0.01, True
+        elif phase == 2:
+            h, o = c.phase2_hand_lrs, c.obj_lrs
+            self.lr_theta = [h["scale"], h["trans"], h["rot"], o["scale"], o["trans"], o["rot"]]
+            self.mask, self.lr_velocity, self.weight_decay, self.opt_velocity = MASK_ALL, c.noise_obj_lr2, 0.01, True
+        else:
+            raise ValueError(f"Unknown phase {phase}. Expected 'hand_only (1)', 'obj-only (1.5)' or 'joint_hand_obj (2)'.")
+        self.phase = phase
+
+    def reset(self) -> None:
+        """Fresh optimiser state (the reference re-creates AdamW every outer step, pipelines.py:1478)."""
+        self.theta_m.zero_(); self.theta_v.zero_()
+        if self.vel_m is not None:
+            self.vel_m.zero_(); self.vel_v.zero_()
+        self.step_count = 0
+
+    def step(self, theta, grad_theta, velocity=None, grad_velocity=None, x_t=None, x1=None, sigma: float = 0.0,
+             stream: Optional[torch.cuda.Stream] = None) -> None:
+        self.step_count += 1
+        d = _lib.UpdateDesc()
+        d.B, d.L, d.step = self.B, self.L, self.step_count
+        d.beta1, d.beta2, d.eps, d.weight_decay = 0.9, 0.999, 1e-4, self.weight_decay
+        for i, v in enumerate(self.lr_theta):
+            d.lr_theta[i] = v
+        d.lr_velocity, d.sigma, d.theta_mask = self.lr_velocity, float(sigma), self.mask
+        d.theta, d.grad_theta = theta.data_ptr(), grad_theta.data_ptr()
+        d.theta_m, d.theta_v = self.theta_m.data_ptr(), self.theta_v.data_ptr()
+        if velocity is not None and self.opt_velocity:
+            d.velocity, d.grad_velocity = velocity.data_ptr(), grad_velocity.data_ptr()
+            d.vel_m, d.vel_v = self.vel_m.data_ptr(), self.vel_v.data_ptr()
+            d.x_t, d.x1 = _ptr(x_t), _ptr(x1)
+        s = stream if stream is not None else torch.cuda.current_stream(self.device)
+        _lib.check("foho_guidance_update", self.lib.foho_guidance_update(C.byref(d), C.c_void_p(s.cuda_stream)))
+
+
+def scheduler_step(x_t: torch.Tensor, velocity: torch.Tensor, sigma: float, sigma_next: float):
+    """``FlowMatchEulerDiscreteScheduler.step`` arithmetic on the device
+    (schedulers.py:294-309): returns (prev_sample, pred_x1)."""
+    lib = _lib.load()
+    prev = torch.empty_like(x_t)
+    x1 = torch.empty_like(x_t)
+    s = torch.cuda.current_stream(x_t.device)
+    _lib.check("foho_scheduler_step", lib.foho_scheduler_step(
+        x_t.data_ptr(), velocity.data_ptr(), prev.data_ptr(), x1.data_ptr(), x_t.numel(), float(sigma),
+        float(sigma_next), C.c_void_p(s.cuda_stream)))
+    return prev, x1
+
+
+class GuidanceFunction(torch.autograd.Function):
+    """Differentiable wrapper so a PyTorch decoder can sit upstream of the kernel:
+    ``E = GuidanceFunction.apply(sdf, theta, engine, statics)`` returns the per-sample
+    total energy [B]; backward scales the kernel's dE/dSDF and dE/dtheta."""
+
+    @staticmethod
+    def forward(ctx, sdf, theta, engine: GuidanceEngine, statics: GuidanceStatics):
+        terms, gs, gt = engine.energy_fwd_bwd(sdf.contiguous(), theta.contiguous(), statics)
+        ctx.save_for_backward(gs.clone(), gt.clone())
+        return terms[:, 0].clone()
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        gs, gt = ctx.saved_tensors
+        return gs * grad_out.view(-1, 1, 1, 1), gt * grad_out.view(-1, 1), None, None

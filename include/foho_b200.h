@@ -1,0 +1,188 @@
+/*
+ * foho_b200.h -- C-ABI of the B200-native FollowMyHold guidance / alignment hot path.
+ *
+ * The reference (aidilayce/FollowMyHold) has no FFI of its own: its hot path is Python
+ * calling pytorch3d / kaolin / scipy / trimesh library kernels.  Each entry point below
+ * therefore names the *Python seam* it replaces (file:line under the reference tree);
+ * INTEGRATION.md shows the ctypes stub a maintainer would drop into the reference.
+ *
+ * Contract:
+ *   - plain C: raw pointers + sizes, no torch / C++ types in any signature;
+ *   - every pointer marked "device" is CUDA device memory owned by the caller;
+ *   - functions enqueue work on the given stream and return without synchronising
+ *     (except the *_host variants, which are synchronous by definition);
+ *   - no allocation: the caller passes a workspace sized by the matching
+ *     *_workspace_bytes() query;
+ *   - return value: 0 ok, <0 invalid argument (FOHO_E_*), >0 a cudaError_t value;
+ *   - thread-safe for distinct (stream, workspace) pairs.
+ *   - there is NO CPU fallback: every compute entry point needs a CUDA device.
+ */
+#ifndef FOHO_B200_H
+#define FOHO_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define FOHO_ABI_VERSION 1
+
+#define FOHO_OK 0
+#define FOHO_E_NULL (-1)      /* required pointer is NULL            */
+#define FOHO_E_SHAPE (-2)     /* size out of the supported range     */
+#define FOHO_E_WORKSPACE (-3) /* workspace too small / misaligned    */
+#define FOHO_E_ARG (-4)       /* other invalid scalar argument       */
+
+/* indices into the per-sample `terms` output of foho_guidance_energy_fwd_bwd */
+enum {
+  FOHO_T_TOTAL = 0,
+  FOHO_T_PEN = 1,     /* NS a13  mean relu(-s_i)                                   */
+  FOHO_T_CON = 2,     /* NS a13  mean clamp(|s_i|-m,0)                             */
+  FOHO_T_INT = 3,     /* NS a14  mean_vox relu(-SDF_o) relu(-SDF_h)                */
+  FOHO_T_COUNT = 4,   /* REF a9  count(sdf_o<0 & sdf_h<0)/1000 (pipelines.py:231)  */
+  FOHO_T_MOM = 5,     /* NS a10v mean_vox relu(-SDF_o)|y|^2                        */
+  FOHO_T_CH = 6,      /* NS a15  symmetric chamfer hand <-> cloud                  */
+  FOHO_T_KP = 7,      /* REF a11 2-D key-point MSE (pipelines.py:1490-1495)        */
+  FOHO_T_TREG_H = 8,  /* REF a10 mean(t_h^2) (pipelines.py:1498)                   */
+  FOHO_T_TREG_O = 9,  /* REF a10 mean(t_o^2) (pipelines.py:1571)                   */
+  FOHO_T_DIST = 10,   /* REF a7  mean clamp(d2-0.01,0) (pipelines.py:1529-1541)    */
+  FOHO_T_VREG = 11,   /* REF a10 mean(obj verts^2) (pipelines.py:1570)             */
+  FOHO_T_EDGE = 12,   /* REF a10 mesh_edge_loss (pipelines.py:1575)                */
+  FOHO_T_MEAN_D2 = 13,/* REF     mean hand->object d2 (weight switch, :1561)       */
+  FOHO_T_NCAND = 14,  /* diagnostics: voxels inside hand & object                  */
+  FOHO_T_FLAGS = 15,  /* diagnostics: bit0 = candidate list overflow               */
+  FOHO_NUM_TERMS = 16
+};
+
+/* Loss weights; the REF defaults are the literals of
+ * third_party_patches/hy3dgen/shapegen/pipelines.py:1499-1504,1561-1564,1578-1588. */
+typedef struct foho_weights {
+  float w_dist, w_vreg, w_edge, w_treg_o, w_hand, w_kp, w_treg_h;
+  float w_int_lo, w_int_hi, dist_margin;
+  float w_pen, w_con, w_ivol, w_ch, w_mom, con_margin;
+} foho_weights;
+
+/* One batched guidance evaluation.  All arrays are contiguous, float32 unless noted.
+ * theta layout per sample: [s_h, t_h(3), q_h(4, wxyz), s_o, t_o(3), q_o(4)] = 16 floats
+ * (leaves of third_party/utilz/code_utils.py:57-78). */
+typedef struct foho_guidance_desc {
+  int32_t B;            /* samples in the batch (>=1)                                   */
+  int32_t D;            /* lattice points per axis (reference 65; 2..1024)              */
+  int32_t Vh;           /* hand vertices (MANO: 778), <= 4096                           */
+  int32_t Fh;           /* hand faces (MANO: 1538), <= 8192                             */
+  int32_t P;            /* cloud points per sample (0 disables the chamfer term)        */
+  int32_t n_joints;     /* rows of j_regressor (MANO: 16), 0 disables key-points        */
+  int32_t image_h, image_w;
+  int32_t late_step;    /* 1 when i >= num_inference_steps-3 (pipelines.py:1561)        */
+  int32_t stream_variant; /* 0 = default kernel choice, 1 = LDG/STG, 2 = TMA bulk       */
+  float fov_deg;        /* MoGe fov_x in degrees (guidance/run.py:228-230)              */
+  float bound;          /* lattice half extent, 1.10 (pipelines.py:1127)                */
+  foho_weights w;
+
+  const float *sdf;          /* device [B,D,D,D]  negative inside, z fastest            */
+  float *grad_sdf;           /* device [B,D,D,D]  OUT dE/dSDF (fully overwritten)       */
+  const float *hand_rest;    /* device [B,Vh,3]   aligned MANO verts, MoGe space        */
+  const int32_t *hand_faces; /* device [Fh,3]     shared topology                       */
+  const float *cloud;        /* device [B,P,3]    MoGe partial cloud (may be NULL if P=0)*/
+  const float *T_h2m;        /* device [B,16]     row-major 4x4 Hunyuan->MoGe similarity */
+  const float *obj_center;   /* device [B,3]      centre of the object similarity       */
+  const float *theta;        /* device [B,16]                                            */
+  const float *j_regressor;  /* device [n_joints,Vh] or NULL                             */
+  const float *kps_2d;       /* device [B,n_joints+5,2] or NULL                          */
+  const float *grad_hand_ext;/* device [B,Vh,3] or NULL: dE_ext/d(transformed hand verts)
+                                added before the chain rule (renderer losses live upstream) */
+  float *grad_theta;         /* device [B,16]  OUT                                       */
+  float *terms;              /* device [B,FOHO_NUM_TERMS] OUT                            */
+  float *hand_moge;          /* device [B,Vh,3] OUT transformed hand verts (may be NULL) */
+  float *hand_grid;          /* device [B,Vh,3] OUT same verts in lattice units (may be NULL) */
+
+  /* optional explicit object mesh (FlexiCubes output, Hunyuan space; pipelines.py:1509) */
+  int32_t Vo_total;          /* total packed object vertices over the batch (0 = none)   */
+  int32_t Eo_total;          /* total packed unique edges                                */
+  const float *obj_verts;    /* device [Vo_total,3]                                      */
+  const int32_t *obj_vert_offsets; /* device [B+1]                                       */
+  const int32_t *obj_edges;  /* device [Eo_total,2] indices into the packed vertex array */
+  const int32_t *obj_edge_offsets; /* device [B+1]                                       */
+  float *grad_obj_verts;     /* device [Vo_total,3] OUT                                  */
+
+  void *workspace;           /* device, >= foho_guidance_workspace_bytes(...)            */
+  size_t workspace_bytes;
+} foho_guidance_desc;
+
+int foho_abi_version(void);
+const char *foho_status_string(int status);
+void foho_default_weights(foho_weights *w);
+
+/* Replaces the body of the phase-2 inner iteration between `scheduler.step_final(...)`
+ * and `total_loss.backward()` of
+ * third_party_patches/hy3dgen/shapegen/pipelines.py:1480-1600 (volume formulation of
+ * BASELINE.json north_star; term-by-term map in DESIGN.md). */
+size_t foho_guidance_workspace_bytes(int32_t B, int32_t D, int32_t Vh, int32_t Fh, int32_t P,
+                                     int32_t Vo_total);
+int foho_guidance_energy_fwd_bwd(const foho_guidance_desc *desc, void *cuda_stream);
+
+/* Replaces `joint_optimizer.step()` (torch.optim.AdamW(eps=1e-4), pipelines.py:1478,1601;
+ * Adam of :1318 with weight_decay=0) fused with `scheduler.step_final`
+ * (schedulers.py:411-493): one launch updates the 16 scalar leaves of every sample and
+ * the velocity tensor, and emits x1 = x_t + (1-sigma) v_new for the next decode. */
+typedef struct foho_update_desc {
+  int32_t B;
+  int32_t L;                 /* velocity elements per sample (3072*64)                   */
+  int32_t step;              /* 1-based optimiser step (state is reset every outer step) */
+  float beta1, beta2, eps, weight_decay;
+  float lr_theta[6];         /* scale_h, trans_h, rot_h, scale_o, trans_o, rot_o
+                                (src/foho/configs/guid_config.py:20-25)                  */
+  float lr_velocity;         /* noise_obj_lr2 = 1e-2 (guid_config.py:26)                 */
+  float sigma;               /* sigma_k of the current outer step                        */
+  uint32_t theta_mask;       /* bit g set = leaf group g is optimised in this phase      */
+  float *theta;              /* device [B,16] in/out                                     */
+  const float *grad_theta;   /* device [B,16]                                            */
+  float *theta_m, *theta_v;  /* device [B,16] Adam moments in/out                        */
+  float *velocity;           /* device [B,L] in/out (may be NULL: scalars only)          */
+  const float *grad_velocity;/* device [B,L]                                             */
+  float *vel_m, *vel_v;      /* device [B,L]                                             */
+  const float *x_t;          /* device [B,L] current latents (may be NULL)               */
+  float *x1;                 /* device [B,L] OUT x_t + (1-sigma) v_new (may be NULL)     */
+} foho_update_desc;
+int foho_guidance_update(const foho_update_desc *desc, void *cuda_stream);
+
+/* Replaces `scheduler.step(noise_pred_obj, t, obj_latents).prev_sample`
+ * (schedulers.py:235-319, call site pipelines.py:1612): prev = x + (sigma_next-sigma) v. */
+int foho_scheduler_step(const float *x_t, const float *velocity, float *prev_sample, float *pred_x1,
+                        int64_t n, float sigma, float sigma_next, void *cuda_stream);
+
+/* Replaces `icp(...)` of src/foho/alignment/mesh_align.py:56-175 for the configuration
+ * both callers use (on_surface=False, no rotation/reflection search): trimmed
+ * similarity ICP, float64, Euclidean 1-NN (scipy cKDTree.query semantics), trim of
+ * int(outliers*count_source) worst pairs, trimesh.registration.procrustes
+ * (reflection=False), scale renormalise + clip, best-by-pre-update-cost.
+ * source [Ns,3], target [Nt,3] device float64.  OUT transform [16] row-major device
+ * float64, OUT cost [1] device float64, OUT (optional) cost_history [n_iter]. */
+size_t foho_icp_workspace_bytes(int32_t Ns, int32_t Nt);
+int foho_icp_run(const double *source, int32_t Ns, const double *target, int32_t Nt, int32_t n_iter,
+                 int32_t n_outliers, int32_t fixed_scale, double min_scale, double max_scale,
+                 double *transform_out, double *cost_out, double *cost_history, int32_t *nn_index_last,
+                 void *workspace, size_t workspace_bytes, void *cuda_stream);
+
+/* Exact mesh -> signed distance on a rectilinear lattice: replaces `mesh2sdf`
+ * (third_party/utilz/kaolin_sdf_ops.py:88-109: kaolin point_to_mesh_distance +
+ * check_sign) for the grid of get_sdf_of_meshes (:131-160), whose points are the
+ * product xs x ys x zs of three np.linspace arrays ("ij" order, z fastest).
+ * verts device [V,3] fp32, faces device [F,3] int32, xs/ys/zs device fp32 ascending,
+ * OUT sdf device [nx,ny,nz] fp32 = sqrt(d2) * (inside ? -1 : +1). */
+size_t foho_mesh2sdf_workspace_bytes(int32_t V, int32_t F, int32_t nx, int32_t ny, int32_t nz);
+int foho_mesh2sdf_lattice(const float *verts, int32_t V, const int32_t *faces, int32_t F, const float *xs,
+                          const float *ys, const float *zs, int32_t nx, int32_t ny, int32_t nz, float *sdf_out,
+                          void *workspace, size_t workspace_bytes, void *cuda_stream);
+
+/* REF a9 on two lattice SDFs: count(sdf_obj<0 & sdf_hand<0) (pipelines.py:231-239).
+ * OUT count device int64[1]. */
+int foho_intersection_count(const float *sdf_hand, const float *sdf_obj, int64_t n, long long *count_out,
+                            void *cuda_stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FOHO_B200_H */
