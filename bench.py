@@ -1,0 +1,322 @@
+#!/usr/bin/env python
+"""Benchmark of the guidance hot path (BASELINE.json metric: guided-denoise steps/sec;
+guidance kernel HBM GB/s).
+
+Workload at every N: BASELINE.json configs[2] -- per GPU a batch of 8 synthetic 256^3
+volumes + random MANO-topology hand poses + 65 536-point clouds, mock latents.  One bench
+"step" = one guided-denoise step of the whole batch = 50 guidance evaluations (decode ->
+fused energy fwd+bwd -> decoder adjoint -> fused AdamW/step_final) + one scheduler.step,
+replayed as ONE CUDA graph.  value = image-steps per second over all GPUs.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W]            (ours)
+  python bench.py --impl reference ...                            (CPU oracle arm)
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "guided_denoise_steps_per_sec"
+UNIT = "image-steps/s"
+B_PER_GPU, D, P, EVALS_PER_STEP = 8, 256, 65536, 50
+STEP_INDEX = 15          # a phase-2 outer step of the 20-step schedule (pipelines.py:1455)
+
+
+def algorithmic_bytes_per_eval(D: int, P: int, Vh: int = 778) -> int:
+    """read SDF once + write dense dE/dSDF once + verts/cloud in, grads out."""
+    return 4 * D ** 3 + 4 * D ** 3 + 2 * 12 * (Vh + P)
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md)."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        super().__init__(daemon=True)
+        self.gpu = gpu_index
+        self.samples = []
+        self._stop = threading.Event()
+
+    def run(self):
+        while not self._stop.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                      "-i", str(self.gpu)], capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.samples.append([x.strip() for x in out.split(",")])
+            except Exception:
+                pass
+            self._stop.wait(0.2)
+
+    def stop(self):
+        self._stop.set()
+        self.join(timeout=3)
+        sm, mx, reasons = [], 0, set()
+        for s in self.samples:
+            try:
+                sm.append(float(s[1])); mx = max(mx, float(s[2]))
+            except Exception:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), s[4:8]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx or None, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def measured_peak_gbs():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured"
+        except Exception:
+            pass
+    return 6650.0, "fallback"
+
+
+# --------------------------------------------------------------------------- CPU arm
+def cpu_guidance_evals_per_sec(seconds_budget: float = 20.0, threads: int = 0, n_min: int = 2):
+    """Time the CPU oracle (the restated reference arithmetic; the reference itself cannot be
+    imported offline) on ONE sample of the bench workload (D=256, P=65 536):
+    forward + backward + AdamW on the 16 leaves, all host threads."""
+    import torch
+    from followmyhold_b200.synthetic import make_guidance_sample
+    from oracle import guidance_oracle as O
+    cores = threads or (os.cpu_count() or 1)
+    torch.set_num_threads(cores)
+    s = make_guidance_sample(D, P, seed=0)
+    th = torch.cat([s.theta_h, s.theta_o]).clone()
+    m = torch.zeros(16); v = torch.zeros(16)
+    n, t0 = 0, time.perf_counter()
+    while True:
+        sdf = s.sdf.clone().requires_grad_(True)
+        a = th[:8].clone().requires_grad_(True); b = th[8:].clone().requires_grad_(True)
+        out = O.guidance_energy(sdf, s.hand_rest, s.hand_faces, s.cloud, a, b, s.T_h2m, s.obj_center,
+                                j_regressor=s.j_regressor, kps_2d=s.kps_2d, fov_deg=s.fov_deg, image_hw=s.image_hw)
+        out["total"].backward()
+        g = torch.cat([a.grad, b.grad])
+        th, m, v = O.adamw_step(th, g, m, v, n + 1, 1e-2)
+        n += 1
+        el = time.perf_counter() - t0
+        if n >= n_min and el >= seconds_budget:
+            break
+        if el > 4 * seconds_budget:
+            break
+    el = time.perf_counter() - t0
+    return n / el, cores, n, el
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    n_gpus = args.gpus
+    K, W = args.steps, args.warmup
+    # each reference "step" is a bounded sample: a few oracle evaluations of one image
+    per_step_budget = max(2.0, min(20.0, 120.0 / max(1, K + W)))
+    vals = []
+    cores = os.cpu_count() or 1
+    n_total = 0
+    t_total = 0.0
+    for i in range(W + K):
+        eps, cores, n, el = cpu_guidance_evals_per_sec(per_step_budget, n_min=1)
+        if i >= W:
+            vals.append(eps); n_total += n; t_total += el
+    evals_per_s = n_total / t_total
+    value = evals_per_s / EVALS_PER_STEP
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": n_gpus, "steps": K, "warmup": W,
+        "ms_per_step": 1e3 / value if value > 0 else None, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "configs[2]: batch-8 synthetic 256^3 volumes + random MANO poses, P=65536, mock latents",
+                   "D": D, "P": P, "evals_per_step": EVALS_PER_STEP},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
+                         "sample": f"{n_total} oracle guidance evaluations (fwd+bwd+AdamW) of ONE image of the workload "
+                                   f"in {t_total:.1f}s; value = evals/s / {EVALS_PER_STEP}",
+                         "evals_per_sec": evals_per_s},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# --------------------------------------------------------------------------- GPU arm
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    from followmyhold_b200 import _lib
+    from followmyhold_b200.guidance.loop import GuidanceLoop
+    from followmyhold_b200.synthetic import cap_boundary_loops, make_guidance_sample, stack_samples
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local}"))
+    if not torch.cuda.is_available():
+        raise _lib.FohoLibraryError("bench.py needs a CUDA device; there is no CPU fallback for the product path")
+    torch.cuda.set_device(local)
+    dev = torch.device(f"cuda:{local}")
+    _lib.load()
+    K, W = args.steps, max(3, args.warmup)
+    B = B_PER_GPU
+
+    # ---- synthetic inputs: images rank*B .. rank*B+B-1 (independent units, no exchange: SURVEY.md §8e)
+    samples = [make_guidance_sample(D, P, seed=rank * B + i) for i in range(B)]
+    sdf0, theta0, st = stack_samples(samples, device=dev, cap=True)
+    loop = GuidanceLoop(B, D, st, P, device=dev, stream_variant=args.variant)
+    g = torch.Generator().manual_seed(1234 + rank)
+    x_t_h = torch.randn(B, loop.L, generator=g).pin_memory()
+    vel_h = (0.1 * torch.randn(B, loop.L, generator=g)).pin_memory()
+    theta_h = theta0.cpu().pin_memory()
+    sdf0_h = torch.empty(sdf0.shape, dtype=sdf0.dtype, pin_memory=True)
+    sdf0_h.copy_(sdf0)
+
+    def load_device_state():
+        loop.sdf0.copy_(sdf0); loop.sdf.copy_(sdf0)
+        loop.x_t.copy_(x_t_h); loop.velocity.copy_(vel_h); loop.theta.copy_(theta0)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    load_device_state()
+    loop.capture(STEP_INDEX)
+    for _ in range(W):
+        loop.run_step_device(STEP_INDEX)
+    torch.cuda.synchronize()
+
+    # ---- timed region: K graph replays, inputs resident in HBM.  The 1.07 GB of volumes
+    #      touched per evaluation exceeds the 126 MB L2, so no L2 flush is needed between steps.
+    sampler = ClockSampler(local) if rank == 0 else None
+    if sampler:
+        sampler.start()
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(K):
+        loop.run_step_device(STEP_INDEX)
+    e1.record()
+    barrier()
+    ms = e0.elapsed_time(e1)
+    clocks = sampler.stop() if sampler else None
+    terms = loop.engine.terms.cpu()
+    assert torch.isfinite(terms).all(), "non-finite guidance terms in the timed region"
+
+    # ---- end to end through the host-buffer API (H2D of the step's inputs + D2H of its results inside)
+    for _ in range(2):
+        loop.denoise_step_host(STEP_INDEX, sdf0_h, x_t_h, vel_h, theta_h)
+    barrier()
+    t0 = time.perf_counter()
+    K2 = max(2, min(K, 10))
+    for _ in range(K2):
+        out = loop.denoise_step_host(STEP_INDEX, sdf0_h, x_t_h, vel_h, theta_h)
+    barrier()
+    e2e_s = time.perf_counter() - t0
+
+    # ---- dominant kernel alone: the dense stream (stage_mask = prep|stream), CUDA events on its stream
+    eng = loop.engine
+    desc = eng.make_desc(loop.sdf, loop.theta, st)
+    desc.stage_mask = 1
+    eng.launch(desc)
+    desc.stage_mask = 2
+    NREP = 50
+    for _ in range(5):
+        eng.launch(desc)
+    torch.cuda.synchronize()
+    s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    s0.record()
+    for _ in range(NREP):
+        eng.launch(desc)
+    s1.record()
+    torch.cuda.synchronize()
+    stream_ms = s0.elapsed_time(s1) / NREP
+    # whole evaluation (all 7 kernels), same method
+    desc.stage_mask = 0
+    for _ in range(3):
+        eng.launch(desc)
+    torch.cuda.synchronize()
+    s0.record()
+    for _ in range(NREP):
+        eng.launch(desc)
+    s1.record()
+    torch.cuda.synchronize()
+    eval_ms = s0.elapsed_time(s1) / NREP
+
+    # ---- max over ranks
+    t = torch.tensor([ms, e2e_s, stream_ms, eval_ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms, e2e_s, stream_ms, eval_ms = [float(x) for x in t.tolist()]
+
+    if rank == 0:
+        value = world * B * K / (ms / 1e3)
+        e2e_value = world * B * K2 / e2e_s
+        peak, peak_kind = measured_peak_gbs()
+        stream_bytes = B * 8 * D ** 3                      # dense stream: 4 B read + 4 B written per voxel
+        achieved = stream_bytes / (stream_ms * 1e-3) / 1e9
+        eval_bytes = B * algorithmic_bytes_per_eval(D, P)
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
+            "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "configs[2]: batch-8 synthetic 256^3 volumes + random MANO poses, P=65536, mock latents",
+                       "images_per_gpu": B, "D": D, "P": P, "evals_per_step": EVALS_PER_STEP, "step_index": STEP_INDEX,
+                       "l2": "inputs larger than L2 (1.07 GB of volumes touched per evaluation vs 126 MB L2)",
+                       "stream_variant": {0: "tma", 1: "ldg", 2: "tma"}.get(args.variant, "tma"),
+                       "evals_per_sec": value * EVALS_PER_STEP, "eval_ms_standalone": eval_ms,
+                       "eval_GBps_algorithmic": eval_bytes / (eval_ms * 1e-3) / 1e9},
+            "clocks": clocks,
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": loop.h2d_bytes_per_step(),
+                    "d2h_bytes_per_step": loop.d2h_bytes_per_step(), "steps": K2},
+            "gpu_launches": K * loop.launches_per_step(),
+            "roofline": {"bound": "hbm", "kernel": "k_stream_tma" if args.variant in (0, 2) else "k_stream_ldg",
+                         "achieved": achieved, "peak": peak, "peak_kind": f"{peak_kind} burst copy (kernel timed alone)",
+                         "unit": "GB/s", "frac": achieved / peak, "bytes_per_launch": stream_bytes,
+                         "ms_per_launch": stream_ms, "traffic": None,
+                         "share_of_eval": stream_ms / eval_ms},
+        }
+        if world == 1 and not args.no_cpu:
+            eps, cores, n, el = cpu_guidance_evals_per_sec(args.cpu_seconds)
+            line["cpu_baseline"] = {"value": eps / EVALS_PER_STEP, "unit": UNIT, "cores": cores, "kind": "port",
+                                    "sample": f"{n} oracle guidance evaluations (fwd+bwd+AdamW) of ONE image of the "
+                                              f"workload in {el:.1f}s; value = evals/s / {EVALS_PER_STEP}",
+                                    "evals_per_sec": eps}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--variant", type=int, default=0, help="dense stream kernel: 0/2 = TMA bulk, 1 = LDG")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--cpu-seconds", type=float, default=15.0)
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

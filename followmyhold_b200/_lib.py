@@ -28,7 +28,8 @@ TERM_NAMES = ["total", "pen", "con", "int", "count", "mom", "ch", "kp", "treg_h"
 EXPORTED_SYMBOLS = [
     "foho_abi_version", "foho_status_string", "foho_default_weights",
     "foho_guidance_workspace_bytes", "foho_guidance_energy_fwd_bwd", "foho_guidance_update",
-    "foho_scheduler_step", "foho_icp_workspace_bytes", "foho_icp_run",
+    "foho_scheduler_step", "foho_mock_decoder_forward", "foho_mock_decoder_backward",
+    "foho_icp_workspace_bytes", "foho_icp_run",
     "foho_mesh2sdf_workspace_bytes", "foho_mesh2sdf_lattice", "foho_intersection_count",
 ]
 
@@ -99,7 +100,7 @@ class GuidanceDesc(C.Structure):
     _fields_ = [
         ("B", C.c_int32), ("D", C.c_int32), ("Vh", C.c_int32), ("Fh", C.c_int32), ("P", C.c_int32),
         ("n_joints", C.c_int32), ("image_h", C.c_int32), ("image_w", C.c_int32), ("late_step", C.c_int32),
-        ("stream_variant", C.c_int32), ("fov_deg", C.c_float), ("bound", C.c_float), ("w", Weights),
+        ("stream_variant", C.c_int32), ("stage_mask", C.c_int32), ("reserved0", C.c_int32), ("fov_deg", C.c_float), ("bound", C.c_float), ("w", Weights),
         ("sdf", C.c_void_p), ("grad_sdf", C.c_void_p), ("hand_rest", C.c_void_p), ("hand_faces", C.c_void_p),
         ("cloud", C.c_void_p), ("T_h2m", C.c_void_p), ("obj_center", C.c_void_p), ("theta", C.c_void_p),
         ("j_regressor", C.c_void_p), ("kps_2d", C.c_void_p), ("grad_hand_ext", C.c_void_p),
@@ -157,6 +158,12 @@ def load(build_if_missing: bool = False) -> C.CDLL:
     lib.foho_scheduler_step.restype = C.c_int
     lib.foho_scheduler_step.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_float,
                                         C.c_float, C.c_void_p]
+    lib.foho_mock_decoder_forward.restype = C.c_int
+    lib.foho_mock_decoder_forward.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int64,
+                                              C.c_int32, C.c_float, C.c_void_p]
+    lib.foho_mock_decoder_backward.restype = C.c_int
+    lib.foho_mock_decoder_backward.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int64, C.c_int32,
+                                               C.c_float, C.c_void_p]
     lib.foho_icp_workspace_bytes.restype = C.c_size_t
     lib.foho_icp_workspace_bytes.argtypes = [C.c_int32, C.c_int32]
     lib.foho_icp_run.restype = C.c_int

@@ -1,0 +1,247 @@
+"""Trimmed similarity ICP with the iteration loop on the GPU.
+
+Mirror of the reference's ``src/foho/alignment/mesh_align.py`` (same function names,
+arguments, defaults and return values: ``icp`` :56-175, ``align_meshes_impl`` :178-217,
+``compute_init_transform`` :25-35, ``get_centroid_scale`` :18-23).  What changed:
+
+* the per-iteration work (transform, 1-NN query, trim, Procrustes, scale clip, best
+  tracking; :104-142) runs in ``foho_icp_run`` (csrc/icp.cu) -- float64, no host round
+  trips inside the loop -- instead of scipy cKDTree + numpy + trimesh on one CPU thread;
+* surface sampling (``trimesh.sample.sample_surface_even``, unseeded in the reference,
+  :79,85) is re-implemented here and takes a ``seed`` so runs are reproducible;
+* ``on_surface=True`` and ``plot=True`` are not offered (both callers pass False:
+  h2m.py:44, mano.py:33).
+
+There is no CPU fallback: the ICP loop needs the CUDA library.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import time
+from typing import Optional, Tuple
+
+import numpy as np
+import torch
+from scipy.spatial import cKDTree   # only for remove_close() in the surface sampler (host pre-processing)
+
+from .. import _lib
+from ..meshio import Geometry, PointCloud, TriMesh, export, load, transform_points
+
+
+def get_centroid_scale(mesh_or_pointcloud: Geometry):
+    """mesh_align.py:18-23."""
+    if isinstance(mesh_or_pointcloud, PointCloud):
+        v = mesh_or_pointcloud.vertices
+        return v.mean(axis=0), np.linalg.norm(v.max(axis=0) - v.min(axis=0))
+    return mesh_or_pointcloud.centroid, mesh_or_pointcloud.scale
+
+
+def translation_matrix(t) -> np.ndarray:
+    T = np.eye(4)
+    T[:3, 3] = t
+    return T
+
+
+def scale_matrix(factor: float, origin) -> np.ndarray:
+    """``trimesh.transformations.scale_matrix(factor, origin)`` (uniform)."""
+    M = np.eye(4) * factor
+    M[3, 3] = 1.0
+    M[:3, 3] = (1.0 - factor) * np.asarray(origin, dtype=np.float64)
+    return M
+
+
+def rotation_matrix(angle: float, axis) -> np.ndarray:
+    axis = np.asarray(axis, dtype=np.float64)
+    axis = axis / np.linalg.norm(axis)
+    c, s = np.cos(angle), np.sin(angle)
+    K = np.array([[0, -axis[2], axis[1]], [axis[2], 0, -axis[0]], [-axis[1], axis[0], 0]])
+    R = c * np.eye(3) + s * K + (1 - c) * np.outer(axis, axis)
+    M = np.eye(4)
+    M[:3, :3] = R
+    return M
+
+
+def compute_init_transform(source_mesh: Geometry, target_mesh: Geometry, fixed_scale: bool) -> np.ndarray:
+    """mesh_align.py:25-35: centroid to centroid, scale by the ratio of bbox diagonals."""
+    source_centroid, source_scale = get_centroid_scale(source_mesh)
+    target_centroid, target_scale = get_centroid_scale(target_mesh)
+    T = translation_matrix(target_centroid - source_centroid)
+    if fixed_scale:
+        return T
+    S = scale_matrix(target_scale / source_scale, origin=source_centroid)
+    return T @ S
+
+
+def get_all_axis_aligned_rotations():
+    """mesh_align.py:37-44."""
+    rotations = []
+    for coord in range(3):
+        axis = np.zeros(3)
+        axis[coord] = 1
+        for angle in [-np.pi / 2, np.pi, np.pi / 2]:
+            rotations.append(rotation_matrix(angle, axis))
+    return rotations
+
+
+def get_all_axis_aligned_reflections():
+    """mesh_align.py:46-54."""
+    return [np.eye(4) * np.append(diag, 1)
+            for diag in [[1, 1, -1], [1, -1, 1], [-1, 1, 1], [-1, -1, 1], [-1, 1, -1], [1, -1, -1], [-1, -1, -1]]]
+
+
+# --------------------------------------------------------------------------- sampling
+def sample_surface(mesh: TriMesh, count: int, rng: np.random.Generator):
+    """Area-weighted uniform surface samples (``trimesh.sample.sample_surface``)."""
+    area = mesh.area_faces
+    cum = np.cumsum(area)
+    pick = rng.random(count) * cum[-1]
+    face_index = np.minimum(np.searchsorted(cum, pick), len(area) - 1)
+    tri = mesh.triangles[face_index]
+    origin = tri[:, 0]
+    vec = tri[:, 1:] - origin[:, None, :]
+    r = rng.random((count, 2, 1))
+    flip = r.sum(axis=1).reshape(-1) > 1.0
+    r[flip] -= 1.0
+    r = np.abs(r)
+    return origin + (vec * r).sum(axis=1), face_index
+
+
+def remove_close(points: np.ndarray, radius: float):
+    """``trimesh.points.remove_close``: for every pair closer than ``radius`` drop the member
+    that appears in more pairs."""
+    tree = cKDTree(points)
+    pairs = tree.query_pairs(radius, output_type="ndarray")
+    mask = np.ones(len(points), dtype=bool)
+    if len(pairs):
+        count = np.bincount(pairs.ravel(), minlength=len(points))
+        column = count[pairs].argmax(axis=1)
+        highest = pairs.ravel()[column + 2 * np.arange(len(column))]
+        mask[highest] = False
+    return points[mask], mask
+
+
+def sample_surface_even(mesh: TriMesh, count: int, rng: np.random.Generator):
+    """``trimesh.sample.sample_surface_even``: 3x oversample, thin by min distance
+    sqrt(area/(3 count)); may return fewer than ``count`` points (mesh_align.py:79,85)."""
+    radius = np.sqrt(mesh.area / (3 * count))
+    points, index = sample_surface(mesh, count * 3, rng)
+    points, mask = remove_close(points, radius)
+    if len(points) >= count:
+        return points[:count], index[mask][:count]
+    return points, index[mask]
+
+
+# --------------------------------------------------------------------------- GPU loop
+def icp_points(source_points: np.ndarray, target_points: np.ndarray, n_iter: int, n_outliers: int,
+               fixed_scale: bool = False, min_scale: float = 0.5, max_scale: float = 2.0, device="cuda:0",
+               return_history: bool = False):
+    """Run the ICP iteration loop (mesh_align.py:104-142) on the device.
+
+    Returns (best_transform [4,4] float64, best_cost float[, cost_history [n_iter]])."""
+    lib = _lib.load()
+    dev = torch.device(device)
+    if dev.type != "cuda":
+        raise _lib.FohoLibraryError("icp needs a CUDA device; there is no CPU fallback")
+    src = torch.as_tensor(np.ascontiguousarray(source_points, dtype=np.float64)).to(dev)
+    tgt = torch.as_tensor(np.ascontiguousarray(target_points, dtype=np.float64)).to(dev)
+    Ns, Nt = src.shape[0], tgt.shape[0]
+    nbytes = lib.foho_icp_workspace_bytes(Ns, Nt)
+    ws = torch.empty(nbytes + 256, dtype=torch.uint8, device=dev)
+    ws_ptr = ws.data_ptr() + ((-ws.data_ptr()) % 256)
+    T = torch.zeros(16, dtype=torch.float64, device=dev)
+    cost = torch.zeros(1, dtype=torch.float64, device=dev)
+    hist = torch.zeros(max(n_iter, 1), dtype=torch.float64, device=dev)
+    with torch.cuda.device(dev):
+        s = torch.cuda.current_stream(dev)
+        _lib.check("foho_icp_run", lib.foho_icp_run(
+            src.data_ptr(), Ns, tgt.data_ptr(), Nt, int(n_iter), int(n_outliers), int(bool(fixed_scale)),
+            float(min_scale), float(max_scale), T.data_ptr(), cost.data_ptr(), hist.data_ptr(), None,
+            C.c_void_p(ws_ptr), nbytes, C.c_void_p(s.cuda_stream)))
+        s.synchronize()
+    out = (T.cpu().numpy().reshape(4, 4), float(cost.item()))
+    if return_history:
+        out = out + (hist.cpu().numpy()[:n_iter],)
+    return out
+
+
+def icp(source_mesh: Geometry, target_mesh: Geometry, n_iter: int, count_source: int = 5_000,
+        count_target: int = 5_000, test_reflections: bool = False, test_rotations: bool = False,
+        fixed_scale: bool = False, outliers: float = 0, on_surface: bool = False, min_scale: float = 0.5,
+        max_scale: float = 2.0, plot: bool = False, seed: Optional[int] = None,
+        device="cuda:0") -> Tuple[np.ndarray, float]:
+    """Same contract as the reference ``icp`` (mesh_align.py:56-175)."""
+    if on_surface:
+        raise NotImplementedError("on_surface=True (trimesh.proximity.closest_point) is not offered; "
+                                  "both reference callers disable it (h2m.py:44, mano.py:33)")
+    if plot:
+        raise NotImplementedError("plot=True needs pyvista and is not part of the hot path")
+    rng = np.random.default_rng(seed)
+    cubes = [np.eye(4)]
+    if test_reflections:
+        cubes += get_all_axis_aligned_reflections()
+    if test_rotations:
+        cubes += get_all_axis_aligned_rotations()
+
+    if isinstance(source_mesh, PointCloud):
+        source_points = source_mesh.vertices
+        count_source = len(source_points)
+    else:
+        source_points = sample_surface_even(source_mesh, count_source, rng)[0]
+    if isinstance(target_mesh, PointCloud):
+        target_points = target_mesh.vertices
+        count_target = len(target_points)
+    else:
+        target_points = sample_surface_even(target_mesh, count_target, rng)[0]
+
+    # reference quirk kept: n_outliers from the *requested* count (mesh_align.py:87)
+    n_outliers = int(outliers * count_source)
+    if n_outliers >= len(source_points):
+        raise ValueError("outlier count exceeds the number of sampled source points")
+
+    best_of_all_cost = np.inf
+    best_of_all_transform = np.eye(4)
+    for cube in cubes:
+        T, cost = icp_points(transform_points(source_points, cube), target_points, n_iter, n_outliers,
+                             fixed_scale, min_scale, max_scale, device=device)
+        if cost < best_of_all_cost:
+            best_of_all_cost = cost
+            best_of_all_transform = T @ cube
+    return best_of_all_transform, best_of_all_cost
+
+
+def align_meshes_impl(source_mesh_path, target_mesh_path, transform_path, transformed_mesh_path, fixed_scale,
+                      outliers, test_rotations, test_reflections, on_surface,
+                      iterations_coarse, count_source_coarse, count_target_coarse,
+                      iterations_fine, count_source_fine, count_target_fine,
+                      min_scale, max_scale, plot, seed: Optional[int] = 0, device="cuda:0"):
+    """Same contract as the reference ``align_meshes_impl`` (mesh_align.py:178-217)."""
+    start_time = time.time()
+    source_mesh = load(source_mesh_path)
+    target_mesh = load(target_mesh_path)
+
+    init_transform = compute_init_transform(source_mesh, target_mesh, fixed_scale)
+    source_mesh.apply_transform(init_transform)
+
+    transform_coarse, _ = icp(source_mesh, target_mesh, n_iter=iterations_coarse, count_source=count_source_coarse,
+                              count_target=count_target_coarse, test_reflections=test_reflections,
+                              test_rotations=test_rotations, fixed_scale=fixed_scale, outliers=outliers,
+                              on_surface=on_surface, min_scale=min_scale, max_scale=max_scale, plot=plot,
+                              seed=seed, device=device)
+    source_mesh.apply_transform(transform_coarse)
+
+    transform_fine, _ = icp(source_mesh, target_mesh, n_iter=iterations_fine, count_source=count_source_fine,
+                            count_target=count_target_fine, outliers=outliers, on_surface=on_surface,
+                            min_scale=min_scale, max_scale=max_scale, plot=plot,
+                            seed=None if seed is None else seed + 1, device=device)
+    source_mesh.apply_transform(transform_fine)
+
+    final_transform = transform_fine @ transform_coarse @ init_transform
+
+    if transform_path is not None:
+        np.save(transform_path, final_transform)
+    if transformed_mesh_path is not None:
+        export(source_mesh, transformed_mesh_path)
+
+    elapsed_time = time.time() - start_time
+    print(f"Elapsed time: {elapsed_time:.2f} seconds")
+    return final_transform

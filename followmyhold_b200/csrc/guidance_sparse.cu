@@ -266,9 +266,10 @@ __global__ void __launch_bounds__(256) k_voxdist(foho_guidance_desc d, FohoWorks
       if (lb > 0.f && lb * lb > best2) continue;
       int ia = sf[3 * f], ib = sf[3 * f + 1], ic = sf[3 * f + 2];
       float wa, wb, wc;
-      float d2 = closest_point_triangle(p, f3(sv[3 * ia], sv[3 * ia + 1], sv[3 * ia + 2]),
-                                        f3(sv[3 * ib], sv[3 * ib + 1], sv[3 * ib + 2]),
-                                        f3(sv[3 * ic], sv[3 * ic + 1], sv[3 * ic + 2]), wa, wb, wc);
+      // translate by -p first: differences of nearby lattice coordinates are (nearly) exact in fp32
+      float d2 = closest_point_triangle(f3(0.f, 0.f, 0.f), f3(sv[3 * ia], sv[3 * ia + 1], sv[3 * ia + 2]) - p,
+                                        f3(sv[3 * ib], sv[3 * ib + 1], sv[3 * ib + 2]) - p,
+                                        f3(sv[3 * ic], sv[3 * ic + 1], sv[3 * ic + 2]) - p, wa, wb, wc);
       if (d2 < best2 || bf < 0) {
         if (d2 <= best2) { best2 = d2; bf = f; bwa = wa; bwb = wb; bwc = wc; }
       }
@@ -288,13 +289,13 @@ __global__ void __launch_bounds__(256) k_voxdist(foho_guidance_desc d, FohoWorks
       atomicAdd(G + v, -d.w.w_ivol * kappa * dist / N);
       if (dist > 0.f) {
         int ia = sf[3 * bf], ib = sf[3 * bf + 1], ic = sf[3 * bf + 2];
-        foho_f3 a = f3(sv[3 * ia], sv[3 * ia + 1], sv[3 * ia + 2]);
-        foho_f3 bb = f3(sv[3 * ib], sv[3 * ib + 1], sv[3 * ib + 2]);
-        foho_f3 cc = f3(sv[3 * ic], sv[3 * ic + 1], sv[3 * ic + 2]);
+        foho_f3 a = f3(sv[3 * ia], sv[3 * ia + 1], sv[3 * ia + 2]) - p;
+        foho_f3 bb = f3(sv[3 * ib], sv[3 * ib + 1], sv[3 * ib + 2]) - p;
+        foho_f3 cc = f3(sv[3 * ic], sv[3 * ic + 1], sv[3 * ic + 2]) - p;
         foho_f3 q = f3(bwa * a.x + bwb * bb.x + bwc * cc.x, bwa * a.y + bwb * bb.y + bwc * cc.y,
-                       bwa * a.z + bwb * bb.z + bwc * cc.z);
+                       bwa * a.z + bwb * bb.z + bwc * cc.z);       // closest point relative to p
         float inv = 1.f / dist;
-        foho_f3 dir = inv * (p - q);
+        foho_f3 dir = (-inv) * q;
         float k = -coef * kappa;                            // d(dist)/dv_k = -w_k dir
         atomicAdd(Ghg + 3 * ia, k * bwa * dir.x); atomicAdd(Ghg + 3 * ia + 1, k * bwa * dir.y); atomicAdd(Ghg + 3 * ia + 2, k * bwa * dir.z);
         atomicAdd(Ghg + 3 * ib, k * bwb * dir.x); atomicAdd(Ghg + 3 * ib + 1, k * bwb * dir.y); atomicAdd(Ghg + 3 * ib + 2, k * bwb * dir.z);
@@ -438,9 +439,10 @@ __global__ void __launch_bounds__(FIN_THREADS) k_finalize(foho_guidance_desc d, 
       for (int i = lane; i < Vh; i += 32) sw += J[i];
       sw = warp_sum(sw);
       if (lane == 0) { kp3[wid][0] = sx + sw * fr.co[0]; kp3[wid][1] = sy + sw * fr.co[1]; kp3[wid][2] = sz + sw * fr.co[2]; }
-    } else if (wid == 16 && lane < 5) {
-      int i = c_tips[lane];
-      kp3[16 + lane][0] = hmc[3 * i] + fr.co[0]; kp3[16 + lane][1] = hmc[3 * i + 1] + fr.co[1]; kp3[16 + lane][2] = hmc[3 * i + 2] + fr.co[2];
+    }
+    if (tid < 5) {
+      int i = c_tips[tid];
+      kp3[16 + tid][0] = hmc[3 * i] + fr.co[0]; kp3[16 + tid][1] = hmc[3 * i + 1] + fr.co[1]; kp3[16 + tid][2] = hmc[3 * i + 2] + fr.co[2];
     }
     __syncthreads();
     if (tid < 21) {
@@ -716,12 +718,19 @@ extern "C" int foho_guidance_energy_fwd_bwd(const foho_guidance_desc *dp, void *
   if (ws.total > d.workspace_bytes) return FOHO_E_WORKSPACE;
   cudaStream_t st = (cudaStream_t)cuda_stream;
 
-  k_prep<<<d.B, 256, 0, st>>>(d, ws);
-  FOHO_LAUNCH_CHECK();
-  int gx = 0;
-  int rc = foho_launch_stream(dp, ws, &gx, st);
-  if (rc != FOHO_OK) return rc;
-  if (d.P > 0) {
+  const int sm = d.stage_mask == 0 ? 0x1f : d.stage_mask;
+  static int last_gx = 1;
+  if (sm & 1) {
+    k_prep<<<d.B, 256, 0, st>>>(d, ws);
+    FOHO_LAUNCH_CHECK();
+  }
+  int gx = last_gx;
+  if (sm & 2) {
+    int rc = foho_launch_stream(dp, ws, &gx, st);
+    if (rc != FOHO_OK) return rc;
+    last_gx = gx;
+  }
+  if ((sm & 4) && d.P > 0) {
     const size_t smem = (size_t)d.Vh * (16 + 8 + 12);
     if (smem > 200 * 1024) return FOHO_E_SHAPE;
     static size_t attr = 0;
@@ -733,11 +742,11 @@ extern "C" int foho_guidance_energy_fwd_bwd(const foho_guidance_desc *dp, void *
     k_chamfer<<<dim3(nchunk, d.B), CH_THREADS, smem, st>>>(d, ws);
     FOHO_LAUNCH_CHECK();
   }
-  k_raster<<<dim3((d.Fh + 127) / 128, d.B), 128, 0, st>>>(d, ws);
-  FOHO_LAUNCH_CHECK();
-  k_compact<<<dim3(16, d.B), 256, 0, st>>>(d, ws);
-  FOHO_LAUNCH_CHECK();
-  {
+  if (sm & 8) {
+    k_raster<<<dim3((d.Fh + 127) / 128, d.B), 128, 0, st>>>(d, ws);
+    FOHO_LAUNCH_CHECK();
+    k_compact<<<dim3(16, d.B), 256, 0, st>>>(d, ws);
+    FOHO_LAUNCH_CHECK();
     const size_t smem = (size_t)d.Fh * 16 + (size_t)d.Vh * 12 + (size_t)d.Fh * 12;
     if (smem > 200 * 1024) return FOHO_E_SHAPE;
     static size_t attr = 0;
@@ -748,7 +757,9 @@ extern "C" int foho_guidance_energy_fwd_bwd(const foho_guidance_desc *dp, void *
     k_voxdist<<<dim3(64, d.B), 256, smem, st>>>(d, ws);
     FOHO_LAUNCH_CHECK();
   }
-  k_finalize<<<d.B, FIN_THREADS, 0, st>>>(d, ws, gx);
-  FOHO_LAUNCH_CHECK();
+  if (sm & 16) {
+    k_finalize<<<d.B, FIN_THREADS, 0, st>>>(d, ws, gx);
+    FOHO_LAUNCH_CHECK();
+  }
   return FOHO_OK;
 }

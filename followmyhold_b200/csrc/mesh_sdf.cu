@@ -109,9 +109,9 @@ __global__ void __launch_bounds__(M2S_THREADS) k_m2s_dist(const float *__restric
       const int f = t0 + k;
       const int ia = faces[3 * f], ib = faces[3 * f + 1], ic = faces[3 * f + 2];
       float wa, wb, wc;
-      const float d2 = closest_point_triangle(p, f3(verts[3 * ia], verts[3 * ia + 1], verts[3 * ia + 2]),
-                                              f3(verts[3 * ib], verts[3 * ib + 1], verts[3 * ib + 2]),
-                                              f3(verts[3 * ic], verts[3 * ic + 1], verts[3 * ic + 2]), wa, wb, wc);
+      const float d2 = closest_point_triangle(f3(0.f, 0.f, 0.f), f3(verts[3 * ia], verts[3 * ia + 1], verts[3 * ia + 2]) - p,
+                                              f3(verts[3 * ib], verts[3 * ib + 1], verts[3 * ib + 2]) - p,
+                                              f3(verts[3 * ic], verts[3 * ic + 1], verts[3 * ic + 2]) - p, wa, wb, wc);
       best2 = fminf(best2, d2);
     }
   }

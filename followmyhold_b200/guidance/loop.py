@@ -1,0 +1,189 @@
+"""Guided-denoise loop over a batch of images: the phase-2 hot loop of the reference
+(third_party_patches/hy3dgen/shapegen/pipelines.py:1455-1612) driven through the C-ABI.
+
+One *guided-denoise step* = ``optimization_steps_joint`` (50) guidance evaluations
+[decode -> energy fwd+bwd -> decoder adjoint -> fused AdamW + step_final] followed by one
+``scheduler.step``.  The whole step is captured once into a CUDA graph and
+replayed, so the inner loop has no host round trips at all (the reference syncs several
+times per iteration).
+
+The VAE decoder (``latent2sdf``) is not built yet; a fixed sparse
+linear decoder stands in for it (``foho_mock_decoder_*``) so latents, velocity and the
+optimiser are exercised with real data flow.  A real decoder plugs in through
+``GuidanceFunction`` (engine.py) instead.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Dict, Optional
+
+import torch
+
+from .. import _lib
+from .config import OptimizationConfig
+from .engine import GuidanceEngine, GuidanceOptimizer, GuidanceStatics
+
+LATENT_SHAPE = (3072, 64)   # Hunyuan3D-2 ShapeVAE latent (pipelines.py:700)
+
+
+def set_timesteps_sigmas(num_inference_steps: int, shift: float = 1.0) -> torch.Tensor:
+    """``FlowMatchEulerDiscreteScheduler.set_timesteps(sigmas=linspace(0,1,N))``
+    (schedulers.py:171-211; call site pipelines.py:1187): N+1 float32 sigmas, last = 1."""
+    s = torch.linspace(0, 1, num_inference_steps, dtype=torch.float64)
+    s = shift * s / (1 + (shift - 1) * s)
+    return torch.cat([s.to(torch.float32), torch.ones(1)])
+
+
+class GuidanceLoop:
+    """Batched guided-denoise steps for B images on one GPU."""
+
+    def __init__(self, B: int, D: int, statics: GuidanceStatics, P: int, device="cuda:0",
+                 config: Optional[OptimizationConfig] = None, weights=None, latent_elems: int = LATENT_SHAPE[0] * LATENT_SHAPE[1],
+                 decoder_alpha: float = 0.05, stream_variant: int = 0, seed: int = 0):
+        self.lib = _lib.load()
+        self.device = torch.device(device)
+        self.B, self.D, self.P, self.L = B, D, P, latent_elems
+        self.cfg = config or OptimizationConfig()
+        self.statics = statics
+        Vh, Fh = statics.hand_rest.shape[1], statics.hand_faces.shape[0]
+        self.engine = GuidanceEngine(B, D, Vh, Fh, P, device=device, weights=weights, stream_variant=stream_variant)
+        self.opt = GuidanceOptimizer(B, self.L, device=device, config=self.cfg)
+        dev = self.device
+        vol = D * D * D
+        if self.L > vol:
+            raise ValueError("mock decoder needs latent_elems <= D^3")
+        g = torch.Generator().manual_seed(seed)
+        self.tap = torch.randperm(vol, generator=g)[: self.L].sort().values.to(dev)      # int64 voxel taps
+        self.alpha = float(decoder_alpha)
+        f32 = torch.float32
+        self.sdf0 = torch.empty(B, D, D, D, dtype=f32, device=dev)     # decoder output for x1 = 0 (per image)
+        self.sdf = torch.empty(B, D, D, D, dtype=f32, device=dev)      # current decode
+        self.x_t = torch.zeros(B, self.L, dtype=f32, device=dev)       # latents
+        self.velocity = torch.zeros(B, self.L, dtype=f32, device=dev)  # model output being optimised
+        self.x1 = torch.zeros(B, self.L, dtype=f32, device=dev)
+        self.grad_velocity = torch.zeros(B, self.L, dtype=f32, device=dev)
+        self.prev = torch.zeros(B, self.L, dtype=f32, device=dev)
+        self.theta = torch.zeros(B, 16, dtype=f32, device=dev)
+        self.reset_leaves()
+        self.sigmas = set_timesteps_sigmas(self.cfg.num_inference_steps)
+        self._graph: Optional[torch.cuda.CUDAGraph] = None
+        self._graph_key = None
+        self.stream = torch.cuda.Stream(device=dev)
+        self.copy_stream = torch.cuda.Stream(device=dev)
+        self._pinned: Dict[str, torch.Tensor] = {}
+
+    # ------------------------------------------------------------------ state
+    def reset_leaves(self) -> None:
+        """Identity similarity leaves (pipelines.py:1208-1215)."""
+        self.theta.zero_()
+        self.theta[:, 0] = 1.0; self.theta[:, 4] = 1.0
+        self.theta[:, 8] = 1.0; self.theta[:, 12] = 1.0
+
+    def kernels_per_eval(self) -> int:
+        return self.engine.launches_per_eval + 3     # + decoder fwd, decoder adjoint, fused update
+
+    # ------------------------------------------------------------------ one evaluation (enqueue only)
+    def _enqueue_eval(self, sigma: float, late_step: bool, s: torch.cuda.Stream) -> None:
+        lib, B, vol = self.lib, self.B, self.D ** 3
+        sp = C.c_void_p(s.cuda_stream)
+        _lib.check("foho_mock_decoder_forward", lib.foho_mock_decoder_forward(
+            self.sdf.data_ptr(), self.sdf0.data_ptr(), self.x1.data_ptr(), self.tap.data_ptr(), B, vol, self.L,
+            self.alpha, sp))
+        desc = self.engine.make_desc(self.sdf, self.theta, self.statics, late_step=late_step)
+        self.engine.launch(desc, s)
+        _lib.check("foho_mock_decoder_backward", lib.foho_mock_decoder_backward(
+            self.engine.grad_sdf.data_ptr(), self.tap.data_ptr(), self.grad_velocity.data_ptr(), B, vol, self.L,
+            self.alpha * (1.0 - sigma), sp))
+        self.opt.step(self.theta, self.engine.grad_theta, self.velocity, self.grad_velocity, self.x_t, self.x1,
+                      sigma=sigma, stream=s)
+
+    def _enqueue_step(self, step_index: int, s: torch.cuda.Stream) -> None:
+        """All kernels of one guided-denoise step (pipelines.py:1461-1612), no syncs."""
+        cfg = self.cfg
+        sigma = float(self.sigmas[step_index]); sigma_next = float(self.sigmas[step_index + 1])
+        late = step_index >= cfg.num_inference_steps - 3
+        self.opt.set_phase(2)
+        self.opt.reset()                                   # fresh AdamW state every outer step (:1478)
+        # x1 for the first decode of this step: step_final with the incoming velocity (:1507)
+        _lib.check("foho_scheduler_step", self.lib.foho_scheduler_step(
+            self.x_t.data_ptr(), self.velocity.data_ptr(), None, self.x1.data_ptr(), self.x_t.numel(), sigma, sigma_next,
+            C.c_void_p(s.cuda_stream)))
+        for _ in range(cfg.optimization_steps_joint):
+            self._enqueue_eval(sigma, late, s)
+        # obj_latents = scheduler.step(noise_pred_obj, t, obj_latents).prev_sample (:1612)
+        _lib.check("foho_scheduler_step", self.lib.foho_scheduler_step(
+            self.x_t.data_ptr(), self.velocity.data_ptr(), self.prev.data_ptr(), None, self.x_t.numel(), sigma, sigma_next,
+            C.c_void_p(s.cuda_stream)))
+
+    def launches_per_step(self) -> int:
+        # opt.reset(): 4 memsets by torch; 2 scheduler launches; evaluations
+        return self.cfg.optimization_steps_joint * self.kernels_per_eval() + 2
+
+    # ------------------------------------------------------------------ graph
+    def capture(self, step_index: int) -> None:
+        """Capture one guided-denoise step for ``step_index`` (sigma is baked into the graph)."""
+        if self._graph is not None and self._graph_key == step_index:
+            return
+        with torch.cuda.device(self.device):
+            s = self.stream
+            s.wait_stream(torch.cuda.current_stream(self.device))
+            with torch.cuda.stream(s):
+                self._enqueue_eval(float(self.sigmas[step_index]), False, s)   # warm-up outside capture (func attrs)
+                self.opt.reset()
+            s.synchronize()
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g, stream=s):
+                self._enqueue_step(step_index, s)
+            self._graph, self._graph_key = g, step_index
+            torch.cuda.current_stream(self.device).wait_stream(s)
+
+    def run_step_device(self, step_index: int) -> None:
+        """Replay one guided-denoise step; inputs (sdf0, x_t, velocity, theta) already in HBM."""
+        self.capture(step_index)
+        self._graph.replay()
+
+    # ------------------------------------------------------------------ host-buffer API (end to end)
+    def _pin(self, name: str, like: torch.Tensor) -> torch.Tensor:
+        t = self._pinned.get(name)
+        if t is None or t.shape != like.shape or t.dtype != like.dtype:
+            t = torch.empty(like.shape, dtype=like.dtype, pin_memory=True)
+            self._pinned[name] = t
+        return t
+
+    def denoise_step_host(self, step_index: int, sdf0_host: torch.Tensor, x_t_host: torch.Tensor,
+                          velocity_host: torch.Tensor, theta_host: torch.Tensor, out: Optional[dict] = None) -> dict:
+        """One guided-denoise step with HOST inputs/outputs (pinned CPU tensors).
+
+        H2D: decoder base volume [B,D,D,D], latents [B,L], model output [B,L], leaves [B,16].
+        D2H: optimised model output [B,L], prev_sample [B,L], leaves [B,16], loss terms [B,16].
+        Returns a dict of pinned host tensors (valid after the call returns)."""
+        self.capture(step_index)
+        dev = self.device
+        with torch.cuda.device(dev):
+            cs = self.copy_stream
+            with torch.cuda.stream(cs):
+                self.sdf0.copy_(sdf0_host, non_blocking=True)
+                self.sdf.copy_(self.sdf0, non_blocking=True)
+                self.x_t.copy_(x_t_host, non_blocking=True)
+                self.velocity.copy_(velocity_host, non_blocking=True)
+                self.theta.copy_(theta_host, non_blocking=True)
+            self.stream.wait_stream(cs)
+            with torch.cuda.stream(self.stream):
+                self._graph.replay()
+                if out is None:
+                    out = {
+                        "velocity": self._pin("o_velocity", self.velocity), "prev_sample": self._pin("o_prev", self.prev),
+                        "theta": self._pin("o_theta", self.theta), "terms": self._pin("o_terms", self.engine.terms),
+                    }
+                out["velocity"].copy_(self.velocity, non_blocking=True)
+                out["prev_sample"].copy_(self.prev, non_blocking=True)
+                out["theta"].copy_(self.theta, non_blocking=True)
+                out["terms"].copy_(self.engine.terms, non_blocking=True)
+            self.stream.synchronize()
+        return out
+
+    def h2d_bytes_per_step(self) -> int:
+        return 4 * (self.B * self.D ** 3 + 2 * self.B * self.L + self.B * 16)
+
+    def d2h_bytes_per_step(self) -> int:
+        return 4 * (2 * self.B * self.L + self.B * 16 + self.B * _lib.FOHO_NUM_TERMS)

@@ -128,6 +128,39 @@ def boundary_edges(faces: np.ndarray) -> np.ndarray:
     return uniq[cnt == 1]
 
 
+def cap_boundary_loops(faces: np.ndarray) -> np.ndarray:
+    """Close every boundary loop with a triangle fan over its own vertices (no new
+    vertices): MANO's 16-edge wrist loop gains 14 faces (1538 -> 1552).
+
+    The inside/outside rule is ray parity; on an open mesh every column through the hole
+    is 'inside' all the way down, so the guidance engine voxelises the *capped* topology
+    (DESIGN.md "sign rule").  Orientation of the fan is opposite to the loop so the cap
+    is consistently oriented with the rest of the surface."""
+    faces = np.asarray(faces)
+    directed = {}
+    for a, b, c in faces:
+        for u, v in ((a, b), (b, c), (c, a)):
+            directed[(int(u), int(v))] = True
+    nxt = {u: v for (u, v) in directed if (v, u) not in directed}   # boundary edges follow face orientation
+    extra = []
+    seen = set()
+    for start in list(nxt):
+        if start in seen:
+            continue
+        loop = [start]
+        seen.add(start)
+        cur = nxt[start]
+        while cur != start and cur in nxt and cur not in seen:
+            loop.append(cur); seen.add(cur); cur = nxt[cur]
+        if cur != start or len(loop) < 3:
+            continue
+        for i in range(1, len(loop) - 1):
+            extra.append((loop[0], loop[i + 1], loop[i]))
+    if not extra:
+        return faces.astype(np.int32)
+    return np.concatenate([faces, np.asarray(extra, dtype=faces.dtype)], 0).astype(np.int32)
+
+
 def standin_j_regressor(seed: int = 0) -> np.ndarray:
     """Sparse convex 16x778 joint regressor (rows sum to 1), like MANO's."""
     rng = np.random.default_rng(seed)
@@ -312,15 +345,17 @@ def random_similarity(seed: int, scale_range=(0.8, 1.5), trans=0.3) -> np.ndarra
     return T
 
 
-def stack_samples(samples, device="cuda:0", with_kp: bool = True):
-    """Batch ``GuidanceSample``s into the engine's inputs: (sdf [B,D,D,D], theta [B,16], GuidanceStatics)."""
+def stack_samples(samples, device="cuda:0", with_kp: bool = True, cap: bool = False):
+    """Batch ``GuidanceSample``s into the engine's inputs: (sdf [B,D,D,D], theta [B,16], GuidanceStatics).
+    ``cap=True`` closes the wrist loop of the (shared) hand topology first."""
     from .guidance.engine import GuidanceStatics
     dev = torch.device(device)
     sdf = torch.stack([s.sdf for s in samples]).to(dev).contiguous()
     theta = torch.stack([torch.cat([s.theta_h, s.theta_o]) for s in samples]).to(dev).contiguous()
     st = GuidanceStatics(
         hand_rest=torch.stack([s.hand_rest for s in samples]).to(dev).contiguous(),
-        hand_faces=samples[0].hand_faces.to(torch.int32).to(dev).contiguous(),
+        hand_faces=(torch.from_numpy(cap_boundary_loops(samples[0].hand_faces.cpu().numpy())) if cap
+                    else samples[0].hand_faces).to(torch.int32).to(dev).contiguous(),
         cloud=torch.stack([s.cloud for s in samples]).to(dev).contiguous(),
         T_h2m=torch.stack([s.T_h2m for s in samples]).to(dev).contiguous(),
         obj_center=torch.stack([s.obj_center for s in samples]).to(dev).contiguous(),

@@ -77,6 +77,9 @@ typedef struct foho_guidance_desc {
   int32_t image_h, image_w;
   int32_t late_step;    /* 1 when i >= num_inference_steps-3 (pipelines.py:1561)        */
   int32_t stream_variant; /* 0 = default kernel choice, 1 = LDG/STG, 2 = TMA bulk       */
+  int32_t stage_mask;   /* profiling hook: 0 = whole evaluation; else bit0 prep, bit1 dense
+                           stream, bit2 chamfer, bit3 hand voxels, bit4 finalize          */
+  int32_t reserved0;
   float fov_deg;        /* MoGe fov_x in degrees (guidance/run.py:228-230)              */
   float bound;          /* lattice half extent, 1.10 (pipelines.py:1127)                */
   foho_weights w;
@@ -152,6 +155,16 @@ int foho_guidance_update(const foho_update_desc *desc, void *cuda_stream);
  * (schedulers.py:235-319, call site pipelines.py:1612): prev = x + (sigma_next-sigma) v. */
 int foho_scheduler_step(const float *x_t, const float *velocity, float *prev_sample, float *pred_x1,
                         int64_t n, float sigma, float sigma_next, void *cuda_stream);
+
+/* Stand-in for `latent2sdf` (pipelines.py:292-338, the VAE decoder -- SURVEY.md 8f rank 1,
+ * not built yet) so the loop can be driven end to end with mock latents: a fixed sparse
+ * linear decoder  SDF[b, tap[j]] = SDF0[b, tap[j]] + alpha * x1[b, j]  and its exact adjoint
+ * g_x1[b, j] = alpha * G[b, tap[j]]  (then dE/dv = (1-sigma) g_x1).  tap: device int64 [L]
+ * distinct voxel indices shared by the batch. */
+int foho_mock_decoder_forward(float *sdf, const float *sdf0, const float *x1, const int64_t *tap, int32_t B,
+                              int64_t vol, int32_t L, float alpha, void *cuda_stream);
+int foho_mock_decoder_backward(const float *grad_sdf, const int64_t *tap, float *grad_velocity, int32_t B,
+                               int64_t vol, int32_t L, float alpha_times_one_minus_sigma, void *cuda_stream);
 
 /* Replaces `icp(...)` of src/foho/alignment/mesh_align.py:56-175 for the configuration
  * both callers use (on_surface=False, no rotation/reflection search): trimmed

