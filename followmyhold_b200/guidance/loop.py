@@ -53,7 +53,10 @@ class GuidanceLoop:
         if self.L > vol:
             raise ValueError("mock decoder needs latent_elems <= D^3")
         g = torch.Generator().manual_seed(seed)
-        self.tap = torch.randperm(vol, generator=g)[: self.L].sort().values.to(dev)      # int64 voxel taps
+        # one latent token (64 channels) drives one run of 64 consecutive voxels along z
+        run = LATENT_SHAPE[1] if (self.L % LATENT_SHAPE[1] == 0 and vol % LATENT_SHAPE[1] == 0) else 1
+        starts = torch.randperm(vol // run, generator=g)[: self.L // run].sort().values * run
+        self.tap = (starts.view(-1, 1) + torch.arange(run).view(1, -1)).reshape(-1).to(dev)   # int64 voxel taps
         self.alpha = float(decoder_alpha)
         f32 = torch.float32
         self.sdf0 = torch.empty(B, D, D, D, dtype=f32, device=dev)     # decoder output for x1 = 0 (per image)

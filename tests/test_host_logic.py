@@ -1,0 +1,147 @@
+"""Host-side logic that needs no GPU: mesh IO, ICP pre-processing, sharding (gloo, world 2),
+configuration mirror, and the no-CPU-fallback guarantees."""
+import os
+import re
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+from followmyhold_b200 import meshio
+from followmyhold_b200.alignment import mesh_align as MA
+from followmyhold_b200.guidance.config import OptimizationConfig
+from followmyhold_b200.synthetic import icosphere, standin_hand_mesh
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_ply_obj_roundtrip(tmp_path):
+    v, f = standin_hand_mesh()
+    p = str(tmp_path / "m.ply")
+    meshio.write_ply(p, v, f)
+    g = meshio.load(p)
+    assert isinstance(g, meshio.TriMesh) and np.array_equal(g.faces, f) and np.allclose(g.vertices, v)
+    pc = str(tmp_path / "c.ply")
+    meshio.write_ply(pc, v)
+    g = meshio.load(pc)
+    assert isinstance(g, meshio.PointCloud) and g.vertices.shape == (778, 3)
+    o = str(tmp_path / "m.obj")
+    meshio.write_obj(o, v, f)
+    g = meshio.load(o)
+    assert np.array_equal(g.faces, f) and np.allclose(g.vertices, v, atol=1e-6)
+    # ascii PLY with extra vertex properties (MoGe pointcloud.ply carries colours + normals)
+    a = str(tmp_path / "a.ply")
+    with open(a, "w") as fh:
+        fh.write("ply\nformat ascii 1.0\ncomment x\nelement vertex 3\nproperty float x\nproperty float y\nproperty float z\n"
+                 "property uchar red\nproperty uchar green\nproperty uchar blue\nelement face 1\n"
+                 "property list uchar int vertex_indices\nend_header\n0 0 0 1 2 3\n1 0 0 4 5 6\n0 1 0 7 8 9\n3 0 1 2\n")
+    g = meshio.load(a)
+    assert g.vertices.shape == (3, 3) and g.faces.tolist() == [[0, 1, 2]]
+    # binary PLY with extra vertex properties, no faces
+    b = str(tmp_path / "b.ply")
+    rec = np.zeros(5, dtype=[("x", "<f4"), ("y", "<f4"), ("z", "<f4"), ("r", "u1"), ("nx", "<f4")])
+    rec["x"] = np.arange(5); rec["z"] = 2
+    with open(b, "wb") as fh:
+        fh.write(b"ply\nformat binary_little_endian 1.0\nelement vertex 5\nproperty float x\nproperty float y\n"
+                 b"property float z\nproperty uchar r\nproperty float nx\nend_header\n")
+        fh.write(rec.tobytes())
+    g = meshio.load(b)
+    assert isinstance(g, meshio.PointCloud) and np.allclose(g.vertices[:, 0], np.arange(5)) and np.allclose(g.vertices[:, 2], 2)
+
+
+def test_centroid_scale_and_init_transform():
+    v, f = icosphere(2, 2.0)
+    m = meshio.TriMesh(v.astype(np.float64) + np.array([1.0, 2.0, 3.0]), f.astype(np.int64))
+    c, s = MA.get_centroid_scale(m)
+    assert np.allclose(c, [1, 2, 3], atol=1e-6) and abs(s - np.linalg.norm(m.vertices.max(0) - m.vertices.min(0))) < 1e-12
+    pc = meshio.PointCloud(m.vertices * 0.5)
+    c2, s2 = MA.get_centroid_scale(pc)
+    assert np.allclose(c2, pc.vertices.mean(0))
+    T = MA.compute_init_transform(m, pc, fixed_scale=False)
+    out = meshio.transform_points(m.vertices, T)
+    # centroid lands on the target centroid and the bbox diagonal matches
+    assert np.allclose(meshio.TriMesh(out, m.faces).centroid, c2, atol=1e-9)
+    assert abs(np.linalg.norm(out.max(0) - out.min(0)) - s2) < 1e-9
+    Tf = MA.compute_init_transform(m, pc, fixed_scale=True)
+    assert np.allclose(Tf[:3, :3], np.eye(3)) and np.allclose(Tf[:3, 3], c2 - c)
+    assert len(MA.get_all_axis_aligned_rotations()) == 9 and len(MA.get_all_axis_aligned_reflections()) == 7
+
+
+def test_sample_surface_even_properties():
+    v, f = icosphere(3, 1.0)
+    m = meshio.TriMesh(v.astype(np.float64), f.astype(np.int64))
+    rng = np.random.default_rng(0)
+    pts, fi = MA.sample_surface_even(m, 1000, rng)
+    assert 0 < len(pts) <= 1000 and len(fi) == len(pts)
+    # on the surface of the (faceted) sphere
+    assert np.all(np.abs(np.linalg.norm(pts, axis=1) - 1.0) < 0.02)
+    # thinning: no two samples closer than the radius sqrt(area / (3 count))
+    from scipy.spatial import cKDTree
+    radius = np.sqrt(m.area / 3000)
+    assert len(cKDTree(pts).query_pairs(radius * 0.999)) == 0
+    # seeded -> reproducible
+    pts2, _ = MA.sample_surface_even(m, 1000, np.random.default_rng(0))
+    assert np.array_equal(pts, pts2)
+
+
+def test_optimization_config_mirrors_reference_constants():
+    c = OptimizationConfig()()
+    assert (c.optimization_steps_hand, c.optimization_steps_joint, c.optimization_steps_scale) == (200, 50, 100)
+    assert (c.num_inference_steps, c.guidance_start_step, c.handopt_start_step, c.guidance_end_step) == (20, 10, 9, 20)
+    assert c.phase2_hand_lrs == {"scale": 1e-4, "trans": 1e-4, "rot": 1e-2}
+    assert c.obj_lrs == {"scale": 5e-2, "trans": 1e-2, "rot": 1e-2} and c.noise_obj_lr2 == 1e-2 and c.noise_obj_lr1 == 1e-4
+    c50 = OptimizationConfig().with_steps(50)
+    assert (c50.guidance_start_step, c50.handopt_start_step) == (25, 24)
+
+
+def test_product_never_imports_the_oracle_and_has_no_cpu_fallback():
+    pkg = os.path.join(ROOT, "followmyhold_b200")
+    for dp, _, files in os.walk(pkg):
+        for fn in files:
+            if fn.endswith((".py", ".cu", ".cuh")):
+                src = open(os.path.join(dp, fn)).read()
+                assert not re.search(r"^\s*(from|import)\s+oracle\b", src, flags=re.M), f"{fn} imports the oracle"
+    from followmyhold_b200 import _lib
+    from followmyhold_b200.guidance.engine import GuidanceEngine
+    with pytest.raises(_lib.FohoLibraryError):
+        GuidanceEngine(1, 32, 778, 1538, 0, device="cpu")
+    with pytest.raises(_lib.FohoLibraryError):
+        MA.icp_points(np.zeros((4, 3)), np.zeros((4, 3)), 1, 0, device="cpu")
+
+
+WORKER = r'''
+import os, sys, json
+sys.path.insert(0, sys.argv[1])
+import torch.distributed as dist
+from followmyhold_b200.parallel import shard_images, gather_timings, aggregate_throughput
+dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{sys.argv[2]}", rank=int(sys.argv[3]), world_size=2)
+r = dist.get_rank()
+imgs = [f"{i}_cropped_obj.png" for i in range(7)]
+mine = shard_images(imgs, r, 2)
+per = gather_timings({"units": float(len(mine)), "seconds": 1.0 + r})
+if r == 0:
+    print(json.dumps({"mine": mine, "per": per, "agg": aggregate_throughput(per)}))
+dist.barrier(); dist.destroy_process_group()
+'''
+
+
+def test_sharding_and_timing_gather_world2_gloo(tmp_path):
+    from followmyhold_b200.parallel import shard_images
+    imgs = [f"{i}_cropped_obj.png" for i in range(7)]
+    parts = [shard_images(imgs, r, 2) for r in range(2)]
+    assert sorted(parts[0] + parts[1]) == sorted(imgs) and not set(parts[0]) & set(parts[1])
+    script = tmp_path / "w.py"
+    script.write_text(WORKER)
+    import socket
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
+    procs = [subprocess.Popen([sys.executable, str(script), ROOT, str(port), str(r)], stdout=subprocess.PIPE, text=True)
+             for r in range(2)]
+    outs = [p.communicate(timeout=120)[0] for p in procs]
+    assert all(p.returncode == 0 for p in procs)
+    import json
+    res = json.loads(outs[0].strip().splitlines()[-1])
+    assert res["mine"] == parts[0]
+    assert [p["units"] for p in res["per"]] == [4.0, 3.0]
+    assert abs(res["agg"] - 7.0 / 2.0) < 1e-12      # all units / slowest rank
