@@ -28,7 +28,7 @@ TERM_NAMES = ["total", "pen", "con", "int", "count", "mom", "ch", "kp", "treg_h"
 EXPORTED_SYMBOLS = [
     "foho_abi_version", "foho_status_string", "foho_default_weights",
     "foho_guidance_workspace_bytes", "foho_guidance_energy_fwd_bwd", "foho_guidance_update",
-    "foho_scheduler_step", "foho_mock_decoder_forward", "foho_mock_decoder_backward",
+    "foho_scheduler_step", "foho_scheduler_step_f16", "foho_mock_decoder_forward", "foho_mock_decoder_backward",
     "foho_icp_workspace_bytes", "foho_icp_run",
     "foho_mesh2sdf_workspace_bytes", "foho_mesh2sdf_lattice", "foho_intersection_count",
 ]
@@ -158,6 +158,8 @@ def load(build_if_missing: bool = False) -> C.CDLL:
     lib.foho_scheduler_step.restype = C.c_int
     lib.foho_scheduler_step.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_float,
                                         C.c_float, C.c_void_p]
+    lib.foho_scheduler_step_f16.restype = C.c_int
+    lib.foho_scheduler_step_f16.argtypes = list(lib.foho_scheduler_step.argtypes)
     lib.foho_mock_decoder_forward.restype = C.c_int
     lib.foho_mock_decoder_forward.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int64,
                                               C.c_int32, C.c_float, C.c_void_p]

@@ -12,6 +12,7 @@
 //   denom = sqrt(v)/sqrt(1-b2^t) + eps ; p -= (lr/(1-b1^t)) * m/denom
 // HBM-bound elementwise stream: 5 reads + 4 writes of 4 B per velocity element.
 #include "foho_common.cuh"
+#include <cuda_fp16.h>
 #include <math.h>
 
 namespace {
@@ -64,7 +65,9 @@ __global__ void __launch_bounds__(256) k_update(foho_update_desc d, AdamScalars 
     P4[i] = p; M4[i] = m; V4[i] = v;
     if (X4 && O4) {
       float4 x = X4[i];
-      O4[i] = make_float4(x.x + oms * p.x, x.y + oms * p.y, x.z + oms * p.z, x.w + oms * p.w);
+      // separately rounded product and sum, like torch's `sample + (1 - sigma) * model_output` (schedulers.py:481)
+      O4[i] = make_float4(__fadd_rn(x.x, __fmul_rn(oms, p.x)), __fadd_rn(x.y, __fmul_rn(oms, p.y)),
+                          __fadd_rn(x.z, __fmul_rn(oms, p.z)), __fadd_rn(x.w, __fmul_rn(oms, p.w)));
     }
   }
 }
@@ -74,8 +77,23 @@ __global__ void __launch_bounds__(256) k_sched_step(const float *__restrict__ x,
                                                     float dsig, float oms) {
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
     float xi = x[i], vi = v[i];
-    if (prev) prev[i] = xi + dsig * vi;
-    if (x1) x1[i] = xi + oms * vi;
+    // no FMA contraction: bit-equal to torch's separately rounded mul and add (schedulers.py:298,305)
+    if (prev) prev[i] = __fadd_rn(xi, __fmul_rn(dsig, vi));
+    if (x1) x1[i] = __fadd_rn(xi, __fmul_rn(oms, vi));
+  }
+}
+
+// fp16 latents / model output (the reference's dtype, pipelines.py:1204): torch evaluates
+// `sample.float() + (sigma_next - sigma) * model_output` with the 0-dim fp32 factor cast to half, the
+// product rounded to half, the sum in fp32, and the result cast back to half.
+__global__ void __launch_bounds__(256) k_sched_step_f16(const __half *__restrict__ x, const __half *__restrict__ v,
+                                                        __half *__restrict__ prev, __half *__restrict__ x1, long long n,
+                                                        float dsig, float oms) {
+  const float dh = __half2float(__float2half_rn(dsig)), oh = __half2float(__float2half_rn(oms));
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const float xi = __half2float(x[i]), vi = __half2float(v[i]);
+    if (prev) prev[i] = __float2half_rn(__fadd_rn(xi, __half2float(__float2half_rn(__fmul_rn(dh, vi)))));
+    if (x1) x1[i] = __float2half_rn(__fadd_rn(xi, __half2float(__float2half_rn(__fmul_rn(oh, vi)))));
   }
 }
 
@@ -155,6 +173,19 @@ extern "C" int foho_scheduler_step(const float *x_t, const float *velocity, floa
   if (blocks > 1184) blocks = 1184;
   k_sched_step<<<(int)blocks, 256, 0, (cudaStream_t)cuda_stream>>>(x_t, velocity, prev_sample, pred_x1, n,
                                                                   sigma_next - sigma, 1.f - sigma);
+  FOHO_LAUNCH_CHECK();
+  return FOHO_OK;
+}
+
+extern "C" int foho_scheduler_step_f16(const void *x_t, const void *velocity, void *prev_sample, void *pred_x1, int64_t n,
+                                       float sigma, float sigma_next, void *cuda_stream) {
+  if (!x_t || !velocity || (!prev_sample && !pred_x1)) return FOHO_E_NULL;
+  if (n < 1) return FOHO_E_SHAPE;
+  long long blocks = (n + 255) / 256;
+  if (blocks > 1184) blocks = 1184;
+  k_sched_step_f16<<<(int)blocks, 256, 0, (cudaStream_t)cuda_stream>>>((const __half *)x_t, (const __half *)velocity,
+                                                                      (__half *)prev_sample, (__half *)pred_x1, n,
+                                                                      sigma_next - sigma, 1.f - sigma);
   FOHO_LAUNCH_CHECK();
   return FOHO_OK;
 }

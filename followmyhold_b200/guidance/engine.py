@@ -216,12 +216,19 @@ def scheduler_step(x_t: torch.Tensor, velocity: torch.Tensor, sigma: float, sigm
     """``FlowMatchEulerDiscreteScheduler.step`` arithmetic on the device
     (schedulers.py:294-309): returns (prev_sample, pred_x1)."""
     lib = _lib.load()
+    if not (x_t.is_cuda and velocity.is_cuda):
+        raise _lib.FohoLibraryError("scheduler_step needs CUDA tensors; there is no CPU fallback")
+    if x_t.dtype != velocity.dtype or x_t.dtype not in (torch.float32, torch.float16):
+        raise ValueError("scheduler_step: x_t and velocity must both be float32 or both float16")
+    x_t, velocity = x_t.contiguous(), velocity.contiguous()
     prev = torch.empty_like(x_t)
     x1 = torch.empty_like(x_t)
-    s = torch.cuda.current_stream(x_t.device)
-    _lib.check("foho_scheduler_step", lib.foho_scheduler_step(
-        x_t.data_ptr(), velocity.data_ptr(), prev.data_ptr(), x1.data_ptr(), x_t.numel(), float(sigma),
-        float(sigma_next), C.c_void_p(s.cuda_stream)))
+    fn = lib.foho_scheduler_step if x_t.dtype == torch.float32 else lib.foho_scheduler_step_f16
+    with torch.cuda.device(x_t.device):
+        s = torch.cuda.current_stream(x_t.device)
+        _lib.check("foho_scheduler_step", fn(
+            x_t.data_ptr(), velocity.data_ptr(), prev.data_ptr(), x1.data_ptr(), x_t.numel(), float(sigma),
+            float(sigma_next), C.c_void_p(s.cuda_stream)))
     return prev, x1
 
 

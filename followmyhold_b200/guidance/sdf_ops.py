@@ -18,20 +18,22 @@ import torch
 from .. import _lib
 
 
+def lattice_axes(bbox_min, bbox_max, cells: int):
+    """The three float32 coordinate arrays of a (cells+1)^3 lattice spanning a bbox."""
+    n = int(cells) + 1
+    return [np.linspace(bbox_min[a], bbox_max[a], n, dtype=np.float32) for a in range(3)]
+
+
 def generate_dense_grid_points(bbox_min: np.ndarray, bbox_max: np.ndarray, octree_depth: int, indexing: str = "ij",
                                octree_resolution: int = None):
-    """kaolin_sdf_ops.py:26-45 (identical arithmetic; returns xyz [N,3] f32, grid_size, length)."""
-    length = bbox_max - bbox_min
-    num_cells = np.exp2(octree_depth)
-    if octree_resolution is not None:
-        num_cells = octree_resolution
-    x = np.linspace(bbox_min[0], bbox_max[0], int(num_cells) + 1, dtype=np.float32)
-    y = np.linspace(bbox_min[1], bbox_max[1], int(num_cells) + 1, dtype=np.float32)
-    z = np.linspace(bbox_min[2], bbox_max[2], int(num_cells) + 1, dtype=np.float32)
-    [xs, ys, zs] = np.meshgrid(x, y, z, indexing=indexing)
-    xyz = np.stack((xs, ys, zs), axis=-1).reshape(-1, 3)
-    grid_size = [int(num_cells) + 1] * 3
-    return xyz, grid_size, length
+    """Same contract as the reference helper (pipelines.py:341-360, used at kaolin_sdf_ops.py:146-152):
+    2**octree_depth cells per axis unless ``octree_resolution`` overrides it; returns
+    (xyz [N,3] f32 in ``indexing`` order, [n,n,n], bbox extent).  The product path never materialises
+    xyz -- it hands ``lattice_axes`` to the kernel -- this exists for callers and tests."""
+    cells = int(octree_resolution) if octree_resolution is not None else int(2 ** octree_depth)
+    axes = lattice_axes(bbox_min, bbox_max, cells)
+    xyz = np.stack(np.meshgrid(*axes, indexing=indexing), axis=-1).reshape(-1, 3)
+    return xyz, [cells + 1] * 3, np.asarray(bbox_max) - np.asarray(bbox_min)
 
 
 def mesh2sdf_axes(verts: torch.Tensor, faces: torch.Tensor, xs, ys, zs) -> torch.Tensor:
@@ -67,7 +69,7 @@ def get_sdf_of_meshes(mesh1, mesh2, device="cuda", resolution=64):
     v1, v2 = mesh1[0].detach(), mesh2[0].detach()
     bbox_min = torch.minimum(v1.min(dim=0)[0], v2.min(dim=0)[0]).cpu().numpy()
     bbox_max = torch.maximum(v1.max(dim=0)[0], v2.max(dim=0)[0]).cpu().numpy()
-    axes = [np.linspace(bbox_min[a], bbox_max[a], int(resolution) + 1, dtype=np.float32) for a in range(3)]
+    axes = lattice_axes(bbox_min, bbox_max, resolution)
     return mesh2sdf(mesh1, axes, device, resolution), mesh2sdf(mesh2, axes, device, resolution)
 
 

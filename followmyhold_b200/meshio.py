@@ -195,11 +195,13 @@ def load(path: str) -> Geometry:
     raise ValueError(f"unsupported mesh format '{ext}' ({path}); GLB targets are not handled by the alignment path")
 
 
-def write_ply(path: str, vertices: np.ndarray, faces: Optional[np.ndarray] = None) -> None:
-    """Binary little-endian PLY (float32 vertices, int32 faces) like ``trimesh`` exports."""
-    v = np.ascontiguousarray(vertices, dtype="<f4")
+def write_ply(path: str, vertices: np.ndarray, faces: Optional[np.ndarray] = None, double: bool = False) -> None:
+    """Binary little-endian PLY (float32 vertices, int32 faces) like ``trimesh`` exports;
+    ``double=True`` keeps float64 coordinates (``property double``)."""
+    v = np.ascontiguousarray(vertices, dtype="<f8" if double else "<f4")
+    t = "double" if double else "float"
     header = ["ply", "format binary_little_endian 1.0", f"element vertex {len(v)}",
-              "property float x", "property float y", "property float z"]
+              f"property {t} x", f"property {t} y", f"property {t} z"]
     if faces is not None and len(faces):
         header += [f"element face {len(faces)}", "property list uchar int vertex_indices"]
     header.append("end_header")

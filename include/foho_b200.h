@@ -156,6 +156,13 @@ int foho_guidance_update(const foho_update_desc *desc, void *cuda_stream);
 int foho_scheduler_step(const float *x_t, const float *velocity, float *prev_sample, float *pred_x1,
                         int64_t n, float sigma, float sigma_next, void *cuda_stream);
 
+/* Same step for fp16 latents / model output (the reference's dtype: latents are created fp16 at
+ * pipelines.py:1204-1205).  Reproduces torch's mixed-precision evaluation of schedulers.py:294-309 bit
+ * for bit: factor and product rounded to half, sum in fp32, result cast back to half.
+ * x_t, velocity, prev_sample, pred_x1: device __half [n]. */
+int foho_scheduler_step_f16(const void *x_t, const void *velocity, void *prev_sample, void *pred_x1, int64_t n,
+                            float sigma, float sigma_next, void *cuda_stream);
+
 /* Stand-in for `latent2sdf` (pipelines.py:292-338, the VAE decoder -- SURVEY.md 8f rank 1,
  * not built yet) so the loop can be driven end to end with mock latents: a fixed sparse
  * linear decoder  SDF[b, tap[j]] = SDF0[b, tap[j]] + alpha * x1[b, j]  and its exact adjoint

@@ -83,3 +83,36 @@ def icp_points(source_points, target_points, n_iter, n_outliers, fixed_scale=Fal
     if return_history:
         return best_transform, best_cost, np.asarray(hist), qi
     return best_transform, best_cost
+
+
+def init_transform_points(src, tgt, fixed_scale=False):
+    """mesh_align.py:18-35 for two point clouds: vertex-mean centroids, bbox-diagonal scales,
+    T(translation) @ S(scale about the source centroid)."""
+    sc, tc = src.mean(axis=0), tgt.mean(axis=0)
+    ss = np.linalg.norm(src.max(axis=0) - src.min(axis=0))
+    ts = np.linalg.norm(tgt.max(axis=0) - tgt.min(axis=0))
+    T = np.eye(4)
+    T[:3, 3] = tc - sc
+    if fixed_scale:
+        return T
+    f = ts / ss
+    S = np.diag([f, f, f, 1.0])
+    S[:3, 3] = sc * (1.0 - f)
+    return T @ S
+
+
+def align_points(src, tgt, outliers=0.2, iterations_coarse=50, iterations_fine=100, min_scale=0.7, max_scale=3.0,
+                 fixed_scale=False):
+    """mesh_align.py:178-217 for two point clouds (the sample counts collapse to the cloud sizes,
+    :75-83): init, coarse ICP, fine ICP (which keeps icp()'s own fixed_scale=False default, :201-204),
+    final = fine @ coarse @ init.  Returns (final [4,4], transformed source points)."""
+    src = np.asarray(src, dtype=np.float64)
+    tgt = np.asarray(tgt, dtype=np.float64)
+    n_out = int(outliers * len(src))
+    init = init_transform_points(src, tgt, fixed_scale)
+    p = transform_points(src, init)
+    coarse, _ = icp_points(p, tgt, iterations_coarse, n_out, fixed_scale, min_scale, max_scale)
+    p = transform_points(p, coarse)
+    fine, _ = icp_points(p, tgt, iterations_fine, n_out, False, min_scale, max_scale)
+    p = transform_points(p, fine)
+    return fine @ coarse @ init, p

@@ -1,0 +1,106 @@
+"""CUDA path (through the C-ABI) against vectors produced by executing the reference's own code
+(tests/golden/ref_golden.npz, generator tests/golden/make_golden.py)."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+G = np.load(os.path.join(os.path.dirname(__file__), "golden", "ref_golden.npz"))
+DEV = "cuda:0"
+
+
+@pytest.mark.parametrize("N,shift", [(20, 1.0), (50, 1.0), (20, 3.0)])
+def test_scheduler_kernels_bit_equal_reference(N, shift):
+    """a2: `scheduler.step` / `step_final` (schedulers.py:235-319,411-493), fp32 and the reference's fp16."""
+    from followmyhold_b200.guidance.engine import scheduler_step
+    from followmyhold_b200.guidance.loop import set_timesteps_sigmas
+    tag = f"sch_N{N}_s{int(shift)}"
+    sig = set_timesteps_sigmas(N, shift)
+    x = torch.from_numpy(G["sch_x"]).to(DEV); v = torch.from_numpy(G["sch_v"]).to(DEV)
+    for dt, dn in ((torch.float32, "f32"), (torch.float16, "f16")):
+        for j, k in enumerate(G[tag + "_ks"]):
+            prev, x1 = scheduler_step(x.to(dt), v.to(dt), float(sig[k]), float(sig[k + 1]))
+            assert prev.dtype == dt
+            assert np.array_equal(prev.float().cpu().numpy(), G[f"{tag}_{dn}_prev"][j])
+            assert np.array_equal(x1.float().cpu().numpy(), G[f"{tag}_{dn}_x1"][j])
+            assert np.array_equal(x1.float().cpu().numpy(), G[f"{tag}_{dn}_final"][j])
+
+
+@pytest.mark.parametrize("phase,tag", [(1, "p1"), (1.5, "p15"), (2, "p2")])
+def test_fused_update_matches_reference_optimiser(phase, tag):
+    """a3+a4: real get_guidance_params groups + torch Adam/AdamW(eps=1e-4) trajectories."""
+    from followmyhold_b200.guidance.engine import GuidanceOptimizer
+    L = G["opt_vel0"].shape[1]
+    theta = torch.from_numpy(G["opt_theta0"]).view(1, 16).clone().to(DEV)
+    vel = torch.from_numpy(G["opt_vel0"]).clone().to(DEV)
+    x_t = torch.zeros_like(vel); x1 = torch.empty_like(vel)
+    opt = GuidanceOptimizer(1, L, device=DEV)
+    opt.set_phase(phase); opt.reset()
+    for k in range(G["opt_grads_theta"].shape[0]):
+        gt = torch.from_numpy(G["opt_grads_theta"][k]).view(1, 16).to(DEV)
+        gv = torch.from_numpy(G["opt_grads_vel"][k]).to(DEV)
+        opt.step(theta, gt, vel, gv, x_t, x1, sigma=0.25)
+        torch.cuda.synchronize()
+        assert torch.allclose(theta.cpu().view(-1), torch.from_numpy(G[f"opt_{tag}_theta"][k]), rtol=3e-6, atol=1e-8)
+        assert torch.allclose(vel.cpu(), torch.from_numpy(G[f"opt_{tag}_vel"][k]), rtol=3e-6, atol=1e-8)
+        if phase != 1:
+            assert torch.equal(x1, 0.75 * vel)              # x1 = x_t + (1-sigma) v with x_t = 0
+
+
+def test_intersection_count_bit_equal_reference():
+    """a9: honerf_intersection_loss (pipelines.py:231-239)."""
+    from followmyhold_b200.guidance import sdf_ops
+    sh = torch.from_numpy(G["a9_sdf_hand"]).to(DEV); so = torch.from_numpy(G["a9_sdf_obj"]).to(DEV)
+    assert float(sdf_ops.honerf_intersection_loss(sh, so)) == float(np.float32(G["a9_count_loss"]))
+
+
+def test_hand_similarity_in_fused_kernel_matches_reference():
+    """a6 as evaluated by k_prep: the engine's transformed hand verts vs the reference's
+    transform_mesh_around_center_w_scale (pipelines.py:108-118) on the same verts / RT / scale."""
+    from followmyhold_b200.guidance.engine import GuidanceEngine, GuidanceStatics
+    from tests.test_golden_reference import _quat_from_matrix
+    verts = G["a6_verts"]
+    V = verts.shape[0]
+    RT = G["a6_RT"].astype(np.float64)
+    q = _quat_from_matrix(RT[:3, :3]) * 1.7
+    theta = np.zeros(16, np.float32)
+    theta[0] = G["a6_scale"][0]; theta[1:4] = RT[:3, 3]; theta[4:8] = q
+    theta[8] = 1.0; theta[12] = 1.0
+    faces = np.stack([np.arange(V - 2), np.arange(1, V - 1), np.arange(2, V)], 1).astype(np.int32)
+    D = 16
+    st = GuidanceStatics(hand_rest=torch.from_numpy(verts).view(1, V, 3).to(DEV), hand_faces=torch.from_numpy(faces).to(DEV),
+                         cloud=None, T_h2m=torch.eye(4).view(1, 4, 4).to(DEV), obj_center=torch.zeros(1, 3, device=DEV))
+    eng = GuidanceEngine(1, D, V, faces.shape[0], 0, device=DEV)
+    sdf = torch.ones(1, D, D, D, device=DEV)
+    eng.energy_fwd_bwd(sdf, torch.from_numpy(theta).view(1, 16).to(DEV), st)
+    torch.cuda.synchronize()
+    assert np.abs(eng.hand_moge[0].cpu().numpy() - G["a6_out"]).max() < 2e-6
+
+
+@pytest.mark.parametrize("tag", ["a", "b", "c", "d"])
+def test_icp_kernel_matches_reference_loop(tag):
+    """a16: the reference's own icp() loop (mesh_align.py:56-175) on fixed point sets."""
+    from followmyhold_b200.alignment.mesh_align import icp
+    from followmyhold_b200.meshio import PointCloud
+    n_iter, outliers, fixed, mn, mx = G[f"icp_{tag}_kw"]
+    T, cost = icp(PointCloud(G[f"icp_{tag}_src"].copy()), PointCloud(G[f"icp_{tag}_tgt"].copy()), int(n_iter),
+                  fixed_scale=bool(fixed), outliers=float(outliers), min_scale=float(mn), max_scale=float(mx), device=DEV)
+    assert np.abs(T - G[f"icp_{tag}_T"]).max() < 1e-9
+    assert abs(cost - float(G[f"icp_{tag}_cost"])) < 1e-11
+
+
+def test_align_meshes_impl_matches_reference_pipeline(tmp_path):
+    """a17+a18: init, coarse(50), fine(100), fine @ coarse @ init, and the exported points."""
+    from followmyhold_b200.alignment.mesh_align import align_meshes_impl
+    from followmyhold_b200.meshio import load, write_ply
+    sp, tp = str(tmp_path / "s.ply"), str(tmp_path / "t.ply")
+    write_ply(sp, G["init_src"], double=True); write_ply(tp, G["init_tgt"], double=True)
+    src_rt = load(sp).vertices
+    T = align_meshes_impl(sp, tp, str(tmp_path / "T.npy"), str(tmp_path / "m.ply"), False, 0.2, False, False, False,
+                          50, 1000, 5000, 100, 5000, 10000, 0.7, 3.0, False, device=DEV)
+    assert np.array_equal(src_rt, G["init_src"])            # float64 PLY round trip is exact
+    assert np.abs(T - G["align_T"]).max() < 1e-8
+    assert np.abs(np.load(str(tmp_path / "T.npy")) - T).max() == 0
+    assert np.abs(load(str(tmp_path / "m.ply")).vertices - G["align_pts"]).max() < 1e-6   # exported as float32

@@ -36,9 +36,12 @@ def test_mesh2sdf_and_count_match_oracle():
     r = np.linalg.norm((P - np.array([0.05, 0.02, 0.0])) / (0.12 * np.array([1.0, 0.8, 0.6])), axis=1)
     g2 = s2.cpu().numpy()
     assert (g2[r < 0.9] < 0).all() and (g2[r > 1.05] > 0).all()
-    ref_cnt = float(((s1 < 0) & (s2 < 0)).sum()) / 1000
-    assert abs(float(cnt) - ref_cnt) < 1e-9
-    assert float(O.honerf_intersection_loss(s1.cpu(), s2.cpu())) == pytest.approx(ref_cnt)
+    n_both = int(((s1 < 0) & (s2 < 0)).sum())
+    assert n_both > 0
+    # the reference returns int64.sum()/1000 = a float32 tensor (pipelines.py:237); so do we: bit-equal
+    ref_cnt = float(torch.tensor(n_both) / 1000)
+    assert float(cnt) == ref_cnt
+    assert float(O.honerf_intersection_loss(s1.cpu(), s2.cpu())) == ref_cnt
 
 
 def test_fused_update_matches_torch_adamw_and_step_final():
