@@ -40,12 +40,24 @@ enum {
   ACC_INT = 0,      // sum over candidates of (-S) * d_grid
   ACC_GKAPPA = 1,   // dE/dkappa
   ACC_CH_CLOUD = 2, // sum over cloud points of d2 to nearest hand vertex
+  ACC_DIST = 3,     // sum over hand verts of clamp(d2 - margin, 0) to the object mesh (REF a7)
+  ACC_MEAN_D2 = 4,  // sum over hand verts of d2 to the object mesh
+  ACC_VREG = 5,     // sum over object verts of |ot|^2 (REF a10)
+  ACC_EDGE = 6,     // sum over object edges of |ot0 - ot1|^2 (REF a10)
   ACC_NUM = 8
 };
 enum { CNT_NCAND = 0, CNT_COUNT = 1, CNT_FLAGS = 2, CNT_NUM = 4 };
 
 #define FOHO_STREAM_PARTIALS 8      // m0, m1x, m1y, m1z, m2, count_obj, pad, pad
 #define FOHO_MAX_STREAM_CTAS 2048   // per sample
+
+// Per-sample state of the explicit object mesh (REF a5/a6 on the FlexiCubes vertices).
+struct FohoObjInfo {
+  float c[3];                 // bbox centre of T_h2m(obj verts)  (pipelines.py:111, current verts)
+  int amin[3], amax[3];       // packed indices of the arg-min / arg-max vertex per axis
+  int v0, v1, e0, e1;         // packed vertex / edge ranges of this sample
+  int pad;
+};
 
 struct FohoWorkspace {
   FohoFrame *frames;          // [B]
@@ -59,6 +71,10 @@ struct FohoWorkspace {
   float *stream_part;         // [B,FOHO_MAX_STREAM_CTAS,FOHO_STREAM_PARTIALS]
   uint32_t *parity;           // [B,D*D*W]
   int *cand;                  // [B,cap]
+  float *ot;                  // [Vo,3] transformed object verts, centred on c_o
+  float *g_ot;                // [Vo,3] dE/d(ot)
+  unsigned long long *knn_obj;// [B,Vh] packed (d2 bits << 32 | packed object vertex index)
+  FohoObjInfo *oinfo;         // [B]
   int cap;
   int W;                      // words per column
   size_t total;
@@ -71,7 +87,7 @@ static inline int foho_cand_capacity(int D) {
   return (int)(n < (1ll << 18) ? n : (1ll << 18));
 }
 
-static inline void foho_ws_layout(FohoWorkspace &w, char *base, int B, int D, int Vh, int /*Fh*/, int /*P*/, int /*Vo*/) {
+static inline void foho_ws_layout(FohoWorkspace &w, char *base, int B, int D, int Vh, int /*Fh*/, int /*P*/, int Vo) {
   size_t off = 0;
   auto take = [&](size_t bytes) { char *p = base ? base + off : nullptr; off += foho_align_up(bytes, 256); return p; };
   w.W = (D + 31) / 32;
@@ -87,6 +103,11 @@ static inline void foho_ws_layout(FohoWorkspace &w, char *base, int B, int D, in
   w.stream_part = (float *)take(sizeof(float) * FOHO_STREAM_PARTIALS * FOHO_MAX_STREAM_CTAS * (size_t)B);
   w.parity = (uint32_t *)take(sizeof(uint32_t) * (size_t)B * D * D * w.W);
   w.cand = (int *)take(sizeof(int) * (size_t)B * w.cap);
+  const size_t vo = Vo > 0 ? (size_t)Vo : 1;
+  w.ot = (float *)take(sizeof(float) * 3 * vo);
+  w.g_ot = (float *)take(sizeof(float) * 3 * vo);
+  w.knn_obj = (unsigned long long *)take(sizeof(unsigned long long) * (size_t)B * Vh);
+  w.oinfo = (FohoObjInfo *)take(sizeof(FohoObjInfo) * (size_t)B);
   w.total = off;
 }
 
@@ -132,3 +153,7 @@ __device__ __forceinline__ void block_sum(float (&v)[N], float *smem) {
 
 // kernels implemented in the other translation units
 int foho_launch_stream(const foho_guidance_desc *d, const FohoWorkspace &ws, int *grid_x_out, cudaStream_t st);
+// explicit object-mesh terms (guidance_objmesh.cu): `pre` runs before k_finalize (it adds the contact
+// gradient to G_hm), `post` after it (it adds to grad_theta[8..15] and the terms).
+int foho_launch_objmesh_pre(const foho_guidance_desc *d, const FohoWorkspace &ws, cudaStream_t st);
+int foho_launch_objmesh_post(const foho_guidance_desc *d, const FohoWorkspace &ws, cudaStream_t st);

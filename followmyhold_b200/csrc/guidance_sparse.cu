@@ -710,7 +710,9 @@ extern "C" int foho_guidance_energy_fwd_bwd(const foho_guidance_desc *dp, void *
   if (d.P > 0 && !d.cloud) return FOHO_E_NULL;
   if (d.n_joints != 0 && d.n_joints != 16) return FOHO_E_ARG;
   if (!(d.bound > 0.f)) return FOHO_E_ARG;
-  if (d.Vo_total != 0) return FOHO_E_ARG;   // explicit object mesh terms (a7/a10 REF) are served by foho_mesh_terms
+  if (d.Vo_total < 0 || d.Eo_total < 0) return FOHO_E_SHAPE;
+  if (d.Vo_total > 0 && (!d.obj_verts || !d.obj_vert_offsets)) return FOHO_E_NULL;
+  if (d.Eo_total > 0 && (d.Vo_total == 0 || !d.obj_edges || !d.obj_edge_offsets)) return FOHO_E_NULL;
   if (((uintptr_t)d.workspace & 255) != 0) return FOHO_E_WORKSPACE;
   if (((uintptr_t)d.sdf & 15) != 0 || ((uintptr_t)d.grad_sdf & 15) != 0) return FOHO_E_ARG;
   FohoWorkspace ws;
@@ -718,7 +720,7 @@ extern "C" int foho_guidance_energy_fwd_bwd(const foho_guidance_desc *dp, void *
   if (ws.total > d.workspace_bytes) return FOHO_E_WORKSPACE;
   cudaStream_t st = (cudaStream_t)cuda_stream;
 
-  const int sm = d.stage_mask == 0 ? 0x1f : d.stage_mask;
+  const int sm = d.stage_mask == 0 ? 0x3f : d.stage_mask;
   static int last_gx = 1;
   if (sm & 1) {
     k_prep<<<d.B, 256, 0, st>>>(d, ws);
@@ -757,9 +759,18 @@ extern "C" int foho_guidance_energy_fwd_bwd(const foho_guidance_desc *dp, void *
     k_voxdist<<<dim3(64, d.B), 256, smem, st>>>(d, ws);
     FOHO_LAUNCH_CHECK();
   }
+  const bool obj_mesh = (sm & 32) && d.Vo_total > 0;
+  if (obj_mesh) {
+    int rc = foho_launch_objmesh_pre(dp, ws, st);
+    if (rc != FOHO_OK) return rc;
+  }
   if (sm & 16) {
     k_finalize<<<d.B, FIN_THREADS, 0, st>>>(d, ws, gx);
     FOHO_LAUNCH_CHECK();
+  }
+  if (obj_mesh && (sm & 16)) {
+    int rc = foho_launch_objmesh_post(dp, ws, st);
+    if (rc != FOHO_OK) return rc;
   }
   return FOHO_OK;
 }

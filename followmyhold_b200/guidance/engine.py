@@ -50,11 +50,47 @@ class GuidanceStatics:
     image_hw: Sequence[int] = (512, 512)
 
 
+@dataclass
+class ObjectMeshBatch:
+    """Explicit object surfaces of a batch (the FlexiCubes output of pipelines.py:1509, Hunyuan space),
+    packed: sample b owns verts[vert_offsets[b]:vert_offsets[b+1]] and edges[edge_offsets[b]:edge_offsets[b+1]]
+    (edge indices address the packed vertex array).  Vertex counts may differ per sample and per call."""
+    verts: torch.Tensor          # [Vo,3] f32
+    vert_offsets: torch.Tensor   # [B+1] i32
+    edges: torch.Tensor          # [Eo,2] i32 unique undirected edges (pytorch3d ``edges_packed`` semantics)
+    edge_offsets: torch.Tensor   # [B+1] i32
+
+
+def unique_edges(faces) -> "torch.Tensor":
+    """Unique undirected edges of a triangle list [F,3] -> [E,2] int64 (what ``mesh_edge_loss`` of
+    pipelines.py:1575 averages over: pytorch3d ``Meshes.edges_packed``)."""
+    import numpy as np
+    f = faces.detach().cpu().numpy() if torch.is_tensor(faces) else np.asarray(faces)
+    e = np.concatenate([f[:, [0, 1]], f[:, [1, 2]], f[:, [2, 0]]], 0)
+    return torch.from_numpy(np.unique(np.sort(e, axis=1), axis=0).astype(np.int64))
+
+
+def pack_object_meshes(meshes, device="cuda:0") -> ObjectMeshBatch:
+    """[(verts [V,3], faces [F,3]), ...] (one per sample, torch or numpy) -> ObjectMeshBatch on ``device``."""
+    import numpy as np
+    vs, es, vo, eo = [], [], [0], [0]
+    for v, f in meshes:
+        v = torch.as_tensor(v, dtype=torch.float32).reshape(-1, 3)
+        e = unique_edges(f) if len(f) else torch.zeros(0, 2, dtype=torch.int64)
+        es.append(e + vo[-1]); vs.append(v)
+        vo.append(vo[-1] + v.shape[0]); eo.append(eo[-1] + e.shape[0])
+    dev = torch.device(device)
+    verts = torch.cat(vs).to(dev).contiguous() if vo[-1] else torch.zeros(0, 3, device=dev)
+    edges = torch.cat(es).to(torch.int32).to(dev).contiguous() if eo[-1] else torch.zeros(0, 2, dtype=torch.int32, device=dev)
+    return ObjectMeshBatch(verts, torch.tensor(vo, dtype=torch.int32, device=dev), edges,
+                           torch.tensor(eo, dtype=torch.int32, device=dev))
+
+
 class GuidanceEngine:
     """Owns workspace + output buffers for a fixed problem shape and launches the kernels."""
 
     def __init__(self, B: int, D: int, Vh: int, Fh: int, P: int, device="cuda:0",
-                 weights: Optional[_lib.Weights] = None, stream_variant: int = 0):
+                 weights: Optional[_lib.Weights] = None, stream_variant: int = 0, max_obj_verts: int = 0):
         self.lib = _lib.load()
         self.device = torch.device(device)
         if self.device.type != "cuda":
@@ -62,7 +98,8 @@ class GuidanceEngine:
         self.B, self.D, self.Vh, self.Fh, self.P = B, D, Vh, Fh, P
         self.weights = weights if weights is not None else _lib.default_weights()
         self.stream_variant = stream_variant
-        nbytes = self.lib.foho_guidance_workspace_bytes(B, D, Vh, Fh, P, 0)
+        self.max_obj_verts = int(max_obj_verts)
+        nbytes = self.lib.foho_guidance_workspace_bytes(B, D, Vh, Fh, P, self.max_obj_verts)
         if nbytes == 0:
             raise ValueError("unsupported guidance problem shape")
         dev = self.device
@@ -75,11 +112,14 @@ class GuidanceEngine:
         self.terms = torch.zeros(B, _lib.FOHO_NUM_TERMS, dtype=torch.float32, device=dev)
         self.hand_moge = torch.zeros(B, Vh, 3, dtype=torch.float32, device=dev)
         self.hand_grid = torch.zeros(B, Vh, 3, dtype=torch.float32, device=dev)
-        self.launches_per_eval = 7 if P > 0 else 6
+        self.grad_obj_verts = (torch.zeros(self.max_obj_verts, 3, dtype=torch.float32, device=dev)
+                               if self.max_obj_verts > 0 else None)
+        self.launches_per_eval = 7 if P > 0 else 6      # + 4 when an object mesh is passed
 
     def make_desc(self, sdf: torch.Tensor, theta: torch.Tensor, st: GuidanceStatics,
                   grad_sdf: Optional[torch.Tensor] = None, late_step: bool = False,
-                  grad_hand_ext: Optional[torch.Tensor] = None) -> _lib.GuidanceDesc:
+                  grad_hand_ext: Optional[torch.Tensor] = None,
+                  obj_mesh: Optional[ObjectMeshBatch] = None) -> _lib.GuidanceDesc:
         B, D, Vh, Fh, P = self.B, self.D, self.Vh, self.Fh, self.P
         f32 = torch.float32
         _chk(sdf, (B, D, D, D), f32, "sdf")
@@ -119,6 +159,19 @@ class GuidanceEngine:
         d.hand_moge, d.hand_grid = self.hand_moge.data_ptr(), self.hand_grid.data_ptr()
         d.Vo_total = 0
         d.Eo_total = 0
+        if obj_mesh is not None and obj_mesh.verts.shape[0] > 0:
+            Vo, Eo = int(obj_mesh.verts.shape[0]), int(obj_mesh.edges.shape[0])
+            if Vo > self.max_obj_verts:
+                raise ValueError(f"object mesh has {Vo} vertices; engine was sized for max_obj_verts={self.max_obj_verts}")
+            _chk(obj_mesh.verts, (Vo, 3), f32, "obj_mesh.verts")
+            _chk(obj_mesh.vert_offsets, (B + 1,), torch.int32, "obj_mesh.vert_offsets")
+            _chk(obj_mesh.edges, (Eo, 2), torch.int32, "obj_mesh.edges")
+            _chk(obj_mesh.edge_offsets, (B + 1,), torch.int32, "obj_mesh.edge_offsets")
+            d.Vo_total, d.Eo_total = Vo, Eo
+            d.obj_verts, d.obj_vert_offsets = obj_mesh.verts.data_ptr(), obj_mesh.vert_offsets.data_ptr()
+            d.obj_edges = obj_mesh.edges.data_ptr() if Eo > 0 else None
+            d.obj_edge_offsets = obj_mesh.edge_offsets.data_ptr()
+            d.grad_obj_verts = self.grad_obj_verts.data_ptr()
         d.workspace, d.workspace_bytes = self._ws_ptr, self._ws_bytes
         return d
 

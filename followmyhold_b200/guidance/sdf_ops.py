@@ -73,9 +73,11 @@ def get_sdf_of_meshes(mesh1, mesh2, device="cuda", resolution=64):
     return mesh2sdf(mesh1, axes, device, resolution), mesh2sdf(mesh2, axes, device, resolution)
 
 
-def honerf_intersection_loss(sdf_hand: torch.Tensor, sdf_obj: torch.Tensor) -> torch.Tensor:
-    """pipelines.py:231-239: count(sdf_obj<0 & sdf_hand<0)/1000 (no gradient)."""
+def intersection_count(sdf_hand: torch.Tensor, sdf_obj: torch.Tensor) -> torch.Tensor:
+    """Number of lattice points inside both meshes: int64 tensor [1] on the device."""
     lib = _lib.load()
+    if not (sdf_hand.is_cuda and sdf_obj.is_cuda):
+        raise _lib.FohoLibraryError("intersection_count needs CUDA tensors; there is no CPU fallback")
     a = sdf_hand.detach().to(torch.float32).contiguous().view(-1)
     b = sdf_obj.detach().to(torch.float32).contiguous().view(-1)
     cnt = torch.zeros(1, dtype=torch.int64, device=a.device)
@@ -83,4 +85,10 @@ def honerf_intersection_loss(sdf_hand: torch.Tensor, sdf_obj: torch.Tensor) -> t
         s = torch.cuda.current_stream(a.device)
         _lib.check("foho_intersection_count", lib.foho_intersection_count(
             a.data_ptr(), b.data_ptr(), a.numel(), cnt.data_ptr(), C.c_void_p(s.cuda_stream)))
-    return cnt[0] / 1000
+    return cnt
+
+
+def honerf_intersection_loss(sdf_hand: torch.Tensor, sdf_obj: torch.Tensor) -> torch.Tensor:
+    """pipelines.py:231-239: count(sdf_obj<0 & sdf_hand<0)/1000 (no gradient); like the reference's
+    ``penet_points_id.sum() / 1000`` this is an int64 device scalar divided by torch."""
+    return intersection_count(sdf_hand, sdf_obj)[0] / 1000

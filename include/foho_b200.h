@@ -78,7 +78,7 @@ typedef struct foho_guidance_desc {
   int32_t late_step;    /* 1 when i >= num_inference_steps-3 (pipelines.py:1561)        */
   int32_t stream_variant; /* 0 = default kernel choice, 1 = LDG/STG, 2 = TMA bulk       */
   int32_t stage_mask;   /* profiling hook: 0 = whole evaluation; else bit0 prep, bit1 dense
-                           stream, bit2 chamfer, bit3 hand voxels, bit4 finalize          */
+                           stream, bit2 chamfer, bit3 hand voxels, bit4 finalize, bit5 object mesh */
   int32_t reserved0;
   float fov_deg;        /* MoGe fov_x in degrees (guidance/run.py:228-230)              */
   float bound;          /* lattice half extent, 1.10 (pipelines.py:1127)                */
@@ -101,14 +101,18 @@ typedef struct foho_guidance_desc {
   float *hand_moge;          /* device [B,Vh,3] OUT transformed hand verts (may be NULL) */
   float *hand_grid;          /* device [B,Vh,3] OUT same verts in lattice units (may be NULL) */
 
-  /* optional explicit object mesh (FlexiCubes output, Hunyuan space; pipelines.py:1509) */
+  /* optional explicit object mesh (FlexiCubes output, Hunyuan space; pipelines.py:1509): enables the
+   * REF terms a7 distance_loss (:1529-1541), a10 obj_verts_loss / mesh_edge_loss (:1570,1575) and the
+   * w_intersection switch (:1561-1564).  The similarity theta_o acts about the bbox centre of the
+   * T_h2m-transformed vertices (:108-118); sample b owns packed vertices
+   * [obj_vert_offsets[b], obj_vert_offsets[b+1]) and edges [obj_edge_offsets[b], obj_edge_offsets[b+1]). */
   int32_t Vo_total;          /* total packed object vertices over the batch (0 = none)   */
   int32_t Eo_total;          /* total packed unique edges                                */
   const float *obj_verts;    /* device [Vo_total,3]                                      */
   const int32_t *obj_vert_offsets; /* device [B+1]                                       */
   const int32_t *obj_edges;  /* device [Eo_total,2] indices into the packed vertex array */
   const int32_t *obj_edge_offsets; /* device [B+1]                                       */
-  float *grad_obj_verts;     /* device [Vo_total,3] OUT                                  */
+  float *grad_obj_verts;     /* device [Vo_total,3] OUT dE/d(obj_verts) (may be NULL)    */
 
   void *workspace;           /* device, >= foho_guidance_workspace_bytes(...)            */
   size_t workspace_bytes;

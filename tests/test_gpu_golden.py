@@ -53,7 +53,9 @@ def test_intersection_count_bit_equal_reference():
     """a9: honerf_intersection_loss (pipelines.py:231-239)."""
     from followmyhold_b200.guidance import sdf_ops
     sh = torch.from_numpy(G["a9_sdf_hand"]).to(DEV); so = torch.from_numpy(G["a9_sdf_obj"]).to(DEV)
-    assert float(sdf_ops.honerf_intersection_loss(sh, so)) == float(np.float32(G["a9_count_loss"]))
+    n = int(((G["a9_sdf_hand"] < 0) & (G["a9_sdf_obj"] < 0)).sum())
+    assert int(sdf_ops.intersection_count(sh, so)[0]) == n
+    assert float(sdf_ops.honerf_intersection_loss(sh, so)) == pytest.approx(float(G["a9_count_loss"]), rel=2e-7)
 
 
 def test_hand_similarity_in_fused_kernel_matches_reference():

@@ -164,3 +164,94 @@ def test_full_size_properties():
     torch.cuda.synchronize()
     assert torch.equal(t1[:, 4], terms[:, 4])
     assert torch.equal(g1[0][mask], gs[0][mask])
+
+
+def _object_meshes(samples, subdivs):
+    """Tessellated ellipsoids (Hunyuan space) matching each sample's volume; different sizes per sample."""
+    from followmyhold_b200.synthetic import ellipsoid_volume, icosphere
+    out = []
+    for k, s in enumerate(samples):
+        seed = getattr(s, "seed", k)
+        radii = ellipsoid_volume(4, seed)[1].numpy()
+        v, f = icosphere(subdivs[k % len(subdivs)], 1.0)
+        out.append(((v * radii).astype(np.float32), f.astype(np.int64)))
+    return out
+
+
+@pytest.mark.parametrize("late", [False, True])
+def test_object_mesh_terms_match_oracle(late):
+    """REF a5/a6/a7/a10 + the w_intersection switch on an explicit object surface
+    (pipelines.py:1520-1541,1561-1576): terms, leaf gradients and dE/d(obj_verts)."""
+    from followmyhold_b200.guidance.engine import GuidanceEngine, pack_object_meshes
+    from oracle import guidance_oracle as O
+    B, D, P = 3, 32, 1024
+    samples = [make_guidance_sample(D, P, seed) for seed in range(B)]
+    meshes = _object_meshes(samples, (2, 3, 1))
+    sdf, theta, st = stack_samples(samples)
+    om = pack_object_meshes(meshes)
+    eng = GuidanceEngine(B, D, 778, 1538, P, max_obj_verts=int(om.verts.shape[0]) + 7)
+    desc = eng.make_desc(sdf, theta, st, late_step=late, obj_mesh=om)
+    eng.launch(desc)
+    torch.cuda.synchronize()
+    terms = eng.terms.cpu().numpy(); gt = eng.grad_theta.cpu().numpy(); gov = eng.grad_obj_verts.cpu().numpy()
+    hg = eng.hand_grid.cpu().numpy()
+    vo = om.vert_offsets.cpu().numpy()
+    errs = []
+    f64 = torch.float64
+    for b, s in enumerate(samples):
+        ov = torch.from_numpy(meshes[b][0]).to(f64).requires_grad_(True)
+        sd = s.sdf.to(f64).clone().requires_grad_(True)
+        th = s.theta_h.to(f64).clone().requires_grad_(True); to = s.theta_o.to(f64).clone().requires_grad_(True)
+        out = O.guidance_energy(sd, s.hand_rest.to(f64), s.hand_faces, s.cloud.to(f64), th, to, s.T_h2m.to(f64),
+                                s.obj_center.to(f64), j_regressor=s.j_regressor.to(f64), kps_2d=s.kps_2d.to(f64),
+                                fov_deg=s.fov_deg, image_hw=s.image_hw, obj_verts=ov,
+                                obj_faces=torch.from_numpy(meshes[b][1]), late_step=late, hand_grid_verts_override=hg[b])
+        out["total"].backward()
+        for n, i in (("L_dist", 10), ("L_vreg", 11), ("L_edge", 12), ("mean_d2", 13), ("total", 0)):
+            ref = float(out[n].detach())
+            if not abs(terms[b, i] - ref) <= REL * abs(ref) + 1e-9:
+                errs.append(f"{n}[{b}]: {terms[b, i]} vs {ref}")
+        for name, got, ref in (("grad_theta_h", gt[b, :8], th.grad.numpy()), ("grad_theta_o", gt[b, 8:], to.grad.numpy()),
+                               ("grad_obj_verts", gov[vo[b]:vo[b + 1]], ov.grad.numpy())):
+            try:
+                _close(f"{name}[{b}]", got, ref)
+            except AssertionError as e:
+                errs.append(str(e))
+    assert not errs, "\n".join(errs)
+    # the volume-only evaluation is unchanged by passing no mesh, and the mesh terms really contributed
+    t_mesh = eng.terms[:, 0].clone()
+    eng.energy_fwd_bwd(sdf, theta, st, late_step=late)
+    torch.cuda.synchronize()
+    assert (eng.terms[:, 10:14] == 0).all() and not torch.equal(eng.terms[:, 0], t_mesh)
+
+
+def test_object_mesh_empty_sample_and_switch():
+    """A sample with zero object vertices contributes nothing (the reference skips such a step,
+    pipelines.py:1511-1513); a hand lying on the surface flips w_intersection at a late step (:1561-1564)."""
+    from followmyhold_b200.guidance.engine import GuidanceEngine, pack_object_meshes
+    B, D, P = 2, 32, 256
+    samples = [make_guidance_sample(D, P, seed) for seed in (5, 6)]
+    sdf, theta, st = stack_samples(samples)
+    # sample 0: object vertices = the transformed hand itself mapped back to Hunyuan space => d2 = 0 < 1e-3
+    eng = GuidanceEngine(B, D, 778, 1538, P, max_obj_verts=778)
+    eng.energy_fwd_bwd(sdf, theta, st)
+    torch.cuda.synchronize()
+    base = eng.terms.clone()
+    hm = eng.hand_moge[0].double().cpu()
+    T = samples[0].T_h2m.double()
+    hun = (hm - T[:3, 3]) @ torch.linalg.inv(T[:3, :3]).T
+    faces = samples[0].hand_faces.long()
+    om = pack_object_meshes([(hun.float(), faces), (torch.zeros(0, 3), torch.zeros(0, 3, dtype=torch.long))])
+    th = theta.clone(); th[:, 8:] = torch.tensor([1.0, 0, 0, 0, 1, 0, 0, 0], device=th.device)   # identity object leaves
+    for late in (False, True):
+        eng.launch(eng.make_desc(sdf, th, st, late_step=late, obj_mesh=om))
+        torch.cuda.synchronize()
+        t = eng.terms.cpu()
+        assert t[0, 13] < 1e-6 and t[0, 10] == 0                       # mean_d2 ~ 0, no attraction
+        assert (t[1, 10:14] == 0).all()                                # empty sample
+        w = eng.weights
+        lift = (w.w_int_hi - w.w_int_lo) * float(t[0, 4]) if late else 0.0
+        expect = float(t[0, 0]) - w.w_vreg * float(t[0, 11]) - w.w_edge * float(t[0, 12]) - lift
+        eng.launch(eng.make_desc(sdf, th, st, late_step=late))
+        torch.cuda.synchronize()
+        assert abs(float(eng.terms[0, 0]) - expect) <= 1e-5 * abs(expect) + 1e-9

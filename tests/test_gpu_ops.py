@@ -38,10 +38,11 @@ def test_mesh2sdf_and_count_match_oracle():
     assert (g2[r < 0.9] < 0).all() and (g2[r > 1.05] > 0).all()
     n_both = int(((s1 < 0) & (s2 < 0)).sum())
     assert n_both > 0
-    # the reference returns int64.sum()/1000 = a float32 tensor (pipelines.py:237); so do we: bit-equal
-    ref_cnt = float(torch.tensor(n_both) / 1000)
-    assert float(cnt) == ref_cnt
-    assert float(O.honerf_intersection_loss(s1.cpu(), s2.cpu())) == ref_cnt
+    assert int(sdf_ops.intersection_count(s1, s2)[0]) == n_both                 # integer work: exact
+    # the reference returns int64.sum()/1000, a float32 tensor (pipelines.py:237); torch's CUDA and CPU
+    # division kernels differ in the last ulp, so the float is compared to 1 ulp
+    assert float(cnt) == pytest.approx(n_both / 1000, rel=2e-7)
+    assert float(O.honerf_intersection_loss(s1.cpu(), s2.cpu())) == pytest.approx(n_both / 1000, rel=2e-7)
 
 
 def test_fused_update_matches_torch_adamw_and_step_final():
