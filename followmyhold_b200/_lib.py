@@ -16,12 +16,13 @@ PKG_DIR = Path(__file__).resolve().parent
 REPO_ROOT = PKG_DIR.parent
 CSRC = PKG_DIR / "csrc"
 LIB_PATH = PKG_DIR / "libfoho_b200.so"
-SOURCES = ["guidance_stream.cu", "guidance_sparse.cu", "guidance_objmesh.cu", "guidance_update.cu", "icp.cu",
+SOURCES = ["guidance_stream.cu", "guidance_sparse.cu", "guidance_objmesh.cu", "guidance_chamfer.cu", "guidance_update.cu", "icp.cu",
            "mesh_sdf.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "-Xcompiler", "-fPIC", "-Xcompiler", "-O3"]
 
 FOHO_NUM_TERMS = 16
+ABI_VERSION = 2
 TERM_NAMES = ["total", "pen", "con", "int", "count", "mom", "ch", "kp", "treg_h", "treg_o", "dist", "vreg",
               "edge", "mean_d2", "ncand", "flags"]
 
@@ -29,6 +30,7 @@ TERM_NAMES = ["total", "pen", "con", "int", "count", "mom", "ch", "kp", "treg_h"
 EXPORTED_SYMBOLS = [
     "foho_abi_version", "foho_status_string", "foho_default_weights",
     "foho_guidance_workspace_bytes", "foho_guidance_energy_fwd_bwd", "foho_guidance_update",
+    "foho_guidance_accel_bytes", "foho_guidance_prepare_statics",
     "foho_scheduler_step", "foho_scheduler_step_f16", "foho_mock_decoder_forward", "foho_mock_decoder_backward",
     "foho_icp_workspace_bytes", "foho_icp_run",
     "foho_mesh2sdf_workspace_bytes", "foho_mesh2sdf_lattice", "foho_intersection_count",
@@ -109,6 +111,7 @@ class GuidanceDesc(C.Structure):
         ("Vo_total", C.c_int32), ("Eo_total", C.c_int32), ("obj_verts", C.c_void_p),
         ("obj_vert_offsets", C.c_void_p), ("obj_edges", C.c_void_p), ("obj_edge_offsets", C.c_void_p),
         ("grad_obj_verts", C.c_void_p), ("workspace", C.c_void_p), ("workspace_bytes", C.c_size_t),
+        ("accel", C.c_void_p), ("accel_bytes", C.c_size_t),
     ]
 
 
@@ -154,6 +157,10 @@ def load(build_if_missing: bool = False) -> C.CDLL:
     lib.foho_guidance_workspace_bytes.argtypes = [C.c_int32] * 6
     lib.foho_guidance_energy_fwd_bwd.restype = C.c_int
     lib.foho_guidance_energy_fwd_bwd.argtypes = [C.POINTER(GuidanceDesc), C.c_void_p]
+    lib.foho_guidance_accel_bytes.restype = C.c_size_t
+    lib.foho_guidance_accel_bytes.argtypes = [C.c_int32] * 3
+    lib.foho_guidance_prepare_statics.restype = C.c_int
+    lib.foho_guidance_prepare_statics.argtypes = [C.POINTER(GuidanceDesc), C.c_void_p]
     lib.foho_guidance_update.restype = C.c_int
     lib.foho_guidance_update.argtypes = [C.POINTER(UpdateDesc), C.c_void_p]
     lib.foho_scheduler_step.restype = C.c_int
@@ -181,7 +188,7 @@ def load(build_if_missing: bool = False) -> C.CDLL:
                                           C.c_size_t, C.c_void_p]
     lib.foho_intersection_count.restype = C.c_int
     lib.foho_intersection_count.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]
-    if lib.foho_abi_version() != 1:
+    if lib.foho_abi_version() != ABI_VERSION:
         raise FohoLibraryError("libfoho_b200.so ABI version mismatch; rebuild it")
     _lib = lib
     return lib

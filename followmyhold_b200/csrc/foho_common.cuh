@@ -80,6 +80,35 @@ struct FohoWorkspace {
   size_t total;
 };
 
+// ---- per-image search structures for the chamfer term (guidance_chamfer.cu), built once by
+//      foho_guidance_prepare_statics into the caller's `accel` buffer
+#define FOHO_ACCEL_HV 1024        // max hand vertices the structured search handles
+#define FOHO_ACCEL_LEAVES 128     // leaves of 8 Morton-consecutive rest vertices
+#define FOHO_ACCEL_SUPERS 16      // super-boxes of 8 leaves
+#define FOHO_ACCEL_G 32           // cloud grid: up to G cubic cells per axis
+#define FOHO_ACCEL_CELLS (FOHO_ACCEL_G * FOHO_ACCEL_G * FOHO_ACCEL_G)
+
+struct FohoAccelHand {
+  float4 v[FOHO_ACCEL_HV];                 // sorted rest verts relative to the rest bbox centre; w = original index
+  float4 leaf_lo[FOHO_ACCEL_LEAVES], leaf_hi[FOHO_ACCEL_LEAVES];
+  float4 sup_lo[FOHO_ACCEL_SUPERS], sup_hi[FOHO_ACCEL_SUPERS];
+  int n_leaves, n_supers, Vh, pad;
+};
+struct FohoAccelGrid {
+  float origin[3];                         // min corner of the cloud bbox (absolute MoGe)
+  float cell, inv_cell;                    // cubic cell edge
+  int dims[3];                             // occupied cells per axis (<= FOHO_ACCEL_G)
+  int P, pad;
+};
+struct FohoAccel {
+  FohoAccelHand *hand;        // [B]
+  FohoAccelGrid *grid;        // [B]
+  int *cell_start;            // [B, CELLS+1] CSR over Morton cell codes
+  int *cell_fill;             // [B, CELLS] build scratch
+  float4 *pts;                // [B,P] cloud sorted by cell; w = original index
+  size_t total;
+};
+
 static inline size_t foho_align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
 static inline int foho_cand_capacity(int D) {
@@ -157,3 +186,5 @@ int foho_launch_stream(const foho_guidance_desc *d, const FohoWorkspace &ws, int
 // gradient to G_hm), `post` after it (it adds to grad_theta[8..15] and the terms).
 int foho_launch_objmesh_pre(const foho_guidance_desc *d, const FohoWorkspace &ws, cudaStream_t st);
 int foho_launch_objmesh_post(const foho_guidance_desc *d, const FohoWorkspace &ws, cudaStream_t st);
+// structured chamfer search (guidance_chamfer.cu); used when desc->accel is set
+int foho_launch_chamfer_accel(const foho_guidance_desc *d, const FohoWorkspace &ws, cudaStream_t st);

@@ -732,7 +732,12 @@ extern "C" int foho_guidance_energy_fwd_bwd(const foho_guidance_desc *dp, void *
     if (rc != FOHO_OK) return rc;
     last_gx = gx;
   }
-  if ((sm & 4) && d.P > 0) {
+  if ((sm & 4) && d.P > 0 && d.accel) {
+    if (d.Vh > FOHO_ACCEL_HV) return FOHO_E_SHAPE;
+    if (((uintptr_t)d.accel & 255) != 0) return FOHO_E_WORKSPACE;
+    int rc = foho_launch_chamfer_accel(dp, ws, st);
+    if (rc != FOHO_OK) return rc;
+  } else if ((sm & 4) && d.P > 0) {
     const size_t smem = (size_t)d.Vh * (16 + 8 + 12);
     if (smem > 200 * 1024) return FOHO_E_SHAPE;
     static size_t attr = 0;

@@ -115,6 +115,34 @@ class GuidanceEngine:
         self.grad_obj_verts = (torch.zeros(self.max_obj_verts, 3, dtype=torch.float32, device=dev)
                                if self.max_obj_verts > 0 else None)
         self.launches_per_eval = 7 if P > 0 else 6      # + 4 when an object mesh is passed
+        self._accel = None
+        self._accel_ptr = 0
+        self._accel_bytes = 0
+        self._accel_for = None
+
+    def prepare(self, st: GuidanceStatics, stream: Optional[torch.cuda.Stream] = None) -> None:
+        """Per-image setup, once per set of statics: build the chamfer search structures
+        (``foho_guidance_prepare_statics``).  Evaluations with the same ``st`` object then use the
+        structured search (one more launch); other statics fall back to the brute-force search."""
+        if self.P <= 0 or st.cloud is None or self.Vh > 1024:
+            return
+        _chk(st.hand_rest, (self.B, self.Vh, 3), torch.float32, "hand_rest")
+        _chk(st.cloud, (self.B, self.P, 3), torch.float32, "cloud")
+        nbytes = self.lib.foho_guidance_accel_bytes(self.B, self.Vh, self.P)
+        if self._accel is None:
+            self._accel = torch.empty(nbytes + 256, dtype=torch.uint8, device=self.device)
+            self._accel_ptr = self._accel.data_ptr() + ((-self._accel.data_ptr()) % 256)
+            self._accel_bytes = nbytes
+        d = _lib.GuidanceDesc()
+        d.B, d.Vh, d.P = self.B, self.Vh, self.P
+        d.hand_rest, d.cloud = st.hand_rest.data_ptr(), st.cloud.data_ptr()
+        d.accel, d.accel_bytes = self._accel_ptr, self._accel_bytes
+        with torch.cuda.device(self.device):
+            s = stream if stream is not None else torch.cuda.current_stream(self.device)
+            _lib.check("foho_guidance_prepare_statics",
+                       self.lib.foho_guidance_prepare_statics(C.byref(d), C.c_void_p(s.cuda_stream)))
+        self._accel_for = st
+        self.launches_per_eval = 8
 
     def make_desc(self, sdf: torch.Tensor, theta: torch.Tensor, st: GuidanceStatics,
                   grad_sdf: Optional[torch.Tensor] = None, late_step: bool = False,
@@ -173,6 +201,8 @@ class GuidanceEngine:
             d.obj_edge_offsets = obj_mesh.edge_offsets.data_ptr()
             d.grad_obj_verts = self.grad_obj_verts.data_ptr()
         d.workspace, d.workspace_bytes = self._ws_ptr, self._ws_bytes
+        if self._accel_for is st and P > 0:
+            d.accel, d.accel_bytes = self._accel_ptr, self._accel_bytes
         return d
 
     def launch(self, desc: _lib.GuidanceDesc, stream: Optional[torch.cuda.Stream] = None) -> None:

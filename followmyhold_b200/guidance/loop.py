@@ -47,6 +47,7 @@ class GuidanceLoop:
         self.statics = statics
         Vh, Fh = statics.hand_rest.shape[1], statics.hand_faces.shape[0]
         self.engine = GuidanceEngine(B, D, Vh, Fh, P, device=device, weights=weights, stream_variant=stream_variant)
+        self.engine.prepare(statics)
         self.opt = GuidanceOptimizer(B, self.L, device=device, config=self.cfg)
         dev = self.device
         vol = D * D * D

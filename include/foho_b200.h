@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define FOHO_ABI_VERSION 1
+#define FOHO_ABI_VERSION 2
 
 #define FOHO_OK 0
 #define FOHO_E_NULL (-1)      /* required pointer is NULL            */
@@ -116,6 +116,12 @@ typedef struct foho_guidance_desc {
 
   void *workspace;           /* device, >= foho_guidance_workspace_bytes(...)            */
   size_t workspace_bytes;
+
+  /* optional per-image search structures for the chamfer term, filled once per image set by
+   * foho_guidance_prepare_statics (hand_rest and cloud must not change afterwards).  NULL selects the
+   * brute-force search; results are identical up to ties between equidistant neighbours. */
+  void *accel;               /* device, 256-byte aligned, >= foho_guidance_accel_bytes(...) */
+  size_t accel_bytes;
 } foho_guidance_desc;
 
 int foho_abi_version(void);
@@ -129,6 +135,12 @@ void foho_default_weights(foho_weights *w);
 size_t foho_guidance_workspace_bytes(int32_t B, int32_t D, int32_t Vh, int32_t Fh, int32_t P,
                                      int32_t Vo_total);
 int foho_guidance_energy_fwd_bwd(const foho_guidance_desc *desc, void *cuda_stream);
+
+/* Build the search structures of desc->accel from desc->hand_rest [B,Vh,3] (Vh <= 1024) and
+ * desc->cloud [B,P,3]: the per-image setup the reference does once before its loop (mesh / target
+ * loading, pipelines.py:1218-1256); only B, Vh, P, hand_rest, cloud, accel, accel_bytes are read. */
+size_t foho_guidance_accel_bytes(int32_t B, int32_t Vh, int32_t P);
+int foho_guidance_prepare_statics(const foho_guidance_desc *desc, void *cuda_stream);
 
 /* Replaces `joint_optimizer.step()` (torch.optim.AdamW(eps=1e-4), pipelines.py:1478,1601;
  * Adam of :1318 with weight_decay=0) fused with `scheduler.step_final`

@@ -54,7 +54,7 @@ def test_argument_validation_without_gpu():
     """Invalid descriptors are rejected before any CUDA call."""
     from followmyhold_b200 import _lib
     lib = _lib.load()
-    assert lib.foho_abi_version() == 1
+    assert lib.foho_abi_version() == _lib.ABI_VERSION
     assert lib.foho_guidance_energy_fwd_bwd(None, None) == -1
     d = _lib.GuidanceDesc()
     assert lib.foho_guidance_energy_fwd_bwd(ctypes.byref(d), None) == -1          # NULL pointers

@@ -31,13 +31,16 @@ def _close(name, got, ref, rel=REL, abs_=1e-9):
     assert err <= rel * scale + abs_, f"{name}: max err {err:.3e} vs scale {scale:.3e} (rel {err / max(scale, 1e-300):.2e})"
 
 
-@pytest.mark.parametrize("D,variant", [(32, 1), (32, 2), (64, 2), (64, 1), (65, 0), (33, 0)])
-def test_energy_and_grads_match_oracle(D, variant):
+@pytest.mark.parametrize("D,variant,accel", [(32, 1, False), (32, 2, True), (64, 2, False), (64, 1, True), (65, 0, True),
+                                             (33, 0, False)])
+def test_energy_and_grads_match_oracle(D, variant, accel):
     from followmyhold_b200.guidance.engine import GuidanceEngine
     B, P = 3, 2048
     samples = [make_guidance_sample(D, P, seed) for seed in range(B)]
     sdf, theta, st = stack_samples(samples)
     eng = GuidanceEngine(B, D, 778, 1538, P, stream_variant=variant)
+    if accel:
+        eng.prepare(st)          # structured chamfer search; otherwise the brute-force kernel
     terms, gs, gt = eng.energy_fwd_bwd(sdf, theta, st)
     torch.cuda.synchronize()
     terms = terms.cpu().numpy(); gs = gs.cpu(); gt = gt.cpu().numpy()
@@ -255,3 +258,41 @@ def test_object_mesh_empty_sample_and_switch():
         eng.launch(eng.make_desc(sdf, th, st, late_step=late))
         torch.cuda.synchronize()
         assert abs(float(eng.terms[0, 0]) - expect) <= 1e-5 * abs(expect) + 1e-9
+
+
+@pytest.mark.parametrize("P,case", [(5, "tiny"), (1500, "ragged"), (4096, "far"), (3000, "degenerate"), (8192, "plain")])
+def test_structured_chamfer_equals_brute_force_and_scipy(P, case):
+    """NS a15 both ways: the grid / box-hierarchy searches return the same nearest neighbours as the
+    brute-force kernel and as scipy's cKDTree (the NN oracle the reference's ICP uses), including a hand
+    far outside the cloud's bbox (ring search gives up -> exhaustive scan) and a zero-extent cloud."""
+    from scipy.spatial import cKDTree
+    from followmyhold_b200 import _lib
+    from followmyhold_b200.guidance.engine import GuidanceEngine
+    B, D = 2, 16
+    samples = [make_guidance_sample(D, P, 70 + i) for i in range(B)]
+    if case == "far":
+        for s in samples:
+            s.cloud = s.cloud * 0.05 + torch.tensor([3.0, -2.0, 1.0])
+    if case == "degenerate":
+        samples[0].cloud = samples[0].cloud[:1].repeat(P, 1)
+    sdf, theta, st = stack_samples(samples)
+    w = _lib.default_weights()
+    for n in ("w_pen", "w_con", "w_ivol", "w_mom", "w_hand", "w_treg_o"):
+        setattr(w, n, 0.0)
+    res = []
+    for accel in (False, True):
+        eng = GuidanceEngine(B, D, 778, 1538, P, weights=w)
+        if accel:
+            eng.prepare(st)
+        terms, _, gt = eng.energy_fwd_bwd(sdf, theta, st)
+        torch.cuda.synchronize()
+        res.append((terms.cpu().numpy().copy(), gt.cpu().numpy().copy(), eng.hand_moge.cpu().numpy().copy()))
+    (t0, g0, hm), (t1, g1, _) = res
+    for b in range(B):
+        cl = samples[b].cloud.double().numpy()
+        d_hc = cKDTree(cl).query(hm[b].astype(np.float64))[0] ** 2
+        d_ch = cKDTree(hm[b].astype(np.float64)).query(cl)[0] ** 2
+        ref = d_hc.mean() + d_ch.mean()
+        assert abs(t0[b, 6] - ref) <= 2e-5 * ref + 1e-12, (case, "brute", t0[b, 6], ref)
+        assert abs(t1[b, 6] - ref) <= 2e-5 * ref + 1e-12, (case, "accel", t1[b, 6], ref)
+        _close(f"grad_theta[{b}] accel vs brute", g1[b], g0[b], rel=2e-5)
