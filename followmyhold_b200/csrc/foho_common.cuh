@@ -85,8 +85,6 @@ struct FohoWorkspace {
 #define FOHO_ACCEL_HV 1024        // max hand vertices the structured search handles
 #define FOHO_ACCEL_LEAVES 128     // leaves of 8 Morton-consecutive rest vertices
 #define FOHO_ACCEL_SUPERS 16      // super-boxes of 8 leaves
-#define FOHO_ACCEL_G 32           // cloud grid: up to G cubic cells per axis
-#define FOHO_ACCEL_CELLS (FOHO_ACCEL_G * FOHO_ACCEL_G * FOHO_ACCEL_G)
 
 struct FohoAccelHand {
   float4 v[FOHO_ACCEL_HV];                 // sorted rest verts relative to the rest bbox centre; w = original index
@@ -96,16 +94,18 @@ struct FohoAccelHand {
 };
 struct FohoAccelGrid {
   float origin[3];                         // min corner of the cloud bbox (absolute MoGe)
-  float cell, inv_cell;                    // cubic cell edge
-  int dims[3];                             // occupied cells per axis (<= FOHO_ACCEL_G)
-  int P, pad;
+  float quant;                             // 1023 / largest bbox extent: Morton quantisation
+  int P, pad[3];
 };
 struct FohoAccel {
   FohoAccelHand *hand;        // [B]
   FohoAccelGrid *grid;        // [B]
-  int *cell_start;            // [B, CELLS+1] CSR over Morton cell codes
-  int *cell_fill;             // [B, CELLS] build scratch
-  float4 *pts;                // [B,P] cloud sorted by cell; w = original index
+  unsigned long long *keys;   // [B,P2] build scratch: (Morton code << 32 | index), sorted
+  int P2;                     // P padded to a power of two >= 2048
+  float4 *pts;                // [B,P] cloud in Morton order; w = original index
+  float4 *g_lo, *g_hi;        // [B,NGcap] AABB of each group of 32 sorted points (absolute MoGe)
+  float4 *s_lo, *s_hi;        // [B,NScap] AABB of each super-group of 32 groups
+  int NGcap, NScap;
   size_t total;
 };
 

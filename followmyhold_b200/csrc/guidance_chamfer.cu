@@ -6,16 +6,17 @@
 //
 //   cloud -> hand : the hand moves by a similarity, so "nearest transformed hand vertex of c" is
 //                   "nearest REST vertex of c pulled back into the rest frame".  The rest vertices are
-//                   Morton-sorted once into leaves of 8 with tight AABBs and super-boxes of 8 leaves;
-//                   each cloud point descends that two-level hierarchy with its running best as the
-//                   pruning radius (k_chamfer_c2h).  The cloud is stored cell-sorted, so the 32 points
-//                   of a warp are neighbours and take the same branches.
-//   hand -> cloud : the cloud never moves: it is binned once into a 32^3 Morton-ordered uniform grid
-//                   (CSR); each hand vertex scans Chebyshev rings of cells until its best distance is
-//                   below the ring radius (k_chamfer_h2c, one warp per vertex).
+//                   Morton-sorted once into leaves of 8 with tight AABBs.  The cloud is stored
+//                   Morton-sorted, so a warp's 32 points are neighbours: the warp prunes the leaves
+//                   against the AABB of its 32 pulled-back points (dual-tree bound) and walks the
+//                   survivors in lock step (k_chamfer_c2h).
+//   hand -> cloud : the cloud never moves: its Morton-sorted points are boxed once in groups of 32 and
+//                   super-groups of 32 groups; one warp per hand vertex descends that hierarchy,
+//                   testing 32 boxes or 32 points per step (k_chamfer_h2c).
 //
-// Both are exact (not approximate) searches; the brute-force k_chamfer in guidance_sparse.cu remains
-// as the path used when the caller passes no accel buffer, and as the cross-check in the tests.
+// Both are exact (not approximate) searches, stateless between evaluations; the brute-force k_chamfer
+// in guidance_sparse.cu remains as the path used when the caller passes no accel buffer, and as the
+// cross-check in the tests.
 #include "foho_common.cuh"
 
 namespace {
@@ -115,22 +116,10 @@ __global__ void __launch_bounds__(ACC_THREADS) k_accel_hand(const float *__restr
   if (tid == 0) { H->n_leaves = nleaf; H->n_supers = nsup; H->Vh = Vh; H->pad = 0; }
 }
 
-// ----------------------------------------------------------------------------- build: cloud grid
-__device__ __forceinline__ unsigned int spread5(unsigned int v) {   // 5 bits -> every third bit
-  v &= 0x1fu;
-  v = (v | (v << 8)) & 0x0000100Fu;
-  v = (v | (v << 4)) & 0x000100C3u;
-  v = (v | (v << 2)) & 0x00001249u;
-  return v;
-}
-__device__ __forceinline__ int cell_code(int ix, int iy, int iz) {
-  return (int)((spread5((unsigned)ix) << 2) | (spread5((unsigned)iy) << 1) | spread5((unsigned)iz));
-}
-__device__ __forceinline__ int cell_coord(float x, float origin, float inv_cell, int dim) {
-  int c = (int)floorf((x - origin) * inv_cell);
-  return c < 0 ? 0 : (c >= dim ? dim - 1 : c);
-}
-
+// ----------------------------------------------------------------------------- build: cloud order
+// The cloud is put into 30-bit Morton order (10 bits per axis over its cubic bbox) by a bitonic sort
+// of (code << 32 | index) keys, so that ANY run of consecutive points is spatially compact.  Runs
+// once per image; not on the per-evaluation path.
 __global__ void __launch_bounds__(ACC_THREADS) k_accel_cloud_bbox(const float *__restrict__ cloud, int P, FohoAccel acc) {
   __shared__ float red[6 * 32];
   const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
@@ -153,81 +142,117 @@ __global__ void __launch_bounds__(ACC_THREADS) k_accel_cloud_bbox(const float *_
     }
     FohoAccelGrid *G = acc.grid + b;
     const float ext = fmaxf(fmaxf(hi[0] - lo[0], hi[1] - lo[1]), fmaxf(hi[2] - lo[2], 1e-20f));
-    const float cell = ext * (1.0f + 1e-5f) / (float)FOHO_ACCEL_G;     // cubic cells
-    G->cell = cell; G->inv_cell = 1.0f / cell;
-    for (int a = 0; a < 3; ++a) {
-      G->origin[a] = lo[a];
-      int dmax = (int)floorf((hi[a] - lo[a]) / cell) + 1;
-      G->dims[a] = dmax < 1 ? 1 : (dmax > FOHO_ACCEL_G ? FOHO_ACCEL_G : dmax);
+    G->quant = 1023.f / ext;
+    for (int a = 0; a < 3; ++a) G->origin[a] = lo[a];
+    G->P = P; G->pad[0] = G->pad[1] = G->pad[2] = 0;
+  }
+}
+
+__global__ void __launch_bounds__(256) k_accel_cloud_keys(const float *__restrict__ cloud, int P, int P2, FohoAccel acc) {
+  const int b = blockIdx.y;
+  const FohoAccelGrid G = acc.grid[b];
+  const float *c = cloud + (size_t)b * P * 3;
+  unsigned long long *keys = acc.keys + (size_t)b * P2;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < P2; i += gridDim.x * blockDim.x) {
+    unsigned long long k = ~0ull;
+    if (i < P) {
+      const unsigned ix = (unsigned)fminf(fmaxf((c[3 * (size_t)i] - G.origin[0]) * G.quant, 0.f), 1023.f);
+      const unsigned iy = (unsigned)fminf(fmaxf((c[3 * (size_t)i + 1] - G.origin[1]) * G.quant, 0.f), 1023.f);
+      const unsigned iz = (unsigned)fminf(fmaxf((c[3 * (size_t)i + 2] - G.origin[2]) * G.quant, 0.f), 1023.f);
+      const unsigned m = (spread3(ix) << 2) | (spread3(iy) << 1) | spread3(iz);
+      k = ((unsigned long long)m << 32) | (unsigned)i;          // unique keys: deterministic order
     }
-    G->P = P; G->pad = 0;
-  }
-  // zero the per-cell counters of this sample
-  int *cnt = acc.cell_fill + (size_t)b * FOHO_ACCEL_CELLS;
-  for (int i = tid; i < FOHO_ACCEL_CELLS; i += blockDim.x) cnt[i] = 0;
-}
-
-__global__ void __launch_bounds__(256) k_accel_cloud_count(const float *__restrict__ cloud, int P, FohoAccel acc) {
-  const int b = blockIdx.y;
-  const FohoAccelGrid G = acc.grid[b];
-  const float *c = cloud + (size_t)b * P * 3;
-  int *cnt = acc.cell_fill + (size_t)b * FOHO_ACCEL_CELLS;
-  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < P; i += gridDim.x * blockDim.x) {
-    const int code = cell_code(cell_coord(c[3 * (size_t)i], G.origin[0], G.inv_cell, G.dims[0]),
-                               cell_coord(c[3 * (size_t)i + 1], G.origin[1], G.inv_cell, G.dims[1]),
-                               cell_coord(c[3 * (size_t)i + 2], G.origin[2], G.inv_cell, G.dims[2]));
-    atomicAdd(cnt + code, 1);
+    keys[i] = k;
   }
 }
 
-// exclusive scan of the 32768 cell counts of one sample: 1024 threads x 32 consecutive cells
-__global__ void __launch_bounds__(ACC_THREADS) k_accel_cloud_scan(FohoAccel acc) {
-  __shared__ int wsum[32];
-  const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-  int *cnt = acc.cell_fill + (size_t)b * FOHO_ACCEL_CELLS;
-  int *start = acc.cell_start + (size_t)b * (FOHO_ACCEL_CELLS + 1);
-  constexpr int PER = FOHO_ACCEL_CELLS / ACC_THREADS;
-  int local[PER], sum = 0;
-#pragma unroll
-  for (int k = 0; k < PER; ++k) { local[k] = cnt[tid * PER + k]; sum += local[k]; }
-  int incl = sum;
-#pragma unroll
-  for (int o = 1; o < 32; o <<= 1) { int v = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += v; }
-  if (lane == 31) wsum[wid] = incl;
+constexpr int SORT_CHUNK = 2048;          // keys per CTA in the shared-memory phases (1024 threads)
+
+__device__ __forceinline__ void sort_cmpx(unsigned long long *sk, int i, int l, bool up) {
+  const unsigned long long a = sk[i], c = sk[l];
+  if ((a > c) == up) { sk[i] = c; sk[l] = a; }
+}
+// kmin == 2: full bitonic sort of each chunk; kmin == kmax > SORT_CHUNK: the j < SORT_CHUNK tail of merge step k
+__global__ void __launch_bounds__(ACC_THREADS) k_sort_local(unsigned long long *__restrict__ keys_all, int P2, int kmin, int kmax) {
+  __shared__ unsigned long long sk[SORT_CHUNK];
+  unsigned long long *keys = keys_all + (size_t)blockIdx.y * P2 + (size_t)blockIdx.x * SORT_CHUNK;
+  const int tid = threadIdx.x, gbase = blockIdx.x * SORT_CHUNK;
+  sk[tid] = keys[tid]; sk[tid + ACC_THREADS] = keys[tid + ACC_THREADS];
   __syncthreads();
-  if (wid == 0) {
-    int v = wsum[lane], inc = v;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) { int u = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += u; }
-    wsum[lane] = inc - v;
+  for (int k = kmin; k <= kmax; k <<= 1) {
+    for (int j = (k < SORT_CHUNK ? k : SORT_CHUNK) >> 1; j > 0; j >>= 1) {
+      const int i = 2 * j * (tid / j) + (tid % j);
+      sort_cmpx(sk, i, i + j, ((gbase + i) & k) == 0);
+      __syncthreads();
+    }
   }
-  __syncthreads();
-  int run = wsum[wid] + incl - sum;
-#pragma unroll
-  for (int k = 0; k < PER; ++k) { start[tid * PER + k] = run; run += local[k]; cnt[tid * PER + k] = 0; }
-  if (tid == ACC_THREADS - 1) start[FOHO_ACCEL_CELLS] = run;
+  keys[tid] = sk[tid]; keys[tid + ACC_THREADS] = sk[tid + ACC_THREADS];
+}
+__global__ void __launch_bounds__(256) k_sort_global(unsigned long long *__restrict__ keys_all, int P2, int j, int k) {
+  unsigned long long *keys = keys_all + (size_t)blockIdx.y * P2;
+  for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < (P2 >> 1); t += gridDim.x * blockDim.x) {
+    const int i = 2 * j * (t / j) + (t % j);
+    sort_cmpx(keys, i, i + j, (i & k) == 0);
+  }
 }
 
-__global__ void __launch_bounds__(256) k_accel_cloud_scatter(const float *__restrict__ cloud, int P, FohoAccel acc) {
+__global__ void __launch_bounds__(256) k_accel_cloud_gather(const float *__restrict__ cloud, int P, int P2, FohoAccel acc) {
   const int b = blockIdx.y;
-  const FohoAccelGrid G = acc.grid[b];
   const float *c = cloud + (size_t)b * P * 3;
-  int *fill = acc.cell_fill + (size_t)b * FOHO_ACCEL_CELLS;
-  const int *start = acc.cell_start + (size_t)b * (FOHO_ACCEL_CELLS + 1);
+  const unsigned long long *keys = acc.keys + (size_t)b * P2;
   float4 *pts = acc.pts + (size_t)b * P;
-  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < P; i += gridDim.x * blockDim.x) {
-    const float x = c[3 * (size_t)i], y = c[3 * (size_t)i + 1], z = c[3 * (size_t)i + 2];
-    const int code = cell_code(cell_coord(x, G.origin[0], G.inv_cell, G.dims[0]), cell_coord(y, G.origin[1], G.inv_cell, G.dims[1]),
-                               cell_coord(z, G.origin[2], G.inv_cell, G.dims[2]));
-    const int slot = start[code] + atomicAdd(fill + code, 1);
-    pts[slot] = make_float4(x, y, z, __int_as_float(i));
+  for (int s = blockIdx.x * blockDim.x + threadIdx.x; s < P; s += gridDim.x * blockDim.x) {
+    const unsigned i = (unsigned)keys[s];
+    pts[s] = make_float4(c[3 * (size_t)i], c[3 * (size_t)i + 1], c[3 * (size_t)i + 2], __int_as_float((int)i));
+  }
+}
+
+// ----------------------------------------------------------------------------- build: cloud boxes
+// AABB of every group of 32 Morton-sorted cloud points, and of every super-group of 32 groups.
+__global__ void __launch_bounds__(256) k_accel_cloud_boxes(int P, FohoAccel acc) {
+  const int b = blockIdx.y, lane = threadIdx.x & 31;
+  const int NG = (P + 31) >> 5;
+  const int g = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (g >= NG) return;
+  const float4 *pts = acc.pts + (size_t)b * P;
+  const int p = g * 32 + lane;
+  const float4 c = pts[p < P ? p : g * 32];
+  const float lx = warp_min(c.x), ly = warp_min(c.y), lz = warp_min(c.z);
+  const float hx = warp_max(c.x), hy = warp_max(c.y), hz = warp_max(c.z);
+  if (lane == 0) {
+    acc.g_lo[(size_t)b * acc.NGcap + g] = make_float4(lx, ly, lz, 0.f);
+    acc.g_hi[(size_t)b * acc.NGcap + g] = make_float4(hx, hy, hz, 0.f);
+  }
+}
+__global__ void __launch_bounds__(256) k_accel_cloud_supers(int P, FohoAccel acc) {
+  const int b = blockIdx.y, lane = threadIdx.x & 31;
+  const int NG = (P + 31) >> 5, NS = (NG + 31) >> 5;
+  const int s = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (s >= NS) return;
+  const int g = s * 32 + lane;
+  const int gg = g < NG ? g : s * 32;
+  const float4 lo = acc.g_lo[(size_t)b * acc.NGcap + gg], hi = acc.g_hi[(size_t)b * acc.NGcap + gg];
+  const float lx = warp_min(lo.x), ly = warp_min(lo.y), lz = warp_min(lo.z);
+  const float hx = warp_max(hi.x), hy = warp_max(hi.y), hz = warp_max(hi.z);
+  if (lane == 0) {
+    acc.s_lo[(size_t)b * acc.NScap + s] = make_float4(lx, ly, lz, 0.f);
+    acc.s_hi[(size_t)b * acc.NScap + s] = make_float4(hx, hy, hz, 0.f);
   }
 }
 
 // ----------------------------------------------------------------------------- cloud -> hand
+// One warp per group of 32 Morton-sorted (= spatially adjacent) cloud points; a dual-tree prune:
+//   1. pull the 32 points back into the hand's rest frame, take their AABB G (warp min/max);
+//   2. lanes evaluate, for the <=128 hand leaves, mindist^2(G, leaf box) and the upper bound
+//      maxdist^2(G, first vertex of the leaf); U = min of the upper bounds bounds every lane's answer;
+//   3. the leaf attaining U is searched first; U is then tightened to the largest per-lane best;
+//   4. the warp walks the surviving leaves (mindist^2 <= U) in lock step; a lane skips a leaf whose
+//      box is farther than its own best; the 8 vertices of a leaf are smem broadcasts.
+// All bounds use the same monotone fp32 expression as the point distance, so pruning is exact in
+// floating point, ties included (ties -> smallest original vertex index).
 constexpr int C2H_THREADS = 256;
-constexpr int C2H_PER_THREAD = 4;
-constexpr int C2H_POINTS = C2H_THREADS * C2H_PER_THREAD;
+constexpr int C2H_GROUPS_PER_WARP = 4;
+constexpr int C2H_GROUPS_PER_CTA = (C2H_THREADS / 32) * C2H_GROUPS_PER_WARP;
 
 __device__ __forceinline__ float box_dist2(float4 lo, float4 hi, float qx, float qy, float qz) {
   const float dx = fmaxf(fmaxf(lo.x - qx, qx - hi.x), 0.f);
@@ -235,21 +260,51 @@ __device__ __forceinline__ float box_dist2(float4 lo, float4 hi, float qx, float
   const float dz = fmaxf(fmaxf(lo.z - qz, qz - hi.z), 0.f);
   return fmaf(dz, dz, fmaf(dy, dy, dx * dx));
 }
+// min squared distance between two boxes
+__device__ __forceinline__ float boxbox_min2(float4 lo, float4 hi, const float (&glo)[3], const float (&ghi)[3]) {
+  const float dx = fmaxf(fmaxf(lo.x - ghi[0], glo[0] - hi.x), 0.f);
+  const float dy = fmaxf(fmaxf(lo.y - ghi[1], glo[1] - hi.y), 0.f);
+  const float dz = fmaxf(fmaxf(lo.z - ghi[2], glo[2] - hi.z), 0.f);
+  return fmaf(dz, dz, fmaf(dy, dy, dx * dx));
+}
+// max squared distance from a point to any point of a box
+__device__ __forceinline__ float box_max2(float4 v, const float (&glo)[3], const float (&ghi)[3]) {
+  const float dx = fmaxf(fabsf(v.x - glo[0]), fabsf(ghi[0] - v.x));
+  const float dy = fmaxf(fabsf(v.y - glo[1]), fabsf(ghi[1] - v.y));
+  const float dz = fmaxf(fabsf(v.z - glo[2]), fabsf(ghi[2] - v.z));
+  return fmaf(dz, dz, fmaf(dy, dy, dx * dx));
+}
+
+struct C2HBest { float d2; int slot; int orig; };
+
+__device__ __forceinline__ void c2h_scan_leaf(const float4 *__restrict__ v, int l, float qx, float qy, float qz, C2HBest &bst) {
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    const float4 p = v[l * 8 + k];
+    const float dx = qx - p.x, dy = qy - p.y, dz = qz - p.z;
+    const float d2 = fmaf(dz, dz, fmaf(dy, dy, dx * dx));
+    const int o = __float_as_int(p.w);
+    if (d2 < bst.d2 || (d2 == bst.d2 && o < bst.orig)) { bst.d2 = d2; bst.slot = l * 8 + k; bst.orig = o; }
+  }
+}
 
 __global__ void __launch_bounds__(C2H_THREADS) k_chamfer_c2h(foho_guidance_desc d, FohoWorkspace ws, FohoAccel acc) {
   __shared__ float4 sv[FOHO_ACCEL_HV];
   __shared__ float4 s_llo[FOHO_ACCEL_LEAVES], s_lhi[FOHO_ACCEL_LEAVES];
-  __shared__ float4 s_slo[FOHO_ACCEL_SUPERS], s_shi[FOHO_ACCEL_SUPERS];
   __shared__ float gacc[FOHO_ACCEL_HV * 3];
   __shared__ float red[32];
-  const int b = blockIdx.y, Vh = d.Vh, P = d.P, tid = threadIdx.x;
-  const int base = blockIdx.x * C2H_POINTS;
-  if (base >= P) return;
+  const int b = blockIdx.y, Vh = d.Vh, P = d.P, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  const int NG = (P + 31) >> 5;
+  const int g0 = blockIdx.x * C2H_GROUPS_PER_CTA;
+  if (g0 >= NG) return;
   const FohoAccelHand *H = acc.hand + b;
   const int nleaf = H->n_leaves, nsup = H->n_supers;
+  const int nleafpad = nsup * 8;
   for (int i = tid; i < nsup * 64; i += blockDim.x) sv[i] = H->v[i];
-  for (int i = tid; i < nsup * 8; i += blockDim.x) { s_llo[i] = H->leaf_lo[i]; s_lhi[i] = H->leaf_hi[i]; }
-  if (tid < FOHO_ACCEL_SUPERS) { s_slo[tid] = H->sup_lo[tid]; s_shi[tid] = H->sup_hi[tid]; }
+  for (int i = tid; i < FOHO_ACCEL_LEAVES; i += blockDim.x) {
+    if (i < nleafpad) { s_llo[i] = H->leaf_lo[i]; s_lhi[i] = H->leaf_hi[i]; }
+    else { s_llo[i] = make_float4(INFINITY, INFINITY, INFINITY, 0.f); s_lhi[i] = make_float4(-INFINITY, -INFINITY, -INFINITY, 0.f); }
+  }
   for (int i = tid; i < Vh * 3; i += blockDim.x) gacc[i] = 0.f;
   __syncthreads();
   const FohoFrame &fr = ws.frames[b];
@@ -267,55 +322,62 @@ __global__ void __launch_bounds__(C2H_THREADS) k_chamfer_c2h(foho_guidance_desc 
   const float *hmc = ws.hmc + (size_t)b * Vh * 3;
   const float coef = 2.f * d.w.w_ch / (float)P;
   float sum = 0.f;
-  int prev_leaf = 0;
 #pragma unroll 1
-  for (int u = 0; u < C2H_PER_THREAD; ++u) {
-    const int i = base + u * C2H_THREADS + tid;
-    if (i >= P) break;
-    const float4 c4 = pts[i];
+  for (int u = 0; u < C2H_GROUPS_PER_WARP; ++u) {
+    const int g = g0 + wid * C2H_GROUPS_PER_WARP + u;
+    if (g >= NG) break;
+    const int pi = g * 32 + lane;
+    const bool valid = pi < P;
+    const float4 c4 = pts[valid ? pi : g * 32];
     const float px = c4.x - cx, py = c4.y - cy, pz = c4.z - cz;          // centred MoGe
     const float rx = px - ox, ry = py - oy, rz = pz - oz;
     const float qx = Rt[0] * rx + Rt[1] * ry + Rt[2] * rz;
     const float qy = Rt[3] * rx + Rt[4] * ry + Rt[5] * rz;
     const float qz = Rt[6] * rx + Rt[7] * ry + Rt[8] * rz;
-    float best = INFINITY;
-    int bj = prev_leaf * 8;
-    // seed the pruning radius with the leaf that held the previous point's neighbour
-    {
-      const float4 *v = sv + prev_leaf * 8;
+    float glo[3] = {warp_min(qx), warp_min(qy), warp_min(qz)};
+    float ghi[3] = {warp_max(qx), warp_max(qy), warp_max(qz)};
+    // bounds of every hand leaf against the group box
+    float lb[4];
+    float ub = INFINITY;
+    int ubl = 0;
 #pragma unroll
-      for (int k = 0; k < 8; ++k) {
-        const float4 p = v[k];
-        const float dx = qx - p.x, dy = qy - p.y, dz = qz - p.z;
-        const float d2 = fmaf(dz, dz, fmaf(dy, dy, dx * dx));
-        if (d2 < best) { best = d2; bj = prev_leaf * 8 + k; }
+    for (int r = 0; r < 4; ++r) {
+      const int l = r * 32 + lane;
+      lb[r] = boxbox_min2(s_llo[l], s_lhi[l], glo, ghi);        // +inf for pad leaves
+      if (l < nleaf) {
+        const float m = box_max2(sv[l * 8], glo, ghi);
+        if (m < ub) { ub = m; ubl = l; }
       }
     }
-    for (int s = 0; s < nsup; ++s) {
-      if (!(box_dist2(s_slo[s], s_shi[s], qx, qy, qz) < best)) continue;
-#pragma unroll 1
-      for (int l = s * 8; l < s * 8 + 8; ++l) {
-        if (l == prev_leaf || !(box_dist2(s_llo[l], s_lhi[l], qx, qy, qz) < best)) continue;
-        const float4 *v = sv + l * 8;
+    // warp arg-min of the upper bound
+    const unsigned ubits = __float_as_uint(ub);
+    const unsigned umin = __reduce_min_sync(0xffffffffu, ubits);
+    const unsigned who = __ballot_sync(0xffffffffu, ubits == umin);
+    const int l0 = __shfl_sync(0xffffffffu, ubl, __ffs(who) - 1);
+    C2HBest bst; bst.d2 = INFINITY; bst.slot = 0; bst.orig = 0x7fffffff;
+    c2h_scan_leaf(sv, l0, qx, qy, qz, bst);
+    float U = warp_max(bst.d2);                                   // every lane's answer is <= its best <= U
 #pragma unroll
-        for (int k = 0; k < 8; ++k) {
-          const float4 p = v[k];
-          const float dx = qx - p.x, dy = qy - p.y, dz = qz - p.z;
-          const float d2 = fmaf(dz, dz, fmaf(dy, dy, dx * dx));
-          if (d2 < best) { best = d2; bj = l * 8 + k; }
-        }
+    for (int r = 0; r < 4; ++r) {
+      unsigned mask = __ballot_sync(0xffffffffu, lb[r] <= U);
+      while (mask) {
+        const int l = r * 32 + __ffs(mask) - 1;
+        mask &= mask - 1;
+        if (l == l0) continue;
+        if (box_dist2(s_llo[l], s_lhi[l], qx, qy, qz) <= bst.d2) c2h_scan_leaf(sv, l, qx, qy, qz, bst);
       }
     }
-    prev_leaf = bj >> 3;
-    // exact squared distance in the (centred) MoGe frame, as the oracle evaluates it
-    const int j = __float_as_int(sv[bj].w);
-    const float hx = hmc[3 * j], hy = hmc[3 * j + 1], hz = hmc[3 * j + 2];
-    const float dx = hx - px, dy = hy - py, dz = hz - pz;
-    sum += fmaf(dz, dz, fmaf(dy, dy, dx * dx));
-    atomicAdd(gacc + 3 * j, coef * dx); atomicAdd(gacc + 3 * j + 1, coef * dy); atomicAdd(gacc + 3 * j + 2, coef * dz);
+    if (valid) {
+      // exact squared distance in the (centred) MoGe frame, as the oracle evaluates it
+      const int j = bst.orig;
+      const float hx = hmc[3 * j], hy = hmc[3 * j + 1], hz = hmc[3 * j + 2];
+      const float dx = hx - px, dy = hy - py, dz = hz - pz;
+      sum += fmaf(dz, dz, fmaf(dy, dy, dx * dx));
+      atomicAdd(gacc + 3 * j, coef * dx); atomicAdd(gacc + 3 * j + 1, coef * dy); atomicAdd(gacc + 3 * j + 2, coef * dz);
+    }
   }
   sum = warp_sum(sum);
-  if ((tid & 31) == 0) red[tid >> 5] = sum;
+  if (lane == 0) red[wid] = sum;
   __syncthreads();
   if (tid == 0) {
     float t = 0.f;
@@ -327,72 +389,95 @@ __global__ void __launch_bounds__(C2H_THREADS) k_chamfer_c2h(foho_guidance_desc 
     const float g = gacc[i];
     if (g != 0.f) atomicAdd(Ghm + i, g);
   }
-  (void)nleaf;
 }
 
 // ----------------------------------------------------------------------------- hand -> cloud
+// One warp per hand vertex over the static two-level box hierarchy of the cloud (groups of 32
+// Morton-sorted points, super-groups of 32 groups): a greedy descent seeds the radius, then every
+// super-group / group whose box is within the current best is scanned, 32 boxes or points per step.
 constexpr int H2C_THREADS = 256;
-constexpr int H2C_MAX_RING = 6;
+
+struct H2CBest { unsigned d2; unsigned idx; };
+// fold the 32 lane candidates (d2 bits, original index) into the warp-uniform best (ties -> smallest index)
+__device__ __forceinline__ void h2c_fold(H2CBest &bst, unsigned d2bits, unsigned idx) {
+  const unsigned wm = __reduce_min_sync(0xffffffffu, d2bits);
+  if (wm > bst.d2) return;                                        // warp-uniform
+  const unsigned im = __reduce_min_sync(0xffffffffu, d2bits == wm ? idx : 0xffffffffu);
+  if (wm < bst.d2 || im < bst.idx) { bst.d2 = wm; bst.idx = im; }
+}
 
 __global__ void __launch_bounds__(H2C_THREADS) k_chamfer_h2c(foho_guidance_desc d, FohoWorkspace ws, FohoAccel acc) {
   const int b = blockIdx.y, Vh = d.Vh, P = d.P;
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   const int i = blockIdx.x * (H2C_THREADS / 32) + wid;
   if (i >= Vh) return;
-  const FohoAccelGrid G = acc.grid[b];
+  const int NG = (P + 31) >> 5, NS = (NG + 31) >> 5;
   const FohoFrame &fr = ws.frames[b];
   const float *hmc = ws.hmc + (size_t)b * Vh * 3;
-  // absolute MoGe position of this hand vertex (the grid lives in absolute coordinates)
+  // absolute MoGe position of this hand vertex (the cloud boxes live in absolute coordinates)
   const float hx = hmc[3 * i] + fr.co[0], hy = hmc[3 * i + 1] + fr.co[1], hz = hmc[3 * i + 2] + fr.co[2];
-  const int c0x = cell_coord(hx, G.origin[0], G.inv_cell, G.dims[0]);
-  const int c0y = cell_coord(hy, G.origin[1], G.inv_cell, G.dims[1]);
-  const int c0z = cell_coord(hz, G.origin[2], G.inv_cell, G.dims[2]);
-  const int *start = acc.cell_start + (size_t)b * (FOHO_ACCEL_CELLS + 1);
   const float4 *pts = acc.pts + (size_t)b * P;
-  float best = INFINITY;
-  int bidx = -1;
-  bool done = false;
-  for (int r = 0; r <= H2C_MAX_RING && !done; ++r) {
-    const int w = 2 * r + 1, n = w * w * w;
-    for (int t = lane; t < n; t += 32) {
-      const int dz = t % w - r, dy = (t / w) % w - r, dx = t / (w * w) - r;
-      if (max(abs(dx), max(abs(dy), abs(dz))) != r) continue;                 // shell only
-      const int x = c0x + dx, y = c0y + dy, z = c0z + dz;
-      if (x < 0 || y < 0 || z < 0 || x >= G.dims[0] || y >= G.dims[1] || z >= G.dims[2]) continue;
-      const int code = cell_code(x, y, z);
-      const int p0 = start[code], p1 = start[code + 1];
-      for (int p = p0; p < p1; ++p) {
-        const float4 c = pts[p];
-        const float ex = hx - c.x, ey = hy - c.y, ez = hz - c.z;
-        const float d2 = fmaf(ez, ez, fmaf(ey, ey, ex * ex));
-        if (d2 < best) { best = d2; bidx = __float_as_int(c.w); }
-      }
-    }
-    // everything outside the cube of half-width r cells around the (clamped) query is at least
-    // r cells away from it (projection onto the grid bbox is non-expansive)
-    const float wb = warp_min(best);
-    const float lim = (float)r * G.cell;
-    done = wb <= lim * lim * 0.9999f;
-    if (r + 1 > max(G.dims[0], max(G.dims[1], G.dims[2]))) done = wb < INFINITY;   // whole grid covered
-  }
-  if (!done) {
-    // far from the cloud: exhaustive scan by the warp (bounded, exact)
-    for (int p = lane; p < P; p += 32) {
+  const float4 *glo = acc.g_lo + (size_t)b * acc.NGcap, *ghi = acc.g_hi + (size_t)b * acc.NGcap;
+  const float4 *slo = acc.s_lo + (size_t)b * acc.NScap, *shi = acc.s_hi + (size_t)b * acc.NScap;
+  const unsigned INF_BITS = 0x7f800000u;
+  H2CBest bst; bst.d2 = 0xffffffffu; bst.idx = 0xffffffffu;
+
+  auto scan_group = [&](int g) {
+    const int p = g * 32 + lane;
+    unsigned db = 0xffffffffu, ix = 0xffffffffu;
+    if (p < P) {
       const float4 c = pts[p];
       const float ex = hx - c.x, ey = hy - c.y, ez = hz - c.z;
-      const float d2 = fmaf(ez, ez, fmaf(ey, ey, ex * ex));
-      if (d2 < best) { best = d2; bidx = __float_as_int(c.w); }
+      db = __float_as_uint(fmaf(ez, ez, fmaf(ey, ey, ex * ex)));
+      ix = (unsigned)__float_as_int(c.w);
+    }
+    h2c_fold(bst, db, ix);
+  };
+  auto scan_super = [&](int s, int skip_g) {
+    const int g = s * 32 + lane;
+    unsigned lb = 0xffffffffu;
+    if (g < NG && g != skip_g) lb = __float_as_uint(box_dist2(glo[g], ghi[g], hx, hy, hz));
+    unsigned mask = __ballot_sync(0xffffffffu, lb <= bst.d2 && lb <= INF_BITS);
+    while (mask) {
+      const int gl = __ffs(mask) - 1;
+      scan_group(s * 32 + gl);
+      mask &= mask - 1;
+      mask &= __ballot_sync(0xffffffffu, lb <= bst.d2);
+    }
+  };
+
+  // greedy seed: nearest super-group -> its nearest group -> scan
+  int s0 = 0, gseed = -1;
+  {
+    unsigned bl = 0xffffffffu; int bs = 0;
+    for (int s = lane; s < NS; s += 32) {
+      const unsigned v = __float_as_uint(box_dist2(slo[s], shi[s], hx, hy, hz));
+      if (v < bl) { bl = v; bs = s; }
+    }
+    const unsigned m = __reduce_min_sync(0xffffffffu, bl);
+    s0 = __shfl_sync(0xffffffffu, bs, __ffs(__ballot_sync(0xffffffffu, bl == m)) - 1);
+    const int g = s0 * 32 + lane;
+    const unsigned lb = g < NG ? __float_as_uint(box_dist2(glo[g], ghi[g], hx, hy, hz)) : 0xffffffffu;
+    const unsigned m2 = __reduce_min_sync(0xffffffffu, lb);
+    gseed = s0 * 32 + __ffs(__ballot_sync(0xffffffffu, lb == m2)) - 1;
+    scan_group(gseed);
+    scan_super(s0, gseed);
+  }
+  // exact pass over the remaining super-groups
+  for (int sb = 0; sb < NS; sb += 32) {
+    const int s = sb + lane;
+    unsigned lb = 0xffffffffu;
+    if (s < NS && s != s0) lb = __float_as_uint(box_dist2(slo[s], shi[s], hx, hy, hz));
+    unsigned mask = __ballot_sync(0xffffffffu, lb <= bst.d2 && lb <= INF_BITS);
+    while (mask) {
+      const int sl = __ffs(mask) - 1;
+      scan_super(sb + sl, -1);
+      mask &= mask - 1;
+      mask &= __ballot_sync(0xffffffffu, lb <= bst.d2);
     }
   }
-  // warp arg-min; ties -> smallest original index
-  unsigned long long key = bidx >= 0 ? (((unsigned long long)__float_as_uint(best) << 32) | (unsigned int)bidx) : ~0ull;
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) {
-    unsigned int lo = __shfl_xor_sync(0xffffffffu, (unsigned int)key, o), hi = __shfl_xor_sync(0xffffffffu, (unsigned int)(key >> 32), o);
-    unsigned long long other = ((unsigned long long)hi << 32) | lo;
-    key = other < key ? other : key;
-  }
-  if (lane == 0) ws.knn[(size_t)b * Vh + i] = key;
+  if (lane == 0)
+    ws.knn[(size_t)b * Vh + i] = bst.idx != 0xffffffffu ? (((unsigned long long)bst.d2 << 32) | bst.idx) : ~0ull;
 }
 
 }  // namespace
@@ -403,9 +488,16 @@ static inline void foho_accel_layout(FohoAccel &a, char *base, int B, int P) {
   auto take = [&](size_t bytes) { char *p = base ? base + off : nullptr; off += foho_align_up(bytes, 256); return p; };
   a.hand = (FohoAccelHand *)take(sizeof(FohoAccelHand) * (size_t)B);
   a.grid = (FohoAccelGrid *)take(sizeof(FohoAccelGrid) * (size_t)B);
-  a.cell_start = (int *)take(sizeof(int) * (size_t)B * (FOHO_ACCEL_CELLS + 1));
-  a.cell_fill = (int *)take(sizeof(int) * (size_t)B * FOHO_ACCEL_CELLS);
+  a.P2 = SORT_CHUNK;
+  while (a.P2 < P) a.P2 <<= 1;
+  a.keys = (unsigned long long *)take(sizeof(unsigned long long) * (size_t)B * a.P2);
   a.pts = (float4 *)take(sizeof(float4) * (size_t)B * (P > 0 ? P : 1));
+  a.NGcap = ((P > 0 ? P : 1) + 31) / 32;
+  a.NScap = (a.NGcap + 31) / 32;
+  a.g_lo = (float4 *)take(sizeof(float4) * (size_t)B * a.NGcap);
+  a.g_hi = (float4 *)take(sizeof(float4) * (size_t)B * a.NGcap);
+  a.s_lo = (float4 *)take(sizeof(float4) * (size_t)B * a.NScap);
+  a.s_hi = (float4 *)take(sizeof(float4) * (size_t)B * a.NScap);
   a.total = off;
 }
 
@@ -430,13 +522,26 @@ extern "C" int foho_guidance_prepare_statics(const foho_guidance_desc *dp, void 
   FOHO_LAUNCH_CHECK();
   k_accel_cloud_bbox<<<d.B, ACC_THREADS, 0, st>>>(d.cloud, d.P, a);
   FOHO_LAUNCH_CHECK();
-  int gx = (d.P + 255) / 256;
-  if (gx > 256) gx = 256;
-  k_accel_cloud_count<<<dim3(gx, d.B), 256, 0, st>>>(d.cloud, d.P, a);
+  int gx = (a.P2 + 255) / 256;
+  if (gx > 512) gx = 512;
+  k_accel_cloud_keys<<<dim3(gx, d.B), 256, 0, st>>>(d.cloud, d.P, a.P2, a);
   FOHO_LAUNCH_CHECK();
-  k_accel_cloud_scan<<<d.B, ACC_THREADS, 0, st>>>(a);
+  const int nchunk = a.P2 / SORT_CHUNK;
+  k_sort_local<<<dim3(nchunk, d.B), ACC_THREADS, 0, st>>>(a.keys, a.P2, 2, SORT_CHUNK);
   FOHO_LAUNCH_CHECK();
-  k_accel_cloud_scatter<<<dim3(gx, d.B), 256, 0, st>>>(d.cloud, d.P, a);
+  for (int k = SORT_CHUNK * 2; k <= a.P2; k <<= 1) {
+    for (int j = k >> 1; j >= SORT_CHUNK; j >>= 1) {
+      k_sort_global<<<dim3(gx, d.B), 256, 0, st>>>(a.keys, a.P2, j, k);
+      FOHO_LAUNCH_CHECK();
+    }
+    k_sort_local<<<dim3(nchunk, d.B), ACC_THREADS, 0, st>>>(a.keys, a.P2, k, k);
+    FOHO_LAUNCH_CHECK();
+  }
+  k_accel_cloud_gather<<<dim3(gx, d.B), 256, 0, st>>>(d.cloud, d.P, a.P2, a);
+  FOHO_LAUNCH_CHECK();
+  k_accel_cloud_boxes<<<dim3((a.NGcap + 7) / 8, d.B), 256, 0, st>>>(d.P, a);
+  FOHO_LAUNCH_CHECK();
+  k_accel_cloud_supers<<<dim3((a.NScap + 7) / 8, d.B), 256, 0, st>>>(d.P, a);
   FOHO_LAUNCH_CHECK();
   return FOHO_OK;
 }
@@ -448,7 +553,8 @@ int foho_launch_chamfer_accel(const foho_guidance_desc *dp, const FohoWorkspace 
   if (a.total > d.accel_bytes) return FOHO_E_WORKSPACE;
   k_chamfer_h2c<<<dim3((d.Vh + H2C_THREADS / 32 - 1) / (H2C_THREADS / 32), d.B), H2C_THREADS, 0, st>>>(d, ws, a);
   FOHO_LAUNCH_CHECK();
-  k_chamfer_c2h<<<dim3((d.P + C2H_POINTS - 1) / C2H_POINTS, d.B), C2H_THREADS, 0, st>>>(d, ws, a);
+  const int NG = (d.P + 31) / 32;
+  k_chamfer_c2h<<<dim3((NG + C2H_GROUPS_PER_CTA - 1) / C2H_GROUPS_PER_CTA, d.B), C2H_THREADS, 0, st>>>(d, ws, a);
   FOHO_LAUNCH_CHECK();
   return FOHO_OK;
 }
