@@ -50,6 +50,7 @@ enum { CNT_NCAND = 0, CNT_COUNT = 1, CNT_FLAGS = 2, CNT_NUM = 4 };
 
 #define FOHO_STREAM_PARTIALS 8      // m0, m1x, m1y, m1z, m2, count_obj, pad, pad
 #define FOHO_MAX_STREAM_CTAS 2048   // per sample
+#define FOHO_FIN_NRED 32            // per-sample sums produced by k_finalize_verts
 
 // Per-sample state of the explicit object mesh (REF a5/a6 on the FlexiCubes vertices).
 struct FohoObjInfo {
@@ -75,6 +76,10 @@ struct FohoWorkspace {
   float *g_ot;                // [Vo,3] dE/d(ot)
   unsigned long long *knn_obj;// [B,Vh] packed (d2 bits << 32 | packed object vertex index)
   FohoObjInfo *oinfo;         // [B]
+  float *fin_acc;             // [B,FOHO_FIN_NRED] per-sample sums of k_finalize_verts
+  float *cand_val;            // [B,cap] dE/dS contribution of each candidate voxel (applied by k_assemble)
+  int *tri_idx;               // [B,Vh,8] voxel index of the trilinear corners of each vertex sample
+  float *tri_val;             // [B,Vh,8] dE/dS contribution at those corners (0 = none)
   int cap;
   int W;                      // words per column
   size_t total;
@@ -106,6 +111,8 @@ struct FohoAccel {
   float4 *g_lo, *g_hi;        // [B,NGcap] AABB of each group of 32 sorted points (absolute MoGe)
   float4 *s_lo, *s_hi;        // [B,NScap] AABB of each super-group of 32 groups
   int NGcap, NScap;
+  int *seed_c2h;              // [B,P]  warm start: hand slot found for each sorted cloud point last time
+  int *seed_h2c;              // [B,FOHO_ACCEL_HV] warm start: sorted cloud position found for each hand vertex
   size_t total;
 };
 
@@ -137,11 +144,45 @@ static inline void foho_ws_layout(FohoWorkspace &w, char *base, int B, int D, in
   w.g_ot = (float *)take(sizeof(float) * 3 * vo);
   w.knn_obj = (unsigned long long *)take(sizeof(unsigned long long) * (size_t)B * Vh);
   w.oinfo = (FohoObjInfo *)take(sizeof(FohoObjInfo) * (size_t)B);
+  w.fin_acc = (float *)take(sizeof(float) * FOHO_FIN_NRED * (size_t)B);
+  w.cand_val = (float *)take(sizeof(float) * (size_t)B * w.cap);
+  w.tri_idx = (int *)take(sizeof(int) * 8 * (size_t)B * Vh);
+  w.tri_val = (float *)take(sizeof(float) * 8 * (size_t)B * Vh);
   w.total = off;
 }
 
 // ---- device reductions -------------------------------------------------------------
 #if defined(__CUDACC__)
+// Object-side part of the per-sample frame: everything that depends only on theta_o, T_h2m, c_o and
+// the lattice (a5/a6 of SURVEY.md section 8a; pipelines.py:108-118,242-250).  Called by k_prep and,
+// so that the dense stream does not have to wait for k_prep, by thread 0 of every stream CTA.
+__device__ __forceinline__ void foho_object_frame(const float *__restrict__ th, const float *__restrict__ T,
+                                                  const float *__restrict__ co, float bound, int D, FohoFrame &fr) {
+  for (int a = 0; a < 3; ++a) fr.co[a] = co[a];
+  fr.so = th[8]; fr.to[0] = th[9]; fr.to[1] = th[10]; fr.to[2] = th[11];
+  quat_to_mat(th + 12, fr.Ro);
+  for (int r = 0; r < 3; ++r)
+    for (int c = 0; c < 3; ++c) fr.Ah[3 * r + c] = T[4 * r + c];
+  fr.step = 2.0f * bound / (float)(D - 1);
+  fr.s_h2m = sqrtf(fr.Ah[0] * fr.Ah[0] + fr.Ah[3] * fr.Ah[3] + fr.Ah[6] * fr.Ah[6]);
+  foho_f3 nb = f3(-bound, -bound, -bound);
+  foho_f3 u0 = mat3_mul(fr.Ah, nb);
+  fr.u0[0] = u0.x + (T[3] - co[0]); fr.u0[1] = u0.y + (T[7] - co[1]); fr.u0[2] = u0.z + (T[11] - co[2]);
+  float Ahs[9], RA[9];
+  for (int k = 0; k < 9; ++k) Ahs[k] = fr.Ah[k] * fr.step;
+  mat3_matmul(fr.Ro, Ahs, RA);
+  for (int k = 0; k < 9; ++k) fr.A[k] = fr.so * RA[k];
+  foho_f3 ru = mat3_mul(fr.Ro, f3(fr.u0[0], fr.u0[1], fr.u0[2]));
+  fr.bc[0] = fr.so * ru.x + fr.to[0]; fr.bc[1] = fr.so * ru.y + fr.to[1]; fr.bc[2] = fr.so * ru.z + fr.to[2];
+  mat3_inverse(fr.A, fr.Ainv);
+  mat3_inverse(Ahs, fr.Ahs_inv);
+  fr.kappa = fr.so * fr.s_h2m * fr.step;
+  foho_f3 babs = f3(fr.bc[0] + co[0], fr.bc[1] + co[1], fr.bc[2] + co[2]);
+  foho_f3 e = mat3_tmul(fr.A, babs);
+  fr.e[0] = e.x; fr.e[1] = e.y; fr.e[2] = e.z;
+  fr.f = dot3(babs, babs);
+}
+
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
@@ -181,7 +222,8 @@ __device__ __forceinline__ void block_sum(float (&v)[N], float *smem) {
 #endif
 
 // kernels implemented in the other translation units
-int foho_launch_stream(const foho_guidance_desc *d, const FohoWorkspace &ws, int *grid_x_out, cudaStream_t st);
+// shared_sm: the sparse kernels run beside the stream (it then leaves them shared memory)
+int foho_launch_stream(const foho_guidance_desc *d, const FohoWorkspace &ws, int *grid_x_out, bool shared_sm, cudaStream_t st);
 // explicit object-mesh terms (guidance_objmesh.cu): `pre` runs before k_finalize (it adds the contact
 // gradient to G_hm), `post` after it (it adds to grad_theta[8..15] and the terms).
 int foho_launch_objmesh_pre(const foho_guidance_desc *d, const FohoWorkspace &ws, cudaStream_t st);

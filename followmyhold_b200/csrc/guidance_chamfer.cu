@@ -275,16 +275,23 @@ __device__ __forceinline__ float box_max2(float4 v, const float (&glo)[3], const
   return fmaf(dz, dz, fmaf(dy, dy, dx * dx));
 }
 
-struct C2HBest { float d2; int slot; int orig; };
+struct C2HBest { float d2; int slot; };
 
+// 8 vertices of one leaf: all distances, a min tree, and (rarely) the arg-min
 __device__ __forceinline__ void c2h_scan_leaf(const float4 *__restrict__ v, int l, float qx, float qy, float qz, C2HBest &bst) {
+  float dd[8];
 #pragma unroll
   for (int k = 0; k < 8; ++k) {
     const float4 p = v[l * 8 + k];
     const float dx = qx - p.x, dy = qy - p.y, dz = qz - p.z;
-    const float d2 = fmaf(dz, dz, fmaf(dy, dy, dx * dx));
-    const int o = __float_as_int(p.w);
-    if (d2 < bst.d2 || (d2 == bst.d2 && o < bst.orig)) { bst.d2 = d2; bst.slot = l * 8 + k; bst.orig = o; }
+    dd[k] = fmaf(dz, dz, fmaf(dy, dy, dx * dx));
+  }
+  const float m = fminf(fminf(fminf(dd[0], dd[1]), fminf(dd[2], dd[3])), fminf(fminf(dd[4], dd[5]), fminf(dd[6], dd[7])));
+  if (m < bst.d2) {
+    int k = 7;
+#pragma unroll
+    for (int t = 6; t >= 0; --t) k = dd[t] == m ? t : k;
+    bst.d2 = m; bst.slot = l * 8 + k;
   }
 }
 
@@ -336,27 +343,40 @@ __global__ void __launch_bounds__(C2H_THREADS) k_chamfer_c2h(foho_guidance_desc 
     const float qz = Rt[6] * rx + Rt[7] * ry + Rt[8] * rz;
     float glo[3] = {warp_min(qx), warp_min(qy), warp_min(qz)};
     float ghi[3] = {warp_max(qx), warp_max(qy), warp_max(qz)};
-    // bounds of every hand leaf against the group box
+    // warm start: the slot found by the previous evaluation (-1 right after prepare_statics).  It only
+    // tightens the pruning radius -- the search below is exact whatever the seed is.
+    int *seedp = acc.seed_c2h + (size_t)b * P + (valid ? pi : g * 32);
+    const int seed = *seedp;
+    const bool seeded = __all_sync(0xffffffffu, seed >= 0);
+    C2HBest bst; bst.d2 = INFINITY; bst.slot = 0;
     float lb[4];
-    float ub = INFINITY;
-    int ubl = 0;
+    int l0 = -1;
+    if (seeded) {
+      const float4 p = sv[seed];
+      const float dx = qx - p.x, dy = qy - p.y, dz = qz - p.z;
+      bst.d2 = fmaf(dz, dz, fmaf(dy, dy, dx * dx)); bst.slot = seed;
 #pragma unroll
-    for (int r = 0; r < 4; ++r) {
-      const int l = r * 32 + lane;
-      lb[r] = boxbox_min2(s_llo[l], s_lhi[l], glo, ghi);        // +inf for pad leaves
-      if (l < nleaf) {
-        const float m = box_max2(sv[l * 8], glo, ghi);
-        if (m < ub) { ub = m; ubl = l; }
+      for (int r = 0; r < 4; ++r) lb[r] = boxbox_min2(s_llo[r * 32 + lane], s_lhi[r * 32 + lane], glo, ghi);
+    } else {
+      // bounds of every hand leaf against the group box; the leaf with the smallest upper bound first
+      float ub = INFINITY;
+      int ubl = 0;
+#pragma unroll
+      for (int r = 0; r < 4; ++r) {
+        const int l = r * 32 + lane;
+        lb[r] = boxbox_min2(s_llo[l], s_lhi[l], glo, ghi);        // +inf for pad leaves
+        if (l < nleaf) {
+          const float m = box_max2(sv[l * 8], glo, ghi);
+          if (m < ub) { ub = m; ubl = l; }
+        }
       }
+      const unsigned ubits = __float_as_uint(ub);
+      const unsigned umin = __reduce_min_sync(0xffffffffu, ubits);
+      const unsigned who = __ballot_sync(0xffffffffu, ubits == umin);
+      l0 = __shfl_sync(0xffffffffu, ubl, __ffs(who) - 1);
+      c2h_scan_leaf(sv, l0, qx, qy, qz, bst);
     }
-    // warp arg-min of the upper bound
-    const unsigned ubits = __float_as_uint(ub);
-    const unsigned umin = __reduce_min_sync(0xffffffffu, ubits);
-    const unsigned who = __ballot_sync(0xffffffffu, ubits == umin);
-    const int l0 = __shfl_sync(0xffffffffu, ubl, __ffs(who) - 1);
-    C2HBest bst; bst.d2 = INFINITY; bst.slot = 0; bst.orig = 0x7fffffff;
-    c2h_scan_leaf(sv, l0, qx, qy, qz, bst);
-    float U = warp_max(bst.d2);                                   // every lane's answer is <= its best <= U
+    const float U = warp_max(bst.d2);                             // every lane's answer is <= its best <= U
 #pragma unroll
     for (int r = 0; r < 4; ++r) {
       unsigned mask = __ballot_sync(0xffffffffu, lb[r] <= U);
@@ -364,12 +384,13 @@ __global__ void __launch_bounds__(C2H_THREADS) k_chamfer_c2h(foho_guidance_desc 
         const int l = r * 32 + __ffs(mask) - 1;
         mask &= mask - 1;
         if (l == l0) continue;
-        if (box_dist2(s_llo[l], s_lhi[l], qx, qy, qz) <= bst.d2) c2h_scan_leaf(sv, l, qx, qy, qz, bst);
+        if (box_dist2(s_llo[l], s_lhi[l], qx, qy, qz) < bst.d2) c2h_scan_leaf(sv, l, qx, qy, qz, bst);
       }
     }
+    if (valid && bst.slot != seed) *seedp = bst.slot;
     if (valid) {
       // exact squared distance in the (centred) MoGe frame, as the oracle evaluates it
-      const int j = bst.orig;
+      const int j = __float_as_int(sv[bst.slot].w);
       const float hx = hmc[3 * j], hy = hmc[3 * j + 1], hz = hmc[3 * j + 2];
       const float dx = hx - px, dy = hy - py, dz = hz - pz;
       sum += fmaf(dz, dz, fmaf(dy, dy, dx * dx));
@@ -397,13 +418,17 @@ __global__ void __launch_bounds__(C2H_THREADS) k_chamfer_c2h(foho_guidance_desc 
 // super-group / group whose box is within the current best is scanned, 32 boxes or points per step.
 constexpr int H2C_THREADS = 256;
 
-struct H2CBest { unsigned d2; unsigned idx; };
+struct H2CBest { unsigned d2; unsigned idx; int pos; };
 // fold the 32 lane candidates (d2 bits, original index) into the warp-uniform best (ties -> smallest index)
-__device__ __forceinline__ void h2c_fold(H2CBest &bst, unsigned d2bits, unsigned idx) {
+__device__ __forceinline__ void h2c_fold(H2CBest &bst, unsigned d2bits, unsigned idx, int pos) {
   const unsigned wm = __reduce_min_sync(0xffffffffu, d2bits);
   if (wm > bst.d2) return;                                        // warp-uniform
   const unsigned im = __reduce_min_sync(0xffffffffu, d2bits == wm ? idx : 0xffffffffu);
-  if (wm < bst.d2 || im < bst.idx) { bst.d2 = wm; bst.idx = im; }
+  if (wm < bst.d2 || im < bst.idx) {
+    bst.d2 = wm; bst.idx = im;
+    const unsigned who = __ballot_sync(0xffffffffu, d2bits == wm && idx == im);
+    bst.pos = __shfl_sync(0xffffffffu, pos, __ffs(who) - 1);
+  }
 }
 
 __global__ void __launch_bounds__(H2C_THREADS) k_chamfer_h2c(foho_guidance_desc d, FohoWorkspace ws, FohoAccel acc) {
@@ -420,7 +445,7 @@ __global__ void __launch_bounds__(H2C_THREADS) k_chamfer_h2c(foho_guidance_desc 
   const float4 *glo = acc.g_lo + (size_t)b * acc.NGcap, *ghi = acc.g_hi + (size_t)b * acc.NGcap;
   const float4 *slo = acc.s_lo + (size_t)b * acc.NScap, *shi = acc.s_hi + (size_t)b * acc.NScap;
   const unsigned INF_BITS = 0x7f800000u;
-  H2CBest bst; bst.d2 = 0xffffffffu; bst.idx = 0xffffffffu;
+  H2CBest bst; bst.d2 = 0xffffffffu; bst.idx = 0xffffffffu; bst.pos = -1;
 
   auto scan_group = [&](int g) {
     const int p = g * 32 + lane;
@@ -431,7 +456,7 @@ __global__ void __launch_bounds__(H2C_THREADS) k_chamfer_h2c(foho_guidance_desc 
       db = __float_as_uint(fmaf(ez, ez, fmaf(ey, ey, ex * ex)));
       ix = (unsigned)__float_as_int(c.w);
     }
-    h2c_fold(bst, db, ix);
+    h2c_fold(bst, db, ix, p);
   };
   auto scan_super = [&](int s, int skip_g) {
     const int g = s * 32 + lane;
@@ -446,9 +471,14 @@ __global__ void __launch_bounds__(H2C_THREADS) k_chamfer_h2c(foho_guidance_desc 
     }
   };
 
-  // greedy seed: nearest super-group -> its nearest group -> scan
-  int s0 = 0, gseed = -1;
-  {
+  // warm start: the sorted position found by the previous evaluation (-1 right after prepare_statics);
+  // otherwise a greedy descent: nearest super-group -> its nearest group -> scan
+  int s0 = -1, gseed = -1;
+  int *seedp = acc.seed_h2c + (size_t)b * Vh + i;
+  const int seed = *seedp;
+  if (seed >= 0 && seed < P) {
+    scan_group(seed >> 5);
+  } else {
     unsigned bl = 0xffffffffu; int bs = 0;
     for (int s = lane; s < NS; s += 32) {
       const unsigned v = __float_as_uint(box_dist2(slo[s], shi[s], hx, hy, hz));
@@ -476,8 +506,10 @@ __global__ void __launch_bounds__(H2C_THREADS) k_chamfer_h2c(foho_guidance_desc 
       mask &= __ballot_sync(0xffffffffu, lb <= bst.d2);
     }
   }
-  if (lane == 0)
+  if (lane == 0) {
     ws.knn[(size_t)b * Vh + i] = bst.idx != 0xffffffffu ? (((unsigned long long)bst.d2 << 32) | bst.idx) : ~0ull;
+    if (bst.pos != seed) *seedp = bst.pos;
+  }
 }
 
 }  // namespace
@@ -498,6 +530,8 @@ static inline void foho_accel_layout(FohoAccel &a, char *base, int B, int P) {
   a.g_hi = (float4 *)take(sizeof(float4) * (size_t)B * a.NGcap);
   a.s_lo = (float4 *)take(sizeof(float4) * (size_t)B * a.NScap);
   a.s_hi = (float4 *)take(sizeof(float4) * (size_t)B * a.NScap);
+  a.seed_c2h = (int *)take(sizeof(int) * (size_t)B * (P > 0 ? P : 1));
+  a.seed_h2c = (int *)take(sizeof(int) * (size_t)B * FOHO_ACCEL_HV);
   a.total = off;
 }
 
@@ -543,6 +577,9 @@ extern "C" int foho_guidance_prepare_statics(const foho_guidance_desc *dp, void 
   FOHO_LAUNCH_CHECK();
   k_accel_cloud_supers<<<dim3((a.NScap + 7) / 8, d.B), 256, 0, st>>>(d.P, a);
   FOHO_LAUNCH_CHECK();
+  // no warm-start hints yet (0xff.. = -1)
+  FOHO_CUDA_TRY(cudaMemsetAsync(a.seed_c2h, 0xff, sizeof(int) * (size_t)d.B * d.P, st));
+  FOHO_CUDA_TRY(cudaMemsetAsync(a.seed_h2c, 0xff, sizeof(int) * (size_t)d.B * FOHO_ACCEL_HV, st));
   return FOHO_OK;
 }
 

@@ -12,6 +12,7 @@
 // :121-135 (a11), :231-239 (a9), :242-250 (a5), :1480-1600 (inner iteration);
 // third_party/utilz/kaolin_sdf_ops.py:88-109 (a8).  Term definitions: DESIGN.md.
 #include "foho_common.cuh"
+#include <mutex>
 
 namespace {
 
@@ -48,33 +49,11 @@ __global__ void __launch_bounds__(256) k_prep(foho_guidance_desc d, FohoWorkspac
       float lo = red[a * 32], hi = red[(3 + a) * 32];
       for (int w = 1; w < nw; ++w) { lo = fminf(lo, red[a * 32 + w]); hi = fmaxf(hi, red[(3 + a) * 32 + w]); }
       fr.ch[a] = (lo + hi) / 2.0f;
-      fr.co[a] = co[a];
       fr.chc[a] = fr.ch[a] - co[a];
     }
     fr.sh = th[0]; fr.th[0] = th[1]; fr.th[1] = th[2]; fr.th[2] = th[3];
     quat_to_mat(th + 4, fr.Rh);
-    fr.so = th[8]; fr.to[0] = th[9]; fr.to[1] = th[10]; fr.to[2] = th[11];
-    quat_to_mat(th + 12, fr.Ro);
-    for (int r = 0; r < 3; ++r)
-      for (int c = 0; c < 3; ++c) fr.Ah[3 * r + c] = T[4 * r + c];
-    fr.step = 2.0f * d.bound / (float)(D - 1);
-    fr.s_h2m = sqrtf(fr.Ah[0] * fr.Ah[0] + fr.Ah[3] * fr.Ah[3] + fr.Ah[6] * fr.Ah[6]);
-    foho_f3 nb = f3(-d.bound, -d.bound, -d.bound);
-    foho_f3 u0 = mat3_mul(fr.Ah, nb);
-    fr.u0[0] = u0.x + (T[3] - co[0]); fr.u0[1] = u0.y + (T[7] - co[1]); fr.u0[2] = u0.z + (T[11] - co[2]);
-    float Ahs[9], RA[9];
-    for (int k = 0; k < 9; ++k) Ahs[k] = fr.Ah[k] * fr.step;
-    mat3_matmul(fr.Ro, Ahs, RA);
-    for (int k = 0; k < 9; ++k) fr.A[k] = fr.so * RA[k];
-    foho_f3 ru = mat3_mul(fr.Ro, f3(fr.u0[0], fr.u0[1], fr.u0[2]));
-    fr.bc[0] = fr.so * ru.x + fr.to[0]; fr.bc[1] = fr.so * ru.y + fr.to[1]; fr.bc[2] = fr.so * ru.z + fr.to[2];
-    mat3_inverse(fr.A, fr.Ainv);
-    mat3_inverse(Ahs, fr.Ahs_inv);
-    fr.kappa = fr.so * fr.s_h2m * fr.step;
-    foho_f3 babs = f3(fr.bc[0] + co[0], fr.bc[1] + co[1], fr.bc[2] + co[2]);
-    foho_f3 e = mat3_tmul(fr.A, babs);
-    fr.e[0] = e.x; fr.e[1] = e.y; fr.e[2] = e.z;
-    fr.f = dot3(babs, babs);
+    foho_object_frame(th, T, co, d.bound, D, fr);
   }
   __syncthreads();
 
@@ -242,9 +221,9 @@ __global__ void __launch_bounds__(256) k_voxdist(foho_guidance_desc d, FohoWorks
   const float kappa = fr.kappa;
   const float N = (float)D * (float)D * (float)D;
   const float *S = d.sdf + (size_t)b * D * D * D;
-  float *G = d.grad_sdf + (size_t)b * D * D * D;
   float *Ghg = ws.G_hg + (size_t)b * Vh * 3;
   const int *cand = ws.cand + (size_t)b * ws.cap;
+  float *cval = ws.cand_val + (size_t)b * ws.cap;   // dE/dS of the candidate, added to G by k_assemble
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   float acc_int = 0.f, acc_gk = 0.f;
   for (int c = blockIdx.x * warps_per_cta + wid; c < n; c += gridDim.x * warps_per_cta) {
@@ -277,7 +256,10 @@ __global__ void __launch_bounds__(256) k_voxdist(foho_guidance_desc d, FohoWorks
     float key = bf >= 0 ? best2 : INFINITY;
     float mk = warp_min(key);
     unsigned vote = __ballot_sync(0xffffffffu, key == mk && bf >= 0);
-    if (vote == 0u) continue;                               // cannot happen for a non-empty mesh
+    if (vote == 0u) {                                       // cannot happen for a non-empty mesh
+      if (lane == 0) cval[c] = 0.f;
+      continue;
+    }
     int leader = __ffs(vote) - 1;
     if (lane == leader) {
       const float s = S[v];                                  // < 0 by construction
@@ -286,7 +268,7 @@ __global__ void __launch_bounds__(256) k_voxdist(foho_guidance_desc d, FohoWorks
       acc_int += ns * dist;
       const float coef = d.w.w_ivol * ns / N;               // dE/d(kappa*dist)
       acc_gk += coef * dist;
-      atomicAdd(G + v, -d.w.w_ivol * kappa * dist / N);
+      cval[c] = -d.w.w_ivol * kappa * dist / N;
       if (dist > 0.f) {
         int ia = sf[3 * bf], ib = sf[3 * bf + 1], ic = sf[3 * bf + 2];
         foho_f3 a = f3(sv[3 * ia], sv[3 * ia + 1], sv[3 * ia + 2]) - p;
@@ -399,11 +381,14 @@ __global__ void __launch_bounds__(CH_THREADS) k_chamfer(foho_guidance_desc d, Fo
 
 // ----------------------------------------------------------------------------- k_finalize
 constexpr int FIN_THREADS = 512;
-constexpr int FIN_NRED = 32;
+constexpr int FIN_NRED = FOHO_FIN_NRED;
 __constant__ int c_tips[5] = {744, 320, 443, 554, 671};                          // pipelines.py:127
 __constant__ int c_openpose[21] = {0, 13, 14, 15, 16, 1, 2, 3, 17, 4, 5, 6, 18, 10, 11, 12, 19, 7, 8, 9, 20};  // :128
 
-__global__ void __launch_bounds__(FIN_THREADS) k_finalize(foho_guidance_desc d, FohoWorkspace ws, int stream_gx) {
+// k_finalize_verts: everything per hand vertex (runs beside the dense stream: it neither reads the
+// stream's moments nor writes G -- its dE/dS corner contributions go to ws.tri_* and are applied by
+// k_assemble once the stream has written G).
+__global__ void __launch_bounds__(FIN_THREADS) k_finalize_verts(foho_guidance_desc d, FohoWorkspace ws) {
   __shared__ FohoFrame fr;
   __shared__ float red[FIN_NRED * 32];
   __shared__ float kp3[21][3];     // concatenated order: 16 regressed + 5 tips
@@ -473,7 +458,8 @@ __global__ void __launch_bounds__(FIN_THREADS) k_finalize(foho_guidance_desc d, 
   for (int k = 0; k < FIN_NRED; ++k) acc[k] = 0.f;
   // layout: 0..2 gt_h, 3 gs_h, 4..12 GR_h, 13..15 gt_o, 16 gs_o, 17..25 GR_o, 26 pen, 27 con, 28 ch_hand
   const float *S = d.sdf + (size_t)b * D * D * D;
-  float *G = d.grad_sdf + (size_t)b * D * D * D;
+  int *tri_idx = ws.tri_idx + (size_t)b * Vh * 8;
+  float *tri_val = ws.tri_val + (size_t)b * Vh * 8;
   const float *Ghm = ws.G_hm + (size_t)b * Vh * 3;
   const float *Ghg = ws.G_hg + (size_t)b * Vh * 3;
   const float *rest = d.hand_rest + (size_t)b * Vh * 3;
@@ -519,17 +505,18 @@ __global__ void __launch_bounds__(FIN_THREADS) k_finalize(foho_guidance_desc d, 
     if (s < 0.f) dLds -= d.w.w_pen * invV;
     if (fabsf(s) > d.w.con_margin) dLds += d.w.w_con * invV * (s > 0.f ? 1.f : -1.f);
     float ghg[3] = {Ghg[3 * i], Ghg[3 * i + 1], Ghg[3 * i + 2]};
+#pragma unroll
+    for (int dx = 0; dx < 2; ++dx)
+#pragma unroll
+      for (int dy = 0; dy < 2; ++dy)
+#pragma unroll
+        for (int dz = 0; dz < 2; ++dz) {
+          float wx = dx ? fx : 1.f - fx, wy = dy ? fy : 1.f - fy, wz = dz ? fz : 1.f - fz;
+          const int k = dx * 4 + dy * 2 + dz;
+          tri_idx[i * 8 + k] = ((i0[0] + dx) * D + (i0[1] + dy)) * D + (i0[2] + dz);
+          tri_val[i * 8 + k] = dLds * (wx * wy * wz);
+        }
     if (dLds != 0.f) {
-#pragma unroll
-      for (int dx = 0; dx < 2; ++dx)
-#pragma unroll
-        for (int dy = 0; dy < 2; ++dy)
-#pragma unroll
-          for (int dz = 0; dz < 2; ++dz) {
-            float wx = dx ? fx : 1.f - fx, wy = dy ? fy : 1.f - fy, wz = dz ? fz : 1.f - fz;
-            float w = wx * wy * wz;
-            if (w != 0.f) atomicAdd(G + ((size_t)(i0[0] + dx) * D + (i0[1] + dy)) * D + (i0[2] + dz), dLds * w);
-          }
       if (live[0]) ghg[0] += dLds * dsx;
       if (live[1]) ghg[1] += dLds * dsy;
       if (live[2]) ghg[2] += dLds * dsz;
@@ -586,8 +573,46 @@ __global__ void __launch_bounds__(FIN_THREADS) k_finalize(foho_guidance_desc d, 
     acc[10] += gm.z * sh * w.x; acc[11] += gm.z * sh * w.y; acc[12] += gm.z * sh * w.z;
   }
   block_sum<FIN_NRED>(acc, red);
-
   if (tid == 0) {
+    float *fa = ws.fin_acc + (size_t)b * FIN_NRED;
+    acc[29] = use_kp ? kp_loss : 0.f;
+#pragma unroll
+    for (int k = 0; k < FIN_NRED; ++k) fa[k] = acc[k];
+  }
+}
+
+// k_assemble: after the dense stream AND the sparse chain: (1) adds the deferred sparse dE/dS
+// contributions (hand-voxel candidates, trilinear corners) to G, (2) block 0 of each sample folds the
+// stream moments and the vertex sums into the 16 leaf gradients and the loss terms.
+constexpr int ASM_THREADS = 256;
+__global__ void __launch_bounds__(ASM_THREADS) k_assemble(foho_guidance_desc d, FohoWorkspace ws, int stream_gx, int do_voxels) {
+  const int b = blockIdx.y, tid = threadIdx.x, Vh = d.Vh, D = d.D;
+  float *G = d.grad_sdf + (size_t)b * D * D * D;
+  {
+    const int *tri_idx = ws.tri_idx + (size_t)b * Vh * 8;
+    const float *tri_val = ws.tri_val + (size_t)b * Vh * 8;
+    for (int k = blockIdx.x * blockDim.x + tid; k < Vh * 8; k += gridDim.x * blockDim.x) {
+      const float v = tri_val[k];
+      if (v != 0.f) atomicAdd(G + tri_idx[k], v);
+    }
+    if (do_voxels) {
+      int n = ws.cnt[(size_t)b * CNT_NUM + CNT_NCAND];
+      if (n > ws.cap) n = ws.cap;
+      const int *cand = ws.cand + (size_t)b * ws.cap;
+      const float *cval = ws.cand_val + (size_t)b * ws.cap;
+      for (int k = blockIdx.x * blockDim.x + tid; k < n; k += gridDim.x * blockDim.x) atomicAdd(G + cand[k], cval[k]);
+    }
+  }
+  if (blockIdx.x == 0 && tid == 0) {
+    const FohoFrame &fr = ws.frames[b];
+    const bool use_kp = d.n_joints == 16 && d.j_regressor && d.kps_2d && Vh > 744;
+    const float invV = 1.f / (float)Vh;
+    float acc[FIN_NRED];
+    {
+      const float *fa = ws.fin_acc + (size_t)b * FIN_NRED;
+      for (int k = 0; k < FIN_NRED; ++k) acc[k] = fa[k];
+    }
+    const float kp_loss = acc[29];
     const foho_weights &W = d.w;
     const double N = (double)D * D * D;
     // stream moments (deterministic fixed-order sum, double)
@@ -671,6 +696,36 @@ __global__ void __launch_bounds__(FIN_THREADS) k_finalize(foho_guidance_desc d, 
 
 }  // namespace
 
+// ----------------------------------------------------------------------------- fork/join context
+// Two high-priority side streams + four events per device, created on first use (do the first call
+// outside a stream capture).  A mutex serialises callers that share them.
+struct ForkCtx {
+  cudaStream_t side[2];
+  cudaEvent_t fork, prep, join_a, join_b;
+  std::mutex mu;
+};
+static ForkCtx *fork_ctx() {
+  static ForkCtx *ctx[64] = {nullptr};
+  static std::mutex mu;
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return nullptr;
+  std::lock_guard<std::mutex> lock(mu);
+  if (!ctx[dev]) {
+    ForkCtx *c = new ForkCtx();
+    int lo = 0, hi = 0;
+    cudaDeviceGetStreamPriorityRange(&lo, &hi);      // hi = numerically lowest = highest priority
+    bool ok = true;
+    for (int i = 0; i < 2; ++i) ok = ok && cudaStreamCreateWithPriority(&c->side[i], cudaStreamNonBlocking, hi) == cudaSuccess;
+    ok = ok && cudaEventCreateWithFlags(&c->fork, cudaEventDisableTiming) == cudaSuccess;
+    ok = ok && cudaEventCreateWithFlags(&c->prep, cudaEventDisableTiming) == cudaSuccess;
+    ok = ok && cudaEventCreateWithFlags(&c->join_a, cudaEventDisableTiming) == cudaSuccess;
+    ok = ok && cudaEventCreateWithFlags(&c->join_b, cudaEventDisableTiming) == cudaSuccess;
+    if (!ok) { delete c; return nullptr; }
+    ctx[dev] = c;
+  }
+  return ctx[dev];
+}
+
 // ----------------------------------------------------------------------------- C-ABI
 extern "C" int foho_abi_version(void) { return FOHO_ABI_VERSION; }
 
@@ -721,21 +776,63 @@ extern "C" int foho_guidance_energy_fwd_bwd(const foho_guidance_desc *dp, void *
   cudaStream_t st = (cudaStream_t)cuda_stream;
 
   const int sm = d.stage_mask == 0 ? 0x3f : d.stage_mask;
+  const bool overlap = d.stage_mask == 0 && d.serial == 0;
   static int last_gx = 1;
+  int gx = last_gx;
+
+  // Stream layout.  overlap: the dense stream depends on nothing but the inputs, so it starts at once
+  // on the caller's stream while k_prep and the sparse chain run on two library-owned side streams:
+  //   caller : fork ------------------ k_stream -------------------------- wait(A) k_assemble [obj post]
+  //   side A : wait(fork) k_prep rec(P) k_chamfer_*      wait(B) [obj pre] k_finalize_verts rec(A)
+  //   side B :                  wait(P) k_raster k_compact k_voxdist rec(B)
+  // Only event record / wait is used, so the same sequence is legal inside a stream capture.
+  ForkCtx *fc = nullptr;
+  cudaStream_t sa = st, sb = st;
+  if (overlap) {
+    fc = fork_ctx();
+    if (!fc) return (int)cudaGetLastError();
+    sa = fc->side[0]; sb = fc->side[1];
+    fc->mu.lock();
+  }
+  struct Unlock { ForkCtx *f; ~Unlock() { if (f) f->mu.unlock(); } } unlock{fc};
+
+  if (overlap) {
+    FOHO_CUDA_TRY(cudaEventRecord(fc->fork, st));
+    FOHO_CUDA_TRY(cudaStreamWaitEvent(sa, fc->fork, 0));
+  }
   if (sm & 1) {
-    k_prep<<<d.B, 256, 0, st>>>(d, ws);
+    k_prep<<<d.B, 256, 0, sa>>>(d, ws);
     FOHO_LAUNCH_CHECK();
   }
-  int gx = last_gx;
+  if (overlap) {
+    FOHO_CUDA_TRY(cudaEventRecord(fc->prep, sa));
+    FOHO_CUDA_TRY(cudaStreamWaitEvent(sb, fc->prep, 0));
+  }
   if (sm & 2) {
-    int rc = foho_launch_stream(dp, ws, &gx, st);
+    int rc = foho_launch_stream(dp, ws, &gx, overlap, st);
     if (rc != FOHO_OK) return rc;
     last_gx = gx;
   }
+  if (sm & 8) {
+    k_raster<<<dim3((d.Fh + 127) / 128, d.B), 128, 0, sb>>>(d, ws);
+    FOHO_LAUNCH_CHECK();
+    k_compact<<<dim3(16, d.B), 256, 0, sb>>>(d, ws);
+    FOHO_LAUNCH_CHECK();
+    const size_t smem = (size_t)d.Fh * 16 + (size_t)d.Vh * 12 + (size_t)d.Fh * 12;
+    if (smem > 200 * 1024) return FOHO_E_SHAPE;
+    static size_t attr = 0;
+    if (smem > 48 * 1024 && smem > attr) {
+      FOHO_CUDA_TRY(cudaFuncSetAttribute(k_voxdist, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      attr = smem;
+    }
+    k_voxdist<<<dim3(64, d.B), 256, smem, sb>>>(d, ws);
+    FOHO_LAUNCH_CHECK();
+  }
+  if (overlap) FOHO_CUDA_TRY(cudaEventRecord(fc->join_b, sb));
   if ((sm & 4) && d.P > 0 && d.accel) {
     if (d.Vh > FOHO_ACCEL_HV) return FOHO_E_SHAPE;
     if (((uintptr_t)d.accel & 255) != 0) return FOHO_E_WORKSPACE;
-    int rc = foho_launch_chamfer_accel(dp, ws, st);
+    int rc = foho_launch_chamfer_accel(dp, ws, sa);
     if (rc != FOHO_OK) return rc;
   } else if ((sm & 4) && d.P > 0) {
     const size_t smem = (size_t)d.Vh * (16 + 8 + 12);
@@ -746,31 +843,25 @@ extern "C" int foho_guidance_energy_fwd_bwd(const foho_guidance_desc *dp, void *
       attr = smem;
     }
     const int nchunk = (d.P + CH_POINTS_PER_CTA - 1) / CH_POINTS_PER_CTA;
-    k_chamfer<<<dim3(nchunk, d.B), CH_THREADS, smem, st>>>(d, ws);
+    k_chamfer<<<dim3(nchunk, d.B), CH_THREADS, smem, sa>>>(d, ws);
     FOHO_LAUNCH_CHECK();
   }
-  if (sm & 8) {
-    k_raster<<<dim3((d.Fh + 127) / 128, d.B), 128, 0, st>>>(d, ws);
-    FOHO_LAUNCH_CHECK();
-    k_compact<<<dim3(16, d.B), 256, 0, st>>>(d, ws);
-    FOHO_LAUNCH_CHECK();
-    const size_t smem = (size_t)d.Fh * 16 + (size_t)d.Vh * 12 + (size_t)d.Fh * 12;
-    if (smem > 200 * 1024) return FOHO_E_SHAPE;
-    static size_t attr = 0;
-    if (smem > 48 * 1024 && smem > attr) {
-      FOHO_CUDA_TRY(cudaFuncSetAttribute(k_voxdist, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      attr = smem;
-    }
-    k_voxdist<<<dim3(64, d.B), 256, smem, st>>>(d, ws);
-    FOHO_LAUNCH_CHECK();
-  }
+  if (overlap) FOHO_CUDA_TRY(cudaStreamWaitEvent(sa, fc->join_b, 0));
   const bool obj_mesh = (sm & 32) && d.Vo_total > 0;
   if (obj_mesh) {
-    int rc = foho_launch_objmesh_pre(dp, ws, st);
+    int rc = foho_launch_objmesh_pre(dp, ws, sa);
     if (rc != FOHO_OK) return rc;
   }
   if (sm & 16) {
-    k_finalize<<<d.B, FIN_THREADS, 0, st>>>(d, ws, gx);
+    k_finalize_verts<<<d.B, FIN_THREADS, 0, sa>>>(d, ws);
+    FOHO_LAUNCH_CHECK();
+  }
+  if (overlap) {
+    FOHO_CUDA_TRY(cudaEventRecord(fc->join_a, sa));
+    FOHO_CUDA_TRY(cudaStreamWaitEvent(st, fc->join_a, 0));
+  }
+  if (sm & 16) {
+    k_assemble<<<dim3(8, d.B), ASM_THREADS, 0, st>>>(d, ws, gx, (sm & 8) ? 1 : 0);
     FOHO_LAUNCH_CHECK();
   }
   if (obj_mesh && (sm & 16)) {

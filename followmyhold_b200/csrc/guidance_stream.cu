@@ -38,6 +38,22 @@ __device__ __forceinline__ StreamCoef load_coef(const FohoFrame &fr, float cN) {
   return c;
 }
 
+// where the per-sample frame comes from: the stream kernels derive their coefficients from the leaves
+// themselves (thread 0 of each CTA), so they do not depend on k_prep and can run beside it.
+struct StreamSrc {
+  const float *theta, *T_h2m, *obj_center;
+  float bound;
+};
+__device__ __forceinline__ StreamCoef stream_coef(const StreamSrc &src, int b, int D, float cN, StreamCoef *sc) {
+  if (threadIdx.x == 0) {
+    FohoFrame fr;
+    foho_object_frame(src.theta + (size_t)b * 16, src.T_h2m + (size_t)b * 16, src.obj_center + (size_t)b * 3, src.bound, D, fr);
+    *sc = load_coef(fr, cN);
+  }
+  __syncthreads();
+  return *sc;
+}
+
 struct StreamAcc {
   float m0, m1x, m1y, m2xy, cnt;
   float az[4];   // per z-slot sum of w (z is a per-thread constant in the fast paths)
@@ -65,7 +81,6 @@ __device__ __forceinline__ float4 voxel4(float4 s, float fx, float fy, const Str
   a.m1x = fmaf(fx, rs, a.m1x);
   a.m1y = fmaf(fy, rs, a.m1y);
   a.m2xy = fmaf(r2, rs, a.m2xy);
-  a.cnt += (s.x < 0.f ? 1.f : 0.f) + (s.y < 0.f ? 1.f : 0.f) + (s.z < 0.f ? 1.f : 0.f) + (s.w < 0.f ? 1.f : 0.f);
   return g;
 }
 
@@ -92,11 +107,12 @@ constexpr int LDG_THREADS = 256;
 constexpr int LDG_UNROLL = 4;
 
 __global__ void __launch_bounds__(LDG_THREADS) k_stream_ldg(const float *__restrict__ sdf, float *__restrict__ grad,
-                                                            const FohoFrame *__restrict__ frames,
+                                                            const StreamSrc src,
                                                             float *__restrict__ partials, int D, int logD, float cN) {
   __shared__ float red[6 * 32];
+  __shared__ StreamCoef sc;
   const int b = blockIdx.y;
-  const StreamCoef c = load_coef(frames[b], cN);
+  const StreamCoef c = stream_coef(src, b, D, cN, &sc);
   const size_t vol = (size_t)D * D * D;
   const float4 *__restrict__ S4 = reinterpret_cast<const float4 *>(sdf + (size_t)b * vol);
   float4 *__restrict__ G4 = reinterpret_cast<float4 *>(grad + (size_t)b * vol);
@@ -138,8 +154,7 @@ constexpr int TMA_THREADS = 256;
 constexpr int TMA_F4_PER_THREAD = 4;                                  // 16 KB tiles
 constexpr int TMA_TILE_F4 = TMA_THREADS * TMA_F4_PER_THREAD;          // 1024 float4
 constexpr int TMA_TILE_BYTES = TMA_TILE_F4 * 16;
-constexpr int TMA_STAGES = 6;
-constexpr int TMA_PREFETCH = 3;
+constexpr int TMA_MAX_STAGES = 8;   // ring depth and prefetch distance are launch parameters
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
@@ -179,15 +194,17 @@ __device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wa
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
 __global__ void __launch_bounds__(TMA_THREADS, 2) k_stream_tma(const float *__restrict__ sdf, float *__restrict__ grad,
-                                                               const FohoFrame *__restrict__ frames,
-                                                               float *__restrict__ partials, int D, int logD, float cN) {
+                                                               const StreamSrc src,
+                                                               float *__restrict__ partials, int D, int logD, float cN,
+                                                               int nstages, int nprefetch) {
+  __shared__ StreamCoef sc;
+  __shared__ uint64_t full[TMA_MAX_STAGES];
+  __shared__ float red[6 * 32];
   extern __shared__ __align__(128) unsigned char smem_raw[];
-  float4 *stage = reinterpret_cast<float4 *>(smem_raw);                       // [STAGES][TILE_F4]
-  uint64_t *full = reinterpret_cast<uint64_t *>(smem_raw + (size_t)TMA_STAGES * TMA_TILE_BYTES);
-  float *red = reinterpret_cast<float *>(full + TMA_STAGES);
+  float4 *stage = reinterpret_cast<float4 *>(smem_raw);                       // [nstages][TILE_F4]
 
   const int b = blockIdx.y;
-  const StreamCoef c = load_coef(frames[b], cN);
+  const StreamCoef c = stream_coef(src, b, D, cN, &sc);
   const size_t vol = (size_t)D * D * D;
   const float4 *S4 = reinterpret_cast<const float4 *>(sdf + (size_t)b * vol);
   float4 *G4 = reinterpret_cast<float4 *>(grad + (size_t)b * vol);
@@ -201,7 +218,7 @@ __global__ void __launch_bounds__(TMA_THREADS, 2) k_stream_tma(const float *__re
   for (int k = 0; k < 4; ++k) { float z = z0 + (float)k; cz[k] = fmaf(c.k2 * z, z, c.ez * z); }
 
   if (threadIdx.x == 0) {
-    for (int s = 0; s < TMA_STAGES; ++s) mbar_init(&full[s], 1);
+    for (int s = 0; s < nstages; ++s) mbar_init(&full[s], 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   __syncthreads();
@@ -215,7 +232,7 @@ __global__ void __launch_bounds__(TMA_THREADS, 2) k_stream_tma(const float *__re
     return (int)(rem < TMA_TILE_F4 ? rem : TMA_TILE_F4);
   };
   if (threadIdx.x == 0) {
-    for (int k = 0; k < TMA_PREFETCH && k < nmine; ++k) {
+    for (int k = 0; k < nprefetch && k < nmine; ++k) {
       int n4 = tile_f4(k);
       mbar_expect_tx(&full[k], (uint32_t)n4 * 16u);
       bulk_load(stage + (size_t)k * TMA_TILE_F4, S4 + (first + (long long)k * gridDim.x) * TMA_TILE_F4, (uint32_t)n4 * 16u,
@@ -223,9 +240,10 @@ __global__ void __launch_bounds__(TMA_THREADS, 2) k_stream_tma(const float *__re
     }
   }
   StreamAcc a; acc_init(a);
+  int s = 0, sn = nprefetch % nstages;     // ring slots of tile k and of tile k + nprefetch
+  uint32_t ph = 0;
+  const int pending = nstages - nprefetch; // store groups that may stay in flight when a slot is refilled
   for (long long k = 0; k < nmine; ++k) {
-    const int s = (int)(k % TMA_STAGES);
-    const uint32_t ph = (uint32_t)((k / TMA_STAGES) & 1);
     const long long t = first + k * gridDim.x;
     const int n4 = tile_f4(k);
     float4 *buf = stage + (size_t)s * TMA_TILE_F4;
@@ -244,18 +262,22 @@ __global__ void __launch_bounds__(TMA_THREADS, 2) k_stream_tma(const float *__re
     __syncthreads();
     if (threadIdx.x == 0) {
       bulk_store(G4 + t * TMA_TILE_F4, buf, (uint32_t)n4 * 16u);
-      long long kn = k + TMA_PREFETCH;
+      long long kn = k + nprefetch;
       if (kn < nmine) {
-        // stage kn % STAGES was last stored from at iteration kn - STAGES = k - (STAGES-PREFETCH);
-        // the (STAGES-PREFETCH) younger store groups (k-2, k-1, k) may stay pending.
-        bulk_wait_read<TMA_STAGES - TMA_PREFETCH>();
-        int sn = (int)(kn % TMA_STAGES);
+        // slot sn was last stored from at iteration kn - nstages = k - pending; the `pending`
+        // younger store groups may stay in flight.
+        if (pending >= 4) bulk_wait_read<4>();
+        else if (pending == 3) bulk_wait_read<3>();
+        else if (pending == 2) bulk_wait_read<2>();
+        else bulk_wait_read<1>();
         int nn4 = tile_f4(kn);
         mbar_expect_tx(&full[sn], (uint32_t)nn4 * 16u);
         bulk_load(stage + (size_t)sn * TMA_TILE_F4, S4 + (first + kn * gridDim.x) * TMA_TILE_F4, (uint32_t)nn4 * 16u,
                   &full[sn]);
       }
     }
+    if (++s == nstages) { s = 0; ph ^= 1u; }
+    if (++sn == nstages) sn = 0;
   }
   if (threadIdx.x == 0) bulk_wait_all();
   acc_store(a, z0, partials + ((size_t)b * FOHO_MAX_STREAM_CTAS + blockIdx.x) * FOHO_STREAM_PARTIALS, red);
@@ -263,11 +285,12 @@ __global__ void __launch_bounds__(TMA_THREADS, 2) k_stream_tma(const float *__re
 
 // ------------------------------------------------------------------------- generic path
 __global__ void __launch_bounds__(256) k_stream_any(const float *__restrict__ sdf, float *__restrict__ grad,
-                                                    const FohoFrame *__restrict__ frames, float *__restrict__ partials,
+                                                    const StreamSrc src, float *__restrict__ partials,
                                                     int D, float cN) {
   __shared__ float red[6 * 32];
+  __shared__ StreamCoef sc;
   const int b = blockIdx.y;
-  const StreamCoef c = load_coef(frames[b], cN);
+  const StreamCoef c = stream_coef(src, b, D, cN, &sc);
   const long long vol = (long long)D * D * D;
   const float *__restrict__ S = sdf + (size_t)b * vol;
   float *__restrict__ G = grad + (size_t)b * vol;
@@ -289,7 +312,6 @@ __global__ void __launch_bounds__(256) k_stream_any(const float *__restrict__ sd
     v[2] = fmaf(fy, w, v[2]);
     v[3] = fmaf(fz, w, v[3]);
     v[4] = fmaf(r2 + fz * fz, w, v[4]);
-    v[5] += s < 0.f ? 1.f : 0.f;
   }
   block_sum<6>(v, red);
   if (threadIdx.x == 0) {
@@ -307,7 +329,7 @@ int ilog2_exact(int D) {
 
 }  // namespace
 
-int foho_launch_stream(const foho_guidance_desc *d, const FohoWorkspace &ws, int *grid_x_out, cudaStream_t st) {
+int foho_launch_stream(const foho_guidance_desc *d, const FohoWorkspace &ws, int *grid_x_out, bool shared_sm, cudaStream_t st) {
   static int sm_count = 0;
   if (sm_count == 0) {
     int dev = 0;
@@ -319,15 +341,25 @@ int foho_launch_stream(const foho_guidance_desc *d, const FohoWorkspace &ws, int
   const float cN = (float)((double)d->w.w_mom / N);
   const int logD = ilog2_exact(D);
   int variant = d->stream_variant;
+  StreamSrc src;
+  src.theta = d->theta; src.T_h2m = d->T_h2m; src.obj_center = d->obj_center; src.bound = d->bound;
   const bool pow2 = logD >= 3 && D <= 1024;       // needs >= 2 float4 per row
   if (!pow2) variant = 3;
   else if (variant == 0) variant = 2;
   int gx;
   if (variant == 2) {
-    const size_t smem = (size_t)TMA_STAGES * TMA_TILE_BYTES + TMA_STAGES * sizeof(uint64_t) + 6 * 32 * sizeof(float);
+    // ring depth: 6 stages / 3 loads in flight when the kernel has the SM to itself; 4 / 2 when the
+    // sparse kernels run beside it and need shared memory of their own (d->stream_stages overrides)
+    int nstages = d->stream_stages > 0 ? d->stream_stages : (shared_sm ? 4 : 6);
+    if (nstages < 2) nstages = 2;
+    if (nstages > TMA_MAX_STAGES) nstages = TMA_MAX_STAGES;
+    int nprefetch = d->stream_prefetch > 0 ? d->stream_prefetch : nstages / 2;
+    if (nprefetch >= nstages) nprefetch = nstages - 1;
+    const size_t smem = (size_t)nstages * TMA_TILE_BYTES;
     static bool attr_done = false;
     if (!attr_done) {
-      FOHO_CUDA_TRY(cudaFuncSetAttribute(k_stream_tma, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      FOHO_CUDA_TRY(cudaFuncSetAttribute(k_stream_tma, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         TMA_MAX_STAGES * TMA_TILE_BYTES));
       attr_done = true;
     }
     long long ntiles = ((long long)(N / 4) + TMA_TILE_F4 - 1) / TMA_TILE_F4;
@@ -335,21 +367,22 @@ int foho_launch_stream(const foho_guidance_desc *d, const FohoWorkspace &ws, int
     if (gx > ntiles) gx = (int)ntiles;
     if (gx > FOHO_MAX_STREAM_CTAS) gx = FOHO_MAX_STREAM_CTAS;
     if (gx < 1) gx = 1;
-    k_stream_tma<<<dim3(gx, B), TMA_THREADS, smem, st>>>(d->sdf, d->grad_sdf, ws.frames, ws.stream_part, D, logD, cN);
+    k_stream_tma<<<dim3(gx, B), TMA_THREADS, smem, st>>>(d->sdf, d->grad_sdf, src, ws.stream_part, D, logD, cN, nstages,
+                                                             nprefetch);
   } else if (variant == 1) {
     long long ntiles = ((long long)(N / 4) + LDG_THREADS * LDG_UNROLL - 1) / (LDG_THREADS * LDG_UNROLL);
     gx = (sm_count * 8 + B - 1) / B;
     if (gx > ntiles) gx = (int)ntiles;
     if (gx > FOHO_MAX_STREAM_CTAS) gx = FOHO_MAX_STREAM_CTAS;
     if (gx < 1) gx = 1;
-    k_stream_ldg<<<dim3(gx, B), LDG_THREADS, 0, st>>>(d->sdf, d->grad_sdf, ws.frames, ws.stream_part, D, logD, cN);
+    k_stream_ldg<<<dim3(gx, B), LDG_THREADS, 0, st>>>(d->sdf, d->grad_sdf, src, ws.stream_part, D, logD, cN);
   } else {
     long long nblk = ((long long)N + 255) / 256;
     gx = (sm_count * 8 + B - 1) / B;
     if (gx > nblk) gx = (int)nblk;
     if (gx > FOHO_MAX_STREAM_CTAS) gx = FOHO_MAX_STREAM_CTAS;
     if (gx < 1) gx = 1;
-    k_stream_any<<<dim3(gx, B), 256, 0, st>>>(d->sdf, d->grad_sdf, ws.frames, ws.stream_part, D, cN);
+    k_stream_any<<<dim3(gx, B), 256, 0, st>>>(d->sdf, d->grad_sdf, src, ws.stream_part, D, cN);
   }
   FOHO_LAUNCH_CHECK();
   *grid_x_out = gx;

@@ -114,7 +114,10 @@ class GuidanceEngine:
         self.hand_grid = torch.zeros(B, Vh, 3, dtype=torch.float32, device=dev)
         self.grad_obj_verts = (torch.zeros(self.max_obj_verts, 3, dtype=torch.float32, device=dev)
                                if self.max_obj_verts > 0 else None)
-        self.launches_per_eval = 7 if P > 0 else 6      # + 4 when an object mesh is passed
+        self.launches_per_eval = 8 if P > 0 else 7      # + 4 when an object mesh is passed
+        self.serial = 0            # 1: every kernel in series on the caller's stream (no internal fork/join)
+        self.stream_stages = 0     # TMA stream ring depth / prefetch distance (0 = library default)
+        self.stream_prefetch = 0
         self._accel = None
         self._accel_ptr = 0
         self._accel_bytes = 0
@@ -142,7 +145,7 @@ class GuidanceEngine:
             _lib.check("foho_guidance_prepare_statics",
                        self.lib.foho_guidance_prepare_statics(C.byref(d), C.c_void_p(s.cuda_stream)))
         self._accel_for = st
-        self.launches_per_eval = 8
+        self.launches_per_eval = 9
 
     def make_desc(self, sdf: torch.Tensor, theta: torch.Tensor, st: GuidanceStatics,
                   grad_sdf: Optional[torch.Tensor] = None, late_step: bool = False,
@@ -173,6 +176,7 @@ class GuidanceEngine:
         d.image_h, d.image_w = int(st.image_hw[0]), int(st.image_hw[1])
         d.late_step = int(late_step)
         d.stream_variant = self.stream_variant
+        d.serial, d.stream_stages, d.stream_prefetch = self.serial, self.stream_stages, self.stream_prefetch
         d.fov_deg = float(st.fov_deg)
         d.bound = GRID_BOUND
         d.w = self.weights

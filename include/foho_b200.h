@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define FOHO_ABI_VERSION 2
+#define FOHO_ABI_VERSION 3
 
 #define FOHO_OK 0
 #define FOHO_E_NULL (-1)      /* required pointer is NULL            */
@@ -79,7 +79,11 @@ typedef struct foho_guidance_desc {
   int32_t stream_variant; /* 0 = default kernel choice, 1 = LDG/STG, 2 = TMA bulk       */
   int32_t stage_mask;   /* profiling hook: 0 = whole evaluation; else bit0 prep, bit1 dense
                            stream, bit2 chamfer, bit3 hand voxels, bit4 finalize, bit5 object mesh */
-  int32_t reserved0;
+  int32_t serial;       /* 0 = the sparse kernels run beside the dense stream on library-owned side
+                           streams (fork/join by events; legal under stream capture); 1 = every kernel
+                           in series on the caller's stream                                    */
+  int32_t stream_stages;   /* TMA stream: ring depth (0 = default: 6 alone, 4 beside the sparse kernels) */
+  int32_t stream_prefetch; /* TMA stream: bulk loads kept in flight per CTA (0 = stages / 2)    */
   float fov_deg;        /* MoGe fov_x in degrees (guidance/run.py:228-230)              */
   float bound;          /* lattice half extent, 1.10 (pipelines.py:1127)                */
   foho_weights w;

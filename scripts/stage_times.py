@@ -43,4 +43,34 @@ for m, n in names.items():
     e1.record()
     torch.cuda.synchronize()
     out[n] = round(e0.elapsed_time(e1) / a.reps * 1e3, 2)
+for name, serial, stages, pre in (("all_serial", 1, 0, 0), ("all_overlap_s4p2", 0, 4, 2), ("all_overlap_s5p3", 0, 5, 3),
+                                  ("all_overlap_s6p3", 0, 6, 3), ("all_overlap_s4p3", 0, 4, 3), ("all_overlap_ldg", 0, 0, 0)):
+    eng.serial, eng.stream_stages, eng.stream_prefetch = serial, stages, pre
+    eng.stream_variant = 1 if name.endswith("ldg") else a.variant
+    desc = eng.make_desc(loop.sdf, loop.theta, st)
+    for _ in range(3):
+        eng.launch(desc)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(a.reps):
+        eng.launch(desc)
+    e1.record()
+    torch.cuda.synchronize()
+    out[name] = round(e0.elapsed_time(e1) / a.reps * 1e3, 2)
+# stream alone with different ring depths
+for stages, pre in ((6, 3), (5, 3), (4, 2), (4, 3), (8, 4), (3, 2)):
+    eng.serial, eng.stream_stages, eng.stream_prefetch, eng.stream_variant = 1, stages, pre, a.variant
+    desc = eng.make_desc(loop.sdf, loop.theta, st)
+    desc.stage_mask = 2
+    for _ in range(3):
+        eng.launch(desc)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(a.reps):
+        eng.launch(desc)
+    e1.record()
+    torch.cuda.synchronize()
+    out[f"stream_s{stages}p{pre}"] = round(e0.elapsed_time(e1) / a.reps * 1e3, 2)
 print(json.dumps({"us_per_launch": out, "B": a.B, "D": a.D, "P": a.P}))
