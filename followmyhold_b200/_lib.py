@@ -16,7 +16,7 @@ PKG_DIR = Path(__file__).resolve().parent
 REPO_ROOT = PKG_DIR.parent
 CSRC = PKG_DIR / "csrc"
 LIB_PATH = PKG_DIR / "libfoho_b200.so"
-SOURCES = ["guidance_stream.cu", "guidance_sparse.cu", "guidance_objmesh.cu", "guidance_chamfer.cu", "guidance_update.cu", "icp.cu",
+SOURCES = ["guidance_stream.cu", "guidance_sparse.cu", "guidance_objmesh.cu", "guidance_chamfer.cu", "guidance_voxdist.cu", "guidance_update.cu", "icp.cu",
            "mesh_sdf.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "-Xcompiler", "-fPIC", "-Xcompiler", "-O3"]
@@ -103,7 +103,7 @@ class GuidanceDesc(C.Structure):
     _fields_ = [
         ("B", C.c_int32), ("D", C.c_int32), ("Vh", C.c_int32), ("Fh", C.c_int32), ("P", C.c_int32),
         ("n_joints", C.c_int32), ("image_h", C.c_int32), ("image_w", C.c_int32), ("late_step", C.c_int32),
-        ("stream_variant", C.c_int32), ("stage_mask", C.c_int32), ("serial", C.c_int32), ("stream_stages", C.c_int32), ("stream_prefetch", C.c_int32), ("fov_deg", C.c_float), ("bound", C.c_float), ("w", Weights),
+        ("stream_variant", C.c_int32), ("stage_mask", C.c_int32), ("serial", C.c_int32), ("stream_stages", C.c_int32), ("stream_prefetch", C.c_int32), ("stream_ctas", C.c_int32), ("reserved0", C.c_int32), ("fov_deg", C.c_float), ("bound", C.c_float), ("w", Weights),
         ("sdf", C.c_void_p), ("grad_sdf", C.c_void_p), ("hand_rest", C.c_void_p), ("hand_faces", C.c_void_p),
         ("cloud", C.c_void_p), ("T_h2m", C.c_void_p), ("obj_center", C.c_void_p), ("theta", C.c_void_p),
         ("j_regressor", C.c_void_p), ("kps_2d", C.c_void_p), ("grad_hand_ext", C.c_void_p),
@@ -112,6 +112,8 @@ class GuidanceDesc(C.Structure):
         ("obj_vert_offsets", C.c_void_p), ("obj_edges", C.c_void_p), ("obj_edge_offsets", C.c_void_p),
         ("grad_obj_verts", C.c_void_p), ("workspace", C.c_void_p), ("workspace_bytes", C.c_size_t),
         ("accel", C.c_void_p), ("accel_bytes", C.c_size_t),
+        ("hand_nbr_off", C.c_void_p), ("hand_nbr", C.c_void_p), ("nbr_stride", C.c_int32), ("reserved1", C.c_int32),
+        ("trace", C.c_void_p),
     ]
 
 

@@ -76,10 +76,13 @@ struct FohoWorkspace {
   float *g_ot;                // [Vo,3] dE/d(ot)
   unsigned long long *knn_obj;// [B,Vh] packed (d2 bits << 32 | packed object vertex index)
   FohoObjInfo *oinfo;         // [B]
+  float4 *sph;                // [B,Fh] bounding sphere (centroid, radius) of each hand face, lattice units
+  float *kpbuf;               // [B,64] k_keypoints -> k_finalize_verts: dE/d(21 key-points) | loss
   float *fin_acc;             // [B,FOHO_FIN_NRED] per-sample sums of k_finalize_verts
   float *cand_val;            // [B,cap] dE/dS contribution of each candidate voxel (applied by k_assemble)
   int *tri_idx;               // [B,Vh,8] voxel index of the trilinear corners of each vertex sample
   float *tri_val;             // [B,Vh,8] dE/dS contribution at those corners (0 = none)
+  unsigned long long *trace;  // optional (desc->trace): per kernel [first CTA start, last CTA end], globaltimer ns
   int cap;
   int W;                      // words per column
   size_t total;
@@ -90,6 +93,7 @@ struct FohoWorkspace {
 #define FOHO_ACCEL_HV 1024        // max hand vertices the structured search handles
 #define FOHO_ACCEL_LEAVES 128     // leaves of 8 Morton-consecutive rest vertices
 #define FOHO_ACCEL_SUPERS 16      // super-boxes of 8 leaves
+#define FOHO_ACCEL_FACES 2048     // max hand faces the grouped point->mesh search handles
 
 struct FohoAccelHand {
   float4 v[FOHO_ACCEL_HV];                 // sorted rest verts relative to the rest bbox centre; w = original index
@@ -111,19 +115,21 @@ struct FohoAccel {
   float4 *g_lo, *g_hi;        // [B,NGcap] AABB of each group of 32 sorted points (absolute MoGe)
   float4 *s_lo, *s_hi;        // [B,NScap] AABB of each super-group of 32 groups
   int NGcap, NScap;
+  int4 *face_sv;              // [B,FOHO_ACCEL_FACES] faces in Morton order of their rest centroid: (ia, ib, ic, face id)
+  int *face_rank;             // [B,FOHO_ACCEL_FACES] face id -> position in that order
   int *seed_c2h;              // [B,P]  warm start: hand slot found for each sorted cloud point last time
   int *seed_h2c;              // [B,FOHO_ACCEL_HV] warm start: sorted cloud position found for each hand vertex
   size_t total;
 };
 
-static inline size_t foho_align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+FOHO_HD size_t foho_align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
 static inline int foho_cand_capacity(int D) {
   long long n = (long long)D * D * D;
   return (int)(n < (1ll << 18) ? n : (1ll << 18));
 }
 
-static inline void foho_ws_layout(FohoWorkspace &w, char *base, int B, int D, int Vh, int /*Fh*/, int /*P*/, int Vo) {
+static inline void foho_ws_layout(FohoWorkspace &w, char *base, int B, int D, int Vh, int Fh, int /*P*/, int Vo) {
   size_t off = 0;
   auto take = [&](size_t bytes) { char *p = base ? base + off : nullptr; off += foho_align_up(bytes, 256); return p; };
   w.W = (D + 31) / 32;
@@ -144,6 +150,8 @@ static inline void foho_ws_layout(FohoWorkspace &w, char *base, int B, int D, in
   w.g_ot = (float *)take(sizeof(float) * 3 * vo);
   w.knn_obj = (unsigned long long *)take(sizeof(unsigned long long) * (size_t)B * Vh);
   w.oinfo = (FohoObjInfo *)take(sizeof(FohoObjInfo) * (size_t)B);
+  w.sph = (float4 *)take(sizeof(float4) * (size_t)B * Fh);
+  w.kpbuf = (float *)take(sizeof(float) * 64 * (size_t)B);
   w.fin_acc = (float *)take(sizeof(float) * FOHO_FIN_NRED * (size_t)B);
   w.cand_val = (float *)take(sizeof(float) * (size_t)B * w.cap);
   w.tri_idx = (int *)take(sizeof(int) * 8 * (size_t)B * Vh);
@@ -151,8 +159,23 @@ static inline void foho_ws_layout(FohoWorkspace &w, char *base, int B, int D, in
   w.total = off;
 }
 
+// kernel ids of the optional timeline trace (desc->trace: 2 x u64 per id, host-initialised to {~0, 0})
+enum { TR_PREP = 0, TR_STREAM, TR_H2C, TR_C2H, TR_CHAMFER, TR_RASTER, TR_COMPACT, TR_VOXDIST, TR_FIN, TR_ASM, TR_KP, TR_NUM };
+
 // ---- device reductions -------------------------------------------------------------
 #if defined(__CUDACC__)
+struct FohoTrace {
+  unsigned long long *p;
+  __device__ __forceinline__ static unsigned long long now() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+  }
+  __device__ __forceinline__ FohoTrace(unsigned long long *base, int id) : p(nullptr) {
+    if (base && threadIdx.x == 0) { p = base + 2 * id; atomicMin(p, now()); }
+  }
+  __device__ __forceinline__ ~FohoTrace() { if (p) atomicMax(p + 1, now()); }
+};
 // Object-side part of the per-sample frame: everything that depends only on theta_o, T_h2m, c_o and
 // the lattice (a5/a6 of SURVEY.md section 8a; pipelines.py:108-118,242-250).  Called by k_prep and,
 // so that the dense stream does not have to wait for k_prep, by thread 0 of every stream CTA.
@@ -229,4 +252,8 @@ int foho_launch_stream(const foho_guidance_desc *d, const FohoWorkspace &ws, int
 int foho_launch_objmesh_pre(const foho_guidance_desc *d, const FohoWorkspace &ws, cudaStream_t st);
 int foho_launch_objmesh_post(const foho_guidance_desc *d, const FohoWorkspace &ws, cudaStream_t st);
 // structured chamfer search (guidance_chamfer.cu); used when desc->accel is set
-int foho_launch_chamfer_accel(const foho_guidance_desc *d, const FohoWorkspace &ws, cudaStream_t st);
+// grouped exact point->mesh distance of the candidate voxels (guidance_voxdist.cu); needs desc->accel
+int foho_launch_voxdist_tree(const foho_guidance_desc *d, const FohoWorkspace &ws, cudaStream_t st);
+void foho_accel_layout(FohoAccel &a, char *base, int B, int P);
+int foho_launch_chamfer_h2c(const foho_guidance_desc *d, const FohoWorkspace &ws, cudaStream_t st);
+int foho_launch_chamfer_c2h(const foho_guidance_desc *d, const FohoWorkspace &ws, cudaStream_t st);

@@ -116,6 +116,67 @@ __global__ void __launch_bounds__(ACC_THREADS) k_accel_hand(const float *__restr
   if (tid == 0) { H->n_leaves = nleaf; H->n_supers = nsup; H->Vh = Vh; H->pad = 0; }
 }
 
+// ----------------------------------------------------------------------------- build: face order
+// Faces in Morton order of their REST centroid (one CTA per sample, bitonic sort in shared memory):
+// any 32 consecutive faces are then a compact patch of the hand, in every pose (the pose is a
+// similarity), which is what k_voxdist_tree's two-level sphere culling needs.
+__global__ void __launch_bounds__(ACC_THREADS) k_accel_faces(const float *__restrict__ hand_rest, const int *__restrict__ faces,
+                                                             int Vh, int Fh, FohoAccel acc) {
+  __shared__ unsigned long long key[FOHO_ACCEL_FACES];
+  __shared__ float red[6 * 32];
+  __shared__ float bb[6];
+  const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  const float *rest = hand_rest + (size_t)b * Vh * 3;
+  float mn[3] = {INFINITY, INFINITY, INFINITY}, mx[3] = {-INFINITY, -INFINITY, -INFINITY};
+  for (int i = tid; i < Vh; i += blockDim.x)
+#pragma unroll
+    for (int a = 0; a < 3; ++a) { float v = rest[3 * i + a]; mn[a] = fminf(mn[a], v); mx[a] = fmaxf(mx[a], v); }
+#pragma unroll
+  for (int a = 0; a < 3; ++a) { mn[a] = warp_min(mn[a]); mx[a] = warp_max(mx[a]); }
+  if (lane == 0)
+#pragma unroll
+    for (int a = 0; a < 3; ++a) { red[a * 32 + wid] = mn[a]; red[(3 + a) * 32 + wid] = mx[a]; }
+  __syncthreads();
+  if (tid < 6) {
+    float v = red[tid * 32];
+    for (int w = 1; w < (int)(blockDim.x >> 5); ++w) v = tid < 3 ? fminf(v, red[tid * 32 + w]) : fmaxf(v, red[tid * 32 + w]);
+    bb[tid] = v;
+  }
+  __syncthreads();
+  const float ext = fmaxf(fmaxf(bb[3] - bb[0], bb[4] - bb[1]), fmaxf(bb[5] - bb[2], 1e-30f));
+  const float q = 1023.f / ext;
+  for (int f = tid; f < FOHO_ACCEL_FACES; f += blockDim.x) {
+    unsigned long long k = ~0ull;
+    if (f < Fh) {
+      const int ia = faces[3 * f], ib = faces[3 * f + 1], ic = faces[3 * f + 2];
+      const float cx = (rest[3 * ia] + rest[3 * ib] + rest[3 * ic]) * (1.f / 3.f);
+      const float cy = (rest[3 * ia + 1] + rest[3 * ib + 1] + rest[3 * ic + 1]) * (1.f / 3.f);
+      const float cz = (rest[3 * ia + 2] + rest[3 * ib + 2] + rest[3 * ic + 2]) * (1.f / 3.f);
+      const unsigned ix = (unsigned)fminf(fmaxf((cx - bb[0]) * q, 0.f), 1023.f);
+      const unsigned iy = (unsigned)fminf(fmaxf((cy - bb[1]) * q, 0.f), 1023.f);
+      const unsigned iz = (unsigned)fminf(fmaxf((cz - bb[2]) * q, 0.f), 1023.f);
+      k = ((unsigned long long)((spread3(ix) << 2) | (spread3(iy) << 1) | spread3(iz)) << 32) | (unsigned)f;
+    }
+    key[f] = k;
+  }
+  __syncthreads();
+  for (int size = 2; size <= FOHO_ACCEL_FACES; size <<= 1)
+    for (int stride = size >> 1; stride > 0; stride >>= 1) {
+      const int i = 2 * stride * (tid / stride) + (tid % stride), j = i + stride;
+      const bool up = (i & size) == 0;
+      const unsigned long long a = key[i], c = key[j];
+      if ((a > c) == up) { key[i] = c; key[j] = a; }
+      __syncthreads();
+    }
+  int4 *sv = acc.face_sv + (size_t)b * FOHO_ACCEL_FACES;
+  int *rank = acc.face_rank + (size_t)b * FOHO_ACCEL_FACES;
+  for (int s = tid; s < Fh; s += blockDim.x) {
+    const int f = (int)(unsigned)key[s];
+    sv[s] = make_int4(faces[3 * f], faces[3 * f + 1], faces[3 * f + 2], f);
+    rank[f] = s;
+  }
+}
+
 // ----------------------------------------------------------------------------- build: cloud order
 // The cloud is put into 30-bit Morton order (10 bits per axis over its cubic bbox) by a bitonic sort
 // of (code << 32 | index) keys, so that ANY run of consecutive points is spatially compact.  Runs
@@ -275,6 +336,23 @@ __device__ __forceinline__ float box_max2(float4 v, const float (&glo)[3], const
   return fmaf(dz, dz, fmaf(dy, dy, dx * dx));
 }
 
+// Add (gx,gy,gz) to gacc[3*j..] for every valid lane, one shared-memory atomic triple per DISTINCT j in
+// the warp: neighbouring cloud points mostly share their nearest vertex, and float atomics on one
+// shared address serialise (CAS loop).  Must be called by all 32 lanes.
+__device__ __forceinline__ void warp_scatter_add3(float *gacc, bool valid, int j, float gx, float gy, float gz) {
+  const int lane = threadIdx.x & 31;
+  unsigned todo = __ballot_sync(0xffffffffu, valid);
+  while (todo) {
+    const int leader = __ffs(todo) - 1;
+    const int key = __shfl_sync(0xffffffffu, j, leader);
+    const bool mine = valid && j == key;
+    const unsigned grp = __ballot_sync(0xffffffffu, mine);
+    const float sx = warp_sum(mine ? gx : 0.f), sy = warp_sum(mine ? gy : 0.f), sz = warp_sum(mine ? gz : 0.f);
+    if (lane == leader) { atomicAdd(gacc + 3 * key, sx); atomicAdd(gacc + 3 * key + 1, sy); atomicAdd(gacc + 3 * key + 2, sz); }
+    todo &= ~grp;
+  }
+}
+
 struct C2HBest { float d2; int slot; };
 
 // 8 vertices of one leaf: all distances, a min tree, and (rarely) the arg-min
@@ -296,6 +374,7 @@ __device__ __forceinline__ void c2h_scan_leaf(const float4 *__restrict__ v, int 
 }
 
 __global__ void __launch_bounds__(C2H_THREADS) k_chamfer_c2h(foho_guidance_desc d, FohoWorkspace ws, FohoAccel acc) {
+  FohoTrace trace_(ws.trace, TR_C2H);
   __shared__ float4 sv[FOHO_ACCEL_HV];
   __shared__ float4 s_llo[FOHO_ACCEL_LEAVES], s_lhi[FOHO_ACCEL_LEAVES];
   __shared__ float gacc[FOHO_ACCEL_HV * 3];
@@ -388,13 +467,13 @@ __global__ void __launch_bounds__(C2H_THREADS) k_chamfer_c2h(foho_guidance_desc 
       }
     }
     if (valid && bst.slot != seed) *seedp = bst.slot;
-    if (valid) {
+    {
       // exact squared distance in the (centred) MoGe frame, as the oracle evaluates it
       const int j = __float_as_int(sv[bst.slot].w);
       const float hx = hmc[3 * j], hy = hmc[3 * j + 1], hz = hmc[3 * j + 2];
       const float dx = hx - px, dy = hy - py, dz = hz - pz;
-      sum += fmaf(dz, dz, fmaf(dy, dy, dx * dx));
-      atomicAdd(gacc + 3 * j, coef * dx); atomicAdd(gacc + 3 * j + 1, coef * dy); atomicAdd(gacc + 3 * j + 2, coef * dz);
+      if (valid) sum += fmaf(dz, dz, fmaf(dy, dy, dx * dx));
+      warp_scatter_add3(gacc, valid, j, coef * dx, coef * dy, coef * dz);
     }
   }
   sum = warp_sum(sum);
@@ -409,6 +488,131 @@ __global__ void __launch_bounds__(C2H_THREADS) k_chamfer_c2h(foho_guidance_desc 
   for (int i = tid; i < Vh * 3; i += blockDim.x) {
     const float g = gacc[i];
     if (g != 0.f) atomicAdd(Ghm + i, g);
+  }
+}
+
+// ----------------------------------------------------------------------------- cloud -> hand, graph walk
+// When the caller supplies the Delaunay neighbour graph of the REST hand vertices (desc->hand_nbr*,
+// built once per image on the host), the nearest rest vertex of a pulled-back cloud point is found by
+// greedy descent: from the vertex found last time, move to the neighbour closest to the query until no
+// neighbour is closer.  On a Delaunay graph that stops only at the true nearest vertex (every
+// non-nearest vertex has a Delaunay neighbour closer to the query), so the result is exact; with the
+// warm start it takes ~0.3 moves and ~27 distance evaluations per point instead of the ~400 of the box
+// search, which matters because most cloud points are far from the hand, where boxes prune poorly.
+constexpr int WALK_THREADS = 256;
+// Per-vertex gradient sums are accumulated per CTA in fixed point (2^-33 units, |h - p| < 64) split over
+// two 32-bit shared-memory words -- hi = v >> 20 (signed), lo = v & 0xFFFFF -- because only 32-bit
+// INTEGER shared atomics are native (float and 64-bit ones are CAS spin loops, and neighbouring cloud
+// points mostly hit the same vertex).  A CTA adds at most 4096 points, so neither word can overflow;
+// integer addition is associative, so the per-CTA sums do not depend on the arrival order.
+constexpr float WALK_FIX = 8589934592.f;             // 2^33
+constexpr float WALK_UNFIX = 1.f / 8589934592.f;
+constexpr int WALK_MAX_CHUNK = 4096;
+__device__ __forceinline__ void walk_fix_add(int *hi, unsigned *lo, float x) {
+  const long long v = __float2ll_rn(fminf(fmaxf(x, -63.f), 63.f) * WALK_FIX);
+  atomicAdd(hi, (int)(v >> 20));
+  atomicAdd(lo, (unsigned)(v & 0xFFFFF));
+}
+
+__global__ void __launch_bounds__(WALK_THREADS) k_chamfer_c2h_walk(foho_guidance_desc d, FohoWorkspace ws, FohoAccel acc,
+                                                                     int chunk) {
+  FohoTrace trace_(ws.trace, TR_C2H);
+  extern __shared__ __align__(16) unsigned char sm_raw[];
+  const int b = blockIdx.y, Vh = d.Vh, P = d.P, tid = threadIdx.x;
+  const int p0 = blockIdx.x * chunk;
+  if (p0 >= P) return;
+  const int p1 = min(P, p0 + chunk);
+  const int *goff = d.hand_nbr_off + (size_t)b * (Vh + 1);
+  const uint16_t *gadj = d.hand_nbr + (size_t)b * d.nbr_stride;
+  const int E = goff[Vh];
+  float4 *sv = reinterpret_cast<float4 *>(sm_raw);                                   // [Vh] rest verts - bbox centre
+  int *ghi = reinterpret_cast<int *>(sv + Vh);                                       // [Vh*3] fixed point, high part
+  unsigned *glo = reinterpret_cast<unsigned *>(ghi + 3 * Vh);                        // [Vh*3] low 20 bits
+  int *soff = reinterpret_cast<int *>(glo + 3 * Vh);                                 // [Vh+1]
+  uint16_t *sadj = reinterpret_cast<uint16_t *>(sm_raw + foho_align_up((size_t)Vh * 40 + (size_t)(Vh + 1) * 4, 16));   // [E]
+  __shared__ float red[32];
+  const FohoFrame &fr = ws.frames[b];
+  const float *rest = d.hand_rest + (size_t)b * Vh * 3;
+  for (int i = tid; i < Vh; i += blockDim.x) {
+    sv[i] = make_float4(rest[3 * i] - fr.ch[0], rest[3 * i + 1] - fr.ch[1], rest[3 * i + 2] - fr.ch[2], 0.f);
+    ghi[3 * i] = 0; ghi[3 * i + 1] = 0; ghi[3 * i + 2] = 0;
+    glo[3 * i] = 0u; glo[3 * i + 1] = 0u; glo[3 * i + 2] = 0u;
+  }
+  for (int i = tid; i <= Vh; i += blockDim.x) soff[i] = goff[i];
+  {
+    // 16-byte copies: nbr_stride is a multiple of 8 and both bases are 16-byte aligned (checked by the launcher)
+    const uint4 *g4 = reinterpret_cast<const uint4 *>(gadj);
+    uint4 *s4 = reinterpret_cast<uint4 *>(sadj);
+    const int n4 = (E + 7) >> 3;
+    for (int i = tid; i < n4; i += blockDim.x) s4[i] = g4[i];
+  }
+  __syncthreads();
+  const float ox = fr.chc[0] + fr.th[0], oy = fr.chc[1] + fr.th[1], oz = fr.chc[2] + fr.th[2];
+  const float is = 1.f / fr.sh;
+  float Rt[9];
+#pragma unroll
+  for (int r = 0; r < 3; ++r)
+#pragma unroll
+    for (int c = 0; c < 3; ++c) Rt[3 * r + c] = fr.Rh[3 * c + r] * is;
+  const float cx = fr.co[0], cy = fr.co[1], cz = fr.co[2];
+  const float4 *pts = acc.pts + (size_t)b * P;
+  int *seeds = acc.seed_c2h + (size_t)b * P;
+  const float *hmc = ws.hmc + (size_t)b * Vh * 3;
+  float sum = 0.f;
+  int prev = 0;
+  for (int pi = p0 + tid; pi < p1; pi += blockDim.x) {
+    const float4 c4 = pts[pi];
+    const int seed = seeds[pi];
+    const float px = c4.x - cx, py = c4.y - cy, pz = c4.z - cz;          // centred MoGe
+    const float rx = px - ox, ry = py - oy, rz = pz - oz;
+    const float qx = Rt[0] * rx + Rt[1] * ry + Rt[2] * rz;
+    const float qy = Rt[3] * rx + Rt[4] * ry + Rt[5] * rz;
+    const float qz = Rt[6] * rx + Rt[7] * ry + Rt[8] * rz;
+    int cur = (seed >= 0 && seed < Vh) ? seed : prev;                    // cold start: this thread's previous answer
+    float dc;
+    {
+      const float4 v = sv[cur];
+      const float dx = qx - v.x, dy = qy - v.y, dz = qz - v.z;
+      dc = fmaf(dz, dz, fmaf(dy, dy, dx * dx));
+    }
+    while (true) {
+      const int e0 = soff[cur], e1 = soff[cur + 1];
+      int best = cur;
+      float db = dc;
+#pragma unroll 4
+      for (int e = e0; e < e1; ++e) {
+        const int n = sadj[e];
+        const float4 v = sv[n];
+        const float dx = qx - v.x, dy = qy - v.y, dz = qz - v.z;
+        const float d2 = fmaf(dz, dz, fmaf(dy, dy, dx * dx));
+        if (d2 < db) { db = d2; best = n; }
+      }
+      if (best == cur) break;
+      cur = best; dc = db;
+    }
+    prev = cur;
+    if (cur != seed) seeds[pi] = cur;
+    // exact squared distance in the (centred) MoGe frame, as the oracle evaluates it
+    const float hx = hmc[3 * cur], hy = hmc[3 * cur + 1], hz = hmc[3 * cur + 2];
+    const float dx = hx - px, dy = hy - py, dz = hz - pz;
+    sum += fmaf(dz, dz, fmaf(dy, dy, dx * dx));
+    walk_fix_add(ghi + 3 * cur, glo + 3 * cur, dx);
+    walk_fix_add(ghi + 3 * cur + 1, glo + 3 * cur + 1, dy);
+    walk_fix_add(ghi + 3 * cur + 2, glo + 3 * cur + 2, dz);
+  }
+  sum = warp_sum(sum);
+  if ((tid & 31) == 0) red[tid >> 5] = sum;
+  __syncthreads();
+  if (tid == 0) {
+    float t = 0.f;
+    for (int w = 0; w < WALK_THREADS / 32; ++w) t += red[w];
+    atomicAdd(ws.acc + (size_t)b * ACC_NUM + ACC_CH_CLOUD, t);
+  }
+  const float coef = 2.f * d.w.w_ch / (float)P * WALK_UNFIX;
+  float *Ghm = ws.G_hm + (size_t)b * Vh * 3;
+  for (int i = tid; i < Vh * 3; i += blockDim.x) {
+    const long long g = ((long long)ghi[i] << 20) + (long long)glo[i];
+    if (g != 0) atomicAdd(Ghm + i, coef * (float)g);
   }
 }
 
@@ -432,6 +636,7 @@ __device__ __forceinline__ void h2c_fold(H2CBest &bst, unsigned d2bits, unsigned
 }
 
 __global__ void __launch_bounds__(H2C_THREADS) k_chamfer_h2c(foho_guidance_desc d, FohoWorkspace ws, FohoAccel acc) {
+  FohoTrace trace_(ws.trace, TR_H2C);
   const int b = blockIdx.y, Vh = d.Vh, P = d.P;
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   const int i = blockIdx.x * (H2C_THREADS / 32) + wid;
@@ -515,7 +720,7 @@ __global__ void __launch_bounds__(H2C_THREADS) k_chamfer_h2c(foho_guidance_desc 
 }  // namespace
 
 // ----------------------------------------------------------------------------- host side
-static inline void foho_accel_layout(FohoAccel &a, char *base, int B, int P) {
+void foho_accel_layout(FohoAccel &a, char *base, int B, int P) {
   size_t off = 0;
   auto take = [&](size_t bytes) { char *p = base ? base + off : nullptr; off += foho_align_up(bytes, 256); return p; };
   a.hand = (FohoAccelHand *)take(sizeof(FohoAccelHand) * (size_t)B);
@@ -530,6 +735,8 @@ static inline void foho_accel_layout(FohoAccel &a, char *base, int B, int P) {
   a.g_hi = (float4 *)take(sizeof(float4) * (size_t)B * a.NGcap);
   a.s_lo = (float4 *)take(sizeof(float4) * (size_t)B * a.NScap);
   a.s_hi = (float4 *)take(sizeof(float4) * (size_t)B * a.NScap);
+  a.face_sv = (int4 *)take(sizeof(int4) * (size_t)B * FOHO_ACCEL_FACES);
+  a.face_rank = (int *)take(sizeof(int) * (size_t)B * FOHO_ACCEL_FACES);
   a.seed_c2h = (int *)take(sizeof(int) * (size_t)B * (P > 0 ? P : 1));
   a.seed_h2c = (int *)take(sizeof(int) * (size_t)B * FOHO_ACCEL_HV);
   a.total = off;
@@ -554,6 +761,12 @@ extern "C" int foho_guidance_prepare_statics(const foho_guidance_desc *dp, void 
   cudaStream_t st = (cudaStream_t)cuda_stream;
   k_accel_hand<<<d.B, ACC_THREADS, 0, st>>>(d.hand_rest, d.Vh, a);
   FOHO_LAUNCH_CHECK();
+  if (d.hand_faces && d.Fh >= 1 && d.Fh <= FOHO_ACCEL_FACES) {
+    k_accel_faces<<<d.B, ACC_THREADS, 0, st>>>(d.hand_rest, d.hand_faces, d.Vh, d.Fh, a);
+    FOHO_LAUNCH_CHECK();
+  } else if (d.Fh >= 1 && d.Fh <= FOHO_ACCEL_FACES) {
+    return FOHO_E_NULL;          // evaluations with this accel would expect the face order
+  }
   k_accel_cloud_bbox<<<d.B, ACC_THREADS, 0, st>>>(d.cloud, d.P, a);
   FOHO_LAUNCH_CHECK();
   int gx = (a.P2 + 255) / 256;
@@ -583,14 +796,60 @@ extern "C" int foho_guidance_prepare_statics(const foho_guidance_desc *dp, void 
   return FOHO_OK;
 }
 
-int foho_launch_chamfer_accel(const foho_guidance_desc *dp, const FohoWorkspace &ws, cudaStream_t st) {
+int foho_launch_chamfer_h2c(const foho_guidance_desc *dp, const FohoWorkspace &ws, cudaStream_t st) {
   const foho_guidance_desc &d = *dp;
   FohoAccel a;
   foho_accel_layout(a, (char *)d.accel, d.B, d.P);
   if (a.total > d.accel_bytes) return FOHO_E_WORKSPACE;
   k_chamfer_h2c<<<dim3((d.Vh + H2C_THREADS / 32 - 1) / (H2C_THREADS / 32), d.B), H2C_THREADS, 0, st>>>(d, ws, a);
   FOHO_LAUNCH_CHECK();
+  return FOHO_OK;
+}
+
+int foho_launch_chamfer_c2h(const foho_guidance_desc *dp, const FohoWorkspace &ws, cudaStream_t st) {
+  const foho_guidance_desc &d = *dp;
+  FohoAccel a;
+  foho_accel_layout(a, (char *)d.accel, d.B, d.P);
+  if (a.total > d.accel_bytes) return FOHO_E_WORKSPACE;
+  if (d.hand_nbr_off && d.hand_nbr) {
+    if (d.nbr_stride < 8 || (d.nbr_stride & 7) != 0 || d.nbr_stride > 65535 * 64) return FOHO_E_ARG;
+    if (((uintptr_t)d.hand_nbr & 15) != 0) return FOHO_E_ARG;
+    // whole neighbour lists in shared memory: size for the worst case the stride allows
+    const size_t smem = foho_align_up((size_t)d.Vh * 40 + (size_t)(d.Vh + 1) * 4, 16) + (size_t)d.nbr_stride * 2;
+    if (smem > 200 * 1024) return FOHO_E_SHAPE;
+    static size_t attr = 0;
+    if (smem > attr) {
+      FOHO_CUDA_TRY(cudaFuncSetAttribute(k_chamfer_c2h_walk, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      FOHO_CUDA_TRY(cudaFuncSetAttribute(k_chamfer_c2h_walk, cudaFuncAttributePreferredSharedMemoryCarveout,
+                                         (int)cudaSharedmemCarveoutMaxShared));
+      attr = smem;
+    }
+    // At most one CTA per SM over the whole batch: beside the dense stream's two CTAs an SM has room
+    // for exactly one of these, and a grid that does not fit at once would hold back every kernel
+    // queued behind it.  Each CTA walks a contiguous chunk of the Morton-sorted cloud.
+    static int sm_count = 0;
+    if (sm_count == 0) {
+      int dev = 0;
+      FOHO_CUDA_TRY(cudaGetDevice(&dev));
+      FOHO_CUDA_TRY(cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev));
+    }
+    int gx = sm_count / d.B;
+    if (gx < 1) gx = 1;
+    int chunk = (d.P + gx - 1) / gx;
+    chunk = (chunk + WALK_THREADS - 1) / WALK_THREADS * WALK_THREADS;
+    if (chunk > WALK_MAX_CHUNK) chunk = WALK_MAX_CHUNK;               // overflow bound of the fixed-point sums
+    gx = (d.P + chunk - 1) / chunk;
+    k_chamfer_c2h_walk<<<dim3(gx, d.B), WALK_THREADS, smem, st>>>(d, ws, a, chunk);
+    FOHO_LAUNCH_CHECK();
+    return FOHO_OK;
+  }
   const int NG = (d.P + 31) / 32;
+  static bool carve = false;
+  if (!carve) {
+    FOHO_CUDA_TRY(cudaFuncSetAttribute(k_chamfer_c2h, cudaFuncAttributePreferredSharedMemoryCarveout,
+                                       (int)cudaSharedmemCarveoutMaxShared));
+    carve = true;
+  }
   k_chamfer_c2h<<<dim3((NG + C2H_GROUPS_PER_CTA - 1) / C2H_GROUPS_PER_CTA, d.B), C2H_THREADS, 0, st>>>(d, ws, a);
   FOHO_LAUNCH_CHECK();
   return FOHO_OK;

@@ -18,6 +18,7 @@ namespace {
 
 // ----------------------------------------------------------------------------- k_prep
 __global__ void __launch_bounds__(256) k_prep(foho_guidance_desc d, FohoWorkspace ws) {
+  FohoTrace trace_(ws.trace, TR_PREP);
   __shared__ FohoFrame fr;
   __shared__ float red[6 * 32];
   const int b = blockIdx.x, tid = threadIdx.x, Vh = d.Vh, D = d.D;
@@ -125,18 +126,31 @@ __global__ void __launch_bounds__(256) k_prep(foho_guidance_desc d, FohoWorkspac
 }
 
 // ----------------------------------------------------------------------------- k_raster
-// one thread per hand face: XOR the "below the crossing" prefix into every column the
-// face's xy-projection covers (rule: foho_math.cuh::column_hits_triangle).
-__global__ void __launch_bounds__(128) k_raster(foho_guidance_desc d, FohoWorkspace ws) {
-  const int b = blockIdx.y, f = blockIdx.x * blockDim.x + threadIdx.x, D = d.D;
+// one warp per hand face, lanes over the columns of the face's xy bounding box: XOR the "below the
+// crossing" prefix into every column the projection covers (rule: foho_math.cuh::column_hits_triangle).
+// (A thread per face leaves the few large faces -- the wrist cap fan -- as a long serial tail.)
+constexpr int RASTER_THREADS = 256;
+__global__ void __launch_bounds__(RASTER_THREADS) k_raster(foho_guidance_desc d, FohoWorkspace ws, const int *__restrict__ face_rank) {
+  FohoTrace trace_(ws.trace, TR_RASTER);
+  const int b = blockIdx.y, D = d.D, lane = threadIdx.x & 31;
+  const int f = blockIdx.x * (RASTER_THREADS / 32) + (threadIdx.x >> 5);
   if (f >= d.Fh) return;
   const FohoFrame &fr = ws.frames[b];
-  if (fr.hi[0] < fr.lo[0] || fr.hi[1] < fr.lo[1] || fr.hi[2] < fr.lo[2]) return;
   const float *hg = ws.hg + (size_t)b * d.Vh * 3;
   const int ia = d.hand_faces[3 * f], ib = d.hand_faces[3 * f + 1], ic = d.hand_faces[3 * f + 2];
   const foho_f3 a = f3(hg[3 * ia], hg[3 * ia + 1], hg[3 * ia + 2]);
   const foho_f3 bb = f3(hg[3 * ib], hg[3 * ib + 1], hg[3 * ib + 2]);
   const foho_f3 c = f3(hg[3 * ic], hg[3 * ic + 1], hg[3 * ic + 2]);
+  if (lane == 0) {
+    // bounding sphere of the face for k_voxdist's culling
+    const foho_f3 m = (1.f / 3.f) * (a + bb + c);
+    const foho_f3 da = a - m, db = bb - m, dc = c - m;
+    const float r2 = fmaxf(dot3(da, da), fmaxf(dot3(db, db), dot3(dc, dc)));
+    // with the per-image face order (accel) the sphere goes to the face's position in that order
+    const int slot = face_rank ? face_rank[(size_t)b * FOHO_ACCEL_FACES + f] : f;
+    ws.sph[(size_t)b * d.Fh + slot] = make_float4(m.x, m.y, m.z, sqrtf(r2) * 1.00001f + 1e-6f);
+  }
+  if (fr.hi[0] < fr.lo[0] || fr.hi[1] < fr.lo[1] || fr.hi[2] < fr.lo[2]) return;
   float fxmin = ceilf(fminf(a.x, fminf(bb.x, c.x))), fxmax = floorf(fmaxf(a.x, fmaxf(bb.x, c.x)));
   float fymin = ceilf(fminf(a.y, fminf(bb.y, c.y))), fymax = floorf(fmaxf(a.y, fmaxf(bb.y, c.y)));
   if (!(fxmin <= fxmax) || !(fymin <= fymax)) return;
@@ -144,23 +158,28 @@ __global__ void __launch_bounds__(128) k_raster(foho_guidance_desc d, FohoWorksp
   int xmax = fxmax >= (float)(D - 1) ? D - 1 : (fxmax < 0.f ? -1 : (int)fxmax);
   int ymin = fymin <= 0.f ? 0 : (fymin >= (float)D ? D : (int)fymin);
   int ymax = fymax >= (float)(D - 1) ? D - 1 : (fymax < 0.f ? -1 : (int)fymax);
+  const int nx = xmax - xmin + 1, ny = ymax - ymin + 1;
+  if (nx <= 0 || ny <= 0) return;
   uint32_t *par = ws.parity + (size_t)b * D * D * ws.W;
-  for (int X = xmin; X <= xmax; ++X)
-    for (int Y = ymin; Y <= ymax; ++Y) {
-      float zc;
-      if (!column_hits_triangle(ia, ib, ic, a, bb, c, (float)X, (float)Y, &zc)) continue;
-      int nz = count_below(zc, D);
-      if (nz <= 0) continue;
-      uint32_t *col = par + ((size_t)X * D + Y) * ws.W;
-      int full = nz >> 5, rem = nz & 31;
-      for (int w = 0; w < full; ++w) atomicXor(col + w, 0xFFFFFFFFu);
-      if (rem) atomicXor(col + full, (1u << rem) - 1u);
-    }
+  for (int k = lane; k < nx * ny; k += 32) {
+    const int X = xmin + k / ny, Y = ymin + k % ny;
+    float zc;
+    if (!column_hits_triangle(ia, ib, ic, a, bb, c, (float)X, (float)Y, &zc)) continue;
+    int nz = count_below(zc, D);
+    if (nz <= 0) continue;
+    uint32_t *col = par + ((size_t)X * D + Y) * ws.W;
+    int full = nz >> 5, rem = nz & 31;
+    for (int w = 0; w < full; ++w) atomicXor(col + w, 0xFFFFFFFFu);
+    if (rem) atomicXor(col + full, (1u << rem) - 1u);
+  }
 }
 
 // ----------------------------------------------------------------------------- k_compact
+// one warp per (column, 32-voxel word) of the hand's lattice bbox; lane z owns bit z: one coalesced
+// 128-byte read of S per word that has any bit set, one slot reservation per warp.
 __global__ void __launch_bounds__(256) k_compact(foho_guidance_desc d, FohoWorkspace ws) {
-  const int b = blockIdx.y, D = d.D;
+  FohoTrace trace_(ws.trace, TR_COMPACT);
+  const int b = blockIdx.y, D = d.D, lane = threadIdx.x & 31;
   const FohoFrame &fr = ws.frames[b];
   const int nx = fr.hi[0] - fr.lo[0] + 1, ny = fr.hi[1] - fr.lo[1] + 1;
   if (nx <= 0 || ny <= 0 || fr.hi[2] < fr.lo[2]) return;
@@ -168,19 +187,38 @@ __global__ void __launch_bounds__(256) k_compact(foho_guidance_desc d, FohoWorks
   const float *S = d.sdf + (size_t)b * D * D * D;
   int *cnt = ws.cnt + (size_t)b * CNT_NUM;
   int *cand = ws.cand + (size_t)b * ws.cap;
-  const int items = nx * ny * ws.W;
-  for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < items; k += gridDim.x * blockDim.x) {
-    int w = k % ws.W, c = k / ws.W;
-    int X = fr.lo[0] + c / ny, Y = fr.lo[1] + c % ny;
-    uint32_t bits = par[((size_t)X * D + Y) * ws.W + w];
-    while (bits) {
-      int z = __ffs(bits) - 1;
-      bits &= bits - 1;
-      int Z = w * 32 + z;
-      if (Z >= D) break;
-      int v = (X * D + Y) * D + Z;
-      if (S[v] < 0.f) {
-        int slot = atomicAdd(cnt + CNT_NCAND, 1);
+  // no crossing lies above the bbox, so words above hi[2] hold no bits (an OPEN mesh leaves bits all
+  // the way down below a hole, so the scan starts at word 0)
+  const int w0 = 0, w1 = fr.hi[2] >> 5, nw = w1 - w0 + 1;
+  const int items = nx * ny * nw;
+  const int warps = (gridDim.x * blockDim.x) >> 5;
+  // each lane fetches one word (32 independent loads per round), then the warp serves the non-zero ones
+  for (int base = ((blockIdx.x * blockDim.x + threadIdx.x) >> 5) * 32; base < items; base += warps * 32) {
+    const int k = base + lane;
+    uint32_t word = 0u;
+    int col = 0, wz = 0;
+    if (k < items) {
+      wz = w0 + k % nw;
+      const int c = k / nw;
+      col = (fr.lo[0] + c / ny) * D + (fr.lo[1] + c % ny);
+      word = par[(size_t)col * ws.W + wz];
+    }
+    unsigned todo = __ballot_sync(0xffffffffu, word != 0u);
+    while (todo) {
+      const int src = __ffs(todo) - 1;
+      todo &= todo - 1;
+      const uint32_t bits = __shfl_sync(0xffffffffu, word, src);
+      const int ccol = __shfl_sync(0xffffffffu, col, src), cw = __shfl_sync(0xffffffffu, wz, src);
+      const int Z = cw * 32 + lane;
+      const int v = ccol * D + Z;
+      const bool hit = ((bits >> lane) & 1u) && Z < D && S[v] < 0.f;
+      const unsigned m = __ballot_sync(0xffffffffu, hit);
+      if (m == 0u) continue;
+      int slot0 = 0;
+      if (lane == 0) slot0 = atomicAdd(cnt + CNT_NCAND, __popc(m));
+      slot0 = __shfl_sync(0xffffffffu, slot0, 0);
+      if (hit) {
+        const int slot = slot0 + __popc(m & ((1u << lane) - 1u));
         if (slot < ws.cap) cand[slot] = v;
         else atomicOr(cnt + CNT_FLAGS, 1);
       }
@@ -192,31 +230,19 @@ __global__ void __launch_bounds__(256) k_compact(foho_guidance_desc d, FohoWorks
 // one warp per candidate voxel: nearest-vertex upper bound, then bounding-sphere culled
 // exact closest point over the faces.
 __global__ void __launch_bounds__(256) k_voxdist(foho_guidance_desc d, FohoWorkspace ws) {
-  extern __shared__ __align__(16) unsigned char sm_raw[];
+  FohoTrace trace_(ws.trace, TR_VOXDIST);
   const int b = blockIdx.y, D = d.D, Vh = d.Vh, Fh = d.Fh;
   const int *cnt = ws.cnt + (size_t)b * CNT_NUM;
   int n = cnt[CNT_NCAND];
   if (n > ws.cap) n = ws.cap;
   const int warps_per_cta = blockDim.x >> 5;
   if ((int)(blockIdx.x * warps_per_cta) >= n) return;
-  float4 *sph = reinterpret_cast<float4 *>(sm_raw);                  // [Fh] centroid + radius
-  float *sv = reinterpret_cast<float *>(sph + Fh);                   // [Vh*3]
-  int *sf = reinterpret_cast<int *>(sv + 3 * Vh);                    // [Fh*3]
-  const float *hg = ws.hg + (size_t)b * Vh * 3;
-  for (int i = threadIdx.x; i < 3 * Vh; i += blockDim.x) sv[i] = hg[i];
-  for (int i = threadIdx.x; i < 3 * Fh; i += blockDim.x) sf[i] = d.hand_faces[i];
-  __syncthreads();
-  for (int f = threadIdx.x; f < Fh; f += blockDim.x) {
-    int ia = sf[3 * f], ib = sf[3 * f + 1], ic = sf[3 * f + 2];
-    foho_f3 a = f3(sv[3 * ia], sv[3 * ia + 1], sv[3 * ia + 2]);
-    foho_f3 bb = f3(sv[3 * ib], sv[3 * ib + 1], sv[3 * ib + 2]);
-    foho_f3 c = f3(sv[3 * ic], sv[3 * ic + 1], sv[3 * ic + 2]);
-    foho_f3 m = (1.f / 3.f) * (a + bb + c);
-    foho_f3 da = a - m, db = bb - m, dc = c - m;
-    float r2 = fmaxf(dot3(da, da), fmaxf(dot3(db, db), dot3(dc, dc)));
-    sph[f] = make_float4(m.x, m.y, m.z, sqrtf(r2) * 1.00001f + 1e-6f);
-  }
-  __syncthreads();
+  // hand geometry straight from global memory: 9 KB of vertices, 25 KB of face spheres (written by
+  // k_raster) and 18 KB of indices per sample stay in L1/L2; no per-CTA staging, no shared memory, so
+  // the kernel fits beside the dense stream's CTAs.
+  const float4 *__restrict__ sph = ws.sph + (size_t)b * Fh;
+  const float *__restrict__ sv = ws.hg + (size_t)b * Vh * 3;
+  const int *__restrict__ sf = d.hand_faces;
   const FohoFrame &fr = ws.frames[b];
   const float kappa = fr.kappa;
   const float N = (float)D * (float)D * (float)D;
@@ -298,6 +324,7 @@ constexpr int CH_THREADS = 256;
 constexpr int CH_POINTS_PER_CTA = 2048;
 
 __global__ void __launch_bounds__(CH_THREADS) k_chamfer(foho_guidance_desc d, FohoWorkspace ws) {
+  FohoTrace trace_(ws.trace, TR_CHAMFER);
   extern __shared__ __align__(16) unsigned char sm_raw[];
   const int b = blockIdx.y, Vh = d.Vh, P = d.P;
   float4 *sh = reinterpret_cast<float4 *>(sm_raw);                               // [Vh]
@@ -385,72 +412,86 @@ constexpr int FIN_NRED = FOHO_FIN_NRED;
 __constant__ int c_tips[5] = {744, 320, 443, 554, 671};                          // pipelines.py:127
 __constant__ int c_openpose[21] = {0, 13, 14, 15, 16, 1, 2, 3, 17, 4, 5, 6, 18, 10, 11, 12, 19, 7, 8, 9, 20};  // :128
 
+// k_keypoints (REF a11, pipelines.py:121-135, 1490-1495): regressed + fingertip key-points, their
+// screen projection, the MSE against the HaMeR 2-D key-points and its gradient w.r.t. the 21 3-D
+// key-points.  Needs only k_prep's output, so it runs early on a side stream; k_finalize_verts picks
+// up ws.kpbuf = [21*3 gradient | loss].
+constexpr int KP_THREADS = 512;
+__global__ void __launch_bounds__(KP_THREADS) k_keypoints(foho_guidance_desc d, FohoWorkspace ws) {
+  FohoTrace trace_(ws.trace, TR_KP);
+  __shared__ float kp3[21][3];     // concatenated order: 16 regressed + 5 tips
+  __shared__ float kpl[21];
+  const int b = blockIdx.x, tid = threadIdx.x, Vh = d.Vh;
+  const int lane = tid & 31, wid = tid >> 5;
+  const FohoFrame &fr = ws.frames[b];
+  const float *hmc = ws.hmc + (size_t)b * Vh * 3;
+  float *out = ws.kpbuf + (size_t)b * 64;
+  const float co[3] = {fr.co[0], fr.co[1], fr.co[2]};
+  if (wid < 16) {
+    const float *J = d.j_regressor + (size_t)wid * Vh;
+    float sx = 0.f, sy = 0.f, sz = 0.f, sw = 0.f;
+#pragma unroll 8
+    for (int i = lane; i < Vh; i += 32) {
+      const float w = J[i];
+      sx = fmaf(w, hmc[3 * i], sx); sy = fmaf(w, hmc[3 * i + 1], sy); sz = fmaf(w, hmc[3 * i + 2], sz);
+      sw += w;
+    }
+    sx = warp_sum(sx); sy = warp_sum(sy); sz = warp_sum(sz); sw = warp_sum(sw);
+    // rows of J sum to 1 for MANO but do not rely on it: add c_o * sum(J)
+    if (lane == 0) { kp3[wid][0] = sx + sw * co[0]; kp3[wid][1] = sy + sw * co[1]; kp3[wid][2] = sz + sw * co[2]; }
+  }
+  if (tid < 5) {
+    int i = c_tips[tid];
+    kp3[16 + tid][0] = hmc[3 * i] + co[0]; kp3[16 + tid][1] = hmc[3 * i + 1] + co[1]; kp3[16 + tid][2] = hmc[3 * i + 2] + co[2];
+  }
+  __syncthreads();
+  if (tid < 21) {
+    const int c = c_openpose[tid];                 // out[tid] = cat[c]
+    const float x = kp3[c][0], y = kp3[c][1], z = kp3[c][2];
+    const float th = tanf(d.fov_deg * 0.017453292519943295f * 0.5f);
+    const float H = (float)d.image_h, W = (float)d.image_w;
+    const float sc = fminf(H, W) * 0.5f;
+    const float xv = -x, yv = y, zv = -z;
+    const float iz = 1.f / (zv * th);
+    const float u = W * 0.5f - sc * xv * iz, v = H * 0.5f - sc * yv * iz;
+    const float *t = d.kps_2d + ((size_t)b * 21 + tid) * 2;
+    const float du = u - t[0], dv = v - t[1];
+    kpl[tid] = (du * du + dv * dv) / 42.f;
+    const float wk = d.w.w_hand * d.w.w_kp * 2.f / 42.f;
+    const float gu = wk * du, gv = wk * dv;
+    // u = W/2 + sc x/(zv th) ; v = H/2 - sc y/(zv th) ; zv = -z
+    out[3 * c] = gu * sc * iz;
+    out[3 * c + 1] = -gv * sc * iz;
+    out[3 * c + 2] = (gu * (-sc * xv * iz / zv) + gv * (-sc * yv * iz / zv));
+  }
+  __syncthreads();
+  if (tid == 0) {
+    float t = 0.f;
+    for (int k = 0; k < 21; ++k) t += kpl[k];
+    out[63] = t;
+  }
+}
+
 // k_finalize_verts: everything per hand vertex (runs beside the dense stream: it neither reads the
 // stream's moments nor writes G -- its dE/dS corner contributions go to ws.tri_* and are applied by
 // k_assemble once the stream has written G).
 __global__ void __launch_bounds__(FIN_THREADS) k_finalize_verts(foho_guidance_desc d, FohoWorkspace ws) {
+  FohoTrace trace_(ws.trace, TR_FIN);
   __shared__ FohoFrame fr;
   __shared__ float red[FIN_NRED * 32];
-  __shared__ float kp3[21][3];     // concatenated order: 16 regressed + 5 tips
   __shared__ float gkp[21][3];     // dE/dkp3 in concatenated order
-  __shared__ float kp_loss;
   const int b = blockIdx.x, tid = threadIdx.x, Vh = d.Vh, D = d.D;
-  const int lane = tid & 31, wid = tid >> 5;
+  const bool use_kp = d.n_joints == 16 && d.j_regressor && d.kps_2d && Vh > 744;
   {
     const int nwords = sizeof(FohoFrame) / 4;
     const uint32_t *src = reinterpret_cast<const uint32_t *>(ws.frames + b);
     uint32_t *dst = reinterpret_cast<uint32_t *>(&fr);
     for (int k = tid; k < nwords; k += blockDim.x) dst[k] = src[k];
   }
-  if (tid < 63) (&gkp[0][0])[tid] = 0.f;
-  if (tid == 0) kp_loss = 0.f;
+  if (tid < 63) (&gkp[0][0])[tid] = use_kp ? ws.kpbuf[(size_t)b * 64 + tid] : 0.f;
   __syncthreads();
   const float *hmc = ws.hmc + (size_t)b * Vh * 3;
   const float *hg = ws.hg + (size_t)b * Vh * 3;
-  const bool use_kp = d.n_joints == 16 && d.j_regressor && d.kps_2d && Vh > 744;
-
-  // ---- a11 key-points (pipelines.py:121-135, 1490-1495)
-  if (use_kp) {
-    if (wid < 16) {
-      const float *J = d.j_regressor + (size_t)wid * Vh;
-      float sx = 0.f, sy = 0.f, sz = 0.f;
-      for (int i = lane; i < Vh; i += 32) {
-        float w = J[i];
-        sx = fmaf(w, hmc[3 * i], sx); sy = fmaf(w, hmc[3 * i + 1], sy); sz = fmaf(w, hmc[3 * i + 2], sz);
-      }
-      sx = warp_sum(sx); sy = warp_sum(sy); sz = warp_sum(sz);
-      // rows of J sum to 1 for MANO but do not rely on it: add c_o * sum(J)
-      float sw = 0.f;
-      for (int i = lane; i < Vh; i += 32) sw += J[i];
-      sw = warp_sum(sw);
-      if (lane == 0) { kp3[wid][0] = sx + sw * fr.co[0]; kp3[wid][1] = sy + sw * fr.co[1]; kp3[wid][2] = sz + sw * fr.co[2]; }
-    }
-    if (tid < 5) {
-      int i = c_tips[tid];
-      kp3[16 + tid][0] = hmc[3 * i] + fr.co[0]; kp3[16 + tid][1] = hmc[3 * i + 1] + fr.co[1]; kp3[16 + tid][2] = hmc[3 * i + 2] + fr.co[2];
-    }
-    __syncthreads();
-    if (tid < 21) {
-      const int c = c_openpose[tid];                 // out[tid] = cat[c]
-      const float x = kp3[c][0], y = kp3[c][1], z = kp3[c][2];
-      const float th = tanf(d.fov_deg * 0.017453292519943295f * 0.5f);
-      const float H = (float)d.image_h, W = (float)d.image_w;
-      const float sc = fminf(H, W) * 0.5f;
-      const float xv = -x, yv = y, zv = -z;
-      const float iz = 1.f / (zv * th);
-      const float u = W * 0.5f - sc * xv * iz, v = H * 0.5f - sc * yv * iz;
-      const float *t = d.kps_2d + ((size_t)b * 21 + tid) * 2;
-      const float du = u - t[0], dv = v - t[1];
-      atomicAdd(&kp_loss, (du * du + dv * dv) / 42.f);
-      const float wk = d.w.w_hand * d.w.w_kp * 2.f / 42.f;
-      const float gu = wk * du, gv = wk * dv;
-      // u = W/2 + sc x/(zv th) ; v = H/2 - sc y/(zv th) ; zv = -z
-      gkp[c][0] = gu * sc * iz;
-      gkp[c][1] = -gv * sc * iz;
-      gkp[c][2] = (gu * (-sc * xv * iz / zv) + gv * (-sc * yv * iz / zv));
-    }
-    __syncthreads();
-  }
 
   // ---- per-vertex pass
   float acc[FIN_NRED];
@@ -575,7 +616,7 @@ __global__ void __launch_bounds__(FIN_THREADS) k_finalize_verts(foho_guidance_de
   block_sum<FIN_NRED>(acc, red);
   if (tid == 0) {
     float *fa = ws.fin_acc + (size_t)b * FIN_NRED;
-    acc[29] = use_kp ? kp_loss : 0.f;
+    acc[29] = use_kp ? ws.kpbuf[(size_t)b * 64 + 63] : 0.f;
 #pragma unroll
     for (int k = 0; k < FIN_NRED; ++k) fa[k] = acc[k];
   }
@@ -586,6 +627,7 @@ __global__ void __launch_bounds__(FIN_THREADS) k_finalize_verts(foho_guidance_de
 // stream moments and the vertex sums into the 16 leaf gradients and the loss terms.
 constexpr int ASM_THREADS = 256;
 __global__ void __launch_bounds__(ASM_THREADS) k_assemble(foho_guidance_desc d, FohoWorkspace ws, int stream_gx, int do_voxels) {
+  FohoTrace trace_(ws.trace, TR_ASM);
   const int b = blockIdx.y, tid = threadIdx.x, Vh = d.Vh, D = d.D;
   float *G = d.grad_sdf + (size_t)b * D * D * D;
   {
@@ -697,11 +739,11 @@ __global__ void __launch_bounds__(ASM_THREADS) k_assemble(foho_guidance_desc d, 
 }  // namespace
 
 // ----------------------------------------------------------------------------- fork/join context
-// Two high-priority side streams + four events per device, created on first use (do the first call
+// Three high-priority side streams + five events per device, created on first use (do the first call
 // outside a stream capture).  A mutex serialises callers that share them.
 struct ForkCtx {
-  cudaStream_t side[2];
-  cudaEvent_t fork, prep, join_a, join_b;
+  cudaStream_t side[3];
+  cudaEvent_t fork, prep, join_a, join_b, join_c;
   std::mutex mu;
 };
 static ForkCtx *fork_ctx() {
@@ -715,11 +757,12 @@ static ForkCtx *fork_ctx() {
     int lo = 0, hi = 0;
     cudaDeviceGetStreamPriorityRange(&lo, &hi);      // hi = numerically lowest = highest priority
     bool ok = true;
-    for (int i = 0; i < 2; ++i) ok = ok && cudaStreamCreateWithPriority(&c->side[i], cudaStreamNonBlocking, hi) == cudaSuccess;
+    for (int i = 0; i < 3; ++i) ok = ok && cudaStreamCreateWithPriority(&c->side[i], cudaStreamNonBlocking, hi) == cudaSuccess;
     ok = ok && cudaEventCreateWithFlags(&c->fork, cudaEventDisableTiming) == cudaSuccess;
     ok = ok && cudaEventCreateWithFlags(&c->prep, cudaEventDisableTiming) == cudaSuccess;
     ok = ok && cudaEventCreateWithFlags(&c->join_a, cudaEventDisableTiming) == cudaSuccess;
     ok = ok && cudaEventCreateWithFlags(&c->join_b, cudaEventDisableTiming) == cudaSuccess;
+    ok = ok && cudaEventCreateWithFlags(&c->join_c, cudaEventDisableTiming) == cudaSuccess;
     if (!ok) { delete c; return nullptr; }
     ctx[dev] = c;
   }
@@ -773,6 +816,7 @@ extern "C" int foho_guidance_energy_fwd_bwd(const foho_guidance_desc *dp, void *
   FohoWorkspace ws;
   foho_ws_layout(ws, (char *)d.workspace, d.B, d.D, d.Vh, d.Fh, d.P, d.Vo_total);
   if (ws.total > d.workspace_bytes) return FOHO_E_WORKSPACE;
+  ws.trace = (unsigned long long *)d.trace;
   cudaStream_t st = (cudaStream_t)cuda_stream;
 
   const int sm = d.stage_mask == 0 ? 0x3f : d.stage_mask;
@@ -781,20 +825,22 @@ extern "C" int foho_guidance_energy_fwd_bwd(const foho_guidance_desc *dp, void *
   int gx = last_gx;
 
   // Stream layout.  overlap: the dense stream depends on nothing but the inputs, so it starts at once
-  // on the caller's stream while k_prep and the sparse chain run on two library-owned side streams:
-  //   caller : fork ------------------ k_stream -------------------------- wait(A) k_assemble [obj post]
-  //   side A : wait(fork) k_prep rec(P) k_chamfer_*      wait(B) [obj pre] k_finalize_verts rec(A)
+  // on the caller's stream while k_prep and the sparse chains run on three library-owned side streams:
+  //   caller : fork ------------------ k_stream --------------------------------- wait(A) k_assemble [obj post]
+  //   side A : wait(fork) k_prep rec(P) k_chamfer_c2h      wait(B) wait(C) [obj pre] k_finalize_verts rec(A)
   //   side B :                  wait(P) k_raster k_compact k_voxdist rec(B)
+  //   side C :                  wait(P) k_keypoints k_chamfer_h2c rec(C)
   // Only event record / wait is used, so the same sequence is legal inside a stream capture.
   ForkCtx *fc = nullptr;
-  cudaStream_t sa = st, sb = st;
+  cudaStream_t sa = st, sb = st, sc = st;
   if (overlap) {
     fc = fork_ctx();
     if (!fc) return (int)cudaGetLastError();
-    sa = fc->side[0]; sb = fc->side[1];
+    sa = fc->side[0]; sb = fc->side[1]; sc = fc->side[2];
     fc->mu.lock();
   }
   struct Unlock { ForkCtx *f; ~Unlock() { if (f) f->mu.unlock(); } } unlock{fc};
+  const bool use_kp = d.n_joints == 16 && d.j_regressor && d.kps_2d && d.Vh > 744;
 
   if (overlap) {
     FOHO_CUDA_TRY(cudaEventRecord(fc->fork, st));
@@ -807,32 +853,18 @@ extern "C" int foho_guidance_energy_fwd_bwd(const foho_guidance_desc *dp, void *
   if (overlap) {
     FOHO_CUDA_TRY(cudaEventRecord(fc->prep, sa));
     FOHO_CUDA_TRY(cudaStreamWaitEvent(sb, fc->prep, 0));
+    FOHO_CUDA_TRY(cudaStreamWaitEvent(sc, fc->prep, 0));
   }
   if (sm & 2) {
     int rc = foho_launch_stream(dp, ws, &gx, overlap, st);
     if (rc != FOHO_OK) return rc;
     last_gx = gx;
   }
-  if (sm & 8) {
-    k_raster<<<dim3((d.Fh + 127) / 128, d.B), 128, 0, sb>>>(d, ws);
-    FOHO_LAUNCH_CHECK();
-    k_compact<<<dim3(16, d.B), 256, 0, sb>>>(d, ws);
-    FOHO_LAUNCH_CHECK();
-    const size_t smem = (size_t)d.Fh * 16 + (size_t)d.Vh * 12 + (size_t)d.Fh * 12;
-    if (smem > 200 * 1024) return FOHO_E_SHAPE;
-    static size_t attr = 0;
-    if (smem > 48 * 1024 && smem > attr) {
-      FOHO_CUDA_TRY(cudaFuncSetAttribute(k_voxdist, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      attr = smem;
-    }
-    k_voxdist<<<dim3(64, d.B), 256, smem, sb>>>(d, ws);
-    FOHO_LAUNCH_CHECK();
-  }
-  if (overlap) FOHO_CUDA_TRY(cudaEventRecord(fc->join_b, sb));
-  if ((sm & 4) && d.P > 0 && d.accel) {
+  const bool accel = (sm & 4) && d.P > 0 && d.accel;
+  if (accel) {
     if (d.Vh > FOHO_ACCEL_HV) return FOHO_E_SHAPE;
     if (((uintptr_t)d.accel & 255) != 0) return FOHO_E_WORKSPACE;
-    int rc = foho_launch_chamfer_accel(dp, ws, sa);
+    int rc = foho_launch_chamfer_c2h(dp, ws, sa);
     if (rc != FOHO_OK) return rc;
   } else if ((sm & 4) && d.P > 0) {
     const size_t smem = (size_t)d.Vh * (16 + 8 + 12);
@@ -846,7 +878,42 @@ extern "C" int foho_guidance_energy_fwd_bwd(const foho_guidance_desc *dp, void *
     k_chamfer<<<dim3(nchunk, d.B), CH_THREADS, smem, sa>>>(d, ws);
     FOHO_LAUNCH_CHECK();
   }
-  if (overlap) FOHO_CUDA_TRY(cudaStreamWaitEvent(sa, fc->join_b, 0));
+  if (sm & 8) {
+    const bool face_tree = d.accel && d.Fh <= FOHO_ACCEL_FACES;
+    const int *face_rank = nullptr;
+    if (face_tree) {
+      if (((uintptr_t)d.accel & 255) != 0) return FOHO_E_WORKSPACE;
+      FohoAccel a;
+      foho_accel_layout(a, (char *)d.accel, d.B, d.P);
+      if (a.total > d.accel_bytes) return FOHO_E_WORKSPACE;
+      face_rank = a.face_rank;
+    }
+    k_raster<<<dim3((d.Fh + RASTER_THREADS / 32 - 1) / (RASTER_THREADS / 32), d.B), RASTER_THREADS, 0, sb>>>(d, ws, face_rank);
+    FOHO_LAUNCH_CHECK();
+    k_compact<<<dim3(32, d.B), 256, 0, sb>>>(d, ws);
+    FOHO_LAUNCH_CHECK();
+    if (face_tree) {
+      int rc = foho_launch_voxdist_tree(dp, ws, sb);
+      if (rc != FOHO_OK) return rc;
+    } else {
+      k_voxdist<<<dim3(64, d.B), 256, 0, sb>>>(d, ws);
+      FOHO_LAUNCH_CHECK();
+    }
+  }
+  if (overlap) FOHO_CUDA_TRY(cudaEventRecord(fc->join_b, sb));
+  if ((sm & 16) && use_kp) {
+    k_keypoints<<<d.B, KP_THREADS, 0, sc>>>(d, ws);
+    FOHO_LAUNCH_CHECK();
+  }
+  if (accel) {
+    int rc = foho_launch_chamfer_h2c(dp, ws, sc);
+    if (rc != FOHO_OK) return rc;
+  }
+  if (overlap) {
+    FOHO_CUDA_TRY(cudaEventRecord(fc->join_c, sc));
+    FOHO_CUDA_TRY(cudaStreamWaitEvent(sa, fc->join_b, 0));
+    FOHO_CUDA_TRY(cudaStreamWaitEvent(sa, fc->join_c, 0));
+  }
   const bool obj_mesh = (sm & 32) && d.Vo_total > 0;
   if (obj_mesh) {
     int rc = foho_launch_objmesh_pre(dp, ws, sa);

@@ -43,6 +43,7 @@ __device__ __forceinline__ StreamCoef load_coef(const FohoFrame &fr, float cN) {
 struct StreamSrc {
   const float *theta, *T_h2m, *obj_center;
   float bound;
+  unsigned long long *trace;
 };
 __device__ __forceinline__ StreamCoef stream_coef(const StreamSrc &src, int b, int D, float cN, StreamCoef *sc) {
   if (threadIdx.x == 0) {
@@ -109,6 +110,7 @@ constexpr int LDG_UNROLL = 4;
 __global__ void __launch_bounds__(LDG_THREADS) k_stream_ldg(const float *__restrict__ sdf, float *__restrict__ grad,
                                                             const StreamSrc src,
                                                             float *__restrict__ partials, int D, int logD, float cN) {
+  FohoTrace trace_(src.trace, TR_STREAM);
   __shared__ float red[6 * 32];
   __shared__ StreamCoef sc;
   const int b = blockIdx.y;
@@ -154,7 +156,7 @@ constexpr int TMA_THREADS = 256;
 constexpr int TMA_F4_PER_THREAD = 4;                                  // 16 KB tiles
 constexpr int TMA_TILE_F4 = TMA_THREADS * TMA_F4_PER_THREAD;          // 1024 float4
 constexpr int TMA_TILE_BYTES = TMA_TILE_F4 * 16;
-constexpr int TMA_MAX_STAGES = 8;   // ring depth and prefetch distance are launch parameters
+constexpr int TMA_MAX_STAGES = 13;   // ring depth and prefetch distance are launch parameters
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
@@ -197,6 +199,7 @@ __global__ void __launch_bounds__(TMA_THREADS, 2) k_stream_tma(const float *__re
                                                                const StreamSrc src,
                                                                float *__restrict__ partials, int D, int logD, float cN,
                                                                int nstages, int nprefetch) {
+  FohoTrace trace_(src.trace, TR_STREAM);
   __shared__ StreamCoef sc;
   __shared__ uint64_t full[TMA_MAX_STAGES];
   __shared__ float red[6 * 32];
@@ -287,6 +290,7 @@ __global__ void __launch_bounds__(TMA_THREADS, 2) k_stream_tma(const float *__re
 __global__ void __launch_bounds__(256) k_stream_any(const float *__restrict__ sdf, float *__restrict__ grad,
                                                     const StreamSrc src, float *__restrict__ partials,
                                                     int D, float cN) {
+  FohoTrace trace_(src.trace, TR_STREAM);
   __shared__ float red[6 * 32];
   __shared__ StreamCoef sc;
   const int b = blockIdx.y;
@@ -329,7 +333,7 @@ int ilog2_exact(int D) {
 
 }  // namespace
 
-int foho_launch_stream(const foho_guidance_desc *d, const FohoWorkspace &ws, int *grid_x_out, bool shared_sm, cudaStream_t st) {
+int foho_launch_stream(const foho_guidance_desc *d, const FohoWorkspace &ws, int *grid_x_out, bool /*shared_sm*/, cudaStream_t st) {
   static int sm_count = 0;
   if (sm_count == 0) {
     int dev = 0;
@@ -343,27 +347,37 @@ int foho_launch_stream(const foho_guidance_desc *d, const FohoWorkspace &ws, int
   int variant = d->stream_variant;
   StreamSrc src;
   src.theta = d->theta; src.T_h2m = d->T_h2m; src.obj_center = d->obj_center; src.bound = d->bound;
+  src.trace = ws.trace;
   const bool pow2 = logD >= 3 && D <= 1024;       // needs >= 2 float4 per row
   if (!pow2) variant = 3;
   else if (variant == 0) variant = 2;
   int gx;
   if (variant == 2) {
-    // ring depth: 6 stages / 3 loads in flight when the kernel has the SM to itself; 4 / 2 when the
-    // sparse kernels run beside it and need shared memory of their own (d->stream_stages overrides)
-    int nstages = d->stream_stages > 0 ? d->stream_stages : (shared_sm ? 4 : 6);
+    // Launch shape (measured on B200, scripts/stage_times.py): what matters is ~64 KB of bulk loads in
+    // flight per SM -- 48 KB or 96 KB are 7-13 % slower, 32 KB 29 % slower -- not how many CTAs issue
+    // them.  One persistent CTA per SM with a 6-slot ring and 4 loads in flight reaches that with 96 KB
+    // of shared memory and 256 threads, leaving the rest of the SM to the sparse kernels that run
+    // beside the stream (d->stream_* override for experiments).
+    const int ctas = d->stream_ctas > 0 ? d->stream_ctas : 1;
+    int nstages = d->stream_stages > 0 ? d->stream_stages : 6;
     if (nstages < 2) nstages = 2;
     if (nstages > TMA_MAX_STAGES) nstages = TMA_MAX_STAGES;
-    int nprefetch = d->stream_prefetch > 0 ? d->stream_prefetch : nstages / 2;
+    int nprefetch = d->stream_prefetch > 0 ? d->stream_prefetch : (d->stream_stages > 0 ? nstages / 2 : 4);
     if (nprefetch >= nstages) nprefetch = nstages - 1;
     const size_t smem = (size_t)nstages * TMA_TILE_BYTES;
     static bool attr_done = false;
     if (!attr_done) {
       FOHO_CUDA_TRY(cudaFuncSetAttribute(k_stream_tma, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          TMA_MAX_STAGES * TMA_TILE_BYTES));
+      // configure the SM with the largest shared-memory carve-out, so that kernels running beside the
+      // stream find room for their own shared memory without waiting for the SM to drain
+      FOHO_CUDA_TRY(cudaFuncSetAttribute(k_stream_tma, cudaFuncAttributePreferredSharedMemoryCarveout,
+                                         (int)cudaSharedmemCarveoutMaxShared));
       attr_done = true;
     }
     long long ntiles = ((long long)(N / 4) + TMA_TILE_F4 - 1) / TMA_TILE_F4;
-    gx = (sm_count * 2 + B - 1) / B;              // 2 resident CTAs per SM over the whole batch
+    gx = sm_count * ctas / B;                     // at most `ctas` resident CTAs per SM over the whole batch:
+                                                  // one wave, never a straggler CTA waiting for a free SM
     if (gx > ntiles) gx = (int)ntiles;
     if (gx > FOHO_MAX_STREAM_CTAS) gx = FOHO_MAX_STREAM_CTAS;
     if (gx < 1) gx = 1;

@@ -86,6 +86,37 @@ def pack_object_meshes(meshes, device="cuda:0") -> ObjectMeshBatch:
                            torch.tensor(eo, dtype=torch.int32, device=dev))
 
 
+def delaunay_neighbours(hand_rest: torch.Tensor):
+    """Delaunay neighbour graph of each sample's rest hand vertices [B,Vh,3] -> (offsets int32 [B,Vh+1],
+    neighbours uint16-valued int16 storage [B,stride]) on the CPU, or None when Qhull cannot triangulate
+    one of them (degenerate input) -- the caller then keeps the box search.  Greedy descent over this
+    graph reaches the exact nearest vertex of any query (a property of Delaunay triangulations)."""
+    import numpy as np
+    try:
+        from scipy.spatial import Delaunay
+        from scipy.spatial import QhullError
+    except Exception:       # pragma: no cover
+        return None
+    v = hand_rest.detach().cpu().numpy().astype(np.float64)
+    B, Vh = v.shape[0], v.shape[1]
+    if Vh < 5 or Vh > 65535:
+        return None
+    offs, nbrs = [], []
+    for b in range(B):
+        try:
+            indptr, indices = Delaunay(v[b]).vertex_neighbor_vertices
+        except (QhullError, ValueError):
+            return None
+        if len(indptr) != Vh + 1 or np.any(np.diff(indptr) == 0):     # a vertex Qhull dropped (duplicate / coplanar)
+            return None
+        offs.append(np.asarray(indptr, dtype=np.int32)); nbrs.append(np.asarray(indices, dtype=np.uint16))
+    stride = (max(len(n) for n in nbrs) + 7) // 8 * 8          # 16-byte rows for the kernel's vector copies
+    pad = np.zeros((B, stride), dtype=np.uint16)
+    for b, n in enumerate(nbrs):
+        pad[b, :len(n)] = n
+    return torch.from_numpy(np.stack(offs)), torch.from_numpy(pad.view(np.int16))
+
+
 class GuidanceEngine:
     """Owns workspace + output buffers for a fixed problem shape and launches the kernels."""
 
@@ -114,21 +145,32 @@ class GuidanceEngine:
         self.hand_grid = torch.zeros(B, Vh, 3, dtype=torch.float32, device=dev)
         self.grad_obj_verts = (torch.zeros(self.max_obj_verts, 3, dtype=torch.float32, device=dev)
                                if self.max_obj_verts > 0 else None)
-        self.launches_per_eval = 8 if P > 0 else 7      # + 4 when an object mesh is passed
+        self.launches_per_eval = 8 if P > 0 else 7      # refreshed by make_desc; + 4 when an object mesh is passed
         self.serial = 0            # 1: every kernel in series on the caller's stream (no internal fork/join)
         self.stream_stages = 0     # TMA stream ring depth / prefetch distance (0 = library default)
         self.stream_prefetch = 0
+        self.stream_ctas = 0       # TMA stream persistent CTAs per SM (0 = library default)
         self._accel = None
         self._accel_ptr = 0
         self._accel_bytes = 0
         self._accel_for = None
+        self._nbr_off = None
+        self._nbr = None
 
-    def prepare(self, st: GuidanceStatics, stream: Optional[torch.cuda.Stream] = None) -> None:
+    def prepare(self, st: GuidanceStatics, stream: Optional[torch.cuda.Stream] = None, delaunay: bool = True) -> None:
         """Per-image setup, once per set of statics: build the chamfer search structures
-        (``foho_guidance_prepare_statics``).  Evaluations with the same ``st`` object then use the
-        structured search (one more launch); other statics fall back to the brute-force search."""
+        (``foho_guidance_prepare_statics``) and, on the host, the Delaunay neighbour graph of each rest
+        hand (``delaunay=True``; scipy/Qhull, ~20 ms per image) for the greedy-walk cloud->hand search.
+        Evaluations with the same ``st`` object then use the structured searches; other statics fall
+        back to the brute-force search."""
         if self.P <= 0 or st.cloud is None or self.Vh > 1024:
             return
+        self._nbr_off = self._nbr = None
+        if delaunay:
+            graph = delaunay_neighbours(st.hand_rest)
+            if graph is not None:
+                off, nbr = graph
+                self._nbr_off, self._nbr = off.to(self.device), nbr.to(self.device)
         _chk(st.hand_rest, (self.B, self.Vh, 3), torch.float32, "hand_rest")
         _chk(st.cloud, (self.B, self.P, 3), torch.float32, "cloud")
         nbytes = self.lib.foho_guidance_accel_bytes(self.B, self.Vh, self.P)
@@ -137,15 +179,15 @@ class GuidanceEngine:
             self._accel_ptr = self._accel.data_ptr() + ((-self._accel.data_ptr()) % 256)
             self._accel_bytes = nbytes
         d = _lib.GuidanceDesc()
-        d.B, d.Vh, d.P = self.B, self.Vh, self.P
+        d.B, d.Vh, d.P, d.Fh = self.B, self.Vh, self.P, self.Fh
         d.hand_rest, d.cloud = st.hand_rest.data_ptr(), st.cloud.data_ptr()
+        d.hand_faces = _chk(st.hand_faces, (self.Fh, 3), torch.int32, "hand_faces").data_ptr()
         d.accel, d.accel_bytes = self._accel_ptr, self._accel_bytes
         with torch.cuda.device(self.device):
             s = stream if stream is not None else torch.cuda.current_stream(self.device)
             _lib.check("foho_guidance_prepare_statics",
                        self.lib.foho_guidance_prepare_statics(C.byref(d), C.c_void_p(s.cuda_stream)))
         self._accel_for = st
-        self.launches_per_eval = 9
 
     def make_desc(self, sdf: torch.Tensor, theta: torch.Tensor, st: GuidanceStatics,
                   grad_sdf: Optional[torch.Tensor] = None, late_step: bool = False,
@@ -176,7 +218,7 @@ class GuidanceEngine:
         d.image_h, d.image_w = int(st.image_hw[0]), int(st.image_hw[1])
         d.late_step = int(late_step)
         d.stream_variant = self.stream_variant
-        d.serial, d.stream_stages, d.stream_prefetch = self.serial, self.stream_stages, self.stream_prefetch
+        d.serial, d.stream_stages, d.stream_prefetch, d.stream_ctas = self.serial, self.stream_stages, self.stream_prefetch, self.stream_ctas
         d.fov_deg = float(st.fov_deg)
         d.bound = GRID_BOUND
         d.w = self.weights
@@ -205,8 +247,13 @@ class GuidanceEngine:
             d.obj_edge_offsets = obj_mesh.edge_offsets.data_ptr()
             d.grad_obj_verts = self.grad_obj_verts.data_ptr()
         d.workspace, d.workspace_bytes = self._ws_ptr, self._ws_bytes
-        if self._accel_for is st and P > 0:
+        accel = self._accel_for is st and P > 0
+        if accel:
             d.accel, d.accel_bytes = self._accel_ptr, self._accel_bytes
+            if self._nbr is not None:
+                d.hand_nbr_off, d.hand_nbr, d.nbr_stride = self._nbr_off.data_ptr(), self._nbr.data_ptr(), int(self._nbr.shape[1])
+        # prep, stream, raster, compact, voxdist, finalize_verts, assemble (+ key-points, + chamfer 1 or 2)
+        self.launches_per_eval = 7 + (1 if use_kp and Vh > 744 else 0) + ((2 if accel else 1) if P > 0 else 0)
         return d
 
     def launch(self, desc: _lib.GuidanceDesc, stream: Optional[torch.cuda.Stream] = None) -> None:

@@ -82,8 +82,10 @@ typedef struct foho_guidance_desc {
   int32_t serial;       /* 0 = the sparse kernels run beside the dense stream on library-owned side
                            streams (fork/join by events; legal under stream capture); 1 = every kernel
                            in series on the caller's stream                                    */
-  int32_t stream_stages;   /* TMA stream: ring depth (0 = default: 6 alone, 4 beside the sparse kernels) */
-  int32_t stream_prefetch; /* TMA stream: bulk loads kept in flight per CTA (0 = stages / 2)    */
+  int32_t stream_stages;   /* TMA stream: ring depth of 16 KB tiles (0 = default 6) */
+  int32_t stream_prefetch; /* TMA stream: bulk loads kept in flight per CTA (0 = default 4)      */
+  int32_t stream_ctas;     /* TMA stream: persistent CTAs per SM (0 = default 1)                */
+  int32_t reserved0;
   float fov_deg;        /* MoGe fov_x in degrees (guidance/run.py:228-230)              */
   float bound;          /* lattice half extent, 1.10 (pipelines.py:1127)                */
   foho_weights w;
@@ -126,7 +128,22 @@ typedef struct foho_guidance_desc {
    * brute-force search; results are identical up to ties between equidistant neighbours. */
   void *accel;               /* device, 256-byte aligned, >= foho_guidance_accel_bytes(...) */
   size_t accel_bytes;
+  /* optional (with accel): Delaunay neighbour graph of the REST hand vertices of every sample, CSR:
+   * sample b's vertex i has neighbours hand_nbr[b*nbr_stride + off[i] .. off[i+1]) with
+   * off = hand_nbr_off + b*(Vh+1).  Enables the greedy-walk cloud->hand search (exact on a Delaunay
+   * graph or any super-graph of it); NULL selects the box search. */
+  const int32_t *hand_nbr_off;   /* device [B,Vh+1] */
+  const uint16_t *hand_nbr;      /* device [B,nbr_stride], 16-byte aligned; nbr_stride a multiple of 8 */
+  int32_t nbr_stride;
+  int32_t reserved1;
+
+  /* optional timeline trace (profiling hook, NULL = off): device [FOHO_TRACE_KERNELS][2] uint64, the
+   * caller initialises every pair to {UINT64_MAX, 0}; each kernel folds in the %globaltimer (ns) of
+   * its first CTA start and last CTA end.  Order: prep, stream, chamfer_h2c, chamfer_c2h,
+   * chamfer_brute, raster, compact, voxdist, finalize_verts, assemble, keypoints. */
+  void *trace;
 } foho_guidance_desc;
+#define FOHO_TRACE_KERNELS 11
 
 int foho_abi_version(void);
 const char *foho_status_string(int status);
@@ -140,9 +157,13 @@ size_t foho_guidance_workspace_bytes(int32_t B, int32_t D, int32_t Vh, int32_t F
                                      int32_t Vo_total);
 int foho_guidance_energy_fwd_bwd(const foho_guidance_desc *desc, void *cuda_stream);
 
-/* Build the search structures of desc->accel from desc->hand_rest [B,Vh,3] (Vh <= 1024) and
- * desc->cloud [B,P,3]: the per-image setup the reference does once before its loop (mesh / target
- * loading, pipelines.py:1218-1256); only B, Vh, P, hand_rest, cloud, accel, accel_bytes are read. */
+/* Build the search structures of desc->accel from desc->hand_rest [B,Vh,3] (Vh <= 1024),
+ * desc->hand_faces [Fh,3] and desc->cloud [B,P,3]: the per-image setup the reference does once before
+ * its loop (mesh / target loading, pipelines.py:1218-1256); only B, Vh, Fh, P, hand_rest, hand_faces,
+ * cloud, accel, accel_bytes are read.  Contents: the cloud in Morton order with a two-level box
+ * hierarchy, the rest hand as Morton-ordered leaves of 8 vertices, the faces in Morton order of their
+ * rest centroids (Fh <= 2048; required then), and warm-start hints that later evaluations update
+ * (they only speed the searches up; results never depend on them). */
 size_t foho_guidance_accel_bytes(int32_t B, int32_t Vh, int32_t P);
 int foho_guidance_prepare_statics(const foho_guidance_desc *desc, void *cuda_stream);
 

@@ -58,9 +58,10 @@ for name, serial, stages, pre in (("all_serial", 1, 0, 0), ("all_overlap_s4p2", 
     e1.record()
     torch.cuda.synchronize()
     out[name] = round(e0.elapsed_time(e1) / a.reps * 1e3, 2)
-# stream alone with different ring depths
-for stages, pre in ((6, 3), (5, 3), (4, 2), (4, 3), (8, 4), (3, 2)):
-    eng.serial, eng.stream_stages, eng.stream_prefetch, eng.stream_variant = 1, stages, pre, a.variant
+# stream alone: persistent CTAs per SM x ring depth x loads in flight
+for ctas, stages, pre in ((2, 6, 3), (2, 4, 2), (2, 3, 2), (2, 3, 1), (2, 2, 1), (1, 8, 4), (1, 6, 3), (1, 4, 2), (1, 4, 3), (1, 6, 4),
+                          (1, 12, 6), (1, 12, 4), (3, 3, 2), (3, 2, 1), (4, 3, 1), (4, 2, 1)):
+    eng.serial, eng.stream_stages, eng.stream_prefetch, eng.stream_ctas, eng.stream_variant = 1, stages, pre, ctas, a.variant
     desc = eng.make_desc(loop.sdf, loop.theta, st)
     desc.stage_mask = 2
     for _ in range(3):
@@ -72,5 +73,5 @@ for stages, pre in ((6, 3), (5, 3), (4, 2), (4, 3), (8, 4), (3, 2)):
         eng.launch(desc)
     e1.record()
     torch.cuda.synchronize()
-    out[f"stream_s{stages}p{pre}"] = round(e0.elapsed_time(e1) / a.reps * 1e3, 2)
+    out[f"stream_c{ctas}s{stages}p{pre}"] = round(e0.elapsed_time(e1) / a.reps * 1e3, 2)
 print(json.dumps({"us_per_launch": out, "B": a.B, "D": a.D, "P": a.P}))

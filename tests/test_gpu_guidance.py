@@ -280,14 +280,17 @@ def test_structured_chamfer_equals_brute_force_and_scipy(P, case):
     for n in ("w_pen", "w_con", "w_ivol", "w_mom", "w_hand", "w_treg_o"):
         setattr(w, n, 0.0)
     res = []
-    for accel in (False, True):
+    for mode in ("brute", "box", "walk", "walk-warm"):
         eng = GuidanceEngine(B, D, 778, 1538, P, weights=w)
-        if accel:
-            eng.prepare(st)
+        if mode != "brute":
+            eng.prepare(st, delaunay=mode.startswith("walk"))
+            assert (eng._nbr is not None) == mode.startswith("walk")
         terms, _, gt = eng.energy_fwd_bwd(sdf, theta, st)
+        if mode == "walk-warm":           # second evaluation starts from the first one's neighbours
+            terms, _, gt = eng.energy_fwd_bwd(sdf, theta, st)
         torch.cuda.synchronize()
         res.append((terms.cpu().numpy().copy(), gt.cpu().numpy().copy(), eng.hand_moge.cpu().numpy().copy()))
-    (t0, g0, hm), (t1, g1, _) = res
+    (t0, g0, hm), (t1, g1, _), (t2, g2, _), (t3, g3, _) = res
     for b in range(B):
         cl = samples[b].cloud.double().numpy()
         d_hc = cKDTree(cl).query(hm[b].astype(np.float64))[0] ** 2
@@ -296,3 +299,6 @@ def test_structured_chamfer_equals_brute_force_and_scipy(P, case):
         assert abs(t0[b, 6] - ref) <= 2e-5 * ref + 1e-12, (case, "brute", t0[b, 6], ref)
         assert abs(t1[b, 6] - ref) <= 2e-5 * ref + 1e-12, (case, "accel", t1[b, 6], ref)
         _close(f"grad_theta[{b}] accel vs brute", g1[b], g0[b], rel=2e-5)
+        for name, t, g in (("walk", t2, g2), ("walk-warm", t3, g3)):
+            assert abs(t[b, 6] - ref) <= 2e-5 * ref + 1e-12, (case, name, t[b, 6], ref)
+            _close(f"grad_theta[{b}] {name} vs brute", g[b], g0[b], rel=2e-5)
