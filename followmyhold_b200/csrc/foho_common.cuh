@@ -50,6 +50,7 @@ enum { CNT_NCAND = 0, CNT_COUNT = 1, CNT_FLAGS = 2, CNT_NUM = 4 };
 
 #define FOHO_STREAM_PARTIALS 8      // m0, m1x, m1y, m1z, m2, count_obj, pad, pad
 #define FOHO_MAX_STREAM_CTAS 2048   // per sample
+#define FOHO_VE_MAX_CTAS 16         // k_vertex_early CTAs per sample (Vh <= 4096)
 #define FOHO_FIN_NRED 32            // per-sample sums produced by k_finalize_verts
 
 // Per-sample state of the explicit object mesh (REF a5/a6 on the FlexiCubes vertices).
@@ -77,6 +78,8 @@ struct FohoWorkspace {
   unsigned long long *knn_obj;// [B,Vh] packed (d2 bits << 32 | packed object vertex index)
   FohoObjInfo *oinfo;         // [B]
   float4 *sph;                // [B,Fh] bounding sphere (centroid, radius) of each hand face, lattice units
+  float *E_hm, *E_hg;         // [B,Vh,3] k_vertex_early: key-point/external part of dE/d(hm), field part of dE/d(hg)
+  float *pen_part;            // [B,FOHO_VE_MAX_CTAS,2] per-CTA sums of the a13 penalties
   float *kpbuf;               // [B,64] k_keypoints -> k_finalize_verts: dE/d(21 key-points) | loss
   float *fin_acc;             // [B,FOHO_FIN_NRED] per-sample sums of k_finalize_verts
   float *cand_val;            // [B,cap] dE/dS contribution of each candidate voxel (applied by k_assemble)
@@ -151,6 +154,9 @@ static inline void foho_ws_layout(FohoWorkspace &w, char *base, int B, int D, in
   w.knn_obj = (unsigned long long *)take(sizeof(unsigned long long) * (size_t)B * Vh);
   w.oinfo = (FohoObjInfo *)take(sizeof(FohoObjInfo) * (size_t)B);
   w.sph = (float4 *)take(sizeof(float4) * (size_t)B * Fh);
+  w.E_hm = (float *)take(sizeof(float) * 3 * (size_t)B * Vh);
+  w.E_hg = (float *)take(sizeof(float) * 3 * (size_t)B * Vh);
+  w.pen_part = (float *)take(sizeof(float) * 2 * FOHO_VE_MAX_CTAS * (size_t)B);
   w.kpbuf = (float *)take(sizeof(float) * 64 * (size_t)B);
   w.fin_acc = (float *)take(sizeof(float) * FOHO_FIN_NRED * (size_t)B);
   w.cand_val = (float *)take(sizeof(float) * (size_t)B * w.cap);

@@ -126,14 +126,15 @@ __global__ void __launch_bounds__(256) k_prep(foho_guidance_desc d, FohoWorkspac
 }
 
 // ----------------------------------------------------------------------------- k_raster
-// one warp per hand face, lanes over the columns of the face's xy bounding box: XOR the "below the
+// eight lanes per hand face, striding over the columns of the face's xy bounding box: XOR the "below the
 // crossing" prefix into every column the projection covers (rule: foho_math.cuh::column_hits_triangle).
 // (A thread per face leaves the few large faces -- the wrist cap fan -- as a long serial tail.)
 constexpr int RASTER_THREADS = 256;
+constexpr int RASTER_LANES = 8;          // lanes per face: a typical face covers ~3x3 columns
 __global__ void __launch_bounds__(RASTER_THREADS) k_raster(foho_guidance_desc d, FohoWorkspace ws, const int *__restrict__ face_rank) {
   FohoTrace trace_(ws.trace, TR_RASTER);
-  const int b = blockIdx.y, D = d.D, lane = threadIdx.x & 31;
-  const int f = blockIdx.x * (RASTER_THREADS / 32) + (threadIdx.x >> 5);
+  const int b = blockIdx.y, D = d.D, lane = threadIdx.x & (RASTER_LANES - 1);
+  const int f = (blockIdx.x * RASTER_THREADS + threadIdx.x) / RASTER_LANES;
   if (f >= d.Fh) return;
   const FohoFrame &fr = ws.frames[b];
   const float *hg = ws.hg + (size_t)b * d.Vh * 3;
@@ -161,7 +162,7 @@ __global__ void __launch_bounds__(RASTER_THREADS) k_raster(foho_guidance_desc d,
   const int nx = xmax - xmin + 1, ny = ymax - ymin + 1;
   if (nx <= 0 || ny <= 0) return;
   uint32_t *par = ws.parity + (size_t)b * D * D * ws.W;
-  for (int k = lane; k < nx * ny; k += 32) {
+  for (int k = lane; k < nx * ny; k += RASTER_LANES) {
     const int X = xmin + k / ny, Y = ymin + k % ny;
     float zc;
     if (!column_hits_triangle(ia, ib, ic, a, bb, c, (float)X, (float)Y, &zc)) continue;
@@ -203,25 +204,49 @@ __global__ void __launch_bounds__(256) k_compact(foho_guidance_desc d, FohoWorks
       col = (fr.lo[0] + c / ny) * D + (fr.lo[1] + c % ny);
       word = par[(size_t)col * ws.W + wz];
     }
+    // pass 1: the hit mask of every non-zero word (lane j keeps the mask of the word lane j fetched);
+    //         four words per step so that their reads of S overlap
     unsigned todo = __ballot_sync(0xffffffffu, word != 0u);
+    unsigned mymask = 0u;
     while (todo) {
-      const int src = __ffs(todo) - 1;
-      todo &= todo - 1;
-      const uint32_t bits = __shfl_sync(0xffffffffu, word, src);
-      const int ccol = __shfl_sync(0xffffffffu, col, src), cw = __shfl_sync(0xffffffffu, wz, src);
-      const int Z = cw * 32 + lane;
-      const int v = ccol * D + Z;
-      const bool hit = ((bits >> lane) & 1u) && Z < D && S[v] < 0.f;
-      const unsigned m = __ballot_sync(0xffffffffu, hit);
-      if (m == 0u) continue;
-      int slot0 = 0;
-      if (lane == 0) slot0 = atomicAdd(cnt + CNT_NCAND, __popc(m));
-      slot0 = __shfl_sync(0xffffffffu, slot0, 0);
-      if (hit) {
-        const int slot = slot0 + __popc(m & ((1u << lane) - 1u));
-        if (slot < ws.cap) cand[slot] = v;
-        else atomicOr(cnt + CNT_FLAGS, 1);
+      int src[4];
+      bool hit[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        src[u] = todo ? __ffs(todo) - 1 : -1;
+        if (todo) todo &= todo - 1;
+        hit[u] = false;
+        if (src[u] >= 0) {
+          const uint32_t bits = __shfl_sync(0xffffffffu, word, src[u]);
+          const int ccol = __shfl_sync(0xffffffffu, col, src[u]), cw = __shfl_sync(0xffffffffu, wz, src[u]);
+          const int Z = cw * 32 + lane;
+          hit[u] = ((bits >> lane) & 1u) && Z < D && S[(size_t)ccol * D + Z] < 0.f;
+        }
       }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        if (src[u] < 0) continue;
+        const unsigned m = __ballot_sync(0xffffffffu, hit[u]);
+        if (lane == src[u]) mymask = m;
+      }
+    }
+    // pass 2: one slot reservation for the whole batch, then every lane writes its own word's hits
+    const int mine = __popc(mymask);
+    int incl = mine;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += t; }
+    const int total = __shfl_sync(0xffffffffu, incl, 31);
+    if (total == 0) continue;
+    int slot0 = 0;
+    if (lane == 0) slot0 = atomicAdd(cnt + CNT_NCAND, total);
+    slot0 = __shfl_sync(0xffffffffu, slot0, 0) + incl - mine;
+    unsigned mm = mymask;
+    while (mm) {
+      const int z = __ffs(mm) - 1;
+      mm &= mm - 1;
+      if (slot0 < ws.cap) cand[slot0] = col * D + wz * 32 + z;
+      else atomicOr(cnt + CNT_FLAGS, 1);
+      ++slot0;
     }
   }
 }
@@ -472,41 +497,30 @@ __global__ void __launch_bounds__(KP_THREADS) k_keypoints(foho_guidance_desc d, 
   }
 }
 
-// k_finalize_verts: everything per hand vertex (runs beside the dense stream: it neither reads the
-// stream's moments nor writes G -- its dE/dS corner contributions go to ws.tri_* and are applied by
-// k_assemble once the stream has written G).
-__global__ void __launch_bounds__(FIN_THREADS) k_finalize_verts(foho_guidance_desc d, FohoWorkspace ws) {
-  FohoTrace trace_(ws.trace, TR_FIN);
-  __shared__ FohoFrame fr;
-  __shared__ float red[FIN_NRED * 32];
+// k_vertex_early: the per-vertex work that needs nothing but k_prep's output (and, for the key-point
+// back-projection, k_keypoints' 21 gradients): the a13 trilinear sample of S at every hand vertex with
+// its penalties, the dE/dS corner contributions (-> ws.tri_*, applied by k_assemble), the field-gradient
+// part of dE/d(lattice position) and the key-point / external part of dE/d(MoGe position).  Runs on a
+// side stream long before the searches finish, so that k_finalize_verts only has to combine vectors.
+constexpr int VE_THREADS = 256;
+__global__ void __launch_bounds__(VE_THREADS) k_vertex_early(foho_guidance_desc d, FohoWorkspace ws) {
+  FohoTrace trace_(ws.trace, TR_KP);
   __shared__ float gkp[21][3];     // dE/dkp3 in concatenated order
-  const int b = blockIdx.x, tid = threadIdx.x, Vh = d.Vh, D = d.D;
+  __shared__ float red[2 * 32];
+  const int b = blockIdx.y, tid = threadIdx.x, Vh = d.Vh, D = d.D;
   const bool use_kp = d.n_joints == 16 && d.j_regressor && d.kps_2d && Vh > 744;
-  {
-    const int nwords = sizeof(FohoFrame) / 4;
-    const uint32_t *src = reinterpret_cast<const uint32_t *>(ws.frames + b);
-    uint32_t *dst = reinterpret_cast<uint32_t *>(&fr);
-    for (int k = tid; k < nwords; k += blockDim.x) dst[k] = src[k];
-  }
   if (tid < 63) (&gkp[0][0])[tid] = use_kp ? ws.kpbuf[(size_t)b * 64 + tid] : 0.f;
   __syncthreads();
-  const float *hmc = ws.hmc + (size_t)b * Vh * 3;
   const float *hg = ws.hg + (size_t)b * Vh * 3;
-
-  // ---- per-vertex pass
-  float acc[FIN_NRED];
-#pragma unroll
-  for (int k = 0; k < FIN_NRED; ++k) acc[k] = 0.f;
-  // layout: 0..2 gt_h, 3 gs_h, 4..12 GR_h, 13..15 gt_o, 16 gs_o, 17..25 GR_o, 26 pen, 27 con, 28 ch_hand
   const float *S = d.sdf + (size_t)b * D * D * D;
   int *tri_idx = ws.tri_idx + (size_t)b * Vh * 8;
   float *tri_val = ws.tri_val + (size_t)b * Vh * 8;
-  const float *Ghm = ws.G_hm + (size_t)b * Vh * 3;
-  const float *Ghg = ws.G_hg + (size_t)b * Vh * 3;
-  const float *rest = d.hand_rest + (size_t)b * Vh * 3;
+  float *Ehg = ws.E_hg + (size_t)b * Vh * 3, *Ehm = ws.E_hm + (size_t)b * Vh * 3;
   const float invV = 1.f / (float)Vh;
   const float Dm1 = (float)(D - 1);
-  for (int i = tid; i < Vh; i += blockDim.x) {
+  float v2[2] = {0.f, 0.f};        // pen, con sums of this CTA
+  const int i = blockIdx.x * blockDim.x + tid;
+  if (i < Vh) {
     // a13 trilinear sample with border clamp
     float g[3] = {hg[3 * i], hg[3 * i + 1], hg[3 * i + 2]};
     float fr_[3]; int i0[3]; bool live[3];
@@ -525,6 +539,23 @@ __global__ void __launch_bounds__(FIN_THREADS) k_finalize_verts(foho_guidance_de
       for (int dy = 0; dy < 2; ++dy)
 #pragma unroll
         for (int dz = 0; dz < 2; ++dz) c[dx][dy][dz] = S[((size_t)(i0[0] + dx) * D + (i0[1] + dy)) * D + (i0[2] + dz)];
+    // key-point back-projection through J and the tips (a11) while the samples are in flight
+    float kx = 0.f, ky = 0.f, kz = 0.f;
+    if (use_kp) {
+      float w[16];
+#pragma unroll
+      for (int j = 0; j < 16; ++j) w[j] = d.j_regressor[(size_t)j * Vh + i];
+#pragma unroll
+      for (int j = 0; j < 16; ++j) { kx = fmaf(w[j], gkp[j][0], kx); ky = fmaf(w[j], gkp[j][1], ky); kz = fmaf(w[j], gkp[j][2], kz); }
+#pragma unroll
+      for (int t = 0; t < 5; ++t)
+        if (i == c_tips[t]) { kx += gkp[16 + t][0]; ky += gkp[16 + t][1]; kz += gkp[16 + t][2]; }
+    }
+    if (d.grad_hand_ext) {
+      const float *e = d.grad_hand_ext + ((size_t)b * Vh + i) * 3;
+      kx += e[0]; ky += e[1]; kz += e[2];
+    }
+    Ehm[3 * i] = kx; Ehm[3 * i + 1] = ky; Ehm[3 * i + 2] = kz;
     const float fx = fr_[0], fy = fr_[1], fz = fr_[2];
     float s = 0.f, dsx = 0.f, dsy = 0.f, dsz = 0.f;
 #pragma unroll
@@ -540,12 +571,11 @@ __global__ void __launch_bounds__(FIN_THREADS) k_finalize_verts(foho_guidance_de
           dsy += (dy ? 1.f : -1.f) * wx * wz * v;
           dsz += (dz ? 1.f : -1.f) * wx * wy * v;
         }
-    acc[26] += fmaxf(-s, 0.f);
-    acc[27] += fmaxf(fabsf(s) - d.w.con_margin, 0.f);
+    v2[0] = fmaxf(-s, 0.f);
+    v2[1] = fmaxf(fabsf(s) - d.w.con_margin, 0.f);
     float dLds = 0.f;
     if (s < 0.f) dLds -= d.w.w_pen * invV;
     if (fabsf(s) > d.w.con_margin) dLds += d.w.w_con * invV * (s > 0.f ? 1.f : -1.f);
-    float ghg[3] = {Ghg[3 * i], Ghg[3 * i + 1], Ghg[3 * i + 2]};
 #pragma unroll
     for (int dx = 0; dx < 2; ++dx)
 #pragma unroll
@@ -557,39 +587,64 @@ __global__ void __launch_bounds__(FIN_THREADS) k_finalize_verts(foho_guidance_de
           tri_idx[i * 8 + k] = ((i0[0] + dx) * D + (i0[1] + dy)) * D + (i0[2] + dz);
           tri_val[i * 8 + k] = dLds * (wx * wy * wz);
         }
+    float e3[3] = {0.f, 0.f, 0.f};
     if (dLds != 0.f) {
-      if (live[0]) ghg[0] += dLds * dsx;
-      if (live[1]) ghg[1] += dLds * dsy;
-      if (live[2]) ghg[2] += dLds * dsz;
+      if (live[0]) e3[0] = dLds * dsx;
+      if (live[1]) e3[1] = dLds * dsy;
+      if (live[2]) e3[2] = dLds * dsz;
     }
+    Ehg[3 * i] = e3[0]; Ehg[3 * i + 1] = e3[1]; Ehg[3 * i + 2] = e3[2];
+  }
+  block_sum<2>(v2, red);
+  if (tid == 0) {
+    // per-CTA partials, summed in fixed order by k_finalize_verts
+    ws.pen_part[((size_t)b * FOHO_VE_MAX_CTAS + blockIdx.x) * 2] = v2[0];
+    ws.pen_part[((size_t)b * FOHO_VE_MAX_CTAS + blockIdx.x) * 2 + 1] = v2[1];
+  }
+}
+
+// k_finalize_verts: everything per hand vertex (runs beside the dense stream: it neither reads the
+// stream's moments nor writes G -- its dE/dS corner contributions go to ws.tri_* and are applied by
+// k_assemble once the stream has written G).
+__global__ void __launch_bounds__(FIN_THREADS) k_finalize_verts(foho_guidance_desc d, FohoWorkspace ws, int ve_ctas) {
+  FohoTrace trace_(ws.trace, TR_FIN);
+  __shared__ FohoFrame fr;
+  __shared__ float red[FIN_NRED * 32];
+  const int b = blockIdx.x, tid = threadIdx.x, Vh = d.Vh;
+  const bool use_kp = d.n_joints == 16 && d.j_regressor && d.kps_2d && Vh > 744;
+  {
+    const int nwords = sizeof(FohoFrame) / 4;
+    const uint32_t *src = reinterpret_cast<const uint32_t *>(ws.frames + b);
+    uint32_t *dst = reinterpret_cast<uint32_t *>(&fr);
+    for (int k = tid; k < nwords; k += blockDim.x) dst[k] = src[k];
+  }
+  __syncthreads();
+  const float *hmc = ws.hmc + (size_t)b * Vh * 3;
+
+  // ---- per-vertex pass
+  float acc[FIN_NRED];
+#pragma unroll
+  for (int k = 0; k < FIN_NRED; ++k) acc[k] = 0.f;
+  // layout: 0..2 gt_h, 3 gs_h, 4..12 GR_h, 13..15 gt_o, 16 gs_o, 17..25 GR_o, 26 pen, 27 con, 28 ch_hand
+  const float *Ghm = ws.G_hm + (size_t)b * Vh * 3;
+  const float *Ghg = ws.G_hg + (size_t)b * Vh * 3;
+  const float *Ehm = ws.E_hm + (size_t)b * Vh * 3;
+  const float *Ehg = ws.E_hg + (size_t)b * Vh * 3;
+  const float *rest = d.hand_rest + (size_t)b * Vh * 3;
+  const float invV = 1.f / (float)Vh;
+  for (int i = tid; i < Vh; i += blockDim.x) {
+    // a15 hand -> cloud: issue the dependent load chain first
+    unsigned long long key = 0xFFFFFFFFFFFFFFFFull;
+    if (d.P > 0 && d.cloud) key = ws.knn[(size_t)b * Vh + i];
+    const float ghg[3] = {Ghg[3 * i] + Ehg[3 * i], Ghg[3 * i + 1] + Ehg[3 * i + 1], Ghg[3 * i + 2] + Ehg[3 * i + 2]};
     // gradient w.r.t. the (centred) MoGe position of this vertex
     const foho_f3 m = f3(hmc[3 * i], hmc[3 * i + 1], hmc[3 * i + 2]);
-    foho_f3 gm = f3(Ghm[3 * i], Ghm[3 * i + 1], Ghm[3 * i + 2]);
-    if (d.grad_hand_ext) {
-      const float *e = d.grad_hand_ext + ((size_t)b * Vh + i) * 3;
-      gm = gm + f3(e[0], e[1], e[2]);
-    }
-    // a15 hand -> cloud
-    if (d.P > 0 && d.cloud) {
-      unsigned long long key = ws.knn[(size_t)b * Vh + i];
-      if (key != 0xFFFFFFFFFFFFFFFFull) {
-        const float *p = d.cloud + ((size_t)b * d.P + (unsigned)(key & 0xFFFFFFFFull)) * 3;
-        foho_f3 df = m - f3(p[0] - fr.co[0], p[1] - fr.co[1], p[2] - fr.co[2]);
-        acc[28] += dot3(df, df);
-        gm = gm + (2.f * d.w.w_ch * invV) * df;
-      }
-    }
-    // a11 back through J and the tips
-    if (use_kp) {
-      float kx = 0.f, ky = 0.f, kz = 0.f;
-      for (int j = 0; j < 16; ++j) {
-        float w = d.j_regressor[(size_t)j * Vh + i];
-        kx = fmaf(w, gkp[j][0], kx); ky = fmaf(w, gkp[j][1], ky); kz = fmaf(w, gkp[j][2], kz);
-      }
-#pragma unroll
-      for (int t = 0; t < 5; ++t)
-        if (i == c_tips[t]) { kx += gkp[16 + t][0]; ky += gkp[16 + t][1]; kz += gkp[16 + t][2]; }
-      gm = gm + f3(kx, ky, kz);
+    foho_f3 gm = f3(Ghm[3 * i] + Ehm[3 * i], Ghm[3 * i + 1] + Ehm[3 * i + 1], Ghm[3 * i + 2] + Ehm[3 * i + 2]);
+    if (key != 0xFFFFFFFFFFFFFFFFull) {
+      const float *p = d.cloud + ((size_t)b * d.P + (unsigned)(key & 0xFFFFFFFFull)) * 3;
+      foho_f3 df = m - f3(p[0] - fr.co[0], p[1] - fr.co[1], p[2] - fr.co[2]);
+      acc[28] += dot3(df, df);
+      gm = gm + (2.f * d.w.w_ch * invV) * df;
     }
     // lattice -> object-centred coordinates
     const foho_f3 gxp = mat3_tmul(fr.Ahs_inv, f3(ghg[0], ghg[1], ghg[2]));       // dE/dx'
@@ -617,6 +672,10 @@ __global__ void __launch_bounds__(FIN_THREADS) k_finalize_verts(foho_guidance_de
   if (tid == 0) {
     float *fa = ws.fin_acc + (size_t)b * FIN_NRED;
     acc[29] = use_kp ? ws.kpbuf[(size_t)b * 64 + 63] : 0.f;
+    for (int k = 0; k < ve_ctas; ++k) {
+      acc[26] += ws.pen_part[((size_t)b * FOHO_VE_MAX_CTAS + k) * 2];
+      acc[27] += ws.pen_part[((size_t)b * FOHO_VE_MAX_CTAS + k) * 2 + 1];
+    }
 #pragma unroll
     for (int k = 0; k < FIN_NRED; ++k) fa[k] = acc[k];
   }
@@ -888,7 +947,7 @@ extern "C" int foho_guidance_energy_fwd_bwd(const foho_guidance_desc *dp, void *
       if (a.total > d.accel_bytes) return FOHO_E_WORKSPACE;
       face_rank = a.face_rank;
     }
-    k_raster<<<dim3((d.Fh + RASTER_THREADS / 32 - 1) / (RASTER_THREADS / 32), d.B), RASTER_THREADS, 0, sb>>>(d, ws, face_rank);
+    k_raster<<<dim3((d.Fh * RASTER_LANES + RASTER_THREADS - 1) / RASTER_THREADS, d.B), RASTER_THREADS, 0, sb>>>(d, ws, face_rank);
     FOHO_LAUNCH_CHECK();
     k_compact<<<dim3(32, d.B), 256, 0, sb>>>(d, ws);
     FOHO_LAUNCH_CHECK();
@@ -901,8 +960,14 @@ extern "C" int foho_guidance_energy_fwd_bwd(const foho_guidance_desc *dp, void *
     }
   }
   if (overlap) FOHO_CUDA_TRY(cudaEventRecord(fc->join_b, sb));
-  if ((sm & 16) && use_kp) {
-    k_keypoints<<<d.B, KP_THREADS, 0, sc>>>(d, ws);
+  const int ve_ctas = (d.Vh + VE_THREADS - 1) / VE_THREADS;
+  if (ve_ctas > FOHO_VE_MAX_CTAS) return FOHO_E_SHAPE;
+  if (sm & 16) {
+    if (use_kp) {
+      k_keypoints<<<d.B, KP_THREADS, 0, sc>>>(d, ws);
+      FOHO_LAUNCH_CHECK();
+    }
+    k_vertex_early<<<dim3(ve_ctas, d.B), VE_THREADS, 0, sc>>>(d, ws);
     FOHO_LAUNCH_CHECK();
   }
   if (accel) {
@@ -920,7 +985,7 @@ extern "C" int foho_guidance_energy_fwd_bwd(const foho_guidance_desc *dp, void *
     if (rc != FOHO_OK) return rc;
   }
   if (sm & 16) {
-    k_finalize_verts<<<d.B, FIN_THREADS, 0, sa>>>(d, ws);
+    k_finalize_verts<<<d.B, FIN_THREADS, 0, sa>>>(d, ws, ve_ctas);
     FOHO_LAUNCH_CHECK();
   }
   if (overlap) {

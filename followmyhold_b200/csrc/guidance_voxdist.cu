@@ -40,8 +40,10 @@ __global__ void __launch_bounds__(VT_THREADS) k_voxdist_staged(foho_guidance_des
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   {
     const float4 *gs = ws.sph + (size_t)b * Fh;
+#pragma unroll 8
     for (int i = threadIdx.x; i < NF; i += blockDim.x) sph[i] = i < Fh ? gs[i] : make_float4(0.f, 0.f, 0.f, -1.f);
     const float *hg = ws.hg + (size_t)b * Vh * 3;
+#pragma unroll 4
     for (int i = threadIdx.x; i < Vh; i += blockDim.x) sv[i] = make_float4(hg[3 * i], hg[3 * i + 1], hg[3 * i + 2], 0.f);
   }
   __syncthreads();
@@ -60,8 +62,19 @@ __global__ void __launch_bounds__(VT_THREADS) k_voxdist_staged(foho_guidance_des
   const int c1 = min(n, c0 + run);
   foho_f3 pprev = f3(0.f, 0.f, 0.f);
   float dprev = -1.f;                                          // distance of the previous candidate of this run
+  // the voxel index and the field value of up to 32 candidates of the run are fetched together (lane k
+  // holds candidate c0+k): one round trip to DRAM per 32 candidates instead of two per candidate
+  int vpre = 0;
+  float spre = 0.f;
   for (int c = c0; c < c1; ++c) {
-    const int v = cand[c];
+    const int k = (c - c0) & 31;
+    if (k == 0) {
+      const int cc = c + lane;
+      vpre = cc < c1 ? cand[cc] : 0;
+      spre = cc < c1 ? S[vpre] : 0.f;
+    }
+    const int v = __shfl_sync(0xffffffffu, vpre, k);
+    const float sval = __shfl_sync(0xffffffffu, spre, k);
     const int Z = v % D, Y = (v / D) % D, X = v / (D * D);
     const foho_f3 p = f3((float)X, (float)Y, (float)Z);
     // ---- bound
@@ -150,7 +163,7 @@ __global__ void __launch_bounds__(VT_THREADS) k_voxdist_staged(foho_guidance_des
     }
     dprev = sqrtf(mb); pprev = p;
     if (lane == __ffs(vote) - 1) {
-      const float s = S[v];                                  // < 0 by construction
+      const float s = sval;                                  // S[v] < 0 by construction
       const float dist = sqrtf(bst.d2);
       const float ns = -s;
       acc_int += ns * dist;

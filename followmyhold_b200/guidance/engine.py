@@ -252,8 +252,8 @@ class GuidanceEngine:
             d.accel, d.accel_bytes = self._accel_ptr, self._accel_bytes
             if self._nbr is not None:
                 d.hand_nbr_off, d.hand_nbr, d.nbr_stride = self._nbr_off.data_ptr(), self._nbr.data_ptr(), int(self._nbr.shape[1])
-        # prep, stream, raster, compact, voxdist, finalize_verts, assemble (+ key-points, + chamfer 1 or 2)
-        self.launches_per_eval = 7 + (1 if use_kp and Vh > 744 else 0) + ((2 if accel else 1) if P > 0 else 0)
+        # prep, stream, raster, compact, voxdist, vertex_early, finalize_verts, assemble (+ key-points, + chamfer 1 or 2)
+        self.launches_per_eval = 8 + (1 if use_kp and Vh > 744 else 0) + ((2 if accel else 1) if P > 0 else 0)
         return d
 
     def launch(self, desc: _lib.GuidanceDesc, stream: Optional[torch.cuda.Stream] = None) -> None:
