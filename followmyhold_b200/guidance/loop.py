@@ -186,6 +186,67 @@ class GuidanceLoop:
             self.stream.synchronize()
         return out
 
+    # ------------------------------------------------------------------ host-buffer API, pipelined
+    def denoise_steps_host(self, step_index: int, batches) -> list:
+        """Guided-denoise steps for a sequence of image batches whose inputs live in pinned HOST memory
+        (``batches``: iterable of ``(sdf0, x_t, velocity, theta)`` CPU tensors, each a different batch of
+        B images -- the way a rank works through its share of ``sorted(images)[rank::world]``).
+
+        Three streams: the upload of batch k+1 into a staging set overlaps the graph replay of batch k,
+        whose results leave through a second staging set while batch k+1 computes.  Every byte still
+        crosses PCIe inside the call (H2D ``h2d_bytes_per_step`` and D2H ``d2h_bytes_per_step`` per
+        batch).  Returns one dict of pinned host tensors per batch, valid when the call returns."""
+        self.capture(step_index)
+        dev = self.device
+        outs = []
+        with torch.cuda.device(dev):
+            if not hasattr(self, "_stage"):
+                self._stage = {n: torch.empty_like(t) for n, t in (("sdf0", self.sdf0), ("x_t", self.x_t),
+                                                                    ("velocity", self.velocity), ("theta", self.theta))}
+                self._ostage = {n: torch.empty_like(t) for n, t in (("velocity", self.velocity), ("prev_sample", self.prev),
+                                                                     ("theta", self.theta), ("terms", self.engine.terms))}
+                self.d2h_stream = torch.cuda.Stream(device=dev)
+                self._ev_stage_free = torch.cuda.Event()
+                self._ev_out_free = torch.cuda.Event()
+            cs, s, ds = self.copy_stream, self.stream, self.d2h_stream
+            st, ost = self._stage, self._ostage
+            cur = torch.cuda.current_stream(dev)
+            for x in (cs, s, ds):
+                x.wait_stream(cur)
+            self._ev_stage_free.record(s)
+            self._ev_out_free.record(ds)
+            for k, (sdf0_h, x_t_h, vel_h, theta_h) in enumerate(batches):
+                out = {n: self._pin(f"p{k}_{n}", t) for n, t in ost.items()}
+                outs.append(out)
+                # upload into the staging set as soon as the previous batch has left it
+                cs.wait_event(self._ev_stage_free)
+                with torch.cuda.stream(cs):
+                    st["sdf0"].copy_(sdf0_h, non_blocking=True)
+                    st["x_t"].copy_(x_t_h, non_blocking=True)
+                    st["velocity"].copy_(vel_h, non_blocking=True)
+                    st["theta"].copy_(theta_h, non_blocking=True)
+                    h2d_done = torch.cuda.Event()
+                    h2d_done.record(cs)
+                s.wait_event(h2d_done)
+                with torch.cuda.stream(s):
+                    self.sdf0.copy_(st["sdf0"]); self.sdf.copy_(st["sdf0"])
+                    self.x_t.copy_(st["x_t"]); self.velocity.copy_(st["velocity"]); self.theta.copy_(st["theta"])
+                    self._ev_stage_free.record(s)
+                    self._graph.replay()
+                    s.wait_event(self._ev_out_free)
+                    ost["velocity"].copy_(self.velocity); ost["prev_sample"].copy_(self.prev)
+                    ost["theta"].copy_(self.theta); ost["terms"].copy_(self.engine.terms)
+                    out_ready = torch.cuda.Event()
+                    out_ready.record(s)
+                ds.wait_event(out_ready)
+                with torch.cuda.stream(ds):
+                    for n in ost:
+                        out[n].copy_(ost[n], non_blocking=True)
+                    self._ev_out_free.record(ds)
+            for x in (cs, s, ds):
+                x.synchronize()
+        return outs
+
     def h2d_bytes_per_step(self) -> int:
         return 4 * (self.B * self.D ** 3 + 2 * self.B * self.L + self.B * 16)
 
