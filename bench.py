@@ -76,6 +76,16 @@ class ClockSampler(threading.Thread):
                 "samples": len(sm)}
 
 
+def ncu_traffic_bytes():
+    """dram__bytes_read.sum + dram__bytes_write.sum of one stream-kernel launch, from the committed
+    `ncu --set full` capture of the same workload (profiles/); None when absent."""
+    p = os.path.join(ROOT, "profiles", "r01_stream_kernel_ncu.json")
+    try:
+        return int(json.load(open(p))["traffic_bytes_per_launch"])
+    except Exception:
+        return None
+
+
 def measured_peak_gbs():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -264,6 +274,21 @@ def run_ours(args):
     torch.cuda.synchronize()
     eval_ms = s0.elapsed_time(s1) / NREP
 
+    # the same evaluation with every kernel in series on one stream (what a profiler's serialised launch
+    # list shows): the stream kernel's share of THAT is the number to hold against the ncu launch list
+    eng.serial = 1
+    desc_s = eng.make_desc(loop.sdf, loop.theta, st)
+    eng.serial = 0
+    for _ in range(3):
+        eng.launch(desc_s)
+    torch.cuda.synchronize()
+    s0.record()
+    for _ in range(NREP):
+        eng.launch(desc_s)
+    s1.record()
+    torch.cuda.synchronize()
+    eval_serial_ms = s0.elapsed_time(s1) / NREP
+
     # ---- max over ranks
     t = torch.tensor([ms, e2e_s, stream_ms, eval_ms], dtype=torch.float64, device=dev)
     if world > 1:
@@ -286,6 +311,7 @@ def run_ours(args):
                        "l2": "inputs larger than L2 (1.07 GB of volumes touched per evaluation vs 126 MB L2)",
                        "stream_variant": {0: "tma", 1: "ldg", 2: "tma"}.get(args.variant, "tma"),
                        "evals_per_sec": value * EVALS_PER_STEP, "eval_ms_standalone": eval_ms,
+                       "eval_ms_serialised": eval_serial_ms,
                        "eval_GBps_algorithmic": eval_bytes / (eval_ms * 1e-3) / 1e9},
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": loop.h2d_bytes_per_step(),
@@ -296,8 +322,12 @@ def run_ours(args):
             "roofline": {"bound": "hbm", "kernel": "k_stream_tma" if args.variant in (0, 2) else "k_stream_ldg",
                          "achieved": achieved, "peak": peak, "peak_kind": f"{peak_kind} burst copy (kernel timed alone)",
                          "unit": "GB/s", "frac": achieved / peak, "bytes_per_launch": stream_bytes,
-                         "ms_per_launch": stream_ms, "traffic": None,
-                         "share_of_eval": stream_ms / eval_ms},
+                         "ms_per_launch": stream_ms, "traffic": ncu_traffic_bytes(),
+                         "share_of_eval": stream_ms / eval_ms,
+                         "share_of_eval_serialised": stream_ms / eval_serial_ms,
+                         "note": "the sparse kernels run beside the stream kernel (fork/join), so it covers "
+                                 "share_of_eval of the evaluation's wall time; with every kernel in series "
+                                 "(as ncu replays them) its share is share_of_eval_serialised"},
         }
         if world == 1 and not args.no_cpu:
             eps, cores, n, el = cpu_guidance_evals_per_sec(args.cpu_seconds)
