@@ -175,11 +175,16 @@ def run_ours(args):
     local = int(os.environ.get("LOCAL_RANK", "0"))
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        if os.environ.get("NCCL_DEBUG", "").upper() == "VERSION":
+            os.environ["NCCL_DEBUG"] = "WARN"      # keep rank 0's stdout to the one JSON line
         dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local}"))
     if not torch.cuda.is_available():
         raise _lib.FohoLibraryError("bench.py needs a CUDA device; there is no CPU fallback for the product path")
     torch.cuda.set_device(local)
     dev = torch.device(f"cuda:{local}")
+    from followmyhold_b200.parallel import bind_to_gpu_numa
+    orig_affinity = os.sched_getaffinity(0)
+    numa = bind_to_gpu_numa(local)      # before the pinned staging buffers exist
     _lib.load()
     K, W = args.steps, max(3, args.warmup)
     B = B_PER_GPU
@@ -240,6 +245,15 @@ def run_ours(args):
     barrier()
     e2e_s = time.perf_counter() - t0
     assert all(torch.isfinite(o["terms"]).all() for o in outs), "non-finite terms in the end-to-end run"
+    # same, with the volumes (the mock decoder's state) resident and only latents / model output / leaves
+    # uploaded per step -- the traffic of the real loop, where the decoder produces the volume on the device
+    lat = (None, x_t_h, vel_h, theta_h)
+    loop.denoise_steps_host(STEP_INDEX, [batch, lat])
+    barrier()
+    t2 = time.perf_counter()
+    loop.denoise_steps_host(STEP_INDEX, [lat] * K2)
+    barrier()
+    e2e_lat_s = time.perf_counter() - t2
     # one batch alone (no overlap possible): the latency a single call sees
     t1 = time.perf_counter()
     loop.denoise_step_host(STEP_INDEX, sdf0_h, x_t_h, vel_h, theta_h)
@@ -290,10 +304,10 @@ def run_ours(args):
     eval_serial_ms = s0.elapsed_time(s1) / NREP
 
     # ---- max over ranks
-    t = torch.tensor([ms, e2e_s, stream_ms, eval_ms], dtype=torch.float64, device=dev)
+    t = torch.tensor([ms, e2e_s, stream_ms, eval_ms, e2e_lat_s], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms, e2e_s, stream_ms, eval_ms = [float(x) for x in t.tolist()]
+    ms, e2e_s, stream_ms, eval_ms, e2e_lat_s = [float(x) for x in t.tolist()]
 
     if rank == 0:
         value = world * B * K / (ms / 1e3)
@@ -311,13 +325,17 @@ def run_ours(args):
                        "l2": "inputs larger than L2 (1.07 GB of volumes touched per evaluation vs 126 MB L2)",
                        "stream_variant": {0: "tma", 1: "ldg", 2: "tma"}.get(args.variant, "tma"),
                        "evals_per_sec": value * EVALS_PER_STEP, "eval_ms_standalone": eval_ms,
-                       "eval_ms_serialised": eval_serial_ms,
+                       "eval_ms_serialised": eval_serial_ms, "host_numa": numa,
                        "eval_GBps_algorithmic": eval_bytes / (eval_ms * 1e-3) / 1e9},
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": loop.h2d_bytes_per_step(),
                     "d2h_bytes_per_step": loop.d2h_bytes_per_step(), "steps": K2,
                     "api": "GuidanceLoop.denoise_steps_host (pinned host buffers in and out, 3-stream pipeline)",
-                    "single_batch_ms": e2e_single_s * 1e3},
+                    "single_batch_ms": e2e_single_s * 1e3,
+                    "volumes_resident": {"value": world * B * K2 / e2e_lat_s, "unit": UNIT,
+                                         "h2d_bytes_per_step": 4 * (2 * B * loop.L + B * 16),
+                                         "note": "decoder base volumes stay on the device; latents, model output "
+                                                 "and leaves cross PCIe every step"}},
             "gpu_launches": K * loop.launches_per_step(),
             "roofline": {"bound": "hbm", "kernel": "k_stream_tma" if args.variant in (0, 2) else "k_stream_ldg",
                          "achieved": achieved, "peak": peak, "peak_kind": f"{peak_kind} burst copy (kernel timed alone)",
@@ -330,6 +348,7 @@ def run_ours(args):
                                  "(as ncu replays them) its share is share_of_eval_serialised"},
         }
         if world == 1 and not args.no_cpu:
+            os.sched_setaffinity(0, orig_affinity)      # the CPU leg gets every host core back
             eps, cores, n, el = cpu_guidance_evals_per_sec(args.cpu_seconds)
             line["cpu_baseline"] = {"value": eps / EVALS_PER_STEP, "unit": UNIT, "cores": cores, "kind": "port",
                                     "sample": f"{n} oracle guidance evaluations (fwd+bwd+AdamW) of ONE image of the "

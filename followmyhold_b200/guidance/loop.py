@@ -190,7 +190,8 @@ class GuidanceLoop:
     def denoise_steps_host(self, step_index: int, batches) -> list:
         """Guided-denoise steps for a sequence of image batches whose inputs live in pinned HOST memory
         (``batches``: iterable of ``(sdf0, x_t, velocity, theta)`` CPU tensors, each a different batch of
-        B images -- the way a rank works through its share of ``sorted(images)[rank::world]``).
+        B images -- the way a rank works through its share of ``sorted(images)[rank::world]``; ``sdf0``
+        may be ``None`` when the batch's decoder base volume is already on the device).
 
         Three streams: the upload of batch k+1 into a staging set overlaps the graph replay of batch k,
         whose results leave through a second staging set while batch k+1 computes.  Every byte still
@@ -221,7 +222,8 @@ class GuidanceLoop:
                 # upload into the staging set as soon as the previous batch has left it
                 cs.wait_event(self._ev_stage_free)
                 with torch.cuda.stream(cs):
-                    st["sdf0"].copy_(sdf0_h, non_blocking=True)
+                    if sdf0_h is not None:          # None: the decoder state of this batch is already resident
+                        st["sdf0"].copy_(sdf0_h, non_blocking=True)
                     st["x_t"].copy_(x_t_h, non_blocking=True)
                     st["velocity"].copy_(vel_h, non_blocking=True)
                     st["theta"].copy_(theta_h, non_blocking=True)
@@ -229,7 +231,9 @@ class GuidanceLoop:
                     h2d_done.record(cs)
                 s.wait_event(h2d_done)
                 with torch.cuda.stream(s):
-                    self.sdf0.copy_(st["sdf0"]); self.sdf.copy_(st["sdf0"])
+                    if sdf0_h is not None:
+                        self.sdf0.copy_(st["sdf0"])
+                    self.sdf.copy_(self.sdf0)
                     self.x_t.copy_(st["x_t"]); self.velocity.copy_(st["velocity"]); self.theta.copy_(st["theta"])
                     self._ev_stage_free.record(s)
                     self._graph.replay()

@@ -45,3 +45,42 @@ def aggregate_throughput(per_rank: List[Dict[str, float]]) -> float:
     units = sum(r["units"] for r in per_rank)
     secs = max(r["seconds"] for r in per_rank)
     return units / secs if secs > 0 else 0.0
+
+
+def parse_cpulist(text: str) -> List[int]:
+    """'0-3,8,10-11' -> [0,1,2,3,8,10,11] (the format of /sys/devices/system/node/node*/cpulist)."""
+    cpus: List[int] = []
+    for part in text.strip().split(","):
+        if not part:
+            continue
+        if "-" in part:
+            a, b = part.split("-")
+            cpus.extend(range(int(a), int(b) + 1))
+        else:
+            cpus.append(int(part))
+    return cpus
+
+
+def bind_to_gpu_numa(device_index: int, sysfs: str = "/sys") -> Dict[str, object]:
+    """Pin this process to the CPUs of the NUMA node its GPU hangs off, BEFORE any pinned host buffer
+    is allocated, so that every rank's H2D/D2H staging memory is local to its GPU's PCIe root (one
+    process per GPU; first-touch places the pages).  Best effort: returns what it found and did."""
+    info: Dict[str, object] = {"numa_node": None, "bound": False}
+    try:
+        p = torch.cuda.get_device_properties(device_index)
+        bdf = f"{p.pci_domain_id:04x}:{p.pci_bus_id:02x}:{p.pci_device_id:02x}.0"
+        with open(os.path.join(sysfs, "bus/pci/devices", bdf, "numa_node")) as f:
+            node = int(f.read().strip())
+        info["numa_node"] = node
+        if node < 0:
+            return info
+        with open(os.path.join(sysfs, f"devices/system/node/node{node}/cpulist")) as f:
+            cpus = parse_cpulist(f.read())
+        allowed = sorted(set(cpus) & set(os.sched_getaffinity(0)))
+        if allowed:
+            os.sched_setaffinity(0, allowed)
+            info["bound"] = True
+            info["cpus"] = len(allowed)
+    except Exception as e:      # no sysfs entry, no permission, old torch: stay unbound
+        info["error"] = type(e).__name__
+    return info

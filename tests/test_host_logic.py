@@ -145,3 +145,12 @@ def test_sharding_and_timing_gather_world2_gloo(tmp_path):
     assert res["mine"] == parts[0]
     assert [p["units"] for p in res["per"]] == [4.0, 3.0]
     assert abs(res["agg"] - 7.0 / 2.0) < 1e-12      # all units / slowest rank
+
+
+def test_cpulist_parser_and_numa_binding_is_best_effort(tmp_path):
+    from followmyhold_b200.parallel import bind_to_gpu_numa, parse_cpulist
+    assert parse_cpulist("0-3,8,10-11\n") == [0, 1, 2, 3, 8, 10, 11]
+    assert parse_cpulist("") == []
+    # no GPU here: the helper must not raise and must report that nothing was bound
+    info = bind_to_gpu_numa(0, sysfs=str(tmp_path))
+    assert info["bound"] is False
