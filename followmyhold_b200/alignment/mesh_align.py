@@ -164,6 +164,44 @@ def icp_points(source_points: np.ndarray, target_points: np.ndarray, n_iter: int
     return out
 
 
+def icp_points_many(problems, n_iter: int, n_outliers, fixed_scale: bool = False, min_scale: float = 0.5,
+                    max_scale: float = 2.0, device="cuda:0"):
+    """Several independent ICP loops at once (one per image of a batch), each on its own CUDA stream.
+
+    ``problems``: list of ``(source_points [Ns,3], target_points [Nt,3])``; ``n_outliers``: int or one
+    int per problem.  A single loop is latency bound (two small kernels per iteration, one of them a
+    single CTA), so the loops of different images overlap almost perfectly.  Returns a list of
+    ``(best_transform [4,4] float64, best_cost)`` -- each identical to what ``icp_points`` returns."""
+    lib = _lib.load()
+    dev = torch.device(device)
+    if dev.type != "cuda":
+        raise _lib.FohoLibraryError("icp needs a CUDA device; there is no CPU fallback")
+    n = len(problems)
+    outs = [n_outliers] * n if isinstance(n_outliers, int) else list(n_outliers)
+    keep = []
+    with torch.cuda.device(dev):
+        cur = torch.cuda.current_stream(dev)
+        streams = [torch.cuda.Stream(device=dev) for _ in range(n)]
+        for (src_np, tgt_np), n_out, st in zip(problems, outs, streams):
+            src = torch.as_tensor(np.ascontiguousarray(src_np, dtype=np.float64)).to(dev)
+            tgt = torch.as_tensor(np.ascontiguousarray(tgt_np, dtype=np.float64)).to(dev)
+            Ns, Nt = src.shape[0], tgt.shape[0]
+            nbytes = lib.foho_icp_workspace_bytes(Ns, Nt)
+            ws = torch.empty(nbytes + 256, dtype=torch.uint8, device=dev)
+            ws_ptr = ws.data_ptr() + ((-ws.data_ptr()) % 256)
+            T = torch.zeros(16, dtype=torch.float64, device=dev)
+            cost = torch.zeros(1, dtype=torch.float64, device=dev)
+            st.wait_stream(cur)
+            _lib.check("foho_icp_run", lib.foho_icp_run(
+                src.data_ptr(), Ns, tgt.data_ptr(), Nt, int(n_iter), int(n_out), int(bool(fixed_scale)),
+                float(min_scale), float(max_scale), T.data_ptr(), cost.data_ptr(), None, None,
+                C.c_void_p(ws_ptr), nbytes, C.c_void_p(st.cuda_stream)))
+            keep.append((src, tgt, ws, T, cost))
+        for st in streams:
+            st.synchronize()
+    return [(T.cpu().numpy().reshape(4, 4), float(cost.item())) for (_, _, _, T, cost) in keep]
+
+
 def icp(source_mesh: Geometry, target_mesh: Geometry, n_iter: int, count_source: int = 5_000,
         count_target: int = 5_000, test_reflections: bool = False, test_rotations: bool = False,
         fixed_scale: bool = False, outliers: float = 0, on_surface: bool = False, min_scale: float = 0.5,

@@ -21,7 +21,8 @@
 namespace {
 
 constexpr int NN_THREADS = 256;
-constexpr int NN_TILE = 1024;          // target points staged per shared-memory tile
+constexpr int NN_TILE = 256;           // target points staged per shared-memory tile
+constexpr int NN_MAX_CHUNKS = 128;
 constexpr int STEP_THREADS = 1024;
 
 struct IcpState {
@@ -49,11 +50,12 @@ inline void icp_ws_layout(IcpWorkspace &w, char *base, int Ns, int Nt) {
   auto take = [&](size_t bytes) { char *p = base ? base + off : nullptr; off += foho_align_up(bytes, 256); return p; };
   // enough chunks to fill the machine, each a multiple of the smem tile
   int blocks_s = (Ns + NN_THREADS - 1) / NN_THREADS;
-  int want = (4 * 148 + blocks_s - 1) / blocks_s;
+  // FP64 issue is the limit (64 lanes per SM): spread the Ns x Nt distance evaluations over ~2 CTAs per SM
+  int want = (2 * 148 + blocks_s - 1) / blocks_s;
   int max_chunks = (Nt + NN_TILE - 1) / NN_TILE;
   int nchunks = want < max_chunks ? want : max_chunks;
   if (nchunks < 1) nchunks = 1;
-  if (nchunks > 64) nchunks = 64;
+  if (nchunks > NN_MAX_CHUNKS) nchunks = NN_MAX_CHUNKS;
   int chunk = (Nt + nchunks - 1) / nchunks;
   chunk = (chunk + NN_TILE - 1) / NN_TILE * NN_TILE;
   nchunks = (Nt + chunk - 1) / chunk;
@@ -127,10 +129,30 @@ __device__ double block_sum_d(double v, double *sm) {
   return r;
 }
 
+// N sums at once: one pair of barriers for all of them; fixed order => deterministic, same value everywhere
+template <int N>
+__device__ void block_sum_dn(double (&v)[N], double *sm /* [N*32] */) {
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
+#pragma unroll
+  for (int k = 0; k < N; ++k)
+    for (int o = 16; o > 0; o >>= 1) v[k] += __shfl_xor_sync(0xffffffffu, v[k], o);
+  __syncthreads();
+  if (lane == 0)
+#pragma unroll
+    for (int k = 0; k < N; ++k) sm[k * 32 + wid] = v[k];
+  __syncthreads();
+#pragma unroll
+  for (int k = 0; k < N; ++k) {
+    double r = 0;
+    for (int w = 0; w < nw; ++w) r += sm[k * 32 + w];
+    v[k] = r;
+  }
+}
+
 __global__ void __launch_bounds__(STEP_THREADS) k_icp_step(const double *__restrict__ tgt, int Ns, int n_outliers,
                                                            int fixed_scale, double min_scale, double max_scale,
                                                            IcpWorkspace w, double *cost_history, int *nn_out) {
-  __shared__ double smd[32];
+  __shared__ double smd[11 * 32];
   __shared__ unsigned int hist[256];
   __shared__ unsigned long long s_prefix;
   __shared__ int s_remaining;
@@ -164,21 +186,43 @@ __global__ void __launch_bounds__(STEP_THREADS) k_icp_step(const double *__restr
       __syncthreads();
       const unsigned long long prefix = s_prefix;
       const unsigned long long mask = shift == 56 ? 0ull : (~0ull << (shift + 8));
-      for (int i = tid; i < Ns; i += STEP_THREADS) {
-        unsigned long long bits = (unsigned long long)__double_as_longlong(w.dist[i]);
-        if ((bits & mask) == prefix) atomicAdd(&hist[(bits >> shift) & 255ull], 1u);
+      // the distances share their leading bytes, so most lanes of a warp hit the same bucket: one
+      // shared-memory atomic per distinct digit per warp instead of one per element
+      for (int base = 0; base < Ns; base += STEP_THREADS) {
+        const int i = base + tid;
+        unsigned int key = 256u;                                  // 256 = not a candidate
+        if (i < Ns) {
+          const unsigned long long bits = (unsigned long long)__double_as_longlong(w.dist[i]);
+          if ((bits & mask) == prefix) key = (unsigned int)((bits >> shift) & 255ull);
+        }
+        const unsigned peers = __match_any_sync(0xffffffffu, key);
+        if (key < 256u && (tid & 31) == __ffs(peers) - 1) atomicAdd(&hist[key], (unsigned int)__popc(peers));
       }
       __syncthreads();
-      if (tid == 0) {
-        int rem = s_remaining;
-        int bkt = 0;
-        for (; bkt < 256; ++bkt) {
-          if ((int)hist[bkt] >= rem) break;
-          rem -= (int)hist[bkt];
+      if (tid < 32) {
+        // warp 0: lane l owns buckets 8l..8l+7; find the bucket holding the s_remaining-th element
+        const int rem0 = s_remaining;
+        unsigned int c[8], tot = 0;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) { c[k] = hist[tid * 8 + k]; tot += c[k]; }
+        unsigned int incl = tot;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const unsigned int t = __shfl_up_sync(0xffffffffu, incl, o); if (tid >= o) incl += t; }
+        const unsigned int excl = incl - tot;
+        const bool mine = (int)excl < rem0 && (int)incl >= rem0;          // exactly one lane (rem0 <= total)
+        const unsigned who = __ballot_sync(0xffffffffu, mine);
+        if (who == 0u) {
+          if (tid == 0) { s_prefix = prefix | (255ull << shift); s_remaining = 0; }
+        } else if (mine) {
+          int rem = rem0 - (int)excl, bkt = 0;
+          for (; bkt < 8; ++bkt) {
+            if ((int)c[bkt] >= rem) break;
+            rem -= (int)c[bkt];
+          }
+          if (bkt > 7) bkt = 7;
+          s_prefix = prefix | ((unsigned long long)(tid * 8 + bkt) << shift);
+          s_remaining = rem;
         }
-        if (bkt > 255) bkt = 255;
-        s_prefix = prefix | ((unsigned long long)bkt << shift);
-        s_remaining = rem;
       }
       __syncthreads();
     }
@@ -238,8 +282,10 @@ __global__ void __launch_bounds__(STEP_THREADS) k_icp_step(const double *__restr
   }
   const double n = (double)n_in;
   double am[3], bm[3];
-  for (int a = 0; a < 3; ++a) { am[a] = block_sum_d(sa[a], smd) / n; bm[a] = block_sum_d(sb[a], smd) / n; }
-  const double cost = block_sum_d(sd, smd) / n;
+  double r7[7] = {sa[0], sa[1], sa[2], sb[0], sb[1], sb[2], sd};
+  block_sum_dn<7>(r7, smd);
+  for (int a = 0; a < 3; ++a) { am[a] = r7[a] / n; bm[a] = r7[3 + a] / n; }
+  const double cost = r7[6] / n;
   double h[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0}, va = 0, vb = 0;
   for (int i = tid; i < Ns; i += STEP_THREADS) {
     bool in = is_inlier(i, dummy);
@@ -255,9 +301,11 @@ __global__ void __launch_bounds__(STEP_THREADS) k_icp_step(const double *__restr
     h[6] += b2 * a0; h[7] += b2 * a1; h[8] += b2 * a2;
   }
   double H[3][3];
-  for (int k = 0; k < 9; ++k) H[k / 3][k % 3] = block_sum_d(h[k], smd);
-  va = block_sum_d(va, smd);
-  vb = block_sum_d(vb, smd);
+  double r11[11] = {h[0], h[1], h[2], h[3], h[4], h[5], h[6], h[7], h[8], va, vb};
+  block_sum_dn<11>(r11, smd);
+  for (int k = 0; k < 9; ++k) H[k / 3][k % 3] = r11[k];
+  va = r11[9];
+  vb = r11[10];
 
   // 4. similarity fit + transform update (thread 0)
   if (tid == 0) {

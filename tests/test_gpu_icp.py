@@ -100,3 +100,19 @@ def test_align_meshes_impl_files(tmp_path):
     mano.run(str(ham), str(hun), str(out))
     g = meshio.load(str(out / "12_hamer_aligned_mano.ply"))
     assert g.vertices.shape == (778, 3) and g.faces.shape == (1538, 3)
+
+
+@pytest.mark.gpu
+def test_concurrent_loops_equal_single_loops():
+    """icp_points_many (one stream per problem) returns exactly what icp_points returns per problem."""
+    from followmyhold_b200.alignment.mesh_align import icp_points, icp_points_many
+    rng = np.random.default_rng(5)
+    probs = []
+    for k in range(4):
+        tgt = rng.normal(size=(1500 + 100 * k, 3))
+        src = (tgt[:400 + 10 * k] - 0.03) / (1.05 + 0.01 * k) + 0.005 * rng.normal(size=(400 + 10 * k, 3))
+        probs.append((src, tgt))
+    many = icp_points_many(probs, 15, [80, 82, 84, 86], False, 0.7, 3.0)
+    for (src, tgt), n_out, (T, c) in zip(probs, [80, 82, 84, 86], many):
+        T1, c1 = icp_points(src, tgt, 15, n_out, False, 0.7, 3.0)
+        assert np.array_equal(T, T1) and c == c1
