@@ -993,7 +993,7 @@ extern "C" int foho_guidance_energy_fwd_bwd(const foho_guidance_desc *dp, void *
     FOHO_CUDA_TRY(cudaStreamWaitEvent(st, fc->join_a, 0));
   }
   if (sm & 16) {
-    k_assemble<<<dim3(8, d.B), ASM_THREADS, 0, st>>>(d, ws, gx, (sm & 8) ? 1 : 0);
+    k_assemble<<<dim3(8, d.B), ASM_THREADS, 0, st>>>(d, ws, (sm & 2) ? gx : 0, (sm & 8) ? 1 : 0);
     FOHO_LAUNCH_CHECK();
   }
   if (obj_mesh && (sm & 16)) {

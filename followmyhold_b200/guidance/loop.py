@@ -72,6 +72,7 @@ class GuidanceLoop:
         self.sigmas = set_timesteps_sigmas(self.cfg.num_inference_steps)
         self._graph: Optional[torch.cuda.CUDAGraph] = None
         self._graph_key = None
+        self._sched_graphs: Dict[tuple, torch.cuda.CUDAGraph] = {}
         self.stream = torch.cuda.Stream(device=dev)
         self.copy_stream = torch.cuda.Stream(device=dev)
         self._pinned: Dict[str, torch.Tensor] = {}
@@ -83,37 +84,89 @@ class GuidanceLoop:
         self.theta[:, 0] = 1.0; self.theta[:, 4] = 1.0
         self.theta[:, 8] = 1.0; self.theta[:, 12] = 1.0
 
+    # ------------------------------------------------------------------ phases
+    def phase_of_step(self, step_index: int) -> float:
+        """Which optimisation the reference runs at denoise step ``i`` (pipelines.py:1293-1295,1361,1455):
+        0 = none (plain scheduler.step), 1 = hand only, 1.5 = object only, 2 = joint."""
+        c = self.cfg
+        if step_index < c.handopt_start_step or step_index > c.guidance_end_step:
+            return 0
+        if step_index == c.handopt_start_step:
+            return 1
+        if step_index == c.handopt_start_step + 1:
+            return 1.5
+        return 2
+
+    def phase_iterations(self, phase: float) -> int:
+        c = self.cfg
+        return {0: 0, 1: c.optimization_steps_hand, 1.5: c.optimization_steps_scale, 2: c.optimization_steps_joint}[phase]
+
+    def phase_weights(self, phase: float):
+        """Loss weights per phase.  REF literals: phase 1 ``total_hand_loss`` = 1e-2 kp + 1e-2 treg_h (+ image
+        terms, pipelines.py:1343-1349); phase 1.5 ``total_obj_loss`` = 1e-3 verts + 1e-2 treg_o (+ image/edge
+        terms, :1433-1440); phase 2 = the defaults (:1499-1504,1578-1588).  The NS data terms follow the
+        leaves being optimised: the chamfer to the observed cloud in the hand phase (it stands where the
+        reference's rendered hand-vs-MoGe terms stand), the volume terms in the object phases."""
+        base = self.engine.weights
+        if phase == 2:
+            return base
+        w = _lib.Weights()
+        C.memmove(C.byref(w), C.byref(base), C.sizeof(_lib.Weights))
+        if phase == 1:
+            w.w_hand, w.w_kp, w.w_treg_h = 1.0, 1e-2, 1e-2
+            for n in ("w_pen", "w_con", "w_ivol", "w_mom", "w_treg_o", "w_int_lo", "w_int_hi", "w_dist", "w_vreg", "w_edge"):
+                setattr(w, n, 0.0)
+        elif phase == 1.5:
+            w.w_treg_o = 1e-2
+            w.w_hand = 0.0
+            w.w_ch = 0.0
+        return w
+
     def kernels_per_eval(self) -> int:
         return self.engine.launches_per_eval + 3     # + decoder fwd, decoder adjoint, fused update
 
     # ------------------------------------------------------------------ one evaluation (enqueue only)
-    def _enqueue_eval(self, sigma: float, late_step: bool, s: torch.cuda.Stream) -> None:
+    def _enqueue_eval(self, sigma: float, late_step: bool, s: torch.cuda.Stream, phase: float = 2) -> None:
         lib, B, vol = self.lib, self.B, self.D ** 3
         sp = C.c_void_p(s.cuda_stream)
-        _lib.check("foho_mock_decoder_forward", lib.foho_mock_decoder_forward(
-            self.sdf.data_ptr(), self.sdf0.data_ptr(), self.x1.data_ptr(), self.tap.data_ptr(), B, vol, self.L,
-            self.alpha, sp))
+        hand_only = phase == 1
+        if not hand_only:
+            _lib.check("foho_mock_decoder_forward", lib.foho_mock_decoder_forward(
+                self.sdf.data_ptr(), self.sdf0.data_ptr(), self.x1.data_ptr(), self.tap.data_ptr(), B, vol, self.L,
+                self.alpha, sp))
         desc = self.engine.make_desc(self.sdf, self.theta, self.statics, late_step=late_step)
+        if phase != 2:
+            self._phase_w = self.phase_weights(phase)      # keep the struct alive while the call reads it
+            desc.w = self._phase_w
+        if hand_only:
+            desc.stage_mask = 1 | 4 | 16                   # no volume term has weight: skip the stream and the voxels
         self.engine.launch(desc, s)
-        _lib.check("foho_mock_decoder_backward", lib.foho_mock_decoder_backward(
-            self.engine.grad_sdf.data_ptr(), self.tap.data_ptr(), self.grad_velocity.data_ptr(), B, vol, self.L,
-            self.alpha * (1.0 - sigma), sp))
+        if not hand_only:
+            _lib.check("foho_mock_decoder_backward", lib.foho_mock_decoder_backward(
+                self.engine.grad_sdf.data_ptr(), self.tap.data_ptr(), self.grad_velocity.data_ptr(), B, vol, self.L,
+                self.alpha * (1.0 - sigma), sp))
         self.opt.step(self.theta, self.engine.grad_theta, self.velocity, self.grad_velocity, self.x_t, self.x1,
                       sigma=sigma, stream=s)
 
-    def _enqueue_step(self, step_index: int, s: torch.cuda.Stream) -> None:
-        """All kernels of one guided-denoise step (pipelines.py:1461-1612), no syncs."""
+    def _enqueue_step(self, step_index: int, s: torch.cuda.Stream, phase: float = 2) -> None:
+        """All kernels of one guided-denoise step (pipelines.py:1293-1612), no syncs.  ``phase``: 1 hand
+        only (:1295-1358), 1.5 object only (:1361-1453), 2 joint (:1455-1601), 0 plain ``scheduler.step``."""
         cfg = self.cfg
         sigma = float(self.sigmas[step_index]); sigma_next = float(self.sigmas[step_index + 1])
         late = step_index >= cfg.num_inference_steps - 3
-        self.opt.set_phase(2)
-        self.opt.reset()                                   # fresh AdamW state every outer step (:1478)
+        if phase == 0:
+            _lib.check("foho_scheduler_step", self.lib.foho_scheduler_step(
+                self.x_t.data_ptr(), self.velocity.data_ptr(), self.prev.data_ptr(), None, self.x_t.numel(), sigma,
+                sigma_next, C.c_void_p(s.cuda_stream)))
+            return
+        self.opt.set_phase(phase)
+        self.opt.reset()                                   # fresh optimiser state every outer step (:1318,1384,1478)
         # x1 for the first decode of this step: step_final with the incoming velocity (:1507)
         _lib.check("foho_scheduler_step", self.lib.foho_scheduler_step(
             self.x_t.data_ptr(), self.velocity.data_ptr(), None, self.x1.data_ptr(), self.x_t.numel(), sigma, sigma_next,
             C.c_void_p(s.cuda_stream)))
-        for _ in range(cfg.optimization_steps_joint):
-            self._enqueue_eval(sigma, late, s)
+        for _ in range(self.phase_iterations(phase)):
+            self._enqueue_eval(sigma, late, s, phase)
         # obj_latents = scheduler.step(noise_pred_obj, t, obj_latents).prev_sample (:1612)
         _lib.check("foho_scheduler_step", self.lib.foho_scheduler_step(
             self.x_t.data_ptr(), self.velocity.data_ptr(), self.prev.data_ptr(), None, self.x_t.numel(), sigma, sigma_next,
@@ -139,6 +192,43 @@ class GuidanceLoop:
             with torch.cuda.graph(g, stream=s):
                 self._enqueue_step(step_index, s)
             self._graph, self._graph_key = g, step_index
+            torch.cuda.current_stream(self.device).wait_stream(s)
+
+    def run_schedule_device(self, model_output, first_step: int = 0, last_step: Optional[int] = None,
+                            use_graphs: bool = True) -> None:
+        """The reference's whole guided denoise loop for the B resident images (pipelines.py:1262-1612):
+        for every step i, ``velocity <- model_output(i, x_t)`` (the DiT + CFG prediction, out of this
+        path's scope: a callable or a sequence of [B,L] device tensors), the phase's optimisation (hand
+        only at ``handopt_start_step``, object only at the next step, joint afterwards), then
+        ``x_t <- scheduler.step(velocity, x_t)``.  Leaves carry over from step to step (:1604-1610)."""
+        cfg = self.cfg
+        last = cfg.num_inference_steps - 1 if last_step is None else last_step
+        with torch.cuda.device(self.device):
+            s = self.stream
+            s.wait_stream(torch.cuda.current_stream(self.device))
+            for i in range(first_step, last + 1):
+                v = model_output(i, self.x_t) if callable(model_output) else model_output[i]
+                with torch.cuda.stream(s):
+                    self.velocity.copy_(v)
+                    phase = self.phase_of_step(i)
+                    if use_graphs and phase != 0:
+                        key = (i, phase)
+                        g = self._sched_graphs.get(key)
+                        if g is None:
+                            # one evaluation outside the capture (function attributes, lazily created side
+                            # streams); it moves the leaves, so put them back before the real run
+                            theta_keep = self.theta.clone()
+                            self._enqueue_eval(float(self.sigmas[i]), False, s, phase)
+                            s.synchronize()
+                            self.theta.copy_(theta_keep); self.velocity.copy_(v)
+                            g = torch.cuda.CUDAGraph()
+                            with torch.cuda.graph(g, stream=s):
+                                self._enqueue_step(i, s, phase)
+                            self._sched_graphs[key] = g
+                        g.replay()
+                    else:
+                        self._enqueue_step(i, s, phase)
+                    self.x_t.copy_(self.prev)
             torch.cuda.current_stream(self.device).wait_stream(s)
 
     def run_step_device(self, step_index: int) -> None:
