@@ -1,0 +1,382 @@
+"""Guidance stage: same ``run(...)`` signature, CLI flags, per-index file contract, skip rules and
+error behaviour as the reference stage ``src/foho/guidance/run.py:188-289`` -- with the guided
+denoise loop of ``Hunyuan3DDiTFlowMatchingPipeline_main.__call__``
+(third_party_patches/hy3dgen/shapegen/pipelines.py:1262-1612) running through ``GuidanceLoop``
+(batched over images, one CUDA graph per denoise step) instead of one image at a time in PyTorch.
+
+What this stage does NOT contain are the two networks of the reference loop, which are outside the
+hot path this package replaces: the Hunyuan3D DiT that predicts the flow velocity at
+every step (pipelines.py:1262-1291) and the ShapeVAE that decodes latents to the volume
+(``latent2sdf``, :292-338).  They enter through a ``GuidanceModel`` object (protocol below); the
+reference's own networks would be wrapped in one.  Without a model the stage fails loudly -- there
+is no fallback.  ``MockGuidanceModel`` (synthetic volumes, the linear tap decoder of
+``foho_mock_decoder_*``) exists for tests and synthetic runs.
+
+Differences a maintainer should know:
+  * the MoGe geometry is read from ``{i}_cropped_hoi/pointcloud.ply`` (or ``mesh.ply``): the guidance
+    energy consumes it as a point cloud; ``mesh.glb`` (which the reference renders, run.py:215) is not
+    read;
+  * images are processed ``batch_size`` at a time; under ``torchrun`` rank r takes
+    ``sorted(images)[r::world]`` (or chunk r of ``task_list_file``, like ``SLURM_ARRAY_TASK_ID``);
+  * mesh post-processing (``FloaterRemover`` ... run.py:158-161) is left to the model's
+    ``extract_mesh``.
+"""
+from __future__ import annotations
+
+import argparse
+import importlib
+import json
+import os
+from typing import List, Optional, Sequence, Tuple
+
+import numpy as np
+import torch
+
+from .. import _lib
+from ..meshio import TriMesh, load, write_ply
+from ..parallel import rank_world, shard_images, task_chunk
+from ..synthetic import cap_boundary_loops, quat_to_mat_np
+from .config import OptimizationConfig
+from .engine import GuidanceStatics
+
+J_REGRESSOR_PATH = "./third_party/estimator/hamer/J_regressor_hamer.pt"     # cwd-relative, pipelines.py:1218
+MODEL_ENV = "FOHO_B200_GUIDANCE_MODEL"                                      # "package.module:factory"
+
+
+class GuidanceModel:
+    """What the stage needs from the networks (duck-typed; subclassing is optional).
+
+    ``D``: lattice points per axis of the decoded volume (reference 65); ``latent_elems``: 3072*64.
+    All tensors live on ``device``."""
+    D: int
+    latent_elems: int
+
+    def begin_batch(self, indices: Sequence[str], image_paths: Sequence[str], device) -> None:
+        """Condition on the batch's images (pipelines.py:1204-1260: image encoder, CFG setup)."""
+        raise NotImplementedError
+
+    def initial_latents(self, batch: int, generator: torch.Generator) -> torch.Tensor:
+        """x_T [B, latent_elems] (``prepare_latents``, pipelines.py:700)."""
+        raise NotImplementedError
+
+    def predict(self, step: int, x_t: torch.Tensor) -> torch.Tensor:
+        """The DiT's classifier-free-guided flow velocity for this step, [B, latent_elems] (:1262-1291)."""
+        raise NotImplementedError
+
+    def decoder_state(self):
+        """(sdf0 [B,D,D,D], tap int64 [latent_elems], alpha) of the linear tap decoder the loop drives;
+        a network decoder plugs in through ``GuidanceFunction`` instead."""
+        raise NotImplementedError
+
+    def extract_mesh(self, sdf: np.ndarray) -> Tuple[np.ndarray, np.ndarray]:
+        """Surface of one decoded volume [D,D,D] (negative inside) -> (verts in Hunyuan space, faces)."""
+        raise NotImplementedError
+
+
+def load_model_from_env() -> Optional[GuidanceModel]:
+    spec = os.environ.get(MODEL_ENV)
+    if not spec:
+        return None
+    mod, _, fn = spec.partition(":")
+    return getattr(importlib.import_module(mod), fn or "make_model")()
+
+
+# --------------------------------------------------------------------------- per-index inputs
+def index_paths(cropped_obj_img: str, cropped_obj_img_dir: str, mask_dir: str, moge_out_dir: str,
+                hunyuan_hoi_mesh_dir: str, hamer_out_dir: str, h2m_rt_dir: str, aligned_mano_dir: str,
+                guidance_out_dir: str) -> dict:
+    """File names of one image, exactly as the reference derives them (run.py:210-222)."""
+    index = cropped_obj_img.split("_")[0]
+    moge_dir = os.path.join(moge_out_dir, f"{index}_cropped_hoi")
+    return dict(
+        index=index,
+        cropped_obj_img_path=os.path.join(cropped_obj_img_dir, cropped_obj_img),
+        cropped_hand_mask_path=os.path.join(mask_dir, f"{index}_cropped_hand_mask.png"),
+        cropped_obj_mask_path=os.path.join(mask_dir, f"{index}_cropped_obj_mask.png"),
+        moge_dir=moge_dir,
+        moge_fov_path=os.path.join(moge_dir, "fov.json"),
+        T_h2m_path=os.path.join(h2m_rt_dir, f"{index}_hoi_mesh.npy"),
+        aligned_mano_mesh_path=os.path.join(aligned_mano_dir, f"{index}_hamer_aligned_mano.ply"),
+        hunyuan_hoi_mesh_path=os.path.join(hunyuan_hoi_mesh_dir, f"{index}_hoi_mesh.ply"),
+        hamer_for_guid_path=os.path.join(hamer_out_dir, f"{index}_kps_for_guidance.npy"),
+        save_path_obj=os.path.join(guidance_out_dir, f"{index}_obj.ply"),
+        save_path_hand=os.path.join(guidance_out_dir, f"{index}_hand.ply"),
+    )
+
+
+def _read_mask(path: str) -> np.ndarray:
+    import cv2
+    m = cv2.imread(path, cv2.IMREAD_UNCHANGED)
+    if m is None:
+        raise FileNotFoundError(path)
+    return m
+
+
+def load_image_inputs(p: dict, n_cloud: int, rng: np.random.Generator) -> dict:
+    """Everything ``__call__`` loads per image before its loop (pipelines.py:1218-1256), as arrays."""
+    with open(p["moge_fov_path"], "r", encoding="utf-8") as f:
+        fovx = float(json.load(f)["fov_x"])                                        # run.py:228-230
+    hand_mask = _read_mask(p["cropped_hand_mask_path"])
+    obj_mask = _read_mask(p["cropped_obj_mask_path"])
+    if hand_mask.max() == 0 or obj_mask.max() == 0:                                # run.py:234-236
+        return {"skip": "empty mask"}
+    H, W = hand_mask.shape[:2]                                                     # run.py:80-82
+    hamer = np.load(p["hamer_for_guid_path"], allow_pickle=True).item()            # pipelines.py:1219-1220
+    kps = np.asarray(hamer["mano_2d_kps"], dtype=np.float32).reshape(21, 2)
+    mano = load(p["aligned_mano_mesh_path"])                                       # :1223 (Hunyuan space)
+    if not isinstance(mano, TriMesh):
+        raise ValueError(f"{p['aligned_mano_mesh_path']} has no faces")
+    T = np.load(p["T_h2m_path"]).astype(np.float64).reshape(4, 4)                  # :1240
+    hand_moge = mano.vertices.astype(np.float64) @ T[:3, :3].T + T[:3, 3]          # :1241 transform_hunyuan2moge
+    cloud_path = None
+    for name in ("pointcloud.ply", "mesh.ply"):
+        if os.path.isfile(os.path.join(p["moge_dir"], name)):
+            cloud_path = os.path.join(p["moge_dir"], name)
+            break
+    if cloud_path is None:
+        raise FileNotFoundError(f"no MoGe geometry (pointcloud.ply / mesh.ply) in {p['moge_dir']}")
+    pts = np.asarray(load(cloud_path).vertices, dtype=np.float64)
+    if pts.shape[0] >= n_cloud:
+        pts = pts[rng.choice(pts.shape[0], n_cloud, replace=False)]
+    else:                                                                           # fewer points than the batch size: repeat them cyclically
+        pts = pts[np.resize(np.arange(pts.shape[0]), n_cloud)]
+    return dict(fovx=fovx, hw=(H, W), kps=kps, hand_moge=hand_moge.astype(np.float32),
+                faces=np.asarray(mano.faces, dtype=np.int32), T_h2m=T.astype(np.float32), cloud=pts.astype(np.float32))
+
+
+def similarity_about(points: np.ndarray, theta8: np.ndarray, center: np.ndarray) -> np.ndarray:
+    """``transform_mesh_around_center_w_scale`` (pipelines.py:108-118) for a fixed centre."""
+    R = quat_to_mat_np(theta8[4:8])
+    return (float(theta8[0]) * (points - center)) @ R.T + center + theta8[1:4]
+
+
+# --------------------------------------------------------------------------- the stage
+def _load_task_list(task_list_file: Optional[str], cropped_obj_img_dir: str) -> List[str]:
+    """run.py:178-185, with the torchrun rank standing in for SLURM_ARRAY_TASK_ID."""
+    rank, world = rank_world()
+    if task_list_file and os.path.exists(task_list_file):
+        with open(task_list_file, "r", encoding="utf-8") as f:
+            chunks = json.load(f)
+        task_id = int(os.environ.get("SLURM_ARRAY_TASK_ID", rank))
+        return task_chunk(chunks, task_id)
+    return shard_images(os.listdir(cropped_obj_img_dir), rank, world)
+
+
+def run(
+    project_root: str,
+    cropped_obj_img_dir: str,
+    mask_dir: str,
+    moge_out_dir: str,
+    hunyuan_hoi_mesh_dir: str,
+    hamer_out_dir: str,
+    h2m_rt_dir: str,
+    aligned_mano_dir: str,
+    guidance_out_dir: str,
+    task_list_file: Optional[str] = None,
+    *,
+    model: Optional[GuidanceModel] = None,
+    batch_size: int = 8,
+    n_cloud: int = 65536,
+    device: str = "cuda:0",
+    config: Optional[OptimizationConfig] = None,
+    j_regressor_path: str = J_REGRESSOR_PATH,
+    seed: int = 2,
+) -> None:
+    """Positional/keyword arguments up to ``task_list_file`` are the reference's (run.py:188-199)."""
+    del project_root                      # the reference only uses it to extend sys.path (run.py:57-62)
+    if model is None:
+        model = load_model_from_env()
+    if model is None:
+        raise _lib.FohoLibraryError(
+            "the guidance stage needs the Hunyuan3D networks (DiT velocity + latent->SDF decoder) wrapped in a "
+            f"GuidanceModel: pass model=... or set {MODEL_ENV}=package.module:factory.  There is no fallback.")
+    _lib.load()
+    config = config or OptimizationConfig()
+    os.makedirs(guidance_out_dir, exist_ok=True)
+    assigned_imgs = _load_task_list(task_list_file, cropped_obj_img_dir)
+    rng = np.random.default_rng(seed)
+
+    # ---- gather the images that are to be processed (skip rules of run.py:224-236)
+    todo = []
+    for cropped_obj_img in assigned_imgs:
+        try:
+            p = index_paths(cropped_obj_img, cropped_obj_img_dir, mask_dir, moge_out_dir, hunyuan_hoi_mesh_dir,
+                            hamer_out_dir, h2m_rt_dir, aligned_mano_dir, guidance_out_dir)
+            if os.path.exists(p["save_path_obj"]) and os.path.exists(p["save_path_hand"]):
+                print(f"{p['index']} already exists, skipping")
+                continue
+            inp = load_image_inputs(p, n_cloud, rng)
+            if "skip" in inp:
+                print(f"Skipping {p['index']} due to {inp['skip']}")
+                continue
+            todo.append((p, inp))
+        except Exception as e:                                   # run.py:257-259: report and go on
+            print(f"Error in processing {cropped_obj_img} : {e}")
+    if not todo:
+        print("Finished processing all images")
+        return
+    J = torch.load(j_regressor_path, map_location="cpu")
+    J = torch.as_tensor(np.asarray(J), dtype=torch.float32).reshape(16, -1)
+
+    from .loop import GuidanceLoop
+    dev = torch.device(device)
+    for b0 in range(0, len(todo), batch_size):
+        chunk = todo[b0:b0 + batch_size]
+        idx = [p["index"] for p, _ in chunk]
+        try:
+            _run_batch(chunk, model, J, config, n_cloud, dev, seed, GuidanceLoop)
+            for i in idx:
+                print(f"Reconstructed object {i}")
+        except Exception as e:
+            print(f"Error in reconstruction for {idx} : {e}")
+    print("Finished processing all images")
+
+
+def _run_batch(chunk, model: GuidanceModel, J: torch.Tensor, config: OptimizationConfig, n_cloud: int, dev, seed: int,
+               GuidanceLoop) -> None:
+    B = len(chunk)
+    inputs = [inp for _, inp in chunk]
+    faces0 = inputs[0]["faces"]
+    for inp in inputs[1:]:
+        if inp["faces"].shape != faces0.shape or not np.array_equal(inp["faces"], faces0):
+            raise ValueError("images of one batch must share the hand topology (MANO)")
+    if len({inp["hw"] for inp in inputs}) != 1 or len({round(inp["fovx"], 6) for inp in inputs}) != 1:
+        raise ValueError("images of one batch must share the crop size and field of view; use batch_size=1 otherwise")
+    capped = cap_boundary_loops(faces0)                          # closed topology for the sign rule
+    st = GuidanceStatics(
+        hand_rest=torch.from_numpy(np.stack([i["hand_moge"] for i in inputs])).to(dev).contiguous(),
+        hand_faces=torch.from_numpy(capped.astype(np.int32)).to(dev).contiguous(),
+        cloud=torch.from_numpy(np.stack([i["cloud"] for i in inputs])).to(dev).contiguous(),
+        T_h2m=torch.from_numpy(np.stack([i["T_h2m"] for i in inputs])).to(dev).contiguous(),
+        obj_center=torch.from_numpy(np.stack([i["T_h2m"][:3, 3] for i in inputs])).to(dev).contiguous(),
+        j_regressor=J.to(dev).contiguous(),
+        kps_2d=torch.from_numpy(np.stack([i["kps"] for i in inputs])).to(dev).contiguous(),
+        fov_deg=inputs[0]["fovx"], image_hw=inputs[0]["hw"])
+    model.begin_batch([p["index"] for p, _ in chunk], [p["cropped_obj_img_path"] for p, _ in chunk], dev)
+    sdf0, tap, alpha = model.decoder_state()
+    loop = GuidanceLoop(B, model.D, st, n_cloud, device=dev, config=config, latent_elems=model.latent_elems,
+                        decoder_alpha=float(alpha))
+    loop.tap = tap.to(dev).to(torch.int64).contiguous()
+    loop.sdf0.copy_(sdf0); loop.sdf.copy_(sdf0)
+    gen = torch.Generator().manual_seed(seed)                   # run.py:120 torch.manual_seed(2)
+    loop.x_t.copy_(model.initial_latents(B, gen))
+    loop.reset_leaves()
+    loop.run_schedule_device(model.predict)
+    # ---- outputs (pipelines.py:1641-1679: final decode, meshes in MoGe space)
+    last = config.num_inference_steps - 1
+    # step_final on the already advanced latents, as the reference does it (:1612-1623); sigma_last = 1
+    x1 = loop.x_t + (1.0 - float(loop.sigmas[last])) * loop.velocity
+    flat0 = loop.sdf0.reshape(B, -1)
+    sdf = flat0.clone()
+    sdf[:, loop.tap] = flat0[:, loop.tap] + loop.alpha * x1
+    sdf = sdf.reshape(B, model.D, model.D, model.D).cpu().numpy()
+    theta = loop.theta.cpu().numpy().astype(np.float64)
+    torch.cuda.synchronize(dev)
+    for b, (p, inp) in enumerate(chunk):
+        hand = inp["hand_moge"].astype(np.float64)
+        ch = (hand.min(0) + hand.max(0)) / 2.0
+        write_ply(p["save_path_hand"], similarity_about(hand, theta[b, :8], ch), inp["faces"])
+        verts, faces = model.extract_mesh(sdf[b])
+        if len(verts) == 0:
+            print(f"Empty mesh for {p['cropped_obj_img_path']}")          # run.py:170-172
+            continue
+        T = inp["T_h2m"].astype(np.float64)
+        vm = verts.astype(np.float64) @ T[:3, :3].T + T[:3, 3]
+        write_ply(p["save_path_obj"], similarity_about(vm, theta[b, 8:], T[:3, 3]), faces)
+
+
+# --------------------------------------------------------------------------- mock networks
+class MockGuidanceModel(GuidanceModel):
+    """Synthetic stand-in for the two networks: a per-image ellipsoid base volume, the linear tap
+    decoder, a fixed random velocity field decaying over the steps.  Tests and synthetic runs only."""
+
+    def __init__(self, D: int = 64, latent_elems: int = 3072 * 64, alpha: float = 0.05, seed: int = 0):
+        self.D, self.latent_elems, self.alpha, self.seed = D, latent_elems, alpha, seed
+        vol = D ** 3
+        if latent_elems > vol or latent_elems % 64 or vol % 64:
+            raise ValueError("need latent_elems <= D^3, both multiples of 64")
+        g = torch.Generator().manual_seed(seed)
+        starts = torch.randperm(vol // 64, generator=g)[: latent_elems // 64].sort().values * 64
+        self.tap = (starts.view(-1, 1) + torch.arange(64).view(1, -1)).reshape(-1)
+        self._sdf0 = None
+        self._v = None
+
+    def begin_batch(self, indices, image_paths, device) -> None:
+        from ..synthetic import ellipsoid_volume
+        vols = []
+        for i in indices:
+            s = sum(ord(c) for c in str(i)) + self.seed
+            vols.append(ellipsoid_volume(self.D, s, device="cpu")[0])
+        self._sdf0 = torch.stack(vols).to(device)
+        g = torch.Generator().manual_seed(self.seed + 17)
+        self._v = (0.1 * torch.randn(len(indices), self.latent_elems, generator=g)).to(device)
+
+    def initial_latents(self, batch, generator):
+        return torch.randn(batch, self.latent_elems, generator=generator)
+
+    def predict(self, step, x_t):
+        return self._v / (1.0 + step)
+
+    def decoder_state(self):
+        return self._sdf0, self.tap, self.alpha
+
+    def extract_mesh(self, sdf: np.ndarray):
+        """Boundary faces of the occupied voxels (a closed, blocky surface) on the Hunyuan lattice."""
+        D = sdf.shape[0]
+        occ = np.zeros((D + 2,) * 3, dtype=bool)
+        occ[1:-1, 1:-1, 1:-1] = sdf < 0
+        step = 2.2 / (D - 1)
+        quads = []
+        corner = {0: [(0, 0, 0), (0, 1, 0), (0, 1, 1), (0, 0, 1)], 1: [(0, 0, 0), (0, 0, 1), (1, 0, 1), (1, 0, 0)],
+                  2: [(0, 0, 0), (1, 0, 0), (1, 1, 0), (0, 1, 0)]}
+        for ax in range(3):
+            for sgn in (0, 1):                         # face on the low / high side of the voxel along ax
+                nb = np.roll(occ, 1 if sgn == 0 else -1, axis=ax)
+                cells = np.argwhere(occ & ~nb) - 1     # voxel indices (un-padded)
+                if cells.size == 0:
+                    continue
+                offs = np.array(corner[ax], dtype=np.int64)
+                if sgn:
+                    offs = offs[::-1].copy()
+                    offs[:, ax] = 1
+                quads.append(cells[:, None, :] + offs[None])
+        if not quads:
+            return np.zeros((0, 3)), np.zeros((0, 3), dtype=np.int32)
+        q = np.concatenate(quads, 0).reshape(-1, 3)
+        uniq, inv = np.unique(q, axis=0, return_inverse=True)
+        inv = inv.reshape(-1, 4)
+        faces = np.concatenate([inv[:, [0, 1, 2]], inv[:, [0, 2, 3]]], 0).astype(np.int32)
+        verts = (uniq.astype(np.float64) - 0.5) * step - 1.10          # voxel corners around lattice points
+        return verts, faces
+
+
+def main() -> None:
+    parser = argparse.ArgumentParser(description="Hunyuan3D-2 guidance")
+    parser.add_argument("--project_root", required=True)
+    parser.add_argument("--cropped_obj_img_dir", required=True)
+    parser.add_argument("--mask_dir", required=True)
+    parser.add_argument("--moge_out_dir", required=True)
+    parser.add_argument("--hunyuan_hoi_mesh_dir", required=True)
+    parser.add_argument("--hamer_out_dir", required=True)
+    parser.add_argument("--h2m_rt_dir", required=True)
+    parser.add_argument("--aligned_mano_dir", required=True)
+    parser.add_argument("--guidance_out_dir", required=True)
+    parser.add_argument("--task_list_file", default=None)
+    args = parser.parse_args()
+
+    run(
+        project_root=args.project_root,
+        cropped_obj_img_dir=args.cropped_obj_img_dir,
+        mask_dir=args.mask_dir,
+        moge_out_dir=args.moge_out_dir,
+        hunyuan_hoi_mesh_dir=args.hunyuan_hoi_mesh_dir,
+        hamer_out_dir=args.hamer_out_dir,
+        h2m_rt_dir=args.h2m_rt_dir,
+        aligned_mano_dir=args.aligned_mano_dir,
+        guidance_out_dir=args.guidance_out_dir,
+        task_list_file=args.task_list_file,
+    )
+
+
+if __name__ == "__main__":
+    main()
