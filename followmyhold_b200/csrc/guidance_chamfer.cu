@@ -508,7 +508,8 @@ constexpr int WALK_THREADS = 256;
 constexpr float WALK_FIX = 8589934592.f;             // 2^33
 constexpr float WALK_UNFIX = 1.f / 8589934592.f;
 constexpr int WALK_MAX_CHUNK = 4096;
-__device__ __forceinline__ void walk_fix_add(int *hi, unsigned *lo, float x) {
+__device__ __forceinline__ void walk_fix_add(int *hi, unsigned *lo, float x, int *flags) {
+  if (!(fabsf(x) <= 63.f)) atomicOr(flags, 2);        // out of the fixed-point range: reported in terms[FLAGS]
   const long long v = __float2ll_rn(fminf(fmaxf(x, -63.f), 63.f) * WALK_FIX);
   atomicAdd(hi, (int)(v >> 20));
   atomicAdd(lo, (unsigned)(v & 0xFFFFF));
@@ -596,9 +597,10 @@ __global__ void __launch_bounds__(WALK_THREADS) k_chamfer_c2h_walk(foho_guidance
     const float hx = hmc[3 * cur], hy = hmc[3 * cur + 1], hz = hmc[3 * cur + 2];
     const float dx = hx - px, dy = hy - py, dz = hz - pz;
     sum += fmaf(dz, dz, fmaf(dy, dy, dx * dx));
-    walk_fix_add(ghi + 3 * cur, glo + 3 * cur, dx);
-    walk_fix_add(ghi + 3 * cur + 1, glo + 3 * cur + 1, dy);
-    walk_fix_add(ghi + 3 * cur + 2, glo + 3 * cur + 2, dz);
+    int *flags = ws.cnt + (size_t)b * CNT_NUM + CNT_FLAGS;
+    walk_fix_add(ghi + 3 * cur, glo + 3 * cur, dx, flags);
+    walk_fix_add(ghi + 3 * cur + 1, glo + 3 * cur + 1, dy, flags);
+    walk_fix_add(ghi + 3 * cur + 2, glo + 3 * cur + 2, dz, flags);
   }
   sum = warp_sum(sum);
   if ((tid & 31) == 0) red[tid >> 5] = sum;

@@ -690,39 +690,67 @@ __global__ void __launch_bounds__(ASM_THREADS) k_assemble(foho_guidance_desc d, 
   const int b = blockIdx.y, tid = threadIdx.x, Vh = d.Vh, D = d.D;
   float *G = d.grad_sdf + (size_t)b * D * D * D;
   {
+    // index and value of every queued contribution are fetched together (independent loads, one round
+    // trip to memory -- the lists were written ~150 us ago and the stream has pushed them out of L2)
     const int *tri_idx = ws.tri_idx + (size_t)b * Vh * 8;
     const float *tri_val = ws.tri_val + (size_t)b * Vh * 8;
-    for (int k = blockIdx.x * blockDim.x + tid; k < Vh * 8; k += gridDim.x * blockDim.x) {
-      const float v = tri_val[k];
-      if (v != 0.f) atomicAdd(G + tri_idx[k], v);
-    }
+    int n = 0;
+    const int *cand = ws.cand + (size_t)b * ws.cap;
+    const float *cval = ws.cand_val + (size_t)b * ws.cap;
     if (do_voxels) {
-      int n = ws.cnt[(size_t)b * CNT_NUM + CNT_NCAND];
+      n = ws.cnt[(size_t)b * CNT_NUM + CNT_NCAND];
       if (n > ws.cap) n = ws.cap;
-      const int *cand = ws.cand + (size_t)b * ws.cap;
-      const float *cval = ws.cand_val + (size_t)b * ws.cap;
-      for (int k = blockIdx.x * blockDim.x + tid; k < n; k += gridDim.x * blockDim.x) atomicAdd(G + cand[k], cval[k]);
+    }
+    const int stride = gridDim.x * blockDim.x;
+    for (int k0 = blockIdx.x * blockDim.x + tid; k0 < Vh * 8 || k0 < n; k0 += 4 * stride) {
+      int ti[4], ci[4];
+      float tv[4], cv[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int k = k0 + u * stride;
+        const bool t = k < Vh * 8, c = k < n;
+        ti[u] = t ? tri_idx[k] : 0; tv[u] = t ? tri_val[k] : 0.f;
+        ci[u] = c ? cand[k] : 0;    cv[u] = c ? cval[k] : 0.f;
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        if (tv[u] != 0.f) atomicAdd(G + ti[u], tv[u]);
+        if (cv[u] != 0.f) atomicAdd(G + ci[u], cv[u]);
+      }
     }
   }
-  if (blockIdx.x == 0 && tid == 0) {
-    const FohoFrame &fr = ws.frames[b];
+  if (blockIdx.x != 0) return;
+  // block 0: stage everything the leaf assembly reads (one round trip for the whole block instead of a
+  // chain of dependent loads in one thread: this kernel sits after the dense stream, on the critical path)
+  __shared__ FohoFrame fr;
+  __shared__ float s_acc[FIN_NRED];
+  __shared__ double s_mom[6];
+  {
+    const int nwords = sizeof(FohoFrame) / 4;
+    const uint32_t *src = reinterpret_cast<const uint32_t *>(ws.frames + b);
+    uint32_t *dst = reinterpret_cast<uint32_t *>(&fr);
+    for (int k = tid; k < nwords; k += blockDim.x) dst[k] = src[k];
+    if (tid < FIN_NRED) s_acc[tid] = ws.fin_acc[(size_t)b * FIN_NRED + tid];
+    // stream moments: thread m < 6 sums moment m over the stream CTAs in fixed order (double)
+    if (tid >= 32 && tid < 38) {
+      const int m = tid - 32;
+      const float *part = ws.stream_part + (size_t)b * FOHO_MAX_STREAM_CTAS * FOHO_STREAM_PARTIALS;
+      double sum = 0;
+#pragma unroll 8
+      for (int k = 0; k < stream_gx; ++k) sum += part[(size_t)k * FOHO_STREAM_PARTIALS + m];
+      s_mom[m] = sum;
+    }
+  }
+  __syncthreads();
+  if (tid == 0) {
     const bool use_kp = d.n_joints == 16 && d.j_regressor && d.kps_2d && Vh > 744;
     const float invV = 1.f / (float)Vh;
     float acc[FIN_NRED];
-    {
-      const float *fa = ws.fin_acc + (size_t)b * FIN_NRED;
-      for (int k = 0; k < FIN_NRED; ++k) acc[k] = fa[k];
-    }
+    for (int k = 0; k < FIN_NRED; ++k) acc[k] = s_acc[k];
     const float kp_loss = acc[29];
     const foho_weights &W = d.w;
     const double N = (double)D * D * D;
-    // stream moments (deterministic fixed-order sum, double)
-    double M0 = 0, M1x = 0, M1y = 0, M1z = 0, M2 = 0, cobj = 0;
-    const float *part = ws.stream_part + (size_t)b * FOHO_MAX_STREAM_CTAS * FOHO_STREAM_PARTIALS;
-    for (int k = 0; k < stream_gx; ++k) {
-      const float *p = part + (size_t)k * FOHO_STREAM_PARTIALS;
-      M0 += p[0]; M1x += p[1]; M1y += p[2]; M1z += p[3]; M2 += p[4]; cobj += p[5];
-    }
+    const double M0 = s_mom[0], M1x = s_mom[1], M1y = s_mom[2], M1z = s_mom[3], M2 = s_mom[4], cobj = s_mom[5];
     const double so = fr.so, hs = (double)fr.s_h2m * fr.step;
     double Ahs[9];
     for (int k = 0; k < 9; ++k) Ahs[k] = (double)fr.Ah[k] * fr.step;
@@ -993,7 +1021,7 @@ extern "C" int foho_guidance_energy_fwd_bwd(const foho_guidance_desc *dp, void *
     FOHO_CUDA_TRY(cudaStreamWaitEvent(st, fc->join_a, 0));
   }
   if (sm & 16) {
-    k_assemble<<<dim3(8, d.B), ASM_THREADS, 0, st>>>(d, ws, (sm & 2) ? gx : 0, (sm & 8) ? 1 : 0);
+    k_assemble<<<dim3(16, d.B), ASM_THREADS, 0, st>>>(d, ws, (sm & 2) ? gx : 0, (sm & 8) ? 1 : 0);
     FOHO_LAUNCH_CHECK();
   }
   if (obj_mesh && (sm & 16)) {

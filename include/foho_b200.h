@@ -52,7 +52,8 @@ enum {
   FOHO_T_EDGE = 12,   /* REF a10 mesh_edge_loss (pipelines.py:1575)                */
   FOHO_T_MEAN_D2 = 13,/* REF     mean hand->object d2 (weight switch, :1561)       */
   FOHO_T_NCAND = 14,  /* diagnostics: voxels inside hand & object                  */
-  FOHO_T_FLAGS = 15,  /* diagnostics: bit0 = candidate list overflow               */
+  FOHO_T_FLAGS = 15,  /* diagnostics: bit0 = candidate list overflow, bit1 = a cloud point farther
+                         than 63 units from its nearest hand vertex (gradient clamped)       */
   FOHO_NUM_TERMS = 16
 };
 
