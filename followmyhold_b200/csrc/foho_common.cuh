@@ -250,6 +250,18 @@ __device__ __forceinline__ void block_sum(float (&v)[N], float *smem) {
 }
 #endif
 
+// ---- per-device launch state (function attributes are per device; one process may drive several)
+enum { FA_STREAM_TMA = 0, FA_CHAMFER, FA_C2H, FA_C2H_WALK, FA_VOXDIST, FA_NUM };
+struct FohoDeviceState {
+  int sm_count;
+  size_t smem_attr[FA_NUM];      // largest dynamic shared-memory size opted into so far, per kernel
+  bool carveout[FA_NUM];         // max-shared carve-out preference already set
+};
+FohoDeviceState *foho_device_state();     // of the current device; nullptr on a CUDA error
+// opt `func` into `smem` bytes of dynamic shared memory (if it is more than before) and, when asked, into
+// the largest shared-memory carve-out, so that kernels sharing an SM do not wait for it to drain
+int foho_func_attrs(const void *func, int id, size_t smem, bool max_carveout);
+
 // kernels implemented in the other translation units
 // shared_sm: the sparse kernels run beside the stream (it then leaves them shared memory)
 int foho_launch_stream(const foho_guidance_desc *d, const FohoWorkspace &ws, int *grid_x_out, bool shared_sm, cudaStream_t st);
@@ -259,7 +271,7 @@ int foho_launch_objmesh_pre(const foho_guidance_desc *d, const FohoWorkspace &ws
 int foho_launch_objmesh_post(const foho_guidance_desc *d, const FohoWorkspace &ws, cudaStream_t st);
 // structured chamfer search (guidance_chamfer.cu); used when desc->accel is set
 // grouped exact point->mesh distance of the candidate voxels (guidance_voxdist.cu); needs desc->accel
-int foho_launch_voxdist_tree(const foho_guidance_desc *d, const FohoWorkspace &ws, cudaStream_t st);
+int foho_launch_voxdist_staged(const foho_guidance_desc *d, const FohoWorkspace &ws, cudaStream_t st);
 void foho_accel_layout(FohoAccel &a, char *base, int B, int P);
 int foho_launch_chamfer_h2c(const foho_guidance_desc *d, const FohoWorkspace &ws, cudaStream_t st);
 int foho_launch_chamfer_c2h(const foho_guidance_desc *d, const FohoWorkspace &ws, cudaStream_t st);

@@ -819,22 +819,16 @@ int foho_launch_chamfer_c2h(const foho_guidance_desc *dp, const FohoWorkspace &w
     // whole neighbour lists in shared memory: size for the worst case the stride allows
     const size_t smem = foho_align_up((size_t)d.Vh * 40 + (size_t)(d.Vh + 1) * 4, 16) + (size_t)d.nbr_stride * 2;
     if (smem > 200 * 1024) return FOHO_E_SHAPE;
-    static size_t attr = 0;
-    if (smem > attr) {
-      FOHO_CUDA_TRY(cudaFuncSetAttribute(k_chamfer_c2h_walk, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      FOHO_CUDA_TRY(cudaFuncSetAttribute(k_chamfer_c2h_walk, cudaFuncAttributePreferredSharedMemoryCarveout,
-                                         (int)cudaSharedmemCarveoutMaxShared));
-      attr = smem;
+    {
+      int rc = foho_func_attrs((const void *)k_chamfer_c2h_walk, FA_C2H_WALK, smem, true);
+      if (rc != FOHO_OK) return rc;
     }
-    // At most one CTA per SM over the whole batch: beside the dense stream's two CTAs an SM has room
+    // At most one CTA per SM over the whole batch: beside the dense stream's CTA an SM has room
     // for exactly one of these, and a grid that does not fit at once would hold back every kernel
     // queued behind it.  Each CTA walks a contiguous chunk of the Morton-sorted cloud.
-    static int sm_count = 0;
-    if (sm_count == 0) {
-      int dev = 0;
-      FOHO_CUDA_TRY(cudaGetDevice(&dev));
-      FOHO_CUDA_TRY(cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev));
-    }
+    FohoDeviceState *ds = foho_device_state();
+    if (!ds) return (int)cudaGetLastError();
+    const int sm_count = ds->sm_count;
     int gx = sm_count / d.B;
     if (gx < 1) gx = 1;
     int chunk = (d.P + gx - 1) / gx;
@@ -846,11 +840,9 @@ int foho_launch_chamfer_c2h(const foho_guidance_desc *dp, const FohoWorkspace &w
     return FOHO_OK;
   }
   const int NG = (d.P + 31) / 32;
-  static bool carve = false;
-  if (!carve) {
-    FOHO_CUDA_TRY(cudaFuncSetAttribute(k_chamfer_c2h, cudaFuncAttributePreferredSharedMemoryCarveout,
-                                       (int)cudaSharedmemCarveoutMaxShared));
-    carve = true;
+  {
+    int rc = foho_func_attrs((const void *)k_chamfer_c2h, FA_C2H, 0, true);
+    if (rc != FOHO_OK) return rc;
   }
   k_chamfer_c2h<<<dim3((NG + C2H_GROUPS_PER_CTA - 1) / C2H_GROUPS_PER_CTA, d.B), C2H_THREADS, 0, st>>>(d, ws, a);
   FOHO_LAUNCH_CHECK();

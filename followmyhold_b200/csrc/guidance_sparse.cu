@@ -856,6 +856,35 @@ static ForkCtx *fork_ctx() {
   return ctx[dev];
 }
 
+FohoDeviceState *foho_device_state() {
+  static FohoDeviceState *st[64] = {nullptr};
+  static std::mutex mu;
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return nullptr;
+  std::lock_guard<std::mutex> lock(mu);
+  if (!st[dev]) {
+    FohoDeviceState *s = new FohoDeviceState();
+    if (cudaDeviceGetAttribute(&s->sm_count, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) { delete s; return nullptr; }
+    for (int i = 0; i < FA_NUM; ++i) { s->smem_attr[i] = 0; s->carveout[i] = false; }
+    st[dev] = s;
+  }
+  return st[dev];
+}
+
+int foho_func_attrs(const void *func, int id, size_t smem, bool max_carveout) {
+  FohoDeviceState *ds = foho_device_state();
+  if (!ds) return (int)cudaGetLastError();
+  if (smem > 48 * 1024 && smem > ds->smem_attr[id]) {
+    FOHO_CUDA_TRY(cudaFuncSetAttribute(func, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    ds->smem_attr[id] = smem;
+  }
+  if (max_carveout && !ds->carveout[id]) {
+    FOHO_CUDA_TRY(cudaFuncSetAttribute(func, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared));
+    ds->carveout[id] = true;
+  }
+  return FOHO_OK;
+}
+
 // ----------------------------------------------------------------------------- C-ABI
 extern "C" int foho_abi_version(void) { return FOHO_ABI_VERSION; }
 
@@ -908,8 +937,7 @@ extern "C" int foho_guidance_energy_fwd_bwd(const foho_guidance_desc *dp, void *
 
   const int sm = d.stage_mask == 0 ? 0x3f : d.stage_mask;
   const bool overlap = d.stage_mask == 0 && d.serial == 0;
-  static int last_gx = 1;
-  int gx = last_gx;
+  int gx = 0;
 
   // Stream layout.  overlap: the dense stream depends on nothing but the inputs, so it starts at once
   // on the caller's stream while k_prep and the sparse chains run on three library-owned side streams:
@@ -945,7 +973,6 @@ extern "C" int foho_guidance_energy_fwd_bwd(const foho_guidance_desc *dp, void *
   if (sm & 2) {
     int rc = foho_launch_stream(dp, ws, &gx, overlap, st);
     if (rc != FOHO_OK) return rc;
-    last_gx = gx;
   }
   const bool accel = (sm & 4) && d.P > 0 && d.accel;
   if (accel) {
@@ -956,10 +983,9 @@ extern "C" int foho_guidance_energy_fwd_bwd(const foho_guidance_desc *dp, void *
   } else if ((sm & 4) && d.P > 0) {
     const size_t smem = (size_t)d.Vh * (16 + 8 + 12);
     if (smem > 200 * 1024) return FOHO_E_SHAPE;
-    static size_t attr = 0;
-    if (smem > 48 * 1024 && smem > attr) {
-      FOHO_CUDA_TRY(cudaFuncSetAttribute(k_chamfer, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      attr = smem;
+    {
+      int rc = foho_func_attrs((const void *)k_chamfer, FA_CHAMFER, smem, false);
+      if (rc != FOHO_OK) return rc;
     }
     const int nchunk = (d.P + CH_POINTS_PER_CTA - 1) / CH_POINTS_PER_CTA;
     k_chamfer<<<dim3(nchunk, d.B), CH_THREADS, smem, sa>>>(d, ws);
@@ -980,7 +1006,7 @@ extern "C" int foho_guidance_energy_fwd_bwd(const foho_guidance_desc *dp, void *
     k_compact<<<dim3(32, d.B), 256, 0, sb>>>(d, ws);
     FOHO_LAUNCH_CHECK();
     if (face_tree) {
-      int rc = foho_launch_voxdist_tree(dp, ws, sb);
+      int rc = foho_launch_voxdist_staged(dp, ws, sb);
       if (rc != FOHO_OK) return rc;
     } else {
       k_voxdist<<<dim3(64, d.B), 256, 0, sb>>>(d, ws);

@@ -334,12 +334,9 @@ int ilog2_exact(int D) {
 }  // namespace
 
 int foho_launch_stream(const foho_guidance_desc *d, const FohoWorkspace &ws, int *grid_x_out, bool /*shared_sm*/, cudaStream_t st) {
-  static int sm_count = 0;
-  if (sm_count == 0) {
-    int dev = 0;
-    FOHO_CUDA_TRY(cudaGetDevice(&dev));
-    FOHO_CUDA_TRY(cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev));
-  }
+  FohoDeviceState *ds = foho_device_state();
+  if (!ds) return (int)cudaGetLastError();
+  const int sm_count = ds->sm_count;
   const int D = d->D, B = d->B;
   const double N = (double)D * D * D;
   const float cN = (float)((double)d->w.w_mom / N);
@@ -365,15 +362,11 @@ int foho_launch_stream(const foho_guidance_desc *d, const FohoWorkspace &ws, int
     int nprefetch = d->stream_prefetch > 0 ? d->stream_prefetch : (d->stream_stages > 0 ? nstages / 2 : 4);
     if (nprefetch >= nstages) nprefetch = nstages - 1;
     const size_t smem = (size_t)nstages * TMA_TILE_BYTES;
-    static bool attr_done = false;
-    if (!attr_done) {
-      FOHO_CUDA_TRY(cudaFuncSetAttribute(k_stream_tma, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         TMA_MAX_STAGES * TMA_TILE_BYTES));
-      // configure the SM with the largest shared-memory carve-out, so that kernels running beside the
-      // stream find room for their own shared memory without waiting for the SM to drain
-      FOHO_CUDA_TRY(cudaFuncSetAttribute(k_stream_tma, cudaFuncAttributePreferredSharedMemoryCarveout,
-                                         (int)cudaSharedmemCarveoutMaxShared));
-      attr_done = true;
+    // the largest ring is opted into once; the max-shared carve-out lets kernels running beside the stream
+    // find room for their own shared memory without waiting for the SM to drain
+    {
+      int rc = foho_func_attrs((const void *)k_stream_tma, FA_STREAM_TMA, (size_t)TMA_MAX_STAGES * TMA_TILE_BYTES, true);
+      if (rc != FOHO_OK) return rc;
     }
     long long ntiles = ((long long)(N / 4) + TMA_TILE_F4 - 1) / TMA_TILE_F4;
     gx = sm_count * ctas / B;                     // at most `ctas` resident CTAs per SM over the whole batch:

@@ -195,7 +195,7 @@ __global__ void __launch_bounds__(VT_THREADS) k_voxdist_staged(foho_guidance_des
 
 }  // namespace
 
-int foho_launch_voxdist_tree(const foho_guidance_desc *dp, const FohoWorkspace &ws, cudaStream_t st) {
+int foho_launch_voxdist_staged(const foho_guidance_desc *dp, const FohoWorkspace &ws, cudaStream_t st) {
   const foho_guidance_desc &d = *dp;
   FohoAccel a;
   foho_accel_layout(a, (char *)d.accel, d.B, d.P);
@@ -203,12 +203,9 @@ int foho_launch_voxdist_tree(const foho_guidance_desc *dp, const FohoWorkspace &
   const int NF = (d.Fh + 31) & ~31;
   const size_t smem = ((size_t)NF + (size_t)d.Vh) * sizeof(float4) + VT_WARPS * VT_QUEUE * sizeof(int);
   if (smem > 200 * 1024) return FOHO_E_SHAPE;
-  static size_t attr = 0;
-  if (smem > attr) {
-    FOHO_CUDA_TRY(cudaFuncSetAttribute(k_voxdist_staged, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    FOHO_CUDA_TRY(cudaFuncSetAttribute(k_voxdist_staged, cudaFuncAttributePreferredSharedMemoryCarveout,
-                                       (int)cudaSharedmemCarveoutMaxShared));
-    attr = smem;
+  {
+    int rc = foho_func_attrs((const void *)k_voxdist_staged, FA_VOXDIST, smem, true);
+    if (rc != FOHO_OK) return rc;
   }
   k_voxdist_staged<<<dim3(32, d.B), VT_THREADS, smem, st>>>(d, ws, a);
   FOHO_LAUNCH_CHECK();

@@ -77,6 +77,46 @@ def test_energy_and_grads_match_oracle(D, variant, accel):
     assert not errs, "\n".join(errs)
 
 
+@pytest.mark.parametrize("case", ["hand_outside_volume", "ragged_cloud_single_image", "hand_deep_inside"])
+def test_edge_cases_match_oracle(case):
+    """Edges of the searches and the samplers: a hand pushed completely out of the lattice (no candidate
+    voxel, border-clamped samples, every cloud point far from the hand), a cloud whose size is not a
+    multiple of the 32-point groups with a batch of one, a hand scaled down into the object's interior
+    (many candidates, long candidate runs)."""
+    from followmyhold_b200.guidance.engine import GuidanceEngine
+    D = 96 if case == "hand_deep_inside" else 48
+    B, P = (1, 1000) if case == "ragged_cloud_single_image" else (2, 1536)
+    samples = [make_guidance_sample(D, P, 300 + i) for i in range(B)]
+    for s in samples:
+        if case == "hand_outside_volume":
+            s.theta_h[1:4] = torch.tensor([2.5, -1.5, 2.0])
+        if case == "hand_deep_inside":
+            c = (s.hand_rest.min(0).values + s.hand_rest.max(0).values) / 2
+            s.theta_h[1:4] = (s.obj_center - c) * 0.9          # towards the object's centre
+            s.theta_h[0] = 1.5
+    sdf, theta, st = stack_samples(samples, cap=True)
+    eng = GuidanceEngine(B, D, 778, st.hand_faces.shape[0], P)
+    eng.prepare(st)
+    for _ in range(2):                                          # second evaluation runs warm-started
+        terms, gs, gt = eng.energy_fwd_bwd(sdf, theta, st)
+    torch.cuda.synchronize()
+    terms = terms.cpu().numpy(); gt = gt.cpu().numpy(); hg = eng.hand_grid.cpu().numpy()
+    faces = st.hand_faces.cpu()
+    for b, s in enumerate(samples):
+        s.hand_faces = faces
+        out, ogs, ogt = _oracle(s, hand_grid=hg[b])
+        assert terms[b, 4] == float(out["count"]) and terms[b, 15] == 0
+        if case == "hand_outside_volume":
+            assert terms[b, 4] == 0
+        if case == "hand_deep_inside":
+            assert terms[b, 14] > 60, terms[b, 14]               # many candidate voxels, long runs per warp
+        for n, i in {"L_pen": 1, "L_con": 2, "L_int": 3, "L_mom": 5, "L_ch": 6, "L_kp": 7}.items():
+            ref = float(out[n].detach())
+            assert abs(terms[b, i] - ref) <= REL * abs(ref) + 1e-9, (case, n, terms[b, i], ref)
+        _close(f"{case} grad_theta[{b}]", gt[b], ogt.numpy())
+        _close(f"{case} grad_sdf[{b}]", gs[b].cpu().numpy(), ogs.numpy())
+
+
 @pytest.mark.parametrize("term", ["w_pen", "w_con", "w_ivol", "w_ch", "w_mom", "kp"])
 def test_single_term_gradients(term):
     """Each term alone (others weighted 0) so a small term cannot hide behind a large one."""
