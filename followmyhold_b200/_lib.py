@@ -103,7 +103,7 @@ class GuidanceDesc(C.Structure):
     _fields_ = [
         ("B", C.c_int32), ("D", C.c_int32), ("Vh", C.c_int32), ("Fh", C.c_int32), ("P", C.c_int32),
         ("n_joints", C.c_int32), ("image_h", C.c_int32), ("image_w", C.c_int32), ("late_step", C.c_int32),
-        ("stream_variant", C.c_int32), ("stage_mask", C.c_int32), ("serial", C.c_int32), ("stream_stages", C.c_int32), ("stream_prefetch", C.c_int32), ("stream_ctas", C.c_int32), ("reserved0", C.c_int32), ("fov_deg", C.c_float), ("bound", C.c_float), ("w", Weights),
+        ("stream_variant", C.c_int32), ("stage_mask", C.c_int32), ("serial", C.c_int32), ("stream_stages", C.c_int32), ("stream_prefetch", C.c_int32), ("stream_ctas", C.c_int32), ("lane", C.c_int32), ("fov_deg", C.c_float), ("bound", C.c_float), ("w", Weights),
         ("sdf", C.c_void_p), ("grad_sdf", C.c_void_p), ("hand_rest", C.c_void_p), ("hand_faces", C.c_void_p),
         ("cloud", C.c_void_p), ("T_h2m", C.c_void_p), ("obj_center", C.c_void_p), ("theta", C.c_void_p),
         ("j_regressor", C.c_void_p), ("kps_2d", C.c_void_p), ("grad_hand_ext", C.c_void_p),

@@ -826,18 +826,21 @@ __global__ void __launch_bounds__(ASM_THREADS) k_assemble(foho_guidance_desc d, 
 }  // namespace
 
 // ----------------------------------------------------------------------------- fork/join context
-// Three high-priority side streams + five events per device, created on first use (do the first call
+// Three high-priority side streams + five events per (device, lane), created on first use (do the first call
 // outside a stream capture).  A mutex serialises callers that share them.
 struct ForkCtx {
   cudaStream_t side[3];
   cudaEvent_t fork, prep, join_a, join_b, join_c;
   std::mutex mu;
 };
-static ForkCtx *fork_ctx() {
-  static ForkCtx *ctx[64] = {nullptr};
+constexpr int FORK_LANES = 4;
+static ForkCtx *fork_ctx(int lane) {
+  static ForkCtx *all[64 * FORK_LANES] = {nullptr};
   static std::mutex mu;
   int dev = 0;
   if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return nullptr;
+  if (lane < 0 || lane >= FORK_LANES) lane = 0;
+  ForkCtx **ctx = all + lane * 64;
   std::lock_guard<std::mutex> lock(mu);
   if (!ctx[dev]) {
     ForkCtx *c = new ForkCtx();
@@ -949,7 +952,7 @@ extern "C" int foho_guidance_energy_fwd_bwd(const foho_guidance_desc *dp, void *
   ForkCtx *fc = nullptr;
   cudaStream_t sa = st, sb = st, sc = st;
   if (overlap) {
-    fc = fork_ctx();
+    fc = fork_ctx(d.lane);
     if (!fc) return (int)cudaGetLastError();
     sa = fc->side[0]; sb = fc->side[1]; sc = fc->side[2];
     fc->mu.lock();

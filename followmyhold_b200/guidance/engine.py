@@ -150,6 +150,7 @@ class GuidanceEngine:
         self.stream_stages = 0     # TMA stream ring depth / prefetch distance (0 = library default)
         self.stream_prefetch = 0
         self.stream_ctas = 0       # TMA stream persistent CTAs per SM (0 = library default)
+        self.lane = 0              # which set of library side streams the evaluations fork onto (0..3)
         self._accel = None
         self._accel_ptr = 0
         self._accel_bytes = 0
@@ -219,6 +220,7 @@ class GuidanceEngine:
         d.late_step = int(late_step)
         d.stream_variant = self.stream_variant
         d.serial, d.stream_stages, d.stream_prefetch, d.stream_ctas = self.serial, self.stream_stages, self.stream_prefetch, self.stream_ctas
+        d.lane = self.lane
         d.fov_deg = float(st.fov_deg)
         d.bound = GRID_BOUND
         d.w = self.weights

@@ -34,22 +34,55 @@ def set_timesteps_sigmas(num_inference_steps: int, shift: float = 1.0) -> torch.
     return torch.cat([s.to(torch.float32), torch.ones(1)])
 
 
+def slice_statics(st: GuidanceStatics, off: int, n: int) -> GuidanceStatics:
+    """Images [off, off+n) of a batch of per-image inputs (topology, regressor and camera are shared)."""
+    cut = lambda t: None if t is None else t.narrow(0, off, n).contiguous()
+    return GuidanceStatics(hand_rest=cut(st.hand_rest), hand_faces=st.hand_faces, cloud=cut(st.cloud), T_h2m=cut(st.T_h2m),
+                           obj_center=cut(st.obj_center), j_regressor=st.j_regressor, kps_2d=cut(st.kps_2d),
+                           fov_deg=st.fov_deg, image_hw=st.image_hw)
+
+
+class _Lane:
+    """One micro-batch of a GuidanceLoop: images [off, off+nb)."""
+    def __init__(self, off, nb, engine, opt, statics, stream):
+        self.off, self.nb, self.engine, self.opt, self.statics, self.stream = off, nb, engine, opt, statics, stream
+
+
 class GuidanceLoop:
     """Batched guided-denoise steps for B images on one GPU."""
 
     def __init__(self, B: int, D: int, statics: GuidanceStatics, P: int, device="cuda:0",
                  config: Optional[OptimizationConfig] = None, weights=None, latent_elems: int = LATENT_SHAPE[0] * LATENT_SHAPE[1],
-                 decoder_alpha: float = 0.05, stream_variant: int = 0, seed: int = 0):
+                 decoder_alpha: float = 0.05, stream_variant: int = 0, seed: int = 0, micro_batches: int = 1):
+        """``micro_batches`` = m > 1 splits the B images into m groups that advance independently inside the
+        one captured graph (own engine, optimiser state, stream and library side-stream lane): while one
+        group's evaluation is in its serial tail (assemble -> decoder adjoint -> update -> decoder forward)
+        the other group's dense stream keeps the HBM busy.  Results are identical: images never interact."""
         self.lib = _lib.load()
         self.device = torch.device(device)
         self.B, self.D, self.P, self.L = B, D, P, latent_elems
         self.cfg = config or OptimizationConfig()
         self.statics = statics
         Vh, Fh = statics.hand_rest.shape[1], statics.hand_faces.shape[0]
-        self.engine = GuidanceEngine(B, D, Vh, Fh, P, device=device, weights=weights, stream_variant=stream_variant)
-        self.engine.prepare(statics)
-        self.opt = GuidanceOptimizer(B, self.L, device=device, config=self.cfg)
+        m = int(micro_batches)
+        if m < 1 or m > 4 or B % m != 0:
+            raise ValueError("micro_batches must be 1..4 and divide the batch")
+        self.micro_batches, nb = m, B // m
         dev = self.device
+        self.terms = torch.zeros(B, _lib.FOHO_NUM_TERMS, dtype=torch.float32, device=dev)
+        self.grad_theta = torch.zeros(B, 16, dtype=torch.float32, device=dev)
+        self.lanes = []
+        for j in range(m):
+            st_j = statics if m == 1 else slice_statics(statics, j * nb, nb)
+            eng = GuidanceEngine(nb, D, Vh, Fh, P, device=device, weights=weights, stream_variant=stream_variant)
+            eng.lane = j
+            eng.terms = self.terms.narrow(0, j * nb, nb)             # the lanes write straight into the
+            eng.grad_theta = self.grad_theta.narrow(0, j * nb, nb)   # loop's [B, .] result buffers
+            eng.prepare(st_j)
+            self.lanes.append(_Lane(j * nb, nb, eng, GuidanceOptimizer(nb, self.L, device=device, config=self.cfg), st_j,
+                                    None if j == 0 else torch.cuda.Stream(device=dev)))
+        self.engine = self.lanes[0].engine       # the whole batch when micro_batches == 1
+        self.opt = self.lanes[0].opt
         vol = D * D * D
         if self.L > vol:
             raise ValueError("mock decoder needs latent_elems <= D^3")
@@ -126,31 +159,35 @@ class GuidanceLoop:
         return self.engine.launches_per_eval + 3     # + decoder fwd, decoder adjoint, fused update
 
     # ------------------------------------------------------------------ one evaluation (enqueue only)
-    def _enqueue_eval(self, sigma: float, late_step: bool, s: torch.cuda.Stream, phase: float = 2) -> None:
-        lib, B, vol = self.lib, self.B, self.D ** 3
+    def _enqueue_eval(self, sigma: float, late_step: bool, s: torch.cuda.Stream, phase: float = 2, lane: Optional[_Lane] = None) -> None:
+        """One evaluation of one lane (default: lane 0) on stream ``s``."""
+        ln = lane or self.lanes[0]
+        lib, vol, off, nb = self.lib, self.D ** 3, ln.off, ln.nb
         sp = C.c_void_p(s.cuda_stream)
+        sdf, sdf0, theta = self.sdf.narrow(0, off, nb), self.sdf0.narrow(0, off, nb), self.theta.narrow(0, off, nb)
+        x_t, x1 = self.x_t.narrow(0, off, nb), self.x1.narrow(0, off, nb)
+        vel, gvel = self.velocity.narrow(0, off, nb), self.grad_velocity.narrow(0, off, nb)
         hand_only = phase == 1
         if not hand_only:
             _lib.check("foho_mock_decoder_forward", lib.foho_mock_decoder_forward(
-                self.sdf.data_ptr(), self.sdf0.data_ptr(), self.x1.data_ptr(), self.tap.data_ptr(), B, vol, self.L,
-                self.alpha, sp))
-        desc = self.engine.make_desc(self.sdf, self.theta, self.statics, late_step=late_step)
+                sdf.data_ptr(), sdf0.data_ptr(), x1.data_ptr(), self.tap.data_ptr(), nb, vol, self.L, self.alpha, sp))
+        desc = ln.engine.make_desc(sdf, theta, ln.statics, late_step=late_step)
         if phase != 2:
             self._phase_w = self.phase_weights(phase)      # keep the struct alive while the call reads it
             desc.w = self._phase_w
         if hand_only:
             desc.stage_mask = 1 | 4 | 16                   # no volume term has weight: skip the stream and the voxels
-        self.engine.launch(desc, s)
+        ln.engine.launch(desc, s)
         if not hand_only:
             _lib.check("foho_mock_decoder_backward", lib.foho_mock_decoder_backward(
-                self.engine.grad_sdf.data_ptr(), self.tap.data_ptr(), self.grad_velocity.data_ptr(), B, vol, self.L,
+                ln.engine.grad_sdf.data_ptr(), self.tap.data_ptr(), gvel.data_ptr(), nb, vol, self.L,
                 self.alpha * (1.0 - sigma), sp))
-        self.opt.step(self.theta, self.engine.grad_theta, self.velocity, self.grad_velocity, self.x_t, self.x1,
-                      sigma=sigma, stream=s)
+        ln.opt.step(theta, ln.engine.grad_theta, vel, gvel, x_t, x1, sigma=sigma, stream=s)
 
     def _enqueue_step(self, step_index: int, s: torch.cuda.Stream, phase: float = 2) -> None:
         """All kernels of one guided-denoise step (pipelines.py:1293-1612), no syncs.  ``phase``: 1 hand
-        only (:1295-1358), 1.5 object only (:1361-1453), 2 joint (:1455-1601), 0 plain ``scheduler.step``."""
+        only (:1295-1358), 1.5 object only (:1361-1453), 2 joint (:1455-1601), 0 plain ``scheduler.step``.
+        With micro-batches every lane runs its images on its own stream, forked from and joined into ``s``."""
         cfg = self.cfg
         sigma = float(self.sigmas[step_index]); sigma_next = float(self.sigmas[step_index + 1])
         late = step_index >= cfg.num_inference_steps - 3
@@ -159,22 +196,32 @@ class GuidanceLoop:
                 self.x_t.data_ptr(), self.velocity.data_ptr(), self.prev.data_ptr(), None, self.x_t.numel(), sigma,
                 sigma_next, C.c_void_p(s.cuda_stream)))
             return
-        self.opt.set_phase(phase)
-        self.opt.reset()                                   # fresh optimiser state every outer step (:1318,1384,1478)
-        # x1 for the first decode of this step: step_final with the incoming velocity (:1507)
-        _lib.check("foho_scheduler_step", self.lib.foho_scheduler_step(
-            self.x_t.data_ptr(), self.velocity.data_ptr(), None, self.x1.data_ptr(), self.x_t.numel(), sigma, sigma_next,
-            C.c_void_p(s.cuda_stream)))
-        for _ in range(self.phase_iterations(phase)):
-            self._enqueue_eval(sigma, late, s, phase)
-        # obj_latents = scheduler.step(noise_pred_obj, t, obj_latents).prev_sample (:1612)
-        _lib.check("foho_scheduler_step", self.lib.foho_scheduler_step(
-            self.x_t.data_ptr(), self.velocity.data_ptr(), self.prev.data_ptr(), None, self.x_t.numel(), sigma, sigma_next,
-            C.c_void_p(s.cuda_stream)))
+        for ln in self.lanes[1:]:
+            ln.stream.wait_stream(s)
+        for ln in self.lanes:
+            st = s if ln.stream is None else ln.stream
+            off, nb = ln.off, ln.nb
+            x_t, vel = self.x_t.narrow(0, off, nb), self.velocity.narrow(0, off, nb)
+            x1, prev = self.x1.narrow(0, off, nb), self.prev.narrow(0, off, nb)
+            with torch.cuda.stream(st):
+                ln.opt.set_phase(phase)
+                ln.opt.reset()                             # fresh optimiser state every outer step (:1318,1384,1478)
+                # x1 for the first decode of this step: step_final with the incoming velocity (:1507)
+                _lib.check("foho_scheduler_step", self.lib.foho_scheduler_step(
+                    x_t.data_ptr(), vel.data_ptr(), None, x1.data_ptr(), x_t.numel(), sigma, sigma_next,
+                    C.c_void_p(st.cuda_stream)))
+                for _ in range(self.phase_iterations(phase)):
+                    self._enqueue_eval(sigma, late, st, phase, ln)
+                # obj_latents = scheduler.step(noise_pred_obj, t, obj_latents).prev_sample (:1612)
+                _lib.check("foho_scheduler_step", self.lib.foho_scheduler_step(
+                    x_t.data_ptr(), vel.data_ptr(), prev.data_ptr(), None, x_t.numel(), sigma, sigma_next,
+                    C.c_void_p(st.cuda_stream)))
+        for ln in self.lanes[1:]:
+            s.wait_stream(ln.stream)
 
     def launches_per_step(self) -> int:
-        # opt.reset(): 4 memsets by torch; 2 scheduler launches; evaluations
-        return self.cfg.optimization_steps_joint * self.kernels_per_eval() + 2
+        # per lane: 2 scheduler launches + the evaluations (opt.reset(): 4 memsets by torch, not counted)
+        return self.micro_batches * (self.cfg.optimization_steps_joint * self.kernels_per_eval() + 2)
 
     # ------------------------------------------------------------------ graph
     def capture(self, step_index: int) -> None:
@@ -185,8 +232,9 @@ class GuidanceLoop:
             s = self.stream
             s.wait_stream(torch.cuda.current_stream(self.device))
             with torch.cuda.stream(s):
-                self._enqueue_eval(float(self.sigmas[step_index]), False, s)   # warm-up outside capture (func attrs)
-                self.opt.reset()
+                for ln in self.lanes:          # warm-up outside capture (function attributes, side streams)
+                    self._enqueue_eval(float(self.sigmas[step_index]), False, s, 2, ln)
+                    ln.opt.reset()
             s.synchronize()
             g = torch.cuda.CUDAGraph()
             with torch.cuda.graph(g, stream=s):
@@ -218,7 +266,8 @@ class GuidanceLoop:
                             # one evaluation outside the capture (function attributes, lazily created side
                             # streams); it moves the leaves, so put them back before the real run
                             theta_keep = self.theta.clone()
-                            self._enqueue_eval(float(self.sigmas[i]), False, s, phase)
+                            for ln in self.lanes:
+                                self._enqueue_eval(float(self.sigmas[i]), False, s, phase, ln)
                             s.synchronize()
                             self.theta.copy_(theta_keep); self.velocity.copy_(v)
                             g = torch.cuda.CUDAGraph()
@@ -267,12 +316,12 @@ class GuidanceLoop:
                 if out is None:
                     out = {
                         "velocity": self._pin("o_velocity", self.velocity), "prev_sample": self._pin("o_prev", self.prev),
-                        "theta": self._pin("o_theta", self.theta), "terms": self._pin("o_terms", self.engine.terms),
+                        "theta": self._pin("o_theta", self.theta), "terms": self._pin("o_terms", self.terms),
                     }
                 out["velocity"].copy_(self.velocity, non_blocking=True)
                 out["prev_sample"].copy_(self.prev, non_blocking=True)
                 out["theta"].copy_(self.theta, non_blocking=True)
-                out["terms"].copy_(self.engine.terms, non_blocking=True)
+                out["terms"].copy_(self.terms, non_blocking=True)
             self.stream.synchronize()
         return out
 
@@ -295,7 +344,7 @@ class GuidanceLoop:
                 self._stage = {n: torch.empty_like(t) for n, t in (("sdf0", self.sdf0), ("x_t", self.x_t),
                                                                     ("velocity", self.velocity), ("theta", self.theta))}
                 self._ostage = {n: torch.empty_like(t) for n, t in (("velocity", self.velocity), ("prev_sample", self.prev),
-                                                                     ("theta", self.theta), ("terms", self.engine.terms))}
+                                                                     ("theta", self.theta), ("terms", self.terms))}
                 self.d2h_stream = torch.cuda.Stream(device=dev)
                 self._ev_stage_free = torch.cuda.Event()
                 self._ev_out_free = torch.cuda.Event()
@@ -306,9 +355,12 @@ class GuidanceLoop:
                 x.wait_stream(cur)
             self._ev_stage_free.record(s)
             self._ev_out_free.record(ds)
+            batches = list(batches)
+            # every batch's pinned result buffers exist before the pipeline starts (cached across calls):
+            # cudaHostAlloc synchronises the device and would stall the three streams mid-flight
+            outs = [{n: self._pin(f"p{k}_{n}", t) for n, t in ost.items()} for k in range(len(batches))]
             for k, (sdf0_h, x_t_h, vel_h, theta_h) in enumerate(batches):
-                out = {n: self._pin(f"p{k}_{n}", t) for n, t in ost.items()}
-                outs.append(out)
+                out = outs[k]
                 # upload into the staging set as soon as the previous batch has left it
                 cs.wait_event(self._ev_stage_free)
                 with torch.cuda.stream(cs):
@@ -329,7 +381,7 @@ class GuidanceLoop:
                     self._graph.replay()
                     s.wait_event(self._ev_out_free)
                     ost["velocity"].copy_(self.velocity); ost["prev_sample"].copy_(self.prev)
-                    ost["theta"].copy_(self.theta); ost["terms"].copy_(self.engine.terms)
+                    ost["theta"].copy_(self.theta); ost["terms"].copy_(self.terms)
                     out_ready = torch.cuda.Event()
                     out_ready.record(s)
                 ds.wait_event(out_ready)

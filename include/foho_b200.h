@@ -86,7 +86,10 @@ typedef struct foho_guidance_desc {
   int32_t stream_stages;   /* TMA stream: ring depth of 16 KB tiles (0 = default 6) */
   int32_t stream_prefetch; /* TMA stream: bulk loads kept in flight per CTA (0 = default 4)      */
   int32_t stream_ctas;     /* TMA stream: persistent CTAs per SM (0 = default 1)                */
-  int32_t reserved0;
+  int32_t lane;            /* 0..3: which set of library side streams this call forks onto; callers
+                              that keep several evaluations in flight (micro-batches on different
+                              streams) give each its own lane so their side chains do not order
+                              behind one another                                                */
   float fov_deg;        /* MoGe fov_x in degrees (guidance/run.py:228-230)              */
   float bound;          /* lattice half extent, 1.10 (pipelines.py:1127)                */
   foho_weights w;
