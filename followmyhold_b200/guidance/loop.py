@@ -76,6 +76,11 @@ class GuidanceLoop:
             st_j = statics if m == 1 else slice_statics(statics, j * nb, nb)
             eng = GuidanceEngine(nb, D, Vh, Fh, P, device=device, weights=weights, stream_variant=stream_variant)
             eng.lane = j
+            if m > 1:
+                # the lanes' stream kernels share the SMs most of the time: 3 bulk loads in flight per CTA
+                # (2 x 48 KB per SM when both run) measured best, 826 vs 792 image-steps/s with 4
+                # (profiles/r01_microbatch_probe.json); a 5-slot ring is enough for that
+                eng.stream_stages, eng.stream_prefetch = 5, 3
             eng.terms = self.terms.narrow(0, j * nb, nb)             # the lanes write straight into the
             eng.grad_theta = self.grad_theta.narrow(0, j * nb, nb)   # loop's [B, .] result buffers
             eng.prepare(st_j)
