@@ -15,6 +15,7 @@ optimiser are exercised with real data flow.  A real decoder plugs in through
 from __future__ import annotations
 
 import ctypes as C
+import time
 from typing import Dict, Optional
 
 import torch
@@ -344,21 +345,26 @@ class GuidanceLoop:
         self.capture(step_index)
         dev = self.device
         outs = []
+        t_begin = time.perf_counter()
         with torch.cuda.device(dev):
             if not hasattr(self, "_stage"):
-                self._stage = {n: torch.empty_like(t) for n, t in (("sdf0", self.sdf0), ("x_t", self.x_t),
-                                                                    ("velocity", self.velocity), ("theta", self.theta))}
+                # two staging sets: the upload of batch k+1 starts the moment batch k's upload ends, so the
+                # PCIe link -- the slowest resource of this path -- never waits for the compute stream
+                self._stage = [{n: torch.empty_like(t) for n, t in (("sdf0", self.sdf0), ("x_t", self.x_t),
+                                                                     ("velocity", self.velocity), ("theta", self.theta))}
+                               for _ in range(2)]
                 self._ostage = {n: torch.empty_like(t) for n, t in (("velocity", self.velocity), ("prev_sample", self.prev),
                                                                      ("theta", self.theta), ("terms", self.terms))}
                 self.d2h_stream = torch.cuda.Stream(device=dev)
-                self._ev_stage_free = torch.cuda.Event()
+                self._ev_stage_free = [torch.cuda.Event(), torch.cuda.Event()]
                 self._ev_out_free = torch.cuda.Event()
             cs, s, ds = self.copy_stream, self.stream, self.d2h_stream
-            st, ost = self._stage, self._ostage
+            ost = self._ostage
             cur = torch.cuda.current_stream(dev)
             for x in (cs, s, ds):
                 x.wait_stream(cur)
-            self._ev_stage_free.record(s)
+            for ev in self._ev_stage_free:
+                ev.record(s)
             self._ev_out_free.record(ds)
             batches = list(batches)
             # every batch's pinned result buffers exist before the pipeline starts (cached across calls):
@@ -366,8 +372,9 @@ class GuidanceLoop:
             outs = [{n: self._pin(f"p{k}_{n}", t) for n, t in ost.items()} for k in range(len(batches))]
             for k, (sdf0_h, x_t_h, vel_h, theta_h) in enumerate(batches):
                 out = outs[k]
-                # upload into the staging set as soon as the previous batch has left it
-                cs.wait_event(self._ev_stage_free)
+                st = self._stage[k & 1]
+                # upload into this batch's staging set as soon as batch k-2 has left it
+                cs.wait_event(self._ev_stage_free[k & 1])
                 with torch.cuda.stream(cs):
                     if sdf0_h is not None:          # None: the decoder state of this batch is already resident
                         st["sdf0"].copy_(sdf0_h, non_blocking=True)
@@ -382,7 +389,7 @@ class GuidanceLoop:
                         self.sdf0.copy_(st["sdf0"])
                     self.sdf.copy_(self.sdf0)
                     self.x_t.copy_(st["x_t"]); self.velocity.copy_(st["velocity"]); self.theta.copy_(st["theta"])
-                    self._ev_stage_free.record(s)
+                    self._ev_stage_free[k & 1].record(s)
                     self._graph.replay()
                     s.wait_event(self._ev_out_free)
                     ost["velocity"].copy_(self.velocity); ost["prev_sample"].copy_(self.prev)
@@ -394,6 +401,7 @@ class GuidanceLoop:
                     for n in ost:
                         out[n].copy_(ost[n], non_blocking=True)
                     self._ev_out_free.record(ds)
+            self._last_enqueue_s = time.perf_counter() - t_begin     # host time to enqueue the whole pipeline
             for x in (cs, s, ds):
                 x.synchronize()
         return outs

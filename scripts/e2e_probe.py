@@ -53,6 +53,7 @@ for m in (1, 2):
     t0 = time.perf_counter()
     lp.denoise_steps_host(STEP, [batch] * 8)
     out[f"m{m}_pipelined_ms_per_batch"] = (time.perf_counter() - t0) / 8 * 1e3
+    out[f"m{m}_host_enqueue_ms_per_batch"] = lp._last_enqueue_s / 8 * 1e3
     del lp
     torch.cuda.empty_cache()
 print(json.dumps(out))
