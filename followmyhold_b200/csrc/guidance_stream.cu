@@ -68,7 +68,7 @@ __device__ __forceinline__ void acc_init(StreamAcc &a) {
 // one float4 of a row (ix,iy) at z = z0..z0+3; cz[k] = k2*z^2 + ez*z precomputed
 __device__ __forceinline__ float4 voxel4(float4 s, float fx, float fy, const StreamCoef &c, const float (&cz)[4],
                                          StreamAcc &a) {
-  float r2 = fx * fx + fy * fy;
+  float r2 = fmaf(fy, fy, __fmul_rn(fx, fx));          // explicit: every instantiation rounds the same way
   float crow = fmaf(c.k2, r2, fmaf(c.ex, fx, fmaf(c.ey, fy, c.f)));
   float w0 = fmaxf(-s.x, 0.f), w1 = fmaxf(-s.y, 0.f), w2 = fmaxf(-s.z, 0.f), w3 = fmaxf(-s.w, 0.f);
   float4 g;
@@ -128,10 +128,25 @@ __global__ void __launch_bounds__(LDG_THREADS) k_stream_ldg(const float *__restr
   float cz[4];
 #pragma unroll
   for (int k = 0; k < 4; ++k) { float z = z0 + (float)k; cz[k] = fmaf(c.k2 * z, z, c.ez * z); }
+  const bool fast = logD >= 6 && log4 <= 8;         // see k_stream_tma
+  const int rows_per_tile = (int)tile4 >> log4;
+  float dy[LDG_UNROLL];
+#pragma unroll
+  for (int u = 0; u < LDG_UNROLL; ++u) dy[u] = (float)((u * LDG_THREADS) >> log4);
   StreamAcc a; acc_init(a);
   for (long long t = blockIdx.x; t < ntiles; t += gridDim.x) {
     long long base = t * tile4 + threadIdx.x;
     float4 s[LDG_UNROLL];
+    if (fast) {
+#pragma unroll
+      for (int u = 0; u < LDG_UNROLL; ++u) s[u] = __ldcs(S4 + base + (long long)u * LDG_THREADS);
+      const int first_row = (int)t * rows_per_tile;
+      const float fx = (float)(first_row >> logD);
+      const float fyb = (float)((first_row & (D - 1)) + (threadIdx.x >> log4));
+#pragma unroll
+      for (int u = 0; u < LDG_UNROLL; ++u) __stcs(G4 + base + (long long)u * LDG_THREADS, voxel4(s[u], fx, fyb + dy[u], c, cz, a));
+      continue;
+    }
 #pragma unroll
     for (int u = 0; u < LDG_UNROLL; ++u) {
       long long i = base + (long long)u * LDG_THREADS;
@@ -242,6 +257,11 @@ __global__ void __launch_bounds__(TMA_THREADS, 2) k_stream_tma(const float *__re
                 &full[k]);
     }
   }
+  const bool fast = logD >= 6 && log4 <= 8;
+  const int rows_per_tile = TMA_TILE_F4 >> log4;
+  float dy[TMA_F4_PER_THREAD];
+#pragma unroll
+  for (int u = 0; u < TMA_F4_PER_THREAD; ++u) dy[u] = (float)((u * TMA_THREADS) >> log4);
   StreamAcc a; acc_init(a);
   int s = 0, sn = nprefetch % nstages;     // ring slots of tile k and of tile k + nprefetch
   uint32_t ph = 0;
@@ -251,14 +271,28 @@ __global__ void __launch_bounds__(TMA_THREADS, 2) k_stream_tma(const float *__re
     const int n4 = tile_f4(k);
     float4 *buf = stage + (size_t)s * TMA_TILE_F4;
     mbar_wait(&full[s], ph);
+    if (fast) {
+      // D >= 64: a tile (4096 voxels) lies inside one x-slab and is never partial, so x is a per-tile
+      // constant and y a per-thread base plus a per-slot constant -- same float values, same arithmetic
+      // as the general path below (bit-identical results), without the per-float4 index math
+      const int first_row = (int)t * rows_per_tile;
+      const float fx = (float)(first_row >> logD);
+      const float fyb = (float)((first_row & (D - 1)) + (threadIdx.x >> log4));
 #pragma unroll
-    for (int u = 0; u < TMA_F4_PER_THREAD; ++u) {
-      int f = threadIdx.x + u * TMA_THREADS;
-      if (f < n4) {
-        long long i = t * TMA_TILE_F4 + f;
-        int row = (int)(i >> log4);
-        float fx = (float)(row >> logD), fy = (float)(row & (D - 1));
-        buf[f] = voxel4(buf[f], fx, fy, c, cz, a);
+      for (int u = 0; u < TMA_F4_PER_THREAD; ++u) {
+        const int f = threadIdx.x + u * TMA_THREADS;
+        buf[f] = voxel4(buf[f], fx, fyb + dy[u], c, cz, a);
+      }
+    } else {
+#pragma unroll
+      for (int u = 0; u < TMA_F4_PER_THREAD; ++u) {
+        int f = threadIdx.x + u * TMA_THREADS;
+        if (f < n4) {
+          long long i = t * TMA_TILE_F4 + f;
+          int row = (int)(i >> log4);
+          float fx = (float)(row >> logD), fy = (float)(row & (D - 1));
+          buf[f] = voxel4(buf[f], fx, fy, c, cz, a);
+        }
       }
     }
     fence_proxy_async();       // make the generic-proxy smem writes visible to the bulk store
