@@ -140,6 +140,31 @@ def test_pipelined_host_api_matches_single_batch_calls():
     assert not torch.allclose(piped[0]["velocity"], piped[1]["velocity"])
 
 
+@pytest.mark.parametrize("m", [2, 4])
+def test_micro_batches_do_not_change_results(m):
+    """The batch advanced as m independent lanes inside the step graph gives what one lane gives:
+    images never interact (pipelines.py processes them one at a time)."""
+    from followmyhold_b200.guidance.config import OptimizationConfig
+    from followmyhold_b200.guidance.loop import GuidanceLoop, slice_statics
+    B, D, P = 4, 64, 1024
+    samples = [make_guidance_sample(D, P, 120 + i) for i in range(B)]
+    sdf0, theta0, st = stack_samples(samples, cap=True)
+    half = slice_statics(st, 2, 2)
+    assert half.hand_rest.shape[0] == 2 and torch.equal(half.cloud, st.cloud[2:4]) and half.hand_faces is st.hand_faces
+    cfg = OptimizationConfig(); cfg.optimization_steps_joint = 4
+    g = torch.Generator().manual_seed(7)
+    res = []
+    for mb in (1, m):
+        lp = GuidanceLoop(B, D, st, P, config=cfg, seed=3, micro_batches=mb)
+        assert len(lp.lanes) == mb and lp.launches_per_step() == mb * (4 * lp.kernels_per_eval() + 2)
+        g.manual_seed(7)
+        x_t = torch.randn(B, lp.L, generator=g); vel = 0.1 * torch.randn(B, lp.L, generator=g)
+        out = lp.denoise_step_host(13, sdf0.cpu().pin_memory(), x_t.pin_memory(), vel.pin_memory(), theta0.cpu().pin_memory())
+        res.append({n: t.clone() for n, t in out.items()})
+    for n in ("theta", "velocity", "prev_sample", "terms"):
+        assert torch.allclose(res[0][n], res[1][n], rtol=1e-4, atol=1e-6), n
+
+
 def test_overlapped_and_serial_evaluations_agree():
     """desc.serial=1 (every kernel in series on the caller's stream) and the default fork/join layout
     give the same energy terms and gradients; the trace hook reports every kernel of the evaluation."""
