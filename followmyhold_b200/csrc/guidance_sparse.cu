@@ -176,8 +176,8 @@ __global__ void __launch_bounds__(RASTER_THREADS) k_raster(foho_guidance_desc d,
 }
 
 // ----------------------------------------------------------------------------- k_compact
-// one warp per (column, 32-voxel word) of the hand's lattice bbox; lane z owns bit z: one coalesced
-// 128-byte read of S per word that has any bit set, one slot reservation per warp.
+// one lane per (column, 32-voxel word) of the hand's lattice bbox: the word of the parity mask, the 128
+// bytes of S under it, the hits; one slot reservation per warp of 32 words.
 __global__ void __launch_bounds__(256) k_compact(foho_guidance_desc d, FohoWorkspace ws) {
   FohoTrace trace_(ws.trace, TR_COMPACT);
   const int b = blockIdx.y, D = d.D, lane = threadIdx.x & 31;
@@ -204,31 +204,27 @@ __global__ void __launch_bounds__(256) k_compact(foho_guidance_desc d, FohoWorks
       col = (fr.lo[0] + c / ny) * D + (fr.lo[1] + c % ny);
       word = par[(size_t)col * ws.W + wz];
     }
-    // pass 1: the hit mask of every non-zero word (lane j keeps the mask of the word lane j fetched);
-    //         four words per step so that their reads of S overlap
-    unsigned todo = __ballot_sync(0xffffffffu, word != 0u);
+    // pass 1: every lane tests its own word: the 32 field values of the word are one 128-byte line,
+    //         fetched with eight independent 16-byte loads (one trip to DRAM for the whole warp's 32 words;
+    //         a lane-per-bit scan needed one dependent trip per non-zero word)
     unsigned mymask = 0u;
-    while (todo) {
-      int src[4];
-      bool hit[4];
+    if (word != 0u) {
+      const size_t v0 = (size_t)col * D + (size_t)wz * 32;
+      const float *sp = S + v0;
+      if ((D & 3) == 0 && wz * 32 + 32 <= D) {
+        const float4 *s4 = reinterpret_cast<const float4 *>(sp);       // (col * D + wz * 32) % 4 == 0
+        float4 q[8];
 #pragma unroll
-      for (int u = 0; u < 4; ++u) {
-        src[u] = todo ? __ffs(todo) - 1 : -1;
-        if (todo) todo &= todo - 1;
-        hit[u] = false;
-        if (src[u] >= 0) {
-          const uint32_t bits = __shfl_sync(0xffffffffu, word, src[u]);
-          const int ccol = __shfl_sync(0xffffffffu, col, src[u]), cw = __shfl_sync(0xffffffffu, wz, src[u]);
-          const int Z = cw * 32 + lane;
-          hit[u] = ((bits >> lane) & 1u) && Z < D && S[(size_t)ccol * D + Z] < 0.f;
+        for (int u = 0; u < 8; ++u) q[u] = s4[u];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+          mymask |= (q[u].x < 0.f ? 1u : 0u) << (4 * u) | (q[u].y < 0.f ? 1u : 0u) << (4 * u + 1) |
+                    (q[u].z < 0.f ? 1u : 0u) << (4 * u + 2) | (q[u].w < 0.f ? 1u : 0u) << (4 * u + 3);
         }
+      } else {
+        for (int z = 0; z < 32 && wz * 32 + z < D; ++z) mymask |= (sp[z] < 0.f ? 1u : 0u) << z;
       }
-#pragma unroll
-      for (int u = 0; u < 4; ++u) {
-        if (src[u] < 0) continue;
-        const unsigned m = __ballot_sync(0xffffffffu, hit[u]);
-        if (lane == src[u]) mymask = m;
-      }
+      mymask &= word;
     }
     // pass 2: one slot reservation for the whole batch, then every lane writes its own word's hits
     const int mine = __popc(mymask);

@@ -37,6 +37,7 @@ __global__ void __launch_bounds__(VT_THREADS) k_voxdist_staged(foho_guidance_des
   float4 *sph = reinterpret_cast<float4 *>(sm_raw);             // [NF] face spheres (pad: r = -1)
   float4 *sv = sph + NF;                                        // [Vh] posed vertices, lattice units
   int *queue = reinterpret_cast<int *>(sv + Vh);                // [VT_WARPS][VT_QUEUE]
+  ushort4 *sfv = reinterpret_cast<ushort4 *>(queue + VT_WARPS * VT_QUEUE);   // [NF] vertex ids of the faces (Vh <= 65535)
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   {
     const float4 *gs = ws.sph + (size_t)b * Fh;
@@ -45,6 +46,12 @@ __global__ void __launch_bounds__(VT_THREADS) k_voxdist_staged(foho_guidance_des
     const float *hg = ws.hg + (size_t)b * Vh * 3;
 #pragma unroll 4
     for (int i = threadIdx.x; i < Vh; i += blockDim.x) sv[i] = make_float4(hg[3 * i], hg[3 * i + 1], hg[3 * i + 2], 0.f);
+    const int4 *gf = acc.face_sv + (size_t)b * FOHO_ACCEL_FACES;
+#pragma unroll 8
+    for (int i = threadIdx.x; i < Fh; i += blockDim.x) {
+      const int4 f = gf[i];
+      sfv[i] = make_ushort4((unsigned short)f.x, (unsigned short)f.y, (unsigned short)f.z, 0);
+    }
   }
   __syncthreads();
 
@@ -55,7 +62,6 @@ __global__ void __launch_bounds__(VT_THREADS) k_voxdist_staged(foho_guidance_des
   float *Ghg = ws.G_hg + (size_t)b * Vh * 3;
   const int *cand = ws.cand + (size_t)b * ws.cap;
   float *cval = ws.cand_val + (size_t)b * ws.cap;   // dE/dS of the candidate, added to G by k_assemble
-  const int4 *fsv = acc.face_sv + (size_t)b * FOHO_ACCEL_FACES;
   int *q = queue + wid * VT_QUEUE;
   float acc_int = 0.f, acc_gk = 0.f;
   const int c0 = (blockIdx.x * VT_WARPS + wid) * run;
@@ -100,7 +106,7 @@ __global__ void __launch_bounds__(VT_THREADS) k_voxdist_staged(foho_guidance_des
     auto drain = [&](int count) {                              // exact test of queue[0..count), one per lane
       if (lane < count) {
         const int s = q[lane];
-        const int4 f = fsv[s];
+        const ushort4 f = sfv[s];
         float wa, wb, wc;
         // translate by -p first: differences of nearby lattice coordinates are (nearly) exact in fp32
         const float4 A = sv[f.x], Bv = sv[f.y], C = sv[f.z];
@@ -139,7 +145,7 @@ __global__ void __launch_bounds__(VT_THREADS) k_voxdist_staged(foho_guidance_des
         nq -= 32;
         const int s = q[nq + lane];
         {
-          const int4 f = fsv[s];
+          const ushort4 f = sfv[s];
           float wa, wb, wc;
           const float4 A = sv[f.x], Bv = sv[f.y], C = sv[f.z];
           const float d2 = closest_point_triangle(f3(0.f, 0.f, 0.f), f3(A.x, A.y, A.z) - p, f3(Bv.x, Bv.y, Bv.z) - p,
@@ -171,7 +177,7 @@ __global__ void __launch_bounds__(VT_THREADS) k_voxdist_staged(foho_guidance_des
       acc_gk += coef * dist;
       cval[c] = -d.w.w_ivol * kappa * dist / N;
       if (dist > 0.f) {
-        const int4 f = fsv[bst.s];
+        const ushort4 f = sfv[bst.s];
         const float4 A = sv[f.x], Bv = sv[f.y], C = sv[f.z];
         const foho_f3 a = f3(A.x, A.y, A.z) - p, bb = f3(Bv.x, Bv.y, Bv.z) - p, cc = f3(C.x, C.y, C.z) - p;
         const foho_f3 qq = f3(bst.wa * a.x + bst.wb * bb.x + bst.wc * cc.x, bst.wa * a.y + bst.wb * bb.y + bst.wc * cc.y,
@@ -201,13 +207,13 @@ int foho_launch_voxdist_staged(const foho_guidance_desc *dp, const FohoWorkspace
   foho_accel_layout(a, (char *)d.accel, d.B, d.P);
   if (a.total > d.accel_bytes) return FOHO_E_WORKSPACE;
   const int NF = (d.Fh + 31) & ~31;
-  const size_t smem = ((size_t)NF + (size_t)d.Vh) * sizeof(float4) + VT_WARPS * VT_QUEUE * sizeof(int);
+  const size_t smem = ((size_t)NF + (size_t)d.Vh) * sizeof(float4) + VT_WARPS * VT_QUEUE * sizeof(int) + (size_t)NF * sizeof(ushort4);
   if (smem > 200 * 1024) return FOHO_E_SHAPE;
   {
     int rc = foho_func_attrs((const void *)k_voxdist_staged, FA_VOXDIST, smem, true);
     if (rc != FOHO_OK) return rc;
   }
-  k_voxdist_staged<<<dim3(32, d.B), VT_THREADS, smem, st>>>(d, ws, a);
+  k_voxdist_staged<<<dim3(64, d.B), VT_THREADS, smem, st>>>(d, ws, a);
   FOHO_LAUNCH_CHECK();
   return FOHO_OK;
 }
