@@ -154,3 +154,39 @@ def test_cpulist_parser_and_numa_binding_is_best_effort(tmp_path):
     # no GPU here: the helper must not raise and must report that nothing was bound
     info = bind_to_gpu_numa(0, sysfs=str(tmp_path))
     assert info["bound"] is False
+
+
+def test_delaunay_graph_makes_greedy_descent_exact():
+    """The claim k_chamfer_c2h_walk rests on: on the Delaunay neighbour graph of the rest hand, moving to
+    the neighbour closest to the query until none is closer ends at the true nearest vertex, from any
+    start, for near and far queries alike.  (Emulated here with numpy on the graph the host builds.)"""
+    import torch
+    from followmyhold_b200.guidance.engine import delaunay_neighbours
+    from followmyhold_b200.synthetic import make_guidance_sample
+    s = make_guidance_sample(16, 64, 5)
+    rest = s.hand_rest.numpy().astype(np.float64)
+    off, nbr = delaunay_neighbours(torch.stack([s.hand_rest, s.hand_rest * 1.3 + 0.1]))
+    assert off.shape == (2, 779) and off.dtype == torch.int32 and nbr.shape[1] % 8 == 0
+    indptr, idx = off[0].numpy(), nbr[0].numpy().view(np.uint16)
+    assert indptr[0] == 0 and (np.diff(indptr) >= 3).all()
+    # symmetric adjacency
+    pairs = {(i, int(j)) for i in range(778) for j in idx[indptr[i]:indptr[i + 1]]}
+    assert all((j, i) in pairs for i, j in pairs)
+    rng = np.random.default_rng(0)
+    c, ext = rest.mean(0), np.ptp(rest, axis=0).max()
+    queries = np.concatenate([rest[rng.integers(0, 778, 300)] + 0.02 * ext * rng.normal(size=(300, 3)),
+                              c + 0.6 * ext * rng.normal(size=(300, 3)), c + 6.0 * ext * rng.normal(size=(300, 3))])
+    for q in queries:
+        d2 = ((rest - q) ** 2).sum(1)
+        cur = int(rng.integers(0, 778))
+        for _ in range(778):
+            nb = idx[indptr[cur]:indptr[cur + 1]].astype(np.int64)
+            k = nb[d2[nb].argmin()]
+            if d2[k] < d2[cur]:
+                cur = int(k)
+            else:
+                break
+        assert d2[cur] == d2.min()
+    # degenerate input (all points in a plane): no graph, the caller keeps the box search
+    flat = s.hand_rest.clone(); flat[:, 2] = 0.0
+    assert delaunay_neighbours(flat[None]) is None
