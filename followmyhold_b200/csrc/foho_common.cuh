@@ -273,5 +273,6 @@ int foho_launch_objmesh_post(const foho_guidance_desc *d, const FohoWorkspace &w
 // grouped exact point->mesh distance of the candidate voxels (guidance_voxdist.cu); needs desc->accel
 int foho_launch_voxdist_staged(const foho_guidance_desc *d, const FohoWorkspace &ws, cudaStream_t st);
 void foho_accel_layout(FohoAccel &a, char *base, int B, int P);
+int foho_sort_u64(unsigned long long *keys, int P2, int batch, cudaStream_t st);   // guidance_chamfer.cu
 int foho_launch_chamfer_h2c(const foho_guidance_desc *d, const FohoWorkspace &ws, cudaStream_t st);
 int foho_launch_chamfer_c2h(const foho_guidance_desc *d, const FohoWorkspace &ws, cudaStream_t st);

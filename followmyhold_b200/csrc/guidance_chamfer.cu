@@ -744,6 +744,25 @@ void foho_accel_layout(FohoAccel &a, char *base, int B, int P) {
   a.total = off;
 }
 
+// bitonic sort of `batch` arrays of P2 (a power of two >= 2048) 64-bit keys, ascending
+int foho_sort_u64(unsigned long long *keys, int P2, int batch, cudaStream_t st) {
+  if (P2 < SORT_CHUNK || (P2 & (P2 - 1)) != 0) return FOHO_E_SHAPE;
+  int gx = (P2 + 255) / 256;
+  if (gx > 512) gx = 512;
+  const int nchunk = P2 / SORT_CHUNK;
+  k_sort_local<<<dim3(nchunk, batch), ACC_THREADS, 0, st>>>(keys, P2, 2, SORT_CHUNK);
+  FOHO_LAUNCH_CHECK();
+  for (int k = SORT_CHUNK * 2; k <= P2; k <<= 1) {
+    for (int j = k >> 1; j >= SORT_CHUNK; j >>= 1) {
+      k_sort_global<<<dim3(gx, batch), 256, 0, st>>>(keys, P2, j, k);
+      FOHO_LAUNCH_CHECK();
+    }
+    k_sort_local<<<dim3(nchunk, batch), ACC_THREADS, 0, st>>>(keys, P2, k, k);
+    FOHO_LAUNCH_CHECK();
+  }
+  return FOHO_OK;
+}
+
 extern "C" size_t foho_guidance_accel_bytes(int32_t B, int32_t Vh, int32_t P) {
   if (B < 1 || Vh < 1 || Vh > FOHO_ACCEL_HV || P < 1) return 0;
   FohoAccel a;
@@ -775,16 +794,9 @@ extern "C" int foho_guidance_prepare_statics(const foho_guidance_desc *dp, void 
   if (gx > 512) gx = 512;
   k_accel_cloud_keys<<<dim3(gx, d.B), 256, 0, st>>>(d.cloud, d.P, a.P2, a);
   FOHO_LAUNCH_CHECK();
-  const int nchunk = a.P2 / SORT_CHUNK;
-  k_sort_local<<<dim3(nchunk, d.B), ACC_THREADS, 0, st>>>(a.keys, a.P2, 2, SORT_CHUNK);
-  FOHO_LAUNCH_CHECK();
-  for (int k = SORT_CHUNK * 2; k <= a.P2; k <<= 1) {
-    for (int j = k >> 1; j >= SORT_CHUNK; j >>= 1) {
-      k_sort_global<<<dim3(gx, d.B), 256, 0, st>>>(a.keys, a.P2, j, k);
-      FOHO_LAUNCH_CHECK();
-    }
-    k_sort_local<<<dim3(nchunk, d.B), ACC_THREADS, 0, st>>>(a.keys, a.P2, k, k);
-    FOHO_LAUNCH_CHECK();
+  {
+    int rc = foho_sort_u64(a.keys, a.P2, d.B, st);
+    if (rc != FOHO_OK) return rc;
   }
   k_accel_cloud_gather<<<dim3(gx, d.B), 256, 0, st>>>(d.cloud, d.P, a.P2, a);
   FOHO_LAUNCH_CHECK();

@@ -41,6 +41,16 @@ struct IcpWorkspace {
   double *dist;        // [Ns]
   int *qi;             // [Ns]
   double *p;           // [Ns,3] transformed source of the current iteration
+  // static search structure over the target (built once per run): Morton-ordered points, AABBs of every
+  // 32 consecutive points and of every 32 such groups
+  unsigned long long *keys;   // [P2] build scratch
+  double *tpts;        // [Nt,3] target in Morton order
+  int *tidx;           // [Nt]   original index of each sorted point
+  double *glo, *ghi;   // [NG,3]
+  double *slo, *shi;   // [NS,3]
+  double *tbox;        // [6] bbox of the target
+  int *seed;           // [Ns] sorted position of last iteration's neighbour (-1: none yet)
+  int P2, NG, NS;
   int nchunks, chunk;
   size_t total;
 };
@@ -66,6 +76,19 @@ inline void icp_ws_layout(IcpWorkspace &w, char *base, int Ns, int Nt) {
   w.dist = (double *)take(sizeof(double) * (size_t)Ns);
   w.qi = (int *)take(sizeof(int) * (size_t)Ns);
   w.p = (double *)take(sizeof(double) * 3 * (size_t)Ns);
+  w.P2 = 2048;
+  while (w.P2 < Nt) w.P2 <<= 1;
+  w.NG = (Nt + 31) / 32;
+  w.NS = (w.NG + 31) / 32;
+  w.keys = (unsigned long long *)take(sizeof(unsigned long long) * (size_t)w.P2);
+  w.tpts = (double *)take(sizeof(double) * 3 * (size_t)Nt);
+  w.tidx = (int *)take(sizeof(int) * (size_t)Nt);
+  w.glo = (double *)take(sizeof(double) * 3 * (size_t)w.NG);
+  w.ghi = (double *)take(sizeof(double) * 3 * (size_t)w.NG);
+  w.slo = (double *)take(sizeof(double) * 3 * (size_t)w.NS);
+  w.shi = (double *)take(sizeof(double) * 3 * (size_t)w.NS);
+  w.tbox = (double *)take(sizeof(double) * 6);
+  w.seed = (int *)take(sizeof(int) * (size_t)Ns);
   w.total = off;
 }
 
@@ -116,6 +139,191 @@ __global__ void __launch_bounds__(NN_THREADS) k_icp_nn(const double *__restrict_
   }
 }
 
+// ---------------------------------------------------------------------------- target search structure
+// The target never moves during a run (150 iterations): it is put into Morton order once and boxed in
+// groups of 32 points and super-groups of 32 groups; every iteration then costs a few dozen box / point
+// evaluations per source point instead of Nt (k_icp_nn above stays as the structure-free path).
+__global__ void __launch_bounds__(1024) k_icp_tbox(const double *__restrict__ tgt, int Nt, IcpWorkspace w) {
+  __shared__ double smn[3][32], smx[3][32];
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  double mn[3] = {INFINITY, INFINITY, INFINITY}, mx[3] = {-INFINITY, -INFINITY, -INFINITY};
+  for (int i = tid; i < Nt; i += blockDim.x)
+    for (int a = 0; a < 3; ++a) { const double v = tgt[3 * (size_t)i + a]; mn[a] = fmin(mn[a], v); mx[a] = fmax(mx[a], v); }
+  for (int a = 0; a < 3; ++a)
+    for (int o = 16; o > 0; o >>= 1) {
+      mn[a] = fmin(mn[a], __shfl_xor_sync(0xffffffffu, mn[a], o));
+      mx[a] = fmax(mx[a], __shfl_xor_sync(0xffffffffu, mx[a], o));
+    }
+  if (lane == 0) for (int a = 0; a < 3; ++a) { smn[a][wid] = mn[a]; smx[a][wid] = mx[a]; }
+  __syncthreads();
+  if (tid < 3) {
+    double lo = smn[tid][0], hi = smx[tid][0];
+    for (int k = 1; k < (int)(blockDim.x >> 5); ++k) { lo = fmin(lo, smn[tid][k]); hi = fmax(hi, smx[tid][k]); }
+    w.tbox[tid] = lo; w.tbox[3 + tid] = hi;
+  }
+}
+
+__device__ __forceinline__ unsigned int icp_spread3(unsigned int v) {   // 10 bits -> every third bit
+  v &= 0x3ffu;
+  v = (v | (v << 16)) & 0x030000FFu;
+  v = (v | (v << 8)) & 0x0300F00Fu;
+  v = (v | (v << 4)) & 0x030C30C3u;
+  v = (v | (v << 2)) & 0x09249249u;
+  return v;
+}
+
+__global__ void __launch_bounds__(256) k_icp_tkeys(const double *__restrict__ tgt, int Nt, IcpWorkspace w) {
+  const double ext = fmax(fmax(w.tbox[3] - w.tbox[0], w.tbox[4] - w.tbox[1]), fmax(w.tbox[5] - w.tbox[2], 1e-300));
+  const double q = 1023.0 / ext;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < w.P2; i += gridDim.x * blockDim.x) {
+    unsigned long long k = ~0ull;
+    if (i < Nt) {
+      unsigned int c[3];
+      for (int a = 0; a < 3; ++a) c[a] = (unsigned int)fmin(fmax((tgt[3 * (size_t)i + a] - w.tbox[a]) * q, 0.0), 1023.0);
+      k = ((unsigned long long)((icp_spread3(c[0]) << 2) | (icp_spread3(c[1]) << 1) | icp_spread3(c[2])) << 32) | (unsigned int)i;
+    }
+    w.keys[i] = k;
+  }
+}
+
+__global__ void __launch_bounds__(256) k_icp_tgather(const double *__restrict__ tgt, int Nt, int Ns, IcpWorkspace w) {
+  for (int s = blockIdx.x * blockDim.x + threadIdx.x; s < Nt; s += gridDim.x * blockDim.x) {
+    const unsigned int i = (unsigned int)w.keys[s];
+    w.tpts[3 * (size_t)s] = tgt[3 * (size_t)i]; w.tpts[3 * (size_t)s + 1] = tgt[3 * (size_t)i + 1];
+    w.tpts[3 * (size_t)s + 2] = tgt[3 * (size_t)i + 2];
+    w.tidx[s] = (int)i;
+  }
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < Ns; i += gridDim.x * blockDim.x) w.seed[i] = -1;
+}
+
+// level 0: one warp per group of 32 sorted points; level 1: one warp per 32 groups
+__global__ void __launch_bounds__(256) k_icp_tboxes(int Nt, int level, IcpWorkspace w) {
+  const int lane = threadIdx.x & 31;
+  const int g = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int n_out = level == 0 ? w.NG : w.NS, n_in = level == 0 ? Nt : w.NG;
+  if (g >= n_out) return;
+  const int i = g * 32 + lane, ii = i < n_in ? i : g * 32;
+  double lo[3], hi[3];
+  for (int a = 0; a < 3; ++a) {
+    lo[a] = level == 0 ? w.tpts[3 * (size_t)ii + a] : w.glo[3 * (size_t)ii + a];
+    hi[a] = level == 0 ? lo[a] : w.ghi[3 * (size_t)ii + a];
+    for (int o = 16; o > 0; o >>= 1) {
+      lo[a] = fmin(lo[a], __shfl_xor_sync(0xffffffffu, lo[a], o));
+      hi[a] = fmax(hi[a], __shfl_xor_sync(0xffffffffu, hi[a], o));
+    }
+  }
+  if (lane == 0)
+    for (int a = 0; a < 3; ++a) {
+      (level == 0 ? w.glo : w.slo)[3 * (size_t)g + a] = lo[a];
+      (level == 0 ? w.ghi : w.shi)[3 * (size_t)g + a] = hi[a];
+    }
+}
+
+__device__ __forceinline__ double icp_box_d2(const double *lo, const double *hi, double x, double y, double z) {
+  const double dx = fmax(fmax(lo[0] - x, x - hi[0]), 0.0);
+  const double dy = fmax(fmax(lo[1] - y, y - hi[1]), 0.0);
+  const double dz = fmax(fmax(lo[2] - z, z - hi[2]), 0.0);
+  return dx * dx + dy * dy + dz * dz;
+}
+
+struct IcpBest { double d2; int idx, pos; };
+// fold the 32 lane candidates into the warp-uniform best: smallest d2, ties -> smallest ORIGINAL index
+// (what the brute-force scan in index order returns)
+__device__ __forceinline__ void icp_fold(IcpBest &b, double d2, int idx, int pos) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const double od = __shfl_xor_sync(0xffffffffu, d2, o);
+    const int oi = __shfl_xor_sync(0xffffffffu, idx, o), op = __shfl_xor_sync(0xffffffffu, pos, o);
+    if (od < d2 || (od == d2 && oi < idx)) { d2 = od; idx = oi; pos = op; }
+  }
+  if (d2 < b.d2 || (d2 == b.d2 && idx < b.idx)) { b.d2 = d2; b.idx = idx; b.pos = pos; }
+}
+
+// one warp per source point: transform, then exact 1-NN over the box hierarchy, warm-started from the
+// group that held last iteration's neighbour.  Writes dist (Euclidean, like cKDTree.query) and the index.
+__global__ void __launch_bounds__(256) k_icp_nn_tree(const double *__restrict__ src, int Ns, int Nt, IcpWorkspace w,
+                                                     int *__restrict__ nn_out) {
+  const int lane = threadIdx.x & 31;
+  const int i = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (i >= Ns) return;
+  const double *T = w.state->T;
+  const double x = src[3 * (size_t)i], y = src[3 * (size_t)i + 1], z = src[3 * (size_t)i + 2];
+  const double px = T[0] * x + T[1] * y + T[2] * z + T[3];
+  const double py = T[4] * x + T[5] * y + T[6] * z + T[7];
+  const double pz = T[8] * x + T[9] * y + T[10] * z + T[11];
+  if (lane == 0) { w.p[3 * (size_t)i] = px; w.p[3 * (size_t)i + 1] = py; w.p[3 * (size_t)i + 2] = pz; }
+  IcpBest b; b.d2 = INFINITY; b.idx = 0x7fffffff; b.pos = -1;
+  auto scan_group = [&](int g) {
+    const int s = g * 32 + lane;
+    double d2 = INFINITY; int idx = 0x7fffffff;
+    if (s < Nt) {
+      const double dx = px - w.tpts[3 * (size_t)s], dy = py - w.tpts[3 * (size_t)s + 1], dz = pz - w.tpts[3 * (size_t)s + 2];
+      d2 = dx * dx + dy * dy + dz * dz;
+      idx = w.tidx[s];
+    }
+    icp_fold(b, d2, idx, s);
+  };
+  auto scan_super = [&](int sg, int skip) {
+    const int g = sg * 32 + lane;
+    double lb = INFINITY;
+    if (g < w.NG && g != skip) lb = icp_box_d2(w.glo + 3 * (size_t)g, w.ghi + 3 * (size_t)g, px, py, pz);
+    unsigned mask = __ballot_sync(0xffffffffu, lb <= b.d2);
+    while (mask) {
+      scan_group(sg * 32 + __ffs(mask) - 1);
+      mask &= mask - 1;
+      mask &= __ballot_sync(0xffffffffu, lb <= b.d2);
+    }
+  };
+  int s0 = -1, g0 = -1;
+  const int seed = w.seed[i];
+  if (seed >= 0 && seed < Nt) {
+    g0 = seed >> 5;
+    scan_group(g0);
+  } else {
+    // greedy descent: nearest super-group, its nearest group
+    double bl = INFINITY; int bs = 0;
+    for (int s = lane; s < w.NS; s += 32) {
+      const double v = icp_box_d2(w.slo + 3 * (size_t)s, w.shi + 3 * (size_t)s, px, py, pz);
+      if (v < bl) { bl = v; bs = s; }
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+      const double ov = __shfl_xor_sync(0xffffffffu, bl, o);
+      const int os = __shfl_xor_sync(0xffffffffu, bs, o);
+      if (ov < bl || (ov == bl && os < bs)) { bl = ov; bs = os; }
+    }
+    s0 = bs;
+    const int g = s0 * 32 + lane;
+    double lb = g < w.NG ? icp_box_d2(w.glo + 3 * (size_t)g, w.ghi + 3 * (size_t)g, px, py, pz) : INFINITY;
+    int bg = g;
+    for (int o = 16; o > 0; o >>= 1) {
+      const double ov = __shfl_xor_sync(0xffffffffu, lb, o);
+      const int og = __shfl_xor_sync(0xffffffffu, bg, o);
+      if (ov < lb || (ov == lb && og < bg)) { lb = ov; bg = og; }
+    }
+    g0 = bg;
+    scan_group(g0);
+    scan_super(s0, g0);
+  }
+  for (int sb = 0; sb < w.NS; sb += 32) {
+    const int s = sb + lane;
+    double lb = INFINITY;
+    if (s < w.NS && s != s0) lb = icp_box_d2(w.slo + 3 * (size_t)s, w.shi + 3 * (size_t)s, px, py, pz);
+    unsigned mask = __ballot_sync(0xffffffffu, lb <= b.d2);
+    while (mask) {
+      const int sg = sb + __ffs(mask) - 1;
+      scan_super(sg, sg == (g0 >> 5) ? g0 : -1);
+      mask &= mask - 1;
+      mask &= __ballot_sync(0xffffffffu, lb <= b.d2);
+    }
+  }
+  if (lane == 0) {
+    w.dist[i] = sqrt(b.d2);
+    w.qi[i] = b.idx;
+    w.seed[i] = b.pos;
+    if (nn_out) nn_out[i] = b.idx;
+  }
+}
+
 // ---- block-wide helpers for k_icp_step (1024 threads)
 __device__ double block_sum_d(double v, double *sm) {
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
@@ -151,7 +359,7 @@ __device__ void block_sum_dn(double (&v)[N], double *sm /* [N*32] */) {
 
 __global__ void __launch_bounds__(STEP_THREADS) k_icp_step(const double *__restrict__ tgt, int Ns, int n_outliers,
                                                            int fixed_scale, double min_scale, double max_scale,
-                                                           IcpWorkspace w, double *cost_history, int *nn_out) {
+                                                           IcpWorkspace w, double *cost_history, int *nn_out, int reduce_partials) {
   __shared__ double smd[11 * 32];
   __shared__ unsigned int hist[256];
   __shared__ unsigned long long s_prefix;
@@ -160,7 +368,7 @@ __global__ void __launch_bounds__(STEP_THREADS) k_icp_step(const double *__restr
   const int tid = threadIdx.x;
 
   // 1. reduce the per-chunk partial minima; dist = sqrt(d2) (cKDTree returns Euclidean distance)
-  for (int i = tid; i < Ns; i += STEP_THREADS) {
+  for (int i = tid; reduce_partials && i < Ns; i += STEP_THREADS) {
     double best = w.pd2[i];
     int bi = w.pidx[i];
     for (int c = 1; c < w.nchunks; ++c) {
@@ -178,6 +386,18 @@ __global__ void __launch_bounds__(STEP_THREADS) k_icp_step(const double *__restr
   const int n_in = Ns - (n_outliers > 0 ? n_outliers : 0);
   unsigned long long thr = ~0ull;
   int take_eq = 0;                       // how many elements equal to thr are inliers (lowest indices first)
+  // the distances stay in registers over the eight radix passes (up to 8 per thread: Ns <= 8192); larger
+  // sets re-read them from memory
+  constexpr int REG_PER = 8;
+  const bool in_regs = Ns <= REG_PER * STEP_THREADS;
+  unsigned long long rbits[REG_PER];
+  if (in_regs) {
+#pragma unroll
+    for (int k = 0; k < REG_PER; ++k) {
+      const int i = tid + k * STEP_THREADS;
+      rbits[k] = i < Ns ? (unsigned long long)__double_as_longlong(w.dist[i]) : ~0ull;
+    }
+  }
   if (n_outliers > 0) {
     if (tid == 0) { s_prefix = 0ull; s_remaining = n_in; }
     __syncthreads();
@@ -188,9 +408,22 @@ __global__ void __launch_bounds__(STEP_THREADS) k_icp_step(const double *__restr
       const unsigned long long mask = shift == 56 ? 0ull : (~0ull << (shift + 8));
       // the distances share their leading bytes, so most lanes of a warp hit the same bucket: one
       // shared-memory atomic per distinct digit per warp instead of one per element
-      for (int base = 0; base < Ns; base += STEP_THREADS) {
+#pragma unroll
+      for (int k = 0; k < REG_PER; ++k) {
+        const int base = k * STEP_THREADS;
+        if (base >= Ns) break;                                    // uniform
         const int i = base + tid;
         unsigned int key = 256u;                                  // 256 = not a candidate
+        if (i < Ns) {
+          const unsigned long long bits = in_regs ? rbits[k] : (unsigned long long)__double_as_longlong(w.dist[i]);
+          if ((bits & mask) == prefix) key = (unsigned int)((bits >> shift) & 255ull);
+        }
+        const unsigned peers = __match_any_sync(0xffffffffu, key);
+        if (key < 256u && (tid & 31) == __ffs(peers) - 1) atomicAdd(&hist[key], (unsigned int)__popc(peers));
+      }
+      for (int base = REG_PER * STEP_THREADS; base < Ns; base += STEP_THREADS) {     // Ns > 8192 only
+        const int i = base + tid;
+        unsigned int key = 256u;
         if (i < Ns) {
           const unsigned long long bits = (unsigned long long)__double_as_longlong(w.dist[i]);
           if ((bits & mask) == prefix) key = (unsigned int)((bits >> shift) & 255ull);
@@ -376,11 +609,28 @@ extern "C" int foho_icp_run(const double *source, int32_t Ns, const double *targ
   cudaStream_t st = (cudaStream_t)cuda_stream;
   k_icp_init<<<1, 32, 0, st>>>(w);
   FOHO_LAUNCH_CHECK();
+  // small targets: the tiled brute-force scan; otherwise the box hierarchy over the (static) target
+  const bool tree = Nt >= 1024 && n_iter > 1;
+  if (tree) {
+    k_icp_tbox<<<1, 1024, 0, st>>>(target, Nt, w);
+    int gx = (w.P2 + 255) / 256;
+    if (gx > 512) gx = 512;
+    k_icp_tkeys<<<gx, 256, 0, st>>>(target, Nt, w);
+    FOHO_LAUNCH_CHECK();
+    int rc = foho_sort_u64(w.keys, w.P2, 1, st);
+    if (rc != FOHO_OK) return rc;
+    k_icp_tgather<<<gx, 256, 0, st>>>(target, Nt, Ns, w);
+    k_icp_tboxes<<<(w.NG + 7) / 8, 256, 0, st>>>(Nt, 0, w);
+    k_icp_tboxes<<<(w.NS + 7) / 8, 256, 0, st>>>(Nt, 1, w);
+    FOHO_LAUNCH_CHECK();
+  }
   const dim3 nn_grid((Ns + NN_THREADS - 1) / NN_THREADS, w.nchunks);
   for (int it = 0; it < n_iter; ++it) {
-    k_icp_nn<<<nn_grid, NN_THREADS, 0, st>>>(source, Ns, target, Nt, w);
+    int *nn_last = it == n_iter - 1 ? nn_index_last : nullptr;
+    if (tree) k_icp_nn_tree<<<(Ns + 7) / 8, 256, 0, st>>>(source, Ns, Nt, w, nn_last);
+    else k_icp_nn<<<nn_grid, NN_THREADS, 0, st>>>(source, Ns, target, Nt, w);
     k_icp_step<<<1, STEP_THREADS, 0, st>>>(target, Ns, n_outliers, fixed_scale, min_scale, max_scale, w, cost_history,
-                                           it == n_iter - 1 ? nn_index_last : nullptr);
+                                           tree ? nullptr : nn_last, tree ? 0 : 1);
   }
   FOHO_LAUNCH_CHECK();
   k_icp_finish<<<1, 32, 0, st>>>(w, transform_out, cost_out);
