@@ -265,7 +265,7 @@ int foho_func_attrs(const void *func, int id, size_t smem, bool max_carveout);
 // kernels implemented in the other translation units
 // shared_sm: the sparse kernels run beside the stream (it then leaves them shared memory)
 int foho_launch_stream(const foho_guidance_desc *d, const FohoWorkspace &ws, int *grid_x_out, bool shared_sm, cudaStream_t st);
-// explicit object-mesh terms (guidance_objmesh.cu): `pre` runs before k_finalize (it adds the contact
+// explicit object-mesh terms (guidance_objmesh.cu): `pre` runs before k_finalize_verts (it adds the contact
 // gradient to G_hm), `post` after it (it adds to grad_theta[8..15] and the terms).
 int foho_launch_objmesh_pre(const foho_guidance_desc *d, const FohoWorkspace &ws, cudaStream_t st);
 int foho_launch_objmesh_post(const foho_guidance_desc *d, const FohoWorkspace &ws, cudaStream_t st);

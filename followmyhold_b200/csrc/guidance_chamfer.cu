@@ -119,7 +119,8 @@ __global__ void __launch_bounds__(ACC_THREADS) k_accel_hand(const float *__restr
 // ----------------------------------------------------------------------------- build: face order
 // Faces in Morton order of their REST centroid (one CTA per sample, bitonic sort in shared memory):
 // any 32 consecutive faces are then a compact patch of the hand, in every pose (the pose is a
-// similarity), which is what k_voxdist_tree's two-level sphere culling needs.
+// similarity), and face structures keyed by this order stay valid for every evaluation (k_raster writes the posed
+// bounding spheres in this order, k_voxdist_staged reads the vertex ids in it).
 __global__ void __launch_bounds__(ACC_THREADS) k_accel_faces(const float *__restrict__ hand_rest, const int *__restrict__ faces,
                                                              int Vh, int Fh, FohoAccel acc) {
   __shared__ unsigned long long key[FOHO_ACCEL_FACES];

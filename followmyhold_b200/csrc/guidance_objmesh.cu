@@ -17,7 +17,7 @@
 //   k_obj_prep   one CTA per sample: T_h2m, bbox centre (+arg indices), similarity, zeroing
 //   k_obj_knn    brute-force 1-NN hand -> object vertices, object tiles in shared memory
 //   k_obj_terms  contact / vertex / edge terms and dE/d(ot)
-//   k_obj_chain  (after k_finalize) dE/d(ot) -> object leaves + grad_obj_verts, loss assembly
+//   k_obj_chain  (after k_assemble) dE/d(ot) -> object leaves + grad_obj_verts, loss assembly
 #include "foho_common.cuh"
 
 namespace {
@@ -262,7 +262,7 @@ __global__ void __launch_bounds__(OBJ_PREP_THREADS) k_obj_chain(foho_guidance_de
     const float L_edge = ne > 0 ? ac[ACC_EDGE] / (float)ne : 0.f;
     Tm[FOHO_T_DIST] = L_dist; Tm[FOHO_T_VREG] = L_vreg; Tm[FOHO_T_EDGE] = L_edge; Tm[FOHO_T_MEAN_D2] = mean_d2;
     float total = Tm[FOHO_T_TOTAL] + W.w_dist * L_dist + W.w_vreg * L_vreg + W.w_edge * L_edge;
-    // pipelines.py:1561-1564 (k_finalize used w_int_lo)
+    // pipelines.py:1561-1564 (k_assemble used w_int_lo)
     if (n > 0 && mean_d2 < 0.001f && d.late_step) total += (W.w_int_hi - W.w_int_lo) * Tm[FOHO_T_COUNT];
     Tm[FOHO_T_TOTAL] = total;
   }

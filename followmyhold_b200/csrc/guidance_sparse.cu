@@ -1,12 +1,16 @@
 // Sparse part of the guidance evaluation: everything that is not the dense volume stream.
 //
-//   k_prep      a5/a6  leaves -> frames, transformed hand verts (MoGe + lattice), bbox, zeroing
-//   k_raster    a8     +z ray-parity voxelisation of the hand on the lattice (sign rule)
-//   k_compact   a9     voxels inside hand & object -> candidate list (= the REF count)
-//   k_voxdist   a14    exact point->mesh distance for the candidates, L_int and its gradients
-//   k_chamfer   a15    brute-force 1-NN both ways between hand verts and the MoGe cloud
-//   k_finalize  a13/a11/a10/a12  trilinear vertex samples, key-points, chain rule to the
-//                      16 leaves, loss assembly
+//   k_prep            a5/a6  leaves -> frames, transformed hand verts (MoGe + lattice), bbox, zeroing
+//   k_raster          a8     +z ray-parity voxelisation of the hand on the lattice (sign rule); face spheres
+//   k_compact         a9     voxels inside hand & object -> candidate list (= the REF count)
+//   k_voxdist         a14    exact point->mesh distance for the candidates (flat sweep; the staged search of
+//                            guidance_voxdist.cu is used when the per-image face order exists)
+//   k_chamfer         a15    brute-force 1-NN both ways between hand verts and the MoGe cloud (no accel buffer;
+//                            the structured searches live in guidance_chamfer.cu)
+//   k_keypoints       a11    key-point regression, projection, MSE and its gradient
+//   k_vertex_early    a13    trilinear vertex samples, penalties, corner lists, key-point back-projection
+//   k_finalize_verts  a12    chain rule from the per-vertex gradients to 26 moments of the 16 leaves
+//   k_assemble        a10/a12  deferred dE/dS scatter; stream moments + vertex sums -> leaf gradients, loss terms
 //
 // Reference seams: third_party_patches/hy3dgen/shapegen/pipelines.py:108-118 (a6),
 // :121-135 (a11), :231-239 (a9), :242-250 (a5), :1480-1600 (inner iteration);
@@ -427,7 +431,7 @@ __global__ void __launch_bounds__(CH_THREADS) k_chamfer(foho_guidance_desc d, Fo
   }
 }
 
-// ----------------------------------------------------------------------------- k_finalize
+// ----------------------------------------------------------------------------- key-points, vertex passes, assembly
 constexpr int FIN_THREADS = 512;
 constexpr int FIN_NRED = FOHO_FIN_NRED;
 __constant__ int c_tips[5] = {744, 320, 443, 554, 671};                          // pipelines.py:127
@@ -941,7 +945,7 @@ extern "C" int foho_guidance_energy_fwd_bwd(const foho_guidance_desc *dp, void *
   // Stream layout.  overlap: the dense stream depends on nothing but the inputs, so it starts at once
   // on the caller's stream while k_prep and the sparse chains run on three library-owned side streams:
   //   caller : fork ------------------ k_stream --------------------------------- wait(A) k_assemble [obj post]
-  //   side A : wait(fork) k_prep rec(P) k_chamfer_c2h      wait(B) wait(C) [obj pre] k_finalize_verts rec(A)
+  //   side A : wait(fork) k_prep rec(P) k_chamfer_c2h*     wait(B) wait(C) [obj pre] k_finalize_verts rec(A)
   //   side B :                  wait(P) k_raster k_compact k_voxdist rec(B)
   //   side C :                  wait(P) k_keypoints k_chamfer_h2c rec(C)
   // Only event record / wait is used, so the same sequence is legal inside a stream capture.

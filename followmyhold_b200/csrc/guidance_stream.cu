@@ -6,7 +6,7 @@
 // third_party_patches/hy3dgen/shapegen/pipelines.py:1570) contributes
 //     G[g] = -(w_mom/N) * |y(g)|^2,   |y|^2 = kappa^2 |g|^2 + 2 e.g + f,
 // and the kernel accumulates the moments  M0 = sum w, M1 = sum w g, M2 = sum w |g|^2,
-// w = relu(-S), plus the interior count; k_finalize turns them into the energy and the
+// w = relu(-S); k_assemble turns them into the energy and the
 // object-leaf gradients.  The sparse terms (hand voxels, vertex samples) are added to G
 // afterwards by their own small kernels.
 //

@@ -304,7 +304,8 @@ def test_object_mesh_empty_sample_and_switch():
 def test_structured_chamfer_equals_brute_force_and_scipy(P, case):
     """NS a15 both ways: the grid / box-hierarchy searches return the same nearest neighbours as the
     brute-force kernel and as scipy's cKDTree (the NN oracle the reference's ICP uses), including a hand
-    far outside the cloud's bbox (ring search gives up -> exhaustive scan) and a zero-extent cloud."""
+    far outside the cloud's bbox (every box is "near", the hierarchy degenerates to a full scan) and a
+    zero-extent cloud."""
     from scipy.spatial import cKDTree
     from followmyhold_b200 import _lib
     from followmyhold_b200.guidance.engine import GuidanceEngine
