@@ -11,10 +11,13 @@
  *   - every pointer marked "device" is CUDA device memory owned by the caller;
  *   - functions enqueue work on the given stream and return without synchronising
  *     (except the *_host variants, which are synchronous by definition);
- *   - no allocation: the caller passes a workspace sized by the matching
- *     *_workspace_bytes() query;
+ *   - no device allocation: the caller passes a workspace sized by the matching
+ *     *_workspace_bytes() query.  The only resources the library creates are host side: per device and
+ *     lane, three CUDA streams and five events for the fork/join of foho_guidance_energy_fwd_bwd,
+ *     created on its first call (make that call outside a stream capture);
  *   - return value: 0 ok, <0 invalid argument (FOHO_E_*), >0 a cudaError_t value;
- *   - thread-safe for distinct (stream, workspace) pairs.
+ *   - thread-safe for distinct (stream, workspace) pairs; calls that share a lane's side streams
+ *     are serialised by an internal mutex while they enqueue.
  *   - there is NO CPU fallback: every compute entry point needs a CUDA device.
  */
 #ifndef FOHO_B200_H
