@@ -77,7 +77,8 @@ def _oracle_schedule(sample, sdf0, tap, alpha, cfg, outputs, x_t, theta0, dt=tor
     return torch.cat(leaves), v, x_t
 
 
-def test_full_schedule_matches_oracle_schedule():
+@pytest.mark.parametrize("micro_batches", [1, 2])
+def test_full_schedule_matches_oracle_schedule(micro_batches):
     from followmyhold_b200.guidance.config import OptimizationConfig
     from followmyhold_b200.guidance.loop import GuidanceLoop
     B, D, P, L = 2, 32, 512, 1024
@@ -90,7 +91,7 @@ def test_full_schedule_matches_oracle_schedule():
     outputs = [0.1 * torch.randn(B, L, generator=g) for _ in range(cfg.num_inference_steps)]
     res = {}
     for use_graphs in (False, True):
-        lp = GuidanceLoop(B, D, st, P, config=cfg, latent_elems=L, seed=4)
+        lp = GuidanceLoop(B, D, st, P, config=cfg, latent_elems=L, seed=4, micro_batches=micro_batches)
         lp.sdf0.copy_(sdf0); lp.sdf.copy_(sdf0); lp.x_t.copy_(x_t); lp.theta.copy_(theta0)
         assert [lp.phase_of_step(i) for i in range(6)] == [0, 0, 1, 1.5, 2, 2]
         lp.run_schedule_device([o.cuda() for o in outputs], use_graphs=use_graphs)
