@@ -336,7 +336,8 @@ class GuidanceLoop:
         """Guided-denoise steps for a sequence of image batches whose inputs live in pinned HOST memory
         (``batches``: iterable of ``(sdf0, x_t, velocity, theta)`` CPU tensors, each a different batch of
         B images -- the way a rank works through its share of ``sorted(images)[rank::world]``; ``sdf0``
-        may be ``None`` when the batch's decoder base volume is already on the device).
+        may be ``None`` when the batch's decoder base volume is already on the device, or float16 -- the
+        decoder's own output dtype -- in which case it is widened on the device).
 
         Three streams: the upload of batch k+1 into a staging set overlaps the graph replay of batch k,
         whose results leave through a second staging set while batch k+1 computes.  Every byte still
@@ -377,7 +378,14 @@ class GuidanceLoop:
                 cs.wait_event(self._ev_stage_free[k & 1])
                 with torch.cuda.stream(cs):
                     if sdf0_h is not None:          # None: the decoder state of this batch is already resident
-                        st["sdf0"].copy_(sdf0_h, non_blocking=True)
+                        if sdf0_h.dtype == torch.float16:
+                            # the decoder's native output (fp16 logits, widened by `.float()` at pipelines.py:309):
+                            # half the bytes on the wire, widened on the device
+                            if "sdf0_h16" not in st:
+                                st["sdf0_h16"] = torch.empty(self.sdf0.shape, dtype=torch.float16, device=dev)
+                            st["sdf0_h16"].copy_(sdf0_h, non_blocking=True)
+                        else:
+                            st["sdf0"].copy_(sdf0_h, non_blocking=True)
                     st["x_t"].copy_(x_t_h, non_blocking=True)
                     st["velocity"].copy_(vel_h, non_blocking=True)
                     st["theta"].copy_(theta_h, non_blocking=True)
@@ -386,7 +394,7 @@ class GuidanceLoop:
                 s.wait_event(h2d_done)
                 with torch.cuda.stream(s):
                     if sdf0_h is not None:
-                        self.sdf0.copy_(st["sdf0"])
+                        self.sdf0.copy_(st["sdf0_h16"] if sdf0_h.dtype == torch.float16 else st["sdf0"])
                     self.sdf.copy_(self.sdf0)
                     self.x_t.copy_(st["x_t"]); self.velocity.copy_(st["velocity"]); self.theta.copy_(st["theta"])
                     self._ev_stage_free[k & 1].record(s)

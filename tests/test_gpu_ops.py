@@ -138,6 +138,16 @@ def test_pipelined_host_api_matches_single_batch_calls():
         for n in ("theta", "velocity", "prev_sample", "terms"):
             assert torch.allclose(piped[k][n], single[k][n], rtol=1e-4, atol=1e-6), (k, n)
     assert not torch.allclose(piped[0]["velocity"], piped[1]["velocity"])
+    # volumes handed over as fp16 (the decoder's output dtype) are widened on the device: same results as
+    # the fp32 call on the fp16-rounded values; a None volume keeps the resident one
+    h16 = sdf0.cpu().half().pin_memory()
+    rounded = h16.float().pin_memory()
+    a = lp.denoise_steps_host(12, [(h16,) + batches[0][1:]])[0]
+    a = {n: t.clone() for n, t in a.items()}
+    b = lp.denoise_steps_host(12, [(rounded,) + batches[0][1:], (None,) + batches[0][1:]])
+    for n in ("theta", "velocity", "prev_sample", "terms"):
+        assert torch.allclose(a[n], b[0][n], rtol=1e-4, atol=1e-6), n
+        assert torch.allclose(b[0][n], b[1][n], rtol=1e-4, atol=1e-6), n
 
 
 @pytest.mark.parametrize("m", [2, 4])
