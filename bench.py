@@ -381,7 +381,11 @@ def run_ours(args):
         if world == 1 and not args.no_cpu:
             os.sched_setaffinity(0, orig_affinity)      # the CPU leg gets every host core back
             eps, cores, n, el = cpu_guidance_evals_per_sec(args.cpu_seconds)
+            eps1, _, n1, el1 = cpu_guidance_evals_per_sec(min(8.0, args.cpu_seconds), threads=1, n_min=1)
             line["cpu_baseline"] = {"value": eps / EVALS_PER_STEP, "unit": UNIT, "cores": cores, "kind": "port",
+                                    "one_thread": {"value": eps1 / EVALS_PER_STEP, "unit": UNIT, "cores": 1,
+                                                   "sample": f"{n1} evaluations in {el1:.1f}s; the reference pins its CPU "
+                                                             "stages to one thread (src/foho/main.py:65-68)"},
                                     "sample": f"{n} oracle guidance evaluations (fwd+bwd+AdamW) of ONE image of the "
                                               f"workload in {el:.1f}s; value = evals/s / {EVALS_PER_STEP}",
                                     "evals_per_sec": eps}
