@@ -117,7 +117,31 @@ def test_edge_cases_match_oracle(case):
         _close(f"{case} grad_sdf[{b}]", gs[b].cpu().numpy(), ogs.numpy())
 
 
-@pytest.mark.parametrize("B,D,P", [(1, 65, 262144), (1, 385, 65536), (3, 128, 200000)])
+def test_config1_anchor_matches_oracle():
+    """BASELINE.json configs[0] -- one 128^3 volume, P = 16 384, seed 2 -- the shape the oracle alone runs
+    on the CPU: the prepared (structured, overlapped) path against it, warm-started second evaluation."""
+    from followmyhold_b200.guidance.engine import GuidanceEngine
+    D, P = 128, 16384
+    s = make_guidance_sample(D, P, 2)
+    sdf, theta, st = stack_samples([s], cap=True)
+    eng = GuidanceEngine(1, D, 778, st.hand_faces.shape[0], P)
+    eng.prepare(st)
+    for _ in range(2):
+        terms, gs, gt = eng.energy_fwd_bwd(sdf, theta, st)
+    torch.cuda.synchronize()
+    s.hand_faces = st.hand_faces.cpu()
+    out, ogs, ogt = _oracle(s, hand_grid=eng.hand_grid.cpu().numpy()[0])
+    t = terms.cpu().numpy()[0]
+    assert int(t[14]) == int(round(float(out["count"]) * 1000)) and t[15] == 0
+    for n, i in {"L_pen": 1, "L_con": 2, "L_int": 3, "L_mom": 5, "L_ch": 6, "L_kp": 7, "L_treg_h": 8, "L_treg_o": 9}.items():
+        ref = float(out[n].detach())
+        assert abs(t[i] - ref) <= REL * abs(ref) + 1e-9, (n, t[i], ref)
+    assert abs(t[0] - float(out["total"].detach())) <= REL * abs(float(out["total"].detach()))
+    _close("config1 grad_theta", gt.cpu().numpy()[0], ogt.numpy())
+    _close("config1 grad_sdf", gs.cpu().numpy()[0], ogs.numpy())
+
+
+@pytest.mark.parametrize("B,D,P", [(1, 65, 262144), (1, 385, 65536), (3, 128, 200000), (8, 256, 65536)])
 def test_large_shapes_structured_equals_brute_force(B, D, P):
     """Sizes the CPU oracle cannot reach in seconds: the reference's 65^3 grid with the largest cloud
     (512^2 crop), its 385^3 export grid (10^4 candidate voxels), a ragged 200 000-point cloud.  The
