@@ -2,9 +2,8 @@
 
 Same ``run(...)`` signature, CLI flags, file naming and ICP hyper-parameters as the
 reference stage ``src/foho/alignment/h2m.py:12-72``; the ICP loop runs on the GPU
-(``mesh_align.align_meshes_impl``).  ``mesh.glb`` targets are skipped with a message: the
-alignment path reads PLY/OBJ only (the default MoGe stage writes ``pointcloud.ply``,
-src/foho/geometry/moge.py:211-213).
+(``mesh_align.align_meshes_impl``).  Targets are looked up in the reference's order: ``mesh.ply``,
+``pointcloud.ply``, ``mesh.glb`` (h2m.py:23-31).
 """
 from __future__ import annotations
 
@@ -29,9 +28,13 @@ def run(hunyuan_mesh_dir: str, moge_out_dir: str, h2m_rt_dir: str, seed: int = 0
         moge_dir = os.path.join(moge_out_dir, f"{i}_cropped_hoi")
         target_mesh = os.path.join(moge_dir, "mesh.ply")
         if not os.path.isfile(target_mesh):
+            # MoGe typically writes pointcloud.ply and/or mesh.glb (h2m.py:25-31).
             pointcloud_mesh = os.path.join(moge_dir, "pointcloud.ply")
+            glb_mesh = os.path.join(moge_dir, "mesh.glb")
             if os.path.isfile(pointcloud_mesh):
                 target_mesh = pointcloud_mesh
+            elif os.path.isfile(glb_mesh):
+                target_mesh = glb_mesh
             else:
                 print(f"No MoGe mesh found for {i} in {moge_dir}. Skipping.")
                 continue

@@ -13,9 +13,8 @@ is no fallback.  ``MockGuidanceModel`` (synthetic volumes, the linear tap decode
 ``foho_mock_decoder_*``) exists for tests and synthetic runs.
 
 Differences a maintainer should know:
-  * the MoGe geometry is read from ``{i}_cropped_hoi/pointcloud.ply`` (or ``mesh.ply``): the guidance
-    energy consumes it as a point cloud; ``mesh.glb`` (which the reference renders, run.py:215) is not
-    read;
+  * the MoGe geometry ``{i}_cropped_hoi/mesh.glb`` (run.py:215; else ``pointcloud.ply`` / ``mesh.ply``)
+    is consumed as a point cloud -- its vertices -- where the reference renders it;
   * images are processed ``batch_size`` at a time; under ``torchrun`` rank r takes
     ``sorted(images)[r::world]`` (or chunk r of ``task_list_file``, like ``SLURM_ARRAY_TASK_ID``);
   * mesh post-processing (``FloaterRemover`` ... run.py:158-161) is left to the model's
@@ -129,12 +128,12 @@ def load_image_inputs(p: dict, n_cloud: int, rng: np.random.Generator) -> dict:
     T = np.load(p["T_h2m_path"]).astype(np.float64).reshape(4, 4)                  # :1240
     hand_moge = mano.vertices.astype(np.float64) @ T[:3, :3].T + T[:3, 3]          # :1241 transform_hunyuan2moge
     cloud_path = None
-    for name in ("pointcloud.ply", "mesh.ply"):
+    for name in ("mesh.glb", "pointcloud.ply", "mesh.ply"):       # mesh.glb is what the reference loads (run.py:215)
         if os.path.isfile(os.path.join(p["moge_dir"], name)):
             cloud_path = os.path.join(p["moge_dir"], name)
             break
     if cloud_path is None:
-        raise FileNotFoundError(f"no MoGe geometry (pointcloud.ply / mesh.ply) in {p['moge_dir']}")
+        raise FileNotFoundError(f"no MoGe geometry (mesh.glb / pointcloud.ply / mesh.ply) in {p['moge_dir']}")
     pts = np.asarray(load(cloud_path).vertices, dtype=np.float64)
     if pts.shape[0] >= n_cloud:
         pts = pts[rng.choice(pts.shape[0], n_cloud, replace=False)]

@@ -1,6 +1,6 @@
 """Dependency-free readers / writers for the files the stages exchange:
-PLY (ascii + binary little/big endian; meshes and face-less point clouds), OBJ, and the
-``.npy`` 4x4 transforms.  Stands in for ``trimesh.load(process=False)`` /
+PLY (ascii + binary little/big endian; meshes and face-less point clouds), OBJ, binary glTF
+(geometry of ``mesh.glb``), and the ``.npy`` 4x4 transforms.  Stands in for ``trimesh.load(process=False)`` /
 ``mesh.export`` as used by the reference's src/foho/alignment/mesh_align.py:186-187,214.
 """
 from __future__ import annotations
@@ -185,14 +185,116 @@ def _read_obj(path: str) -> Geometry:
     return TriMesh(v, np.asarray(fs, dtype=np.int64))
 
 
+_GLTF_DTYPES = {5120: "i1", 5121: "u1", 5122: "<i2", 5123: "<u2", 5125: "<u4", 5126: "<f4"}
+_GLTF_NCOMP = {"SCALAR": 1, "VEC2": 2, "VEC3": 3, "VEC4": 4, "MAT2": 4, "MAT3": 9, "MAT4": 16}
+
+
+def _read_glb(path: str) -> Geometry:
+    """Binary glTF 2.0 (what MoGe's ``save_glb`` writes as ``mesh.glb``, src/foho/geometry/moge.py:159-160;
+    the reference reads it with trimesh / pytorch3d's MeshGlbFormat, alignment/h2m.py:27-31,
+    pipelines.py:1247-1250): every triangle primitive of the default scene, node transforms applied,
+    concatenated into one mesh (like ``trimesh.Scene.dump(concatenate=True)``).  Geometry only: positions
+    and indices; normals, colours, textures are skipped."""
+    import json
+    import struct
+    with open(path, "rb") as f:
+        data = f.read()
+    if len(data) < 20 or data[:4] != b"glTF":
+        raise ValueError(f"{path}: not a binary glTF file")
+    version, length = struct.unpack_from("<II", data, 4)
+    if version != 2:
+        raise ValueError(f"{path}: glTF version {version} is not supported")
+    off, gltf, blob = 12, None, b""
+    while off + 8 <= min(length, len(data)):
+        clen, ctype = struct.unpack_from("<II", data, off)
+        chunk = data[off + 8: off + 8 + clen]
+        if ctype == 0x4E4F534A:
+            gltf = json.loads(chunk.decode("utf-8"))
+        elif ctype == 0x004E4942 and not blob:
+            blob = chunk
+        off += 8 + clen + (-clen) % 4
+    if gltf is None:
+        raise ValueError(f"{path}: no JSON chunk")
+
+    def accessor(i: int) -> np.ndarray:
+        a = gltf["accessors"][i]
+        ncomp, dt = _GLTF_NCOMP[a["type"]], np.dtype(_GLTF_DTYPES[a["componentType"]])
+        count = int(a["count"])
+        if "bufferView" not in a:
+            return np.zeros((count, ncomp), dtype=dt)
+        bv = gltf["bufferViews"][a["bufferView"]]
+        if bv.get("buffer", 0) != 0:
+            raise ValueError(f"{path}: external buffers are not supported")
+        start = int(bv.get("byteOffset", 0)) + int(a.get("byteOffset", 0))
+        stride = int(bv.get("byteStride", 0)) or ncomp * dt.itemsize
+        raw = np.frombuffer(blob, dtype=np.uint8, count=(count - 1) * stride + ncomp * dt.itemsize, offset=start) if count else np.zeros(0, np.uint8)
+        out = np.lib.stride_tricks.as_strided(raw, shape=(count, ncomp * dt.itemsize), strides=(stride, 1)) if count else raw.reshape(0, ncomp * dt.itemsize)
+        return np.ascontiguousarray(out).view(dt).reshape(count, ncomp)
+
+    def node_matrix(n: dict) -> np.ndarray:
+        if "matrix" in n:
+            return np.asarray(n["matrix"], dtype=np.float64).reshape(4, 4).T          # column-major
+        M = np.eye(4)
+        if "scale" in n:
+            M = np.diag(list(n["scale"]) + [1.0]) @ M
+        if "rotation" in n:                                                             # xyzw
+            x, y, z, w = [float(c) for c in n["rotation"]]
+            R = np.array([[1 - 2 * (y * y + z * z), 2 * (x * y - z * w), 2 * (x * z + y * w)],
+                          [2 * (x * y + z * w), 1 - 2 * (x * x + z * z), 2 * (y * z - x * w)],
+                          [2 * (x * z - y * w), 2 * (y * z + x * w), 1 - 2 * (x * x + y * y)]])
+            Rm = np.eye(4); Rm[:3, :3] = R
+            M = Rm @ M
+        if "translation" in n:
+            Tm = np.eye(4); Tm[:3, 3] = n["translation"]
+            M = Tm @ M
+        return M
+
+    verts, faces, nv = [], [], 0
+    nodes = gltf.get("nodes", [])
+    scenes = gltf.get("scenes", [])
+    roots = scenes[gltf.get("scene", 0)].get("nodes", []) if scenes else list(range(len(nodes)))
+    stack = [(r, np.eye(4)) for r in roots]
+    if not nodes:                                    # no scene graph: take the meshes as they are
+        stack = []
+        for m in gltf.get("meshes", []):
+            nodes.append({"mesh": gltf["meshes"].index(m)})
+            stack.append((len(nodes) - 1, np.eye(4)))
+    while stack:
+        i, parent = stack.pop()
+        n = nodes[i]
+        M = parent @ node_matrix(n)
+        stack.extend((c, M) for c in n.get("children", []))
+        if "mesh" not in n:
+            continue
+        for prim in gltf["meshes"][n["mesh"]].get("primitives", []):
+            if "POSITION" not in prim.get("attributes", {}):
+                continue
+            v = transform_points(accessor(prim["attributes"]["POSITION"]).astype(np.float64), M)
+            mode = prim.get("mode", 4)
+            if mode == 4:
+                idx = accessor(prim["indices"]).astype(np.int64).reshape(-1) if "indices" in prim else np.arange(len(v))
+                faces.append(idx[: len(idx) // 3 * 3].reshape(-1, 3) + nv)
+            elif mode != 0:
+                raise ValueError(f"{path}: primitive mode {mode} is not supported (triangles and points only)")
+            verts.append(v)
+            nv += len(v)
+    if not verts:
+        raise ValueError(f"{path}: no geometry")
+    V = np.concatenate(verts, 0)
+    F = np.concatenate(faces, 0) if faces else np.zeros((0, 3), dtype=np.int64)
+    return TriMesh(V, F) if len(F) else PointCloud(V)
+
+
 def load(path: str) -> Geometry:
-    """``trimesh.load(path, process=False)`` for the formats the alignment stages see."""
+    """``trimesh.load(path, process=False)`` for the formats the stages exchange."""
     ext = os.path.splitext(path)[1].lower()
     if ext == ".ply":
         return _read_ply(path)
     if ext == ".obj":
         return _read_obj(path)
-    raise ValueError(f"unsupported mesh format '{ext}' ({path}); GLB targets are not handled by the alignment path")
+    if ext == ".glb":
+        return _read_glb(path)
+    raise ValueError(f"unsupported mesh format '{ext}' ({path})")
 
 
 def write_ply(path: str, vertices: np.ndarray, faces: Optional[np.ndarray] = None, double: bool = False) -> None:

@@ -190,3 +190,64 @@ def test_delaunay_graph_makes_greedy_descent_exact():
     # degenerate input (all points in a plane): no graph, the caller keeps the box search
     flat = s.hand_rest.clone(); flat[:, 2] = 0.0
     assert delaunay_neighbours(flat[None]) is None
+
+
+def _write_glb(path, prims, nodes):
+    """Minimal binary glTF 2.0 writer for the reader's test: prims = [(verts, indices or None, index dtype)]."""
+    import json
+    import struct
+    blob, views, accs, meshes = b"", [], [], []
+    for v, idx, dt in prims:
+        v = np.asarray(v, "<f4")
+        views.append({"buffer": 0, "byteOffset": len(blob), "byteLength": v.nbytes})
+        blob += v.tobytes() + b"\0" * ((-v.nbytes) % 4)
+        accs.append({"bufferView": len(views) - 1, "componentType": 5126, "count": len(v), "type": "VEC3"})
+        prim = {"attributes": {"POSITION": len(accs) - 1}}
+        if idx is not None:
+            a = np.asarray(idx, dt).reshape(-1)
+            views.append({"buffer": 0, "byteOffset": len(blob), "byteLength": a.nbytes})
+            blob += a.tobytes() + b"\0" * ((-a.nbytes) % 4)
+            accs.append({"bufferView": len(views) - 1, "componentType": {"u1": 5121, "<u2": 5123, "<u4": 5125}[dt],
+                         "count": int(a.size), "type": "SCALAR"})
+            prim["indices"] = len(accs) - 1
+        else:
+            prim["mode"] = 0
+        meshes.append({"primitives": [prim]})
+    g = {"asset": {"version": "2.0"}, "scene": 0, "scenes": [{"nodes": [0]}], "nodes": nodes, "meshes": meshes,
+         "accessors": accs, "bufferViews": views, "buffers": [{"byteLength": len(blob)}]}
+    js = json.dumps(g).encode()
+    js += b" " * ((-len(js)) % 4)
+    with open(path, "wb") as f:
+        f.write(b"glTF" + struct.pack("<II", 2, 28 + len(js) + len(blob)) + struct.pack("<II", len(js), 0x4E4F534A) + js
+                + struct.pack("<II", len(blob), 0x004E4942) + blob)
+
+
+def test_glb_reader_geometry_and_node_transforms(tmp_path):
+    """``mesh.glb`` (MoGe's output, which the reference loads at guidance/run.py:215 and alignment/h2m.py:27-31):
+    positions + indices of every triangle primitive, scene-graph transforms applied, concatenated."""
+    rng = np.random.default_rng(0)
+    v0, f0 = rng.normal(size=(5, 3)), [[0, 1, 2], [2, 3, 4]]
+    v1, f1 = rng.normal(size=(4, 3)), [[0, 1, 2], [1, 2, 3]]
+    nodes = [{"children": [1, 2], "translation": [1.0, 2.0, 3.0]}, {"mesh": 0},
+             {"mesh": 1, "scale": [2, 2, 2], "rotation": [0, 0, 0.7071067811865476, 0.7071067811865476]}]   # 90 deg about z
+    _write_glb(str(tmp_path / "mesh.glb"), [(v0, f0, "<u2"), (v1, f1, "<u4")], nodes)
+    m = meshio.load(str(tmp_path / "mesh.glb"))
+    assert isinstance(m, meshio.TriMesh) and m.vertices.shape == (9, 3) and m.faces.shape == (4, 3)
+    Rz = np.array([[0, -1, 0], [1, 0, 0], [0, 0, 1.0]])
+    want = np.concatenate([v0.astype("f4") + [1, 2, 3], (2 * v1.astype("f4")) @ Rz.T + [1, 2, 3]])
+    got_tris = np.sort(np.round(m.vertices[m.faces].reshape(4, -1), 5), axis=0)
+    want_tris = np.sort(np.round(np.concatenate([want[:5][np.array(f0)], want[5:][np.array(f1)]]).reshape(4, -1), 5), axis=0)
+    assert np.allclose(got_tris, want_tris, atol=1e-5)
+    # points only -> PointCloud; byte indices; garbage -> ValueError
+    _write_glb(str(tmp_path / "p.glb"), [(v0, None, None)], [{"mesh": 0}])
+    pc = meshio.load(str(tmp_path / "p.glb"))
+    assert isinstance(pc, meshio.PointCloud) and np.allclose(pc.vertices, v0.astype("f4"), atol=1e-6)
+    _write_glb(str(tmp_path / "b.glb"), [(v1, f1, "u1")], [{"mesh": 0}])
+    assert meshio.load(str(tmp_path / "b.glb")).faces.tolist() == f1
+    (tmp_path / "bad.glb").write_bytes(b"not a gltf file at all.....")
+    with pytest.raises(ValueError):
+        meshio.load(str(tmp_path / "bad.glb"))
+    # the guidance stage prefers mesh.glb, like the reference
+    from followmyhold_b200.guidance import run as R
+    src = inspect_source = __import__("inspect").getsource(R.load_image_inputs)
+    assert src.index('"mesh.glb"') < src.index('"pointcloud.ply"')
