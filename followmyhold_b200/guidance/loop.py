@@ -1,11 +1,14 @@
-"""Guided-denoise loop over a batch of images: the phase-2 hot loop of the reference
-(third_party_patches/hy3dgen/shapegen/pipelines.py:1455-1612) driven through the C-ABI.
+"""Guided-denoise loop over a batch of images: the optimisation-in-the-loop part of the reference's
+``__call__`` (third_party_patches/hy3dgen/shapegen/pipelines.py:1262-1612: plain steps, the hand-only,
+object-only and joint phases) driven through the C-ABI.
 
 One *guided-denoise step* = ``optimization_steps_joint`` (50) guidance evaluations
 [decode -> energy fwd+bwd -> decoder adjoint -> fused AdamW + step_final] followed by one
 ``scheduler.step``.  The whole step is captured once into a CUDA graph and
 replayed, so the inner loop has no host round trips at all (the reference syncs several
-times per iteration).
+times per iteration).  ``micro_batches`` > 1 advances groups of images as
+independent lanes inside that graph; ``run_schedule_device`` runs the whole schedule;
+``denoise_steps_host`` is the pinned-host-buffer API with upload / compute / download pipelined.
 
 The VAE decoder (``latent2sdf``) is not built yet; a fixed sparse
 linear decoder stands in for it (``foho_mock_decoder_*``) so latents, velocity and the
