@@ -29,7 +29,7 @@ TERM_NAMES = ["total", "pen", "con", "int", "count", "mom", "ch", "kp", "treg_h"
 # every symbol include/foho_b200.h declares (tests/test_capi_symbols.py checks both directions)
 EXPORTED_SYMBOLS = [
     "foho_abi_version", "foho_status_string", "foho_default_weights",
-    "foho_guidance_workspace_bytes", "foho_guidance_energy_fwd_bwd", "foho_guidance_update",
+    "foho_guidance_workspace_bytes", "foho_guidance_energy_fwd_bwd", "foho_guidance_update", "foho_guidance_update_f16",
     "foho_guidance_accel_bytes", "foho_guidance_prepare_statics",
     "foho_scheduler_step", "foho_scheduler_step_f16", "foho_mock_decoder_forward", "foho_mock_decoder_backward",
     "foho_icp_workspace_bytes", "foho_icp_run",
@@ -165,6 +165,8 @@ def load(build_if_missing: bool = False) -> C.CDLL:
     lib.foho_guidance_prepare_statics.argtypes = [C.POINTER(GuidanceDesc), C.c_void_p]
     lib.foho_guidance_update.restype = C.c_int
     lib.foho_guidance_update.argtypes = [C.POINTER(UpdateDesc), C.c_void_p]
+    lib.foho_guidance_update_f16.restype = C.c_int
+    lib.foho_guidance_update_f16.argtypes = [C.POINTER(UpdateDesc), C.c_void_p]
     lib.foho_scheduler_step.restype = C.c_int
     lib.foho_scheduler_step.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_float,
                                         C.c_float, C.c_void_p]

@@ -13,40 +13,28 @@
 // HBM-bound elementwise stream: 5 reads + 4 writes of 4 B per velocity element.
 #include "foho_common.cuh"
 #include <cuda_fp16.h>
-#include <math.h>
+#include "foho_adamw.cuh"
 
 namespace {
 
-struct AdamScalars {
-  float b1, b2, one_m_b1, one_m_b2, eps, inv_bc2_sqrt;
-};
+using AdamScalars = foho_adam_scalars_t;
 
-__device__ __forceinline__ void adamw_one(float &p, float g, float &m, float &v, float decay, float step_size,
-                                          const AdamScalars &s) {
-  p = p * decay;
-  m = m + (g - m) * s.one_m_b1;                 // torch lerp_ (weight < 0.5 branch)
-  v = v * s.b2 + s.one_m_b2 * g * g;            // mul_(b2).addcmul_(g, g, 1-b2)
-  float denom = sqrtf(v) * s.inv_bc2_sqrt + s.eps;
-  p = p - step_size * (m / denom);
+// the 16 scalar leaves are float32 in every variant (pipelines.py:1208-1215): one thread per float
+__device__ __forceinline__ void update_scalar_leaves(const foho_update_desc &d, const AdamScalars &s, int b, int k) {
+  const int grp = k < 8 ? (k == 0 ? 0 : (k < 4 ? 1 : 2)) : (k == 8 ? 3 : (k < 12 ? 4 : 5));
+  if ((d.theta_mask >> grp) & 1u) {
+    const size_t o = (size_t)b * 16 + k;
+    float p = d.theta[o], m = d.theta_m[o], v = d.theta_v[o];
+    foho_adamw_one<false>(p, d.grad_theta[o], m, v, s.decay_theta[grp], s.neg_step_theta[grp], s);
+    d.theta[o] = p; d.theta_m[o] = m; d.theta_v[o] = v;
+  }
 }
 
-__global__ void __launch_bounds__(256) k_update(foho_update_desc d, AdamScalars s, float bc1) {
+__global__ void __launch_bounds__(256) k_update(foho_update_desc d, AdamScalars s) {
   const int b = blockIdx.y;
-  // scalar leaves: one thread per float, first CTA of each sample
-  if (blockIdx.x == 0 && threadIdx.x < 16) {
-    const int k = threadIdx.x;
-    const int grp = k < 8 ? (k == 0 ? 0 : (k < 4 ? 1 : 2)) : (k == 8 ? 3 : (k < 12 ? 4 : 5));
-    if ((d.theta_mask >> grp) & 1u) {
-      const float lr = d.lr_theta[grp];
-      const size_t o = (size_t)b * 16 + k;
-      float p = d.theta[o], m = d.theta_m[o], v = d.theta_v[o];
-      adamw_one(p, d.grad_theta[o], m, v, 1.f - lr * d.weight_decay, lr / bc1, s);
-      d.theta[o] = p; d.theta_m[o] = m; d.theta_v[o] = v;
-    }
-  }
+  if (blockIdx.x == 0 && threadIdx.x < 16) update_scalar_leaves(d, s, b, threadIdx.x);
   if (!d.velocity) return;
-  const float lr = d.lr_velocity;
-  const float decay = 1.f - lr * d.weight_decay, step_size = lr / bc1;
+  const float decay = s.decay_vel, neg_step = s.neg_step_vel;
   const float oms = 1.f - d.sigma;
   const size_t base = (size_t)b * d.L;
   const int L4 = d.L >> 2;
@@ -58,16 +46,69 @@ __global__ void __launch_bounds__(256) k_update(foho_update_desc d, AdamScalars 
   float4 *O4 = d.x1 ? reinterpret_cast<float4 *>(d.x1 + base) : nullptr;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < L4; i += gridDim.x * blockDim.x) {
     float4 p = P4[i], g = G4[i], m = M4[i], v = V4[i];
-    adamw_one(p.x, g.x, m.x, v.x, decay, step_size, s);
-    adamw_one(p.y, g.y, m.y, v.y, decay, step_size, s);
-    adamw_one(p.z, g.z, m.z, v.z, decay, step_size, s);
-    adamw_one(p.w, g.w, m.w, v.w, decay, step_size, s);
+    foho_adamw_one<false>(p.x, g.x, m.x, v.x, decay, neg_step, s);
+    foho_adamw_one<false>(p.y, g.y, m.y, v.y, decay, neg_step, s);
+    foho_adamw_one<false>(p.z, g.z, m.z, v.z, decay, neg_step, s);
+    foho_adamw_one<false>(p.w, g.w, m.w, v.w, decay, neg_step, s);
     P4[i] = p; M4[i] = m; V4[i] = v;
     if (X4 && O4) {
       float4 x = X4[i];
       // separately rounded product and sum, like torch's `sample + (1 - sigma) * model_output` (schedulers.py:481)
-      O4[i] = make_float4(__fadd_rn(x.x, __fmul_rn(oms, p.x)), __fadd_rn(x.y, __fmul_rn(oms, p.y)),
-                          __fadd_rn(x.z, __fmul_rn(oms, p.z)), __fadd_rn(x.w, __fmul_rn(oms, p.w)));
+      O4[i] = make_float4(foho_step_final_one<false>(x.x, p.x, oms), foho_step_final_one<false>(x.y, p.y, oms),
+                          foho_step_final_one<false>(x.z, p.z, oms), foho_step_final_one<false>(x.w, p.w, oms));
+    }
+  }
+}
+
+// fp16 velocity / latents (the reference's dtype: the leaf is a clone of the DiT's half output,
+// code_utils.py:43-78; latents pipelines.py:1204).  torch's AdamW on a half parameter keeps the moments in
+// half and rounds after EVERY elementwise op (each op computes in float and stores half) -- adamw_one<true>.
+// 8 halves (16 B) per thread and access; L is a multiple of 8 (checked by the launcher).
+struct __align__(16) Half8 { __half2 a, b, c, d; };
+
+__device__ __forceinline__ void unpack8(const Half8 &h, float (&f)[8]) {
+  float2 t;
+  t = __half22float2(h.a); f[0] = t.x; f[1] = t.y;
+  t = __half22float2(h.b); f[2] = t.x; f[3] = t.y;
+  t = __half22float2(h.c); f[4] = t.x; f[5] = t.y;
+  t = __half22float2(h.d); f[6] = t.x; f[7] = t.y;
+}
+__device__ __forceinline__ Half8 pack8(const float (&f)[8]) {
+  Half8 h;
+  h.a = __floats2half2_rn(f[0], f[1]); h.b = __floats2half2_rn(f[2], f[3]);
+  h.c = __floats2half2_rn(f[4], f[5]); h.d = __floats2half2_rn(f[6], f[7]);
+  return h;
+}
+
+__global__ void __launch_bounds__(256) k_update_f16(foho_update_desc d, AdamScalars s) {
+  const int b = blockIdx.y;
+  if (blockIdx.x == 0 && threadIdx.x < 16) update_scalar_leaves(d, s, b, threadIdx.x);
+  if (!d.velocity) return;
+  const float decay = s.decay_vel, neg_step = s.neg_step_vel;
+  // `(1 - sigma) * model_output`: the 0-dim fp32 factor is cast to half, the product is rounded to half,
+  // the sum with the fp32 sample is taken in fp32 and cast back (schedulers.py:470-484; same rule as
+  // k_sched_step_f16, which is pinned bit for bit by the reference scheduler's golden vectors)
+  const float oms = 1.f - d.sigma;
+  const size_t base = (size_t)b * d.L;
+  const int L8 = d.L >> 3;
+  Half8 *P8 = reinterpret_cast<Half8 *>(reinterpret_cast<__half *>(d.velocity) + base);
+  const Half8 *G8 = reinterpret_cast<const Half8 *>(reinterpret_cast<const __half *>(d.grad_velocity) + base);
+  Half8 *M8 = reinterpret_cast<Half8 *>(reinterpret_cast<__half *>(d.vel_m) + base);
+  Half8 *V8 = reinterpret_cast<Half8 *>(reinterpret_cast<__half *>(d.vel_v) + base);
+  const Half8 *X8 = d.x_t ? reinterpret_cast<const Half8 *>(reinterpret_cast<const __half *>(d.x_t) + base) : nullptr;
+  Half8 *O8 = d.x1 ? reinterpret_cast<Half8 *>(reinterpret_cast<__half *>(d.x1) + base) : nullptr;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < L8; i += gridDim.x * blockDim.x) {
+    float p[8], g[8], m[8], v[8];
+    unpack8(P8[i], p); unpack8(G8[i], g); unpack8(M8[i], m); unpack8(V8[i], v);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) foho_adamw_one<true>(p[j], g[j], m[j], v[j], decay, neg_step, s);
+    P8[i] = pack8(p); M8[i] = pack8(m); V8[i] = pack8(v);
+    if (X8 && O8) {
+      float x[8];
+      unpack8(X8[i], x);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) x[j] = foho_step_final_one<true>(x[j], p[j], oms);
+      O8[i] = pack8(x);
     }
   }
 }
@@ -136,31 +177,47 @@ extern "C" int foho_mock_decoder_backward(const float *grad_sdf, const int64_t *
   return FOHO_OK;
 }
 
-extern "C" int foho_guidance_update(const foho_update_desc *dp, void *cuda_stream) {
-  if (!dp) return FOHO_E_NULL;
-  const foho_update_desc &d = *dp;
+static int update_checks(const foho_update_desc &d, int vec, int align) {
   if (!d.theta || !d.grad_theta || !d.theta_m || !d.theta_v) return FOHO_E_NULL;
   if (d.velocity && (!d.grad_velocity || !d.vel_m || !d.vel_v)) return FOHO_E_NULL;
   if (d.B < 1 || d.step < 1 || (d.velocity && d.L < 1)) return FOHO_E_SHAPE;
-  if (d.velocity && (d.L & 3) != 0) return FOHO_E_SHAPE;   // float4 stream
+  if (d.velocity && (d.L % vec) != 0) return FOHO_E_SHAPE;   // 16-byte vector stream
   if (d.velocity && (((uintptr_t)d.velocity | (uintptr_t)d.grad_velocity | (uintptr_t)d.vel_m | (uintptr_t)d.vel_v |
-                      (uintptr_t)d.x_t | (uintptr_t)d.x1) & 15) != 0)
+                      (uintptr_t)d.x_t | (uintptr_t)d.x1) & (uintptr_t)(align - 1)) != 0)
     return FOHO_E_ARG;
-  AdamScalars s;
-  s.b1 = d.beta1; s.b2 = d.beta2;
-  s.one_m_b1 = 1.f - d.beta1; s.one_m_b2 = 1.f - d.beta2;
-  s.eps = d.eps;
-  // torch computes the bias corrections in double (python floats)
-  const double bc1 = 1.0 - pow((double)d.beta1, (double)d.step);
-  const double bc2 = 1.0 - pow((double)d.beta2, (double)d.step);
-  s.inv_bc2_sqrt = (float)(1.0 / sqrt(bc2));
+  return FOHO_OK;
+}
+
+static AdamScalars adam_scalars(const foho_update_desc &d) {
+  return foho_adam_scalars(d.beta1, d.beta2, d.eps, d.weight_decay, d.lr_theta, d.lr_velocity, d.step);
+}
+
+extern "C" int foho_guidance_update(const foho_update_desc *dp, void *cuda_stream) {
+  if (!dp) return FOHO_E_NULL;
+  const foho_update_desc &d = *dp;
+  if (int rc = update_checks(d, 4, 16)) return rc;
   int gx = 1;
   if (d.velocity) {
     gx = (d.L / 4 + 255) / 256;
     if (gx > 592) gx = 592;
     if (gx < 1) gx = 1;
   }
-  k_update<<<dim3(gx, d.B), 256, 0, (cudaStream_t)cuda_stream>>>(d, s, (float)bc1);
+  k_update<<<dim3(gx, d.B), 256, 0, (cudaStream_t)cuda_stream>>>(d, adam_scalars(d));
+  FOHO_LAUNCH_CHECK();
+  return FOHO_OK;
+}
+
+extern "C" int foho_guidance_update_f16(const foho_update_desc *dp, void *cuda_stream) {
+  if (!dp) return FOHO_E_NULL;
+  const foho_update_desc &d = *dp;
+  if (int rc = update_checks(d, 8, 16)) return rc;
+  int gx = 1;
+  if (d.velocity) {
+    gx = (d.L / 8 + 255) / 256;
+    if (gx > 592) gx = 592;
+    if (gx < 1) gx = 1;
+  }
+  k_update_f16<<<dim3(gx, d.B), 256, 0, (cudaStream_t)cuda_stream>>>(d, adam_scalars(d));
   FOHO_LAUNCH_CHECK();
   return FOHO_OK;
 }

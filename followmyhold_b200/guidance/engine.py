@@ -289,18 +289,27 @@ class GuidanceOptimizer:
     Mirrors ``get_guidance_params`` (third_party/utilz/code_utils.py:3-83): state is
     created fresh for every outer denoise step, learning rates per group come from
     ``OptimizationConfig`` (src/foho/configs/guid_config.py:20-27).
+
+    ``velocity_dtype=torch.float16`` is the reference's configuration: the velocity leaf is a clone of the
+    DiT's half output (code_utils.py:43-78), so torch keeps its moments in half and rounds after every op;
+    velocity, its gradient, ``x_t`` and ``x1`` are then half tensors (``foho_guidance_update_f16``).  The 16
+    scalar leaves are float32 either way (pipelines.py:1208-1215).
     """
 
-    def __init__(self, B: int, L: int, device="cuda:0", config: Optional[OptimizationConfig] = None):
+    def __init__(self, B: int, L: int, device="cuda:0", config: Optional[OptimizationConfig] = None,
+                 velocity_dtype: torch.dtype = torch.float32):
+        if velocity_dtype not in (torch.float32, torch.float16):
+            raise ValueError("velocity_dtype must be torch.float32 or torch.float16")
         self.lib = _lib.load()
         self.B, self.L = B, L
         self.device = torch.device(device)
         self.config = config or OptimizationConfig()
+        self.velocity_dtype = velocity_dtype
         dev = self.device
         self.theta_m = torch.zeros(B, 16, device=dev)
         self.theta_v = torch.zeros(B, 16, device=dev)
-        self.vel_m = torch.zeros(B, L, device=dev) if L > 0 else None
-        self.vel_v = torch.zeros(B, L, device=dev) if L > 0 else None
+        self.vel_m = torch.zeros(B, L, device=dev, dtype=velocity_dtype) if L > 0 else None
+        self.vel_v = torch.zeros(B, L, device=dev, dtype=velocity_dtype) if L > 0 else None
         self.step_count = 0
         self.set_phase(2)
 
@@ -341,11 +350,18 @@ class GuidanceOptimizer:
         d.theta, d.grad_theta = theta.data_ptr(), grad_theta.data_ptr()
         d.theta_m, d.theta_v = self.theta_m.data_ptr(), self.theta_v.data_ptr()
         if velocity is not None and self.opt_velocity:
+            for name, t in (("velocity", velocity), ("grad_velocity", grad_velocity), ("x_t", x_t), ("x1", x1)):
+                if t is not None and t.dtype != self.velocity_dtype:
+                    raise ValueError(f"GuidanceOptimizer.step: {name} is {t.dtype}, optimiser state is {self.velocity_dtype}")
             d.velocity, d.grad_velocity = velocity.data_ptr(), grad_velocity.data_ptr()
             d.vel_m, d.vel_v = self.vel_m.data_ptr(), self.vel_v.data_ptr()
             d.x_t, d.x1 = _ptr(x_t), _ptr(x1)
         s = stream if stream is not None else torch.cuda.current_stream(self.device)
-        _lib.check("foho_guidance_update", self.lib.foho_guidance_update(C.byref(d), C.c_void_p(s.cuda_stream)))
+        if self.velocity_dtype == torch.float16:
+            _lib.check("foho_guidance_update_f16",
+                       self.lib.foho_guidance_update_f16(C.byref(d), C.c_void_p(s.cuda_stream)))
+        else:
+            _lib.check("foho_guidance_update", self.lib.foho_guidance_update(C.byref(d), C.c_void_p(s.cuda_stream)))
 
 
 def scheduler_step(x_t: torch.Tensor, velocity: torch.Tensor, sigma: float, sigma_next: float):

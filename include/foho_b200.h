@@ -199,6 +199,13 @@ typedef struct foho_update_desc {
 } foho_update_desc;
 int foho_guidance_update(const foho_update_desc *desc, void *cuda_stream);
 
+/* Same update with the velocity / latent arrays in fp16 -- the reference's dtype (the leaf is a clone of
+ * the DiT's half output, code_utils.py:43-78): `velocity`, `grad_velocity`, `vel_m`, `vel_v`, `x_t`, `x1`
+ * of the descriptor then point to __half [B,L]; the 16 scalar leaves and their moments stay float32.
+ * Reproduces torch.optim.AdamW on a half parameter op by op (moments in half, a rounding after every
+ * elementwise op) and the half `step_final` (schedulers.py:470-484). */
+int foho_guidance_update_f16(const foho_update_desc *desc, void *cuda_stream);
+
 /* Replaces `scheduler.step(noise_pred_obj, t, obj_latents).prev_sample`
  * (schedulers.py:235-319, call site pipelines.py:1612): prev = x + (sigma_next-sigma) v. */
 int foho_scheduler_step(const float *x_t, const float *velocity, float *prev_sample, float *pred_x1,

@@ -491,3 +491,62 @@ def adamw_step(p, g, m, v, step: int, lr: float, beta1=0.9, beta2=0.999, eps=1e-
     denom = v.sqrt() / (bc2 ** 0.5) + eps
     p = p - (lr / bc1) * (m / denom)
     return p, m, v
+
+
+def _fma32(a, b, c):
+    """One correctly rounded float32 fused multiply-add (numpy has none): the product of two float32 is
+    exact in the 64-bit mantissa of x87 long double, so only the final rounding to float32 matters."""
+    ld = np.longdouble
+    return (np.asarray(a, np.float32).astype(ld) * np.asarray(b, np.float32).astype(ld)
+            + np.asarray(c, np.float32).astype(ld)).astype(np.float32)
+
+
+def adamw_step_torch_ops(p, g, m, v, step: int, lr: float, beta1=0.9, beta2=0.999, eps=1e-4, weight_decay=0.01,
+                         order: str = "cuda"):
+    """REF a4, rounding for rounding: one torch.optim.Adam/AdamW step on numpy float32 or float16 arrays as
+    the sequence of elementwise ops torch launches (torch/optim/adam.py; call sites pipelines.py:1318,
+    1384,1478), each op computed in float32 and rounded to the tensors' dtype -- for a half leaf (the
+    reference's velocity, code_utils.py:43-78) the moments are half and every op rounds to half:
+
+        p.mul_(1-lr*wd); m.lerp_(g, 1-b1); v.mul_(b2).addcmul_(g, g, 1-b2)
+        den = (v.sqrt() / bc2**0.5).add_(eps); p.addcdiv_(m, den, -lr/bc1)
+
+    ``order`` picks how torch's kernels group the three `a + s*x` ops:
+      "cuda": lerp = fma(w, g-m, m); addcmul = fma(s, g*g, v); addcdiv = fma(s, m/den, p)  (ATen CUDA
+              functors `a + alpha * (b * c)` / `a + alpha * (b / c)`, contracted by nvcc; the path the
+              reference runs, and the one the kernels follow),
+      "cpu":  lerp = fma(w, g-m, m); addcmul = fma(s*g, g, v); addcdiv = p + (s*m)/den  (ATen CPU kernels
+              `self + alpha * t1 * t2`, `self + alpha * t1 / t2`) -- pinned bit for bit by torch.optim on
+              CPU in tests/test_oracle_update.py.
+    Scalars are python doubles cast to float32, as torch passes them.  Returns (p, m, v) in the input dtype."""
+    dt = np.asarray(p).dtype
+    assert dt in (np.float32, np.float16)
+    f32 = np.float32
+    R = (lambda x: x.astype(f32)) if dt == np.float32 else (lambda x: x.astype(np.float16).astype(f32))
+    p, g, m, v = (np.asarray(a).astype(f32) for a in (p, g, m, v))
+    w1, w2, b2 = f32(1 - beta1), f32(1 - beta2), f32(beta2)
+    bc1 = 1 - beta1 ** step
+    bc2_sqrt = f32((1 - beta2 ** step) ** 0.5)
+    neg_step = f32((lr / bc1) * -1)
+    p = R(p * f32(1 - lr * weight_decay))
+    m = R(_fma32(w1, g - m, m))
+    v = R(v * b2)
+    v = R(_fma32(w2, g * g, v)) if order == "cuda" else R(_fma32(w2 * g, g, v))
+    den = R(np.sqrt(v))
+    den = R(den / bc2_sqrt)
+    den = R(den + f32(eps))
+    p = R(_fma32(neg_step, m / den, p)) if order == "cuda" else R(p + (neg_step * m) / den)
+    return p.astype(dt), m.astype(dt), v.astype(dt)
+
+
+def step_final_torch_ops(x_t, v, sigma: float):
+    """REF a2 ``step_final`` on numpy float32 / float16 arrays with torch's rounding (schedulers.py:470-484):
+    float32: separately rounded product and sum; float16: the fp32 0-dim factor is cast to half, the product
+    rounded to half, the sum with the upcast sample taken in fp32 and cast back to half."""
+    dt = np.asarray(v).dtype
+    f32 = np.float32
+    oms = f32(1.0) - f32(sigma)
+    if dt == np.float32:
+        return (x_t.astype(f32) + oms * v.astype(f32)).astype(f32)
+    prod = (oms.astype(np.float16).astype(f32) * v.astype(f32)).astype(np.float16).astype(f32)
+    return (x_t.astype(f32) + prod).astype(np.float16)

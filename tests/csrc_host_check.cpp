@@ -2,6 +2,7 @@
 // the CPU test-suite can check the exact arithmetic the kernels use (no GPU on the build box).
 // TEST INFRASTRUCTURE ONLY -- never linked into libfoho_b200.so.
 #include "../followmyhold_b200/csrc/foho_math.cuh"
+#include "../followmyhold_b200/csrc/foho_adamw.cuh"
 #include <string.h>
 
 extern "C" {
@@ -48,5 +49,34 @@ void host_kabsch(const double *H9, double *R9) {
   kabsch_rotation(H, R);
   for (int i = 0; i < 9; ++i) R9[i] = R[i / 3][i % 3];
 }
+
+// fused AdamW / step_final arithmetic of k_update / k_update_f16 (foho_adamw.cuh), one tensor of n elements
+// with learning rate `lr`; half tensors travel as their 16-bit patterns
+static float h2f(uint16_t b) { _Float16 h; memcpy(&h, &b, 2); return (float)h; }
+static uint16_t f2h(float f) { _Float16 h = (_Float16)f; uint16_t b; memcpy(&b, &h, 2); return b; }
+
+void host_adamw_f32(float *p, const float *g, float *m, float *v, long n, float beta1, float beta2, float eps,
+                    float weight_decay, float lr, int step, const float *x_t, float *x1, float sigma) {
+  float lrs[6] = {lr, lr, lr, lr, lr, lr};
+  foho_adam_scalars_t s = foho_adam_scalars(beta1, beta2, eps, weight_decay, lrs, lr, step);
+  for (long i = 0; i < n; ++i) {
+    foho_adamw_one<false>(p[i], g[i], m[i], v[i], s.decay_vel, s.neg_step_vel, s);
+    if (x_t && x1) x1[i] = foho_step_final_one<false>(x_t[i], p[i], 1.f - sigma);
+  }
+}
+
+void host_adamw_f16(uint16_t *p, const uint16_t *g, uint16_t *m, uint16_t *v, long n, float beta1, float beta2,
+                    float eps, float weight_decay, float lr, int step, const uint16_t *x_t, uint16_t *x1, float sigma) {
+  float lrs[6] = {lr, lr, lr, lr, lr, lr};
+  foho_adam_scalars_t s = foho_adam_scalars(beta1, beta2, eps, weight_decay, lrs, lr, step);
+  for (long i = 0; i < n; ++i) {
+    float pf = h2f(p[i]), mf = h2f(m[i]), vf = h2f(v[i]);
+    foho_adamw_one<true>(pf, h2f(g[i]), mf, vf, s.decay_vel, s.neg_step_vel, s);
+    p[i] = f2h(pf); m[i] = f2h(mf); v[i] = f2h(vf);
+    if (x_t && x1) x1[i] = f2h(foho_step_final_one<true>(h2f(x_t[i]), pf, 1.f - sigma));
+  }
+}
+
+double host_as_written(float f) { return foho_as_written(f); }
 
 }  // extern "C"

@@ -87,6 +87,81 @@ def test_fused_update_matches_torch_adamw_and_step_final():
     assert torch.allclose(prev.cpu(), rp, atol=1e-6) and torch.allclose(px1.cpu(), rx, atol=1e-6)
 
 
+@pytest.mark.parametrize("dtype", [torch.float16, torch.float32])
+@pytest.mark.parametrize("phase", [2, 1.5])
+def test_fused_update_bit_equal_to_oracle_and_torch_cuda_optimiser(dtype, phase):
+    """k_update / k_update_f16 against (1) the op-exact oracle in ATen's CUDA grouping: every bit of the
+    parameters, both moments and the fused step_final output, for float32 and for the reference's half
+    velocity leaf (code_utils.py:43-78); (2) torch.optim.AdamW stepping CUDA parameters -- the optimiser
+    object the reference constructs (pipelines.py:1384,1478), multi-tensor path."""
+    from followmyhold_b200.guidance.engine import GROUPS, GuidanceOptimizer
+    from oracle import guidance_oracle as O
+    B, L, steps, sigma = 2, 8192, 6, 0.4375
+    dev = "cuda:0"
+    g = torch.Generator().manual_seed(11)
+    theta = torch.randn(B, 16, generator=g).to(dev)
+    v = (0.5 * torch.randn(B, L, generator=g)).to(dtype).to(dev)
+    x_t = torch.randn(B, L, generator=g).to(dtype).to(dev)
+    x1 = torch.empty_like(v)
+    opt = GuidanceOptimizer(B, L, device=dev, velocity_dtype=dtype)
+    opt.set_phase(phase); opt.reset()
+    grp_of = [0, 1, 1, 1, 2, 2, 2, 2, 3, 4, 4, 4, 5, 5, 5, 5]
+    active = [k for k in range(16) if (opt.mask >> grp_of[k]) & 1]
+    # oracle state
+    npdt = np.float16 if dtype == torch.float16 else np.float32
+    ov = v.cpu().numpy().copy(); om = np.zeros_like(ov); ovv = np.zeros_like(ov)
+    oth = theta.cpu().numpy().copy(); otm = np.zeros_like(oth); otv = np.zeros_like(oth)
+    # torch's own optimiser on CUDA parameters, grouped like get_guidance_params (code_utils.py:57-78)
+    tp = [theta[:, k:k + 1].clone().requires_grad_(True) for k in range(16)]
+    tv = v.clone().requires_grad_(True)
+    topt = torch.optim.AdamW([{"params": [tp[k]], "lr": opt.lr_theta[grp_of[k]]} for k in active] +
+                             [{"params": [tv], "lr": opt.lr_velocity}], eps=1e-4)
+    for k in range(steps):
+        gt = torch.randn(B, 16, generator=g).to(dev)
+        gv = (torch.randn(B, L, generator=g) * (0.05 if k % 2 else 2.0)).to(dtype).to(dev)
+        opt.step(theta, gt, v, gv, x_t, x1, sigma=sigma)
+        for j in active:
+            tp[j].grad = gt[:, j:j + 1].clone()
+        tv.grad = gv.clone()
+        topt.step()
+        ov, om, ovv = O.adamw_step_torch_ops(ov, gv.cpu().numpy(), om, ovv, k + 1, opt.lr_velocity, order="cuda")
+        for j in active:
+            oth[:, j], otm[:, j], otv[:, j] = O.adamw_step_torch_ops(
+                oth[:, j], gt[:, j].cpu().numpy(), otm[:, j], otv[:, j], k + 1, opt.lr_theta[grp_of[j]], order="cuda")
+        torch.cuda.synchronize()
+        assert np.array_equal(v.cpu().numpy(), ov), f"velocity differs from the oracle at step {k + 1}"
+        assert np.array_equal(opt.vel_m.cpu().numpy(), om) and np.array_equal(opt.vel_v.cpu().numpy(), ovv)
+        assert np.array_equal(x1.cpu().numpy(), O.step_final_torch_ops(x_t.cpu().numpy(), ov, sigma))
+        assert np.array_equal(theta.cpu().numpy(), oth)
+        assert np.array_equal(opt.theta_m.cpu().numpy(), otm) and np.array_equal(opt.theta_v.cpu().numpy(), otv)
+    assert v.dtype == dtype and opt.vel_m.dtype == dtype and ov.dtype == npdt
+    # torch's CUDA optimiser: expected bit-equal; tolerate isolated last-bit differences (other torch builds
+    # may group an op differently), never more
+    ref_v = tv.detach()
+    ref_t = torch.cat([tp[j].detach() if j in active else theta[:, j:j + 1] for j in range(16)], 1)
+    frac = float((v != ref_v).float().mean())
+    ulp = float(torch.finfo(dtype).eps) * float(ref_v.abs().max())
+    print(f"AdamW vs torch CUDA optimiser [{dtype}, phase {phase}]: velocity mismatches {int((v != ref_v).sum())}/{v.numel()}, "
+          f"leaves {int((theta != ref_t).sum())}/{theta.numel()}")
+    assert frac < 2e-3 and float((v.float() - ref_v.float()).abs().max()) <= 2 * ulp
+    assert torch.allclose(theta, ref_t, rtol=2e-6, atol=1e-7)
+
+
+def test_fused_update_f16_rejects_misuse():
+    from followmyhold_b200 import _lib
+    from followmyhold_b200.guidance.engine import GuidanceOptimizer
+    opt = GuidanceOptimizer(1, 64, device="cuda:0", velocity_dtype=torch.float16)
+    th = torch.zeros(1, 16, device="cuda:0"); v32 = torch.zeros(1, 64, device="cuda:0")
+    with pytest.raises(ValueError):
+        opt.step(th, th.clone(), v32, v32.clone())                      # dtype mismatch caught on the host side
+    opt6 = GuidanceOptimizer(1, 60, device="cuda:0", velocity_dtype=torch.float16)    # L not a multiple of 8
+    v16 = torch.zeros(1, 60, device="cuda:0", dtype=torch.float16)
+    with pytest.raises(_lib.FohoStatusError):
+        opt6.step(th, th.clone(), v16, v16.clone())
+    with pytest.raises(ValueError):
+        GuidanceOptimizer(1, 64, device="cuda:0", velocity_dtype=torch.bfloat16)
+
+
 def test_graph_loop_matches_eager_and_host_api():
     from followmyhold_b200.guidance.config import OptimizationConfig
     from followmyhold_b200.guidance.loop import GuidanceLoop
