@@ -43,7 +43,10 @@ def test_fused_update_matches_reference_optimiser(phase, tag):
         gv = torch.from_numpy(G["opt_grads_vel"][k]).to(DEV)
         opt.step(theta, gt, vel, gv, x_t, x1, sigma=0.25)
         torch.cuda.synchronize()
-        assert torch.allclose(theta.cpu().view(-1), torch.from_numpy(G[f"opt_{tag}_theta"][k]), rtol=3e-6, atol=1e-8)
+        # the golden trajectories were produced by torch's CPU kernels; the CUDA kernels group addcmul / addcdiv
+        # the way ATen's CUDA functors do (oracle.adamw_step_torch_ops), so a step may differ by one ulp of its
+        # operands (lr 0.5 on a quaternion component near 0.5: 6e-8) even where the result cancels to ~1e-3
+        assert torch.allclose(theta.cpu().view(-1), torch.from_numpy(G[f"opt_{tag}_theta"][k]), rtol=3e-6, atol=1.2e-7)
         assert torch.allclose(vel.cpu(), torch.from_numpy(G[f"opt_{tag}_vel"][k]), rtol=3e-6, atol=1e-8)
         if phase != 1:
             assert torch.equal(x1, 0.75 * vel)              # x1 = x_t + (1-sigma) v with x_t = 0
