@@ -255,6 +255,18 @@ def run_ours(args):
     loop.denoise_steps_host(STEP_INDEX, [lat] * K2)
     barrier()
     e2e_lat_s = time.perf_counter() - t2
+    # same, with the volumes uploaded in the dtype the reference's decoder emits them (fp16 logits, widened by
+    # `.float()`, pipelines.py:303-309) and widened on the device: half the PCIe bytes.  No gain on one GPU (the
+    # path is not PCIe bound there); it matters once several GPUs share the host's PCIe fabric.
+    sdf0_h16 = torch.empty(sdf0.shape, dtype=torch.float16, pin_memory=True)
+    sdf0_h16.copy_(sdf0)
+    b16 = (sdf0_h16, x_t_h, vel_h, theta_h)
+    loop.denoise_steps_host(STEP_INDEX, [b16] * K2)
+    barrier()
+    t3 = time.perf_counter()
+    loop.denoise_steps_host(STEP_INDEX, [b16] * K2)
+    barrier()
+    e2e_h16_s = time.perf_counter() - t3
     # one batch alone (no overlap possible): the latency a single call sees
     t1 = time.perf_counter()
     loop.denoise_step_host(STEP_INDEX, sdf0_h, x_t_h, vel_h, theta_h)
@@ -330,10 +342,10 @@ def run_ours(args):
     eval_serial_ms = s0.elapsed_time(s1) / NREP
 
     # ---- max over ranks
-    t = torch.tensor([ms, e2e_s, stream_ms, eval_ms, e2e_lat_s], dtype=torch.float64, device=dev)
+    t = torch.tensor([ms, e2e_s, stream_ms, eval_ms, e2e_lat_s, e2e_h16_s], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms, e2e_s, stream_ms, eval_ms, e2e_lat_s = [float(x) for x in t.tolist()]
+    ms, e2e_s, stream_ms, eval_ms, e2e_lat_s, e2e_h16_s = [float(x) for x in t.tolist()]
 
     if rank == 0:
         value = world * B * K / (ms / 1e3)
@@ -363,7 +375,11 @@ def run_ours(args):
                     "volumes_resident": {"value": world * B * K2 / e2e_lat_s, "unit": UNIT,
                                          "h2d_bytes_per_step": 4 * (2 * B * loop.L + B * 16),
                                          "note": "decoder base volumes stay on the device; latents, model output "
-                                                 "and leaves cross PCIe every step"}},
+                                                 "and leaves cross PCIe every step"},
+                    "volumes_fp16": {"value": world * B * K2 / e2e_h16_s, "unit": UNIT,
+                                     "h2d_bytes_per_step": 2 * B * D ** 3 + 4 * (2 * B * loop.L + B * 16),
+                                     "note": "volumes cross PCIe as the fp16 the reference's decoder emits "
+                                             "(pipelines.py:303-309) and are widened on the device; compute is fp32"}},
             "gpu_launches": K * loop.launches_per_step(),
             "roofline": {"bound": "hbm", "kernel": "k_stream_tma" if args.variant in (0, 2) else "k_stream_ldg",
                          "achieved": achieved, "peak": peak, "peak_kind": f"{peak_kind} burst copy (kernel timed alone)",

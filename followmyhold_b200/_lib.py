@@ -22,7 +22,7 @@ NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", 
               "-Xcompiler", "-fPIC", "-Xcompiler", "-O3"]
 
 FOHO_NUM_TERMS = 16
-ABI_VERSION = 3
+ABI_VERSION = 4
 TERM_NAMES = ["total", "pen", "con", "int", "count", "mom", "ch", "kp", "treg_h", "treg_o", "dist", "vreg",
               "edge", "mean_d2", "ncand", "flags"]
 
@@ -125,6 +125,7 @@ class UpdateDesc(C.Structure):
         ("theta", C.c_void_p), ("grad_theta", C.c_void_p), ("theta_m", C.c_void_p), ("theta_v", C.c_void_p),
         ("velocity", C.c_void_p), ("grad_velocity", C.c_void_p), ("vel_m", C.c_void_p), ("vel_v", C.c_void_p),
         ("x_t", C.c_void_p), ("x1", C.c_void_p),
+        ("terms", C.c_void_p), ("nan_flag", C.c_void_p),
     ]
 
 

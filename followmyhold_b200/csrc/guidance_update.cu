@@ -30,8 +30,20 @@ __device__ __forceinline__ void update_scalar_leaves(const foho_update_desc &d, 
   }
 }
 
+// NaN guard (pipelines.py:1442-1444,1590-1592): true = this sample's inner loop has been left, nothing of
+// it is updated any more.  Every thread decides alike -- the flag only ever changes from 0 to non-zero, and
+// only in a launch whose total is NaN, where the second test alone already says "skip".
+__device__ __forceinline__ bool sample_halted(const foho_update_desc &d, int b) {
+  if (!d.terms || !d.nan_flag) return false;
+  const bool bad = isnan(d.terms[(size_t)b * FOHO_NUM_TERMS + FOHO_T_TOTAL]);
+  const int flag = d.nan_flag[b];
+  if (bad && flag == 0 && blockIdx.x == 0 && threadIdx.x == 0) d.nan_flag[b] = d.step;
+  return bad || flag != 0;
+}
+
 __global__ void __launch_bounds__(256) k_update(foho_update_desc d, AdamScalars s) {
   const int b = blockIdx.y;
+  if (sample_halted(d, b)) return;
   if (blockIdx.x == 0 && threadIdx.x < 16) update_scalar_leaves(d, s, b, threadIdx.x);
   if (!d.velocity) return;
   const float decay = s.decay_vel, neg_step = s.neg_step_vel;
@@ -82,6 +94,7 @@ __device__ __forceinline__ Half8 pack8(const float (&f)[8]) {
 
 __global__ void __launch_bounds__(256) k_update_f16(foho_update_desc d, AdamScalars s) {
   const int b = blockIdx.y;
+  if (sample_halted(d, b)) return;
   if (blockIdx.x == 0 && threadIdx.x < 16) update_scalar_leaves(d, s, b, threadIdx.x);
   if (!d.velocity) return;
   const float decay = s.decay_vel, neg_step = s.neg_step_vel;
@@ -180,6 +193,7 @@ extern "C" int foho_mock_decoder_backward(const float *grad_sdf, const int64_t *
 static int update_checks(const foho_update_desc &d, int vec, int align) {
   if (!d.theta || !d.grad_theta || !d.theta_m || !d.theta_v) return FOHO_E_NULL;
   if (d.velocity && (!d.grad_velocity || !d.vel_m || !d.vel_v)) return FOHO_E_NULL;
+  if ((d.terms == nullptr) != (d.nan_flag == nullptr)) return FOHO_E_NULL;      // the guard needs both
   if (d.B < 1 || d.step < 1 || (d.velocity && d.L < 1)) return FOHO_E_SHAPE;
   if (d.velocity && (d.L % vec) != 0) return FOHO_E_SHAPE;   // 16-byte vector stream
   if (d.velocity && (((uintptr_t)d.velocity | (uintptr_t)d.grad_velocity | (uintptr_t)d.vel_m | (uintptr_t)d.vel_v |

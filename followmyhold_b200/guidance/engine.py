@@ -339,7 +339,17 @@ class GuidanceOptimizer:
         self.step_count = 0
 
     def step(self, theta, grad_theta, velocity=None, grad_velocity=None, x_t=None, x1=None, sigma: float = 0.0,
-             stream: Optional[torch.cuda.Stream] = None) -> None:
+             stream: Optional[torch.cuda.Stream] = None, terms: Optional[torch.Tensor] = None,
+             nan_flag: Optional[torch.Tensor] = None) -> None:
+        """One fused optimiser step (+ ``step_final`` into ``x1``).  ``terms`` [B,16] float32 (the evaluation
+        just done) and ``nan_flag`` [B] int32 switch the reference's NaN guard on (pipelines.py:1442-1444,
+        1590-1592): once a sample's total is NaN it is left untouched and ``nan_flag`` holds the optimiser
+        step at which that happened -- decided on the device, no host sync."""
+        if (terms is None) != (nan_flag is None):
+            raise ValueError("GuidanceOptimizer.step: the NaN guard needs both `terms` and `nan_flag`")
+        if nan_flag is not None and (nan_flag.dtype != torch.int32 or terms.dtype != torch.float32
+                                     or not terms.is_contiguous() or terms.shape[-1] != _lib.FOHO_NUM_TERMS):
+            raise ValueError("GuidanceOptimizer.step: terms must be contiguous float32 [B,16], nan_flag int32 [B]")
         self.step_count += 1
         d = _lib.UpdateDesc()
         d.B, d.L, d.step = self.B, self.L, self.step_count
@@ -356,6 +366,7 @@ class GuidanceOptimizer:
             d.velocity, d.grad_velocity = velocity.data_ptr(), grad_velocity.data_ptr()
             d.vel_m, d.vel_v = self.vel_m.data_ptr(), self.vel_v.data_ptr()
             d.x_t, d.x1 = _ptr(x_t), _ptr(x1)
+        d.terms, d.nan_flag = _ptr(terms), _ptr(nan_flag)
         s = stream if stream is not None else torch.cuda.current_stream(self.device)
         if self.velocity_dtype == torch.float16:
             _lib.check("foho_guidance_update_f16",

@@ -57,8 +57,13 @@ class GuidanceLoop:
 
     def __init__(self, B: int, D: int, statics: GuidanceStatics, P: int, device="cuda:0",
                  config: Optional[OptimizationConfig] = None, weights=None, latent_elems: int = LATENT_SHAPE[0] * LATENT_SHAPE[1],
-                 decoder_alpha: float = 0.05, stream_variant: int = 0, seed: int = 0, micro_batches: int = 1):
-        """``micro_batches`` = m > 1 splits the B images into m groups that advance independently inside the
+                 decoder_alpha: float = 0.05, stream_variant: int = 0, seed: int = 0, micro_batches: int = 1,
+                 loss_log_every: int = 0):
+        """``loss_log_every`` = n > 0 keeps the loss terms of every n-th inner iteration of every step
+        (``loss_history``; the reference logs every 10th when ``FOHO_DEBUG_DIR`` is set, pipelines.py:1446-1450,
+        1594-1598) -- device-to-device copies inside the step graph, no host sync.
+
+        ``micro_batches`` = m > 1 splits the B images into m groups that advance independently inside the
         one captured graph (own engine, optimiser state, stream and library side-stream lane): while one
         group's evaluation is in its serial tail (assemble -> decoder adjoint -> update -> decoder forward)
         the other group's dense stream keeps the HBM busy.  Results are identical: images never interact."""
@@ -112,6 +117,16 @@ class GuidanceLoop:
         self.theta = torch.zeros(B, 16, dtype=f32, device=dev)
         self.reset_leaves()
         self.sigmas = set_timesteps_sigmas(self.cfg.num_inference_steps)
+        # NaN guard (pipelines.py:1442-1444,1590-1592), kept on the device: nan_flag[b] = inner iteration (1-based)
+        # at which image b's total became NaN in the current outer step, nan_steps[i] = that flag after step i
+        self.nan_flag = torch.zeros(B, dtype=torch.int32, device=dev)
+        self.nan_steps = torch.zeros(self.cfg.num_inference_steps, B, dtype=torch.int32, device=dev)
+        self.loss_log_every = int(loss_log_every)
+        self.loss_history: Optional[torch.Tensor] = None
+        if self.loss_log_every > 0:
+            kmax = max(self.cfg.optimization_steps_hand, self.cfg.optimization_steps_scale, self.cfg.optimization_steps_joint)
+            self.loss_history = torch.full((self.cfg.num_inference_steps, (kmax + self.loss_log_every - 1) // self.loss_log_every,
+                                            B, _lib.FOHO_NUM_TERMS), float("nan"), dtype=f32, device=dev)
         self._graph: Optional[torch.cuda.CUDAGraph] = None
         self._graph_key = None
         self._sched_graphs: Dict[tuple, torch.cuda.CUDAGraph] = {}
@@ -168,8 +183,10 @@ class GuidanceLoop:
         return self.engine.launches_per_eval + 3     # + decoder fwd, decoder adjoint, fused update
 
     # ------------------------------------------------------------------ one evaluation (enqueue only)
-    def _enqueue_eval(self, sigma: float, late_step: bool, s: torch.cuda.Stream, phase: float = 2, lane: Optional[_Lane] = None) -> None:
-        """One evaluation of one lane (default: lane 0) on stream ``s``."""
+    def _enqueue_eval(self, sigma: float, late_step: bool, s: torch.cuda.Stream, phase: float = 2, lane: Optional[_Lane] = None,
+                      log_slot: Optional[torch.Tensor] = None) -> None:
+        """One evaluation of one lane (default: lane 0) on stream ``s``.  ``log_slot`` [nb,16]: where to keep
+        this evaluation's loss terms (the values the reference prints before ``backward()``)."""
         ln = lane or self.lanes[0]
         lib, vol, off, nb = self.lib, self.D ** 3, ln.off, ln.nb
         sp = C.c_void_p(s.cuda_stream)
@@ -191,7 +208,15 @@ class GuidanceLoop:
             _lib.check("foho_mock_decoder_backward", lib.foho_mock_decoder_backward(
                 ln.engine.grad_sdf.data_ptr(), self.tap.data_ptr(), gvel.data_ptr(), nb, vol, self.L,
                 self.alpha * (1.0 - sigma), sp))
-        ln.opt.step(theta, ln.engine.grad_theta, vel, gvel, x_t, x1, sigma=sigma, stream=s)
+        if log_slot is not None:
+            with torch.cuda.stream(s):
+                log_slot.copy_(ln.engine.terms)
+        # NaN guard in every phase.  The reference tests the total in phases 1.5 and 2 only (:1442,1590); a NaN
+        # total in its hand phase turns the hand leaves into NaN, the renders of the next phase with them and the
+        # image ends at the `return None` of :1444 -- the same outcome as stopping the image here, but the
+        # leaves (and with them every coordinate the kernels loop over) stay finite
+        ln.opt.step(theta, ln.engine.grad_theta, vel, gvel, x_t, x1, sigma=sigma, stream=s,
+                    terms=ln.engine.terms, nan_flag=self.nan_flag.narrow(0, off, nb))
 
     def _enqueue_step(self, step_index: int, s: torch.cuda.Stream, phase: float = 2) -> None:
         """All kernels of one guided-denoise step (pipelines.py:1293-1612), no syncs.  ``phase``: 1 hand
@@ -215,12 +240,17 @@ class GuidanceLoop:
             with torch.cuda.stream(st):
                 ln.opt.set_phase(phase)
                 ln.opt.reset()                             # fresh optimiser state every outer step (:1318,1384,1478)
+                self.nan_flag.narrow(0, off, nb).zero_()   # the NaN `break` ends one outer step's inner loop only
                 # x1 for the first decode of this step: step_final with the incoming velocity (:1507)
                 _lib.check("foho_scheduler_step", self.lib.foho_scheduler_step(
                     x_t.data_ptr(), vel.data_ptr(), None, x1.data_ptr(), x_t.numel(), sigma, sigma_next,
                     C.c_void_p(st.cuda_stream)))
-                for _ in range(self.phase_iterations(phase)):
-                    self._enqueue_eval(sigma, late, st, phase, ln)
+                for k in range(self.phase_iterations(phase)):
+                    slot = None
+                    if self.loss_history is not None and k % self.loss_log_every == 0:
+                        slot = self.loss_history[step_index, k // self.loss_log_every].narrow(0, off, nb)
+                    self._enqueue_eval(sigma, late, st, phase, ln, slot)
+                self.nan_steps[step_index].narrow(0, off, nb).copy_(self.nan_flag.narrow(0, off, nb))
                 # obj_latents = scheduler.step(noise_pred_obj, t, obj_latents).prev_sample (:1612)
                 _lib.check("foho_scheduler_step", self.lib.foho_scheduler_step(
                     x_t.data_ptr(), vel.data_ptr(), prev.data_ptr(), None, x_t.numel(), sigma, sigma_next,
@@ -231,6 +261,44 @@ class GuidanceLoop:
     def launches_per_step(self) -> int:
         # per lane: 2 scheduler launches + the evaluations (opt.reset(): 4 memsets by torch, not counted)
         return self.micro_batches * (self.cfg.optimization_steps_joint * self.kernels_per_eval() + 2)
+
+    # ------------------------------------------------------------------ NaN guard, loss log (host side, after the run)
+    def nan_report(self) -> Dict[int, Dict[int, int]]:
+        """{denoise step: {image: inner iteration (0-based, like the reference's ``k``) whose total was NaN}}.
+        Synchronises; call it after the schedule."""
+        ns = self.nan_steps.cpu()
+        rep: Dict[int, Dict[int, int]] = {}
+        for i, b in ns.nonzero().tolist():
+            rep.setdefault(i, {})[b] = int(ns[i, b]) - 1
+        return rep
+
+    def failed_images(self) -> list:
+        """Images whose hand-only or object-only phase hit a NaN total: the reference's ``__call__`` returns
+        ``None`` for them (pipelines.py:1442-1444; a NaN hand phase gets there one step later) and the stage
+        reports the image as failed (run.py:257-259).  A NaN in the joint phase only ends that step's inner
+        loop (:1590-1592)."""
+        bad = set()
+        for i, imgs in self.nan_report().items():
+            if self.phase_of_step(i) in (1, 1.5):
+                bad.update(imgs)
+        return sorted(bad)
+
+    def loss_log_lines(self, image: int) -> list:
+        """The reference's ``losses.txt`` lines for one image ("Opt step k, ..." every ``loss_log_every``
+        iterations of every optimised step), with this path's term names."""
+        if self.loss_history is None:
+            return []
+        h = self.loss_history[:, :, image].cpu()
+        lines = []
+        for i in range(h.shape[0]):
+            phase = self.phase_of_step(i)
+            if phase == 0:
+                continue
+            for j in range((self.phase_iterations(phase) + self.loss_log_every - 1) // self.loss_log_every):
+                t = h[i, j]
+                body = ", ".join(f"{n}: {float(t[q])}" for q, n in enumerate(_lib.TERM_NAMES) if n and q < t.numel())
+                lines.append(f"Denoise step {i} phase {phase}, Opt step {j * self.loss_log_every}, {body}")
+        return lines
 
     # ------------------------------------------------------------------ graph
     def capture(self, step_index: int) -> None:

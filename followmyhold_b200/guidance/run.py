@@ -253,8 +253,9 @@ def _run_batch(chunk, model: GuidanceModel, J: torch.Tensor, config: Optimizatio
         fov_deg=inputs[0]["fovx"], image_hw=inputs[0]["hw"])
     model.begin_batch([p["index"] for p, _ in chunk], [p["cropped_obj_img_path"] for p, _ in chunk], dev)
     sdf0, tap, alpha = model.decoder_state()
+    debug_root = os.environ.get("FOHO_DEBUG_DIR")               # pipelines.py:1076-1091: debug dumps when set
     loop = GuidanceLoop(B, model.D, st, n_cloud, device=dev, config=config, latent_elems=model.latent_elems,
-                        decoder_alpha=float(alpha))
+                        decoder_alpha=float(alpha), loss_log_every=10 if debug_root else 0)
     loop.tap = tap.to(dev).to(torch.int64).contiguous()
     loop.sdf0.copy_(sdf0); loop.sdf.copy_(sdf0)
     gen = torch.Generator().manual_seed(seed)                   # run.py:120 torch.manual_seed(2)
@@ -271,7 +272,13 @@ def _run_batch(chunk, model: GuidanceModel, J: torch.Tensor, config: Optimizatio
     sdf = sdf.reshape(B, model.D, model.D, model.D).cpu().numpy()
     theta = loop.theta.cpu().numpy().astype(np.float64)
     torch.cuda.synchronize(dev)
+    nan_rep, failed = loop.nan_report(), set(loop.failed_images())
+    if debug_root:
+        _write_debug_dumps(debug_root, [p["index"] for p, _ in chunk], config, loop)
+    skip = report_nan_images([p["cropped_obj_img_path"] for p, _ in chunk], nan_rep, failed)
     for b, (p, inp) in enumerate(chunk):
+        if b in skip:
+            continue
         hand = inp["hand_moge"].astype(np.float64)
         ch = (hand.min(0) + hand.max(0)) / 2.0
         write_ply(p["save_path_hand"], similarity_about(hand, theta[b, :8], ch), inp["faces"])
@@ -282,6 +289,38 @@ def _run_batch(chunk, model: GuidanceModel, J: torch.Tensor, config: Optimizatio
         T = inp["T_h2m"].astype(np.float64)
         vm = verts.astype(np.float64) @ T[:3, :3].T + T[:3, 3]
         write_ply(p["save_path_obj"], similarity_about(vm, theta[b, 8:], T[:3, 3]), faces)
+
+
+def report_nan_images(image_paths: Sequence[str], nan_report: dict, failed) -> set:
+    """Messages of the reference for images whose loss became NaN: "Total loss is NaN" (pipelines.py:1443,1591),
+    and for those whose ``__call__`` returned ``None`` (:1442-1444) the per-image error of the stage -- unpacking
+    ``None`` raises inside its try block (run.py:141,257-259), the image is reported and nothing is written.
+    Returns the images to skip."""
+    skip = set()
+    for b, path in enumerate(image_paths):
+        if any(b in imgs for imgs in nan_report.values()):
+            print("Total loss is NaN")
+        if b in failed:
+            print(f"Error in processing {os.path.basename(path)} : cannot unpack non-iterable NoneType object")
+            skip.add(b)
+    return skip
+
+
+def _write_debug_dumps(debug_root: str, indices: Sequence[str], config: OptimizationConfig, loop) -> None:
+    """``FOHO_DEBUG_DIR`` dumps of the reference (pipelines.py:1076-1091,1145-1183,1446-1450,1594-1598): one
+    ``{timestamp}_exp_obj{index}_inpainted`` directory per image with ``params.json`` (the optimisation
+    configuration) and ``losses.txt`` (the loss terms of every 10th inner iteration)."""
+    import datetime
+    stamp = datetime.datetime.now().strftime("%Y%m%d_%H%M%S")
+    params = {k: v for k, v in vars(config).items() if isinstance(v, (int, float, bool, str, dict, list, tuple))}
+    for b, index in enumerate(indices):
+        save_dir = os.path.join(debug_root, f"{stamp}_exp_obj{index}_inpainted")
+        os.makedirs(save_dir, exist_ok=True)
+        with open(os.path.join(save_dir, "params.json"), "w") as f:
+            json.dump(params, f, indent=4)
+        with open(os.path.join(save_dir, "losses.txt"), "w") as f:
+            for line in loop.loss_log_lines(b):
+                f.write(line + "\n")
 
 
 # --------------------------------------------------------------------------- mock networks

@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define FOHO_ABI_VERSION 3
+#define FOHO_ABI_VERSION 4
 
 #define FOHO_OK 0
 #define FOHO_E_NULL (-1)      /* required pointer is NULL            */
@@ -196,6 +196,15 @@ typedef struct foho_update_desc {
   float *vel_m, *vel_v;      /* device [B,L]                                             */
   const float *x_t;          /* device [B,L] current latents (may be NULL)               */
   float *x1;                 /* device [B,L] OUT x_t + (1-sigma) v_new (may be NULL)     */
+  /* NaN guard of the inner loop, evaluated on the device (no host round trip).  The reference tests
+   * `torch.isnan(total_loss)` BEFORE `backward()` / `optimizer.step()` and leaves the inner loop
+   * (`break`, pipelines.py:1590-1592; `return None` in the object-only phase, :1442-1444).  With both
+   * pointers set, sample b is left untouched (leaves, moments, velocity, x1) by this and every later
+   * update of the outer step once `terms[b*FOHO_NUM_TERMS + FOHO_T_TOTAL]` is NaN; `nan_flag[b]`
+   * receives the 1-based optimiser step at which that first happened (0 = never; the caller zeroes
+   * it when a new outer step starts).  Both NULL: no guard.                                         */
+  const float *terms;        /* device [B,FOHO_NUM_TERMS] of the evaluation just done     */
+  int32_t *nan_flag;         /* device [B] in/out                                         */
 } foho_update_desc;
 int foho_guidance_update(const foho_update_desc *desc, void *cuda_stream);
 

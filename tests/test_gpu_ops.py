@@ -171,6 +171,60 @@ def test_fused_update_f16_rejects_misuse():
         GuidanceOptimizer(1, 64, device="cuda:0", velocity_dtype=torch.bfloat16)
 
 
+@pytest.mark.parametrize("dtype", [torch.float32, torch.float16])
+def test_update_nan_guard_leaves_the_sample_untouched(dtype):
+    """pipelines.py:1590-1592: `if torch.isnan(total_loss): break` comes before backward()/step().  On the device:
+    the sample whose total is NaN is not updated by this or any later step of the outer step, its flag holds the
+    optimiser step of the first NaN, the other samples advance exactly as without the guard."""
+    from followmyhold_b200 import _lib
+    from followmyhold_b200.guidance.engine import GuidanceOptimizer
+    B, L, dev = 3, 1024, "cuda:0"
+    g = torch.Generator().manual_seed(4)
+    theta0 = torch.randn(B, 16, generator=g).to(dev)
+    v0 = torch.randn(B, L, generator=g).to(dtype).to(dev)
+    x_t = torch.randn(B, L, generator=g).to(dtype).to(dev)
+    runs = []
+    for guarded in (True, False):
+        theta, v, x1 = theta0.clone(), v0.clone(), torch.zeros_like(v0)
+        opt = GuidanceOptimizer(B, L, device=dev, velocity_dtype=dtype)
+        opt.set_phase(2); opt.reset()
+        flag = torch.zeros(B, dtype=torch.int32, device=dev)
+        gg = torch.Generator().manual_seed(5)
+        for k in range(4):
+            gt = torch.randn(B, 16, generator=gg).to(dev); gv = torch.randn(B, L, generator=gg).to(dtype).to(dev)
+            terms = torch.rand(B, _lib.FOHO_NUM_TERMS, generator=gg).to(dev)
+            if k == 1:
+                terms[1, 0] = float("nan")              # sample 1: NaN total at the 2nd inner iteration only
+            if guarded:
+                opt.step(theta, gt, v, gv, x_t, x1, sigma=0.5, terms=terms, nan_flag=flag)
+            else:
+                opt.step(theta, gt, v, gv, x_t, x1, sigma=0.5)
+            if k == 0:
+                after_first = (theta.clone(), v.clone(), x1.clone(), opt.vel_m.clone(), opt.theta_v.clone())
+        torch.cuda.synchronize()
+        runs.append((theta, v, x1, opt, flag))
+    (th_g, v_g, x1_g, opt_g, flag), (th_u, v_u, x1_u, opt_u, _) = runs
+    assert flag.tolist() == [0, 2, 0]
+    for b in (0, 2):                                     # untouched by the guard: bit-equal to the unguarded run
+        assert torch.equal(th_g[b], th_u[b]) and torch.equal(v_g[b], v_u[b]) and torch.equal(x1_g[b], x1_u[b])
+        assert torch.equal(opt_g.vel_v[b], opt_u.vel_v[b]) and torch.equal(opt_g.theta_m[b], opt_u.theta_m[b])
+    # sample 1 stopped after the first iteration: parameters, moments and x1 are those of iteration 1
+    # (`after_first` was taken in the unguarded run, whose first iteration is identical)
+    th1, v1, x11, m1, tv1 = after_first
+    assert torch.equal(th_g[1], th1[1]) and torch.equal(v_g[1], v1[1]) and torch.equal(x1_g[1], x11[1])
+    assert torch.equal(opt_g.vel_m[1], m1[1]) and torch.equal(opt_g.theta_v[1], tv1[1])
+    assert not torch.equal(v_u[1], v1[1])                # ... whereas without the guard it kept moving
+    # the guard needs both pointers
+    with pytest.raises(ValueError):
+        opt_g.step(th_g, th_g.clone(), v_g, v_g.clone(), terms=torch.zeros(B, 16, device=dev))
+    d = _lib.UpdateDesc()
+    d.B, d.L, d.step = B, L, 1
+    d.theta = d.grad_theta = d.theta_m = d.theta_v = th_g.data_ptr()
+    d.terms = th_g.data_ptr()                            # nan_flag missing
+    import ctypes
+    assert _lib.load().foho_guidance_update(ctypes.byref(d), None) == -1          # FOHO_E_NULL
+
+
 def test_graph_loop_matches_eager_and_host_api():
     from followmyhold_b200.guidance.config import OptimizationConfig
     from followmyhold_b200.guidance.loop import GuidanceLoop
@@ -196,6 +250,50 @@ def test_graph_loop_matches_eager_and_host_api():
     assert not torch.equal(out["theta"], theta0.cpu())
     sig = loops[1].sigmas
     assert torch.allclose(out["prev_sample"], x_t + (sig[13] - sig[12]) * out["velocity"], atol=1e-5)
+
+
+@pytest.mark.parametrize("phase", [2, 1.5])
+def test_loop_nan_guard_and_loss_history(phase):
+    """An image whose total is NaN (here: a NaN 2-D key-point target) leaves its inner loop at once -- nothing of
+    it moves, the step is reported -- while the other image of the batch is optimised exactly as if it were
+    alone; in the object-only phase that image counts as failed (``return None``, pipelines.py:1442-1444).
+    ``loss_log_every`` keeps the terms of every n-th inner iteration (the FOHO_DEBUG_DIR loss log)."""
+    from followmyhold_b200.guidance.config import OptimizationConfig
+    from followmyhold_b200.guidance.loop import GuidanceLoop
+    B, D, P = 2, 32, 512
+    samples = [make_guidance_sample(D, P, 70 + i) for i in range(B)]
+    sdf0, theta0, st = stack_samples(samples, cap=True)
+    cfg = OptimizationConfig()
+    cfg.optimization_steps_joint, cfg.optimization_steps_scale, cfg.optimization_steps_hand = 5, 5, 5
+    import dataclasses
+    kps_bad = st.kps_2d.clone(); kps_bad[1, 3, 0] = float("nan")
+    st_bad = dataclasses.replace(st, kps_2d=kps_bad)
+    step = cfg.handopt_start_step + (2 if phase == 2 else 1)
+    g = torch.Generator().manual_seed(0)
+    x_t = torch.randn(B, 1024, generator=g); vel = 0.1 * torch.randn(B, 1024, generator=g)
+    res = []
+    for poison in (True, False):
+        lp = GuidanceLoop(B, D, st_bad if poison else st, P, config=cfg, latent_elems=1024, seed=1, loss_log_every=2)
+        lp.sdf0.copy_(sdf0); lp.sdf.copy_(sdf0); lp.x_t.copy_(x_t); lp.velocity.copy_(vel); lp.theta.copy_(theta0)
+        lp._enqueue_step(step, torch.cuda.current_stream(), phase)
+        torch.cuda.synchronize()
+        res.append(lp)
+    bad, good = res
+    assert torch.equal(bad.theta[0], good.theta[0]) and torch.equal(bad.velocity[0], good.velocity[0])
+    assert torch.equal(bad.prev[0], good.prev[0])
+    assert torch.equal(bad.velocity[1], vel[1].cuda())                           # never updated
+    assert torch.equal(bad.theta[1], theta0[1].cuda())
+    assert not torch.equal(good.velocity[1], vel[1].cuda())
+    assert bad.nan_flag.tolist() == [0, 1] and good.nan_flag.tolist() == [0, 0]
+    assert bad.nan_report() == {step: {1: 0}} and good.nan_report() == {}
+    assert bad.failed_images() == ([1] if phase == 1.5 else []) and good.failed_images() == []
+    # loss history: iterations 0, 2, 4 of this step; finite for the clean image, total NaN for the poisoned one
+    h = good.loss_history[step]
+    assert h.shape[0] == 3 and torch.isfinite(h[:, :, 0]).all()
+    assert torch.equal(h[2], good.terms)                                         # last logged = last evaluation (k = 4)
+    assert torch.isnan(bad.loss_history[step][:, 1, 0]).all() and torch.isfinite(bad.loss_history[step][:, 0, 0]).all()
+    lines = good.loss_log_lines(0)
+    assert len(lines) == 3 and lines[1].startswith(f"Denoise step {step} phase {phase}, Opt step 2, total: ")
 
 
 def test_pipelined_host_api_matches_single_batch_calls():

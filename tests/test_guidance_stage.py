@@ -109,6 +109,44 @@ def test_inputs_loader_and_mock_surface(tmp_path):
     assert np.allclose(R.similarity_about(v, np.array([1, 0, 0, 0, 1, 0, 0, 0.0]), np.zeros(3)), v)
 
 
+def test_nan_images_are_reported_like_the_reference(capsys):
+    """NaN total: "Total loss is NaN" (pipelines.py:1443,1591); an image whose hand / object-only phase hit it is
+    the reference's `return None` -> the stage's per-image error line, nothing written (run.py:141,257-259)."""
+    paths = ["/d/000_cropped_obj_1.png", "/d/001_cropped_obj_1.png", "/d/002_cropped_obj_1.png"]
+    skip = R.report_nan_images(paths, {10: {1: 0}, 14: {2: 7}}, failed={1})
+    out = capsys.readouterr().out.splitlines()
+    assert skip == {1}
+    assert out == ["Total loss is NaN", "Error in processing 001_cropped_obj_1.png : cannot unpack non-iterable NoneType object",
+                   "Total loss is NaN"]
+    assert R.report_nan_images(paths, {}, failed=set()) == set() and capsys.readouterr().out == ""
+
+
+@pytest.mark.gpu
+def test_stage_writes_the_debug_dumps_when_asked(tmp_path, monkeypatch):
+    """FOHO_DEBUG_DIR (pipelines.py:1076-1091): params.json + losses.txt per image, a line every 10th inner iteration."""
+    from followmyhold_b200.guidance.config import OptimizationConfig
+    d, jpath = write_dataset(str(tmp_path), 2)
+    dbg = tmp_path / "debug"
+    monkeypatch.setenv("FOHO_DEBUG_DIR", str(dbg))
+    cfg = OptimizationConfig().with_steps(6)
+    cfg.optimization_steps_hand, cfg.optimization_steps_scale, cfg.optimization_steps_joint = 12, 3, 11
+    R.run(**_kwargs(d), model=R.MockGuidanceModel(D=32, latent_elems=1024), batch_size=2, n_cloud=1024, config=cfg,
+          j_regressor_path=jpath)
+    dirs = sorted(os.listdir(dbg))
+    assert len(dirs) == 2 and dirs[0].endswith("_exp_obj000_inpainted") and dirs[1].endswith("_exp_obj001_inpainted")
+    params = json.load(open(dbg / dirs[0] / "params.json"))
+    assert params["optimization_steps_joint"] == 11 and params["phase1_hand_lrs"] == {"scale": 1e-2, "trans": 1e-2, "rot": 0.5}
+    assert params["noise_obj_lr2"] == 1e-2 and params["use_intersection_loss"] is True
+    lines = open(dbg / dirs[1] / "losses.txt").read().splitlines()
+    # steps 2 (hand: k = 0, 10), 3 (object: k = 0), 4 and 5 (joint: k = 0, 10)
+    assert [l.split(",")[0] + "," + l.split(",")[1] for l in lines] == [
+        "Denoise step 2 phase 1, Opt step 0", "Denoise step 2 phase 1, Opt step 10", "Denoise step 3 phase 1.5, Opt step 0",
+        "Denoise step 4 phase 2, Opt step 0", "Denoise step 4 phase 2, Opt step 10",
+        "Denoise step 5 phase 2, Opt step 0", "Denoise step 5 phase 2, Opt step 10"]
+    assert all("nan" not in l for l in lines)
+    assert os.path.exists(os.path.join(d["out"], "000_obj.ply")) and os.path.exists(os.path.join(d["out"], "001_hand.ply"))
+
+
 @pytest.mark.gpu
 def test_stage_runs_three_synthetic_images_and_skips_done_ones(tmp_path, capsys):
     from followmyhold_b200.guidance.config import OptimizationConfig
