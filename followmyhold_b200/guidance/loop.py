@@ -296,6 +296,8 @@ class GuidanceLoop:
                 continue
             for j in range((self.phase_iterations(phase) + self.loss_log_every - 1) // self.loss_log_every):
                 t = h[i, j]
+                if bool(torch.isnan(t).all()):         # slot never written: that step has not been run
+                    continue
                 body = ", ".join(f"{n}: {float(t[q])}" for q, n in enumerate(_lib.TERM_NAMES) if n and q < t.numel())
                 lines.append(f"Denoise step {i} phase {phase}, Opt step {j * self.loss_log_every}, {body}")
         return lines
