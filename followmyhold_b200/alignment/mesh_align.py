@@ -202,12 +202,11 @@ def icp_points_many(problems, n_iter: int, n_outliers, fixed_scale: bool = False
     return [(T.cpu().numpy().reshape(4, 4), float(cost.item())) for (_, _, _, T, cost) in keep]
 
 
-def icp(source_mesh: Geometry, target_mesh: Geometry, n_iter: int, count_source: int = 5_000,
-        count_target: int = 5_000, test_reflections: bool = False, test_rotations: bool = False,
-        fixed_scale: bool = False, outliers: float = 0, on_surface: bool = False, min_scale: float = 0.5,
-        max_scale: float = 2.0, plot: bool = False, seed: Optional[int] = None,
-        device="cuda:0") -> Tuple[np.ndarray, float]:
-    """Same contract as the reference ``icp`` (mesh_align.py:56-175)."""
+def _icp_problem(source_mesh: Geometry, target_mesh: Geometry, count_source: int, count_target: int,
+                 test_reflections: bool, test_rotations: bool, outliers: float, on_surface: bool, plot: bool,
+                 seed: Optional[int]):
+    """Host part of ``icp`` before the loop (mesh_align.py:69-102): candidate cube transforms, surface samples,
+    outlier count.  Returns (cubes, source_points, target_points, n_outliers)."""
     if on_surface:
         raise NotImplementedError("on_surface=True (trimesh.proximity.closest_point) is not offered; "
                                   "both reference callers disable it (h2m.py:44, mano.py:33)")
@@ -235,7 +234,18 @@ def icp(source_mesh: Geometry, target_mesh: Geometry, n_iter: int, count_source:
     n_outliers = int(outliers * count_source)
     if n_outliers >= len(source_points):
         raise ValueError("outlier count exceeds the number of sampled source points")
+    return cubes, source_points, target_points, n_outliers
 
+
+def icp(source_mesh: Geometry, target_mesh: Geometry, n_iter: int, count_source: int = 5_000,
+        count_target: int = 5_000, test_reflections: bool = False, test_rotations: bool = False,
+        fixed_scale: bool = False, outliers: float = 0, on_surface: bool = False, min_scale: float = 0.5,
+        max_scale: float = 2.0, plot: bool = False, seed: Optional[int] = None,
+        device="cuda:0") -> Tuple[np.ndarray, float]:
+    """Same contract as the reference ``icp`` (mesh_align.py:56-175)."""
+    cubes, source_points, target_points, n_outliers = _icp_problem(
+        source_mesh, target_mesh, count_source, count_target, test_reflections, test_rotations, outliers,
+        on_surface, plot, seed)
     best_of_all_cost = np.inf
     best_of_all_transform = np.eye(4)
     for cube in cubes:
@@ -245,6 +255,28 @@ def icp(source_mesh: Geometry, target_mesh: Geometry, n_iter: int, count_source:
             best_of_all_cost = cost
             best_of_all_transform = T @ cube
     return best_of_all_transform, best_of_all_cost
+
+
+def icp_many(pairs, n_iter: int, count_source: int = 5_000, count_target: int = 5_000,
+             test_reflections: bool = False, test_rotations: bool = False, fixed_scale: bool = False,
+             outliers: float = 0, on_surface: bool = False, min_scale: float = 0.5, max_scale: float = 2.0,
+             plot: bool = False, seeds=None, device="cuda:0"):
+    """``icp`` for several (source, target) pairs -- the images of a batch -- with all their iteration loops
+    (every pair x every candidate cube) in flight at once (``icp_points_many``).  ``seeds``: one per pair.
+    Returns one (transform, cost) per pair, each equal to what ``icp`` returns for that pair and seed."""
+    seeds = [None] * len(pairs) if seeds is None else list(seeds)
+    preps = [_icp_problem(s, t, count_source, count_target, test_reflections, test_rotations, outliers, on_surface,
+                          plot, sd) for (s, t), sd in zip(pairs, seeds)]
+    problems, n_out, owner = [], [], []
+    for j, (cubes, sp, tp, no) in enumerate(preps):
+        for cube in cubes:
+            problems.append((transform_points(sp, cube), tp)); n_out.append(no); owner.append((j, cube))
+    results = icp_points_many(problems, n_iter, n_out, fixed_scale, min_scale, max_scale, device=device) if problems else []
+    best = [(np.eye(4), np.inf) for _ in pairs]
+    for (T, cost), (j, cube) in zip(results, owner):
+        if cost < best[j][1]:                      # first cube wins ties, like the sequential loop
+            best[j] = (T @ cube, cost)
+    return best
 
 
 def align_meshes_impl(source_mesh_path, target_mesh_path, transform_path, transformed_mesh_path, fixed_scale,
@@ -283,3 +315,49 @@ def align_meshes_impl(source_mesh_path, target_mesh_path, transform_path, transf
     elapsed_time = time.time() - start_time
     print(f"Elapsed time: {elapsed_time:.2f} seconds")
     return final_transform
+
+
+def align_meshes_many(jobs, fixed_scale, outliers, test_rotations, test_reflections, on_surface,
+                      iterations_coarse, count_source_coarse, count_target_coarse,
+                      iterations_fine, count_source_fine, count_target_fine,
+                      min_scale, max_scale, plot, seed: Optional[int] = 0, device="cuda:0", concurrent: int = 8):
+    """``align_meshes_impl`` for a list of images at once.
+
+    ``jobs``: list of ``(source_mesh_path, target_mesh_path, transform_path, transformed_mesh_path)``.  The
+    images are taken ``concurrent`` at a time; within a group the coarse loops of all images run together,
+    then the fine loops (a single loop is latency bound -- two small kernels per iteration -- so the loops
+    of different images overlap; profiles/r01_icp_bench.json: 3.3x with 8).  Every image gets the same seeds
+    as a call of ``align_meshes_impl`` would give it, so files and transforms are identical to the
+    one-at-a-time path.  Returns the final transforms in job order."""
+    finals = []
+    for g0 in range(0, len(jobs), max(1, int(concurrent))):
+        group = jobs[g0:g0 + max(1, int(concurrent))]
+        start_time = time.time()
+        sources = [load(j[0]) for j in group]
+        targets = [load(j[1]) for j in group]
+        inits = [compute_init_transform(s, t, fixed_scale) for s, t in zip(sources, targets)]
+        for s, T0 in zip(sources, inits):
+            s.apply_transform(T0)
+        coarse = icp_many(list(zip(sources, targets)), n_iter=iterations_coarse, count_source=count_source_coarse,
+                          count_target=count_target_coarse, test_reflections=test_reflections,
+                          test_rotations=test_rotations, fixed_scale=fixed_scale, outliers=outliers,
+                          on_surface=on_surface, min_scale=min_scale, max_scale=max_scale, plot=plot,
+                          seeds=[seed] * len(group), device=device)
+        for s, (Tc, _) in zip(sources, coarse):
+            s.apply_transform(Tc)
+        # the fine stage of the reference call passes neither fixed_scale nor the cube tests (mesh_align.py:203-208)
+        fine = icp_many(list(zip(sources, targets)), n_iter=iterations_fine, count_source=count_source_fine,
+                        count_target=count_target_fine, outliers=outliers, on_surface=on_surface,
+                        min_scale=min_scale, max_scale=max_scale, plot=plot,
+                        seeds=[None if seed is None else seed + 1] * len(group), device=device)
+        elapsed_time = time.time() - start_time
+        for job, s, T0, (Tc, _), (Tf, _) in zip(group, sources, inits, coarse, fine):
+            s.apply_transform(Tf)
+            final_transform = Tf @ Tc @ T0
+            if job[2] is not None:
+                np.save(job[2], final_transform)
+            if job[3] is not None:
+                export(s, job[3])
+            finals.append(final_transform)
+            print(f"Elapsed time: {elapsed_time / len(group):.2f} seconds")
+    return finals

@@ -116,3 +116,48 @@ def test_concurrent_loops_equal_single_loops():
     for (src, tgt), n_out, (T, c) in zip(probs, [80, 82, 84, 86], many):
         T1, c1 = icp_points(src, tgt, 15, n_out, False, 0.7, 3.0)
         assert np.array_equal(T, T1) and c == c1
+
+
+def test_batched_sharded_alignment_stage_equals_one_image_at_a_time(tmp_path, monkeypatch):
+    """The stages align the images of a batch with their ICP loops in flight together, and a rank only its
+    share ``sorted(meshes)[r::world]`` -- transforms and meshes are bit-equal to one ``align_meshes_impl`` call
+    per image (the reference's one-at-a-time loop, h2m.py:17-54 / mano.py:17-43)."""
+    from followmyhold_b200 import meshio
+    from followmyhold_b200.alignment import h2m, mano
+    from followmyhold_b200.alignment.mesh_align import align_meshes_impl
+    hv, hf = standin_hand_mesh(0.35)
+    hun = tmp_path / "hunyuan"; ham = tmp_path / "hamer"
+    hun.mkdir(); ham.mkdir()
+    rng = np.random.default_rng(1)
+    ids = ["03", "07", "11"]
+    for k, i in enumerate(ids):
+        v, f = icosphere(3, 0.4)
+        v = v.astype(np.float64) * np.array([1.0, 0.7 + 0.05 * k, 0.5])
+        meshio.write_ply(str(hun / f"{i}_hoi_mesh.ply"), v, f)
+        md = tmp_path / "moge" / f"{i}_cropped_hoi"; md.mkdir(parents=True)
+        T = random_similarity(5 + k, (0.3, 0.4), 0.1)
+        T[:3, :3] = np.linalg.norm(T[:3, 0]) * np.eye(3)
+        T[:3, 3] += np.array([0, 0, -1.5])
+        tri = v[f]
+        cloud = tri[rng.integers(0, len(f), 12000)].mean(1) @ T[:3, :3].T + T[:3, 3]
+        meshio.write_ply(str(md / "pointcloud.ply"), cloud)
+        meshio.write_obj(str(ham / f"{i}_hamer.obj"), hv * (1.2 + 0.1 * k) + 0.1 * k, hf)
+    kw = dict(fixed_scale=False, outliers=0.2, test_rotations=False, test_reflections=False, on_surface=False,
+              iterations_coarse=50, count_source_coarse=1000, count_target_coarse=5000, iterations_fine=100,
+              count_source_fine=5000, count_target_fine=10000, min_scale=0.7, max_scale=3.0, plot=False, seed=0)
+    # batched (all three in one group), and rank 1 of 2 (only image "07")
+    h2m.run(str(hun), str(tmp_path / "moge"), str(tmp_path / "rt"), concurrent=3)
+    mano.run(str(ham), str(hun), str(tmp_path / "aligned"), concurrent=2)
+    monkeypatch.setenv("RANK", "1"); monkeypatch.setenv("WORLD_SIZE", "2")
+    h2m.run(str(hun), str(tmp_path / "moge"), str(tmp_path / "rt_rank1"))
+    monkeypatch.delenv("RANK"); monkeypatch.delenv("WORLD_SIZE")
+    assert sorted(p.name for p in (tmp_path / "rt_rank1").iterdir()) == ["07_hoi_mesh.npy"]
+    for i in ids:
+        ref = align_meshes_impl(str(hun / f"{i}_hoi_mesh.ply"), str(tmp_path / "moge" / f"{i}_cropped_hoi" / "pointcloud.ply"),
+                                str(tmp_path / f"one_{i}"), None, **kw)
+        assert np.array_equal(np.load(tmp_path / "rt" / f"{i}_hoi_mesh.npy"), ref)
+        align_meshes_impl(str(ham / f"{i}_hamer.obj"), str(hun / f"{i}_hoi_mesh.ply"), None, str(tmp_path / f"one_{i}.ply"), **kw)
+        a = meshio.load(str(tmp_path / "aligned" / f"{i}_hamer_aligned_mano.ply")).vertices
+        b = meshio.load(str(tmp_path / f"one_{i}.ply")).vertices
+        assert np.array_equal(a, b)
+    assert np.array_equal(np.load(tmp_path / "rt_rank1" / "07_hoi_mesh.npy"), np.load(tmp_path / "rt" / "07_hoi_mesh.npy"))

@@ -251,3 +251,40 @@ def test_glb_reader_geometry_and_node_transforms(tmp_path):
     from followmyhold_b200.guidance import run as R
     src = inspect_source = __import__("inspect").getsource(R.load_image_inputs)
     assert src.index('"mesh.glb"') < src.index('"pointcloud.ply"')
+
+
+def test_align_meshes_many_host_logic_equals_one_at_a_time(tmp_path, monkeypatch):
+    """Grouping, seeds, composition and file writing of the batched alignment, with the CPU oracle standing in
+    for the device loop (tests only): every image gets what one ``align_meshes_impl`` call gives it."""
+    from followmyhold_b200 import meshio
+    from followmyhold_b200.synthetic import icosphere, standin_hand_mesh
+    from oracle import icp_oracle as IO
+
+    def one(src, tgt, n_iter, n_out, fixed_scale=False, min_scale=0.5, max_scale=2.0, device=None, return_history=False):
+        return IO.icp_points(src, tgt, n_iter, n_out, fixed_scale, min_scale, max_scale)
+
+    def many(problems, n_iter, n_outliers, fixed_scale=False, min_scale=0.5, max_scale=2.0, device=None):
+        outs = [n_outliers] * len(problems) if isinstance(n_outliers, int) else n_outliers
+        return [one(s, t, n_iter, o, fixed_scale, min_scale, max_scale) for (s, t), o in zip(problems, outs)]
+
+    monkeypatch.setattr(MA, "icp_points", one)
+    monkeypatch.setattr(MA, "icp_points_many", many)
+    hv, hf = standin_hand_mesh(0.35)
+    jobs = []
+    for k in range(3):
+        v, f = icosphere(2, 0.4)
+        src = tmp_path / f"{k}_src.obj"; tgt = tmp_path / f"{k}_tgt.ply"
+        meshio.write_obj(str(src), hv * (1.1 + 0.1 * k) + 0.05 * k, hf)
+        meshio.write_ply(str(tgt), v.astype(np.float64) * np.array([1.0, 0.8, 0.6 + 0.1 * k]), f)
+        jobs.append((str(src), str(tgt), str(tmp_path / f"many_{k}"), str(tmp_path / f"many_{k}.ply")))
+    kw = dict(fixed_scale=False, outliers=0.2, test_rotations=False, test_reflections=True, on_surface=False,
+              iterations_coarse=4, count_source_coarse=150, count_target_coarse=300, iterations_fine=5,
+              count_source_fine=200, count_target_fine=400, min_scale=0.7, max_scale=3.0, plot=False, seed=3)
+    finals = MA.align_meshes_many(jobs, concurrent=2, **kw)
+    for k, (src, tgt, _, _) in enumerate(jobs):
+        ref = MA.align_meshes_impl(src, tgt, str(tmp_path / f"one_{k}"), str(tmp_path / f"one_{k}.ply"), **kw)
+        assert np.array_equal(finals[k], ref)
+        assert np.array_equal(np.load(tmp_path / f"many_{k}.npy"), np.load(tmp_path / f"one_{k}.npy"))
+        assert np.array_equal(meshio.load(str(tmp_path / f"many_{k}.ply")).vertices,
+                              meshio.load(str(tmp_path / f"one_{k}.ply")).vertices)
+    assert MA.align_meshes_many([], **kw) == []
