@@ -279,8 +279,10 @@ def test_loop_nan_guard_and_loss_history(phase):
         torch.cuda.synchronize()
         res.append(lp)
     bad, good = res
-    assert torch.equal(bad.theta[0], good.theta[0]) and torch.equal(bad.velocity[0], good.velocity[0])
-    assert torch.equal(bad.prev[0], good.prev[0])
+    # the other image is optimised as if it were alone (two runs agree to the order of the float scatter-adds)
+    for a, b in ((bad.theta[0], good.theta[0]), (bad.velocity[0], good.velocity[0]), (bad.prev[0], good.prev[0])):
+        assert torch.allclose(a, b, rtol=1e-4, atol=1e-6)
+    assert not torch.equal(good.velocity[0], vel[0].cuda())
     assert torch.equal(bad.velocity[1], vel[1].cuda())                           # never updated
     assert torch.equal(bad.theta[1], theta0[1].cuda())
     assert not torch.equal(good.velocity[1], vel[1].cuda())
