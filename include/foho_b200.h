@@ -177,7 +177,12 @@ int foho_guidance_prepare_statics(const foho_guidance_desc *desc, void *cuda_str
 /* Replaces `joint_optimizer.step()` (torch.optim.AdamW(eps=1e-4), pipelines.py:1478,1601;
  * Adam of :1318 with weight_decay=0) fused with `scheduler.step_final`
  * (schedulers.py:411-493): one launch updates the 16 scalar leaves of every sample and
- * the velocity tensor, and emits x1 = x_t + (1-sigma) v_new for the next decode. */
+ * the velocity tensor, and emits x1 = x_t + (1-sigma) v_new for the next decode.
+ * Arithmetic: the op sequence of torch's multi-tensor CUDA path with its rounding (mul, lerp, mul, addcmul,
+ * sqrt, div, add, addcdiv; csrc/foho_adamw.cuh) -- bit-equal to torch.optim.Adam/AdamW stepping CUDA
+ * parameters.  The hyper-parameters travel as float; derived scalars (1-beta, 1-lr*wd, lr/(1-beta1^t)) are
+ * formed in double from the shortest decimal that round-trips each float, i.e. from the value the caller
+ * wrote (0.9, 1e-4, ...), as torch forms them from python floats. */
 typedef struct foho_update_desc {
   int32_t B;
   int32_t L;                 /* velocity elements per sample (3072*64)                   */
