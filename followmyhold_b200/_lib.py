@@ -17,7 +17,7 @@ REPO_ROOT = PKG_DIR.parent
 CSRC = PKG_DIR / "csrc"
 LIB_PATH = PKG_DIR / "libfoho_b200.so"
 SOURCES = ["guidance_stream.cu", "guidance_sparse.cu", "guidance_objmesh.cu", "guidance_chamfer.cu", "guidance_voxdist.cu", "guidance_update.cu", "icp.cu",
-           "mesh_sdf.cu"]
+           "mesh_sdf.cu", "mesh_decimate.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "-Xcompiler", "-fPIC", "-Xcompiler", "-O3"]
 
@@ -33,7 +33,7 @@ EXPORTED_SYMBOLS = [
     "foho_guidance_accel_bytes", "foho_guidance_prepare_statics",
     "foho_scheduler_step", "foho_scheduler_step_f16", "foho_mock_decoder_forward", "foho_mock_decoder_backward",
     "foho_icp_workspace_bytes", "foho_icp_run",
-    "foho_mesh2sdf_workspace_bytes", "foho_mesh2sdf_lattice", "foho_intersection_count",
+    "foho_mesh2sdf_workspace_bytes", "foho_mesh2sdf_lattice", "foho_intersection_count", "foho_mesh_decimate",
 ]
 
 
@@ -193,6 +193,9 @@ def load(build_if_missing: bool = False) -> C.CDLL:
                                           C.c_size_t, C.c_void_p]
     lib.foho_intersection_count.restype = C.c_int
     lib.foho_intersection_count.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]
+    lib.foho_mesh_decimate.restype = C.c_int
+    lib.foho_mesh_decimate.argtypes = [C.c_void_p, C.c_int32, C.c_void_p, C.c_int32, C.c_int32, C.c_double, C.c_void_p,
+                                       C.POINTER(C.c_int32), C.c_void_p, C.POINTER(C.c_int32)]
     if lib.foho_abi_version() != ABI_VERSION:
         raise FohoLibraryError("libfoho_b200.so ABI version mismatch; rebuild it")
     _lib = lib

@@ -17,8 +17,8 @@ Differences a maintainer should know:
     is consumed as a point cloud -- its vertices -- where the reference renders it;
   * images are processed ``batch_size`` at a time; under ``torchrun`` rank r takes
     ``sorted(images)[r::world]`` (or chunk r of ``task_list_file``, like ``SLURM_ARRAY_TASK_ID``);
-  * mesh post-processing (``FloaterRemover`` ... run.py:158-161) is left to the model's
-    ``extract_mesh``.
+  * the mesh post-processors of run.py:158-161 (``FloaterRemover``, ``DegenerateFaceRemover``,
+    ``FaceReducer``) are ``followmyhold_b200.meshproc``'s (hy3dgen / MeshLab are not needed).
 """
 from __future__ import annotations
 
@@ -33,6 +33,7 @@ import torch
 
 from .. import _lib
 from ..meshio import TriMesh, load, write_ply
+from ..meshproc import DegenerateFaceRemover, FaceReducer, FloaterRemover
 from ..parallel import rank_world, shard_images, task_chunk
 from ..synthetic import cap_boundary_loops, quat_to_mat_np
 from .config import OptimizationConfig
@@ -283,12 +284,19 @@ def _run_batch(chunk, model: GuidanceModel, J: torch.Tensor, config: Optimizatio
         ch = (hand.min(0) + hand.max(0)) / 2.0
         write_ply(p["save_path_hand"], similarity_about(hand, theta[b, :8], ch), inp["faces"])
         verts, faces = model.extract_mesh(sdf[b])
-        if len(verts) == 0:
-            print(f"Empty mesh for {p['cropped_obj_img_path']}")          # run.py:170-172
-            continue
         T = inp["T_h2m"].astype(np.float64)
-        vm = verts.astype(np.float64) @ T[:3, :3].T + T[:3, 3]
-        write_ply(p["save_path_obj"], similarity_about(vm, theta[b, 8:], T[:3, 3]), faces)
+        try:                                                               # run.py:155-167
+            vm = np.asarray(verts, dtype=np.float64).reshape(-1, 3) @ T[:3, :3].T + T[:3, 3]
+            obj = TriMesh(similarity_about(vm, theta[b, 8:], T[:3, 3]) if len(vm) else vm,
+                          np.asarray(faces, dtype=np.int64).reshape(-1, 3))
+            obj = FaceReducer()(DegenerateFaceRemover()(FloaterRemover()(obj)))
+            if len(obj.vertices) == 0:
+                print(f"Empty mesh for {p['cropped_obj_img_path']}")      # run.py:170-172
+                continue
+            write_ply(p["save_path_obj"], obj.vertices, obj.faces)
+        except Exception:
+            print(f"Error in saving mesh for {p['cropped_obj_img_path']}")
+            continue
 
 
 def report_nan_images(image_paths: Sequence[str], nan_report: dict, failed) -> set:

@@ -271,6 +271,17 @@ int foho_mesh2sdf_lattice(const float *verts, int32_t V, const int32_t *faces, i
 int foho_intersection_count(const float *sdf_hand, const float *sdf_obj, int64_t n, long long *count_out,
                             void *cuda_stream);
 
+/* HOST function (CPU memory, no stream): quadric edge-collapse decimation of a triangle mesh down to
+ * `target_faces`.  Replaces `FaceReducer()(mesh)` of the guidance stage (src/foho/guidance/run.py:161 ->
+ * hy3dgen reduce_face -> MeshLab meshing_decimation_quadric_edge_collapse with preserveboundary,
+ * boundaryweight=3, preservenormal, preservetopology); runs once per image after the loop.
+ * IN  verts double [V,3], faces int32 [F,3];  OUT out_verts double [<=V,3], out_faces int32 [<=F,3] (caller
+ * allocates V and F rows), *out_V / *out_F = rows written.  A mesh with F <= target_faces comes back
+ * unchanged apart from dropped index-degenerate faces and unreferenced vertices. */
+int foho_mesh_decimate(const double *verts, int32_t V, const int32_t *faces, int32_t F, int32_t target_faces,
+                       double boundary_weight, double *out_verts, int32_t *out_V, int32_t *out_faces,
+                       int32_t *out_F);
+
 #ifdef __cplusplus
 }
 #endif
