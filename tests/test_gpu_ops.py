@@ -144,13 +144,10 @@ def test_fused_update_bit_equal_to_oracle_and_torch_cuda_optimiser(dtype, phase)
            "velocity_elems": v.numel(), "leaf_mismatch": int((theta != ref_t).sum()), "leaf_elems": theta.numel(),
            "velocity_max_abs_diff": float((v.float() - ref_v.float()).abs().max()), "torch": torch.__version__}
     print("AdamW vs torch CUDA optimiser:", rec)
-    try:
-        import json, os
-        os.makedirs("gpurun_out", exist_ok=True)
+    import json, os
+    if os.path.isdir("gpurun_out"):                      # scratch directory of a GPU-box run: keep the record
         with open("gpurun_out/adamw_vs_torch_cuda.jsonl", "a") as f:
             f.write(json.dumps(rec) + "\n")
-    except OSError:
-        pass
     ulp = float(torch.finfo(dtype).eps) * float(ref_v.abs().max())
     assert rec["velocity_max_abs_diff"] <= 4 * ulp
     assert torch.allclose(theta, ref_t, rtol=3e-6, atol=2e-7)
