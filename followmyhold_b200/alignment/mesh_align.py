@@ -17,7 +17,9 @@ There is no CPU fallback: the ICP loop needs the CUDA library.
 from __future__ import annotations
 
 import ctypes as C
+import os
 import time
+from concurrent.futures import ThreadPoolExecutor
 from typing import Optional, Tuple
 
 import numpy as np
@@ -257,16 +259,38 @@ def icp(source_mesh: Geometry, target_mesh: Geometry, n_iter: int, count_source:
     return best_of_all_transform, best_of_all_cost
 
 
+def host_workers(n_items: int) -> int:
+    """Threads for the per-image host work (mesh I/O, surface sampling: numpy / cKDTree, which release the
+    GIL): the CPUs this process may run on, shared between the ranks of the node."""
+    try:
+        cpus = len(os.sched_getaffinity(0))
+    except AttributeError:
+        cpus = os.cpu_count() or 1
+    local_world = max(1, int(os.environ.get("LOCAL_WORLD_SIZE", "1")))
+    return max(1, min(int(n_items), cpus // local_world))
+
+
+def _pool_map(fn, items, workers: Optional[int]):
+    items = list(items)
+    w = host_workers(len(items)) if workers is None else max(1, int(workers))
+    if w <= 1 or len(items) <= 1:
+        return [fn(x) for x in items]
+    with ThreadPoolExecutor(max_workers=w) as ex:
+        return list(ex.map(fn, items))           # results in input order; every item has its own generator
+
+
 def icp_many(pairs, n_iter: int, count_source: int = 5_000, count_target: int = 5_000,
              test_reflections: bool = False, test_rotations: bool = False, fixed_scale: bool = False,
              outliers: float = 0, on_surface: bool = False, min_scale: float = 0.5, max_scale: float = 2.0,
-             plot: bool = False, seeds=None, device="cuda:0"):
+             plot: bool = False, seeds=None, device="cuda:0", workers: Optional[int] = None):
     """``icp`` for several (source, target) pairs -- the images of a batch -- with all their iteration loops
-    (every pair x every candidate cube) in flight at once (``icp_points_many``).  ``seeds``: one per pair.
+    (every pair x every candidate cube) in flight at once (``icp_points_many``) and their host-side surface
+    sampling spread over ``workers`` threads (default: ``host_workers``).  ``seeds``: one per pair.
     Returns one (transform, cost) per pair, each equal to what ``icp`` returns for that pair and seed."""
     seeds = [None] * len(pairs) if seeds is None else list(seeds)
-    preps = [_icp_problem(s, t, count_source, count_target, test_reflections, test_rotations, outliers, on_surface,
-                          plot, sd) for (s, t), sd in zip(pairs, seeds)]
+    preps = _pool_map(lambda a: _icp_problem(a[0][0], a[0][1], count_source, count_target, test_reflections,
+                                             test_rotations, outliers, on_surface, plot, a[1]),
+                      zip(pairs, seeds), workers)
     problems, n_out, owner = [], [], []
     for j, (cubes, sp, tp, no) in enumerate(preps):
         for cube in cubes:
@@ -320,44 +344,53 @@ def align_meshes_impl(source_mesh_path, target_mesh_path, transform_path, transf
 def align_meshes_many(jobs, fixed_scale, outliers, test_rotations, test_reflections, on_surface,
                       iterations_coarse, count_source_coarse, count_target_coarse,
                       iterations_fine, count_source_fine, count_target_fine,
-                      min_scale, max_scale, plot, seed: Optional[int] = 0, device="cuda:0", concurrent: int = 8):
+                      min_scale, max_scale, plot, seed: Optional[int] = 0, device="cuda:0", concurrent: int = 8,
+                      workers: Optional[int] = None):
     """``align_meshes_impl`` for a list of images at once.
 
     ``jobs``: list of ``(source_mesh_path, target_mesh_path, transform_path, transformed_mesh_path)``.  The
     images are taken ``concurrent`` at a time; within a group the coarse loops of all images run together,
     then the fine loops (a single loop is latency bound -- two small kernels per iteration -- so the loops
-    of different images overlap; profiles/r01_icp_bench.json: 3.3x with 8).  Every image gets the same seeds
+    of different images overlap; profiles/r01_icp_bench.json: 3.3x with 8), and the host work around them
+    (mesh I/O, surface sampling -- most of a stage's wall time once the loop is on the GPU) runs on
+    ``workers`` threads.  Every image gets the same seeds
     as a call of ``align_meshes_impl`` would give it, so files and transforms are identical to the
     one-at-a-time path.  Returns the final transforms in job order."""
     finals = []
     for g0 in range(0, len(jobs), max(1, int(concurrent))):
         group = jobs[g0:g0 + max(1, int(concurrent))]
         start_time = time.time()
-        sources = [load(j[0]) for j in group]
-        targets = [load(j[1]) for j in group]
-        inits = [compute_init_transform(s, t, fixed_scale) for s, t in zip(sources, targets)]
-        for s, T0 in zip(sources, inits):
+        def _open(job):
+            s, t = load(job[0]), load(job[1])
+            T0 = compute_init_transform(s, t, fixed_scale)
             s.apply_transform(T0)
+            return s, t, T0
+        opened = _pool_map(_open, group, workers)
+        sources, targets, inits = [o[0] for o in opened], [o[1] for o in opened], [o[2] for o in opened]
         coarse = icp_many(list(zip(sources, targets)), n_iter=iterations_coarse, count_source=count_source_coarse,
                           count_target=count_target_coarse, test_reflections=test_reflections,
                           test_rotations=test_rotations, fixed_scale=fixed_scale, outliers=outliers,
                           on_surface=on_surface, min_scale=min_scale, max_scale=max_scale, plot=plot,
-                          seeds=[seed] * len(group), device=device)
+                          seeds=[seed] * len(group), device=device, workers=workers)
         for s, (Tc, _) in zip(sources, coarse):
             s.apply_transform(Tc)
         # the fine stage of the reference call passes neither fixed_scale nor the cube tests (mesh_align.py:203-208)
         fine = icp_many(list(zip(sources, targets)), n_iter=iterations_fine, count_source=count_source_fine,
                         count_target=count_target_fine, outliers=outliers, on_surface=on_surface,
                         min_scale=min_scale, max_scale=max_scale, plot=plot,
-                        seeds=[None if seed is None else seed + 1] * len(group), device=device)
-        elapsed_time = time.time() - start_time
-        for job, s, T0, (Tc, _), (Tf, _) in zip(group, sources, inits, coarse, fine):
+                        seeds=[None if seed is None else seed + 1] * len(group), device=device, workers=workers)
+
+        def _close(a):
+            job, s, T0, (Tc, _), (Tf, _) = a
             s.apply_transform(Tf)
             final_transform = Tf @ Tc @ T0
             if job[2] is not None:
                 np.save(job[2], final_transform)
             if job[3] is not None:
                 export(s, job[3])
-            finals.append(final_transform)
+            return final_transform
+        finals += _pool_map(_close, zip(group, sources, inits, coarse, fine), workers)
+        elapsed_time = time.time() - start_time
+        for _ in group:
             print(f"Elapsed time: {elapsed_time / len(group):.2f} seconds")
     return finals

@@ -280,7 +280,10 @@ def test_align_meshes_many_host_logic_equals_one_at_a_time(tmp_path, monkeypatch
     kw = dict(fixed_scale=False, outliers=0.2, test_rotations=False, test_reflections=True, on_surface=False,
               iterations_coarse=4, count_source_coarse=150, count_target_coarse=300, iterations_fine=5,
               count_source_fine=200, count_target_fine=400, min_scale=0.7, max_scale=3.0, plot=False, seed=3)
-    finals = MA.align_meshes_many(jobs, concurrent=2, **kw)
+    finals = MA.align_meshes_many(jobs, concurrent=2, workers=3, **kw)
+    serial = MA.align_meshes_many([(a, b, None, None) for a, b, _, _ in jobs], concurrent=3, workers=1, **kw)
+    assert all(np.array_equal(x, y) for x, y in zip(finals, serial))       # host threads do not change results
+    assert 1 <= MA.host_workers(5) <= 5 and MA.host_workers(0) == 1
     for k, (src, tgt, _, _) in enumerate(jobs):
         ref = MA.align_meshes_impl(src, tgt, str(tmp_path / f"one_{k}"), str(tmp_path / f"one_{k}.ply"), **kw)
         assert np.array_equal(finals[k], ref)
