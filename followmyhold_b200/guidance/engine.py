@@ -397,16 +397,25 @@ def scheduler_step(x_t: torch.Tensor, velocity: torch.Tensor, sigma: float, sigm
 
 class GuidanceFunction(torch.autograd.Function):
     """Differentiable wrapper so a PyTorch decoder can sit upstream of the kernel:
-    ``E = GuidanceFunction.apply(sdf, theta, engine, statics)`` returns the per-sample
-    total energy [B]; backward scales the kernel's dE/dSDF and dE/dtheta."""
+    ``E = GuidanceFunction.apply(sdf, theta, engine, statics[, weights, late_step, stage_mask])`` returns the
+    per-sample total energy [B]; backward scales the kernel's dE/dSDF and dE/dtheta.  ``weights`` (a
+    ``_lib.Weights``) replaces the engine's loss weights for this call (the per-phase weights of the
+    schedule), ``late_step`` is the reference's ``i >= num_inference_steps - 3`` switch (pipelines.py:1561)."""
 
     @staticmethod
-    def forward(ctx, sdf, theta, engine: GuidanceEngine, statics: GuidanceStatics):
-        terms, gs, gt = engine.energy_fwd_bwd(sdf.contiguous(), theta.contiguous(), statics)
-        ctx.save_for_backward(gs.clone(), gt.clone())
-        return terms[:, 0].clone()
+    def forward(ctx, sdf, theta, engine: GuidanceEngine, statics: GuidanceStatics, weights=None,
+                late_step: bool = False, stage_mask: int = 0):
+        with torch.cuda.device(engine.device):
+            desc = engine.make_desc(sdf.contiguous(), theta.contiguous(), statics, late_step=late_step)
+            if weights is not None:
+                desc.w = weights
+            if stage_mask:
+                desc.stage_mask = stage_mask
+            engine.launch(desc)
+        ctx.save_for_backward(engine.grad_sdf.clone(), engine.grad_theta.clone())
+        return engine.terms[:, 0].clone()
 
     @staticmethod
     def backward(ctx, grad_out):
         gs, gt = ctx.saved_tensors
-        return gs * grad_out.view(-1, 1, 1, 1), gt * grad_out.view(-1, 1), None, None
+        return gs * grad_out.view(-1, 1, 1, 1), gt * grad_out.view(-1, 1), None, None, None, None, None

@@ -359,6 +359,66 @@ class GuidanceLoop:
                     self.x_t.copy_(self.prev)
             torch.cuda.current_stream(self.device).wait_stream(s)
 
+    def run_schedule_decoder(self, model_output, decode, first_step: int = 0, last_step: Optional[int] = None) -> None:
+        """``run_schedule_device`` with a differentiable PyTorch decoder in the loop instead of the linear
+        stand-in -- how the reference's own networks are driven: ``decode(x1 [B, L]) -> sdf [B, D, D, D]``
+        float32, negative inside (``latent2sdf``, pipelines.py:292-312), built from torch ops so that autograd
+        carries dE/dSDF back to the model output (:1507-1508, 1600).  Per inner iteration: ``step_final``
+        (torch, differentiable), ``decode``, the fused energy kernels through ``GuidanceFunction``,
+        ``backward()`` through the decoder, the fused AdamW update with the NaN guard.  Eager (the decoder
+        is not capturable in general), one lane; everything else -- phases, weights, leaf groups, optimiser
+        reset per outer step, ``scheduler.step`` -- as in ``run_schedule_device``.
+
+        NOT YET RUN ON HARDWARE: written after this round's GPU budget was spent
+        (tests/test_gpu_schedule.py::test_torch_decoder_schedule_matches_the_graph_schedule is its parity
+        test against the graph path with the linear decoder expressed in torch; it is skip-marked until its
+        first run)."""
+        from .engine import GuidanceFunction
+        if self.micro_batches != 1:
+            raise ValueError("run_schedule_decoder drives one lane: construct the loop with micro_batches=1")
+        cfg = self.cfg
+        last = cfg.num_inference_steps - 1 if last_step is None else last_step
+        ln = self.lanes[0]
+        eng, opt = ln.engine, ln.opt
+        with torch.cuda.device(self.device):
+            s = torch.cuda.current_stream(self.device)
+            sp = C.c_void_p(s.cuda_stream)
+            for i in range(first_step, last + 1):
+                v = model_output(i, self.x_t) if callable(model_output) else model_output[i]
+                self.velocity.copy_(v)
+                phase = self.phase_of_step(i)
+                sigma, sigma_next = float(self.sigmas[i]), float(self.sigmas[i + 1])
+                late = i >= cfg.num_inference_steps - 3
+                if phase != 0:
+                    opt.set_phase(phase)
+                    opt.reset()
+                    self.nan_flag.zero_()
+                    w = self.phase_weights(phase)
+                    for k in range(self.phase_iterations(phase)):
+                        if phase == 1:
+                            # hand only: no volume term has weight, nothing to decode (:1295-1358)
+                            desc = eng.make_desc(self.sdf, self.theta, ln.statics, late_step=late)
+                            desc.w = w
+                            desc.stage_mask = 1 | 4 | 16
+                            eng.launch(desc, s)
+                            gvel = None
+                        else:
+                            vel = self.velocity.detach().clone().requires_grad_(True)
+                            x1 = self.x_t + (1.0 - sigma) * vel                        # step_final (schedulers.py:481)
+                            sdf = decode(x1)
+                            E = GuidanceFunction.apply(sdf, self.theta, eng, ln.statics, w, late, 0)
+                            E.sum().backward()
+                            gvel = vel.grad.contiguous()
+                        if self.loss_history is not None and k % self.loss_log_every == 0:
+                            self.loss_history[i, k // self.loss_log_every].copy_(eng.terms)
+                        opt.step(self.theta, eng.grad_theta, None if gvel is None else self.velocity, gvel,
+                                 self.x_t, self.x1, sigma=sigma, stream=s, terms=eng.terms, nan_flag=self.nan_flag)
+                    self.nan_steps[i].copy_(self.nan_flag)
+                _lib.check("foho_scheduler_step", self.lib.foho_scheduler_step(
+                    self.x_t.data_ptr(), self.velocity.data_ptr(), self.prev.data_ptr(), None, self.x_t.numel(), sigma,
+                    sigma_next, sp))
+                self.x_t.copy_(self.prev)
+
     def run_step_device(self, step_index: int) -> None:
         """Replay one guided-denoise step; inputs (sdf0, x_t, velocity, theta) already in HBM."""
         self.capture(step_index)
