@@ -367,12 +367,10 @@ class GuidanceLoop:
         (torch, differentiable), ``decode``, the fused energy kernels through ``GuidanceFunction``,
         ``backward()`` through the decoder, the fused AdamW update with the NaN guard.  Eager (the decoder
         is not capturable in general), one lane; everything else -- phases, weights, leaf groups, optimiser
-        reset per outer step, ``scheduler.step`` -- as in ``run_schedule_device``.
-
-        NOT YET RUN ON HARDWARE: written after this round's GPU budget was spent
-        (tests/test_gpu_schedule.py::test_torch_decoder_schedule_matches_the_graph_schedule is its parity
-        test against the graph path with the linear decoder expressed in torch; it is skip-marked until its
-        first run)."""
+        reset per outer step, ``scheduler.step`` -- as in ``run_schedule_device``
+        (tests/test_gpu_schedule.py::test_torch_decoder_schedule_matches_the_graph_schedule: equal to the graph
+        path when the torch decoder is the linear stand-in).  ``self.sdf`` must hold a finite volume for the
+        hand-only phase: its volume terms have zero weight there but are still evaluated."""
         from .engine import GuidanceFunction
         if self.micro_batches != 1:
             raise ValueError("run_schedule_decoder drives one lane: construct the loop with micro_batches=1")

@@ -64,9 +64,13 @@ class GuidanceModel:
         raise NotImplementedError
 
     def decoder_state(self):
-        """(sdf0 [B,D,D,D], tap int64 [latent_elems], alpha) of the linear tap decoder the loop drives;
-        a network decoder plugs in through ``GuidanceFunction`` instead."""
+        """(sdf0 [B,D,D,D], tap int64 [latent_elems], alpha) of the linear tap decoder the graph-captured loop
+        drives (``GuidanceLoop.run_schedule_device``).  A model that has a ``decode`` method is driven through
+        ``GuidanceLoop.run_schedule_decoder`` instead and need not implement this."""
         raise NotImplementedError
+
+    # Optional: ``decode(x1 [B, latent_elems]) -> sdf [B,D,D,D]`` float32, negative inside, differentiable torch
+    # ops (``latent2sdf``, pipelines.py:292-312).  The reference's VAE + geo_decoder are wrapped this way.
 
     def extract_mesh(self, sdf: np.ndarray) -> Tuple[np.ndarray, np.ndarray]:
         """Surface of one decoded volume [D,D,D] (negative inside) -> (verts in Hunyuan space, faces)."""
@@ -253,24 +257,37 @@ def _run_batch(chunk, model: GuidanceModel, J: torch.Tensor, config: Optimizatio
         kps_2d=torch.from_numpy(np.stack([i["kps"] for i in inputs])).to(dev).contiguous(),
         fov_deg=inputs[0]["fovx"], image_hw=inputs[0]["hw"])
     model.begin_batch([p["index"] for p, _ in chunk], [p["cropped_obj_img_path"] for p, _ in chunk], dev)
-    sdf0, tap, alpha = model.decoder_state()
     debug_root = os.environ.get("FOHO_DEBUG_DIR")               # pipelines.py:1076-1091: debug dumps when set
-    loop = GuidanceLoop(B, model.D, st, n_cloud, device=dev, config=config, latent_elems=model.latent_elems,
-                        decoder_alpha=float(alpha), loss_log_every=10 if debug_root else 0)
-    loop.tap = tap.to(dev).to(torch.int64).contiguous()
-    loop.sdf0.copy_(sdf0); loop.sdf.copy_(sdf0)
     gen = torch.Generator().manual_seed(seed)                   # run.py:120 torch.manual_seed(2)
-    loop.x_t.copy_(model.initial_latents(B, gen))
-    loop.reset_leaves()
-    loop.run_schedule_device(model.predict)
-    # ---- outputs (pipelines.py:1641-1679: final decode, meshes in MoGe space)
     last = config.num_inference_steps - 1
-    # step_final on the already advanced latents, as the reference does it (:1612-1623); sigma_last = 1
-    x1 = loop.x_t + (1.0 - float(loop.sigmas[last])) * loop.velocity
-    flat0 = loop.sdf0.reshape(B, -1)
-    sdf = flat0.clone()
-    sdf[:, loop.tap] = flat0[:, loop.tap] + loop.alpha * x1
-    sdf = sdf.reshape(B, model.D, model.D, model.D).cpu().numpy()
+    decode = getattr(model, "decode", None)
+    if callable(decode):
+        # a differentiable network decoder in the loop (eager; autograd carries dE/dSDF to the model output)
+        loop = GuidanceLoop(B, model.D, st, n_cloud, device=dev, config=config, latent_elems=model.latent_elems,
+                            loss_log_every=10 if debug_root else 0)
+        loop.sdf.fill_(1.0)                                     # finite "outside" volume for the hand-only phase
+        loop.x_t.copy_(model.initial_latents(B, gen))
+        loop.reset_leaves()
+        loop.run_schedule_decoder(model.predict, decode)
+        with torch.no_grad():                                   # final decode (:1641), sigma_last = 1
+            x1 = loop.x_t + (1.0 - float(loop.sigmas[last])) * loop.velocity
+            sdf = decode(x1).float().reshape(B, model.D, model.D, model.D).cpu().numpy()
+    else:
+        sdf0, tap, alpha = model.decoder_state()
+        loop = GuidanceLoop(B, model.D, st, n_cloud, device=dev, config=config, latent_elems=model.latent_elems,
+                            decoder_alpha=float(alpha), loss_log_every=10 if debug_root else 0)
+        loop.tap = tap.to(dev).to(torch.int64).contiguous()
+        loop.sdf0.copy_(sdf0); loop.sdf.copy_(sdf0)
+        loop.x_t.copy_(model.initial_latents(B, gen))
+        loop.reset_leaves()
+        loop.run_schedule_device(model.predict)
+        # ---- outputs (pipelines.py:1641-1679: final decode, meshes in MoGe space)
+        # step_final on the already advanced latents, as the reference does it (:1612-1623); sigma_last = 1
+        x1 = loop.x_t + (1.0 - float(loop.sigmas[last])) * loop.velocity
+        flat0 = loop.sdf0.reshape(B, -1)
+        sdf = flat0.clone()
+        sdf[:, loop.tap] = flat0[:, loop.tap] + loop.alpha * x1
+        sdf = sdf.reshape(B, model.D, model.D, model.D).cpu().numpy()
     theta = loop.theta.cpu().numpy().astype(np.float64)
     torch.cuda.synchronize(dev)
     nan_rep, failed = loop.nan_report(), set(loop.failed_images())

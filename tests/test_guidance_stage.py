@@ -168,3 +168,28 @@ def test_stage_runs_three_synthetic_images_and_skips_done_ones(tmp_path, capsys)
     R.run(**_kwargs(d), model=model, batch_size=2, n_cloud=1024, config=cfg, j_regressor_path=jpath)
     out = capsys.readouterr().out
     assert out.count("already exists, skipping") == 3 and os.path.getmtime(os.path.join(d["out"], "000_hand.ply")) == stamp
+
+
+@pytest.mark.gpu
+def test_stage_with_a_torch_decoder_model_equals_the_stand_in_path(tmp_path):
+    """A model exposing ``decode`` (a differentiable torch decoder, as the reference's VAE would be wrapped) is driven
+    through ``run_schedule_decoder``; with the linear stand-in expressed in torch the stage writes the same meshes."""
+    from followmyhold_b200.guidance.config import OptimizationConfig
+
+    class TorchDecoderModel(R.MockGuidanceModel):
+        def decode(self, x1):
+            flat0 = self._sdf0.reshape(x1.shape[0], -1)
+            tap = self.tap.to(x1.device)
+            return flat0.scatter(1, tap.view(1, -1).expand(x1.shape[0], -1), flat0[:, tap] + self.alpha * x1).reshape(self._sdf0.shape)
+
+    cfg = OptimizationConfig().with_steps(6)
+    cfg.optimization_steps_hand, cfg.optimization_steps_scale, cfg.optimization_steps_joint = 4, 3, 2
+    outs = []
+    for k, cls in enumerate((R.MockGuidanceModel, TorchDecoderModel)):
+        d, jpath = write_dataset(str(tmp_path / f"run{k}"), 2)
+        R.run(**_kwargs(d), model=cls(D=32, latent_elems=1024), batch_size=2, n_cloud=1024, config=cfg, j_regressor_path=jpath)
+        outs.append([(load(os.path.join(d["out"], f"{i:03d}_hand.ply")).vertices, load(os.path.join(d["out"], f"{i:03d}_obj.ply")).vertices)
+                     for i in range(2)])
+    for (h0, o0), (h1, o1) in zip(*outs):
+        assert np.allclose(h0, h1, atol=2e-5)
+        assert o0.shape == o1.shape and np.allclose(o0, o1, atol=2e-4)
