@@ -117,3 +117,30 @@ def test_floater_and_degenerate_removers():
     # the reference's call sequence (run.py:158-161) on TriMesh objects
     m = MP.FaceReducer()(MP.DegenerateFaceRemover()(MP.FloaterRemover()(TriMesh(V, F))), max_facenum=500)
     assert isinstance(m, TriMesh) and len(m.faces) <= 500
+
+
+def test_decimator_survives_triangle_soups_and_keeps_the_genus():
+    """Host C++ inside the stage must not fall over on bad input: random soups (index-degenerate, duplicate and
+    non-manifold faces, duplicate positions, planar sets) come back with valid indices; a torus keeps genus 1."""
+    rng = np.random.default_rng(0)
+    for trial in range(200):
+        V = int(rng.integers(4, 60)); F = int(rng.integers(1, 200))
+        v = rng.standard_normal((V, 3))
+        if trial % 5 == 0:
+            v[:, 2] = 0
+        if trial % 7 == 0:
+            v[rng.integers(V)] = v[rng.integers(V)]
+        f = rng.integers(0, V, (F, 3)).astype(np.int32)
+        ov, of = MP.reduce_faces(v, f, int(rng.integers(0, F + 1)))
+        assert of.ndim == 2 and len(of) <= F and np.isfinite(ov).all()
+        assert len(of) == 0 or (of.min() >= 0 and of.max() < len(ov))
+        MP.remove_floaters(v, f.astype(np.int64)); MP.remove_degenerate_faces(v, f.astype(np.int64))
+    n, m = 48, 24
+    u, w = np.meshgrid(np.linspace(0, 2 * np.pi, n, endpoint=False), np.linspace(0, 2 * np.pi, m, endpoint=False), indexing="ij")
+    tv = np.stack([(1 + 0.35 * np.cos(w)) * np.cos(u), (1 + 0.35 * np.cos(w)) * np.sin(u), 0.35 * np.sin(w)], -1).reshape(-1, 3)
+    idx = np.arange(n * m).reshape(n, m)
+    a, b, c, d = idx, np.roll(idx, -1, 0), np.roll(np.roll(idx, -1, 0), -1, 1), np.roll(idx, -1, 1)
+    tf = np.concatenate([np.stack([a, b, c], -1).reshape(-1, 3), np.stack([a, c, d], -1).reshape(-1, 3)]).astype(np.int32)
+    ov, of = MP.reduce_faces(tv, tf, 600)
+    edges, cnt = edge_face_counts(of)
+    assert len(of) <= 600 and (cnt == 2).all() and len(ov) - len(edges) + len(of) == 0
