@@ -15,6 +15,10 @@ stages run in (``write_pth()`` does that) -- or import this module from a ``site
 
     import followmyhold_b200.dropin as d; d.install()
 
+Side effect to know about: importing the package sets ``CUDA_DEVICE_MAX_CONNECTIONS=32`` if it is unset
+(``followmyhold_b200/__init__.py``), so with the ``.pth`` line every interpreter of that environment starts
+with 32 hardware work queues instead of 8; export the variable yourself to keep another value.
+
 ``FOHO_B200_DROPIN=0`` switches the redirect off (A/B runs against the reference stages).  The guidance stage
 additionally needs the Hunyuan3D networks wrapped in a ``GuidanceModel`` named by ``FOHO_B200_GUIDANCE_MODEL``
 (guidance/run.py); without one it fails loudly.
