@@ -12,7 +12,7 @@ import glob
 import os
 
 from ..parallel import rank_world, shard_images
-from .mesh_align import align_meshes_many
+from .mesh_align import STAGE_ICP_KWARGS, align_meshes_many
 
 
 def run(hamer_out_dir: str, hunyuan_mesh_dir: str, aligned_mano_dir: str, seed: int = 0, device: str = "cuda:0",
@@ -25,43 +25,24 @@ def run(hamer_out_dir: str, hunyuan_mesh_dir: str, aligned_mano_dir: str, seed: 
     rank, world = rank_world()
     meshes = shard_images(meshes, rank, world)
 
-    jobs = []
-    for mesh_path in meshes:
-        base_name = os.path.basename(mesh_path)
-        i = base_name.split("_")[0]
-        j = os.path.splitext(base_name)[0]
-        target_mesh = os.path.join(hunyuan_mesh_dir, f"{i}_hoi_mesh.ply")
-        out_path = os.path.join(aligned_mano_dir, f"{j}_aligned_mano.ply")
-        jobs.append((mesh_path, target_mesh, None, out_path))
-    align_meshes_many(
-        jobs,
-        fixed_scale=False,
-        outliers=0.2,
-        test_rotations=False,
-        test_reflections=False,
-        on_surface=False,
-        iterations_coarse=50,
-        count_source_coarse=1000,
-        count_target_coarse=5000,
-        iterations_fine=100,
-        count_source_fine=5000,
-        count_target_fine=10000,
-        min_scale=0.7,
-        max_scale=3.0,
-        plot=False,
-        seed=seed,
-        device=device,
-        concurrent=concurrent,
-    )
+    def job(mesh_path):
+        # {i}_*.obj is aligned to {i}_hoi_mesh.ply and written as {name}_aligned_mano.ply (mano.py:18-23)
+        stem = os.path.splitext(os.path.basename(mesh_path))[0]
+        return (mesh_path, os.path.join(hunyuan_mesh_dir, f"{stem.split('_')[0]}_hoi_mesh.ply"), None,
+                os.path.join(aligned_mano_dir, f"{stem}_aligned_mano.ply"))
+
+    jobs = [job(m) for m in meshes]
+    align_meshes_many(jobs, **STAGE_ICP_KWARGS, seed=seed, device=device, concurrent=concurrent)
+
+
+FLAGS = ('hamer_out_dir', 'hunyuan_mesh_dir', 'aligned_mano_dir')      # the reference stage's CLI flags = run()'s arguments
 
 
 def main() -> None:
     parser = argparse.ArgumentParser()
-    parser.add_argument("--hamer_out_dir", required=True)
-    parser.add_argument("--hunyuan_mesh_dir", required=True)
-    parser.add_argument("--aligned_mano_dir", required=True)
-    args = parser.parse_args()
-    run(hamer_out_dir=args.hamer_out_dir, hunyuan_mesh_dir=args.hunyuan_mesh_dir, aligned_mano_dir=args.aligned_mano_dir)
+    for flag in FLAGS:
+        parser.add_argument(f"--{flag}", required=True)
+    run(**vars(parser.parse_args()))
 
 
 if __name__ == "__main__":

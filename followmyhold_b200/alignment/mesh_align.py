@@ -341,6 +341,15 @@ def align_meshes_impl(source_mesh_path, target_mesh_path, transform_path, transf
     return final_transform
 
 
+# The ICP configuration both stage callers use, verbatim from their calls (h2m.py:35-54 and mano.py:24-43 pass the
+# same fourteen values): similarity fit, 20 % trimmed, identity start only, 50 coarse + 100 fine iterations.
+STAGE_ICP_KWARGS = dict(
+    fixed_scale=False, outliers=0.2, test_rotations=False, test_reflections=False, on_surface=False,
+    iterations_coarse=50, count_source_coarse=1000, count_target_coarse=5000,
+    iterations_fine=100, count_source_fine=5000, count_target_fine=10000,
+    min_scale=0.7, max_scale=3.0, plot=False)
+
+
 def align_meshes_many(jobs, fixed_scale, outliers, test_rotations, test_reflections, on_surface,
                       iterations_coarse, count_source_coarse, count_target_coarse,
                       iterations_fine, count_source_fine, count_target_fine,

@@ -291,3 +291,61 @@ def test_align_meshes_many_host_logic_equals_one_at_a_time(tmp_path, monkeypatch
         assert np.array_equal(meshio.load(str(tmp_path / f"many_{k}.ply")).vertices,
                               meshio.load(str(tmp_path / f"one_{k}.ply")).vertices)
     assert MA.align_meshes_many([], **kw) == []
+
+
+def test_alignment_stage_glue_on_files_with_the_oracle_loop(tmp_path, monkeypatch, capsys):
+    """``h2m.run`` / ``mano.run`` end to end on files (target lookup order, file names, the callers' ICP constants,
+    rank sharding) with the CPU oracle standing in for the device loop: same artefacts as one reference-style
+    ``align_meshes_impl`` call per image with the constants of h2m.py:35-54 / mano.py:24-43."""
+    from followmyhold_b200 import meshio
+    from followmyhold_b200.alignment import h2m, mano
+    from followmyhold_b200.synthetic import icosphere, standin_hand_mesh
+    from oracle import icp_oracle as IO
+
+    def one(src, tgt, n_iter, n_out, fixed_scale=False, min_scale=0.5, max_scale=2.0, device=None, return_history=False):
+        return IO.icp_points(src, tgt, n_iter, n_out, fixed_scale, min_scale, max_scale)
+
+    monkeypatch.setattr(MA, "icp_points", one)
+    monkeypatch.setattr(MA, "icp_points_many", lambda probs, n_iter, n_out, fs=False, lo=0.5, hi=2.0, device=None:
+                        [one(s, t, n_iter, o, fs, lo, hi) for (s, t), o in zip(probs, n_out)])
+    assert MA.STAGE_ICP_KWARGS == dict(fixed_scale=False, outliers=0.2, test_rotations=False, test_reflections=False,
+                                       on_surface=False, iterations_coarse=50, count_source_coarse=1000,
+                                       count_target_coarse=5000, iterations_fine=100, count_source_fine=5000,
+                                       count_target_fine=10000, min_scale=0.7, max_scale=3.0, plot=False)
+    hv, hf = standin_hand_mesh(0.35)
+    hun = tmp_path / "hun"; ham = tmp_path / "hamer"; hun.mkdir(); ham.mkdir()
+    rng = np.random.default_rng(0)
+    for k, i in enumerate(("04", "09")):
+        v, f = icosphere(2, 0.4)
+        v = v.astype(np.float64) * np.array([1.0, 0.75, 0.5 + 0.1 * k])
+        meshio.write_ply(str(hun / f"{i}_hoi_mesh.ply"), v, f)
+        md = tmp_path / "moge" / f"{i}_cropped_hoi"; md.mkdir(parents=True)
+        cloud = v[f][rng.integers(0, len(f), 3000)].mean(1) * 0.4 + np.array([0.1, 0.0, -1.2])
+        # image 04 has both candidates: pointcloud.ply must win over mesh.glb; 09 has only a decoy name
+        meshio.write_ply(str(md / "pointcloud.ply"), cloud)
+        if k == 0:
+            (md / "mesh.glb").write_bytes(b"not read")
+        meshio.write_obj(str(ham / f"{i}_hamer.obj"), hv * 1.2 + 0.1, hf)
+    (tmp_path / "moge" / "09_cropped_hoi" / "pointcloud.ply").rename(tmp_path / "moge" / "09_cropped_hoi" / "mesh.ply")
+    h2m.run(str(hun), str(tmp_path / "moge"), str(tmp_path / "rt"), concurrent=2)
+    mano.run(str(ham), str(hun), str(tmp_path / "aligned"), concurrent=1)
+    assert sorted(os.listdir(tmp_path / "rt")) == ["04_hoi_mesh.npy", "09_hoi_mesh.npy"]
+    assert sorted(os.listdir(tmp_path / "aligned")) == ["04_hamer_aligned_mano.ply", "09_hamer_aligned_mano.ply"]
+    for i, tgt in (("04", "pointcloud.ply"), ("09", "mesh.ply")):
+        ref = MA.align_meshes_impl(str(hun / f"{i}_hoi_mesh.ply"), str(tmp_path / "moge" / f"{i}_cropped_hoi" / tgt),
+                                   None, None, **MA.STAGE_ICP_KWARGS, seed=0)
+        got = np.load(tmp_path / "rt" / f"{i}_hoi_mesh.npy")
+        assert got.dtype == np.float64 and np.array_equal(got, ref)
+        assert 0.3 < np.linalg.norm(got[:3, 0]) < 0.5                                 # the 0.4x similarity is recovered
+    # rank 1 of 2 aligns only its share; a frame without MoGe geometry is reported and skipped
+    monkeypatch.setenv("RANK", "1"); monkeypatch.setenv("WORLD_SIZE", "2")
+    h2m.run(str(hun), str(tmp_path / "moge"), str(tmp_path / "rt1"))
+    assert os.listdir(tmp_path / "rt1") == ["09_hoi_mesh.npy"]
+    monkeypatch.delenv("RANK"); monkeypatch.delenv("WORLD_SIZE")
+    import shutil
+    shutil.rmtree(tmp_path / "moge" / "04_cropped_hoi")
+    capsys.readouterr()
+    h2m.run(str(hun), str(tmp_path / "moge"), str(tmp_path / "rt2"))
+    assert "No MoGe mesh found for 04" in capsys.readouterr().out and os.listdir(tmp_path / "rt2") == ["09_hoi_mesh.npy"]
+    h2m.run(str(tmp_path / "empty"), str(tmp_path / "moge"), str(tmp_path / "rt3"))
+    assert "No Hunyuan HOI meshes found" in capsys.readouterr().out
