@@ -17,12 +17,12 @@ REPO_ROOT = PKG_DIR.parent
 CSRC = PKG_DIR / "csrc"
 LIB_PATH = PKG_DIR / "libfoho_b200.so"
 SOURCES = ["guidance_stream.cu", "guidance_sparse.cu", "guidance_objmesh.cu", "guidance_chamfer.cu", "guidance_voxdist.cu", "guidance_update.cu", "icp.cu",
-           "mesh_sdf.cu", "mesh_decimate.cu"]
+           "mesh_sdf.cu", "mesh_decimate.cu", "decoder_gemm.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "-Xcompiler", "-fPIC", "-Xcompiler", "-O3"]
 
 FOHO_NUM_TERMS = 16
-ABI_VERSION = 4
+ABI_VERSION = 5
 TERM_NAMES = ["total", "pen", "con", "int", "count", "mom", "ch", "kp", "treg_h", "treg_o", "dist", "vreg",
               "edge", "mean_d2", "ncand", "flags"]
 
@@ -34,6 +34,7 @@ EXPORTED_SYMBOLS = [
     "foho_scheduler_step", "foho_scheduler_step_f16", "foho_mock_decoder_forward", "foho_mock_decoder_backward",
     "foho_icp_workspace_bytes", "foho_icp_run",
     "foho_mesh2sdf_workspace_bytes", "foho_mesh2sdf_lattice", "foho_intersection_count", "foho_mesh_decimate",
+    "foho_tc_gemm",
 ]
 
 
@@ -129,6 +130,20 @@ class UpdateDesc(C.Structure):
     ]
 
 
+class GemmDesc(C.Structure):
+    _fields_ = [
+        ("M", C.c_int32), ("N", C.c_int32), ("K", C.c_int32), ("batch", C.c_int32),
+        ("a_mn_major", C.c_int32), ("b_mn_major", C.c_int32), ("c_f32", C.c_int32), ("res_f32", C.c_int32),
+        ("act", C.c_int32), ("block_n", C.c_int32), ("max_ctas", C.c_int32), ("alpha", C.c_float),
+        ("A", C.c_void_p), ("lda", C.c_int64), ("bsa", C.c_int64),
+        ("B", C.c_void_p), ("ldb", C.c_int64), ("bsb", C.c_int64),
+        ("C", C.c_void_p), ("ldc", C.c_int64), ("bsc", C.c_int64),
+        ("bias", C.c_void_p),
+        ("res", C.c_void_p), ("ldr", C.c_int64), ("bsr", C.c_int64),
+        ("aux_in", C.c_void_p), ("aux_out", C.c_void_p), ("ldaux", C.c_int64), ("bsaux", C.c_int64),
+    ]
+
+
 _lib: Optional[C.CDLL] = None
 
 
@@ -196,6 +211,8 @@ def load(build_if_missing: bool = False) -> C.CDLL:
     lib.foho_mesh_decimate.restype = C.c_int
     lib.foho_mesh_decimate.argtypes = [C.c_void_p, C.c_int32, C.c_void_p, C.c_int32, C.c_int32, C.c_double, C.c_void_p,
                                        C.POINTER(C.c_int32), C.c_void_p, C.POINTER(C.c_int32)]
+    lib.foho_tc_gemm.restype = C.c_int
+    lib.foho_tc_gemm.argtypes = [C.POINTER(GemmDesc), C.c_void_p]
     if lib.foho_abi_version() != ABI_VERSION:
         raise FohoLibraryError("libfoho_b200.so ABI version mismatch; rebuild it")
     _lib = lib

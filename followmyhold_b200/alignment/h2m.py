@@ -12,11 +12,11 @@ import argparse
 import glob
 import os
 
-from ..parallel import rank_world, shard_images
+from ..parallel import default_device, rank_world, shard_images
 from .mesh_align import STAGE_ICP_KWARGS, align_meshes_many
 
 
-def run(hunyuan_mesh_dir: str, moge_out_dir: str, h2m_rt_dir: str, seed: int = 0, device: str = "cuda:0",
+def run(hunyuan_mesh_dir: str, moge_out_dir: str, h2m_rt_dir: str, seed: int = 0, device: str = None,
         concurrent: int = 8) -> None:
     meshes = sorted(glob.glob(os.path.join(hunyuan_mesh_dir, "*.ply")))
     if not meshes:
@@ -40,7 +40,7 @@ def run(hunyuan_mesh_dir: str, moge_out_dir: str, h2m_rt_dir: str, seed: int = 0
             print(f"No MoGe mesh found for {i} in {moge_dir}. Skipping.")
             continue
         jobs.append((mesh_path, target_mesh, os.path.join(h2m_rt_dir, j), None))
-    align_meshes_many(jobs, **STAGE_ICP_KWARGS, seed=seed, device=device, concurrent=concurrent)
+    align_meshes_many(jobs, **STAGE_ICP_KWARGS, seed=seed, device=device or default_device(), concurrent=concurrent)
 
 
 FLAGS = ('hunyuan_mesh_dir', 'moge_out_dir', 'h2m_rt_dir')      # the reference stage's CLI flags = run()'s arguments

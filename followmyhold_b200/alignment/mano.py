@@ -11,11 +11,11 @@ import argparse
 import glob
 import os
 
-from ..parallel import rank_world, shard_images
+from ..parallel import default_device, rank_world, shard_images
 from .mesh_align import STAGE_ICP_KWARGS, align_meshes_many
 
 
-def run(hamer_out_dir: str, hunyuan_mesh_dir: str, aligned_mano_dir: str, seed: int = 0, device: str = "cuda:0",
+def run(hamer_out_dir: str, hunyuan_mesh_dir: str, aligned_mano_dir: str, seed: int = 0, device: str = None,
         concurrent: int = 8) -> None:
     meshes = sorted(glob.glob(os.path.join(hamer_out_dir, "*.obj")))
     if not meshes:
@@ -32,7 +32,7 @@ def run(hamer_out_dir: str, hunyuan_mesh_dir: str, aligned_mano_dir: str, seed: 
                 os.path.join(aligned_mano_dir, f"{stem}_aligned_mano.ply"))
 
     jobs = [job(m) for m in meshes]
-    align_meshes_many(jobs, **STAGE_ICP_KWARGS, seed=seed, device=device, concurrent=concurrent)
+    align_meshes_many(jobs, **STAGE_ICP_KWARGS, seed=seed, device=device or default_device(), concurrent=concurrent)
 
 
 FLAGS = ('hamer_out_dir', 'hunyuan_mesh_dir', 'aligned_mano_dir')      # the reference stage's CLI flags = run()'s arguments

@@ -1,0 +1,316 @@
+// Hand-written tcgen05 GEMM for the latent -> SDF decoder (row f1; the dense contractions of
+// third_party_patches/hy3dgen/shapegen/pipelines.py:292-312 `latent2sdf`: ShapeVAE transformer + geo_decoder).
+//
+//   C[b][m][n] = epilogue( alpha * sum_k A[b](m,k) * B[b](n,k) )        fp16 operands, fp32 accumulation in TMEM
+//
+// Each operand is either K-major (rows of k, the nn.Linear weight layout [out,in] and activations [tokens,in]) or
+// MN-major (k-rows of m / n: lets P^T, dS^T, V, K enter the attention-gradient products without a transpose).
+//
+// One persistent CTA per SM, warp-specialised:
+//   warp 0   TMA producer: cp.async.bulk.tensor (128-byte swizzle) into a ring of kStages {A,B} tiles, mbarrier full/empty
+//   warp 1   one thread issues tcgen05.mma (M=128, N=BN, K=16) into one of two TMEM accumulators, tcgen05.commit frees slots
+//   warp 2   TMEM allocator
+//   warps 4-7 epilogue: tcgen05.ld -> bias / GELU / GELU' / residual -> global, overlapped with the next tile's mainloop
+#include "foho_common.cuh"
+#include "foho_tc.cuh"
+#include <cuda_fp16.h>
+
+namespace {
+
+constexpr int BM = 128, BK = 64, UMMA_K = 16;
+
+struct GemmParams {
+  int M, N, K, batch;
+  int tiles_m, tiles_n;
+  // epilogue
+  void *C; long long ldc, bsc; int c_f32;
+  const float *bias;
+  const void *res; long long ldr, bsr; int res_f32;
+  const __half *aux_in; __half *aux_out; long long ldaux, bsaux;
+  float alpha; int act;
+};
+
+template <int BN>
+struct Cfg {
+  static constexpr int A_BYTES = BM * BK * 2, B_BYTES = BN * BK * 2, STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int STAGES = (200 * 1024 / STAGE_BYTES) > 8 ? 8 : (200 * 1024 / STAGE_BYTES);
+  static constexpr int SMEM = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+  static constexpr uint32_t TMEM_COLS = 2 * BN;
+};
+
+__device__ __forceinline__ float gelu_f(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752f)); }
+__device__ __forceinline__ float dgelu_f(float x) {
+  return 0.5f * (1.0f + erff(x * 0.70710678118654752f)) + x * 0.3989422804014327f * __expf(-0.5f * x * x);
+}
+
+template <int BN, bool A_MN, bool B_MN>
+__global__ void __launch_bounds__(256, 1)
+k_gemm_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmParams p) {
+  using C_ = Cfg<BN>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t *bars = reinterpret_cast<uint64_t *>(smem + C_::STAGES * C_::STAGE_BYTES);
+  uint64_t *full = bars, *empty = bars + C_::STAGES, *tfull = bars + 2 * C_::STAGES, *tempty = tfull + 2;
+  uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(tempty + 2);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int nkb = (p.K + BK - 1) / BK;
+  const int tiles_per_batch = p.tiles_m * p.tiles_n;
+  const int num_tiles = tiles_per_batch * p.batch;
+
+  if (warp == 0 && lane == 0) {
+    tc::tma_prefetch_desc(&tmA);
+    tc::tma_prefetch_desc(&tmB);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int i = 0; i < C_::STAGES; ++i) { tc::mbar_init(&full[i], 1); tc::mbar_init(&empty[i], 1); }
+    for (int i = 0; i < 2; ++i) { tc::mbar_init(&tfull[i], 1); tc::mbar_init(&tempty[i], 128); }
+    tc::fence_barrier_init();
+  }
+  if (warp == 2) tc::tmem_alloc<C_::TMEM_COLS>(tmem_slot);
+  tc::tc_fence_before();
+  __syncthreads();
+  tc::tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0 && lane == 0) {
+    // ------------------------------------------------------------ TMA producer
+    uint32_t it = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      const int b = tile / tiles_per_batch, r = tile - b * tiles_per_batch;
+      const int m0 = (r / p.tiles_n) * BM, n0 = (r % p.tiles_n) * BN;
+      for (int kb = 0; kb < nkb; ++kb, ++it) {
+        const uint32_t s = it % C_::STAGES, ph = (it / C_::STAGES) & 1;
+        tc::mbar_wait(&empty[s], ph ^ 1);
+        tc::mbar_expect_tx(&full[s], C_::STAGE_BYTES);
+        uint8_t *sa = smem + s * C_::STAGE_BYTES, *sb = sa + C_::A_BYTES;
+        const int k0 = kb * BK;
+        if (A_MN) {
+#pragma unroll
+          for (int j = 0; j < BM / 64; ++j) tc::tma_load_3d(sa + j * (BK * 128), &tmA, &full[s], m0 + 64 * j, k0, b);
+        } else {
+          tc::tma_load_3d(sa, &tmA, &full[s], k0, m0, b);
+        }
+        if (B_MN) {
+#pragma unroll
+          for (int j = 0; j < BN / 64; ++j) tc::tma_load_3d(sb + j * (BK * 128), &tmB, &full[s], n0 + 64 * j, k0, b);
+        } else {
+          tc::tma_load_3d(sb, &tmB, &full[s], k0, n0, b);
+        }
+      }
+    }
+  } else if (warp == 1 && lane == 0) {
+    // ------------------------------------------------------------ MMA issuer
+    constexpr uint32_t idesc = tc::idesc_f16(BM, BN, A_MN ? 1u : 0u, B_MN ? 1u : 0u);
+    uint32_t it = 0, acc_it = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++acc_it) {
+      const uint32_t acc = acc_it & 1, acc_ph = (acc_it >> 1) & 1;
+      tc::mbar_wait(&tempty[acc], acc_ph ^ 1);
+      tc::tc_fence_after();
+      const uint32_t d_tmem = tmem_base + acc * BN;
+      for (int kb = 0; kb < nkb; ++kb, ++it) {
+        const uint32_t s = it % C_::STAGES, ph = (it / C_::STAGES) & 1;
+        tc::mbar_wait(&full[s], ph);
+        tc::tc_fence_after();
+        const uint32_t sa = tc::smem_u32(smem + s * C_::STAGE_BYTES), sb = sa + C_::A_BYTES;
+#pragma unroll
+        for (int k = 0; k < BK / UMMA_K; ++k) {
+          // K-major: 16 halves = 32 B further along the 128-B swizzled row; MN-major: 16 k-rows = 2048 B further
+          const uint64_t ad = A_MN ? tc::smem_desc_sw128(sa + k * (UMMA_K * 128), BK * 128, 1024)
+                                   : tc::smem_desc_sw128(sa + k * (UMMA_K * 2), 16, 1024);
+          const uint64_t bd = B_MN ? tc::smem_desc_sw128(sb + k * (UMMA_K * 128), BK * 128, 1024)
+                                   : tc::smem_desc_sw128(sb + k * (UMMA_K * 2), 16, 1024);
+          tc::mma_f16_ss(d_tmem, ad, bd, idesc, (kb | k) != 0);
+        }
+        tc::mma_commit(&empty[s]);      // slot free once these MMAs have read it
+      }
+      tc::mma_commit(&tfull[acc]);      // accumulator complete
+    }
+  } else if (warp >= 4) {
+    // ------------------------------------------------------------ epilogue (128 threads, thread = one row of the tile)
+    const int q = warp & 3;             // TMEM lane quarter this warp may access
+    uint32_t acc_it = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++acc_it) {
+      const int b = tile / tiles_per_batch, r = tile - b * tiles_per_batch;
+      const int m0 = (r / p.tiles_n) * BM, n0 = (r % p.tiles_n) * BN;
+      const uint32_t acc = acc_it & 1, acc_ph = (acc_it >> 1) & 1;
+      tc::mbar_wait(&tfull[acc], acc_ph);
+      tc::tc_fence_after();
+      const int m = m0 + q * 32 + lane;
+      const bool row_ok = m < p.M;
+#pragma unroll 1
+      for (int c = 0; c < BN / 32; ++c) {
+        uint32_t v[32];
+        tc::tmem_ld32(tmem_base + acc * BN + c * 32 + ((uint32_t)(q * 32) << 16), v);
+        tc::tmem_ld_wait();
+        const int n = n0 + c * 32;
+        if (row_ok && n < p.N) {
+          const bool full_chunk = (n + 32 <= p.N);
+          float f[32];
+#pragma unroll
+          for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]) * p.alpha;
+          if (p.bias) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) if (full_chunk || n + j < p.N) f[j] += __ldg(p.bias + n + j);
+          }
+          if (p.aux_out) {
+            __half *ao = p.aux_out + (long long)b * p.bsaux + (long long)m * p.ldaux + n;
+            if (full_chunk && ((reinterpret_cast<uintptr_t>(ao) & 15) == 0)) {
+#pragma unroll
+              for (int j = 0; j < 32; j += 8) {
+                __align__(16) __half2 h[4];
+#pragma unroll
+                for (int t = 0; t < 4; ++t) h[t] = __floats2half2_rn(f[j + 2 * t], f[j + 2 * t + 1]);
+                *reinterpret_cast<uint4 *>(ao + j) = *reinterpret_cast<uint4 *>(h);
+              }
+            } else {
+              _Pragma("unroll") for (int j = 0; j < 32; ++j) if (n + j < p.N) ao[j] = __float2half_rn(f[j]);
+            }
+          }
+          if (p.act == 1) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) f[j] = gelu_f(f[j]);
+          } else if (p.act == 2) {
+            const __half *ai = p.aux_in + (long long)b * p.bsaux + (long long)m * p.ldaux + n;
+            if (full_chunk && ((reinterpret_cast<uintptr_t>(ai) & 15) == 0)) {
+#pragma unroll
+              for (int j = 0; j < 32; j += 8) {
+                uint4 u = __ldg(reinterpret_cast<const uint4 *>(ai + j));
+                const __half2 *h = reinterpret_cast<const __half2 *>(&u);
+#pragma unroll
+                for (int t = 0; t < 4; ++t) {
+                  float2 x = __half22float2(h[t]);
+                  f[j + 2 * t] *= dgelu_f(x.x);
+                  f[j + 2 * t + 1] *= dgelu_f(x.y);
+                }
+              }
+            } else {
+              _Pragma("unroll") for (int j = 0; j < 32; ++j) if (n + j < p.N) f[j] *= dgelu_f(__half2float(ai[j]));
+            }
+          }
+          if (p.res) {
+            if (p.res_f32) {
+              const float *rp = reinterpret_cast<const float *>(p.res) + (long long)b * p.bsr + (long long)m * p.ldr + n;
+              if (full_chunk && ((reinterpret_cast<uintptr_t>(rp) & 15) == 0)) {
+#pragma unroll
+                for (int j = 0; j < 32; j += 4) {
+                  float4 x = *reinterpret_cast<const float4 *>(rp + j);
+                  f[j] += x.x; f[j + 1] += x.y; f[j + 2] += x.z; f[j + 3] += x.w;
+                }
+              } else {
+                _Pragma("unroll") for (int j = 0; j < 32; ++j) if (n + j < p.N) f[j] += rp[j];
+              }
+            } else {
+              const __half *rp = reinterpret_cast<const __half *>(p.res) + (long long)b * p.bsr + (long long)m * p.ldr + n;
+              if (full_chunk && ((reinterpret_cast<uintptr_t>(rp) & 15) == 0)) {
+#pragma unroll
+                for (int j = 0; j < 32; j += 8) {
+                  uint4 u = *reinterpret_cast<const uint4 *>(rp + j);
+                  const __half2 *h = reinterpret_cast<const __half2 *>(&u);
+#pragma unroll
+                  for (int t = 0; t < 4; ++t) {
+                    float2 x = __half22float2(h[t]);
+                    f[j + 2 * t] += x.x; f[j + 2 * t + 1] += x.y;
+                  }
+                }
+              } else {
+                _Pragma("unroll") for (int j = 0; j < 32; ++j) if (n + j < p.N) f[j] += __half2float(rp[j]);
+              }
+            }
+          }
+          if (p.c_f32) {
+            float *cp = reinterpret_cast<float *>(p.C) + (long long)b * p.bsc + (long long)m * p.ldc + n;
+            if (full_chunk && ((reinterpret_cast<uintptr_t>(cp) & 15) == 0)) {
+#pragma unroll
+              for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4 *>(cp + j) = make_float4(f[j], f[j + 1], f[j + 2], f[j + 3]);
+            } else {
+              _Pragma("unroll") for (int j = 0; j < 32; ++j) if (n + j < p.N) cp[j] = f[j];
+            }
+          } else {
+            __half *cp = reinterpret_cast<__half *>(p.C) + (long long)b * p.bsc + (long long)m * p.ldc + n;
+            if (full_chunk && ((reinterpret_cast<uintptr_t>(cp) & 15) == 0)) {
+#pragma unroll
+              for (int j = 0; j < 32; j += 8) {
+                __align__(16) __half2 h[4];
+#pragma unroll
+                for (int t = 0; t < 4; ++t) h[t] = __floats2half2_rn(f[j + 2 * t], f[j + 2 * t + 1]);
+                *reinterpret_cast<uint4 *>(cp + j) = *reinterpret_cast<uint4 *>(h);
+              }
+            } else {
+              _Pragma("unroll") for (int j = 0; j < 32; ++j) if (n + j < p.N) cp[j] = __float2half_rn(f[j]);
+            }
+          }
+        }
+      }
+      tc::tc_fence_before();
+      tc::mbar_arrive(&tempty[acc]);
+    }
+  }
+  tc::tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc::tc_fence_after();
+    tc::tmem_dealloc<C_::TMEM_COLS>(tmem_base);
+  }
+}
+
+template <int BN, bool A_MN, bool B_MN>
+int launch_gemm(const foho_gemm_desc *d, cudaStream_t st) {
+  using C_ = Cfg<BN>;
+  CUtensorMap tmA, tmB;
+  int rc;
+  // K-major: dims {K, rows, batch}, box {64, BM|BN}; MN-major: dims {rows, K, batch}, box {64, BK}
+  if (A_MN) rc = tc::make_tmap_f16(&tmA, d->A, d->M, d->K, d->batch, d->lda, d->bsa, BK);
+  else      rc = tc::make_tmap_f16(&tmA, d->A, d->K, d->M, d->batch, d->lda, d->bsa, BM);
+  if (rc) return rc;
+  if (B_MN) rc = tc::make_tmap_f16(&tmB, d->B, d->N, d->K, d->batch, d->ldb, d->bsb, BK);
+  else      rc = tc::make_tmap_f16(&tmB, d->B, d->K, d->N, d->batch, d->ldb, d->bsb, BN);
+  if (rc) return rc;
+  GemmParams p;
+  p.M = d->M; p.N = d->N; p.K = d->K; p.batch = d->batch;
+  p.tiles_m = (d->M + BM - 1) / BM; p.tiles_n = (d->N + BN - 1) / BN;
+  p.C = d->C; p.ldc = d->ldc; p.bsc = d->bsc; p.c_f32 = d->c_f32;
+  p.bias = d->bias;
+  p.res = d->res; p.ldr = d->ldr; p.bsr = d->bsr; p.res_f32 = d->res_f32;
+  p.aux_in = reinterpret_cast<const __half *>(d->aux_in); p.aux_out = reinterpret_cast<__half *>(d->aux_out);
+  p.ldaux = d->ldaux; p.bsaux = d->bsaux;
+  p.alpha = d->alpha; p.act = d->act;
+  static int sm_count = 0;
+  if (!sm_count) {
+    int dev = 0;
+    FOHO_CUDA_TRY(cudaGetDevice(&dev));
+    FOHO_CUDA_TRY(cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev));
+  }
+  FOHO_CUDA_TRY(cudaFuncSetAttribute(k_gemm_tc<BN, A_MN, B_MN>, cudaFuncAttributeMaxDynamicSharedMemorySize, C_::SMEM));
+  long long tiles = (long long)p.tiles_m * p.tiles_n * p.batch;
+  int grid = (int)(tiles < sm_count ? tiles : sm_count);
+  if (d->max_ctas > 0 && grid > d->max_ctas) grid = d->max_ctas;
+  k_gemm_tc<BN, A_MN, B_MN><<<grid, 256, C_::SMEM, st>>>(tmA, tmB, p);
+  FOHO_LAUNCH_CHECK();
+  return 0;
+}
+
+template <int BN>
+int dispatch_major(const foho_gemm_desc *d, cudaStream_t st) {
+  if (d->a_mn_major) return d->b_mn_major ? launch_gemm<BN, true, true>(d, st) : launch_gemm<BN, true, false>(d, st);
+  return d->b_mn_major ? launch_gemm<BN, false, true>(d, st) : launch_gemm<BN, false, false>(d, st);
+}
+
+}  // namespace
+
+extern "C" int foho_tc_gemm(const foho_gemm_desc *d, void *cuda_stream) {
+  if (!d || !d->A || !d->B || !d->C) return FOHO_E_NULL;
+  if (d->M <= 0 || d->N <= 0 || d->K <= 0 || d->batch <= 0) return FOHO_E_ARG;
+  if (d->act < 0 || d->act > 2 || (d->act == 2 && !d->aux_in)) return FOHO_E_ARG;
+  if (d->K % 8 || d->lda % 8 || d->ldb % 8) return FOHO_E_ARG;   // 16-byte TMA strides
+  if ((d->a_mn_major && d->M % 8) || (d->b_mn_major && d->N % 8)) return FOHO_E_ARG;
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(cuda_stream);
+  int bn = d->block_n;
+  if (bn == 0) bn = d->N > 128 ? 256 : (d->N > 64 ? 128 : 64);
+  switch (bn) {
+    case 64: return dispatch_major<64>(d, st);
+    case 128: return dispatch_major<128>(d, st);
+    case 256: return dispatch_major<256>(d, st);
+  }
+  return FOHO_E_ARG;
+}

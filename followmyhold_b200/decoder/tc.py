@@ -1,0 +1,85 @@
+"""Thin torch-tensor front of the tensor-core building blocks of the C-ABI (``foho_tc_gemm`` ...).
+
+Nothing here computes: it only fills descriptors with raw device pointers.  No CPU fallback."""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional
+
+import torch
+
+from .. import _lib
+
+ACT_NONE, ACT_GELU, ACT_DGELU = 0, 1, 2
+
+
+def _stream_ptr(stream: Optional[torch.cuda.Stream]) -> C.c_void_p:
+    s = stream if stream is not None else torch.cuda.current_stream()
+    return C.c_void_p(s.cuda_stream)
+
+
+def _rows(t: torch.Tensor):
+    """(batch, rows, cols, ld, batch_stride) of a 2-D or 3-D tensor whose last dim is contiguous."""
+    if t.dim() == 2:
+        t = t.unsqueeze(0)
+    if t.dim() != 3 or t.stride(2) != 1:
+        raise ValueError("operand must be [rows, cols] or [batch, rows, cols] with a contiguous last dimension")
+    return t.shape[0], t.shape[1], t.shape[2], t.stride(1), (t.stride(0) if t.shape[0] > 1 else 0)
+
+
+def gemm(a: torch.Tensor, b: torch.Tensor, out: Optional[torch.Tensor] = None, *, a_mn: bool = False, b_mn: bool = False,
+         bias: Optional[torch.Tensor] = None, act: int = ACT_NONE, res: Optional[torch.Tensor] = None,
+         aux_in: Optional[torch.Tensor] = None, aux_out: Optional[torch.Tensor] = None, alpha: float = 1.0,
+         out_dtype: torch.dtype = torch.float16, block_n: int = 0, max_ctas: int = 0,
+         stream: Optional[torch.cuda.Stream] = None) -> torch.Tensor:
+    """``out[b] = res[b] + act(alpha * A[b] @ B[b]^T + bias)`` on the tensor cores (fp16 operands, fp32 accumulate).
+
+    ``a``: [.., M, K] (or [.., K, M] when ``a_mn``); ``b``: [.., N, K] -- the ``nn.Linear`` weight layout -- (or
+    [.., K, N] when ``b_mn``).  Batched operands may be strided views (e.g. one attention head of a
+    [tokens, heads*64] tensor) as long as the last dimension is contiguous."""
+    lib = _lib.load()
+    if a.dtype != torch.float16 or b.dtype != torch.float16 or not a.is_cuda:
+        raise ValueError("tensor-core GEMM operands must be CUDA float16 tensors")
+    ba, ra, ca, lda, bsa = _rows(a)
+    bb, rb, cb, ldb, bsb = _rows(b)
+    M, K = (ca, ra) if a_mn else (ra, ca)
+    N, Kb = (cb, rb) if b_mn else (rb, cb)
+    if K != Kb:
+        raise ValueError(f"inner dimensions differ: {K} vs {Kb}")
+    batch = max(ba, bb)
+    if (ba not in (1, batch)) or (bb not in (1, batch)):
+        raise ValueError("batch sizes differ")
+    if out is None:
+        out = torch.empty((batch, M, N) if (a.dim() == 3 or b.dim() == 3) else (M, N), dtype=out_dtype, device=a.device)
+    bo, ro, co, ldc, bsc = _rows(out)
+    if (ro, co) != (M, N) or bo != batch:
+        raise ValueError("output shape mismatch")
+    d = _lib.GemmDesc()
+    d.M, d.N, d.K, d.batch = M, N, K, batch
+    d.a_mn_major, d.b_mn_major = int(a_mn), int(b_mn)
+    d.c_f32 = int(out.dtype == torch.float32)
+    d.act, d.block_n, d.max_ctas, d.alpha = act, block_n, max_ctas, alpha
+    d.A, d.lda, d.bsa = a.data_ptr(), lda, bsa
+    d.B, d.ldb, d.bsb = b.data_ptr(), ldb, bsb
+    d.C, d.ldc, d.bsc = out.data_ptr(), ldc, bsc
+    if bias is not None:
+        if bias.dtype != torch.float32 or bias.numel() != N:
+            raise ValueError("bias must be float32 [N]")
+        d.bias = bias.data_ptr()
+    if res is not None:
+        br, rr, cr, ldr, bsr = _rows(res)
+        if (rr, cr) != (M, N):
+            raise ValueError("residual shape mismatch")
+        d.res, d.ldr, d.bsr, d.res_f32 = res.data_ptr(), ldr, bsr, int(res.dtype == torch.float32)
+    for t in (aux_in, aux_out):
+        if t is not None:
+            bx, rx, cx, ldx, bsx = _rows(t)
+            if (rx, cx) != (M, N) or t.dtype != torch.float16:
+                raise ValueError("aux tensors must be float16 [.., M, N]")
+            d.ldaux, d.bsaux = ldx, bsx
+    if aux_in is not None:
+        d.aux_in = aux_in.data_ptr()
+    if aux_out is not None:
+        d.aux_out = aux_out.data_ptr()
+    _lib.check("foho_tc_gemm", lib.foho_tc_gemm(C.byref(d), _stream_ptr(stream)))
+    return out

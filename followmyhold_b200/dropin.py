@@ -19,9 +19,15 @@ Side effect to know about: importing the package sets ``CUDA_DEVICE_MAX_CONNECTI
 (``followmyhold_b200/__init__.py``), so with the ``.pth`` line every interpreter of that environment starts
 with 32 hardware work queues instead of 8; export the variable yourself to keep another value.
 
-``FOHO_B200_DROPIN=0`` switches the redirect off (A/B runs against the reference stages).  The guidance stage
-additionally needs the Hunyuan3D networks wrapped in a ``GuidanceModel`` named by ``FOHO_B200_GUIDANCE_MODEL``
-(guidance/run.py); without one it fails loudly.
+``FOHO_B200_DROPIN=0`` switches the redirect off (A/B runs against the reference stages).
+
+The two alignment stages are redirected by default: they compute what the reference computes (golden-pinned
+ICP).  The guidance stage is redirected ONLY with ``FOHO_B200_DROPIN_GUIDANCE=1``: its energy is not the
+reference's yet -- the rendered normal / disparity / silhouette terms (pipelines.py:1339-1349,1566-1588) are
+absent, chamfer and volume terms stand in for them -- so its outputs are not comparable with the reference's
+although the file names match, and swapping it silently would be wrong.  It additionally needs the Hunyuan3D
+networks wrapped in a ``GuidanceModel`` named by ``FOHO_B200_GUIDANCE_MODEL`` (guidance/run.py); without one
+it fails loudly.
 """
 from __future__ import annotations
 
@@ -41,15 +47,22 @@ PTH_NAME = "foho_b200_dropin.pth"
 PTH_LINE = "import followmyhold_b200.dropin as _foho_b200_dropin; _foho_b200_dropin.install()"
 
 
-def enabled() -> bool:
-    return os.environ.get("FOHO_B200_DROPIN", "1") not in ("0", "false", "False", "")
+OPT_IN = {"foho.guidance.run": "FOHO_B200_DROPIN_GUIDANCE"}       # redirected only when this variable is truthy
+_OFF = ("0", "false", "False", "")
+
+
+def enabled(fullname: Optional[str] = None) -> bool:
+    if os.environ.get("FOHO_B200_DROPIN", "1") in _OFF:
+        return False
+    var = OPT_IN.get(fullname) if fullname else None
+    return var is None or os.environ.get(var, "0") not in _OFF
 
 
 class StageRedirect(importlib.abc.MetaPathFinder):
     """Resolves the three stage modules to their shims; declines everything else."""
 
     def find_spec(self, fullname, path=None, target=None):
-        if fullname not in REDIRECTS or not enabled():
+        if fullname not in REDIRECTS or not enabled(fullname):
             return None
         shim = os.path.join(_SHIM_DIR, fullname.replace(".", "_") + ".py")
         return importlib.util.spec_from_file_location(fullname, shim)

@@ -146,12 +146,16 @@ class GuidanceLoop:
         """Which optimisation the reference runs at denoise step ``i`` (pipelines.py:1293-1295,1361,1455):
         0 = none (plain scheduler.step), 1 = hand only, 1.5 = object only, 2 = joint."""
         c = self.cfg
-        if step_index < c.handopt_start_step or step_index > c.guidance_end_step:
+        # the reference gates the hand-only and object-only steps on `i >= handopt_start_step` alone
+        # (pipelines.py:1293-1361); guidance_end_step bounds the joint phase only (:1455)
+        if step_index < c.handopt_start_step:
             return 0
         if step_index == c.handopt_start_step:
             return 1
         if step_index == c.handopt_start_step + 1:
             return 1.5
+        if step_index > c.guidance_end_step:
+            return 0
         return 2
 
     def phase_iterations(self, phase: float) -> int:
@@ -333,8 +337,15 @@ class GuidanceLoop:
         with torch.cuda.device(self.device):
             s = self.stream
             s.wait_stream(torch.cuda.current_stream(self.device))
+            cur = torch.cuda.current_stream(self.device)
             for i in range(first_step, last + 1):
+                # the prediction runs on the ambient stream and reads x_t, which step i-1's graph and copy (on
+                # `s`) wrote: order the two streams both ways, and keep v's memory alive for `s`
+                cur.wait_stream(s)
                 v = model_output(i, self.x_t) if callable(model_output) else model_output[i]
+                s.wait_stream(cur)
+                if v.is_cuda:
+                    v.record_stream(s)
                 with torch.cuda.stream(s):
                     self.velocity.copy_(v)
                     phase = self.phase_of_step(i)

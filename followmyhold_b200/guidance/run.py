@@ -26,7 +26,7 @@ import argparse
 import importlib
 import json
 import os
-from typing import List, Optional, Sequence, Tuple
+from typing import Dict, List, Optional, Sequence, Tuple
 
 import numpy as np
 import torch
@@ -181,7 +181,7 @@ def run(
     model: Optional[GuidanceModel] = None,
     batch_size: int = 8,
     n_cloud: int = 65536,
-    device: str = "cuda:0",
+    device: Optional[str] = None,
     config: Optional[OptimizationConfig] = None,
     j_regressor_path: str = J_REGRESSOR_PATH,
     seed: int = 2,
@@ -223,17 +223,49 @@ def run(
     J = torch.as_tensor(np.asarray(J), dtype=torch.float32).reshape(16, -1)
 
     from .loop import GuidanceLoop
-    dev = torch.device(device)
-    for b0 in range(0, len(todo), batch_size):
-        chunk = todo[b0:b0 + batch_size]
+    dev = torch.device(device if device is not None else f"cuda:{int(os.environ.get('LOCAL_RANK', '0'))}")
+    for chunk in batches_of_compatible_images(todo, batch_size):
         idx = [p["index"] for p, _ in chunk]
         try:
             _run_batch(chunk, model, J, config, n_cloud, dev, seed, GuidanceLoop)
             for i in idx:
                 print(f"Reconstructed object {i}")
         except Exception as e:
-            print(f"Error in reconstruction for {idx} : {e}")
+            if len(chunk) == 1:
+                print(f"Error in reconstruction for {idx} : {e}")
+                continue
+            # one bad image must not take its batch mates with it (the reference works image by image,
+            # run.py:208-259): retry them one at a time
+            print(f"Error in reconstruction for batch {idx} : {e}; retrying its images one by one")
+            for item in chunk:
+                try:
+                    _run_batch([item], model, J, config, n_cloud, dev, seed, GuidanceLoop)
+                    print(f"Reconstructed object {item[0]['index']}")
+                except Exception as e1:
+                    print(f"Error in reconstruction for {item[0]['index']} : {e1}")
     print("Finished processing all images")
+
+
+def batch_key(inp: dict) -> tuple:
+    """Images that may share one batched launch: the kernels take ONE camera (fov, crop size) and ONE hand
+    topology per batch.  MoGe estimates fov_x per image (geometry/moge.py:126-131), crops differ, and left hands
+    come with flipped winding, so real image sets are heterogeneous: group first, never assume."""
+    import hashlib
+    f = np.ascontiguousarray(inp["faces"], dtype=np.int32)
+    return (tuple(int(x) for x in inp["hw"]), round(float(inp["fovx"]), 6), f.shape[0], hashlib.sha1(f.tobytes()).hexdigest())
+
+
+def batches_of_compatible_images(todo: list, batch_size: int) -> List[list]:
+    """Split ``todo`` [(paths, inputs)] into batches of at most ``batch_size`` images with equal ``batch_key``,
+    keeping the sorted image order inside every group; singletons become batches of one."""
+    groups: Dict[tuple, list] = {}
+    for item in todo:
+        groups.setdefault(batch_key(item[1]), []).append(item)
+    out = []
+    for items in groups.values():
+        for b0 in range(0, len(items), max(1, int(batch_size))):
+            out.append(items[b0:b0 + batch_size])
+    return out
 
 
 def _run_batch(chunk, model: GuidanceModel, J: torch.Tensor, config: OptimizationConfig, n_cloud: int, dev, seed: int,
@@ -299,7 +331,6 @@ def _run_batch(chunk, model: GuidanceModel, J: torch.Tensor, config: Optimizatio
             continue
         hand = inp["hand_moge"].astype(np.float64)
         ch = (hand.min(0) + hand.max(0)) / 2.0
-        write_ply(p["save_path_hand"], similarity_about(hand, theta[b, :8], ch), inp["faces"])
         verts, faces = model.extract_mesh(sdf[b])
         T = inp["T_h2m"].astype(np.float64)
         try:                                                               # run.py:155-167
@@ -310,9 +341,15 @@ def _run_batch(chunk, model: GuidanceModel, J: torch.Tensor, config: Optimizatio
             if len(obj.vertices) == 0:
                 print(f"Empty mesh for {p['cropped_obj_img_path']}")      # run.py:170-172
                 continue
+            # object first, hand only once the object is on disk (run.py:168-175): a failed object must not
+            # leave a hand-only output behind
             write_ply(p["save_path_obj"], obj.vertices, obj.faces)
+            write_ply(p["save_path_hand"], similarity_about(hand, theta[b, :8], ch), inp["faces"])
         except Exception:
             print(f"Error in saving mesh for {p['cropped_obj_img_path']}")
+            for k in ("save_path_obj", "save_path_hand"):
+                if os.path.exists(p[k]):
+                    os.remove(p[k])
             continue
 
 

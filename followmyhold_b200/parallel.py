@@ -12,9 +12,20 @@ import torch.distributed as dist
 
 
 def rank_world():
+    """(rank, world) this process shards its images by.  An initialised process group wins; otherwise the
+    RANK / WORLD_SIZE variables count only when the process was started by torchrun (TORCHELASTIC_RUN_ID) or
+    sharding was asked for explicitly (FOHO_B200_SHARD=1) -- a stray RANK inherited from the environment
+    ``foho.main`` runs in must not make a stage silently skip images."""
     if dist.is_available() and dist.is_initialized():
         return dist.get_rank(), dist.get_world_size()
-    return int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1"))
+    if "TORCHELASTIC_RUN_ID" in os.environ or os.environ.get("FOHO_B200_SHARD", "0") not in ("0", "", "false", "False"):
+        return int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1"))
+    return 0, 1
+
+
+def default_device() -> str:
+    """One process per GPU: ``cuda:$LOCAL_RANK`` (cuda:0 outside torchrun)."""
+    return f"cuda:{int(os.environ.get('LOCAL_RANK', '0'))}"
 
 
 def shard_images(images: Sequence[str], rank: int, world: int) -> List[str]:

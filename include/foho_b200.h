@@ -30,13 +30,14 @@
 extern "C" {
 #endif
 
-#define FOHO_ABI_VERSION 4
+#define FOHO_ABI_VERSION 5
 
 #define FOHO_OK 0
 #define FOHO_E_NULL (-1)      /* required pointer is NULL            */
 #define FOHO_E_SHAPE (-2)     /* size out of the supported range     */
 #define FOHO_E_WORKSPACE (-3) /* workspace too small / misaligned    */
 #define FOHO_E_ARG (-4)       /* other invalid scalar argument       */
+#define FOHO_E_DRIVER (-5)    /* cuTensorMapEncodeTiled unavailable / rejected the tensor map */
 
 /* indices into the per-sample `terms` output of foho_guidance_energy_fwd_bwd */
 enum {
@@ -281,6 +282,38 @@ int foho_intersection_count(const float *sdf_hand, const float *sdf_obj, int64_t
 int foho_mesh_decimate(const double *verts, int32_t V, const int32_t *faces, int32_t F, int32_t target_faces,
                        double boundary_weight, double *out_verts, int32_t *out_V, int32_t *out_faces,
                        int32_t *out_F);
+
+/* ---------------------------------------------------------------------------------------------
+ * Row f1: latent -> SDF decode (third_party_patches/hy3dgen/shapegen/pipelines.py:292-312 `latent2sdf`,
+ * call sites :1392,1508,1641).  The dense contractions run on the 5th-generation tensor cores
+ * (tcgen05.mma, TMEM accumulators, TMA operand tiles); everything is fp16 operands / fp32 accumulation,
+ * the reference's own dtype (`vae` is fp16, pipelines.py:302-306).
+ * --------------------------------------------------------------------------------------------- */
+
+/* One (batched) tensor-core GEMM with a fused epilogue -- the building block every nn.Linear of the
+ * decoder and every attention product of its adjoint goes through:
+ *     C[b][m][n] = res[b][m][n] + act( alpha * sum_k A[b](m,k) B[b](n,k) + bias[n] )
+ * A is [M,K] and B is [N,K] (the nn.Linear weight layout) when K-major; an MN-major operand is stored
+ * [K,M] / [K,N] instead (row = k).  Leading dimensions and batch strides in ELEMENTS; operands fp16,
+ * 16-byte aligned, lda/ldb/K multiples of 8.  act: 0 none, 1 GELU (erf), 2 multiply by GELU'(aux_in[m][n])
+ * (the backward of act 1).  aux_out (optional, fp16) receives the pre-activation value. */
+typedef struct foho_gemm_desc {
+  int32_t M, N, K, batch;
+  int32_t a_mn_major, b_mn_major;
+  int32_t c_f32;             /* C is float32 (else fp16)                                    */
+  int32_t res_f32;           /* res is float32 (else fp16)                                  */
+  int32_t act;
+  int32_t block_n;           /* 0 = choose; 64 / 128 / 256 columns per CTA tile             */
+  int32_t max_ctas;          /* 0 = one persistent CTA per SM                               */
+  float alpha;
+  const void *A; int64_t lda, bsa;
+  const void *B; int64_t ldb, bsb;
+  void *C; int64_t ldc, bsc;
+  const float *bias;         /* device [N] float32 or NULL                                   */
+  const void *res; int64_t ldr, bsr;     /* NULL = none; may alias C (in-place accumulate)  */
+  const void *aux_in; void *aux_out; int64_t ldaux, bsaux;
+} foho_gemm_desc;
+int foho_tc_gemm(const foho_gemm_desc *desc, void *cuda_stream);
 
 #ifdef __cplusplus
 }

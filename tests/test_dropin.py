@@ -47,8 +47,11 @@ def test_python_dash_m_runs_the_mirror_and_leaves_other_modules_alone(fake_refer
     assert r.stdout.strip() == "REFERENCE alignment/h2m"
     code = ("import foho.guidance.run as g, foho.alignment.mano as m, foho.utils.runner as u;"
             "print(g.run.__module__, m.run.__module__, u.run())")
-    r = _run(["-c", code], src, site)
+    r = _run(["-c", code], src, site, FOHO_B200_DROPIN_GUIDANCE="1")
     assert r.stdout.split() == ["followmyhold_b200.guidance.run", "followmyhold_b200.alignment.mano", "REFERENCE"], r.stderr
+    # the guidance stage optimises a different energy from the reference's: it is redirected on opt-in only
+    r = _run(["-c", code], src, site)
+    assert r.stdout.split() == ["foho.guidance.run", "followmyhold_b200.alignment.mano", "REFERENCE"], r.stderr
 
 
 def test_install_is_idempotent_and_pth_file(tmp_path):
@@ -58,12 +61,15 @@ def test_install_is_idempotent_and_pth_file(tmp_path):
         assert sum(isinstance(f, dropin.StageRedirect) for f in sys.meta_path) == 1
         f = dropin.StageRedirect()
         assert f.find_spec("foho.main") is None and f.find_spec("foho.guidance") is None
+        assert f.find_spec("foho.guidance.run") is None                   # opt-in only
+        os.environ["FOHO_B200_DROPIN_GUIDANCE"] = "1"
         spec = f.find_spec("foho.guidance.run")
         assert spec is not None and spec.origin.endswith("_shims/foho_guidance_run.py") and os.path.exists(spec.origin)
         os.environ["FOHO_B200_DROPIN"] = "0"
         assert f.find_spec("foho.guidance.run") is None and dropin.install() is False
     finally:
         os.environ.pop("FOHO_B200_DROPIN", None)
+        os.environ.pop("FOHO_B200_DROPIN_GUIDANCE", None)
         dropin.uninstall()
         assert sys.meta_path == before
     p = dropin.write_pth(str(tmp_path))

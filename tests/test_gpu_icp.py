@@ -148,9 +148,9 @@ def test_batched_sharded_alignment_stage_equals_one_image_at_a_time(tmp_path, mo
     # batched (all three in one group), and rank 1 of 2 (only image "07")
     h2m.run(str(hun), str(tmp_path / "moge"), str(tmp_path / "rt"), concurrent=3)
     mano.run(str(ham), str(hun), str(tmp_path / "aligned"), concurrent=2)
-    monkeypatch.setenv("RANK", "1"); monkeypatch.setenv("WORLD_SIZE", "2")
+    monkeypatch.setenv("RANK", "1"); monkeypatch.setenv("WORLD_SIZE", "2"); monkeypatch.setenv("FOHO_B200_SHARD", "1")
     h2m.run(str(hun), str(tmp_path / "moge"), str(tmp_path / "rt_rank1"))
-    monkeypatch.delenv("RANK"); monkeypatch.delenv("WORLD_SIZE")
+    monkeypatch.delenv("RANK"); monkeypatch.delenv("WORLD_SIZE"); monkeypatch.delenv("FOHO_B200_SHARD")
     assert sorted(p.name for p in (tmp_path / "rt_rank1").iterdir()) == ["07_hoi_mesh.npy"]
     for i in ids:
         ref = align_meshes_impl(str(hun / f"{i}_hoi_mesh.ply"), str(tmp_path / "moge" / f"{i}_cropped_hoi" / "pointcloud.ply"),

@@ -338,10 +338,10 @@ def test_alignment_stage_glue_on_files_with_the_oracle_loop(tmp_path, monkeypatc
         assert got.dtype == np.float64 and np.array_equal(got, ref)
         assert 0.3 < np.linalg.norm(got[:3, 0]) < 0.5                                 # the 0.4x similarity is recovered
     # rank 1 of 2 aligns only its share; a frame without MoGe geometry is reported and skipped
-    monkeypatch.setenv("RANK", "1"); monkeypatch.setenv("WORLD_SIZE", "2")
+    monkeypatch.setenv("RANK", "1"); monkeypatch.setenv("WORLD_SIZE", "2"); monkeypatch.setenv("FOHO_B200_SHARD", "1")
     h2m.run(str(hun), str(tmp_path / "moge"), str(tmp_path / "rt1"))
     assert os.listdir(tmp_path / "rt1") == ["09_hoi_mesh.npy"]
-    monkeypatch.delenv("RANK"); monkeypatch.delenv("WORLD_SIZE")
+    monkeypatch.delenv("RANK"); monkeypatch.delenv("WORLD_SIZE"); monkeypatch.delenv("FOHO_B200_SHARD")
     import shutil
     shutil.rmtree(tmp_path / "moge" / "04_cropped_hoi")
     capsys.readouterr()
