@@ -17,7 +17,7 @@ REPO_ROOT = PKG_DIR.parent
 CSRC = PKG_DIR / "csrc"
 LIB_PATH = PKG_DIR / "libfoho_b200.so"
 SOURCES = ["guidance_stream.cu", "guidance_sparse.cu", "guidance_objmesh.cu", "guidance_chamfer.cu", "guidance_voxdist.cu", "guidance_update.cu", "icp.cu",
-           "mesh_sdf.cu", "mesh_decimate.cu", "decoder_gemm.cu"]
+           "mesh_sdf.cu", "mesh_decimate.cu", "decoder_gemm.cu", "decoder_attn.cu", "decoder_ops.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "-Xcompiler", "-fPIC", "-Xcompiler", "-O3"]
 
@@ -34,7 +34,9 @@ EXPORTED_SYMBOLS = [
     "foho_scheduler_step", "foho_scheduler_step_f16", "foho_mock_decoder_forward", "foho_mock_decoder_backward",
     "foho_icp_workspace_bytes", "foho_icp_run",
     "foho_mesh2sdf_workspace_bytes", "foho_mesh2sdf_lattice", "foho_intersection_count", "foho_mesh_decimate",
-    "foho_tc_gemm",
+    "foho_tc_gemm", "foho_tc_attention",
+    "foho_dec_layernorm", "foho_dec_layernorm_bwd", "foho_dec_softmax", "foho_dec_softmax_bwd", "foho_dec_fourier_embed",
+    "foho_dec_head", "foho_dec_head_bwd", "foho_dec_gather_rows", "foho_dec_cast",
 ]
 
 
@@ -144,6 +146,17 @@ class GemmDesc(C.Structure):
     ]
 
 
+class AttnDesc(C.Structure):
+    _fields_ = [
+        ("n_img", C.c_int32), ("heads", C.c_int32), ("n_q", C.c_int32), ("n_k", C.c_int32),
+        ("q_shared", C.c_int32), ("max_ctas", C.c_int32), ("scale", C.c_float), ("reserved", C.c_int32),
+        ("q", C.c_void_p), ("ldq", C.c_int64), ("hsq", C.c_int64),
+        ("k", C.c_void_p), ("ldk", C.c_int64), ("hsk", C.c_int64),
+        ("v", C.c_void_p), ("ldv", C.c_int64), ("hsv", C.c_int64),
+        ("out", C.c_void_p), ("ldo", C.c_int64), ("out_img_stride", C.c_int64),
+    ]
+
+
 _lib: Optional[C.CDLL] = None
 
 
@@ -213,6 +226,20 @@ def load(build_if_missing: bool = False) -> C.CDLL:
                                        C.POINTER(C.c_int32), C.c_void_p, C.POINTER(C.c_int32)]
     lib.foho_tc_gemm.restype = C.c_int
     lib.foho_tc_gemm.argtypes = [C.POINTER(GemmDesc), C.c_void_p]
+    lib.foho_tc_attention.restype = C.c_int
+    lib.foho_tc_attention.argtypes = [C.POINTER(AttnDesc), C.c_void_p]
+    vp, i32, i64, f32 = C.c_void_p, C.c_int32, C.c_int64, C.c_float
+    lib.foho_dec_layernorm.argtypes = [vp, i32, i64, i64, vp, vp, f32, vp, i32, i64, i64, i64, i32, vp]
+    lib.foho_dec_layernorm_bwd.argtypes = [vp, i32, i64, i64, vp, f32, vp, i32, i64, i64, vp, vp, i32, i64, i64, i64, i32, vp]
+    lib.foho_dec_softmax.argtypes = [vp, vp, i64, i32, vp]
+    lib.foho_dec_softmax_bwd.argtypes = [vp, vp, vp, i64, i32, f32, vp]
+    lib.foho_dec_fourier_embed.argtypes = [vp, vp, i64, i32, i32, i32, vp]
+    lib.foho_dec_head.argtypes = [vp, i64, vp, vp, f32, vp, f32, vp, vp, i64, vp]
+    lib.foho_dec_head_bwd.argtypes = [vp, i64, vp, f32, vp, vp, vp, f32, vp, i64, i64, vp]
+    lib.foho_dec_gather_rows.argtypes = [vp, i64, vp, vp, i64, i64, i32, vp]
+    lib.foho_dec_cast.argtypes = [vp, vp, i64, f32, i32, vp]
+    for _n in ("layernorm", "layernorm_bwd", "softmax", "softmax_bwd", "fourier_embed", "head", "head_bwd", "gather_rows", "cast"):
+        getattr(lib, "foho_dec_" + _n).restype = C.c_int
     if lib.foho_abi_version() != ABI_VERSION:
         raise FohoLibraryError("libfoho_b200.so ABI version mismatch; rebuild it")
     _lib = lib

@@ -83,3 +83,30 @@ def gemm(a: torch.Tensor, b: torch.Tensor, out: Optional[torch.Tensor] = None, *
         d.aux_out = aux_out.data_ptr()
     _lib.check("foho_tc_gemm", lib.foho_tc_gemm(C.byref(d), _stream_ptr(stream)))
     return out
+
+
+def attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, n_img: int, out: Optional[torch.Tensor] = None, *,
+              q_shared: bool = False, scale: float = 0.125, max_ctas: int = 0,
+              stream: Optional[torch.cuda.Stream] = None) -> torch.Tensor:
+    """``out[i, q, h, :] = softmax_k(scale * Q[q, h] . K[i, k, h]) V[i, k, h]`` on the tensor cores.
+
+    ``q``: [n_q (shared) or n_img*n_q, heads, 64]; ``k``, ``v``: [n_img*n_k, heads, 64] -- strided views of the
+    fused projections are fine (last dimension contiguous).  Returns fp16 [n_img, n_q, heads*64]."""
+    lib = _lib.load()
+    for t in (q, k, v):
+        if t.dtype != torch.float16 or not t.is_cuda or t.dim() != 3 or t.shape[2] != 64 or t.stride(2) != 1:
+            raise ValueError("q, k, v must be CUDA float16 [rows, heads, 64] views with a contiguous last dimension")
+    heads = q.shape[1]
+    n_q = q.shape[0] if q_shared else q.shape[0] // n_img
+    n_k = k.shape[0] // n_img
+    if out is None:
+        out = torch.empty(n_img, n_q, heads * 64, dtype=torch.float16, device=q.device)
+    d = _lib.AttnDesc()
+    d.n_img, d.heads, d.n_q, d.n_k = n_img, heads, n_q, n_k
+    d.q_shared, d.max_ctas, d.scale = int(q_shared), max_ctas, scale
+    d.q, d.ldq, d.hsq = q.data_ptr(), q.stride(0), q.stride(1)
+    d.k, d.ldk, d.hsk = k.data_ptr(), k.stride(0), k.stride(1)
+    d.v, d.ldv, d.hsv = v.data_ptr(), v.stride(0), v.stride(1)
+    d.out, d.ldo, d.out_img_stride = out.data_ptr(), out.stride(1), out.stride(0)
+    _lib.check("foho_tc_attention", lib.foho_tc_attention(C.byref(d), _stream_ptr(stream)))
+    return out

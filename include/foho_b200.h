@@ -315,6 +315,53 @@ typedef struct foho_gemm_desc {
 } foho_gemm_desc;
 int foho_tc_gemm(const foho_gemm_desc *desc, void *cuda_stream);
 
+/* Attention forward on the tensor cores (head dimension 64, no mask):
+ *     O[i][q][h*64 + :] = softmax_k( scale * Q[q][h] . K[i][k][h] ) V[i][k][h]
+ * the cross attention of the lattice queries onto the latent tokens (hy3dgen geo_decoder, called at
+ * pipelines.py:304) and the self attention of the ShapeVAE transformer (pipelines.py:299).  Q, K, V are fp16
+ * row-major with leading dimensions ld* (elements) and head h at column offset h*hs* -- so the fused
+ * [tokens, heads, (q|k|v)] projections are read in place.  q holds n_q rows when q_shared (one lattice for all
+ * images), else n_img*n_q rows; k, v hold n_img*n_k rows; n_k must be a multiple of 128. */
+typedef struct foho_attn_desc {
+  int32_t n_img, heads, n_q, n_k;
+  int32_t q_shared;
+  int32_t max_ctas;          /* 0 = one persistent CTA per SM */
+  float scale;               /* 1/sqrt(64) = 0.125 */
+  int32_t reserved;
+  const void *q; int64_t ldq, hsq;
+  const void *k; int64_t ldk, hsk;
+  const void *v; int64_t ldv, hsv;
+  void *out; int64_t ldo, out_img_stride;   /* fp16 [n_img][n_q][heads*64], 16-byte aligned */
+} foho_attn_desc;
+int foho_tc_attention(const foho_attn_desc *desc, void *cuda_stream);
+
+/* Row-wise kernels of the decoder (HBM-bound; fp16 activations, fp32 arithmetic; every pointer device memory).
+ * A "row view" addresses row r of a [outer, inner, width] tensor at base + (r / inner)*ldo + (r % inner)*ldi
+ * (elements), so the per-head q_norm / k_norm (width 64) read the fused projections in place. */
+int foho_dec_layernorm(const void *x, int32_t inner_x, int64_t ldo_x, int64_t ldi_x, const float *w, const float *b, float eps,
+                       void *y, int32_t inner_y, int64_t ldo_y, int64_t ldi_y, int64_t rows, int32_t width /* 64 | 1024 */,
+                       void *cuda_stream);
+/* dx = dLN/dx^T dy (+ add): weights are frozen, only the input gradient exists */
+int foho_dec_layernorm_bwd(const void *x, int32_t inner_x, int64_t ldo_x, int64_t ldi_x, const float *w, float eps, const void *dy,
+                           int32_t inner_dy, int64_t ldo_dy, int64_t ldi_dy, const void *add, void *dx, int32_t inner_dx,
+                           int64_t ldo_dx, int64_t ldi_dx, int64_t rows, int32_t width, void *cuda_stream);
+/* materialised attention of the adjoint: P = softmax(S) (S float32, P fp16); dS = scale * P o (dP - rowsum(P o dP)) */
+int foho_dec_softmax(const float *S, void *P, int64_t rows, int32_t T, void *cuda_stream);
+int foho_dec_softmax_bwd(const void *P, const float *dP, void *dS, int64_t rows, int32_t T, float scale, void *cuda_stream);
+/* hy3dgen FourierEmbedder: [x, sin(x 2^k), cos(x 2^k)] of fp16-rounded coordinates -> fp16 [n, ld], padding zeroed */
+int foho_dec_fourier_embed(const float *xyz, void *out, int64_t n, int32_t ld, int32_t num_freqs, int32_t include_pi, void *cuda_stream);
+/* sdf[idx ? idx[r] : r] = -(w_out . ln_post(x[r]) + b_out): the last two modules of geo_decoder, the float cast and the
+ * sign flip of pipelines.py:309-312 */
+int foho_dec_head(const void *x, int64_t ldx, const float *ln_w, const float *ln_b, float eps, const float *w_out, float b_out,
+                  const int32_t *idx, float *out, int64_t rows, void *cuda_stream);
+/* its backward for the rows that carry a gradient: dx[r] = d(-logit)/dx * g_scale * dS[idx ? idx[r] : r] */
+int foho_dec_head_bwd(const void *x, int64_t ldx, const float *ln_w, float eps, const float *w_out, const int32_t *idx, const float *dS,
+                      float g_scale, void *dx, int64_t lddx, int64_t rows, void *cuda_stream);
+int foho_dec_gather_rows(const void *in, int64_t ld_in, const int32_t *idx, void *out, int64_t ld_out, int64_t rows, int32_t width,
+                         void *cuda_stream);
+/* mode 0: f32 -> f16 (x scale); 1: f16 -> f32 (x scale); 2: f16 -> f32 accumulate; 3: out += in (fp16) */
+int foho_dec_cast(const void *in, void *out, int64_t n, float scale, int32_t mode, void *cuda_stream);
+
 #ifdef __cplusplus
 }
 #endif
