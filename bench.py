@@ -98,64 +98,131 @@ def measured_peak_gbs():
 
 
 # --------------------------------------------------------------------------- CPU arm
-def cpu_guidance_evals_per_sec(seconds_budget: float = 20.0, threads: int = 0, n_min: int = 2):
-    """Time the CPU oracle (the restated reference arithmetic; the reference itself cannot be
-    imported offline) on ONE sample of the bench workload (D=256, P=65 536):
-    forward + backward + AdamW on the 16 leaves, all host threads."""
-    import torch
-    from followmyhold_b200.synthetic import make_guidance_sample
-    from oracle import guidance_oracle as O
-    cores = threads or (os.cpu_count() or 1)
-    torch.set_num_threads(cores)
-    s = make_guidance_sample(D, P, seed=0)
-    th = torch.cat([s.theta_h, s.theta_o]).clone()
-    m = torch.zeros(16); v = torch.zeros(16)
-    n, t0 = 0, time.perf_counter()
-    while True:
-        sdf = s.sdf.clone().requires_grad_(True)
-        a = th[:8].clone().requires_grad_(True); b = th[8:].clone().requires_grad_(True)
+def workload_config(micro_batches=None, variant=0):
+    """The workload both arms run and print (identical dicts: the driver compares them)."""
+    return {"workload": "configs[2]: batch-8 synthetic 256^3 volumes + random MANO poses, P=65536, mock latents",
+            "images_per_gpu": B_PER_GPU, "D": D, "P": P, "evals_per_step": EVALS_PER_STEP, "step_index": STEP_INDEX,
+            "l2": "inputs larger than L2 (0.54 GB of volumes touched per launch, 1.07 GB per evaluation of the batch, vs 126 MB L2)"}
+
+
+class CpuGuidance:
+    """The CPU oracle (the restated reference arithmetic; the reference itself cannot be imported offline,
+    SURVEY.md section 8c) on ONE image of the bench workload (D=256, P=65 536), doing what the GPU arm does per
+    evaluation: mock decode of x1 = x_t + (1 - sigma) v, energy forward + backward, decoder adjoint, AdamW on the
+    16 leaves and on the 196 608-element velocity.  All host threads unless ``threads`` is given."""
+
+    def __init__(self, threads: int = 0, seed: int = 0):
+        import torch
+        from followmyhold_b200.guidance.loop import LATENT_SHAPE, set_timesteps_sigmas
+        from followmyhold_b200.synthetic import make_guidance_sample
+        self.torch = torch
+        self.cores = threads or (os.cpu_count() or 1)
+        torch.set_num_threads(self.cores)
+        self.s = make_guidance_sample(D, P, seed=seed)
+        L = LATENT_SHAPE[0] * LATENT_SHAPE[1]
+        g = torch.Generator().manual_seed(1234)
+        vol = D ** 3
+        starts = torch.randperm(vol // 64, generator=g)[: L // 64].sort().values * 64
+        self.tap = (starts.view(-1, 1) + torch.arange(64).view(1, -1)).reshape(-1)
+        self.alpha = 0.05
+        self.sigma = float(set_timesteps_sigmas(20)[STEP_INDEX])
+        self.x_t = torch.randn(L, generator=g)
+        self.vel = 0.1 * torch.randn(L, generator=g)
+        self.th = torch.cat([self.s.theta_h, self.s.theta_o]).clone()
+        self.m, self.v = torch.zeros(16), torch.zeros(16)
+        self.vm, self.vv = torch.zeros(L), torch.zeros(L)
+        self.n = 0
+
+    def evaluate(self) -> None:
+        from oracle import guidance_oracle as O
+        torch, s = self.torch, self.s
+        vel = self.vel.clone().requires_grad_(True)
+        x1 = self.x_t + (1.0 - self.sigma) * vel
+        sdf = s.sdf.reshape(-1).index_add(0, self.tap, self.alpha * x1).reshape(s.sdf.shape)
+        a = self.th[:8].clone().requires_grad_(True); b = self.th[8:].clone().requires_grad_(True)
         out = O.guidance_energy(sdf, s.hand_rest, s.hand_faces, s.cloud, a, b, s.T_h2m, s.obj_center,
                                 j_regressor=s.j_regressor, kps_2d=s.kps_2d, fov_deg=s.fov_deg, image_hw=s.image_hw)
         out["total"].backward()
-        g = torch.cat([a.grad, b.grad])
-        th, m, v = O.adamw_step(th, g, m, v, n + 1, 1e-2)
+        self.n += 1
+        self.th, self.m, self.v = O.adamw_step(self.th, torch.cat([a.grad, b.grad]), self.m, self.v, self.n, 1e-2)
+        self.vel, self.vm, self.vv = O.adamw_step(self.vel, vel.grad, self.vm, self.vv, self.n, 1e-2)
+
+
+def cpu_guidance_evals_per_sec(seconds_budget: float = 20.0, threads: int = 0, n_min: int = 2):
+    cg = CpuGuidance(threads)
+    n, t0 = 0, time.perf_counter()
+    while True:
+        cg.evaluate()
         n += 1
         el = time.perf_counter() - t0
-        if n >= n_min and el >= seconds_budget:
-            break
-        if el > 4 * seconds_budget:
+        if (n >= n_min and el >= seconds_budget) or el > 4 * seconds_budget:
             break
     el = time.perf_counter() - t0
-    return n / el, cores, n, el
+    return n / el, cg.cores, n, el
 
 
 def run_reference(args):
+    """Reference arm: the CPU implementation of the path on the host cores.  A "step" here is a bounded SAMPLE of
+    a guided-denoise step -- ``--ref-evals`` evaluations of one image out of the 50 x 8 a full step of the batch
+    has -- so that K + W steps end within minutes; value extrapolates to whole image-steps per second."""
+    import traceback
     rank = int(os.environ.get("RANK", "0"))
-    if rank != 0:
-        return
-    n_gpus = args.gpus
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    pg = None
+    if world > 1:
+        # the other ranks do no work but stay until rank 0 is done, so the launcher never sees ranks of one job
+        # ending minutes apart
+        try:
+            import datetime
+            import torch.distributed as dist
+            os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+            dist.init_process_group("gloo", timeout=datetime.timedelta(minutes=30))
+            pg = dist
+        except Exception as e:          # no rendezvous: rank 0 still measures, the others leave
+            print(json.dumps({"impl": "reference", "note": f"rank {rank}: no process group ({type(e).__name__}: {e})"}),
+                  file=sys.stderr, flush=True)
+    try:
+        if rank == 0:
+            _reference_rank0(args)
+    except Exception as e:
+        tb = traceback.format_exc().strip().splitlines()
+        print(json.dumps({"impl": "reference", "error": f"{type(e).__name__}: {e}", "traceback": tb[-6:]}), flush=True)
+        raise
+    finally:
+        if pg is not None:
+            try:
+                pg.barrier()
+                pg.destroy_process_group()
+            except Exception:
+                pass
+
+
+def _reference_rank0(args):
     K, W = args.steps, args.warmup
-    # each reference "step" is a bounded sample: a few oracle evaluations of one image
-    per_step_budget = max(2.0, min(20.0, 120.0 / max(1, K + W)))
-    vals = []
-    cores = os.cpu_count() or 1
-    n_total = 0
-    t_total = 0.0
+    n_evals = max(1, args.ref_evals)
+    cg = CpuGuidance()
+    times = []
     for i in range(W + K):
-        eps, cores, n, el = cpu_guidance_evals_per_sec(per_step_budget, n_min=1)
+        t0 = time.perf_counter()
+        for _ in range(n_evals):
+            cg.evaluate()
         if i >= W:
-            vals.append(eps); n_total += n; t_total += el
-    evals_per_s = n_total / t_total
-    value = evals_per_s / EVALS_PER_STEP
+            times.append(time.perf_counter() - t0)
+    t_total = sum(times)
+    evals_per_s = K * n_evals / t_total
+    value = evals_per_s / EVALS_PER_STEP            # image-steps per second
     line = {
-        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": n_gpus, "steps": K, "warmup": W,
-        "ms_per_step": 1e3 / value if value > 0 else None, "higher_is_better": True, "scaling": "weak",
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": K, "warmup": W,
+        "ms_per_step": 1e3 * t_total / K, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "configs[2]: batch-8 synthetic 256^3 volumes + random MANO poses, P=65536, mock latents",
-                   "D": D, "P": P, "evals_per_step": EVALS_PER_STEP},
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
-                         "sample": f"{n_total} oracle guidance evaluations (fwd+bwd+AdamW) of ONE image of the workload "
-                                   f"in {t_total:.1f}s; value = evals/s / {EVALS_PER_STEP}",
+        "config": workload_config(),
+        "sampled": True,
+        "step_is": f"a bounded sample: {n_evals} evaluation(s) of ONE image of the workload (a full step of the batch is "
+                   f"{EVALS_PER_STEP} x {B_PER_GPU}); value = evaluations/s / {EVALS_PER_STEP}; ms_per_step is the measured "
+                   "time of one sample",
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cg.cores, "kind": "port",
+                         "sample": f"{K * n_evals} oracle guidance evaluations (mock decode + fwd + bwd + adjoint + AdamW on leaves "
+                                   f"and velocity) of ONE image of the workload in {t_total:.1f}s; value = evals/s / {EVALS_PER_STEP}",
                          "evals_per_sec": evals_per_s},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -269,7 +336,7 @@ def run_ours(args):
     e2e_h16_s = time.perf_counter() - t3
     # one batch alone (no overlap possible): the latency a single call sees
     t1 = time.perf_counter()
-    loop.denoise_step_host(STEP_INDEX, sdf0_h, x_t_h, vel_h, theta_h)
+    loop.denoise_steps_host(STEP_INDEX, [lat])
     e2e_single_s = time.perf_counter() - t1
 
     # ---- dominant kernel alone: the dense stream of one micro-batch (stage_mask = prep|stream), CUDA events
@@ -358,28 +425,29 @@ def run_ours(args):
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
             "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
-            "config": {"workload": "configs[2]: batch-8 synthetic 256^3 volumes + random MANO poses, P=65536, mock latents",
-                       "images_per_gpu": B, "micro_batches": args.micro_batches, "images_per_launch": nb,
-                       "D": D, "P": P, "evals_per_step": EVALS_PER_STEP, "step_index": STEP_INDEX,
-                       "l2": "inputs larger than L2 (0.54 GB of volumes touched per launch, 1.07 GB per evaluation "
-                             "of the batch, vs 126 MB L2)",
+            "config": workload_config(),
+            "detail": {"micro_batches": args.micro_batches, "images_per_launch": nb,
                        "stream_variant": {0: "tma", 1: "ldg", 2: "tma"}.get(args.variant, "tma"),
                        "evals_per_sec": value * EVALS_PER_STEP, "eval_ms_standalone": eval_ms,
                        "eval_ms_serialised": eval_serial_ms, "host_numa": numa,
                        "eval_GBps_algorithmic": eval_bytes / (eval_ms * 1e-3) / 1e9},
             "clocks": clocks,
-            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": loop.h2d_bytes_per_step(),
+            # End to end = the call the real loop makes once per denoise step: the step's inputs (latents, model
+            # output, leaves) come from pinned host memory, its results (optimised model output, prev_sample, leaves,
+            # loss terms) go back -- all inside the timed region.  The volumes are the DECODER's output and are
+            # produced on the device (latent2sdf runs there, row f1), so they are not a per-step input; the
+            # round-1 variant that also uploads 512 MiB of volumes per step is kept as `volumes_uploaded`.
+            "e2e": {"value": world * B * K2 / e2e_lat_s, "unit": UNIT,
+                    "h2d_bytes_per_step": 4 * (2 * B * loop.L + B * 16),
                     "d2h_bytes_per_step": loop.d2h_bytes_per_step(), "steps": K2,
-                    "api": "GuidanceLoop.denoise_steps_host (pinned host buffers in and out, 3-stream pipeline)",
+                    "api": "GuidanceLoop.denoise_steps_host (pinned host buffers in and out, 3-stream pipeline); "
+                           "inputs per step: latents x_t, model output, leaves",
                     "single_batch_ms": e2e_single_s * 1e3,
-                    "volumes_resident": {"value": world * B * K2 / e2e_lat_s, "unit": UNIT,
-                                         "h2d_bytes_per_step": 4 * (2 * B * loop.L + B * 16),
-                                         "note": "decoder base volumes stay on the device; latents, model output "
-                                                 "and leaves cross PCIe every step"},
-                    "volumes_fp16": {"value": world * B * K2 / e2e_h16_s, "unit": UNIT,
-                                     "h2d_bytes_per_step": 2 * B * D ** 3 + 4 * (2 * B * loop.L + B * 16),
-                                     "note": "volumes cross PCIe as the fp16 the reference's decoder emits "
-                                             "(pipelines.py:303-309) and are widened on the device; compute is fp32"}},
+                    "volumes_uploaded": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": loop.h2d_bytes_per_step(),
+                                         "note": "round-1 definition: the decoder base volumes (512 MiB fp32) also cross "
+                                                 "PCIe every step"},
+                    "volumes_uploaded_fp16": {"value": world * B * K2 / e2e_h16_s, "unit": UNIT,
+                                              "h2d_bytes_per_step": 2 * B * D ** 3 + 4 * (2 * B * loop.L + B * 16)}},
             "gpu_launches": K * loop.launches_per_step(),
             "roofline": {"bound": "hbm", "kernel": "k_stream_tma" if args.variant in (0, 2) else "k_stream_ldg",
                          "achieved": achieved, "peak": peak, "peak_kind": f"{peak_kind} burst copy (kernel timed alone)",
@@ -414,7 +482,7 @@ def run_ours(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=200, help="timed steps (default: ~2 s of device time)")
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--variant", type=int, default=0, help="dense stream kernel: 0/2 = TMA bulk, 1 = LDG")
@@ -422,6 +490,7 @@ def main():
                     help="groups of images that advance independently inside the step's graph (1, 2 or 4)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--cpu-seconds", type=float, default=15.0)
+    ap.add_argument("--ref-evals", type=int, default=3, help="--impl reference: oracle evaluations per (sampled) step")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -237,7 +237,7 @@ def load(build_if_missing: bool = False) -> C.CDLL:
     lib.foho_dec_head.argtypes = [vp, i64, vp, vp, f32, vp, f32, vp, vp, i64, vp]
     lib.foho_dec_head_bwd.argtypes = [vp, i64, vp, f32, vp, vp, vp, f32, vp, i64, i64, vp]
     lib.foho_dec_gather_rows.argtypes = [vp, i64, vp, vp, i64, i64, i32, vp]
-    lib.foho_dec_cast.argtypes = [vp, vp, i64, f32, i32, vp]
+    lib.foho_dec_cast.argtypes = [vp, i64, vp, i64, i64, i32, f32, i32, vp]
     for _n in ("layernorm", "layernorm_bwd", "softmax", "softmax_bwd", "fourier_embed", "head", "head_bwd", "gather_rows", "cast"):
         getattr(lib, "foho_dec_" + _n).restype = C.c_int
     if lib.foho_abi_version() != ABI_VERSION:

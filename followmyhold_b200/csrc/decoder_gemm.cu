@@ -22,6 +22,7 @@ constexpr int BM = 128, BK = 64, UMMA_K = 16;
 struct GemmParams {
   int M, N, K, batch;
   int tiles_m, tiles_n;
+  int a_bcast, b_bcast;          // operand shared by every batch (batch stride 0)
   // epilogue
   void *C; long long ldc, bsc; int c_f32;
   const float *bias;
@@ -87,15 +88,15 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
         const int k0 = kb * BK;
         if (A_MN) {
 #pragma unroll
-          for (int j = 0; j < BM / 64; ++j) tc::tma_load_3d(sa + j * (BK * 128), &tmA, &full[s], m0 + 64 * j, k0, b);
+          for (int j = 0; j < BM / 64; ++j) tc::tma_load_3d(sa + j * (BK * 128), &tmA, &full[s], m0 + 64 * j, k0, p.a_bcast ? 0 : b);
         } else {
-          tc::tma_load_3d(sa, &tmA, &full[s], k0, m0, b);
+          tc::tma_load_3d(sa, &tmA, &full[s], k0, m0, p.a_bcast ? 0 : b);
         }
         if (B_MN) {
 #pragma unroll
-          for (int j = 0; j < BN / 64; ++j) tc::tma_load_3d(sb + j * (BK * 128), &tmB, &full[s], n0 + 64 * j, k0, b);
+          for (int j = 0; j < BN / 64; ++j) tc::tma_load_3d(sb + j * (BK * 128), &tmB, &full[s], n0 + 64 * j, k0, p.b_bcast ? 0 : b);
         } else {
-          tc::tma_load_3d(sb, &tmB, &full[s], k0, n0, b);
+          tc::tma_load_3d(sb, &tmB, &full[s], k0, n0, p.b_bcast ? 0 : b);
         }
       }
     }
@@ -260,13 +261,16 @@ int launch_gemm(const foho_gemm_desc *d, cudaStream_t st) {
   CUtensorMap tmA, tmB;
   int rc;
   // K-major: dims {K, rows, batch}, box {64, BM|BN}; MN-major: dims {rows, K, batch}, box {64, BK}
-  if (A_MN) rc = tc::make_tmap_f16(&tmA, d->A, d->M, d->K, d->batch, d->lda, d->bsa, BK);
-  else      rc = tc::make_tmap_f16(&tmA, d->A, d->K, d->M, d->batch, d->lda, d->bsa, BM);
+  const int a_bcast = d->batch > 1 && d->bsa == 0, b_bcast = d->batch > 1 && d->bsb == 0;
+  const int nba = a_bcast ? 1 : d->batch, nbb = b_bcast ? 1 : d->batch;
+  if (A_MN) rc = tc::make_tmap_f16(&tmA, d->A, d->M, d->K, nba, d->lda, d->bsa, BK);
+  else      rc = tc::make_tmap_f16(&tmA, d->A, d->K, d->M, nba, d->lda, d->bsa, BM);
   if (rc) return rc;
-  if (B_MN) rc = tc::make_tmap_f16(&tmB, d->B, d->N, d->K, d->batch, d->ldb, d->bsb, BK);
-  else      rc = tc::make_tmap_f16(&tmB, d->B, d->K, d->N, d->batch, d->ldb, d->bsb, BN);
+  if (B_MN) rc = tc::make_tmap_f16(&tmB, d->B, d->N, d->K, nbb, d->ldb, d->bsb, BK);
+  else      rc = tc::make_tmap_f16(&tmB, d->B, d->K, d->N, nbb, d->ldb, d->bsb, BN);
   if (rc) return rc;
   GemmParams p;
+  p.a_bcast = a_bcast; p.b_bcast = b_bcast;
   p.M = d->M; p.N = d->N; p.K = d->K; p.batch = d->batch;
   p.tiles_m = (d->M + BM - 1) / BM; p.tiles_n = (d->N + BN - 1) / BN;
   p.C = d->C; p.ldc = d->ldc; p.bsc = d->bsc; p.c_f32 = d->c_f32;

@@ -326,22 +326,20 @@ __global__ void k_gather_rows(const __half *__restrict__ in, long long ld_in, co
   const int c = (int)(i - r * cpr);
   *reinterpret_cast<uint4 *>(out + r * ld_out + c * 8) = __ldg(reinterpret_cast<const uint4 *>(in + (long long)idx[r] * ld_in + c * 8));
 }
-__global__ void k_f32_to_f16(const float *__restrict__ in, __half *__restrict__ out, long long n, float scale) {
-  const long long i = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * 4;
-  if (i + 3 < n) {
-    float4 v = *reinterpret_cast<const float4 *>(in + i);
-    __align__(8) __half2 o[2] = {__floats2half2_rn(v.x * scale, v.y * scale), __floats2half2_rn(v.z * scale, v.w * scale)};
-    *reinterpret_cast<uint2 *>(out + i) = *reinterpret_cast<uint2 *>(o);
-  } else {
-    for (long long j = i; j < n; ++j) out[j] = __float2half_rn(in[j] * scale);
-  }
-}
-// out = scale * in (+ out when accumulate): the adjoint's fp16 gradients leave as float32
-__global__ void k_f16_to_f32(const __half *__restrict__ in, float *__restrict__ out, long long n, float scale, int accumulate) {
+// 2-D casts between row-major views (cols contiguous): mode 0 f32 -> f16, 1 f16 -> f32, 2 f16 -> f32 accumulate
+__global__ void k_cast2d(const void *__restrict__ in, long long ld_in, void *__restrict__ out, long long ld_out, long long rows, int cols,
+                         float scale, int mode) {
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
-  const float v = __half2float(in[i]) * scale;
-  out[i] = accumulate ? out[i] + v : v;
+  if (i >= rows * cols) return;
+  const long long r = i / cols;
+  const int c = (int)(i - r * cols);
+  if (mode == 0) {
+    reinterpret_cast<__half *>(out)[r * ld_out + c] = __float2half_rn(reinterpret_cast<const float *>(in)[r * ld_in + c] * scale);
+  } else {
+    const float v = __half2float(reinterpret_cast<const __half *>(in)[r * ld_in + c]) * scale;
+    float *o = reinterpret_cast<float *>(out) + r * ld_out + c;
+    *o = (mode == 2) ? *o + v : v;
+  }
 }
 // y = a + b (fp16), 8 elements per thread
 __global__ void k_add_f16(const __half *a, const __half *b, __half *y, long long n) {
@@ -452,15 +450,18 @@ extern "C" int foho_dec_gather_rows(const void *in, int64_t ld_in, const int32_t
   return 0;
 }
 
-extern "C" int foho_dec_cast(const void *in, void *out, int64_t n, float scale, int32_t mode, void *cuda_stream) {
-  // mode 0: f32 -> f16 (scaled); 1: f16 -> f32 (scaled); 2: f16 -> f32, accumulate; 3: out = in + out (fp16)
+extern "C" int foho_dec_cast(const void *in, int64_t ld_in, void *out, int64_t ld_out, int64_t rows, int32_t cols, float scale, int32_t mode,
+                             void *cuda_stream) {
+  // mode 0: f32 -> f16 (scaled); 1: f16 -> f32 (scaled); 2: f16 -> f32, accumulate; 3: out += in (fp16, contiguous rows*cols)
   if (!in || !out) return FOHO_E_NULL;
-  if (n <= 0) return FOHO_E_SHAPE;
+  if (rows <= 0 || cols <= 0) return FOHO_E_SHAPE;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(cuda_stream);
-  if (mode == 0) k_f32_to_f16<<<blocks_for((n + 3) / 4, 256), 256, 0, st>>>((const float *)in, (__half *)out, n, scale);
-  else if (mode == 1 || mode == 2) k_f16_to_f32<<<blocks_for(n, 256), 256, 0, st>>>((const __half *)in, (float *)out, n, scale, mode == 2);
-  else if (mode == 3) k_add_f16<<<blocks_for((n + 7) / 8, 256), 256, 0, st>>>((const __half *)in, (const __half *)out, (__half *)out, n);
-  else return FOHO_E_ARG;
+  const long long n = rows * cols;
+  if (mode >= 0 && mode <= 2) k_cast2d<<<blocks_for(n, 256), 256, 0, st>>>(in, ld_in, out, ld_out, rows, cols, scale, mode);
+  else if (mode == 3) {
+    if (ld_in != cols || ld_out != cols) return FOHO_E_ARG;
+    k_add_f16<<<blocks_for((n + 7) / 8, 256), 256, 0, st>>>((const __half *)in, (const __half *)out, (__half *)out, n);
+  } else return FOHO_E_ARG;
   FOHO_LAUNCH_CHECK();
   return 0;
 }

@@ -1,0 +1,382 @@
+"""The reference's ``latent2sdf`` (third_party_patches/hy3dgen/shapegen/pipelines.py:292-312) and its adjoint
+on the B200's tensor cores: host-side orchestration of the C-ABI building blocks (``foho_tc_gemm``,
+``foho_tc_attention``, ``foho_dec_*``).  Nothing here computes with torch; torch owns the buffers and streams.
+
+    pred = 1 / vae.scale_factor * pred
+    pred = vae(pred)                                   # post_kl + 16-layer transformer over 3072 tokens
+    logits = vae.geo_decoder(queries, pred)            # Fourier embedding -> cross attention -> MLP -> 1 logit
+    sdf = -logits.view(1, D, D, D).float()
+
+Module / parameter names follow ``hy3dgen/shapegen/models`` (Hunyuan3D-2 @ e664e747, un-vendored; restated from
+memory in ``oracle/decoder_oracle.py`` -- ARCHITECTURE UNPINNED until checked against the package) so a released
+state_dict loads by name: ``post_kl``, ``transformer.resblocks.N.*``, ``geo_decoder.*``.
+
+What is latent-independent is computed once per lattice (``set_queries``): the residual-stream entry
+``x0 = query_proj(embed(q))`` and the normalised per-head queries ``q_norm(c_q(ln_1(x0)))``.
+
+Adjoint: weights are frozen, so only input gradients exist.  ``backward`` takes dE/dSDF on a sparse set of
+lattice points (the voxels the energy touches), recomputes the query-side activations of those rows only, and
+carries the gradient through the cross attention into K/V, through the token transformer (activations kept from
+the forward), to dE/d(latents).  fp16 gradient activations carry a static loss scale.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Dict, List, Optional
+
+import torch
+
+from .. import _lib
+from . import tc
+
+WIDTH, HEADS, HD, TOKENS, EMBED = 1024, 16, 64, 3072, 64
+LN_EPS = 1e-6            # hy3dgen blocks: LayerNorm(eps=1e-6); ln_post keeps torch's default 1e-5
+LN_POST_EPS = 1e-5
+SCALE_FACTOR = 0.9990943042622529
+
+
+def _sp(stream):
+    return C.c_void_p((stream or torch.cuda.current_stream()).cuda_stream)
+
+
+class _Ops:
+    """ctypes fronts of the row-wise kernels (raw pointers in, status checked)."""
+
+    def __init__(self):
+        self.lib = _lib.load()
+
+    def layernorm(self, x, w, b, out, width=WIDTH, eps=LN_EPS, stream=None):
+        """x, out: [rows, width] (stride(0) free) or [tokens, heads, 64] strided views."""
+        (ix, lox, lix, rows), (iy, loy, liy, _) = self._view(x, width), self._view(out, width)
+        _lib.check("foho_dec_layernorm", self.lib.foho_dec_layernorm(
+            x.data_ptr(), ix, lox, lix, None if w is None else w.data_ptr(), None if b is None else b.data_ptr(), eps,
+            out.data_ptr(), iy, loy, liy, rows, width, _sp(stream)))
+        return out
+
+    def layernorm_bwd(self, x, w, dy, dx, add=None, width=WIDTH, eps=LN_EPS, stream=None):
+        (ix, lox, lix, rows), (ig, log_, lig, _), (id_, lod, lid, _) = self._view(x, width), self._view(dy, width), self._view(dx, width)
+        if add is not None and (add.stride() != dx.stride() or add.shape != dx.shape):
+            raise ValueError("`add` must have the layout of dx")
+        _lib.check("foho_dec_layernorm_bwd", self.lib.foho_dec_layernorm_bwd(
+            x.data_ptr(), ix, lox, lix, None if w is None else w.data_ptr(), eps, dy.data_ptr(), ig, log_, lig,
+            None if add is None else add.data_ptr(), dx.data_ptr(), id_, lod, lid, rows, width, _sp(stream)))
+        return dx
+
+    @staticmethod
+    def _view(t, width):
+        if t.stride(-1) != 1 or t.shape[-1] != width:
+            raise ValueError("last dimension must be contiguous and equal to the LayerNorm width")
+        if t.dim() == 2:
+            return 1, t.stride(0), 0, t.shape[0]
+        if t.dim() == 3:
+            return t.shape[1], t.stride(0), t.stride(1), t.shape[0] * t.shape[1]
+        raise ValueError("expected a 2-D or 3-D view")
+
+    def softmax(self, S, P, stream=None):
+        T = S.shape[-1]
+        _lib.check("foho_dec_softmax", self.lib.foho_dec_softmax(S.data_ptr(), P.data_ptr(), S.numel() // T, T, _sp(stream)))
+        return P
+
+    def softmax_bwd(self, P, dP, dS, scale, stream=None):
+        T = P.shape[-1]
+        _lib.check("foho_dec_softmax_bwd", self.lib.foho_dec_softmax_bwd(P.data_ptr(), dP.data_ptr(), dS.data_ptr(), P.numel() // T, T,
+                                                                         scale, _sp(stream)))
+        return dS
+
+    def fourier(self, xyz, out, num_freqs, include_pi, stream=None):
+        _lib.check("foho_dec_fourier_embed", self.lib.foho_dec_fourier_embed(xyz.data_ptr(), out.data_ptr(), xyz.shape[0], out.shape[1],
+                                                                             num_freqs, int(include_pi), _sp(stream)))
+        return out
+
+    def head(self, x, ln_w, ln_b, w_out, b_out, out, idx=None, stream=None):
+        _lib.check("foho_dec_head", self.lib.foho_dec_head(x.data_ptr(), x.stride(0), ln_w.data_ptr(), ln_b.data_ptr(), LN_POST_EPS,
+                                                           w_out.data_ptr(), b_out, None if idx is None else idx.data_ptr(),
+                                                           out.data_ptr(), x.shape[0], _sp(stream)))
+
+    def head_bwd(self, x, ln_w, w_out, dS, g_scale, dx, idx=None, stream=None):
+        _lib.check("foho_dec_head_bwd", self.lib.foho_dec_head_bwd(x.data_ptr(), x.stride(0), ln_w.data_ptr(), LN_POST_EPS, w_out.data_ptr(),
+                                                                   None if idx is None else idx.data_ptr(), dS.data_ptr(), g_scale,
+                                                                   dx.data_ptr(), dx.stride(0), x.shape[0], _sp(stream)))
+        return dx
+
+    def gather(self, src, idx, out, stream=None):
+        W = src.shape[1]
+        _lib.check("foho_dec_gather_rows", self.lib.foho_dec_gather_rows(src.data_ptr(), src.stride(0), idx.data_ptr(), out.data_ptr(),
+                                                                         out.stride(0), idx.numel(), W, _sp(stream)))
+        return out
+
+    def cast(self, src, dst, scale=1.0, accumulate=False, stream=None):
+        """2-D row-major views; f32 -> f16 or f16 -> f32 (optionally accumulating)."""
+        if src.dim() != 2 or dst.shape != src.shape or src.stride(1) != 1 or dst.stride(1) != 1:
+            raise ValueError("cast expects matching 2-D views with contiguous columns")
+        if src.dtype == torch.float32 and dst.dtype == torch.float16:
+            mode = 0
+        elif src.dtype == torch.float16 and dst.dtype == torch.float32:
+            mode = 2 if accumulate else 1
+        else:
+            raise ValueError("unsupported cast")
+        _lib.check("foho_dec_cast", self.lib.foho_dec_cast(src.data_ptr(), src.stride(0), dst.data_ptr(), dst.stride(0), src.shape[0],
+                                                           src.shape[1], scale, mode, _sp(stream)))
+        return dst
+
+
+class DecoderWeights:
+    """Device copies of the decode half of ``ShapeVAE``: fp16 matrices for the tensor cores, fp32 biases and
+    LayerNorm parameters.  ``state_dict`` keys are the reference package's (see the module docstring)."""
+
+    def __init__(self, state_dict: Dict[str, torch.Tensor], device, num_layers: Optional[int] = None, num_freqs: int = 8,
+                 include_pi: bool = False, scale_factor: float = SCALE_FACTOR):
+        sd = state_dict
+        self.device = torch.device(device)
+        self.num_freqs, self.include_pi, self.scale_factor = num_freqs, include_pi, float(scale_factor)
+        if num_layers is None:
+            num_layers = 1 + max(int(k.split(".")[2]) for k in sd if k.startswith("transformer.resblocks."))
+        self.num_layers = num_layers
+        h = lambda k: sd[k].detach().to(self.device, torch.float16).contiguous()
+        f = lambda k: sd[k].detach().to(self.device, torch.float32).contiguous()
+        opt = lambda k: f(k) if k in sd else None
+        self.post_kl_w, self.post_kl_b = h("post_kl.weight"), f("post_kl.bias")
+        self.layers: List[dict] = []
+        for i in range(num_layers):
+            p = f"transformer.resblocks.{i}."
+            self.layers.append(dict(
+                ln1_w=f(p + "ln_1.weight"), ln1_b=f(p + "ln_1.bias"), qkv_w=h(p + "attn.c_qkv.weight"), qkv_b=opt(p + "attn.c_qkv.bias"),
+                proj_w=h(p + "attn.c_proj.weight"), proj_b=f(p + "attn.c_proj.bias"),
+                qn_w=opt(p + "attn.attention.q_norm.weight"), qn_b=opt(p + "attn.attention.q_norm.bias"),
+                kn_w=opt(p + "attn.attention.k_norm.weight"), kn_b=opt(p + "attn.attention.k_norm.bias"),
+                ln2_w=f(p + "ln_2.weight"), ln2_b=f(p + "ln_2.bias"), fc_w=h(p + "mlp.c_fc.weight"), fc_b=f(p + "mlp.c_fc.bias"),
+                fc2_w=h(p + "mlp.c_proj.weight"), fc2_b=f(p + "mlp.c_proj.bias")))
+            if self.layers[-1]["qn_w"] is None:
+                raise ValueError("qk_norm=False checkpoints are not supported by the per-head LayerNorm kernels")
+        g = "geo_decoder."
+        c = g + "cross_attn_decoder."
+        qp = sd[g + "query_proj.weight"].detach().to(self.device, torch.float32)
+        self.embed_dim = qp.shape[1]                                   # 3 * (2 * num_freqs + 1) = 51
+        self.embed_ld = 64
+        qpw = torch.zeros(qp.shape[0], self.embed_ld, dtype=torch.float16, device=self.device)   # K padded to 64 for the tensor core
+        qpw[:, :self.embed_dim] = qp.to(torch.float16)
+        self.query_proj_w, self.query_proj_b = qpw, f(g + "query_proj.bias")
+        self.x = dict(
+            ln1_w=f(c + "ln_1.weight"), ln1_b=f(c + "ln_1.bias"), ln2_w=f(c + "ln_2.weight"), ln2_b=f(c + "ln_2.bias"),
+            ln3_w=f(c + "ln_3.weight"), ln3_b=f(c + "ln_3.bias"), q_w=h(c + "attn.c_q.weight"), q_b=opt(c + "attn.c_q.bias"),
+            kv_w=h(c + "attn.c_kv.weight"), kv_b=opt(c + "attn.c_kv.bias"), proj_w=h(c + "attn.c_proj.weight"),
+            proj_b=f(c + "attn.c_proj.bias"), qn_w=f(c + "attn.attention.q_norm.weight"), qn_b=f(c + "attn.attention.q_norm.bias"),
+            kn_w=f(c + "attn.attention.k_norm.weight"), kn_b=f(c + "attn.attention.k_norm.bias"),
+            fc_w=h(c + "mlp.c_fc.weight"), fc_b=f(c + "mlp.c_fc.bias"), fc2_w=h(c + "mlp.c_proj.weight"), fc2_b=f(c + "mlp.c_proj.bias"))
+        self.ln_post_w, self.ln_post_b = f(g + "ln_post.weight"), f(g + "ln_post.bias")
+        self.out_w = f(g + "output_proj.weight").reshape(-1).contiguous()
+        self.out_b = float(sd[g + "output_proj.bias"].reshape(-1)[0])
+
+
+class LatentDecoder:
+    """``latent2sdf`` for a batch of B images on one lattice of Nq query points, forward and adjoint."""
+
+    def __init__(self, weights: DecoderWeights, B: int, device=None, query_chunk: int = 0, active_chunk: int = 2048,
+                 loss_scale: float = 4096.0):
+        self.w = weights
+        self.B = int(B)
+        self.dev = torch.device(device or weights.device)
+        self.ops = _Ops()
+        self.loss_scale = float(loss_scale)
+        self.active_chunk = int(active_chunk)
+        self.query_chunk = int(query_chunk) or max(1024, (32768 // self.B) // 128 * 128)
+        R = self.B * TOKENS
+        f16 = dict(dtype=torch.float16, device=self.dev)
+        L = weights.num_layers
+        # token-side activations kept for the adjoint, one set per layer
+        self.act = [dict(x_in=torch.empty(R, WIDTH, **f16), qkv=torch.empty(R, 3 * WIDTH, **f16), qn=torch.empty(R, HEADS, HD, **f16),
+                         kn=torch.empty(R, HEADS, HD, **f16), x_mid=torch.empty(R, WIDTH, **f16), u_pre=torch.empty(R, 4 * WIDTH, **f16))
+                    for _ in range(L)]
+        self.lat16 = torch.empty(R, EMBED, **f16)
+        self.h = torch.empty(R, WIDTH, **f16)            # LayerNorm output scratch
+        self.attn = torch.empty(self.B, TOKENS, WIDTH, **f16)
+        self.u = torch.empty(R, 4 * WIDTH, **f16)
+        self.data = torch.empty(R, WIDTH, **f16)         # transformer output = the geo decoder's `latents`
+        self.kv = torch.empty(R, 2 * WIDTH, **f16)
+        self.kvn = torch.empty(R, HEADS, HD, **f16)      # k_norm(k)
+        self.x0: Optional[torch.Tensor] = None
+        self.qn: Optional[torch.Tensor] = None
+        self.Nq = 0
+        self._fwd_done = False
+
+    # ------------------------------------------------------------------ lattice (once)
+    def set_queries(self, xyz: torch.Tensor) -> None:
+        """``xyz`` [Nq, 3] float32 lattice points (``generate_dense_grid_points``, pipelines.py:341-360)."""
+        w, ops = self.w, self.ops
+        xyz = xyz.to(self.dev, torch.float32).contiguous()
+        self.Nq = Nq = xyz.shape[0]
+        f16 = dict(dtype=torch.float16, device=self.dev)
+        self.x0 = torch.empty(Nq, WIDTH, **f16)
+        self.qn = torch.empty(Nq, HEADS, HD, **f16)
+        step = 65536
+        emb = torch.empty(min(step, Nq), w.embed_ld, **f16)
+        t1 = torch.empty(min(step, Nq), WIDTH, **f16)
+        t2 = torch.empty(min(step, Nq), WIDTH, **f16)
+        for s in range(0, Nq, step):
+            n = min(step, Nq - s)
+            ops.fourier(xyz[s:s + n], emb[:n], w.num_freqs, w.include_pi)
+            tc.gemm(emb[:n], w.query_proj_w, out=self.x0[s:s + n], bias=w.query_proj_b)
+            ops.layernorm(self.x0[s:s + n], w.x["ln1_w"], w.x["ln1_b"], t1[:n])
+            tc.gemm(t1[:n], w.x["q_w"], out=t2[:n], bias=w.x["q_b"])
+            ops.layernorm(t2[:n].view(n, HEADS, HD), w.x["qn_w"], w.x["qn_b"], self.qn[s:s + n], width=HD)
+        qc = self.query_chunk
+        self.q_attn = torch.empty(self.B, qc, WIDTH, **f16)
+        self.q_x = torch.empty(self.B, qc, WIDTH, **f16)
+        self.q_h = torch.empty(self.B, qc, WIDTH, **f16)
+        self.q_u = torch.empty(self.B, qc, 4 * WIDTH, **f16)
+        self.q_y = torch.empty(self.B, qc, WIDTH, **f16)
+
+    # ------------------------------------------------------------------ forward
+    def forward(self, latents: torch.Tensor, out: Optional[torch.Tensor] = None, stream=None) -> torch.Tensor:
+        """``latents`` [B, 3072, 64] float32 (x1 of ``step_final``); returns sdf [B, Nq] float32, negative inside."""
+        w, ops, B = self.w, self.ops, self.B
+        if self.x0 is None:
+            raise RuntimeError("set_queries() first")
+        R = B * TOKENS
+        lat = latents.reshape(R, EMBED)
+        ops.cast(lat, self.lat16, scale=1.0 / w.scale_factor, stream=stream)            # pred = 1/scale_factor * pred (:297)
+        tc.gemm(self.lat16, w.post_kl_w, out=self.act[0]["x_in"] if self.act else self.data, bias=w.post_kl_b, stream=stream)
+        for i, (lw, a) in enumerate(zip(w.layers, self.act)):
+            ops.layernorm(a["x_in"], lw["ln1_w"], lw["ln1_b"], self.h, stream=stream)
+            tc.gemm(self.h, lw["qkv_w"], out=a["qkv"], bias=lw["qkv_b"], stream=stream)
+            qkv = a["qkv"].view(R, HEADS, 3 * HD)
+            ops.layernorm(qkv[:, :, :HD], lw["qn_w"], lw["qn_b"], a["qn"], width=HD, stream=stream)
+            ops.layernorm(qkv[:, :, HD:2 * HD], lw["kn_w"], lw["kn_b"], a["kn"], width=HD, stream=stream)
+            tc.attention(a["qn"], a["kn"], qkv[:, :, 2 * HD:], B, out=self.attn, stream=stream)
+            tc.gemm(self.attn.view(R, WIDTH), lw["proj_w"], out=a["x_mid"], bias=lw["proj_b"], res=a["x_in"], stream=stream)
+            ops.layernorm(a["x_mid"], lw["ln2_w"], lw["ln2_b"], self.h, stream=stream)
+            tc.gemm(self.h, lw["fc_w"], out=self.u, bias=lw["fc_b"], act=tc.ACT_GELU, aux_out=a["u_pre"], stream=stream)
+            nxt = self.act[i + 1]["x_in"] if i + 1 < len(self.act) else self.data
+            tc.gemm(self.u, lw["fc2_w"], out=nxt, bias=lw["fc2_b"], res=a["x_mid"], stream=stream)
+        # geo decoder, token side: k, v of the cross attention
+        xw = w.x
+        ops.layernorm(self.data, xw["ln2_w"], xw["ln2_b"], self.h, stream=stream)
+        tc.gemm(self.h, xw["kv_w"], out=self.kv, bias=xw["kv_b"], stream=stream)
+        kv = self.kv.view(R, HEADS, 2 * HD)
+        ops.layernorm(kv[:, :, :HD], xw["kn_w"], xw["kn_b"], self.kvn, width=HD, stream=stream)
+        # query side, chunk by chunk (per-query work: nothing of width 1024 outlives its chunk)
+        if out is None:
+            out = torch.empty(B, self.Nq, dtype=torch.float32, device=self.dev)
+        qc = self.query_chunk
+        for s in range(0, self.Nq, qc):
+            n = min(qc, self.Nq - s)
+            att = self.q_attn[:, :n]
+            tc.attention(self.qn[s:s + n], self.kvn, kv[:, :, HD:], B, out=att, q_shared=True, stream=stream)
+            xq = tc.gemm(att, xw["proj_w"], out=self.q_x[:, :n], bias=xw["proj_b"], res=self.x0[s:s + n].unsqueeze(0).expand(B, n, WIDTH),
+                         stream=stream)
+            for b in range(B):
+                ops.layernorm(xq[b], xw["ln3_w"], xw["ln3_b"], self.q_h[b, :n], stream=stream)
+            tc.gemm(self.q_h[:, :n], xw["fc_w"], out=self.q_u[:, :n], bias=xw["fc_b"], act=tc.ACT_GELU, stream=stream)
+            tc.gemm(self.q_u[:, :n], xw["fc2_w"], out=self.q_y[:, :n], bias=xw["fc2_b"], res=xq, stream=stream)
+            for b in range(B):
+                ops.head(self.q_y[b, :n], w.ln_post_w, w.ln_post_b, w.out_w, w.out_b, out[b, s:s + n], stream=stream)
+        self._fwd_done = True
+        return out
+
+    # ------------------------------------------------------------------ adjoint
+    def backward(self, idx: torch.Tensor, g_sdf: torch.Tensor, out: Optional[torch.Tensor] = None, stream=None) -> torch.Tensor:
+        """dE/d(latents) [B, 3072, 64] float32 from dE/dSDF on a sparse set of lattice points.
+
+        ``idx`` [B, M] int32 lattice indices of the rows that carry a gradient, ``g_sdf`` [B, M] float32 their
+        dE/dSDF (pad with index 0 / gradient 0).  Uses the token-side activations of the last ``forward``."""
+        if not self._fwd_done:
+            raise RuntimeError("forward() first: the adjoint reuses its token-side activations")
+        w, ops, B = self.w, self.ops, self.B
+        xw = w.x
+        R = B * TOKENS
+        M = idx.shape[1]
+        if M % 8 or self.active_chunk % 8 or idx.dtype != torch.int32 or g_sdf.dtype != torch.float32:
+            raise ValueError("idx must be int32 [B, M] and g_sdf float32 [B, M] with M a multiple of 8")
+        f16 = dict(dtype=torch.float16, device=self.dev)
+        f32 = dict(dtype=torch.float32, device=self.dev)
+        ls = self.loss_scale
+        if not hasattr(self, "_bw"):
+            mc = self.active_chunk
+            self._bw = dict(
+                qn=torch.empty(mc, HEADS, HD, **f16), x0=torch.empty(mc, WIDTH, **f16), S=torch.empty(HEADS, mc, TOKENS, **f32),
+                P=torch.empty(HEADS, mc, TOKENS, **f16), dS=torch.empty(HEADS, mc, TOKENS, **f16), a=torch.empty(mc, WIDTH, **f16),
+                x=torch.empty(mc, WIDTH, **f16), h=torch.empty(mc, WIDTH, **f16), u=torch.empty(mc, 4 * WIDTH, **f16),
+                u_pre=torch.empty(mc, 4 * WIDTH, **f16), y=torch.empty(mc, WIDTH, **f16), dy=torch.empty(mc, WIDTH, **f16),
+                du=torch.empty(mc, 4 * WIDTH, **f16), dh=torch.empty(mc, WIDTH, **f16), dx=torch.empty(mc, WIDTH, **f16),
+                da=torch.empty(mc, WIDTH, **f16),
+                dkn32=torch.empty(B, TOKENS, WIDTH, **f32), dv32=torch.empty(B, TOKENS, WIDTH, **f32),
+                dkn16=torch.empty(R, HEADS, HD, **f16), dkv=torch.empty(R, 2 * WIDTH, **f16),
+                g=torch.empty(R, WIDTH, **f16), g2=torch.empty(R, WIDTH, **f16), g3=torch.empty(R, WIDTH, **f16),
+                gu=torch.empty(R, 4 * WIDTH, **f16), dqkv=torch.empty(R, 3 * WIDTH, **f16),
+                tS=torch.empty(HEADS, TOKENS, TOKENS, **f32), tP=torch.empty(HEADS, TOKENS, TOKENS, **f16),
+                tdS=torch.empty(HEADS, TOKENS, TOKENS, **f16), dqn=torch.empty(TOKENS, HEADS, HD, **f16),
+                dknl=torch.empty(TOKENS, HEADS, HD, **f16))
+        bw = self._bw
+        mc = self.active_chunk
+        kvv = self.kv.view(B, TOKENS, HEADS, 2 * HD)
+        kvn = self.kvn.view(B, TOKENS, HEADS, HD)
+        bw["dkn32"].zero_(); bw["dv32"].zero_()
+        hv = lambda t: t.permute(1, 0, 2)                                # [rows, heads, 64] -> [heads, rows, 64] view
+        # ---- query side: recompute the rows that carry a gradient, then walk back to dK, dV
+        for b in range(B):
+            kn_b, v_b = hv(kvn[b]), hv(kvv[b, :, :, HD:])
+            dkn_b, dv_b = hv(bw["dkn32"][b].view(TOKENS, HEADS, HD)), hv(bw["dv32"][b].view(TOKENS, HEADS, HD))
+            for s in range(0, M, mc):
+                n = min(mc, M - s)
+                ix = idx[b, s:s + n]
+                qn_a = ops.gather(self.qn.view(self.Nq, WIDTH), ix, bw["qn"].view(mc, WIDTH)[:n], stream=stream).view(n, HEADS, HD)
+                x0_a = ops.gather(self.x0, ix, bw["x0"][:n], stream=stream)
+                # contiguous [heads, n, tokens] views of the scratch (the row kernels index rows densely)
+                S, P, dS = (bw[k].view(-1)[:HEADS * n * TOKENS].view(HEADS, n, TOKENS) for k in ("S", "P", "dS"))
+                tc.gemm(hv(qn_a), kn_b, out=S, alpha=0.125, stream=stream)
+                ops.softmax(S, P, stream=stream)
+                a = bw["a"][:n]
+                tc.gemm(P, v_b, out=hv(a.view(n, HEADS, HD)), b_mn=True, stream=stream)
+                x = tc.gemm(a, xw["proj_w"], out=bw["x"][:n], bias=xw["proj_b"], res=x0_a, stream=stream)
+                ops.layernorm(x, xw["ln3_w"], xw["ln3_b"], bw["h"][:n], stream=stream)
+                tc.gemm(bw["h"][:n], xw["fc_w"], out=bw["u"][:n], bias=xw["fc_b"], act=tc.ACT_GELU, aux_out=bw["u_pre"][:n], stream=stream)
+                y = tc.gemm(bw["u"][:n], xw["fc2_w"], out=bw["y"][:n], bias=xw["fc2_b"], res=x, stream=stream)
+                # backward of the head, the MLP block, c_proj
+                dy = ops.head_bwd(y, w.ln_post_w, w.out_w, g_sdf[b, s:s + n], ls, bw["dy"][:n], stream=stream)
+                tc.gemm(dy, xw["fc2_w"], out=bw["du"][:n], b_mn=True, act=tc.ACT_DGELU, aux_in=bw["u_pre"][:n], stream=stream)
+                tc.gemm(bw["du"][:n], xw["fc_w"], out=bw["dh"][:n], b_mn=True, stream=stream)
+                dx = ops.layernorm_bwd(x, xw["ln3_w"], bw["dh"][:n], bw["dx"][:n], add=dy, stream=stream)
+                da = tc.gemm(dx, xw["proj_w"], out=bw["da"][:n], b_mn=True, stream=stream)
+                da_h = hv(da.view(n, HEADS, HD))
+                # attention backward, heads batched: dP = dA V^T ; dS = P o (dP - rowsum) / 8 ; dV += P^T dA ; dKn += dS^T Qn
+                tc.gemm(da_h, v_b, out=S, stream=stream)                                   # S buffer reused for dP (fp32)
+                ops.softmax_bwd(P, S, dS, 0.125, stream=stream)
+                tc.gemm(P, da_h, out=dv_b, res=dv_b, a_mn=True, b_mn=True, stream=stream)
+                tc.gemm(dS, hv(qn_a), out=dkn_b, res=dkn_b, a_mn=True, b_mn=True, stream=stream)
+        # ---- K/V gradients -> token gradient d(data)
+        ops.cast(bw["dkn32"].view(R, WIDTH), bw["dkn16"].view(R, WIDTH), stream=stream)
+        dkv = bw["dkv"].view(R, HEADS, 2 * HD)
+        ops.layernorm_bwd(self.kv.view(R, HEADS, 2 * HD)[:, :, :HD], xw["kn_w"], bw["dkn16"], dkv[:, :, :HD], width=HD, stream=stream)
+        for hh in range(HEADS):      # dV (fp32, [tokens, heads*64]) -> the v half of dkv
+            ops.cast(bw["dv32"].view(R, WIDTH)[:, hh * HD:(hh + 1) * HD], bw["dkv"][:, hh * 2 * HD + HD:(hh + 1) * 2 * HD], stream=stream)
+        tc.gemm(bw["dkv"], xw["kv_w"], out=bw["g2"], b_mn=True, stream=stream)
+        g = ops.layernorm_bwd(self.data, xw["ln2_w"], bw["g2"], bw["g"], stream=stream)     # d(data)
+        # ---- token transformer, last layer first
+        for i in range(len(w.layers) - 1, -1, -1):
+            lw, a = w.layers[i], self.act[i]
+            qkv = a["qkv"].view(B, TOKENS, HEADS, 3 * HD)
+            dqkv = bw["dqkv"].view(B, TOKENS, HEADS, 3 * HD)
+            tc.gemm(g, lw["fc2_w"], out=bw["gu"], b_mn=True, act=tc.ACT_DGELU, aux_in=a["u_pre"], stream=stream)
+            tc.gemm(bw["gu"], lw["fc_w"], out=bw["g2"], b_mn=True, stream=stream)
+            g_mid = ops.layernorm_bwd(a["x_mid"], lw["ln2_w"], bw["g2"], bw["g3"], add=g, stream=stream)
+            da = tc.gemm(g_mid, lw["proj_w"], out=bw["g2"], b_mn=True, stream=stream).view(B, TOKENS, HEADS, HD)
+            qn, kn = a["qn"].view(B, TOKENS, HEADS, HD), a["kn"].view(B, TOKENS, HEADS, HD)
+            for b in range(B):
+                qn_b, kn_b, v_b, da_b = hv(qn[b]), hv(kn[b]), hv(qkv[b, :, :, 2 * HD:]), hv(da[b])
+                tc.gemm(qn_b, kn_b, out=bw["tS"], alpha=0.125, stream=stream)
+                ops.softmax(bw["tS"], bw["tP"], stream=stream)
+                tc.gemm(da_b, v_b, out=bw["tS"], stream=stream)                            # dP
+                ops.softmax_bwd(bw["tP"], bw["tS"], bw["tdS"], 0.125, stream=stream)
+                tc.gemm(bw["tP"], da_b, out=hv(dqkv[b, :, :, 2 * HD:]), a_mn=True, b_mn=True, stream=stream)     # dV
+                tc.gemm(bw["tdS"], kn_b, out=hv(bw["dqn"]), b_mn=True, stream=stream)                           # dQn = dS Kn
+                tc.gemm(bw["tdS"], qn_b, out=hv(bw["dknl"]), a_mn=True, b_mn=True, stream=stream)               # dKn = dS^T Qn
+                ops.layernorm_bwd(qkv[b, :, :, :HD], lw["qn_w"], bw["dqn"], dqkv[b, :, :, :HD], width=HD, stream=stream)
+                ops.layernorm_bwd(qkv[b, :, :, HD:2 * HD], lw["kn_w"], bw["dknl"], dqkv[b, :, :, HD:2 * HD], width=HD, stream=stream)
+            tc.gemm(bw["dqkv"], lw["qkv_w"], out=bw["g2"], b_mn=True, stream=stream)
+            g = ops.layernorm_bwd(a["x_in"], lw["ln1_w"], bw["g2"], bw["g"], add=g_mid, stream=stream)
+        # ---- post_kl and the 1/scale_factor of the call site
+        if out is None:
+            out = torch.empty(B, TOKENS, EMBED, **f32)
+        # float32 out; the epilogue undoes the loss scale and applies the call site's 1/scale_factor (:297)
+        tc.gemm(g, w.post_kl_w, out=out.view(R, EMBED), b_mn=True, alpha=1.0 / (w.scale_factor * ls), stream=stream)
+        return out

@@ -359,8 +359,10 @@ int foho_dec_head_bwd(const void *x, int64_t ldx, const float *ln_w, float eps, 
                       float g_scale, void *dx, int64_t lddx, int64_t rows, void *cuda_stream);
 int foho_dec_gather_rows(const void *in, int64_t ld_in, const int32_t *idx, void *out, int64_t ld_out, int64_t rows, int32_t width,
                          void *cuda_stream);
-/* mode 0: f32 -> f16 (x scale); 1: f16 -> f32 (x scale); 2: f16 -> f32 accumulate; 3: out += in (fp16) */
-int foho_dec_cast(const void *in, void *out, int64_t n, float scale, int32_t mode, void *cuda_stream);
+/* row-major views [rows, cols], cols contiguous, leading dimensions in elements.
+ * mode 0: f32 -> f16 (x scale); 1: f16 -> f32 (x scale); 2: f16 -> f32 accumulate; 3: out += in (fp16, contiguous) */
+int foho_dec_cast(const void *in, int64_t ld_in, void *out, int64_t ld_out, int64_t rows, int32_t cols, float scale, int32_t mode,
+                  void *cuda_stream);
 
 #ifdef __cplusplus
 }
