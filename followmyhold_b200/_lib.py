@@ -22,6 +22,7 @@ NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", 
               "-Xcompiler", "-fPIC", "-Xcompiler", "-O3"]
 
 FOHO_NUM_TERMS = 16
+FOHO_E_WORKSPACE = -3
 ABI_VERSION = 5
 TERM_NAMES = ["total", "pen", "con", "int", "count", "mom", "ch", "kp", "treg_h", "treg_o", "dist", "vreg",
               "edge", "mean_d2", "ncand", "flags"]
@@ -37,6 +38,7 @@ EXPORTED_SYMBOLS = [
     "foho_tc_gemm", "foho_tc_attention",
     "foho_dec_layernorm", "foho_dec_layernorm_bwd", "foho_dec_softmax", "foho_dec_softmax_bwd", "foho_dec_fourier_embed",
     "foho_dec_head", "foho_dec_head_bwd", "foho_dec_gather_rows", "foho_dec_cast",
+    "foho_dec_compact_workspace_bytes", "foho_dec_compact_grad",
 ]
 
 
@@ -116,7 +118,7 @@ class GuidanceDesc(C.Structure):
         ("grad_obj_verts", C.c_void_p), ("workspace", C.c_void_p), ("workspace_bytes", C.c_size_t),
         ("accel", C.c_void_p), ("accel_bytes", C.c_size_t),
         ("hand_nbr_off", C.c_void_p), ("hand_nbr", C.c_void_p), ("nbr_stride", C.c_int32), ("reserved1", C.c_int32),
-        ("trace", C.c_void_p),
+        ("trace", C.c_void_p), ("sticky_flags", C.c_void_p),
     ]
 
 
@@ -149,7 +151,7 @@ class GemmDesc(C.Structure):
 class AttnDesc(C.Structure):
     _fields_ = [
         ("n_img", C.c_int32), ("heads", C.c_int32), ("n_q", C.c_int32), ("n_k", C.c_int32),
-        ("q_shared", C.c_int32), ("max_ctas", C.c_int32), ("scale", C.c_float), ("reserved", C.c_int32),
+        ("q_shared", C.c_int32), ("max_ctas", C.c_int32), ("scale", C.c_float), ("variant", C.c_int32),
         ("q", C.c_void_p), ("ldq", C.c_int64), ("hsq", C.c_int64),
         ("k", C.c_void_p), ("ldk", C.c_int64), ("hsk", C.c_int64),
         ("v", C.c_void_p), ("ldv", C.c_int64), ("hsv", C.c_int64),
@@ -238,6 +240,10 @@ def load(build_if_missing: bool = False) -> C.CDLL:
     lib.foho_dec_head_bwd.argtypes = [vp, i64, vp, f32, vp, vp, vp, f32, vp, i64, i64, vp]
     lib.foho_dec_gather_rows.argtypes = [vp, i64, vp, vp, i64, i64, i32, vp]
     lib.foho_dec_cast.argtypes = [vp, i64, vp, i64, i64, i32, f32, i32, vp]
+    lib.foho_dec_compact_workspace_bytes.argtypes = [i32, i64]
+    lib.foho_dec_compact_workspace_bytes.restype = C.c_size_t
+    lib.foho_dec_compact_grad.argtypes = [vp, i32, i64, i32, vp, vp, vp, vp, vp, C.c_size_t, vp]
+    lib.foho_dec_compact_grad.restype = C.c_int
     for _n in ("layernorm", "layernorm_bwd", "softmax", "softmax_bwd", "fourier_embed", "head", "head_bwd", "gather_rows", "cast"):
         getattr(lib, "foho_dec_" + _n).restype = C.c_int
     if lib.foho_abi_version() != ABI_VERSION:

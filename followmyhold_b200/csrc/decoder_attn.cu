@@ -250,6 +250,239 @@ k_attn_fwd(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUte
   }
 }
 
+
+// ================================================================================================
+// Variant 2 (default): two query tiles per CTA in ping-pong.  With one softmax warp per scheduler the exp2 / pack /
+// store chain of a tile cannot hide its own latencies and the tensor core idles for two thirds of the time (384
+// TFLOP/s); a second softmax warpgroup on a second tile fills those slots.  One S buffer per tile (TMEM: S_A | S_B |
+// O_A | O_B), registers moved from the producer / MMA warps to the softmax warps with setmaxnreg.
+//   warp 0 TMA, warp 1 MMA, warp 2 TMEM alloc, warps 4-7 softmax of tile A, warps 8-11 softmax of tile B
+//   MMA order per key block j:  [P_A(j) ready -> O_A += P_A V_j ; S_A(j+1)]  [P_B(j) ready -> O_B += P_B V_j ; S_B(j+1)]
+// ================================================================================================
+constexpr int ATT2_SMEM = 2 * Q_BYTES + KV_STAGES * (K_BYTES + V_BYTES) + 2 * P_BYTES + 1024 + 256;
+constexpr uint32_t T2_S = 0, T2_O = 256;          // S_g at g*128, O_g at 256 + g*64
+
+__device__ __forceinline__ float ex2_approx(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
+__global__ void __launch_bounds__(384, 1)
+k_attn_fwd2(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK, const __grid_constant__ CUtensorMap tmV,
+            const AttnParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t *sQ = smem;                                           // tile A, tile B
+  uint8_t *sKV = sQ + 2 * Q_BYTES;
+  uint8_t *sP = sKV + KV_STAGES * (K_BYTES + V_BYTES);          // P_A, P_B
+  uint64_t *bars = reinterpret_cast<uint64_t *>(sP + 2 * P_BYTES);
+  uint64_t *q_full = bars, *q_empty = bars + 1;
+  uint64_t *k_full = bars + 2, *v_full = k_full + KV_STAGES, *kv_empty = v_full + KV_STAGES;
+  uint64_t *s_full = kv_empty + KV_STAGES, *s_empty = s_full + 2, *p_full = s_empty + 2, *p_empty = p_full + 2, *o_empty = p_empty + 2;
+  uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(o_empty + 2);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int nblk = p.n_k / AK;
+  const int pair_tiles = (p.q_tiles + 1) / 2;
+  const int items_per_img = p.heads * pair_tiles;
+  const int n_items = p.n_img * items_per_img;
+
+  if (warp == 0 && lane == 0) {
+    tc::tma_prefetch_desc(&tmQ); tc::tma_prefetch_desc(&tmK); tc::tma_prefetch_desc(&tmV);
+  }
+  if (warp == 1 && lane == 0) {
+    tc::mbar_init(q_full, 1); tc::mbar_init(q_empty, 1);
+    for (int i = 0; i < KV_STAGES; ++i) { tc::mbar_init(&k_full[i], 1); tc::mbar_init(&v_full[i], 1); tc::mbar_init(&kv_empty[i], 1); }
+    for (int i = 0; i < 2; ++i) {
+      tc::mbar_init(&s_full[i], 1); tc::mbar_init(&s_empty[i], 128);
+      tc::mbar_init(&p_full[i], 128); tc::mbar_init(&p_empty[i], 1); tc::mbar_init(&o_empty[i], 128);
+    }
+    tc::fence_barrier_init();
+  }
+  if (warp == 2) tc::tmem_alloc<TM_COLS>(tmem_slot);
+  tc::tc_fence_before();
+  __syncthreads();
+  tc::tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp < 4) {
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 64;");
+    if (warp == 0 && lane == 0) {
+      // ---------------------------------------------------------- TMA producer
+      uint32_t g = 0, w = 0;
+      for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++w) {
+        const int img = item / items_per_img, r = item - img * items_per_img;
+        const int h = r / pair_tiles, pt = r - h * pair_tiles;
+        tc::mbar_wait(q_empty, (w & 1) ^ 1);
+        tc::mbar_expect_tx(q_full, 2 * Q_BYTES);
+        const int qrow0 = (int)(img * p.q_rows_per_img) + pt * 2 * AQ;
+        tc::tma_load_3d(sQ, &tmQ, q_full, 0, qrow0, h);
+        tc::tma_load_3d(sQ + Q_BYTES, &tmQ, q_full, 0, qrow0 + AQ, h);      // beyond the last row: zero filled
+        for (int j = 0; j < nblk; ++j, ++g) {
+          const uint32_t s = g % KV_STAGES, ph = (g / KV_STAGES) & 1;
+          tc::mbar_wait(&kv_empty[s], ph ^ 1);
+          uint8_t *sk = sKV + s * (K_BYTES + V_BYTES), *sv = sk + K_BYTES;
+          tc::mbar_expect_tx(&k_full[s], K_BYTES);
+          tc::tma_load_3d(sk, &tmK, &k_full[s], 0, img * p.n_k + j * AK, h);
+          tc::mbar_expect_tx(&v_full[s], V_BYTES);
+          tc::tma_load_3d(sv, &tmV, &v_full[s], 0, img * p.n_k + j * AK, h);
+        }
+      }
+    } else if (warp == 1 && lane == 0) {
+      // ---------------------------------------------------------- MMA issuer
+      constexpr uint32_t idesc_s = tc::idesc_f16(AQ, AK, 0, 0);
+      constexpr uint32_t idesc_o = tc::idesc_f16(AQ, HD, 0, 1);
+      uint32_t g = 0, w = 0;
+      auto issue_s = [&](uint32_t gg, int grp) {          // S_grp(gg) = Q_grp K_gg^T
+        const uint32_t s = gg % KV_STAGES, ph = (gg / KV_STAGES) & 1;
+        tc::mbar_wait(&k_full[s], ph);
+        tc::mbar_wait(&s_empty[grp], (gg & 1) ^ 1);
+        tc::tc_fence_after();
+        const uint32_t q_addr = tc::smem_u32(sQ + grp * Q_BYTES);
+        const uint32_t k_addr = tc::smem_u32(sKV + s * (K_BYTES + V_BYTES));
+#pragma unroll
+        for (int k = 0; k < HD / 16; ++k)
+          tc::mma_f16_ss(tmem_base + T2_S + grp * 128, tc::smem_desc_sw128(q_addr + k * 32, 16, 1024),
+                         tc::smem_desc_sw128(k_addr + k * 32, 16, 1024), idesc_s, k != 0);
+        tc::mma_commit(&s_full[grp]);
+      };
+      for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++w) {
+        tc::mbar_wait(q_full, w & 1);
+        issue_s(g, 0);
+        issue_s(g, 1);
+        for (int j = 0; j < nblk; ++j, ++g) {
+          const uint32_t s = g % KV_STAGES, ph = (g / KV_STAGES) & 1;
+          const uint32_t v_addr = tc::smem_u32(sKV + s * (K_BYTES + V_BYTES) + K_BYTES);
+#pragma unroll
+          for (int grp = 0; grp < 2; ++grp) {
+            tc::mbar_wait(&p_full[grp], g & 1);
+            if (grp == 0) tc::mbar_wait(&v_full[s], ph);
+            if (j == 0) tc::mbar_wait(&o_empty[grp], (w & 1) ^ 1);
+            tc::tc_fence_after();
+            const uint32_t p_addr = tc::smem_u32(sP + grp * P_BYTES);
+#pragma unroll
+            for (int k = 0; k < AK / 16; ++k)
+              tc::mma_f16_ss(tmem_base + T2_O + grp * 64, tc::smem_desc_sw128(p_addr + (k >> 2) * (AQ * 128) + (k & 3) * 32, 16, 1024),
+                             tc::smem_desc_sw128(v_addr + k * 2048, AK * 128, 1024), idesc_o, (j | k) != 0);
+            tc::mma_commit(&p_empty[grp]);
+            if (grp == 1) tc::mma_commit(&kv_empty[s]);
+            if (j + 1 < nblk) issue_s(g + 1, grp);
+            else if (grp == 1) tc::mma_commit(q_empty);
+          }
+        }
+      }
+    }
+  } else {
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 208;");
+    // ------------------------------------------------------------ softmax group grp on its query tile
+    const int grp = (warp - 4) >> 2;
+    const int q = warp & 3;
+    const int row = q * 32 + lane;
+    const uint32_t lane_off = (uint32_t)(q * 32) << 16;
+    const uint32_t s_addr = tmem_base + T2_S + grp * 128 + lane_off;
+    const uint32_t o_addr = tmem_base + T2_O + grp * 64 + lane_off;
+    uint8_t *pb = sP + grp * P_BYTES + row * 128;
+    uint32_t g = 0, w = 0;
+    for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++w) {
+      const int img = item / items_per_img, r = item - img * items_per_img;
+      const int h = r / pair_tiles, pt = r - h * pair_tiles;
+      float m_used = 0.f, l = 0.f;
+      for (int j = 0; j < nblk; ++j, ++g) {
+        tc::mbar_wait(&s_full[grp], g & 1);
+        tc::tc_fence_after();
+        uint32_t sv[4][32];
+#pragma unroll
+        for (int c = 0; c < 4; ++c) tc::tmem_ld32(s_addr + c * 32, sv[c]);
+        tc::tmem_ld_wait();
+        tc::tc_fence_before();
+        tc::mbar_arrive(&s_empty[grp]);
+        float bm0 = -INFINITY, bm1 = -INFINITY, bm2 = -INFINITY, bm3 = -INFINITY;
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+          bm0 = fmaxf(bm0, __uint_as_float(sv[0][i])); bm1 = fmaxf(bm1, __uint_as_float(sv[1][i]));
+          bm2 = fmaxf(bm2, __uint_as_float(sv[2][i])); bm3 = fmaxf(bm3, __uint_as_float(sv[3][i]));
+        }
+        const float bm = fmaxf(fmaxf(bm0, bm1), fmaxf(bm2, bm3)) * p.scale_log2;
+        float corr = 1.f;
+        bool need = false;
+        if (j == 0) {
+          m_used = bm;
+        } else if (bm > m_used + 8.f) {
+          corr = ex2_approx(m_used - bm);
+          m_used = bm;
+          need = true;
+        }
+        // the previous product of this tile must be complete before O is rescaled or P overwritten
+        tc::mbar_wait(&p_empty[grp], (g & 1) ^ 1);
+        if (__any_sync(0xffffffffu, need)) {
+          tc::tc_fence_after();
+#pragma unroll
+          for (int c = 0; c < 2; ++c) {
+            uint32_t ov[32];
+            tc::tmem_ld32(o_addr + c * 32, ov);
+            tc::tmem_ld_wait();
+#pragma unroll
+            for (int i = 0; i < 32; ++i) ov[i] = __float_as_uint(__uint_as_float(ov[i]) * corr);
+            tc::tmem_st32(o_addr + c * 32, ov);
+          }
+          tc::tmem_st_wait();
+        }
+        float sum0 = 0.f, sum1 = 0.f;
+        const float neg_m = -m_used;
+#pragma unroll
+        for (int cc = 0; cc < 16; ++cc) {                          // 16-byte chunk cc = keys 8cc .. 8cc+7
+          uint32_t pk[4];
+#pragma unroll
+          for (int t = 0; t < 4; ++t) {
+            const int e = (cc & 3) * 8 + 2 * t;
+            const float a = ex2_approx(fmaf(__uint_as_float(sv[cc >> 2][e]), p.scale_log2, neg_m));
+            const float b = ex2_approx(fmaf(__uint_as_float(sv[cc >> 2][e + 1]), p.scale_log2, neg_m));
+            sum0 += a; sum1 += b;
+            const __half2 hh = __floats2half2_rn(a, b);
+            pk[t] = *reinterpret_cast<const uint32_t *>(&hh);
+          }
+          *reinterpret_cast<uint4 *>(pb + (cc >> 3) * (AQ * 128) + (((cc & 7) ^ (row & 7)) << 4)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+        }
+        l = l * corr + (sum0 + sum1);
+        tc::fence_proxy_async_smem();
+        tc::tc_fence_before();
+        tc::mbar_arrive(&p_full[grp]);
+      }
+      // ---- epilogue: O / l
+      tc::mbar_wait(&p_empty[grp], (g & 1) ^ 1);                    // the last product of this item (block g-1)
+      tc::tc_fence_after();
+      const int qrow = (pt * 2 + grp) * AQ + row;
+      const float inv = 1.f / l;
+      __half *op = p.out + (long long)img * p.out_img_stride + (long long)qrow * p.ldo + h * HD;
+#pragma unroll
+      for (int c = 0; c < 2; ++c) {
+        uint32_t ov[32];
+        tc::tmem_ld32(o_addr + c * 32, ov);
+        tc::tmem_ld_wait();
+        if (qrow < p.n_q) {
+#pragma unroll
+          for (int i = 0; i < 32; i += 8) {
+            __align__(16) __half2 hh[4];
+#pragma unroll
+            for (int t = 0; t < 4; ++t)
+              hh[t] = __floats2half2_rn(__uint_as_float(ov[i + 2 * t]) * inv, __uint_as_float(ov[i + 2 * t + 1]) * inv);
+            *reinterpret_cast<uint4 *>(op + c * 32 + i) = *reinterpret_cast<uint4 *>(hh);
+          }
+        }
+      }
+      tc::tc_fence_before();
+      tc::mbar_arrive(&o_empty[grp]);
+    }
+  }
+  tc::tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc::tc_fence_after();
+    tc::tmem_dealloc<TM_COLS>(tmem_base);
+  }
+}
+
 }  // namespace
 
 extern "C" int foho_tc_attention(const foho_attn_desc *d, void *cuda_stream) {
@@ -278,11 +511,19 @@ extern "C" int foho_tc_attention(const foho_attn_desc *d, void *cuda_stream) {
     FOHO_CUDA_TRY(cudaGetDevice(&dev));
     FOHO_CUDA_TRY(cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev));
   }
-  FOHO_CUDA_TRY(cudaFuncSetAttribute(k_attn_fwd, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM));
-  long long items = (long long)p.n_img * p.heads * p.q_tiles;
-  int grid = (int)(items < sm_count ? items : sm_count);
-  if (d->max_ctas > 0 && grid > d->max_ctas) grid = d->max_ctas;
-  k_attn_fwd<<<grid, 256, ATT_SMEM, st>>>(tmQ, tmK, tmV, p);
+  if (d->variant == 1) {     // one query tile per CTA (the first version; kept for A/B measurements)
+    FOHO_CUDA_TRY(cudaFuncSetAttribute(k_attn_fwd, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM));
+    long long items = (long long)p.n_img * p.heads * p.q_tiles;
+    int grid = (int)(items < sm_count ? items : sm_count);
+    if (d->max_ctas > 0 && grid > d->max_ctas) grid = d->max_ctas;
+    k_attn_fwd<<<grid, 256, ATT_SMEM, st>>>(tmQ, tmK, tmV, p);
+  } else {
+    FOHO_CUDA_TRY(cudaFuncSetAttribute(k_attn_fwd2, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT2_SMEM));
+    long long items = (long long)p.n_img * p.heads * ((p.q_tiles + 1) / 2);
+    int grid = (int)(items < sm_count ? items : sm_count);
+    if (d->max_ctas > 0 && grid > d->max_ctas) grid = d->max_ctas;
+    k_attn_fwd2<<<grid, 384, ATT2_SMEM, st>>>(tmQ, tmK, tmV, p);
+  }
   FOHO_LAUNCH_CHECK();
   return 0;
 }

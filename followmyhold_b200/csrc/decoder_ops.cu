@@ -356,6 +356,94 @@ __global__ void k_add_f16(const __half *a, const __half *b, __half *y, long long
   }
 }
 
+
+// ---------------------------------------------------------------- sparse view of a dense gradient volume
+// The energy touches a few thousand voxels of the lattice (trilinear corners of the hand vertices, the voxels inside
+// both hand and object); the adjoint of the decoder only needs those rows.  Deterministic three-pass compaction
+// (count per 4096-voxel block, exclusive scan, scatter) of the non-zero entries of g [B, V] into idx / val [B, cap].
+constexpr int NZ_BLOCK = 4096;
+__device__ __forceinline__ int nz_local(const float *g, long long V, long long base, int t, float (&v)[16]) {
+  int c = 0;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const long long e = base + ((long long)i * 256 + t) * 4;
+    float4 x = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (e + 3 < V) x = *reinterpret_cast<const float4 *>(g + e);
+    else { if (e < V) x.x = g[e]; if (e + 1 < V) x.y = g[e + 1]; if (e + 2 < V) x.z = g[e + 2]; }
+    v[4 * i] = x.x; v[4 * i + 1] = x.y; v[4 * i + 2] = x.z; v[4 * i + 3] = x.w;
+    c += (x.x != 0.f) + (x.y != 0.f) + (x.z != 0.f) + (x.w != 0.f);
+  }
+  return c;
+}
+__global__ void k_nz_count(const float *__restrict__ g, long long V, int nblk, int *__restrict__ counts) {
+  const int b = blockIdx.y, blk = blockIdx.x, t = threadIdx.x;
+  float v[16];
+  int c = nz_local(g + (long long)b * V, V, (long long)blk * NZ_BLOCK, t, v);
+  c = __reduce_add_sync(0xffffffffu, c);
+  __shared__ int ws[8];
+  if ((t & 31) == 0) ws[t >> 5] = c;
+  __syncthreads();
+  if (t == 0) { int s = 0; for (int i = 0; i < 8; ++i) s += ws[i]; counts[(long long)b * nblk + blk] = s; }
+}
+__global__ void k_nz_scan(int *__restrict__ counts, int nblk, int *__restrict__ total, int cap, int *__restrict__ flags) {
+  // one CTA per image: exclusive scan of its block counts in place
+  const int b = blockIdx.x, t = threadIdx.x;
+  int *c = counts + (long long)b * nblk;
+  __shared__ int ws[32];
+  __shared__ int carry;
+  if (t == 0) carry = 0;
+  __syncthreads();
+  for (int base = 0; base < nblk; base += 1024) {
+    const int i = base + t;
+    const int x = i < nblk ? c[i] : 0;
+    int incl = x;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { int y = __shfl_up_sync(0xffffffffu, incl, o); if ((t & 31) >= o) incl += y; }
+    if ((t & 31) == 31) ws[t >> 5] = incl;
+    __syncthreads();
+    if (t < 32) {
+      int w = ws[t], wi = w;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) { int y = __shfl_up_sync(0xffffffffu, wi, o); if (t >= o) wi += y; }
+      ws[t] = wi - w;
+    }
+    __syncthreads();
+    const int excl = carry + ws[t >> 5] + incl - x;
+    if (i < nblk) c[i] = excl;
+    __syncthreads();
+    if (t == 1023) carry = excl + x;
+    __syncthreads();
+  }
+  if (t == 0) { total[b] = carry; if (carry > cap && flags) atomicOr(flags, 1); }
+}
+__global__ void k_nz_scatter(const float *__restrict__ g, long long V, int nblk, const int *__restrict__ offsets, int cap, int *__restrict__ idx,
+                             float *__restrict__ val) {
+  const int b = blockIdx.y, blk = blockIdx.x, t = threadIdx.x;
+  float v[16];
+  const int c = nz_local(g + (long long)b * V, V, (long long)blk * NZ_BLOCK, t, v);
+  int incl = c;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) { int y = __shfl_up_sync(0xffffffffu, incl, o); if ((t & 31) >= o) incl += y; }
+  __shared__ int ws[8];
+  if ((t & 31) == 31) ws[t >> 5] = incl;
+  __syncthreads();
+  int pre = 0;
+  for (int i = 0; i < (t >> 5); ++i) pre += ws[i];
+  int pos = offsets[(long long)b * nblk + blk] + pre + incl - c;
+  if (c == 0) return;
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+      if (v[4 * i + k] != 0.f) {
+        if (pos < cap) {
+          idx[(long long)b * cap + pos] = (int)((long long)blk * NZ_BLOCK + ((long long)i * 256 + t) * 4 + k);
+          val[(long long)b * cap + pos] = v[4 * i + k];
+        }
+        ++pos;
+      }
+}
+
 inline int blocks_for(long long work, int per_block) { return (int)((work + per_block - 1) / per_block); }
 
 }  // namespace
@@ -462,6 +550,28 @@ extern "C" int foho_dec_cast(const void *in, int64_t ld_in, void *out, int64_t l
     if (ld_in != cols || ld_out != cols) return FOHO_E_ARG;
     k_add_f16<<<blocks_for((n + 7) / 8, 256), 256, 0, st>>>((const __half *)in, (const __half *)out, (__half *)out, n);
   } else return FOHO_E_ARG;
+  FOHO_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" size_t foho_dec_compact_workspace_bytes(int32_t B, int64_t V) {
+  if (B <= 0 || V <= 0) return 0;
+  return (size_t)B * (size_t)((V + NZ_BLOCK - 1) / NZ_BLOCK) * sizeof(int);
+}
+
+extern "C" int foho_dec_compact_grad(const float *g, int32_t B, int64_t V, int32_t cap, int32_t *idx, float *val, int32_t *count,
+                                     int32_t *flags, void *workspace, size_t workspace_bytes, void *cuda_stream) {
+  if (!g || !idx || !val || !count || !workspace) return FOHO_E_NULL;
+  if (B <= 0 || V <= 0 || cap <= 0 || V > 0x7fffffffLL) return FOHO_E_SHAPE;
+  if (workspace_bytes < foho_dec_compact_workspace_bytes(B, V) || (reinterpret_cast<uintptr_t>(g) & 15) || V % 4) return FOHO_E_WORKSPACE;
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(cuda_stream);
+  const int nblk = (int)((V + NZ_BLOCK - 1) / NZ_BLOCK);
+  int *counts = reinterpret_cast<int *>(workspace);
+  FOHO_CUDA_TRY(cudaMemsetAsync(idx, 0, (size_t)B * cap * sizeof(int), st));
+  FOHO_CUDA_TRY(cudaMemsetAsync(val, 0, (size_t)B * cap * sizeof(float), st));
+  k_nz_count<<<dim3(nblk, B), 256, 0, st>>>(g, V, nblk, counts);
+  k_nz_scan<<<B, 1024, 0, st>>>(counts, nblk, count, cap, flags);
+  k_nz_scatter<<<dim3(nblk, B), 256, 0, st>>>(g, V, nblk, counts, cap, idx, val);
   FOHO_LAUNCH_CHECK();
   return 0;
 }

@@ -11,6 +11,10 @@
 #define FOHO_HD inline
 #endif
 
+// max(x, 0) that keeps a NaN, like torch.relu (fmaxf returns 0 for a NaN input, and a NaN volume would slip past the
+// NaN guard of pipelines.py:1442-1444,1590-1592)
+FOHO_HD float foho_relu(float x) { return x > 0.f ? x : (x != x ? x : 0.f); }
+
 // IEEE single ops that must never be contracted into FMAs: the inside/outside rule is
 // specified bit-for-bit (oracle/guidance_oracle.py::raster_parity_inside).
 #if defined(__CUDA_ARCH__)

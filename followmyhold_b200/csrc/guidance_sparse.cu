@@ -571,8 +571,8 @@ __global__ void __launch_bounds__(VE_THREADS) k_vertex_early(foho_guidance_desc 
           dsy += (dy ? 1.f : -1.f) * wx * wz * v;
           dsz += (dz ? 1.f : -1.f) * wx * wy * v;
         }
-    v2[0] = fmaxf(-s, 0.f);
-    v2[1] = fmaxf(fabsf(s) - d.w.con_margin, 0.f);
+    v2[0] = foho_relu(-s);
+    v2[1] = foho_relu(fabsf(s) - d.w.con_margin);
     float dLds = 0.f;
     if (s < 0.f) dLds -= d.w.w_pen * invV;
     if (fabsf(s) > d.w.con_margin) dLds += d.w.w_con * invV * (s > 0.f ? 1.f : -1.f);
@@ -817,6 +817,7 @@ __global__ void __launch_bounds__(ASM_THREADS) k_assemble(foho_guidance_desc d, 
     T[FOHO_T_DIST] = 0.f; T[FOHO_T_VREG] = 0.f; T[FOHO_T_EDGE] = 0.f; T[FOHO_T_MEAN_D2] = 0.f;
     T[FOHO_T_NCAND] = (float)cn[CNT_NCAND];
     T[FOHO_T_FLAGS] = (float)cn[CNT_FLAGS];
+    if (d.sticky_flags && cn[CNT_FLAGS]) atomicOr(d.sticky_flags + b, cn[CNT_FLAGS]);
     (void)cobj;
     T[FOHO_T_TOTAL] = w_int * count + W.w_treg_o * tr_o + W.w_hand * (W.w_kp * L_kp + W.w_treg_h * tr_h) +
                       W.w_pen * L_pen + W.w_con * L_con + W.w_ivol * L_int + W.w_ch * L_ch + W.w_mom * (float)L_mom;

@@ -70,7 +70,7 @@ __device__ __forceinline__ float4 voxel4(float4 s, float fx, float fy, const Str
                                          StreamAcc &a) {
   float r2 = fmaf(fy, fy, __fmul_rn(fx, fx));          // explicit: every instantiation rounds the same way
   float crow = fmaf(c.k2, r2, fmaf(c.ex, fx, fmaf(c.ey, fy, c.f)));
-  float w0 = fmaxf(-s.x, 0.f), w1 = fmaxf(-s.y, 0.f), w2 = fmaxf(-s.z, 0.f), w3 = fmaxf(-s.w, 0.f);
+  float w0 = foho_relu(-s.x), w1 = foho_relu(-s.y), w2 = foho_relu(-s.z), w3 = foho_relu(-s.w);
   float4 g;
   g.x = s.x < 0.f ? cz[0] + crow : 0.f;
   g.y = s.y < 0.f ? cz[1] + crow : 0.f;
@@ -343,7 +343,7 @@ __global__ void __launch_bounds__(256) k_stream_any(const float *__restrict__ sd
     float r2 = fx * fx + fy * fy;
     float crow = fmaf(c.k2, r2, fmaf(c.ex, fx, fmaf(c.ey, fy, c.f)));
     float czz = fmaf(c.k2 * fz, fz, c.ez * fz);
-    float w = fmaxf(-s, 0.f);
+    float w = foho_relu(-s);
     __stcs(G + i, s < 0.f ? czz + crow : 0.f);
     v[0] += w;
     v[1] = fmaf(fx, w, v[1]);

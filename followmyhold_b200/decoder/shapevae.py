@@ -120,6 +120,29 @@ class _Ops:
         return dst
 
 
+class GradCompactor:
+    """dense dE/dSDF [B, V] -> (idx int32 [B, cap], val float32 [B, cap], count int32 [B]) on the device
+    (``foho_dec_compact_grad``: deterministic order, zero padded, overflow flag)."""
+
+    def __init__(self, B: int, V: int, cap: int, device):
+        self.lib = _lib.load()
+        self.B, self.V, self.cap = B, V, cap
+        self.idx = torch.zeros(B, cap, dtype=torch.int32, device=device)
+        self.val = torch.zeros(B, cap, dtype=torch.float32, device=device)
+        self.count = torch.zeros(B, dtype=torch.int32, device=device)
+        self.flags = torch.zeros(1, dtype=torch.int32, device=device)
+        nbytes = self.lib.foho_dec_compact_workspace_bytes(B, V)
+        self.ws = torch.empty(max(nbytes, 16), dtype=torch.uint8, device=device)
+
+    def __call__(self, g: torch.Tensor, stream=None):
+        if g.dtype != torch.float32 or not g.is_contiguous() or g.numel() != self.B * self.V:
+            raise ValueError("expected a contiguous float32 [B, V] gradient")
+        _lib.check("foho_dec_compact_grad", self.lib.foho_dec_compact_grad(
+            g.data_ptr(), self.B, self.V, self.cap, self.idx.data_ptr(), self.val.data_ptr(), self.count.data_ptr(),
+            self.flags.data_ptr(), self.ws.data_ptr(), self.ws.numel(), _sp(stream)))
+        return self.idx, self.val
+
+
 class DecoderWeights:
     """Device copies of the decode half of ``ShapeVAE``: fp16 matrices for the tensor cores, fp32 biases and
     LayerNorm parameters.  ``state_dict`` keys are the reference package's (see the module docstring)."""
@@ -274,11 +297,14 @@ class LatentDecoder:
         return out
 
     # ------------------------------------------------------------------ adjoint
-    def backward(self, idx: torch.Tensor, g_sdf: torch.Tensor, out: Optional[torch.Tensor] = None, stream=None) -> torch.Tensor:
+    def backward(self, idx: torch.Tensor, g_sdf: torch.Tensor, out: Optional[torch.Tensor] = None, stream=None,
+                 out_scale: float = 1.0) -> torch.Tensor:
         """dE/d(latents) [B, 3072, 64] float32 from dE/dSDF on a sparse set of lattice points.
 
         ``idx`` [B, M] int32 lattice indices of the rows that carry a gradient, ``g_sdf`` [B, M] float32 their
-        dE/dSDF (pad with index 0 / gradient 0).  Uses the token-side activations of the last ``forward``."""
+        dE/dSDF (pad with index 0 / gradient 0).  Uses the token-side activations of the last ``forward``.
+        ``out_scale`` multiplies the result (the ``1 - sigma`` of ``x1 = x_t + (1 - sigma) v``, schedulers.py:481,
+        turns dE/dx1 into dE/dv)."""
         if not self._fwd_done:
             raise RuntimeError("forward() first: the adjoint reuses its token-side activations")
         w, ops, B = self.w, self.ops, self.B
@@ -378,5 +404,5 @@ class LatentDecoder:
         if out is None:
             out = torch.empty(B, TOKENS, EMBED, **f32)
         # float32 out; the epilogue undoes the loss scale and applies the call site's 1/scale_factor (:297)
-        tc.gemm(g, w.post_kl_w, out=out.view(R, EMBED), b_mn=True, alpha=1.0 / (w.scale_factor * ls), stream=stream)
+        tc.gemm(g, w.post_kl_w, out=out.view(R, EMBED), b_mn=True, alpha=out_scale / (w.scale_factor * ls), stream=stream)
         return out

@@ -86,7 +86,7 @@ def gemm(a: torch.Tensor, b: torch.Tensor, out: Optional[torch.Tensor] = None, *
 
 
 def attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, n_img: int, out: Optional[torch.Tensor] = None, *,
-              q_shared: bool = False, scale: float = 0.125, max_ctas: int = 0,
+              q_shared: bool = False, scale: float = 0.125, max_ctas: int = 0, variant: int = 0,
               stream: Optional[torch.cuda.Stream] = None) -> torch.Tensor:
     """``out[i, q, h, :] = softmax_k(scale * Q[q, h] . K[i, k, h]) V[i, k, h]`` on the tensor cores.
 
@@ -103,7 +103,7 @@ def attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, n_img: int, out
         out = torch.empty(n_img, n_q, heads * 64, dtype=torch.float16, device=q.device)
     d = _lib.AttnDesc()
     d.n_img, d.heads, d.n_q, d.n_k = n_img, heads, n_q, n_k
-    d.q_shared, d.max_ctas, d.scale = int(q_shared), max_ctas, scale
+    d.q_shared, d.max_ctas, d.scale, d.variant = int(q_shared), max_ctas, scale, variant
     d.q, d.ldq, d.hsq = q.data_ptr(), q.stride(0), q.stride(1)
     d.k, d.ldk, d.hsk = k.data_ptr(), k.stride(0), k.stride(1)
     d.v, d.ldv, d.hsv = v.data_ptr(), v.stride(0), v.stride(1)

@@ -249,6 +249,9 @@ class GuidanceEngine:
             d.obj_edge_offsets = obj_mesh.edge_offsets.data_ptr()
             d.grad_obj_verts = self.grad_obj_verts.data_ptr()
         d.workspace, d.workspace_bytes = self._ws_ptr, self._ws_bytes
+        if getattr(self, "sticky_flags", None) is None or self.sticky_flags.shape[0] != B:
+            self.sticky_flags = torch.zeros(B, dtype=torch.int32, device=self.device)
+        d.sticky_flags = self.sticky_flags.data_ptr()
         accel = self._accel_for is st and P > 0
         if accel:
             d.accel, d.accel_bytes = self._accel_ptr, self._accel_bytes
@@ -257,6 +260,19 @@ class GuidanceEngine:
         # prep, stream, raster, compact, voxdist, vertex_early, finalize_verts, assemble (+ key-points, + chamfer 1 or 2)
         self.launches_per_eval = 8 + (1 if use_kp and Vh > 744 else 0) + ((2 if accel else 1) if P > 0 else 0)
         return d
+
+    def check_flags(self) -> None:
+        """Hard error for what the kernels can only flag (they never synchronise): a candidate-list overflow in ANY
+        evaluation since the engine was built (bit0: more voxels inside both hand and object than the workspace
+        holds -- the penetration term and count were truncated).  Synchronises; call it after a run."""
+        sf = getattr(self, "sticky_flags", None)
+        if sf is None:
+            return
+        bad = [(b, int(f)) for b, f in enumerate(sf.cpu().tolist()) if int(f) & 1]
+        if bad:
+            raise _lib.FohoStatusError("foho_guidance_energy_fwd_bwd", _lib.FOHO_E_WORKSPACE,
+                                       f"candidate list overflow for images {[b for b, _ in bad]}: the hand/object "
+                                       "intersection has more voxels than the workspace capacity")
 
     def launch(self, desc: _lib.GuidanceDesc, stream: Optional[torch.cuda.Stream] = None) -> None:
         s = stream if stream is not None else torch.cuda.current_stream(self.device)

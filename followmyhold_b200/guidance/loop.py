@@ -58,7 +58,7 @@ class GuidanceLoop:
     def __init__(self, B: int, D: int, statics: GuidanceStatics, P: int, device="cuda:0",
                  config: Optional[OptimizationConfig] = None, weights=None, latent_elems: int = LATENT_SHAPE[0] * LATENT_SHAPE[1],
                  decoder_alpha: float = 0.05, stream_variant: int = 0, seed: int = 0, micro_batches: int = 1,
-                 loss_log_every: int = 0):
+                 loss_log_every: int = 0, mock_decoder: bool = True):
         """``loss_log_every`` = n > 0 keeps the loss terms of every n-th inner iteration of every step
         (``loss_history``; the reference logs every 10th when ``FOHO_DEBUG_DIR`` is set, pipelines.py:1446-1450,
         1594-1598) -- device-to-device copies inside the step graph, no host sync.
@@ -98,16 +98,20 @@ class GuidanceLoop:
         self.engine = self.lanes[0].engine       # the whole batch when micro_batches == 1
         self.opt = self.lanes[0].opt
         vol = D * D * D
-        if self.L > vol:
-            raise ValueError("mock decoder needs latent_elems <= D^3")
-        g = torch.Generator().manual_seed(seed)
-        # one latent token (64 channels) drives one run of 64 consecutive voxels along z
-        run = LATENT_SHAPE[1] if (self.L % LATENT_SHAPE[1] == 0 and vol % LATENT_SHAPE[1] == 0) else 1
-        starts = torch.randperm(vol // run, generator=g)[: self.L // run].sort().values * run
-        self.tap = (starts.view(-1, 1) + torch.arange(run).view(1, -1)).reshape(-1).to(dev)   # int64 voxel taps
-        self.alpha = float(decoder_alpha)
+        self.mock_decoder = bool(mock_decoder)
         f32 = torch.float32
-        self.sdf0 = torch.empty(B, D, D, D, dtype=f32, device=dev)     # decoder output for x1 = 0 (per image)
+        self.alpha = float(decoder_alpha)
+        if self.mock_decoder:
+            # the linear stand-in decoder: one latent token (64 channels) drives one run of 64 consecutive voxels along z
+            if self.L > vol:
+                raise ValueError("mock decoder needs latent_elems <= D^3 (pass mock_decoder=False to drive a real decoder)")
+            g = torch.Generator().manual_seed(seed)
+            run = LATENT_SHAPE[1] if (self.L % LATENT_SHAPE[1] == 0 and vol % LATENT_SHAPE[1] == 0) else 1
+            starts = torch.randperm(vol // run, generator=g)[: self.L // run].sort().values * run
+            self.tap = (starts.view(-1, 1) + torch.arange(run).view(1, -1)).reshape(-1).to(dev)   # int64 voxel taps
+            self.sdf0 = torch.empty(B, D, D, D, dtype=f32, device=dev)     # decoder output for x1 = 0 (per image)
+        else:
+            self.tap, self.sdf0 = None, None         # run_schedule_decoder / run_schedule_tc_decoder only
         self.sdf = torch.empty(B, D, D, D, dtype=f32, device=dev)      # current decode
         self.x_t = torch.zeros(B, self.L, dtype=f32, device=dev)       # latents
         self.velocity = torch.zeros(B, self.L, dtype=f32, device=dev)  # model output being optimised
@@ -427,6 +431,91 @@ class GuidanceLoop:
                     self.x_t.data_ptr(), self.velocity.data_ptr(), self.prev.data_ptr(), None, self.x_t.numel(), sigma,
                     sigma_next, sp))
                 self.x_t.copy_(self.prev)
+
+    def run_schedule_tc_decoder(self, model_output, decoder, first_step: int = 0, last_step: Optional[int] = None,
+                                grad_cap: int = 8192, keep_mom: bool = False) -> None:
+        """The guided denoise loop with the reference's OWN decoder in it -- ``latent2sdf`` (pipelines.py:292-312)
+        and its adjoint on the tensor cores (``decoder``: a ``followmyhold_b200.decoder.shapevae.LatentDecoder``
+        whose lattice is this loop's D^3 grid) -- instead of torch autograd through a torch module
+        (``run_schedule_decoder``) or the linear stand-in (``run_schedule_device``).  Per inner iteration
+        (:1507-1601): ``step_final`` -> decode -> fused energy kernels -> sparse view of dE/dSDF (the energy
+        touches a few thousand voxels) -> decoder adjoint -> dE/dv = (1 - sigma) dE/dx1 -> fused AdamW.
+        No torch arithmetic, no host sync inside the loop.
+
+        The builder-added dense volume term ``L_mom`` is switched off here unless ``keep_mom``: it would make
+        every interior voxel carry a gradient; its reference twin (``obj_verts_loss``, :1570) lives on the
+        extracted mesh.  ``grad_cap``: rows per image the adjoint handles; an overflow sets
+        ``self.grad_compactor.flags`` (checked by ``check_overflow()``)."""
+        from ..decoder.shapevae import GradCompactor
+        if self.micro_batches != 1:
+            raise ValueError("run_schedule_tc_decoder drives one lane: construct the loop with micro_batches=1")
+        if decoder.B != self.B or decoder.Nq != self.D ** 3 or self.L != LATENT_SHAPE[0] * LATENT_SHAPE[1]:
+            raise ValueError("decoder batch / lattice / latent shape do not match this loop")
+        cfg = self.cfg
+        last = cfg.num_inference_steps - 1 if last_step is None else last_step
+        ln = self.lanes[0]
+        eng, opt = ln.engine, ln.opt
+        B, V = self.B, self.D ** 3
+        if getattr(self, "grad_compactor", None) is None or self.grad_compactor.cap != grad_cap:
+            self.grad_compactor = GradCompactor(B, V, grad_cap, self.device)
+        comp = self.grad_compactor
+        with torch.cuda.device(self.device):
+            s = torch.cuda.current_stream(self.device)
+            sp = C.c_void_p(s.cuda_stream)
+            for i in range(first_step, last + 1):
+                v = model_output(i, self.x_t) if callable(model_output) else model_output[i]
+                self.velocity.copy_(v)
+                phase = self.phase_of_step(i)
+                sigma, sigma_next = float(self.sigmas[i]), float(self.sigmas[i + 1])
+                late = i >= cfg.num_inference_steps - 3
+                if phase != 0:
+                    opt.set_phase(phase)
+                    opt.reset()
+                    self.nan_flag.zero_()
+                    w = _lib.Weights()
+                    C.memmove(C.byref(w), C.byref(self.phase_weights(phase)), C.sizeof(_lib.Weights))
+                    if not keep_mom:
+                        w.w_mom = 0.0
+                    for k in range(self.phase_iterations(phase)):
+                        if phase == 1:
+                            desc = eng.make_desc(self.sdf, self.theta, ln.statics, late_step=late)
+                            desc.w = w
+                            desc.stage_mask = 1 | 4 | 16
+                            eng.launch(desc, s)
+                            vel = gvel = None
+                        else:
+                            _lib.check("foho_scheduler_step", self.lib.foho_scheduler_step(
+                                self.x_t.data_ptr(), self.velocity.data_ptr(), None, self.x1.data_ptr(), self.x_t.numel(),
+                                sigma, sigma_next, sp))                                   # step_final (:1507)
+                            decoder.forward(self.x1.view(B, LATENT_SHAPE[0], LATENT_SHAPE[1]), out=self.sdf.view(B, V), stream=s)
+                            desc = eng.make_desc(self.sdf, self.theta, ln.statics, late_step=late)
+                            desc.w = w
+                            eng.launch(desc, s)
+                            idx, val = comp(eng.grad_sdf.view(B, V), stream=s)
+                            decoder.backward(idx, val, out=self.grad_velocity.view(B, LATENT_SHAPE[0], LATENT_SHAPE[1]), stream=s,
+                                             out_scale=1.0 - sigma)
+                            vel, gvel = self.velocity, self.grad_velocity
+                        if self.loss_history is not None and k % self.loss_log_every == 0:
+                            self.loss_history[i, k // self.loss_log_every].copy_(eng.terms)
+                        opt.step(self.theta, eng.grad_theta, vel, gvel, self.x_t, self.x1, sigma=sigma, stream=s,
+                                 terms=eng.terms, nan_flag=self.nan_flag)
+                    self.nan_steps[i].copy_(self.nan_flag)
+                _lib.check("foho_scheduler_step", self.lib.foho_scheduler_step(
+                    self.x_t.data_ptr(), self.velocity.data_ptr(), self.prev.data_ptr(), None, self.x_t.numel(), sigma,
+                    sigma_next, sp))
+                self.x_t.copy_(self.prev)
+
+    def check_flags(self) -> None:
+        """Raise if any evaluation of any lane overflowed its candidate list (see GuidanceEngine.check_flags)."""
+        for ln in self.lanes:
+            ln.engine.check_flags()
+
+    def check_overflow(self) -> None:
+        """Raise when the sparse gradient view of ``run_schedule_tc_decoder`` overflowed its capacity (synchronises)."""
+        comp = getattr(self, "grad_compactor", None)
+        if comp is not None and int(comp.flags.item()) & 1:
+            raise _lib.FohoStatusError("foho_dec_compact_grad", -2, f"more than grad_cap={comp.cap} voxels of one image carry a "
+                                       f"gradient (counts {comp.count.tolist()}); raise grad_cap")
 
     def run_step_device(self, step_index: int) -> None:
         """Replay one guided-denoise step; inputs (sdf0, x_t, velocity, theta) already in HBM."""

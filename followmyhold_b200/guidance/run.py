@@ -322,6 +322,7 @@ def _run_batch(chunk, model: GuidanceModel, J: torch.Tensor, config: Optimizatio
         sdf = sdf.reshape(B, model.D, model.D, model.D).cpu().numpy()
     theta = loop.theta.cpu().numpy().astype(np.float64)
     torch.cuda.synchronize(dev)
+    loop.check_flags()                  # truncated penetration term = wrong result: fail the batch loudly (it is retried per image)
     nan_rep, failed = loop.nan_report(), set(loop.failed_images())
     if debug_root:
         _write_debug_dumps(debug_root, [p["index"] for p, _ in chunk], config, loop)

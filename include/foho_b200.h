@@ -150,6 +150,9 @@ typedef struct foho_guidance_desc {
    * its first CTA start and last CTA end.  Order: prep, stream, chamfer_h2c, chamfer_c2h,
    * chamfer_brute, raster, compact, voxdist, finalize_verts, assemble, keypoints. */
   void *trace;
+  /* optional: device [B] int32, OR-accumulated with every evaluation's FOHO_T_FLAGS so that an overflow in ANY
+   * evaluation of a captured graph is still visible afterwards (the host layer turns bit0 into a hard error) */
+  int32_t *sticky_flags;
 } foho_guidance_desc;
 #define FOHO_TRACE_KERNELS 11
 
@@ -327,7 +330,7 @@ typedef struct foho_attn_desc {
   int32_t q_shared;
   int32_t max_ctas;          /* 0 = one persistent CTA per SM */
   float scale;               /* 1/sqrt(64) = 0.125 */
-  int32_t reserved;
+  int32_t variant;           /* 0 = two query tiles per CTA in ping-pong (default); 1 = one tile per CTA */
   const void *q; int64_t ldq, hsq;
   const void *k; int64_t ldk, hsk;
   const void *v; int64_t ldv, hsv;
@@ -363,6 +366,14 @@ int foho_dec_gather_rows(const void *in, int64_t ld_in, const int32_t *idx, void
  * mode 0: f32 -> f16 (x scale); 1: f16 -> f32 (x scale); 2: f16 -> f32 accumulate; 3: out += in (fp16, contiguous) */
 int foho_dec_cast(const void *in, int64_t ld_in, void *out, int64_t ld_out, int64_t rows, int32_t cols, float scale, int32_t mode,
                   void *cuda_stream);
+
+/* Sparse view of a dense dE/dSDF [B, V] (V a multiple of 4, 16-byte aligned): the non-zero entries of image b, in a
+ * deterministic order, go to idx / val [b, 0..count[b]) (capacity cap per image, the rest zeroed: index 0, gradient 0);
+ * count [B] receives the true number, bit 0 of *flags (optional) is set when it exceeds cap.  This is what the
+ * decoder's adjoint consumes: the energy touches a few thousand voxels, not the lattice. */
+size_t foho_dec_compact_workspace_bytes(int32_t B, int64_t V);
+int foho_dec_compact_grad(const float *g, int32_t B, int64_t V, int32_t cap, int32_t *idx, float *val, int32_t *count,
+                          int32_t *flags, void *workspace, size_t workspace_bytes, void *cuda_stream);
 
 #ifdef __cplusplus
 }

@@ -24,6 +24,11 @@ def ref_attn(q, k, v, n_img, q_shared):
 
 
 def case(name, n_img, H, n_q, n_k, q_shared, qscale=1.0, fused=False, max_ctas=0):
+    for variant in (0, 1):
+        _case(f"v{variant} {name}", n_img, H, n_q, n_k, q_shared, qscale, fused, max_ctas, variant)
+
+
+def _case(name, n_img, H, n_q, n_k, q_shared, qscale, fused, max_ctas, variant):
     global all_ok
     if fused:      # self-attention layout: one [tokens, heads, 192] projection
         qkv = torch.randn(n_img * n_k, H, 192, device=dev).half()
@@ -33,7 +38,7 @@ def case(name, n_img, H, n_q, n_k, q_shared, qscale=1.0, fused=False, max_ctas=0
         q = (qscale * torch.randn(n_q if q_shared else n_img * n_q, H, 64, device=dev)).half()
         kv = torch.randn(n_img * n_k, H, 128, device=dev).half()
         k, v = kv[:, :, :64], kv[:, :, 64:]
-    out = tc.attention(q, k, v, n_img, q_shared=q_shared, max_ctas=max_ctas)
+    out = tc.attention(q, k, v, n_img, q_shared=q_shared, max_ctas=max_ctas, variant=variant)
     torch.cuda.synchronize()
     ref = ref_attn(q, k, v, n_img, q_shared)
     err = (out.float() - ref).abs().max().item()
@@ -52,6 +57,7 @@ case("several items per CTA", 2, 4, 1000, 1024, True, max_ctas=3)
 case("peaked softmax (rescale path)", 1, 2, 256, 3072, True, qscale=6.0)
 case("self attention fused qkv", 2, 16, 384, 384, False, fused=True)
 case("cross attention 16 heads", 2, 16, 5000, 3072, True)
+case("odd number of tiles", 1, 2, 128 * 3 + 5, 256, True)
 
 perf = []
 for (n_img, n_q) in ((1, 148 * 128), (1, 274625), (4, 65536)):
@@ -60,19 +66,20 @@ for (n_img, n_q) in ((1, 148 * 128), (1, 274625), (4, 65536)):
     kv = torch.randn(n_img * n_k, H, 128, device=dev).half()
     k, v = kv[:, :, :64], kv[:, :, 64:]
     out = torch.empty(n_img, n_q, H * 64, dtype=torch.float16, device=dev)
-    for _ in range(2):
-        tc.attention(q, k, v, n_img, out=out, q_shared=True)
-    torch.cuda.synchronize()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    R = 5
-    for _ in range(R):
-        tc.attention(q, k, v, n_img, out=out, q_shared=True)
-    e1.record(); torch.cuda.synchronize()
-    ms = e0.elapsed_time(e1) / R
     fl = 4.0 * n_img * n_q * n_k * H * 64
-    perf.append({"n_img": n_img, "n_q": n_q, "ms": ms, "tflops": fl / ms / 1e9})
-    print(perf[-1], flush=True)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    R = 5
+    for variant in (0, 1):
+        for _ in range(2):
+            tc.attention(q, k, v, n_img, out=out, q_shared=True, variant=variant)
+        torch.cuda.synchronize()
+        e0.record()
+        for _ in range(R):
+            tc.attention(q, k, v, n_img, out=out, q_shared=True, variant=variant)
+        e1.record(); torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / R
+        perf.append({"n_img": n_img, "n_q": n_q, "variant": variant, "ms": ms, "tflops": fl / ms / 1e9})
+        print(perf[-1], flush=True)
     if n_q <= 65536:
         qq = q.unsqueeze(0).expand(n_img, -1, -1, -1).transpose(1, 2).contiguous()
         kk = k.reshape(n_img, n_k, H, 64).transpose(1, 2).contiguous(); vv = v.reshape(n_img, n_k, H, 64).transpose(1, 2).contiguous()

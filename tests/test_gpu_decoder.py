@@ -133,3 +133,91 @@ def test_reference_lattice_65_sampled_rows():
         ref = -vae_g.geo_decoder(xyz[rows].to(dev).half().float()[None], pred).reshape(-1)
     got = sdf[0, rows.to(dev)]
     assert (got - ref).abs().max().item() <= 2 * TOL * ref.abs().max().item()
+
+
+# --------------------------------------------------------------------------- the decoder inside the guidance loop
+def _loop_setup(D=17, B=2, P=1024, layers=2):
+    from followmyhold_b200.decoder.shapevae import DecoderWeights, LatentDecoder
+    from followmyhold_b200.guidance.config import OptimizationConfig
+    from followmyhold_b200.guidance.loop import GuidanceLoop
+    from followmyhold_b200.synthetic import make_guidance_sample, stack_samples
+    dev = "cuda:0"
+    samples = [make_guidance_sample(D, P, seed) for seed in range(B)]
+    sdf0, theta0, st = stack_samples(samples, device=dev, cap=True)
+    cfg = OptimizationConfig()
+    cfg.optimization_steps_hand, cfg.optimization_steps_scale, cfg.optimization_steps_joint = 3, 2, 2
+    cfg.with_steps(6)
+    loop = GuidanceLoop(B, D, st, P, device=dev, config=cfg, micro_batches=1, mock_decoder=False)
+    loop.theta.copy_(theta0)
+    vae = _vae(layers, seed=11)
+    with torch.no_grad():                          # a field with an inside: shift the logits so part of the lattice is < 0
+        vae.geo_decoder.output_proj.weight.mul_(2.0)
+    dec = LatentDecoder(DecoderWeights(vae.state_dict(), dev), B, query_chunk=2048, active_chunk=512)
+    dec.set_queries(_lattice(D))
+    g = torch.Generator().manual_seed(7)
+    loop.x_t.copy_(torch.randn(B, loop.L, generator=g))
+    vel = 0.5 * torch.randn(B, loop.L, generator=g)
+    return loop, dec, vae.to(dev), vel.to(dev), st, D, B
+
+
+def test_loop_gradient_through_the_tc_decoder_matches_autograd_through_the_oracle():
+    """dE/d(model output) of one inner iteration (pipelines.py:1507-1600): tensor-core decode -> energy kernels ->
+    sparse dE/dSDF -> tensor-core adjoint, against torch autograd through the oracle decoder and the same kernels."""
+    import ctypes as C
+    from followmyhold_b200 import _lib
+    from followmyhold_b200.decoder.shapevae import GradCompactor
+    from followmyhold_b200.guidance.engine import GuidanceFunction
+    from oracle import decoder_oracle as DO
+    loop, dec, vae, vel, st, D, B = _loop_setup()
+    eng = loop.lanes[0].engine
+    sigma = 0.6
+    w = _lib.Weights()
+    C.memmove(C.byref(w), C.byref(eng.weights), C.sizeof(_lib.Weights))
+    w.w_mom = 0.0
+    xyz = _lattice(D).cuda()
+    # oracle path
+    v = vel.clone().requires_grad_(True)
+    x1 = loop.x_t + (1.0 - sigma) * v
+    sdf_o = torch.cat([DO.latent2sdf(x1[b].view(1, 3072, 64), xyz, (D, D, D), vae) for b in range(B)])
+    E = GuidanceFunction.apply(sdf_o, loop.theta, eng, st, w, False, 0)
+    E.sum().backward()
+    gref = v.grad
+    terms_ref = eng.terms.clone()
+    # tensor-core path
+    x1 = (loop.x_t + (1.0 - sigma) * vel).contiguous()
+    sdf = dec.forward(x1.view(B, 3072, 64)).view(B, D, D, D)
+    assert (sdf - sdf_o.detach()).abs().max().item() <= TOL * sdf_o.abs().max().item()
+    desc = eng.make_desc(sdf, loop.theta, st)
+    desc.w = w
+    eng.launch(desc)
+    comp = GradCompactor(B, D ** 3, 4096, "cuda:0")
+    idx, val = comp(eng.grad_sdf.view(B, -1))
+    torch.cuda.synchronize()
+    # the sparse view holds exactly the non-zero entries of the dense gradient
+    dense = eng.grad_sdf.view(B, -1)
+    for b in range(B):
+        n = int(comp.count[b])
+        assert n == int((dense[b] != 0).sum()) and 0 < n <= 4096
+        assert torch.equal(dense[b][idx[b, :n].long()], val[b, :n]) and idx[b, :n].unique().numel() == n
+        assert not val[b, n:].any()
+    got = dec.backward(idx, val, out_scale=1.0 - sigma).view(B, -1)
+    torch.cuda.synchronize()
+    assert int(comp.flags) == 0
+    assert torch.allclose(eng.terms[:, 0], terms_ref[:, 0], rtol=2e-2, atol=1e-4)
+    cos = torch.nn.functional.cosine_similarity(got.reshape(1, -1), gref.reshape(1, -1)).item()
+    assert cos > 0.999, cos
+    assert (got - gref).abs().max().item() <= 2e-2 * gref.abs().max().item()
+
+
+def test_schedule_with_the_tc_decoder_runs_all_phases():
+    loop, dec, vae, vel, st, D, B = _loop_setup()
+    theta0 = loop.theta.clone()
+    x0 = loop.x_t.clone()
+    loop.sdf.fill_(1.0)
+    loop.run_schedule_tc_decoder(lambda i, x_t: vel / (1.0 + i), dec)
+    torch.cuda.synchronize()
+    loop.check_overflow()
+    assert torch.isfinite(loop.x_t).all() and torch.isfinite(loop.theta).all() and torch.isfinite(loop.terms).all()
+    assert not torch.equal(loop.theta, theta0) and not torch.equal(loop.x_t, x0)
+    assert loop.nan_report() == {}
+    assert float(loop.grad_velocity.abs().max()) > 0          # the adjoint reached the model output
