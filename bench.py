@@ -230,6 +230,82 @@ def _reference_rank0(args):
     print(json.dumps(line), flush=True)
 
 
+
+# --------------------------------------------------------------------------- decoder leg (row f1)
+def decoder_leg(dev, n_images: int = 1, D_lat: int = 65, n_active: int = 8192, reps: int = 3, layers: int = 16):
+    """The reference's real inner iteration shape: ``latent2sdf`` of the 65^3 lattice
+    (pipelines.py:292-312, 1126-1137) and its adjoint on the tensor cores, random-init weights of the released
+    architecture, timed with CUDA events.  Returned as extra keys of the bench line; the roofline here is the
+    tensor one: achieved = algorithmic FLOPs / time against the measured cuBLAS bf16 rate."""
+    import torch
+    from followmyhold_b200.decoder import tc
+    from followmyhold_b200.decoder.shapevae import (DecoderWeights, LatentDecoder, adjoint_flops, decode_flops, lattice_points,
+                                                    random_state_dict)
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    peak_sus = float(peaks.get("bf16_tflops_sustained", 1400.0))
+    peak_burst = float(peaks.get("bf16_tflops", 1590.0))
+    kind = "measured" if peaks else "fallback"
+    W = DecoderWeights(random_state_dict(layers, seed=0), dev)
+    dec = LatentDecoder(W, n_images, device=dev)
+    dec.set_queries(lattice_points(D_lat))
+    g = torch.Generator().manual_seed(3)
+    lat = torch.randn(n_images, 3072, 64, generator=g).to(dev)
+    Nq = D_lat ** 3
+    idx = torch.randint(0, Nq, (n_images, n_active), generator=g).to(torch.int32).to(dev)
+    gs = (1e-2 * torch.randn(n_images, n_active, generator=g)).to(dev)
+    sdf = torch.empty(n_images, Nq, device=dev)
+    gl = torch.empty(n_images, 3072, 64, device=dev)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+
+    def timed(fn, n):
+        fn(); torch.cuda.synchronize()
+        e0.record()
+        for _ in range(n):
+            fn()
+        e1.record(); torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / n
+
+    fwd_ms = timed(lambda: dec.forward(lat, out=sdf), reps)
+    bwd_ms = timed(lambda: dec.backward(idx, gs, out=gl), reps)
+    assert torch.isfinite(sdf).all() and torch.isfinite(gl).all()
+    fl = decode_flops(Nq, layers)
+    fwd_tf = n_images * fl["forward"] / fwd_ms / 1e9
+    bwd_tf = n_images * adjoint_flops(n_active, layers) / bwd_ms / 1e9
+    # the two tensor-core kernels alone, at the shapes the decode launches them with
+    n = min(32768, Nq) // 128 * 128
+    q = torch.randn(n, 16, 64, device=dev).half()
+    kv = torch.randn(n_images * 3072, 16, 128, device=dev).half()
+    o = torch.empty(n_images, n, 1024, dtype=torch.float16, device=dev)
+    att_ms = timed(lambda: tc.attention(q, kv[:, :, :64], kv[:, :, 64:], n_images, out=o, q_shared=True), 5)
+    att_tf = 4.0 * n_images * n * 3072 * 1024 / att_ms / 1e9
+    a = torch.randn(n_images * n, 1024, device=dev).half()
+    wfc = torch.randn(4096, 1024, device=dev).half()
+    u = torch.empty(n_images * n, 4096, dtype=torch.float16, device=dev)
+    bias = torch.zeros(4096, device=dev)
+    gemm_ms = timed(lambda: tc.gemm(a, wfc, out=u, bias=bias, act=tc.ACT_GELU), 5)
+    gemm_tf = 2.0 * n_images * n * 4096 * 1024 / gemm_ms / 1e9
+    return {
+        "workload": f"latent2sdf + adjoint, {n_images} image(s), {D_lat}^3 = {Nq} lattice queries, 3072 x 64 latents, {layers}-layer "
+                    f"ShapeVAE decoder (random-init weights), {n_active} lattice points carrying a gradient",
+        "dtype": "f16 operands, f32 accumulation (the reference decodes in fp16, pipelines.py:302-306)",
+        "forward_ms": fwd_ms, "adjoint_ms": bwd_ms, "forward_tflops": fwd_tf, "adjoint_tflops": bwd_tf,
+        "flops_forward_per_image": fl, "flops_adjoint_per_image": adjoint_flops(n_active, layers),
+        "decodes_per_sec": n_images * 1e3 / fwd_ms, "evaluations_per_sec_decoder_only": n_images * 1e3 / (fwd_ms + bwd_ms),
+        "roofline": {"bound": "tensor", "kernel": "latent2sdf forward (k_attn_fwd2 + k_gemm_tc + row kernels)", "achieved": fwd_tf,
+                     "peak": peak_sus, "peak_kind": f"{kind} cuBLAS bf16, sustained (kernels timed inside a long step)",
+                     "unit": "TFLOP/s", "frac": fwd_tf / peak_sus, "traffic": None},
+        "kernels_alone": {
+            "k_gemm_tc": {"shape": [n_images * n, 4096, 1024], "epilogue": "bias + GELU", "ms": gemm_ms, "tflops": gemm_tf,
+                          "frac_of_burst_peak": gemm_tf / peak_burst, "peak": peak_burst},
+            "k_attn_fwd2": {"queries": n, "keys": 3072, "heads": 16, "images": n_images, "ms": att_ms, "tflops": att_tf,
+                            "frac_of_burst_peak": att_tf / peak_burst, "peak": peak_burst}},
+    }
+
+
 # --------------------------------------------------------------------------- GPU arm
 def run_ours(args):
     import torch
@@ -462,6 +538,11 @@ def run_ours(args):
                                  "share_of_eval of the evaluation's wall time; with every kernel in series "
                                  "(as ncu replays them) its share is share_of_eval_serialised"},
         }
+        if world == 1 and not args.no_decoder:
+            try:
+                line["decoder"] = decoder_leg(dev)
+            except Exception as e:          # the headline line must survive a failure of this extra leg
+                line["decoder"] = {"error": f"{type(e).__name__}: {e}"}
         if world == 1 and not args.no_cpu:
             os.sched_setaffinity(0, orig_affinity)      # the CPU leg gets every host core back
             eps, cores, n, el = cpu_guidance_evals_per_sec(args.cpu_seconds)
@@ -489,6 +570,7 @@ def main():
     ap.add_argument("--micro-batches", type=int, default=2,
                     help="groups of images that advance independently inside the step's graph (1, 2 or 4)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-decoder", action="store_true", help="skip the tensor-core decoder leg (row f1)")
     ap.add_argument("--cpu-seconds", type=float, default=15.0)
     ap.add_argument("--ref-evals", type=int, default=3, help="--impl reference: oracle evaluations per (sampled) step")
     args = ap.parse_args()

@@ -257,7 +257,8 @@ k_attn_fwd(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUte
 // TFLOP/s); a second softmax warpgroup on a second tile fills those slots.  One S buffer per tile (TMEM: S_A | S_B |
 // O_A | O_B), registers moved from the producer / MMA warps to the softmax warps with setmaxnreg.
 //   warp 0 TMA, warp 1 MMA, warp 2 TMEM alloc, warps 4-7 softmax of tile A, warps 8-11 softmax of tile B
-//   MMA order per key block j:  [P_A(j) ready -> O_A += P_A V_j ; S_A(j+1)]  [P_B(j) ready -> O_B += P_B V_j ; S_B(j+1)]
+//   MMA order per key block j:  S_A(j+1), S_B(j+1) (as soon as the groups hold block j in registers), then
+//   [P_A(j) ready -> O_A += P_A V_j]  [P_B(j) ready -> O_B += P_B V_j]
 // ================================================================================================
 constexpr int ATT2_SMEM = 2 * Q_BYTES + KV_STAGES * (K_BYTES + V_BYTES) + 2 * P_BYTES + 1024 + 256;
 constexpr uint32_t T2_S = 0, T2_O = 256;          // S_g at g*128, O_g at 256 + g*64
@@ -354,6 +355,10 @@ k_attn_fwd2(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUt
         for (int j = 0; j < nblk; ++j, ++g) {
           const uint32_t s = g % KV_STAGES, ph = (g / KV_STAGES) & 1;
           const uint32_t v_addr = tc::smem_u32(sKV + s * (K_BYTES + V_BYTES) + K_BYTES);
+          // the next scores first: a softmax group frees its S buffer as soon as the scores are in its registers,
+          // so S(j+1) is computed while the group is still exponentiating block j
+          if (j + 1 < nblk) { issue_s(g + 1, 0); issue_s(g + 1, 1); }
+          else tc::mma_commit(q_empty);
 #pragma unroll
           for (int grp = 0; grp < 2; ++grp) {
             tc::mbar_wait(&p_full[grp], g & 1);
@@ -367,8 +372,6 @@ k_attn_fwd2(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUt
                              tc::smem_desc_sw128(v_addr + k * 2048, AK * 128, 1024), idesc_o, (j | k) != 0);
             tc::mma_commit(&p_empty[grp]);
             if (grp == 1) tc::mma_commit(&kv_empty[s]);
-            if (j + 1 < nblk) issue_s(g + 1, grp);
-            else if (grp == 1) tc::mma_commit(q_empty);
           }
         }
       }

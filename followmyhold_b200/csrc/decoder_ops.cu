@@ -363,15 +363,14 @@ __global__ void k_add_f16(const __half *a, const __half *b, __half *y, long long
 // (count per 4096-voxel block, exclusive scan, scatter) of the non-zero entries of g [B, V] into idx / val [B, cap].
 constexpr int NZ_BLOCK = 4096;
 __device__ __forceinline__ int nz_local(const float *g, long long V, long long base, int t, float (&v)[16]) {
+  // element i of thread t = base + i * 256 + t: coalesced scalar loads (V and the per-image base need no alignment:
+  // the reference's 65^3 lattice is odd)
   int c = 0;
 #pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    const long long e = base + ((long long)i * 256 + t) * 4;
-    float4 x = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (e + 3 < V) x = *reinterpret_cast<const float4 *>(g + e);
-    else { if (e < V) x.x = g[e]; if (e + 1 < V) x.y = g[e + 1]; if (e + 2 < V) x.z = g[e + 2]; }
-    v[4 * i] = x.x; v[4 * i + 1] = x.y; v[4 * i + 2] = x.z; v[4 * i + 3] = x.w;
-    c += (x.x != 0.f) + (x.y != 0.f) + (x.z != 0.f) + (x.w != 0.f);
+  for (int i = 0; i < 16; ++i) {
+    const long long e = base + (long long)i * 256 + t;
+    v[i] = e < V ? __ldg(g + e) : 0.f;
+    c += v[i] != 0.f;
   }
   return c;
 }
@@ -432,16 +431,14 @@ __global__ void k_nz_scatter(const float *__restrict__ g, long long V, int nblk,
   int pos = offsets[(long long)b * nblk + blk] + pre + incl - c;
   if (c == 0) return;
 #pragma unroll
-  for (int i = 0; i < 4; ++i)
-#pragma unroll
-    for (int k = 0; k < 4; ++k)
-      if (v[4 * i + k] != 0.f) {
-        if (pos < cap) {
-          idx[(long long)b * cap + pos] = (int)((long long)blk * NZ_BLOCK + ((long long)i * 256 + t) * 4 + k);
-          val[(long long)b * cap + pos] = v[4 * i + k];
-        }
-        ++pos;
+  for (int i = 0; i < 16; ++i)
+    if (v[i] != 0.f) {
+      if (pos < cap) {
+        idx[(long long)b * cap + pos] = (int)((long long)blk * NZ_BLOCK + (long long)i * 256 + t);
+        val[(long long)b * cap + pos] = v[i];
       }
+      ++pos;
+    }
 }
 
 inline int blocks_for(long long work, int per_block) { return (int)((work + per_block - 1) / per_block); }
@@ -563,7 +560,7 @@ extern "C" int foho_dec_compact_grad(const float *g, int32_t B, int64_t V, int32
                                      int32_t *flags, void *workspace, size_t workspace_bytes, void *cuda_stream) {
   if (!g || !idx || !val || !count || !workspace) return FOHO_E_NULL;
   if (B <= 0 || V <= 0 || cap <= 0 || V > 0x7fffffffLL) return FOHO_E_SHAPE;
-  if (workspace_bytes < foho_dec_compact_workspace_bytes(B, V) || (reinterpret_cast<uintptr_t>(g) & 15) || V % 4) return FOHO_E_WORKSPACE;
+  if (workspace_bytes < foho_dec_compact_workspace_bytes(B, V)) return FOHO_E_WORKSPACE;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(cuda_stream);
   const int nblk = (int)((V + NZ_BLOCK - 1) / NZ_BLOCK);
   int *counts = reinterpret_cast<int *>(workspace);

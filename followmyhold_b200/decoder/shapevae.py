@@ -406,3 +406,69 @@ class LatentDecoder:
         # float32 out; the epilogue undoes the loss scale and applies the call site's 1/scale_factor (:297)
         tc.gemm(g, w.post_kl_w, out=out.view(R, EMBED), b_mn=True, alpha=out_scale / (w.scale_factor * ls), stream=stream)
         return out
+
+
+def random_state_dict(num_layers: int = 16, seed: int = 0, device="cpu", num_freqs: int = 8) -> Dict[str, torch.Tensor]:
+    """Random-init weights with the names and shapes of the decode half of Hunyuan3D-2's ShapeVAE (3072 x 64 latents,
+    width 1024, 16 heads, qk_norm, no qkv bias) -- for benchmarks and synthetic runs: there is no network for the
+    released checkpoint.  nn.Linear-style uniform init, LayerNorm weights around 1."""
+    g = torch.Generator(device="cpu").manual_seed(seed)
+    dev = torch.device(device)
+    sd: Dict[str, torch.Tensor] = {}
+
+    def lin(name, out_f, in_f, bias=True):
+        b = 1.0 / in_f ** 0.5
+        sd[name + ".weight"] = ((torch.rand(out_f, in_f, generator=g) * 2 - 1) * b).to(dev)
+        if bias:
+            sd[name + ".bias"] = ((torch.rand(out_f, generator=g) * 2 - 1) * b).to(dev)
+
+    def ln(name, n):
+        sd[name + ".weight"] = (1.0 + 0.1 * torch.randn(n, generator=g)).to(dev)
+        sd[name + ".bias"] = (0.02 * torch.randn(n, generator=g)).to(dev)
+
+    lin("post_kl", WIDTH, EMBED)
+    for i in range(num_layers):
+        p = f"transformer.resblocks.{i}."
+        ln(p + "ln_1", WIDTH); ln(p + "ln_2", WIDTH)
+        lin(p + "attn.c_qkv", 3 * WIDTH, WIDTH, bias=False); lin(p + "attn.c_proj", WIDTH, WIDTH)
+        ln(p + "attn.attention.q_norm", HD); ln(p + "attn.attention.k_norm", HD)
+        lin(p + "mlp.c_fc", 4 * WIDTH, WIDTH); lin(p + "mlp.c_proj", WIDTH, 4 * WIDTH)
+    gd = "geo_decoder."
+    c = gd + "cross_attn_decoder."
+    lin(gd + "query_proj", WIDTH, 3 * (2 * num_freqs + 1))
+    for n in ("ln_1", "ln_2", "ln_3"):
+        ln(c + n, WIDTH)
+    lin(c + "attn.c_q", WIDTH, WIDTH, bias=False); lin(c + "attn.c_kv", 2 * WIDTH, WIDTH, bias=False); lin(c + "attn.c_proj", WIDTH, WIDTH)
+    ln(c + "attn.attention.q_norm", HD); ln(c + "attn.attention.k_norm", HD)
+    lin(c + "mlp.c_fc", 4 * WIDTH, WIDTH); lin(c + "mlp.c_proj", WIDTH, 4 * WIDTH)
+    ln(gd + "ln_post", WIDTH)
+    lin(gd + "output_proj", 1, WIDTH)
+    return sd
+
+
+def lattice_points(D: int, bound: float = 1.10) -> torch.Tensor:
+    """``generate_dense_grid_points`` (pipelines.py:341-360): linspace(-bound, bound, D)^3, ``ij`` order, z fastest."""
+    axis = torch.linspace(-bound, bound, D)
+    return torch.stack(torch.meshgrid(axis, axis, axis, indexing="ij"), -1).reshape(-1, 3)
+
+
+def decode_flops(n_queries: int, num_layers: int = 16) -> Dict[str, float]:
+    """Multiply-add FLOPs (2 per MAC) of one ``latent2sdf`` of one image (the accounting of DESIGN.md section 8)."""
+    T, W = TOKENS, WIDTH
+    layer = 2 * T * 12 * W * W + 4 * T * T * W
+    transformer = num_layers * layer + 2 * T * EMBED * W
+    kv = 2 * T * W * 2 * W
+    attn = 4 * n_queries * T * W
+    post = 2 * n_queries * (W * W + 8 * W * W + W)
+    return {"transformer": transformer, "kv": kv, "cross_attention": attn, "per_query_mlp": post, "forward": transformer + kv + attn + post}
+
+
+def adjoint_flops(n_active: int, num_layers: int = 16) -> float:
+    """FLOPs of ``LatentDecoder.backward`` for one image with ``n_active`` rows carrying a gradient: input gradients
+    only (weights are frozen): every linear layer once more, attention backward = recomputed scores + four products,
+    plus the recompute of the active query rows."""
+    T, W, M = TOKENS, WIDTH, n_active
+    token = num_layers * (2 * T * 12 * W * W + 10 * T * T * W) + 2 * T * W * 2 * W + 2 * T * EMBED * W
+    query = 4 * M * T * W + 2 * M * 9 * W * W            # recompute: attention + c_proj + MLP
+    query += 2 * M * 9 * W * W + 6 * M * T * W           # backward: MLP + c_proj, then dP, dV, dKn
+    return float(token + query)

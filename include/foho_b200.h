@@ -367,7 +367,7 @@ int foho_dec_gather_rows(const void *in, int64_t ld_in, const int32_t *idx, void
 int foho_dec_cast(const void *in, int64_t ld_in, void *out, int64_t ld_out, int64_t rows, int32_t cols, float scale, int32_t mode,
                   void *cuda_stream);
 
-/* Sparse view of a dense dE/dSDF [B, V] (V a multiple of 4, 16-byte aligned): the non-zero entries of image b, in a
+/* Sparse view of a dense dE/dSDF [B, V]: the non-zero entries of image b, in a
  * deterministic order, go to idx / val [b, 0..count[b]) (capacity cap per image, the rest zeroed: index 0, gradient 0);
  * count [B] receives the true number, bit 0 of *flags (optional) is set when it exceeds cap.  This is what the
  * decoder's adjoint consumes: the energy touches a few thousand voxels, not the lattice. */

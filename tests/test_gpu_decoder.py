@@ -214,10 +214,17 @@ def test_schedule_with_the_tc_decoder_runs_all_phases():
     theta0 = loop.theta.clone()
     x0 = loop.x_t.clone()
     loop.sdf.fill_(1.0)
-    loop.run_schedule_tc_decoder(lambda i, x_t: vel / (1.0 + i), dec)
+    model = lambda i, x_t: vel / (1.0 + i)
+    last = loop.cfg.num_inference_steps - 1
+    loop.run_schedule_tc_decoder(model, dec, last_step=last - 1)
     torch.cuda.synchronize()
-    loop.check_overflow()
+    assert float(loop.grad_velocity.abs().max()) > 0          # the adjoint reached the model output ...
+    assert not torch.equal(loop.velocity, model(last - 1, None))      # ... and AdamW moved it (:1600-1601)
+    loop.run_schedule_tc_decoder(model, dec, first_step=last)
+    torch.cuda.synchronize()
+    # sigma = 1 at the last step: x1 = x_t + (1 - sigma) v does not depend on v any more (schedulers.py:481)
+    assert float(loop.grad_velocity.abs().max()) == 0
+    loop.check_overflow(); loop.check_flags()
     assert torch.isfinite(loop.x_t).all() and torch.isfinite(loop.theta).all() and torch.isfinite(loop.terms).all()
     assert not torch.equal(loop.theta, theta0) and not torch.equal(loop.x_t, x0)
     assert loop.nan_report() == {}
-    assert float(loop.grad_velocity.abs().max()) > 0          # the adjoint reached the model output
