@@ -17,7 +17,7 @@ REPO_ROOT = PKG_DIR.parent
 CSRC = PKG_DIR / "csrc"
 LIB_PATH = PKG_DIR / "libfoho_b200.so"
 SOURCES = ["guidance_stream.cu", "guidance_sparse.cu", "guidance_objmesh.cu", "guidance_chamfer.cu", "guidance_voxdist.cu", "guidance_update.cu", "icp.cu",
-           "mesh_sdf.cu", "mesh_decimate.cu", "decoder_gemm.cu", "decoder_attn.cu", "decoder_ops.cu"]
+           "mesh_sdf.cu", "mesh_decimate.cu", "decoder_gemm.cu", "decoder_attn.cu", "decoder_ops.cu", "guidance_raster.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "-Xcompiler", "-fPIC", "-Xcompiler", "-O3"]
 
@@ -39,6 +39,7 @@ EXPORTED_SYMBOLS = [
     "foho_dec_layernorm", "foho_dec_layernorm_bwd", "foho_dec_softmax", "foho_dec_softmax_bwd", "foho_dec_fourier_embed",
     "foho_dec_head", "foho_dec_head_bwd", "foho_dec_gather_rows", "foho_dec_cast",
     "foho_dec_compact_workspace_bytes", "foho_dec_compact_grad",
+    "foho_raster_workspace_bytes", "foho_raster_losses_fwd_bwd",
 ]
 
 
@@ -159,6 +160,18 @@ class AttnDesc(C.Structure):
     ]
 
 
+class RasterDesc(C.Structure):
+    _fields_ = [
+        ("B", C.c_int32), ("V_total", C.c_int32), ("F_total", C.c_int32), ("H", C.c_int32), ("W", C.c_int32),
+        ("tile_cap", C.c_int32), ("w_normal", C.c_float), ("w_disp", C.c_float), ("w_sil", C.c_float), ("reserved", C.c_int32),
+        ("verts", C.c_void_p), ("faces", C.c_void_p), ("vert_offsets", C.c_void_p), ("face_offsets", C.c_void_p),
+        ("fov_deg", C.c_void_p), ("gt_normals", C.c_void_p), ("gt_mask", C.c_void_p), ("n_valid", C.c_void_p),
+        ("gt_disp", C.c_void_p), ("gt_sil", C.c_void_p), ("losses", C.c_void_p), ("grad_verts", C.c_void_p),
+        ("out_p2f", C.c_void_p), ("out_zbuf", C.c_void_p), ("out_nraw", C.c_void_p),
+        ("workspace", C.c_void_p), ("workspace_bytes", C.c_size_t),
+    ]
+
+
 _lib: Optional[C.CDLL] = None
 
 
@@ -240,6 +253,10 @@ def load(build_if_missing: bool = False) -> C.CDLL:
     lib.foho_dec_head_bwd.argtypes = [vp, i64, vp, f32, vp, vp, vp, f32, vp, i64, i64, vp]
     lib.foho_dec_gather_rows.argtypes = [vp, i64, vp, vp, i64, i64, i32, vp]
     lib.foho_dec_cast.argtypes = [vp, i64, vp, i64, i64, i32, f32, i32, vp]
+    lib.foho_raster_workspace_bytes.argtypes = [C.POINTER(RasterDesc)]
+    lib.foho_raster_workspace_bytes.restype = C.c_size_t
+    lib.foho_raster_losses_fwd_bwd.argtypes = [C.POINTER(RasterDesc), vp]
+    lib.foho_raster_losses_fwd_bwd.restype = C.c_int
     lib.foho_dec_compact_workspace_bytes.argtypes = [i32, i64]
     lib.foho_dec_compact_workspace_bytes.restype = C.c_size_t
     lib.foho_dec_compact_grad.argtypes = [vp, i32, i64, i32, vp, vp, vp, vp, vp, C.c_size_t, vp]

@@ -375,6 +375,44 @@ size_t foho_dec_compact_workspace_bytes(int32_t B, int64_t V);
 int foho_dec_compact_grad(const float *g, int32_t B, int64_t V, int32_t cap, int32_t *idx, float *val, int32_t *count,
                           int32_t *flags, void *workspace, size_t workspace_bytes, void *cuda_stream);
 
+/* ---------------------------------------------------------------------------------------------
+ * Row f2, first part: the renderer of the guidance loop and its image-space losses, forward and backward to the mesh
+ * vertices.  Replaces, per inner iteration, `render_normal_and_disparity(renderer, mesh)`
+ * (third_party_patches/hy3dgen/shapegen/pipelines.py:272-289: pytorch3d naive rasteriser with faces_per_pixel = 1 +
+ * the PhongNormalShader of :74-92 + min/max normalisation), `normal_alignment_loss` (:178-187), the disparity L1 and the
+ * silhouette BCE (:1567-1569) with their weights (:1580-1583), and the autograd pass back to the vertices; camera and
+ * raster settings of src/foho/guidance/run.py:84-116 (R = diag(-1,1,-1), T = 0, fov_x per image).
+ * Meshes of the B images are packed: image b owns vertices [vert_offsets[b], vert_offsets[b+1]) and faces
+ * [face_offsets[b], face_offsets[b+1]); face indices address the packed vertex array.  The silhouette is hard
+ * (sigma = 1e-8): its BCE is reported, no gradient flows through it.  pytorch3d semantics are restated from memory
+ * (oracle/raster_oracle.py): PARITY UNPINNED.
+ * --------------------------------------------------------------------------------------------- */
+typedef struct foho_raster_desc {
+  int32_t B, V_total, F_total, H, W;
+  int32_t tile_cap;            /* faces per 16x16-pixel tile the workspace holds (0 = 1024); overflow -> losses[b][7] = 1 */
+  float w_normal, w_disp, w_sil;   /* 10, 10, 10 (pipelines.py:1580-1583) */
+  int32_t reserved;
+  const float *verts;          /* device [V_total,3] world (MoGe) space                       */
+  const int32_t *faces;        /* device [F_total,3]                                          */
+  const int32_t *vert_offsets; /* device [B+1]                                                */
+  const int32_t *face_offsets; /* device [B+1]                                                */
+  const float *fov_deg;        /* device [B] MoGe fov_x in degrees                            */
+  const float *gt_normals;     /* device [B,H,W,3] target normal map                          */
+  const uint8_t *gt_mask;      /* device [B,H,W]   valid mask of the normal loss              */
+  const int32_t *n_valid;      /* device [B]       number of set pixels of gt_mask            */
+  const float *gt_disp;        /* device [B,H,W]   target (normalised) disparity              */
+  const float *gt_sil;         /* device [B,H,W]   target silhouette                          */
+  float *losses;               /* device [B,8] OUT: l_normal, l_disp, l_sil, weighted total, min / max of the raw normal
+                                  colours, max disparity, tile overflow flag                  */
+  float *grad_verts;           /* device [V_total,3] OUT dE/d(verts), or NULL (forward only)  */
+  int32_t *out_p2f;            /* optional device [B,H,W] OUT packed face index per pixel (-1 = background) */
+  float *out_zbuf;             /* optional device [B,H,W] OUT view depth (-1 = background)    */
+  float *out_nraw;             /* optional device [B,H,W,3] OUT blended normal colour before normalisation */
+  void *workspace; size_t workspace_bytes;   /* >= foho_raster_workspace_bytes(desc), 256-byte aligned */
+} foho_raster_desc;
+size_t foho_raster_workspace_bytes(const foho_raster_desc *desc);
+int foho_raster_losses_fwd_bwd(const foho_raster_desc *desc, void *cuda_stream);
+
 #ifdef __cplusplus
 }
 #endif
