@@ -38,7 +38,7 @@ EXPORTED_SYMBOLS = [
     "foho_tc_gemm", "foho_tc_attention",
     "foho_dec_layernorm", "foho_dec_layernorm_bwd", "foho_dec_softmax", "foho_dec_softmax_bwd", "foho_dec_fourier_embed",
     "foho_dec_head", "foho_dec_head_bwd", "foho_dec_gather_rows", "foho_dec_cast",
-    "foho_dec_compact_workspace_bytes", "foho_dec_compact_grad",
+    "foho_dec_rowdot", "foho_dec_gather_f32", "foho_dec_compact_workspace_bytes", "foho_dec_compact_grad",
     "foho_raster_workspace_bytes", "foho_raster_losses_fwd_bwd",
 ]
 
@@ -146,6 +146,7 @@ class GemmDesc(C.Structure):
         ("bias", C.c_void_p),
         ("res", C.c_void_p), ("ldr", C.c_int64), ("bsr", C.c_int64),
         ("aux_in", C.c_void_p), ("aux_out", C.c_void_p), ("ldaux", C.c_int64), ("bsaux", C.c_int64),
+        ("row_vec", C.c_void_p), ("bs_rowvec", C.c_int64),
     ]
 
 
@@ -156,7 +157,7 @@ class AttnDesc(C.Structure):
         ("q", C.c_void_p), ("ldq", C.c_int64), ("hsq", C.c_int64),
         ("k", C.c_void_p), ("ldk", C.c_int64), ("hsk", C.c_int64),
         ("v", C.c_void_p), ("ldv", C.c_int64), ("hsv", C.c_int64),
-        ("out", C.c_void_p), ("ldo", C.c_int64), ("out_img_stride", C.c_int64),
+        ("out", C.c_void_p), ("ldo", C.c_int64), ("out_img_stride", C.c_int64), ("lse2", C.c_void_p), ("lse2_stride", C.c_int64),
     ]
 
 
@@ -257,6 +258,10 @@ def load(build_if_missing: bool = False) -> C.CDLL:
     lib.foho_raster_workspace_bytes.restype = C.c_size_t
     lib.foho_raster_losses_fwd_bwd.argtypes = [C.POINTER(RasterDesc), vp]
     lib.foho_raster_losses_fwd_bwd.restype = C.c_int
+    lib.foho_dec_rowdot.argtypes = [vp, i64, vp, i64, vp, i64, i32, vp]
+    lib.foho_dec_rowdot.restype = C.c_int
+    lib.foho_dec_gather_f32.argtypes = [vp, i64, vp, vp, i64, i32, vp]
+    lib.foho_dec_gather_f32.restype = C.c_int
     lib.foho_dec_compact_workspace_bytes.argtypes = [i32, i64]
     lib.foho_dec_compact_workspace_bytes.restype = C.c_size_t
     lib.foho_dec_compact_grad.argtypes = [vp, i32, i64, i32, vp, vp, vp, vp, vp, C.c_size_t, vp]

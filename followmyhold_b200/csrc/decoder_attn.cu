@@ -35,6 +35,8 @@ struct AttnParams {
   long long q_rows_per_img;            // row offset of image i's queries in the Q tensor map (0: queries shared)
   __half *out; long long ldo, out_img_stride;   // O[i][q][h*64 + d]
   float scale_log2;                    // softmax scale * log2(e)
+  float *lse2;                         // optional [n_img][heads][lse_stride]: m + log2(l) of the scaled scores (variant 0 only)
+  long long lse_stride;
 };
 
 __global__ void __launch_bounds__(256, 1)
@@ -457,6 +459,7 @@ k_attn_fwd2(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUt
       tc::tc_fence_after();
       const int qrow = (pt * 2 + grp) * AQ + row;
       const float inv = 1.f / l;
+      if (p.lse2 && qrow < p.n_q) p.lse2[((long long)img * p.heads + h) * p.lse_stride + qrow] = m_used + log2f(l);
       __half *op = p.out + (long long)img * p.out_img_stride + (long long)qrow * p.ldo + h * HD;
 #pragma unroll
       for (int c = 0; c < 2; ++c) {
@@ -508,6 +511,9 @@ extern "C" int foho_tc_attention(const foho_attn_desc *d, void *cuda_stream) {
   p.q_rows_per_img = d->q_shared ? 0 : d->n_q;
   p.out = reinterpret_cast<__half *>(d->out); p.ldo = d->ldo; p.out_img_stride = d->out_img_stride;
   p.scale_log2 = d->scale * 1.4426950408889634f;
+  p.lse2 = d->lse2;
+  p.lse_stride = d->lse2_stride > 0 ? d->lse2_stride : d->n_q;
+  if (d->lse2 && d->variant == 1) return FOHO_E_ARG;
   static int sm_count = 0;
   if (!sm_count) {
     int dev = 0;

@@ -30,6 +30,7 @@ struct GemmParams {
   const void *res; long long ldr, bsr; int res_f32;
   const __half *aux_in; __half *aux_out; long long ldaux, bsaux;
   float alpha; int act;
+  const float *row_vec; long long bs_rowvec;     // act 3 / 4: one float per output row
 };
 
 template <int BN>
@@ -156,6 +157,7 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
       tc::tc_fence_after();
       const int m = m0 + q * 32 + lane;
       const bool row_ok = m < p.M;
+      const float rv = (p.act >= 3 && row_ok) ? __ldg(p.row_vec + (long long)b * p.bs_rowvec + m) : 0.f;
 #pragma unroll 1
       for (int c = half * (BN / 64); c < (half + 1) * (BN / 64); ++c) {
         uint32_t v[32];
@@ -188,6 +190,26 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
           if (p.act == 1) {
 #pragma unroll
             for (int j = 0; j < 32; ++j) f[j] = gelu_f(f[j]);
+          } else if (p.act == 3) {            // softmax probabilities from saved log-sum-exps: exp2(alpha acc - lse2[m])
+#pragma unroll
+            for (int j = 0; j < 32; ++j) f[j] = exp2f(f[j] - rv);
+          } else if (p.act == 4) {            // softmax backward: P o (dP - delta[m]) (alpha carries the score scale)
+            const __half *ai = p.aux_in + (long long)b * p.bsaux + (long long)m * p.ldaux + n;
+            if (full_chunk && ((reinterpret_cast<uintptr_t>(ai) & 15) == 0)) {
+#pragma unroll
+              for (int j = 0; j < 32; j += 8) {
+                uint4 u = __ldg(reinterpret_cast<const uint4 *>(ai + j));
+                const __half2 *h = reinterpret_cast<const __half2 *>(&u);
+#pragma unroll
+                for (int t = 0; t < 4; ++t) {
+                  float2 x = __half22float2(h[t]);
+                  f[j + 2 * t] = x.x * (f[j + 2 * t] - p.alpha * rv);
+                  f[j + 2 * t + 1] = x.y * (f[j + 2 * t + 1] - p.alpha * rv);
+                }
+              }
+            } else {
+              _Pragma("unroll") for (int j = 0; j < 32; ++j) if (n + j < p.N) f[j] = __half2float(ai[j]) * (f[j] - p.alpha * rv);
+            }
           } else if (p.act == 2) {
             const __half *ai = p.aux_in + (long long)b * p.bsaux + (long long)m * p.ldaux + n;
             if (full_chunk && ((reinterpret_cast<uintptr_t>(ai) & 15) == 0)) {
@@ -296,6 +318,7 @@ int launch_gemm(const foho_gemm_desc *d, cudaStream_t st) {
   p.aux_in = reinterpret_cast<const __half *>(d->aux_in); p.aux_out = reinterpret_cast<__half *>(d->aux_out);
   p.ldaux = d->ldaux; p.bsaux = d->bsaux;
   p.alpha = d->alpha; p.act = d->act;
+  p.row_vec = d->row_vec; p.bs_rowvec = d->bs_rowvec;
   static int sm_count = 0;
   if (!sm_count) {
     int dev = 0;
@@ -322,7 +345,7 @@ int dispatch_major(const foho_gemm_desc *d, cudaStream_t st) {
 extern "C" int foho_tc_gemm(const foho_gemm_desc *d, void *cuda_stream) {
   if (!d || !d->A || !d->B || !d->C) return FOHO_E_NULL;
   if (d->M <= 0 || d->N <= 0 || d->K <= 0 || d->batch <= 0) return FOHO_E_ARG;
-  if (d->act < 0 || d->act > 2 || (d->act == 2 && !d->aux_in)) return FOHO_E_ARG;
+  if (d->act < 0 || d->act > 4 || ((d->act == 2 || d->act == 4) && !d->aux_in) || (d->act >= 3 && !d->row_vec)) return FOHO_E_ARG;
   if (d->K % 8 || d->lda % 8 || d->ldb % 8) return FOHO_E_ARG;   // 16-byte TMA strides
   if ((d->a_mn_major && d->M % 8) || (d->b_mn_major && d->N % 8)) return FOHO_E_ARG;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(cuda_stream);

@@ -441,6 +441,35 @@ __global__ void k_nz_scatter(const float *__restrict__ g, long long V, int nblk,
     }
 }
 
+// delta[h][r] = <a[r][h][:], b[r][h][:]>, 64 channels: 8 lanes per (row, head), one 16-byte load each
+__global__ void k_rowdot(const __half *__restrict__ a, long long lda, const __half *__restrict__ b, long long ldb, float *__restrict__ out,
+                         long long rows, int heads) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long pair = i >> 3;
+  const int sub = (int)(i & 7);
+  float acc = 0.f;
+  const bool live = pair < rows * heads;
+  long long r = 0; int h = 0;
+  if (live) {
+    r = pair / heads; h = (int)(pair - r * heads);
+    uint4 ua = __ldg(reinterpret_cast<const uint4 *>(a + r * lda + h * 64 + sub * 8));
+    uint4 ub = __ldg(reinterpret_cast<const uint4 *>(b + r * ldb + h * 64 + sub * 8));
+    const __half2 *ha = reinterpret_cast<const __half2 *>(&ua), *hb = reinterpret_cast<const __half2 *>(&ub);
+#pragma unroll
+    for (int t = 0; t < 4; ++t) { float2 x = __half22float2(ha[t]), y = __half22float2(hb[t]); acc += x.x * y.x + x.y * y.y; }
+  }
+  acc += __shfl_xor_sync(0xffffffffu, acc, 1); acc += __shfl_xor_sync(0xffffffffu, acc, 2); acc += __shfl_xor_sync(0xffffffffu, acc, 4);
+  if (live && sub == 0) out[(long long)h * rows + r] = acc;
+}
+__global__ void k_gather_f32(const float *__restrict__ src, long long hs, const int *__restrict__ idx, float *__restrict__ out, long long n,
+                             int heads) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n * heads) return;
+  const int h = (int)(i / n);
+  const long long k = i - (long long)h * n;
+  out[i] = __ldg(src + (long long)h * hs + idx[k]);
+}
+
 inline int blocks_for(long long work, int per_block) { return (int)((work + per_block - 1) / per_block); }
 
 }  // namespace
@@ -569,6 +598,25 @@ extern "C" int foho_dec_compact_grad(const float *g, int32_t B, int64_t V, int32
   k_nz_count<<<dim3(nblk, B), 256, 0, st>>>(g, V, nblk, counts);
   k_nz_scan<<<B, 1024, 0, st>>>(counts, nblk, count, cap, flags);
   k_nz_scatter<<<dim3(nblk, B), 256, 0, st>>>(g, V, nblk, counts, cap, idx, val);
+  FOHO_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int foho_dec_rowdot(const void *a, int64_t lda, const void *b, int64_t ldb, float *out, int64_t rows, int32_t heads,
+                               void *cuda_stream) {
+  if (!a || !b || !out) return FOHO_E_NULL;
+  if (rows <= 0 || heads <= 0 || lda % 8 || ldb % 8) return FOHO_E_SHAPE;
+  k_rowdot<<<blocks_for(rows * heads * 8, 256), 256, 0, reinterpret_cast<cudaStream_t>(cuda_stream)>>>((const __half *)a, lda, (const __half *)b,
+                                                                                                        ldb, out, rows, heads);
+  FOHO_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int foho_dec_gather_f32(const float *src, int64_t src_head_stride, const int32_t *idx, float *out, int64_t n, int32_t heads,
+                                   void *cuda_stream) {
+  if (!src || !idx || !out) return FOHO_E_NULL;
+  if (n <= 0 || heads <= 0) return FOHO_E_SHAPE;
+  k_gather_f32<<<blocks_for(n * heads, 256), 256, 0, reinterpret_cast<cudaStream_t>(cuda_stream)>>>(src, src_head_stride, idx, out, n, heads);
   FOHO_LAUNCH_CHECK();
   return 0;
 }

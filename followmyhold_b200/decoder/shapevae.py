@@ -33,6 +33,7 @@ WIDTH, HEADS, HD, TOKENS, EMBED = 1024, 16, 64, 3072, 64
 LN_EPS = 1e-6            # hy3dgen blocks: LayerNorm(eps=1e-6); ln_post keeps torch's default 1e-5
 LN_POST_EPS = 1e-5
 SCALE_FACTOR = 0.9990943042622529
+LOG2E = 1.4426950408889634
 
 
 def _sp(stream):
@@ -103,6 +104,18 @@ class _Ops:
         W = src.shape[1]
         _lib.check("foho_dec_gather_rows", self.lib.foho_dec_gather_rows(src.data_ptr(), src.stride(0), idx.data_ptr(), out.data_ptr(),
                                                                          out.stride(0), idx.numel(), W, _sp(stream)))
+        return out
+
+    def rowdot(self, a, b, out, heads=HEADS, stream=None):
+        """out[h, r] = <a[r, h, :], b[r, h, :]> (float32 [heads, rows]): rowsum(dO o O) of the attention backward."""
+        _lib.check("foho_dec_rowdot", self.lib.foho_dec_rowdot(a.data_ptr(), a.stride(0), b.data_ptr(), b.stride(0), out.data_ptr(),
+                                                               a.shape[0], heads, _sp(stream)))
+        return out
+
+    def gather_f32(self, src, idx, out, stream=None):
+        """out[h, i] = src[h, idx[i]] for float32 src [heads, n_src]."""
+        _lib.check("foho_dec_gather_f32", self.lib.foho_dec_gather_f32(src.data_ptr(), src.stride(0), idx.data_ptr(), out.data_ptr(),
+                                                                       idx.numel(), src.shape[0], _sp(stream)))
         return out
 
     def cast(self, src, dst, scale=1.0, accumulate=False, stream=None):
@@ -208,11 +221,12 @@ class LatentDecoder:
         L = weights.num_layers
         # token-side activations kept for the adjoint, one set per layer
         self.act = [dict(x_in=torch.empty(R, WIDTH, **f16), qkv=torch.empty(R, 3 * WIDTH, **f16), qn=torch.empty(R, HEADS, HD, **f16),
-                         kn=torch.empty(R, HEADS, HD, **f16), x_mid=torch.empty(R, WIDTH, **f16), u_pre=torch.empty(R, 4 * WIDTH, **f16))
+                         kn=torch.empty(R, HEADS, HD, **f16), x_mid=torch.empty(R, WIDTH, **f16), u_pre=torch.empty(R, 4 * WIDTH, **f16),
+                         o=torch.empty(self.B, TOKENS, WIDTH, **f16),
+                         lse=torch.empty(self.B, HEADS, TOKENS, dtype=torch.float32, device=self.dev))
                     for _ in range(L)]
         self.lat16 = torch.empty(R, EMBED, **f16)
         self.h = torch.empty(R, WIDTH, **f16)            # LayerNorm output scratch
-        self.attn = torch.empty(self.B, TOKENS, WIDTH, **f16)
         self.u = torch.empty(R, 4 * WIDTH, **f16)
         self.data = torch.empty(R, WIDTH, **f16)         # transformer output = the geo decoder's `latents`
         self.kv = torch.empty(R, 2 * WIDTH, **f16)
@@ -248,6 +262,7 @@ class LatentDecoder:
         self.q_h = torch.empty(self.B, qc, WIDTH, **f16)
         self.q_u = torch.empty(self.B, qc, 4 * WIDTH, **f16)
         self.q_y = torch.empty(self.B, qc, WIDTH, **f16)
+        self.q_lse = torch.empty(self.B, HEADS, Nq, dtype=torch.float32, device=self.dev)      # log2-sum-exp of every query row
 
     # ------------------------------------------------------------------ forward
     def forward(self, latents: torch.Tensor, out: Optional[torch.Tensor] = None, stream=None) -> torch.Tensor:
@@ -265,8 +280,8 @@ class LatentDecoder:
             qkv = a["qkv"].view(R, HEADS, 3 * HD)
             ops.layernorm(qkv[:, :, :HD], lw["qn_w"], lw["qn_b"], a["qn"], width=HD, stream=stream)
             ops.layernorm(qkv[:, :, HD:2 * HD], lw["kn_w"], lw["kn_b"], a["kn"], width=HD, stream=stream)
-            tc.attention(a["qn"], a["kn"], qkv[:, :, 2 * HD:], B, out=self.attn, stream=stream)
-            tc.gemm(self.attn.view(R, WIDTH), lw["proj_w"], out=a["x_mid"], bias=lw["proj_b"], res=a["x_in"], stream=stream)
+            tc.attention(a["qn"], a["kn"], qkv[:, :, 2 * HD:], B, out=a["o"], lse2=a["lse"], stream=stream)
+            tc.gemm(a["o"].view(R, WIDTH), lw["proj_w"], out=a["x_mid"], bias=lw["proj_b"], res=a["x_in"], stream=stream)
             ops.layernorm(a["x_mid"], lw["ln2_w"], lw["ln2_b"], self.h, stream=stream)
             tc.gemm(self.h, lw["fc_w"], out=self.u, bias=lw["fc_b"], act=tc.ACT_GELU, aux_out=a["u_pre"], stream=stream)
             nxt = self.act[i + 1]["x_in"] if i + 1 < len(self.act) else self.data
@@ -284,7 +299,7 @@ class LatentDecoder:
         for s in range(0, self.Nq, qc):
             n = min(qc, self.Nq - s)
             att = self.q_attn[:, :n]
-            tc.attention(self.qn[s:s + n], self.kvn, kv[:, :, HD:], B, out=att, q_shared=True, stream=stream)
+            tc.attention(self.qn[s:s + n], self.kvn, kv[:, :, HD:], B, out=att, q_shared=True, lse2=self.q_lse[:, :, s:s + n], stream=stream)
             xq = tc.gemm(att, xw["proj_w"], out=self.q_x[:, :n], bias=xw["proj_b"], res=self.x0[s:s + n].unsqueeze(0).expand(B, n, WIDTH),
                          stream=stream)
             for b in range(B):
@@ -319,7 +334,8 @@ class LatentDecoder:
         if not hasattr(self, "_bw"):
             mc = self.active_chunk
             self._bw = dict(
-                qn=torch.empty(mc, HEADS, HD, **f16), x0=torch.empty(mc, WIDTH, **f16), S=torch.empty(HEADS, mc, TOKENS, **f32),
+                qn=torch.empty(mc, HEADS, HD, **f16), x0=torch.empty(mc, WIDTH, **f16), lse=torch.empty(HEADS, mc, **f32),
+                delta=torch.empty(HEADS, mc, **f32),
                 P=torch.empty(HEADS, mc, TOKENS, **f16), dS=torch.empty(HEADS, mc, TOKENS, **f16), a=torch.empty(mc, WIDTH, **f16),
                 x=torch.empty(mc, WIDTH, **f16), h=torch.empty(mc, WIDTH, **f16), u=torch.empty(mc, 4 * WIDTH, **f16),
                 u_pre=torch.empty(mc, 4 * WIDTH, **f16), y=torch.empty(mc, WIDTH, **f16), dy=torch.empty(mc, WIDTH, **f16),
@@ -329,7 +345,7 @@ class LatentDecoder:
                 dkn16=torch.empty(R, HEADS, HD, **f16), dkv=torch.empty(R, 2 * WIDTH, **f16),
                 g=torch.empty(R, WIDTH, **f16), g2=torch.empty(R, WIDTH, **f16), g3=torch.empty(R, WIDTH, **f16),
                 gu=torch.empty(R, 4 * WIDTH, **f16), dqkv=torch.empty(R, 3 * WIDTH, **f16),
-                tS=torch.empty(HEADS, TOKENS, TOKENS, **f32), tP=torch.empty(HEADS, TOKENS, TOKENS, **f16),
+                tP=torch.empty(HEADS, TOKENS, TOKENS, **f16), tdelta=torch.empty(HEADS, TOKENS, **f32),
                 tdS=torch.empty(HEADS, TOKENS, TOKENS, **f16), dqn=torch.empty(TOKENS, HEADS, HD, **f16),
                 dknl=torch.empty(TOKENS, HEADS, HD, **f16))
         bw = self._bw
@@ -347,10 +363,10 @@ class LatentDecoder:
                 ix = idx[b, s:s + n]
                 qn_a = ops.gather(self.qn.view(self.Nq, WIDTH), ix, bw["qn"].view(mc, WIDTH)[:n], stream=stream).view(n, HEADS, HD)
                 x0_a = ops.gather(self.x0, ix, bw["x0"][:n], stream=stream)
-                # contiguous [heads, n, tokens] views of the scratch (the row kernels index rows densely)
-                S, P, dS = (bw[k].view(-1)[:HEADS * n * TOKENS].view(HEADS, n, TOKENS) for k in ("S", "P", "dS"))
-                tc.gemm(hv(qn_a), kn_b, out=S, alpha=0.125, stream=stream)
-                ops.softmax(S, P, stream=stream)
+                P, dS = (bw[k].view(-1)[:HEADS * n * TOKENS].view(HEADS, n, TOKENS) for k in ("P", "dS"))
+                lse_a = ops.gather_f32(self.q_lse[b], ix, bw["lse"].view(-1)[:HEADS * n].view(HEADS, n), stream=stream)
+                # P = exp2(log2(e)/8 * Qn Kn^T - lse2) straight out of the score product's epilogue: no float32 scores in HBM
+                tc.gemm(hv(qn_a), kn_b, out=P, alpha=0.125 * LOG2E, act=tc.ACT_EXP2_ROW, row_vec=lse_a, stream=stream)
                 a = bw["a"][:n]
                 tc.gemm(P, v_b, out=hv(a.view(n, HEADS, HD)), b_mn=True, stream=stream)
                 x = tc.gemm(a, xw["proj_w"], out=bw["x"][:n], bias=xw["proj_b"], res=x0_a, stream=stream)
@@ -364,9 +380,10 @@ class LatentDecoder:
                 dx = ops.layernorm_bwd(x, xw["ln3_w"], bw["dh"][:n], bw["dx"][:n], add=dy, stream=stream)
                 da = tc.gemm(dx, xw["proj_w"], out=bw["da"][:n], b_mn=True, stream=stream)
                 da_h = hv(da.view(n, HEADS, HD))
-                # attention backward, heads batched: dP = dA V^T ; dS = P o (dP - rowsum) / 8 ; dV += P^T dA ; dKn += dS^T Qn
-                tc.gemm(da_h, v_b, out=S, stream=stream)                                   # S buffer reused for dP (fp32)
-                ops.softmax_bwd(P, S, dS, 0.125, stream=stream)
+                # attention backward, heads batched: dS = P o (dA V^T - rowsum(dA o A)) / 8 in the product's epilogue;
+                # dV += P^T dA ; dKn += dS^T Qn
+                delta = ops.rowdot(da, a, bw["delta"].view(-1)[:HEADS * n].view(HEADS, n), stream=stream)
+                tc.gemm(da_h, v_b, out=dS, alpha=0.125, act=tc.ACT_DSOFTMAX, aux_in=P, row_vec=delta, stream=stream)
                 tc.gemm(P, da_h, out=dv_b, res=dv_b, a_mn=True, b_mn=True, stream=stream)
                 tc.gemm(dS, hv(qn_a), out=dkn_b, res=dkn_b, a_mn=True, b_mn=True, stream=stream)
         # ---- K/V gradients -> token gradient d(data)
@@ -389,10 +406,9 @@ class LatentDecoder:
             qn, kn = a["qn"].view(B, TOKENS, HEADS, HD), a["kn"].view(B, TOKENS, HEADS, HD)
             for b in range(B):
                 qn_b, kn_b, v_b, da_b = hv(qn[b]), hv(kn[b]), hv(qkv[b, :, :, 2 * HD:]), hv(da[b])
-                tc.gemm(qn_b, kn_b, out=bw["tS"], alpha=0.125, stream=stream)
-                ops.softmax(bw["tS"], bw["tP"], stream=stream)
-                tc.gemm(da_b, v_b, out=bw["tS"], stream=stream)                            # dP
-                ops.softmax_bwd(bw["tP"], bw["tS"], bw["tdS"], 0.125, stream=stream)
+                tc.gemm(qn_b, kn_b, out=bw["tP"], alpha=0.125 * LOG2E, act=tc.ACT_EXP2_ROW, row_vec=a["lse"][b], stream=stream)
+                ops.rowdot(da[b].reshape(TOKENS, WIDTH), a["o"][b], bw["tdelta"], stream=stream)
+                tc.gemm(da_b, v_b, out=bw["tdS"], alpha=0.125, act=tc.ACT_DSOFTMAX, aux_in=bw["tP"], row_vec=bw["tdelta"], stream=stream)
                 tc.gemm(bw["tP"], da_b, out=hv(dqkv[b, :, :, 2 * HD:]), a_mn=True, b_mn=True, stream=stream)     # dV
                 tc.gemm(bw["tdS"], kn_b, out=hv(bw["dqn"]), b_mn=True, stream=stream)                           # dQn = dS Kn
                 tc.gemm(bw["tdS"], qn_b, out=hv(bw["dknl"]), a_mn=True, b_mn=True, stream=stream)               # dKn = dS^T Qn

@@ -10,7 +10,7 @@ import torch
 
 from .. import _lib
 
-ACT_NONE, ACT_GELU, ACT_DGELU = 0, 1, 2
+ACT_NONE, ACT_GELU, ACT_DGELU, ACT_EXP2_ROW, ACT_DSOFTMAX = 0, 1, 2, 3, 4
 
 
 def _stream_ptr(stream: Optional[torch.cuda.Stream]) -> C.c_void_p:
@@ -31,7 +31,7 @@ def gemm(a: torch.Tensor, b: torch.Tensor, out: Optional[torch.Tensor] = None, *
          bias: Optional[torch.Tensor] = None, act: int = ACT_NONE, res: Optional[torch.Tensor] = None,
          aux_in: Optional[torch.Tensor] = None, aux_out: Optional[torch.Tensor] = None, alpha: float = 1.0,
          out_dtype: torch.dtype = torch.float16, block_n: int = 0, max_ctas: int = 0,
-         stream: Optional[torch.cuda.Stream] = None) -> torch.Tensor:
+         row_vec: Optional[torch.Tensor] = None, stream: Optional[torch.cuda.Stream] = None) -> torch.Tensor:
     """``out[b] = res[b] + act(alpha * A[b] @ B[b]^T + bias)`` on the tensor cores (fp16 operands, fp32 accumulate).
 
     ``a``: [.., M, K] (or [.., K, M] when ``a_mn``); ``b``: [.., N, K] -- the ``nn.Linear`` weight layout -- (or
@@ -77,6 +77,10 @@ def gemm(a: torch.Tensor, b: torch.Tensor, out: Optional[torch.Tensor] = None, *
             if (rx, cx) != (M, N) or t.dtype != torch.float16:
                 raise ValueError("aux tensors must be float16 [.., M, N]")
             d.ldaux, d.bsaux = ldx, bsx
+    if row_vec is not None:
+        if row_vec.dtype != torch.float32 or row_vec.stride(-1) != 1 or row_vec.shape[-1] != M:
+            raise ValueError("row_vec must be float32 [.., M]")
+        d.row_vec, d.bs_rowvec = row_vec.data_ptr(), (row_vec.stride(0) if row_vec.dim() == 2 and row_vec.shape[0] > 1 else 0)
     if aux_in is not None:
         d.aux_in = aux_in.data_ptr()
     if aux_out is not None:
@@ -87,7 +91,7 @@ def gemm(a: torch.Tensor, b: torch.Tensor, out: Optional[torch.Tensor] = None, *
 
 def attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, n_img: int, out: Optional[torch.Tensor] = None, *,
               q_shared: bool = False, scale: float = 0.125, max_ctas: int = 0, variant: int = 0,
-              stream: Optional[torch.cuda.Stream] = None) -> torch.Tensor:
+              lse2: Optional[torch.Tensor] = None, stream: Optional[torch.cuda.Stream] = None) -> torch.Tensor:
     """``out[i, q, h, :] = softmax_k(scale * Q[q, h] . K[i, k, h]) V[i, k, h]`` on the tensor cores.
 
     ``q``: [n_q (shared) or n_img*n_q, heads, 64]; ``k``, ``v``: [n_img*n_k, heads, 64] -- strided views of the
@@ -108,5 +112,11 @@ def attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, n_img: int, out
     d.k, d.ldk, d.hsk = k.data_ptr(), k.stride(0), k.stride(1)
     d.v, d.ldv, d.hsv = v.data_ptr(), v.stride(0), v.stride(1)
     d.out, d.ldo, d.out_img_stride = out.data_ptr(), out.stride(1), out.stride(0)
+    if lse2 is not None:
+        # [n_img, heads, n_q] view of a (possibly longer) [n_img, heads, N] table: row stride = N
+        if lse2.dtype != torch.float32 or lse2.shape != (n_img, heads, n_q) or lse2.stride(2) != 1 or \
+                (n_img > 1 and lse2.stride(0) != heads * lse2.stride(1)):
+            raise ValueError("lse2 must be a float32 [n_img, heads, n_q] view with uniform head stride")
+        d.lse2, d.lse2_stride = lse2.data_ptr(), lse2.stride(1)
     _lib.check("foho_tc_attention", lib.foho_tc_attention(C.byref(d), _stream_ptr(stream)))
     return out

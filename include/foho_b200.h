@@ -299,7 +299,9 @@ int foho_mesh_decimate(const double *verts, int32_t V, const int32_t *faces, int
  * A is [M,K] and B is [N,K] (the nn.Linear weight layout) when K-major; an MN-major operand is stored
  * [K,M] / [K,N] instead (row = k).  Leading dimensions and batch strides in ELEMENTS; operands fp16,
  * 16-byte aligned, lda/ldb/K multiples of 8.  act: 0 none, 1 GELU (erf), 2 multiply by GELU'(aux_in[m][n])
- * (the backward of act 1).  aux_out (optional, fp16) receives the pre-activation value. */
+ * (the backward of act 1), 3 exp2(x - row_vec[m]) (softmax probabilities from saved log2-sum-exps: the attention
+ * adjoint never materialises float32 scores), 4 aux_in[m][n] * (x - alpha * row_vec[m]) (softmax backward, row_vec =
+ * rowsum(dO o O)).  aux_out (optional, fp16) receives the pre-activation value. */
 typedef struct foho_gemm_desc {
   int32_t M, N, K, batch;
   int32_t a_mn_major, b_mn_major;
@@ -315,6 +317,7 @@ typedef struct foho_gemm_desc {
   const float *bias;         /* device [N] float32 or NULL                                   */
   const void *res; int64_t ldr, bsr;     /* NULL = none; may alias C (in-place accumulate)  */
   const void *aux_in; void *aux_out; int64_t ldaux, bsaux;
+  const float *row_vec; int64_t bs_rowvec;   /* act 3 / 4: one float per output row (batch stride in elements) */
 } foho_gemm_desc;
 int foho_tc_gemm(const foho_gemm_desc *desc, void *cuda_stream);
 
@@ -335,6 +338,9 @@ typedef struct foho_attn_desc {
   const void *k; int64_t ldk, hsk;
   const void *v; int64_t ldv, hsv;
   void *out; int64_t ldo, out_img_stride;   /* fp16 [n_img][n_q][heads*64], 16-byte aligned */
+  float *lse2;               /* optional OUT float32 [n_img][heads][lse2_stride]: log2-sum-exp of the scaled scores of query
+                                row q at [..][q] (variant 0) */
+  int64_t lse2_stride;       /* 0 = n_q; larger when a chunk of queries writes into the rows of a longer table */
 } foho_attn_desc;
 int foho_tc_attention(const foho_attn_desc *desc, void *cuda_stream);
 
@@ -366,6 +372,13 @@ int foho_dec_gather_rows(const void *in, int64_t ld_in, const int32_t *idx, void
  * mode 0: f32 -> f16 (x scale); 1: f16 -> f32 (x scale); 2: f16 -> f32 accumulate; 3: out += in (fp16, contiguous) */
 int foho_dec_cast(const void *in, int64_t ld_in, void *out, int64_t ld_out, int64_t rows, int32_t cols, float scale, int32_t mode,
                   void *cuda_stream);
+
+/* delta[h][r] = sum_d a[r][h][d] * b[r][h][d] (64 channels per head; a, b fp16 [rows, heads*64] with leading dimensions lda,
+ * ldb): the rowsum(dO o O) of the attention backward.  out float32 [heads, rows]. */
+int foho_dec_rowdot(const void *a, int64_t lda, const void *b, int64_t ldb, float *out, int64_t rows, int32_t heads, void *cuda_stream);
+/* out[h][i] = src[h * src_head_stride + idx[i]] (float32): per-head gather of saved log-sum-exps for the active rows */
+int foho_dec_gather_f32(const float *src, int64_t src_head_stride, const int32_t *idx, float *out, int64_t n, int32_t heads,
+                        void *cuda_stream);
 
 /* Sparse view of a dense dE/dSDF [B, V]: the non-zero entries of image b, in a
  * deterministic order, go to idx / val [b, 0..count[b]) (capacity cap per image, the rest zeroed: index 0, gradient 0);

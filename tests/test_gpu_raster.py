@@ -68,7 +68,7 @@ def test_rasteriser_losses_and_vertex_gradients_match_the_oracle(B, H, W):
     fovs = [41.0, 55.0][:B]
     scenes = [_scene(10 + b, H, W, fovs[b]) for b in range(B)]
     verts, faces, vo, fo = pack_meshes([(s[0], s[1]) for s in scenes])
-    R = ImageLossRenderer(B, H, W, verts.shape[0], faces.shape[0])
+    R = ImageLossRenderer(B, H, W, verts.shape[0], faces.shape[0], tile_cap=2304)   # tiny image: a whole mesh per tile
     R.set_targets(ImageTargets(gt_normals=torch.stack([s[2] for s in scenes]), gt_mask=torch.stack([s[3] for s in scenes]),
                                gt_disp=torch.stack([s[4] for s in scenes]), gt_sil=torch.stack([s[5] for s in scenes]),
                                fov_deg=torch.tensor(fovs)))
@@ -76,6 +76,9 @@ def test_rasteriser_losses_and_vertex_gradients_match_the_oracle(B, H, W):
     torch.cuda.synchronize()
     losses = losses.cpu().double(); gv = gv.cpu().double()
     assert (losses[:, 7] == 0).all()                        # no tile overflow
+    R_small = ImageLossRenderer(B, H, W, verts.shape[0], faces.shape[0], tile_cap=64)
+    R_small.targets, R_small._n_valid = R.targets, R._n_valid
+    assert (R_small(verts, faces, vo, fo, backward=False)[0][:, 7] == 1).all()          # ... and an overflow is reported, not silent
     off = 0
     for b, (v, f, gt_n, gt_m, gt_d, gt_s) in enumerate(scenes):
         vq = v.float().double().clone().requires_grad_(True)            # the kernel sees float32 vertices
