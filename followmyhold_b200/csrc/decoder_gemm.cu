@@ -30,14 +30,17 @@ struct GemmParams {
   const void *res; long long ldr, bsr; int res_f32;
   const __half *aux_in; __half *aux_out; long long ldaux, bsaux;
   float alpha; int act;
+  int c_fast, aux_fast;          // 16-byte aligned rows: outputs leave through the coalescing shared-memory stage
   const float *row_vec; long long bs_rowvec;     // act 3 / 4: one float per output row
 };
 
 template <int BN>
 struct Cfg {
   static constexpr int A_BYTES = BM * BK * 2, B_BYTES = BN * BK * 2, STAGE_BYTES = A_BYTES + B_BYTES;
-  static constexpr int STAGES = (200 * 1024 / STAGE_BYTES) > 8 ? 8 : (200 * 1024 / STAGE_BYTES);
-  static constexpr int SMEM = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+  static constexpr int STG_ROW = 144;                       // bytes per staged output row (128 + 16: conflict-free 16-byte writes)
+  static constexpr int STG_BYTES = 8 * 16 * STG_ROW;         // eight epilogue warps x 16 rows (a chunk leaves in two halves)
+  static constexpr int STAGES = (192 * 1024 / STAGE_BYTES) > 8 ? 8 : (192 * 1024 / STAGE_BYTES);
+  static constexpr int SMEM = STAGES * STAGE_BYTES + STG_BYTES + 1024 /*align*/ + 256 /*barriers*/;
   static constexpr uint32_t TMEM_COLS = 2 * BN;
 };
 
@@ -46,12 +49,14 @@ struct Cfg {
 // is what the tile's 256 x 128 outputs spend their time on
 __device__ __forceinline__ float erf_fast(float x) {
   const float ax = fabsf(x);
-  const float t = __frcp_rn(fmaf(0.3275911f, ax, 1.0f));
+  float t;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t) : "f"(fmaf(0.3275911f, ax, 1.0f)));
   float p = fmaf(1.061405429f, t, -1.453152027f);
   p = fmaf(p, t, 1.421413741f);
   p = fmaf(p, t, -0.284496736f);
   p = fmaf(p, t, 0.254829592f);
-  const float e = exp2f(-1.4426950408889634f * ax * ax);
+  float e;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(-1.4426950408889634f * ax * ax));
   const float r = fmaf(-p * t, e, 1.0f);
   return copysignf(r, x);
 }
@@ -60,13 +65,55 @@ __device__ __forceinline__ float dgelu_f(float x) {
   return 0.5f * (1.0f + erf_fast(x * 0.70710678118654752f)) + x * 0.3989422804014327f * exp2f(-0.72134752044448170f * x * x);
 }
 
+// One warp's 32 x 32 chunk of outputs (lane = row) -> global memory in full 16-byte x 4 (fp16) / x 8 (fp32) row segments:
+// each lane parks its row in shared memory, then the warp writes 8 (fp16) or 4 (fp32) rows per instruction, so an
+// instruction touches 8 / 4 cache lines instead of 32 (row-per-lane stores were what bounded every K <= 1024 product).
+template <bool F32>
+__device__ __forceinline__ void staged_store(uint8_t *stg, int lane, const float (&f)[32], void *C, long long row0_off, long long ld,
+                                             int rows_valid, int cols_valid) {
+  constexpr int SEG = F32 ? 8 : 4;            // 16-byte segments per row
+  constexpr int RPI = 32 / SEG;               // rows per instruction
+  constexpr int EPS = F32 ? 4 : 8;            // elements per segment
+  const int seg = lane % SEG, rsub = lane / SEG;
+#pragma unroll
+  for (int hf = 0; hf < 2; ++hf) {            // rows 0..15, then 16..31: the stage holds 16 rows per warp
+    if ((lane >> 4) == hf) {
+      uint8_t *mine = stg + (lane & 15) * 144;
+      if (F32) {
+#pragma unroll
+        for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4 *>(mine + j * 4) = make_float4(f[j], f[j + 1], f[j + 2], f[j + 3]);
+      } else {
+#pragma unroll
+        for (int j = 0; j < 32; j += 8) {
+          __align__(16) __half2 h[4];
+#pragma unroll
+          for (int t = 0; t < 4; ++t) h[t] = __floats2half2_rn(f[j + 2 * t], f[j + 2 * t + 1]);
+          *reinterpret_cast<uint4 *>(mine + j * 2) = *reinterpret_cast<uint4 *>(h);
+        }
+      }
+    }
+    __syncwarp();
+#pragma unroll
+    for (int i = 0; i < 16 / RPI; ++i) {
+      const int rl = i * RPI + rsub, r = hf * 16 + rl;
+      if (r < rows_valid && seg * EPS < cols_valid) {
+        const uint4 v = *reinterpret_cast<const uint4 *>(stg + rl * 144 + seg * 16);
+        uint8_t *dst = reinterpret_cast<uint8_t *>(C) + (row0_off + (long long)r * ld + seg * EPS) * (F32 ? 4 : 2);
+        *reinterpret_cast<uint4 *>(dst) = v;
+      }
+    }
+    __syncwarp();
+  }
+}
+
 template <int BN, bool A_MN, bool B_MN>
 __global__ void __launch_bounds__(384, 1)
 k_gemm_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmParams p) {
   using C_ = Cfg<BN>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint64_t *bars = reinterpret_cast<uint64_t *>(smem + C_::STAGES * C_::STAGE_BYTES);
+  uint8_t *stg_base = smem + C_::STAGES * C_::STAGE_BYTES;
+  uint64_t *bars = reinterpret_cast<uint64_t *>(stg_base + C_::STG_BYTES);
   uint64_t *full = bars, *empty = bars + C_::STAGES, *tfull = bars + 2 * C_::STAGES, *tempty = tfull + 2;
   uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(tempty + 2);
 
@@ -164,9 +211,14 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
         tc::tmem_ld32(tmem_base + acc * BN + c * 32 + ((uint32_t)(q * 32) << 16), v);
         tc::tmem_ld_wait();
         const int n = n0 + c * 32;
-        if (row_ok && n < p.N) {
-          const bool full_chunk = (n + 32 <= p.N);
-          float f[32];
+        if (n >= p.N) continue;                           // warp-uniform: whole chunk outside the matrix
+        const bool full_chunk = (n + 32 <= p.N);
+        const int rows_valid = min(32, p.M - (m0 + q * 32)), cols_valid = min(32, p.N - n);
+        uint8_t *stg = stg_base + (warp - 4) * (16 * C_::STG_ROW);
+        const long long row0 = (long long)(m0 + q * 32);
+        float f[32];
+        float pre[32];
+        if (row_ok) {
 #pragma unroll
           for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]) * p.alpha;
           if (p.bias) {
@@ -174,18 +226,8 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
             for (int j = 0; j < 32; ++j) if (full_chunk || n + j < p.N) f[j] += __ldg(p.bias + n + j);
           }
           if (p.aux_out) {
-            __half *ao = p.aux_out + (long long)b * p.bsaux + (long long)m * p.ldaux + n;
-            if (full_chunk && ((reinterpret_cast<uintptr_t>(ao) & 15) == 0)) {
 #pragma unroll
-              for (int j = 0; j < 32; j += 8) {
-                __align__(16) __half2 h[4];
-#pragma unroll
-                for (int t = 0; t < 4; ++t) h[t] = __floats2half2_rn(f[j + 2 * t], f[j + 2 * t + 1]);
-                *reinterpret_cast<uint4 *>(ao + j) = *reinterpret_cast<uint4 *>(h);
-              }
-            } else {
-              _Pragma("unroll") for (int j = 0; j < 32; ++j) if (n + j < p.N) ao[j] = __float2half_rn(f[j]);
-            }
+            for (int j = 0; j < 32; ++j) pre[j] = f[j];
           }
           if (p.act == 1) {
 #pragma unroll
@@ -258,27 +300,25 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
               }
             }
           }
+        }
+        if (p.aux_out) {
+          if (p.aux_fast) {
+            staged_store<false>(stg, lane, pre, p.aux_out, (long long)b * p.bsaux + row0 * p.ldaux + n, p.ldaux, rows_valid, cols_valid);
+          } else if (row_ok) {
+            __half *ao = p.aux_out + (long long)b * p.bsaux + (long long)m * p.ldaux + n;
+            _Pragma("unroll") for (int j = 0; j < 32; ++j) if (n + j < p.N) ao[j] = __float2half_rn(pre[j]);
+          }
+        }
+        if (p.c_fast) {
+          if (p.c_f32) staged_store<true>(stg, lane, f, p.C, (long long)b * p.bsc + row0 * p.ldc + n, p.ldc, rows_valid, cols_valid);
+          else staged_store<false>(stg, lane, f, p.C, (long long)b * p.bsc + row0 * p.ldc + n, p.ldc, rows_valid, cols_valid);
+        } else if (row_ok) {
           if (p.c_f32) {
             float *cp = reinterpret_cast<float *>(p.C) + (long long)b * p.bsc + (long long)m * p.ldc + n;
-            if (full_chunk && ((reinterpret_cast<uintptr_t>(cp) & 15) == 0)) {
-#pragma unroll
-              for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4 *>(cp + j) = make_float4(f[j], f[j + 1], f[j + 2], f[j + 3]);
-            } else {
-              _Pragma("unroll") for (int j = 0; j < 32; ++j) if (n + j < p.N) cp[j] = f[j];
-            }
+            _Pragma("unroll") for (int j = 0; j < 32; ++j) if (n + j < p.N) cp[j] = f[j];
           } else {
             __half *cp = reinterpret_cast<__half *>(p.C) + (long long)b * p.bsc + (long long)m * p.ldc + n;
-            if (full_chunk && ((reinterpret_cast<uintptr_t>(cp) & 15) == 0)) {
-#pragma unroll
-              for (int j = 0; j < 32; j += 8) {
-                __align__(16) __half2 h[4];
-#pragma unroll
-                for (int t = 0; t < 4; ++t) h[t] = __floats2half2_rn(f[j + 2 * t], f[j + 2 * t + 1]);
-                *reinterpret_cast<uint4 *>(cp + j) = *reinterpret_cast<uint4 *>(h);
-              }
-            } else {
-              _Pragma("unroll") for (int j = 0; j < 32; ++j) if (n + j < p.N) cp[j] = __float2half_rn(f[j]);
-            }
+            _Pragma("unroll") for (int j = 0; j < 32; ++j) if (n + j < p.N) cp[j] = __float2half_rn(f[j]);
           }
         }
       }
@@ -318,6 +358,12 @@ int launch_gemm(const foho_gemm_desc *d, cudaStream_t st) {
   p.aux_in = reinterpret_cast<const __half *>(d->aux_in); p.aux_out = reinterpret_cast<__half *>(d->aux_out);
   p.ldaux = d->ldaux; p.bsaux = d->bsaux;
   p.alpha = d->alpha; p.act = d->act;
+  {
+    const int es = d->c_f32 ? 4 : 2;
+    p.c_fast = ((reinterpret_cast<uintptr_t>(d->C) & 15) == 0) && (d->ldc * es) % 16 == 0 && (d->bsc * es) % 16 == 0 && d->N % (16 / es) == 0;
+    p.aux_fast = d->aux_out && ((reinterpret_cast<uintptr_t>(d->aux_out) & 15) == 0) && (d->ldaux * 2) % 16 == 0 && (d->bsaux * 2) % 16 == 0 &&
+                 d->N % 8 == 0;
+  }
   p.row_vec = d->row_vec; p.bs_rowvec = d->bs_rowvec;
   static int sm_count = 0;
   if (!sm_count) {

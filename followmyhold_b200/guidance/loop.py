@@ -190,6 +190,49 @@ class GuidanceLoop:
     def kernels_per_eval(self) -> int:
         return self.engine.launches_per_eval + 3     # + decoder fwd, decoder adjoint, fused update
 
+    # ------------------------------------------------------------------ rendered hand terms (row f2, first part)
+    def enable_image_terms(self, targets, hand_faces_render: Optional[torch.Tensor] = None, tile_cap: int = 1024) -> None:
+        """Switch on the rendered hand terms of the reference: phase 1 ``1 * normal + 10 * disparity + 1 * silhouette``
+        (pipelines.py:1327-1349), phases 2 ``hand_loss`` part ``10 * normal + 10 * disparity`` (:1488-1504, inside the
+        ``1e-3 * hand_loss`` of :1588).  ``targets``: ``render.ImageTargets`` for the B images -- MoGe normal map with
+        the hand mask as valid mask, ``moge_disp * hand_mask``, the hand silhouette (:1230-1256).  ``hand_faces_render``
+        [F,3] int32: the topology to render (default: the statics' faces; pass the uncapped MANO faces when those
+        were closed for the sign rule).  The transformed hand is rendered by ``foho_raster_losses_fwd_bwd``; its
+        vertex gradient enters the fused evaluation through ``grad_hand_ext``.  The joined hand + object terms
+        (:1544-1569) need the extracted object mesh (FlexiCubes, not built) and are not part of this."""
+        from .render import ImageLossRenderer, ImageTargets
+        Vh = self.statics.hand_rest.shape[1]
+        faces = (hand_faces_render if hand_faces_render is not None else self.statics.hand_faces).to(self.device, torch.int32)
+        H, W = int(targets.gt_normals.shape[1]), int(targets.gt_normals.shape[2])
+        for ln in self.lanes:
+            nb = ln.nb
+            r = ImageLossRenderer(nb, H, W, nb * Vh, nb * faces.shape[0], device=self.device, tile_cap=tile_cap)
+            cut = lambda t: t.narrow(0, ln.off, nb)
+            r.set_targets(ImageTargets(gt_normals=cut(targets.gt_normals), gt_mask=cut(targets.gt_mask), gt_disp=cut(targets.gt_disp),
+                                       gt_sil=cut(targets.gt_sil), fov_deg=cut(targets.fov_deg)))
+            ln.renderer = r
+            ln.render_faces = torch.cat([faces + b * Vh for b in range(nb)]).contiguous()
+            ln.render_vo = torch.arange(0, (nb + 1) * Vh, Vh, dtype=torch.int32, device=self.device)
+            ln.render_fo = torch.arange(0, (nb + 1) * faces.shape[0], faces.shape[0], dtype=torch.int32, device=self.device)
+        self.image_terms = torch.zeros(self.B, 8, dtype=torch.float32, device=self.device)
+
+    def _hand_image_grad(self, ln: _Lane, phase: float, s: torch.cuda.Stream, weights=None) -> Optional[torch.Tensor]:
+        """Enqueue prep (-> transformed hand) + renderer; returns dE_img/d(transformed hand verts) [nb,Vh,3] or None."""
+        r = getattr(ln, "renderer", None)
+        if r is None or phase == 1.5:                        # the object-only step does not move the hand (:1361-1453)
+            return None
+        w_hand = float((weights or self.phase_weights(phase)).w_hand)
+        r.w = (1.0 * w_hand, 10.0 * w_hand, 1.0 * w_hand) if phase == 1 else (10.0 * w_hand, 10.0 * w_hand, 0.0)
+        theta = self.theta.narrow(0, ln.off, ln.nb)
+        desc = ln.engine.make_desc(self.sdf.narrow(0, ln.off, ln.nb), theta, ln.statics)
+        desc.stage_mask = 1                                  # prep only: leaves -> transformed hand vertices
+        ln.engine.launch(desc, s)
+        Vh = ln.statics.hand_rest.shape[1]
+        losses, g = r(ln.engine.hand_moge.view(-1, 3), ln.render_faces, ln.render_vo, ln.render_fo, stream=s)
+        with torch.cuda.stream(s):
+            self.image_terms.narrow(0, ln.off, ln.nb).copy_(losses)
+        return g.view(ln.nb, Vh, 3)
+
     # ------------------------------------------------------------------ one evaluation (enqueue only)
     def _enqueue_eval(self, sigma: float, late_step: bool, s: torch.cuda.Stream, phase: float = 2, lane: Optional[_Lane] = None,
                       log_slot: Optional[torch.Tensor] = None) -> None:
@@ -205,7 +248,7 @@ class GuidanceLoop:
         if not hand_only:
             _lib.check("foho_mock_decoder_forward", lib.foho_mock_decoder_forward(
                 sdf.data_ptr(), sdf0.data_ptr(), x1.data_ptr(), self.tap.data_ptr(), nb, vol, self.L, self.alpha, sp))
-        desc = ln.engine.make_desc(sdf, theta, ln.statics, late_step=late_step)
+        desc = ln.engine.make_desc(sdf, theta, ln.statics, late_step=late_step, grad_hand_ext=self._hand_image_grad(ln, phase, s))
         if phase != 2:
             self._phase_w = self.phase_weights(phase)      # keep the struct alive while the call reads it
             desc.w = self._phase_w
@@ -477,8 +520,9 @@ class GuidanceLoop:
                     if not keep_mom:
                         w.w_mom = 0.0
                     for k in range(self.phase_iterations(phase)):
+                        g_img = self._hand_image_grad(ln, phase, s, w)
                         if phase == 1:
-                            desc = eng.make_desc(self.sdf, self.theta, ln.statics, late_step=late)
+                            desc = eng.make_desc(self.sdf, self.theta, ln.statics, late_step=late, grad_hand_ext=g_img)
                             desc.w = w
                             desc.stage_mask = 1 | 4 | 16
                             eng.launch(desc, s)
@@ -488,7 +532,7 @@ class GuidanceLoop:
                                 self.x_t.data_ptr(), self.velocity.data_ptr(), None, self.x1.data_ptr(), self.x_t.numel(),
                                 sigma, sigma_next, sp))                                   # step_final (:1507)
                             decoder.forward(self.x1.view(B, LATENT_SHAPE[0], LATENT_SHAPE[1]), out=self.sdf.view(B, V), stream=s)
-                            desc = eng.make_desc(self.sdf, self.theta, ln.statics, late_step=late)
+                            desc = eng.make_desc(self.sdf, self.theta, ln.statics, late_step=late, grad_hand_ext=g_img)
                             desc.w = w
                             eng.launch(desc, s)
                             idx, val = comp(eng.grad_sdf.view(B, V), stream=s)

@@ -293,7 +293,20 @@ def _run_batch(chunk, model: GuidanceModel, J: torch.Tensor, config: Optimizatio
     gen = torch.Generator().manual_seed(seed)                   # run.py:120 torch.manual_seed(2)
     last = config.num_inference_steps - 1
     decode = getattr(model, "decode", None)
-    if callable(decode):
+    tc_decoder = getattr(model, "tc_decoder", None)
+    if callable(tc_decoder):
+        # the reference's own decoder on the tensor cores: latent2sdf + adjoint as kernels, no autograd (row f1)
+        dec = tc_decoder(B)
+        loop = GuidanceLoop(B, model.D, st, n_cloud, device=dev, config=config, latent_elems=model.latent_elems,
+                            loss_log_every=10 if debug_root else 0, mock_decoder=False)
+        loop.sdf.fill_(1.0)                                     # finite "outside" volume for the hand-only phase
+        loop.x_t.copy_(model.initial_latents(B, gen))
+        loop.reset_leaves()
+        loop.run_schedule_tc_decoder(model.predict, dec)
+        loop.check_overflow()
+        x1 = (loop.x_t + (1.0 - float(loop.sigmas[last])) * loop.velocity).contiguous()      # final decode (:1641), sigma_last = 1
+        sdf = dec.forward(x1.view(B, 3072, 64)).reshape(B, model.D, model.D, model.D).cpu().numpy()
+    elif callable(decode):
         # a differentiable network decoder in the loop (eager; autograd carries dE/dSDF to the model output)
         loop = GuidanceLoop(B, model.D, st, n_cloud, device=dev, config=config, latent_elems=model.latent_elems,
                             loss_log_every=10 if debug_root else 0)

@@ -117,3 +117,61 @@ def test_forward_only_and_determinism():
         assert torch.equal(l0, l1) and torch.equal(g0, g1)
     l2, g2 = R(verts, faces, vo, fo, backward=False)
     assert g2 is None and torch.equal(l2, l0)
+
+
+def test_rendered_hand_terms_reach_the_leaves_like_autograd():
+    """Phase-1 hand terms of the reference (1 * normal + 10 * disparity + 1 * silhouette, pipelines.py:1327-1349) wired
+    into the fused evaluation through ``grad_hand_ext``: the change they make to dE/d(s_h, t_h, q_h) equals autograd
+    through the oracle's similarity transform (a6), renderer and losses."""
+    from followmyhold_b200.guidance.loop import GuidanceLoop
+    from followmyhold_b200.guidance.render import ImageTargets
+    from followmyhold_b200.synthetic import make_guidance_sample, stack_samples
+    from oracle import guidance_oracle as O
+    from oracle import raster_oracle as RO
+    B, D, P, H, W = 2, 32, 512, 96, 96
+    fovs = [41.0, 47.0]
+    samples = [make_guidance_sample(D, P, 30 + i) for i in range(B)]
+    sdf, theta, st = stack_samples(samples, cap=True)
+    raw_faces = samples[0].hand_faces.to(torch.int64)
+    assert float(st.hand_rest[..., 2].max()) < 0          # MoGe frame: the scene sits in front of a camera looking down -z
+    loop = GuidanceLoop(B, D, st, P, micro_batches=1, mock_decoder=False)
+    loop.theta.copy_(theta); loop.sdf.copy_(sdf)
+    tg = []
+    for b in range(B):
+        th = theta[b, :8].cpu().double()
+        hm = O.transform_around_center_w_scale(st.hand_rest[b].cpu().double(), th)
+        tv = hm + torch.tensor([0.01, -0.015, 0.02], dtype=torch.float64)
+        with torch.no_grad():
+            n4, zb, _ = RO.render_normals_and_depth(tv, raw_faces, fovs[b], H, W)
+            m = n4[..., 3] > 0
+            _, _, _, rn, rd = _image_losses_torch(n4, zb, torch.ones(H, W, 3, dtype=torch.float64), m, torch.zeros(H, W, dtype=torch.float64),
+                                                  torch.zeros(H, W, dtype=torch.float64))
+        tg.append((rn, m, rd * m, m.double()))
+    assert all(int(t[1].sum()) > 50 for t in tg), "the synthetic hand must be visible"
+    loop.enable_image_terms(ImageTargets(gt_normals=torch.stack([t[0] for t in tg]), gt_mask=torch.stack([t[1] for t in tg]),
+                                         gt_disp=torch.stack([t[2] for t in tg]), gt_sil=torch.stack([t[3] for t in tg]),
+                                         fov_deg=torch.tensor(fovs)), hand_faces_render=raw_faces.to(torch.int32), tile_cap=2048)
+    ln = loop.lanes[0]
+    eng = ln.engine
+    s = torch.cuda.current_stream()
+    w1 = loop.phase_weights(1)
+    res = []
+    for with_img in (False, True):
+        g = loop._hand_image_grad(ln, 1, s, w1) if with_img else None
+        desc = eng.make_desc(loop.sdf, loop.theta, st, grad_hand_ext=g)
+        desc.w = w1
+        eng.launch(desc, s)
+        torch.cuda.synchronize()
+        res.append(eng.grad_theta.clone().cpu().double())
+    diff = (res[1] - res[0])[:, :8]
+    assert (res[1] - res[0])[:, 8:].abs().max() == 0            # the object leaves do not see the hand render
+    for b in range(B):
+        th = theta[b, :8].cpu().double().clone().requires_grad_(True)
+        hm = O.transform_around_center_w_scale(st.hand_rest[b].cpu().double(), th)
+        n4, zb, _ = RO.render_normals_and_depth(hm, raw_faces, fovs[b], H, W)
+        l_n, l_d, l_s, _, _ = _image_losses_torch(n4, zb, *tg[b])
+        (float(w1.w_hand) * (1.0 * l_n + 10.0 * l_d)).backward()
+        ref = th.grad
+        assert abs(float(loop.image_terms[b, 0]) - float(l_n)) <= 5e-3 * abs(float(l_n)) + 1e-6
+        assert abs(float(loop.image_terms[b, 1]) - float(l_d)) <= 5e-3 * abs(float(l_d)) + 1e-6
+        assert (diff[b] - ref).abs().max().item() <= 3e-2 * ref.abs().max().item(), (diff[b], ref)
