@@ -306,6 +306,60 @@ def decoder_leg(dev, n_images: int = 1, D_lat: int = 65, n_active: int = 8192, r
     }
 
 
+# --------------------------------------------------------------------------- the reference's own lattices (extra keys)
+def reference_lattice_leg(dev, steps: int = 10):
+    """Not the headline: the same loop at the reference's real shapes -- B = 8 images on the 65^3
+    lattice with the largest cloud (512^2 crop = 262 144 points), 50 evaluations per step, mock latents; and one
+    evaluation on the 385^3 export lattice.  Both go through the generic stream kernel (`k_stream_any`: D is odd)."""
+    import torch
+    from followmyhold_b200.guidance.engine import GuidanceEngine
+    from followmyhold_b200.guidance.loop import GuidanceLoop
+    from followmyhold_b200.synthetic import make_guidance_sample, stack_samples
+    out = {}
+    B, D65, P65 = 8, 65, 262144
+    samples = [make_guidance_sample(D65, P65, seed=900 + i) for i in range(B)]
+    sdf0, theta0, st = stack_samples(samples, device=dev, cap=True)
+    loop = GuidanceLoop(B, D65, st, P65, device=dev, micro_batches=2)
+    g = torch.Generator().manual_seed(5)
+    loop.sdf0.copy_(sdf0); loop.sdf.copy_(sdf0); loop.theta.copy_(theta0)
+    loop.x_t.copy_(torch.randn(B, loop.L, generator=g)); loop.velocity.copy_(0.1 * torch.randn(B, loop.L, generator=g))
+    loop.capture(STEP_INDEX)
+    for _ in range(3):
+        loop.run_step_device(STEP_INDEX)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        loop.run_step_device(STEP_INDEX)
+    e1.record(); torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / steps
+    assert torch.isfinite(loop.terms).all()
+    out["ref65"] = {"workload": "B=8, D=65 (pipelines.py:1126-1137), P=262144, 50 evaluations per step, mock latents",
+                    "image_steps_per_sec": B * 1e3 / ms, "ms_per_step": ms, "evals_per_sec": B * EVALS_PER_STEP * 1e3 / ms,
+                    "us_per_evaluation_of_the_batch": 1e3 * ms / EVALS_PER_STEP,
+                    "launches_per_evaluation": loop.kernels_per_eval() * loop.micro_batches,
+                    "note": "1.1 MB of volume per image: launch / latency bound, not HBM bound"}
+    del loop
+    D385, P385 = 385, 65536
+    s = make_guidance_sample(D385, P385, seed=950)
+    sdf, theta, st1 = stack_samples([s], device=dev, cap=True)
+    eng = GuidanceEngine(1, D385, 778, st1.hand_faces.shape[0], P385, device=dev)
+    eng.prepare(st1)
+    for _ in range(3):
+        eng.energy_fwd_bwd(sdf, theta, st1)
+    torch.cuda.synchronize()
+    e0.record()
+    for _ in range(20):
+        eng.energy_fwd_bwd(sdf, theta, st1)
+    e1.record(); torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / 20
+    peak, _ = measured_peak_gbs()
+    out["export385"] = {"workload": "one 385^3 volume (the export lattice, pipelines.py:1624-1639), P=65536, one evaluation",
+                        "eval_ms": ms, "GBps_algorithmic": 8 * D385 ** 3 / (ms * 1e-3) / 1e9, "frac_of_hbm_peak": 8 * D385 ** 3 / (ms * 1e-3) / 1e9 / peak,
+                        "stream_kernel": "k_stream_any"}
+    return out
+
+
 # --------------------------------------------------------------------------- GPU arm
 def run_ours(args):
     import torch
@@ -541,8 +595,18 @@ def run_ours(args):
         if world == 1 and not args.no_decoder:
             try:
                 line["decoder"] = decoder_leg(dev)
+                d8 = decoder_leg(dev, n_images=8, reps=2)
+                line["decoder"]["batch8"] = {k: d8[k] for k in ("workload", "forward_ms", "adjoint_ms", "forward_tflops", "adjoint_tflops",
+                                                                 "decodes_per_sec", "evaluations_per_sec_decoder_only")}
+                line["decoder"]["batch8"]["frac_forward"] = d8["roofline"]["frac"]
             except Exception as e:          # the headline line must survive a failure of this extra leg
-                line["decoder"] = {"error": f"{type(e).__name__}: {e}"}
+                line.setdefault("decoder", {})["error"] = f"{type(e).__name__}: {e}"
+            torch.cuda.empty_cache()
+            try:
+                line["reference_lattices"] = reference_lattice_leg(dev)
+            except Exception as e:
+                line["reference_lattices"] = {"error": f"{type(e).__name__}: {e}"}
+            torch.cuda.empty_cache()
         if world == 1 and not args.no_cpu:
             os.sched_setaffinity(0, orig_affinity)      # the CPU leg gets every host core back
             eps, cores, n, el = cpu_guidance_evals_per_sec(args.cpu_seconds)

@@ -359,6 +359,74 @@ __global__ void __launch_bounds__(256) k_stream_any(const float *__restrict__ sd
   }
 }
 
+// Generic path, vectorised: the volume of image b is one flat array; a 16-byte aligned body is streamed as float4
+// (head / tail of at most 3 voxels scalar, by one thread), lattice coordinates come from one magic-number division
+// per float4 and a carry for the other three voxels -- no per-voxel div / mod (the reference's lattices are odd:
+// 65^3, 385^3).
+__global__ void __launch_bounds__(256) k_stream_any4(const float *__restrict__ sdf, float *__restrict__ grad,
+                                                     const StreamSrc src, float *__restrict__ partials,
+                                                     int D, float cN, unsigned long long magic) {
+  FohoTrace trace_(src.trace, TR_STREAM);
+  __shared__ float red[6 * 32];
+  __shared__ StreamCoef sc;
+  const int b = blockIdx.y;
+  const StreamCoef c = stream_coef(src, b, D, cN, &sc);
+  const long long vol = (long long)D * D * D;
+  const float *__restrict__ S = sdf + (size_t)b * vol;
+  float *__restrict__ G = grad + (size_t)b * vol;
+  float v[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  auto one = [&](long long i, int ix, int iy, int iz, float s) -> float {
+    const float fx = (float)ix, fy = (float)iy, fz = (float)iz;
+    const float r2 = fx * fx + fy * fy;
+    const float crow = fmaf(c.k2, r2, fmaf(c.ex, fx, fmaf(c.ey, fy, c.f)));
+    const float czz = fmaf(c.k2 * fz, fz, c.ez * fz);
+    const float w = foho_relu(-s);
+    v[0] += w;
+    v[1] = fmaf(fx, w, v[1]);
+    v[2] = fmaf(fy, w, v[2]);
+    v[3] = fmaf(fz, w, v[3]);
+    v[4] = fmaf(r2 + fz * fz, w, v[4]);
+    (void)i;
+    return s < 0.f ? czz + crow : 0.f;
+  };
+  auto coords = [&](long long i, int &ix, int &iy, int &iz) {
+    const unsigned long long r = ((unsigned long long)i * magic) >> 40;     // i / D, exact for i < 2^40 / D
+    iz = (int)(i - (long long)r * D);
+    const unsigned long long q = (r * magic) >> 40;
+    ix = (int)q; iy = (int)(r - q * D);
+  };
+  const int head = (int)((4 - ((reinterpret_cast<uintptr_t>(S) >> 2) & 3)) & 3);          // voxels before the aligned body
+  const long long n4 = (vol - head) >> 2;
+  const long long tail0 = head + (n4 << 2);
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    for (long long i = 0; i < head && i < vol; ++i) { int ix, iy, iz; coords(i, ix, iy, iz); G[i] = one(i, ix, iy, iz, S[i]); }
+    for (long long i = tail0; i < vol; ++i) { int ix, iy, iz; coords(i, ix, iy, iz); G[i] = one(i, ix, iy, iz, S[i]); }
+  }
+  const float4 *__restrict__ S4 = reinterpret_cast<const float4 *>(S + head);
+  float4 *__restrict__ G4 = reinterpret_cast<float4 *>(G + head);
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x; k < n4; k += stride) {
+    const long long i = head + (k << 2);
+    int ix, iy, iz;
+    coords(i, ix, iy, iz);
+    const float4 s = __ldcs(S4 + k);
+    const float sv[4] = {s.x, s.y, s.z, s.w};
+    float g[4];
+#pragma unroll
+    for (int t = 0; t < 4; ++t) {
+      g[t] = one(i + t, ix, iy, iz, sv[t]);
+      if (++iz == D) { iz = 0; if (++iy == D) { iy = 0; ++ix; } }
+    }
+    __stcs(G4 + k, make_float4(g[0], g[1], g[2], g[3]));
+  }
+  block_sum<6>(v, red);
+  if (threadIdx.x == 0) {
+    float *part = partials + ((size_t)b * FOHO_MAX_STREAM_CTAS + blockIdx.x) * FOHO_STREAM_PARTIALS;
+    for (int i = 0; i < 6; ++i) part[i] = v[i];
+    part[6] = part[7] = 0.f;
+  }
+}
+
 int ilog2_exact(int D) {
   int l = 0;
   while ((1 << l) < D) ++l;
@@ -423,7 +491,13 @@ int foho_launch_stream(const foho_guidance_desc *d, const FohoWorkspace &ws, int
     if (gx > nblk) gx = (int)nblk;
     if (gx > FOHO_MAX_STREAM_CTAS) gx = FOHO_MAX_STREAM_CTAS;
     if (gx < 1) gx = 1;
-    k_stream_any<<<dim3(gx, B), 256, 0, st>>>(d->sdf, d->grad_sdf, src, ws.stream_part, D, cN);
+    if (((reinterpret_cast<uintptr_t>(d->sdf) | reinterpret_cast<uintptr_t>(d->grad_sdf)) & 3) == 0 &&
+        (reinterpret_cast<uintptr_t>(d->sdf) & 15) == (reinterpret_cast<uintptr_t>(d->grad_sdf) & 15) && D >= 4) {
+      const unsigned long long magic = ((1ull << 40) + (unsigned long long)D - 1) / (unsigned long long)D;
+      k_stream_any4<<<dim3(gx, B), 256, 0, st>>>(d->sdf, d->grad_sdf, src, ws.stream_part, D, cN, magic);
+    } else {
+      k_stream_any<<<dim3(gx, B), 256, 0, st>>>(d->sdf, d->grad_sdf, src, ws.stream_part, D, cN);
+    }
   }
   FOHO_LAUNCH_CHECK();
   *grid_x_out = gx;

@@ -72,7 +72,7 @@ class HunyuanGuidanceModel:
         """:1269-1291: DiT on ``[latents] * 2``, classifier-free guidance with the scale decaying after
         ``guidance_start_step`` (``scale * (1 - i / N)`` for ``i >= guidance_start_step + 1``)."""
         cfg, pipe = self.cfg, self.pipe
-        t = pipe.scheduler.timesteps[step]
+        t = pipe.scheduler.timesteps[step].to(x_t.device)
         scale = cfg.obj_guidance_scale
         if step >= cfg.guidance_start_step + 1:
             scale = cfg.obj_guidance_scale * (1 - step / cfg.num_inference_steps)

@@ -128,8 +128,8 @@ def test_rendered_hand_terms_reach_the_leaves_like_autograd():
     from followmyhold_b200.synthetic import make_guidance_sample, stack_samples
     from oracle import guidance_oracle as O
     from oracle import raster_oracle as RO
-    B, D, P, H, W = 2, 32, 512, 96, 96
-    fovs = [41.0, 47.0]
+    B, D, P, H, W = 2, 32, 512, 128, 128
+    fovs = [20.0, 24.0]                      # narrow: the 0.1-unit hand at 1.5 units covers a few hundred pixels
     samples = [make_guidance_sample(D, P, 30 + i) for i in range(B)]
     sdf, theta, st = stack_samples(samples, cap=True)
     raw_faces = samples[0].hand_faces.to(torch.int64)
