@@ -258,6 +258,9 @@ k_attn_fwd(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUte
 // store chain of a tile cannot hide its own latencies and the tensor core idles for two thirds of the time (384
 // TFLOP/s); a second softmax warpgroup on a second tile fills those slots.  One S buffer per tile (TMEM: S_A | S_B |
 // O_A | O_B), registers moved from the producer / MMA warps to the softmax warps with setmaxnreg.
+// Measured and dropped (profiles/r02_tc_attention_probe.json history in DESIGN.md section 8): packed-half exponentials
+// (ex2.approx.f16x2 compiles to two MUFU.EX2.F16 + PRMT: 205 TFLOP/s), and row sums on the tensor core (P V made 80 wide
+// with a tile of ones) with the max pass folded into the exponential loop (545 vs 614 TFLOP/s).
 //   warp 0 TMA, warp 1 MMA, warp 2 TMEM alloc, warps 4-7 softmax of tile A, warps 8-11 softmax of tile B
 //   MMA order per key block j:  S_A(j+1), S_B(j+1) (as soon as the groups hold block j in registers), then
 //   [P_A(j) ready -> O_A += P_A V_j]  [P_B(j) ready -> O_B += P_B V_j]
@@ -387,7 +390,7 @@ k_attn_fwd2(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUt
     const uint32_t lane_off = (uint32_t)(q * 32) << 16;
     const uint32_t s_addr = tmem_base + T2_S + grp * 128 + lane_off;
     const uint32_t o_addr = tmem_base + T2_O + grp * 64 + lane_off;
-    uint8_t *pb = sP + grp * P_BYTES + row * 128;
+    const uint32_t pb_s = tc::smem_u32(sP + grp * P_BYTES + row * 128);
     uint32_t g = 0, w = 0;
     for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++w) {
       const int img = item / items_per_img, r = item - img * items_per_img;
@@ -447,7 +450,9 @@ k_attn_fwd2(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUt
             const __half2 hh = __floats2half2_rn(a, b);
             pk[t] = *reinterpret_cast<const uint32_t *>(&hh);
           }
-          *reinterpret_cast<uint4 *>(pb + (cc >> 3) * (AQ * 128) + (((cc & 7) ^ (row & 7)) << 4)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(pb_s + (cc >> 3) * (AQ * 128) + (((cc & 7) ^ (row & 7)) << 4)),
+                       "r"(pk[0]), "r"(pk[1]), "r"(pk[2]), "r"(pk[3])
+                       : "memory");
         }
         l = l * corr + (sum0 + sum1);
         tc::fence_proxy_async_smem();
@@ -489,6 +494,7 @@ k_attn_fwd2(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUt
   }
 }
 
+
 }  // namespace
 
 extern "C" int foho_tc_attention(const foho_attn_desc *d, void *cuda_stream) {
@@ -527,10 +533,10 @@ extern "C" int foho_tc_attention(const foho_attn_desc *d, void *cuda_stream) {
     if (d->max_ctas > 0 && grid > d->max_ctas) grid = d->max_ctas;
     k_attn_fwd<<<grid, 256, ATT_SMEM, st>>>(tmQ, tmK, tmV, p);
   } else {
-    FOHO_CUDA_TRY(cudaFuncSetAttribute(k_attn_fwd2, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT2_SMEM));
     long long items = (long long)p.n_img * p.heads * ((p.q_tiles + 1) / 2);
     int grid = (int)(items < sm_count ? items : sm_count);
     if (d->max_ctas > 0 && grid > d->max_ctas) grid = d->max_ctas;
+    FOHO_CUDA_TRY(cudaFuncSetAttribute(k_attn_fwd2, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT2_SMEM));
     k_attn_fwd2<<<grid, 384, ATT2_SMEM, st>>>(tmQ, tmK, tmV, p);
   }
   FOHO_LAUNCH_CHECK();

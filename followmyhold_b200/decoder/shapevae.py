@@ -311,6 +311,56 @@ class LatentDecoder:
         self._fwd_done = True
         return out
 
+    # ------------------------------------------------------------------ export lattice (forward only, query side on the fly)
+    def decode_lattice(self, latents: torch.Tensor, D: int, bound: float = 1.10, chunk: int = 0, stream=None) -> torch.Tensor:
+        """``latent2sdf`` on ANOTHER lattice than the resident one -- the reference's final export re-grids to 385^3
+        (pipelines.py:1624-1641; 57 M queries: their latent-independent query side would take 233 GB, so it is
+        computed chunk by chunk here instead of once).  Runs the token side, then streams the lattice; returns
+        float32 [B, D, D, D], negative inside.  Forward only."""
+        w, ops, B = self.w, self.ops, self.B
+        xw = w.x
+        R = B * TOKENS
+        if self.x0 is None:
+            raise RuntimeError("set_queries() first (any lattice): the token side shares its buffers")
+        saved = (self.Nq, self.x0, self.qn, self.q_lse)
+        try:
+            # token side exactly as in forward(): reuse it by decoding zero queries of the resident lattice
+            self.Nq = 0
+            self.forward(latents, out=torch.empty(B, 0, dtype=torch.float32, device=self.dev), stream=stream)
+        finally:
+            self.Nq, self.x0, self.qn, self.q_lse = saved
+        kv = self.kv.view(R, HEADS, 2 * HD)
+        qc = int(chunk) or self.query_chunk
+        qc = min(qc, self.query_chunk)
+        f16 = dict(dtype=torch.float16, device=self.dev)
+        axis = torch.linspace(-bound, bound, D, device=self.dev)
+        out = torch.empty(B, D * D * D, dtype=torch.float32, device=self.dev)
+        emb = torch.empty(qc, w.embed_ld, **f16)
+        x0 = torch.empty(qc, WIDTH, **f16)
+        t1 = torch.empty(qc, WIDTH, **f16)
+        t2 = torch.empty(qc, WIDTH, **f16)
+        qn = torch.empty(qc, HEADS, HD, **f16)
+        N = D * D * D
+        for s in range(0, N, qc):
+            n = min(qc, N - s)
+            idx = torch.arange(s, s + n, device=self.dev)                       # lattice points of this chunk, `ij` order, z fastest
+            xyz = torch.stack([axis[idx // (D * D)], axis[(idx // D) % D], axis[idx % D]], -1).contiguous()
+            ops.fourier(xyz, emb[:n], w.num_freqs, w.include_pi, stream=stream)
+            tc.gemm(emb[:n], w.query_proj_w, out=x0[:n], bias=w.query_proj_b, stream=stream)
+            ops.layernorm(x0[:n], xw["ln1_w"], xw["ln1_b"], t1[:n], stream=stream)
+            tc.gemm(t1[:n], xw["q_w"], out=t2[:n], bias=xw["q_b"], stream=stream)
+            ops.layernorm(t2[:n].view(n, HEADS, HD), xw["qn_w"], xw["qn_b"], qn[:n], width=HD, stream=stream)
+            att = self.q_attn[:, :n]
+            tc.attention(qn[:n], self.kvn, kv[:, :, HD:], B, out=att, q_shared=True, stream=stream)
+            xq = tc.gemm(att, xw["proj_w"], out=self.q_x[:, :n], bias=xw["proj_b"], res=x0[:n].unsqueeze(0).expand(B, n, WIDTH), stream=stream)
+            for b in range(B):
+                ops.layernorm(xq[b], xw["ln3_w"], xw["ln3_b"], self.q_h[b, :n], stream=stream)
+            tc.gemm(self.q_h[:, :n], xw["fc_w"], out=self.q_u[:, :n], bias=xw["fc_b"], act=tc.ACT_GELU, stream=stream)
+            tc.gemm(self.q_u[:, :n], xw["fc2_w"], out=self.q_y[:, :n], bias=xw["fc2_b"], res=xq, stream=stream)
+            for b in range(B):
+                ops.head(self.q_y[b, :n], w.ln_post_w, w.ln_post_b, w.out_w, w.out_b, out[b, s:s + n], stream=stream)
+        return out.view(B, D, D, D)
+
     # ------------------------------------------------------------------ adjoint
     def backward(self, idx: torch.Tensor, g_sdf: torch.Tensor, out: Optional[torch.Tensor] = None, stream=None,
                  out_scale: float = 1.0) -> torch.Tensor:

@@ -228,3 +228,19 @@ def test_schedule_with_the_tc_decoder_runs_all_phases():
     assert torch.isfinite(loop.x_t).all() and torch.isfinite(loop.theta).all() and torch.isfinite(loop.terms).all()
     assert not torch.equal(loop.theta, theta0) and not torch.equal(loop.x_t, x0)
     assert loop.nan_report() == {}
+
+
+def test_export_lattice_decode_streams_the_query_side(small):
+    """The final export re-grids to another lattice (pipelines.py:1624-1641): ``decode_lattice`` computes the query side
+    chunk by chunk instead of keeping it resident.  Same lattice -> the very same numbers; another lattice -> the oracle."""
+    s = small
+    D, B = s["D"], s["B"]
+    a = s["dec"].forward(s["lat"]).clone()
+    b = s["dec"].decode_lattice(s["lat"], D, chunk=512)
+    torch.cuda.synchronize()
+    assert b.shape == (B, D, D, D) and torch.equal(a.view(B, D, D, D), b)
+    assert torch.equal(s["dec"].forward(s["lat"]), a)                     # the resident lattice is untouched
+    D2 = 9
+    c = s["dec"].decode_lattice(s["lat"], D2)
+    ref = torch.stack([s["DO"].latent2sdf(s["lat"][i:i + 1], _lattice(D2).cuda(), (D2, D2, D2), s["vae"]).reshape(D2, D2, D2) for i in range(B)])
+    assert (c - ref).abs().max().item() <= TOL * ref.abs().max().item()
