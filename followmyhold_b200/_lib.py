@@ -17,7 +17,7 @@ REPO_ROOT = PKG_DIR.parent
 CSRC = PKG_DIR / "csrc"
 LIB_PATH = PKG_DIR / "libfoho_b200.so"
 SOURCES = ["guidance_stream.cu", "guidance_sparse.cu", "guidance_objmesh.cu", "guidance_chamfer.cu", "guidance_voxdist.cu", "guidance_update.cu", "icp.cu",
-           "mesh_sdf.cu", "mesh_decimate.cu", "decoder_gemm.cu", "decoder_attn.cu", "decoder_ops.cu", "guidance_raster.cu"]
+           "mesh_sdf.cu", "mesh_decimate.cu", "decoder_gemm.cu", "decoder_attn.cu", "decoder_ops.cu", "guidance_raster.cu", "guidance_dmc.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "-Xcompiler", "-fPIC", "-Xcompiler", "-O3"]
 
@@ -40,6 +40,7 @@ EXPORTED_SYMBOLS = [
     "foho_dec_head", "foho_dec_head_bwd", "foho_dec_gather_rows", "foho_dec_cast",
     "foho_dec_rowdot", "foho_dec_gather_f32", "foho_dec_compact_workspace_bytes", "foho_dec_compact_grad",
     "foho_raster_workspace_bytes", "foho_raster_losses_fwd_bwd",
+    "foho_dmc_workspace_bytes", "foho_dmc_extract", "foho_dmc_backward",
 ]
 
 
@@ -173,6 +174,16 @@ class RasterDesc(C.Structure):
     ]
 
 
+class DmcDesc(C.Structure):
+    _fields_ = [
+        ("B", C.c_int32), ("D", C.c_int32), ("bound", C.c_float), ("cap_verts", C.c_int32), ("cap_faces", C.c_int32),
+        ("cap_edges", C.c_int32), ("index_base", C.c_int32), ("reserved", C.c_int32),
+        ("sdf", C.c_void_p), ("verts", C.c_void_p), ("faces", C.c_void_p), ("edges", C.c_void_p),
+        ("vert_offsets", C.c_void_p), ("face_offsets", C.c_void_p), ("edge_offsets", C.c_void_p),
+        ("cube_of_vert", C.c_void_p), ("flags", C.c_void_p), ("workspace", C.c_void_p), ("workspace_bytes", C.c_size_t),
+    ]
+
+
 _lib: Optional[C.CDLL] = None
 
 
@@ -254,6 +265,12 @@ def load(build_if_missing: bool = False) -> C.CDLL:
     lib.foho_dec_head_bwd.argtypes = [vp, i64, vp, f32, vp, vp, vp, f32, vp, i64, i64, vp]
     lib.foho_dec_gather_rows.argtypes = [vp, i64, vp, vp, i64, i64, i32, vp]
     lib.foho_dec_cast.argtypes = [vp, i64, vp, i64, i64, i32, f32, i32, vp]
+    lib.foho_dmc_workspace_bytes.argtypes = [i32, i32]
+    lib.foho_dmc_workspace_bytes.restype = C.c_size_t
+    lib.foho_dmc_extract.argtypes = [C.POINTER(DmcDesc), vp]
+    lib.foho_dmc_extract.restype = C.c_int
+    lib.foho_dmc_backward.argtypes = [C.POINTER(DmcDesc), vp, vp, vp]
+    lib.foho_dmc_backward.restype = C.c_int
     lib.foho_raster_workspace_bytes.argtypes = [C.POINTER(RasterDesc)]
     lib.foho_raster_workspace_bytes.restype = C.c_size_t
     lib.foho_raster_losses_fwd_bwd.argtypes = [C.POINTER(RasterDesc), vp]

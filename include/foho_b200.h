@@ -426,6 +426,36 @@ typedef struct foho_raster_desc {
 size_t foho_raster_workspace_bytes(const foho_raster_desc *desc);
 int foho_raster_losses_fwd_bwd(const foho_raster_desc *desc, void *cuda_stream);
 
+/* ---------------------------------------------------------------------------------------------
+ * Row f2, second part: surface extraction from the decoded volume and its backward -- where the reference calls kaolin's
+ * FlexiCubes without weights (third_party_patches/hy3dgen/shapegen/pipelines.py:1142-1143,1393,1509,1642).  NOT a
+ * restatement of FlexiCubes (its tables are not reproducible offline): Dual Marching Cubes as defined in
+ * oracle/surface_oracle.py -- one dual vertex per sign-changing cube at the mean of its edge zero crossings, one quad per
+ * interior sign-changing lattice edge, wound inside -> outside, split along (0, 2).  Meshes of the B images come out
+ * packed: image b owns vertices [vert_offsets[b], vert_offsets[b+1]), triangles [face_offsets[b], ..) and unique edges
+ * [edge_offsets[b], ..); counts stay on the device.  Orders are deterministic.  *flags: bit0 vertex capacity, bit1 face
+ * capacity, bit2 edge capacity exceeded (the mesh is then truncated).
+ * --------------------------------------------------------------------------------------------- */
+typedef struct foho_dmc_desc {
+  int32_t B, D;                /* volumes [B,D,D,D], negative inside, lattice linspace(-bound, bound, D)          */
+  float bound;                 /* 1.10                                                                           */
+  int32_t cap_verts, cap_faces, cap_edges;   /* capacities of the packed outputs (totals over the batch)         */
+  int32_t index_base;          /* added to every vertex index written to `faces` (the renderer's joint vertex array) */
+  int32_t reserved;
+  const float *sdf;            /* device [B,D,D,D]                                                               */
+  float *verts;                /* device [cap_verts,3] OUT, Hunyuan space                                        */
+  int32_t *faces;              /* device [cap_faces,3] OUT                                                       */
+  int32_t *edges;              /* device [cap_edges,2] OUT packed vertex indices (no base), or NULL              */
+  int32_t *vert_offsets, *face_offsets, *edge_offsets;   /* device [B+1] OUT                                     */
+  int32_t *cube_of_vert;       /* device [cap_verts] OUT: lattice cube of each vertex (needed by the backward)   */
+  int32_t *flags;              /* device [1], OR-accumulated                                                     */
+  void *workspace; size_t workspace_bytes;   /* >= foho_dmc_workspace_bytes(B, D), 256-byte aligned; shared by both calls */
+} foho_dmc_desc;
+size_t foho_dmc_workspace_bytes(int32_t B, int32_t D);
+int foho_dmc_extract(const foho_dmc_desc *desc, void *cuda_stream);
+/* grad_sdf [B,D,D,D] += d(verts)/d(sdf)^T grad_verts (of the extraction this descriptor last produced) */
+int foho_dmc_backward(const foho_dmc_desc *desc, const float *grad_verts, float *grad_sdf, void *cuda_stream);
+
 #ifdef __cplusplus
 }
 #endif
