@@ -120,7 +120,7 @@ class GuidanceDesc(C.Structure):
         ("grad_obj_verts", C.c_void_p), ("workspace", C.c_void_p), ("workspace_bytes", C.c_size_t),
         ("accel", C.c_void_p), ("accel_bytes", C.c_size_t),
         ("hand_nbr_off", C.c_void_p), ("hand_nbr", C.c_void_p), ("nbr_stride", C.c_int32), ("reserved1", C.c_int32),
-        ("trace", C.c_void_p), ("sticky_flags", C.c_void_p),
+        ("trace", C.c_void_p), ("sticky_flags", C.c_void_p), ("obj_moge", C.c_void_p), ("grad_obj_ext", C.c_void_p),
     ]
 
 
@@ -165,7 +165,9 @@ class AttnDesc(C.Structure):
 class RasterDesc(C.Structure):
     _fields_ = [
         ("B", C.c_int32), ("V_total", C.c_int32), ("F_total", C.c_int32), ("H", C.c_int32), ("W", C.c_int32),
-        ("tile_cap", C.c_int32), ("w_normal", C.c_float), ("w_disp", C.c_float), ("w_sil", C.c_float), ("reserved", C.c_int32),
+        ("tile_cap", C.c_int32), ("w_normal", C.c_float), ("w_disp", C.c_float), ("w_sil", C.c_float), ("accumulate_grad", C.c_int32),
+        ("V1", C.c_int32), ("F1", C.c_int32), ("skip_set1", C.c_int32), ("reserved", C.c_int32),
+        ("vert_offsets2", C.c_void_p), ("face_offsets2", C.c_void_p),
         ("verts", C.c_void_p), ("faces", C.c_void_p), ("vert_offsets", C.c_void_p), ("face_offsets", C.c_void_p),
         ("fov_deg", C.c_void_p), ("gt_normals", C.c_void_p), ("gt_mask", C.c_void_p), ("n_valid", C.c_void_p),
         ("gt_disp", C.c_void_p), ("gt_sil", C.c_void_p), ("losses", C.c_void_p), ("grad_verts", C.c_void_p),

@@ -108,6 +108,10 @@ __global__ void __launch_bounds__(OBJ_PREP_THREADS) k_obj_prep(foho_guidance_des
     float *o = ws.ot + 3 * (size_t)j, *g = ws.g_ot + 3 * (size_t)j;
     o[0] = r.x + off.x; o[1] = r.y + off.y; o[2] = r.z + off.z;
     g[0] = 0.f; g[1] = 0.f; g[2] = 0.f;
+    if (d.obj_moge) {                        // absolute MoGe coordinates for the renderer
+      float *om = d.obj_moge + 3 * (size_t)j;
+      om[0] = o[0] + fr.co[0]; om[1] = o[1] + fr.co[1]; om[2] = o[2] + fr.co[2];
+    }
   }
   for (int i = tid; i < d.Vh; i += blockDim.x) ws.knn_obj[(size_t)b * d.Vh + i] = ~0ull;
 }
@@ -231,7 +235,11 @@ __global__ void __launch_bounds__(OBJ_PREP_THREADS) k_obj_chain(foho_guidance_de
 #pragma unroll
   for (int k = 0; k < 12; ++k) acc[k] = 0.f;
   for (int j = info.v0 + tid; j < info.v1; j += blockDim.x) {
-    const float *g = ws.g_ot + 3 * (size_t)j;
+    float *g = ws.g_ot + 3 * (size_t)j;
+    if (d.grad_obj_ext) {                    // renderer terms join here: dE/d(ot) += dE_ext/d(ot)
+      const float *ge = d.grad_obj_ext + 3 * (size_t)j;
+      g[0] += ge[0]; g[1] += ge[1]; g[2] += ge[2];
+    }
     const foho_f3 w = obj_to_moge(fr.Ah, T, d.obj_verts + 3 * (size_t)j) - c;
     acc[0] += g[0]; acc[1] += g[1]; acc[2] += g[2];
     acc[3] += g[0] * w.x; acc[4] += g[0] * w.y; acc[5] += g[0] * w.z;

@@ -72,6 +72,24 @@ __device__ __forceinline__ int image_of(const int *offsets, int B, int i) {     
   return lo;
 }
 
+// Two vertex / face sets per image: set 1 = the first V1 vertices / F1 faces with static per-image ranges (the hand),
+// set 2 = what follows, with per-image ranges whose counts live on the device (the extracted object mesh: dynamic shapes
+// without a host sync -- launches are capacity sized, threads beyond the count leave).  Without set 2 everything is set 1.
+__device__ __forceinline__ int vert_image(const foho_raster_desc &d, int i, bool *valid) {
+  const int V1 = d.vert_offsets2 ? d.V1 : d.V_total;
+  if (i < V1) { *valid = true; return image_of(d.vert_offsets, d.B, i); }
+  const int j = i - V1;
+  *valid = j < d.vert_offsets2[d.B];
+  return *valid ? image_of(d.vert_offsets2, d.B, j) : 0;
+}
+__device__ __forceinline__ int face_image(const foho_raster_desc &d, int f, bool *valid) {
+  const int F1 = d.face_offsets2 ? d.F1 : d.F_total;
+  if (f < F1) { *valid = !d.skip_set1; return image_of(d.face_offsets, d.B, f); }
+  const int j = f - F1;
+  *valid = j < d.face_offsets2[d.B];
+  return *valid ? image_of(d.face_offsets2, d.B, j) : 0;
+}
+
 // ---------------------------------------------------------------- geometry
 __global__ void k_rs_verts(foho_raster_desc d, RsWork w) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -84,18 +102,23 @@ __global__ void k_rs_verts(foho_raster_desc d, RsWork w) {
   }
   if (i < d.B * w.tiles_x * w.tiles_y) w.tile_cnt[i] = 0;
   if (i >= d.V_total) return;
-  const int b = image_of(d.vert_offsets, d.B, i);
+#pragma unroll
+  for (int a = 0; a < 3; ++a) { w.nacc[3 * i + a] = 0; w.gn[3 * i + a] = 0; w.gp[3 * i + a] = 0; }
+  bool valid;
+  const int b = vert_image(d, i, &valid);
+  if (!valid) { w.ndc[3 * i] = 0.f; w.ndc[3 * i + 1] = 0.f; w.ndc[3 * i + 2] = -1.f; return; }
   const float t = tanf(d.fov_deg[b] * 0.00872664625997164788f);       // tan(fov / 2)
   // view = X R + T with R = diag(-1, 1, -1), T = 0 (guidance/run.py:84-90)
   const float xv = -d.verts[3 * i], yv = d.verts[3 * i + 1], zv = -d.verts[3 * i + 2];
   w.ndc[3 * i] = xv / (zv * t); w.ndc[3 * i + 1] = yv / (zv * t); w.ndc[3 * i + 2] = zv;
-#pragma unroll
-  for (int a = 0; a < 3; ++a) { w.nacc[3 * i + a] = 0; w.gn[3 * i + a] = 0; w.gp[3 * i + a] = 0; }
 }
 
 __global__ void k_rs_facenrm(foho_raster_desc d, RsWork w) {
   const int f = blockIdx.x * blockDim.x + threadIdx.x;
   if (f >= d.F_total) return;
+  bool valid;
+  face_image(d, f, &valid);
+  if (!valid) return;
   const int i0 = d.faces[3 * f], i1 = d.faces[3 * f + 1], i2 = d.faces[3 * f + 2];
   const float *v = d.verts;
   const float ax = v[3 * i1] - v[3 * i0], ay = v[3 * i1 + 1] - v[3 * i0 + 1], az = v[3 * i1 + 2] - v[3 * i0 + 2];
@@ -118,7 +141,9 @@ __global__ void k_rs_vertnrm(foho_raster_desc d, RsWork w) {
 __global__ void k_rs_bin(foho_raster_desc d, RsWork w) {
   const int f = blockIdx.x * blockDim.x + threadIdx.x;
   if (f >= d.F_total) return;
-  const int b = image_of(d.face_offsets, d.B, f);
+  bool valid;
+  const int b = face_image(d, f, &valid);
+  if (!valid) return;
   const int i0 = d.faces[3 * f], i1 = d.faces[3 * f + 1], i2 = d.faces[3 * f + 2];
   const float x0 = w.ndc[3 * i0], y0 = w.ndc[3 * i0 + 1], z0 = w.ndc[3 * i0 + 2];
   const float x1 = w.ndc[3 * i1], y1 = w.ndc[3 * i1 + 1], z1 = w.ndc[3 * i1 + 2];
@@ -410,6 +435,9 @@ __global__ void k_rs_bwd_vnrm(foho_raster_desc d, RsWork w) {
 __global__ void k_rs_bwd_face(foho_raster_desc d, RsWork w) {
   const int f = blockIdx.x * blockDim.x + threadIdx.x;
   if (f >= d.F_total) return;
+  bool valid;
+  face_image(d, f, &valid);
+  if (!valid) return;
   const int i0 = d.faces[3 * f], i1 = d.faces[3 * f + 1], i2 = d.faces[3 * f + 2];
   const float gc[3] = {w.gs[3 * i0] + w.gs[3 * i1] + w.gs[3 * i2], w.gs[3 * i0 + 1] + w.gs[3 * i1 + 1] + w.gs[3 * i2 + 1],
                        w.gs[3 * i0 + 2] + w.gs[3 * i1 + 2] + w.gs[3 * i2 + 2]};
@@ -437,7 +465,10 @@ __global__ void k_rs_final(foho_raster_desc d, RsWork w) {
   }
   if (i < d.V_total && d.grad_verts)
 #pragma unroll
-    for (int a = 0; a < 3; ++a) d.grad_verts[3 * i + a] = (float)((double)w.gp[3 * i + a] / FX_G);
+    for (int a = 0; a < 3; ++a) {
+      const float g = (float)((double)w.gp[3 * i + a] / FX_G);
+      d.grad_verts[3 * i + a] = d.accumulate_grad ? d.grad_verts[3 * i + a] + g : g;
+    }
 }
 
 size_t align_up(size_t x) { return (x + 255) & ~size_t(255); }
@@ -469,6 +500,8 @@ extern "C" size_t foho_raster_workspace_bytes(const foho_raster_desc *d) {
 extern "C" int foho_raster_losses_fwd_bwd(const foho_raster_desc *dp, void *cuda_stream) {
   if (!dp) return FOHO_E_NULL;
   const foho_raster_desc &d = *dp;
+  if ((d.vert_offsets2 == nullptr) != (d.face_offsets2 == nullptr)) return FOHO_E_ARG;
+  if (d.vert_offsets2 && (d.V1 < 0 || d.V1 > d.V_total || d.F1 < 0 || d.F1 > d.F_total)) return FOHO_E_SHAPE;
   if (!d.verts || !d.faces || !d.vert_offsets || !d.face_offsets || !d.fov_deg || !d.gt_normals || !d.gt_mask || !d.gt_disp || !d.gt_sil ||
       !d.n_valid || !d.losses || !d.workspace)
     return FOHO_E_NULL;

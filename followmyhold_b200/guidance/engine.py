@@ -193,7 +193,8 @@ class GuidanceEngine:
     def make_desc(self, sdf: torch.Tensor, theta: torch.Tensor, st: GuidanceStatics,
                   grad_sdf: Optional[torch.Tensor] = None, late_step: bool = False,
                   grad_hand_ext: Optional[torch.Tensor] = None,
-                  obj_mesh: Optional[ObjectMeshBatch] = None) -> _lib.GuidanceDesc:
+                  obj_mesh: Optional[ObjectMeshBatch] = None, obj_moge: Optional[torch.Tensor] = None,
+                  grad_obj_ext: Optional[torch.Tensor] = None) -> _lib.GuidanceDesc:
         B, D, Vh, Fh, P = self.B, self.D, self.Vh, self.Fh, self.P
         f32 = torch.float32
         _chk(sdf, (B, D, D, D), f32, "sdf")
@@ -248,6 +249,12 @@ class GuidanceEngine:
             d.obj_edges = obj_mesh.edges.data_ptr() if Eo > 0 else None
             d.obj_edge_offsets = obj_mesh.edge_offsets.data_ptr()
             d.grad_obj_verts = self.grad_obj_verts.data_ptr()
+            if obj_moge is not None:
+                _chk(obj_moge, (Vo, 3), f32, "obj_moge")
+                d.obj_moge = obj_moge.data_ptr()
+            if grad_obj_ext is not None:
+                _chk(grad_obj_ext, (Vo, 3), f32, "grad_obj_ext")
+                d.grad_obj_ext = grad_obj_ext.data_ptr()
         d.workspace, d.workspace_bytes = self._ws_ptr, self._ws_bytes
         if getattr(self, "sticky_flags", None) is None or self.sticky_flags.shape[0] != B:
             self.sticky_flags = torch.zeros(B, dtype=torch.int32, device=self.device)

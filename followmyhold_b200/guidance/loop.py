@@ -19,6 +19,7 @@ from __future__ import annotations
 
 import ctypes as C
 import time
+import types
 from typing import Dict, Optional
 
 import torch
@@ -58,7 +59,7 @@ class GuidanceLoop:
     def __init__(self, B: int, D: int, statics: GuidanceStatics, P: int, device="cuda:0",
                  config: Optional[OptimizationConfig] = None, weights=None, latent_elems: int = LATENT_SHAPE[0] * LATENT_SHAPE[1],
                  decoder_alpha: float = 0.05, stream_variant: int = 0, seed: int = 0, micro_batches: int = 1,
-                 loss_log_every: int = 0, mock_decoder: bool = True):
+                 loss_log_every: int = 0, mock_decoder: bool = True, max_obj_verts: int = 0):
         """``loss_log_every`` = n > 0 keeps the loss terms of every n-th inner iteration of every step
         (``loss_history``; the reference logs every 10th when ``FOHO_DEBUG_DIR`` is set, pipelines.py:1446-1450,
         1594-1598) -- device-to-device copies inside the step graph, no host sync.
@@ -83,7 +84,8 @@ class GuidanceLoop:
         self.lanes = []
         for j in range(m):
             st_j = statics if m == 1 else slice_statics(statics, j * nb, nb)
-            eng = GuidanceEngine(nb, D, Vh, Fh, P, device=device, weights=weights, stream_variant=stream_variant)
+            eng = GuidanceEngine(nb, D, Vh, Fh, P, device=device, weights=weights, stream_variant=stream_variant,
+                                 max_obj_verts=max_obj_verts)
             eng.lane = j
             if m > 1:
                 # the lanes' stream kernels share the SMs most of the time: 3 bulk loads in flight per CTA
@@ -216,22 +218,109 @@ class GuidanceLoop:
             ln.render_fo = torch.arange(0, (nb + 1) * faces.shape[0], faces.shape[0], dtype=torch.int32, device=self.device)
         self.image_terms = torch.zeros(self.B, 8, dtype=torch.float32, device=self.device)
 
-    def _hand_image_grad(self, ln: _Lane, phase: float, s: torch.cuda.Stream, weights=None) -> Optional[torch.Tensor]:
-        """Enqueue prep (-> transformed hand) + renderer; returns dE_img/d(transformed hand verts) [nb,Vh,3] or None."""
+    def _hand_image_grad(self, ln: _Lane, phase: float, s: torch.cuda.Stream, weights=None, grad_out=None, prep: bool = True):
+        """Enqueue prep (-> transformed hand) + renderer; returns dE_img/d(transformed hand verts) [nb,Vh,3] or None.
+        ``grad_out`` [>= nb*Vh, 3]: accumulate into it instead (the joined render has already written there)."""
         r = getattr(ln, "renderer", None)
         if r is None or phase == 1.5:                        # the object-only step does not move the hand (:1361-1453)
             return None
         w_hand = float((weights or self.phase_weights(phase)).w_hand)
         r.w = (1.0 * w_hand, 10.0 * w_hand, 1.0 * w_hand) if phase == 1 else (10.0 * w_hand, 10.0 * w_hand, 0.0)
         theta = self.theta.narrow(0, ln.off, ln.nb)
-        desc = ln.engine.make_desc(self.sdf.narrow(0, ln.off, ln.nb), theta, ln.statics)
-        desc.stage_mask = 1                                  # prep only: leaves -> transformed hand vertices
-        ln.engine.launch(desc, s)
+        if prep:
+            desc = ln.engine.make_desc(self.sdf.narrow(0, ln.off, ln.nb), theta, ln.statics)
+            desc.stage_mask = 1                              # prep only: leaves -> transformed hand vertices
+            ln.engine.launch(desc, s)
         Vh = ln.statics.hand_rest.shape[1]
-        losses, g = r(ln.engine.hand_moge.view(-1, 3), ln.render_faces, ln.render_vo, ln.render_fo, stream=s)
+        losses, g = r(ln.engine.hand_moge.view(-1, 3), ln.render_faces, ln.render_vo, ln.render_fo, stream=s,
+                      accumulate=grad_out is not None, grad_out=grad_out)
         with torch.cuda.stream(s):
             self.image_terms.narrow(0, ln.off, ln.nb).copy_(losses)
-        return g.view(ln.nb, Vh, 3)
+        return g[:ln.nb * Vh].view(ln.nb, Vh, 3)
+
+    # ------------------------------------------------------------------ extracted object mesh: REF mesh terms + joined renders
+    def enable_object_terms(self, hoi_targets=None, obj_targets=None, cap_verts: int = 0, tile_cap: int = 1024) -> None:
+        """Put the extracted object surface into ``run_schedule_tc_decoder`` (one lane): every inner iteration of the
+        object-only and joint phases extracts the mesh from the decoded volume (``foho_dmc_extract``, where the
+        reference calls FlexiCubes, pipelines.py:1393,1509), feeds it to the explicit-mesh terms a7 / a10
+        (``distance_loss``, ``obj_verts_loss``, ``mesh_edge_loss``, :1529-1541,1570-1576) and -- with targets -- to the
+        renderer: object alone in the object-only phase (``10 nrm + 10 disp + 100 sil``, :1413-1440), hand + object joined
+        in the joint phase (``10 nrm + 10 disp + 10 sil``, :1544-1569,1580-1583); all vertex gradients return through the
+        object similarity and T_h2m to the mesh, through the extraction to dE/dSDF, and on through the decoder adjoint.
+        Needs ``enable_image_terms`` first when targets are given (the hand renderer supplies the topology)."""
+        from .render import ImageLossRenderer
+        from .surface import SurfaceExtractor
+        if self.micro_batches != 1:
+            raise ValueError("object terms drive one lane")
+        ln = self.lanes[0]
+        B, D, Vh = self.B, self.D, self.statics.hand_rest.shape[1]
+        cap_v = int(cap_verts) or B * 6 * D * D
+        if ln.engine.max_obj_verts < cap_v:
+            raise ValueError(f"construct the loop with max_obj_verts >= {cap_v}")
+        V1 = B * Vh
+        rf = getattr(ln, "render_faces", None)
+        F1 = 0 if rf is None else int(rf.shape[0])
+        cap_f = 2 * cap_v + 64
+        o = types.SimpleNamespace()
+        o.V1, o.F1, o.cap_v, o.cap_f = V1, F1, cap_v, cap_f
+        o.joint_verts = torch.zeros(V1 + cap_v, 3, dtype=torch.float32, device=self.device)       # [hand (MoGe) | object (MoGe)]
+        o.joint_faces = torch.zeros(F1 + cap_f, 3, dtype=torch.int32, device=self.device)
+        if rf is not None:
+            o.joint_faces[:F1].copy_(rf)
+        o.G = torch.zeros(V1 + cap_v, 3, dtype=torch.float32, device=self.device)                 # dE_img/d(joint vertices)
+        o.ex = SurfaceExtractor(B, D, device=self.device, cap_verts=cap_v, cap_faces=cap_f, index_base=V1, faces_out=o.joint_faces[F1:])
+        ln.engine.hand_moge = o.joint_verts[:V1].view(B, Vh, 3)          # the engine writes the transformed hand in place
+        o.R_hoi = o.R_obj = None
+        if hoi_targets is not None or obj_targets is not None:
+            if rf is None:
+                raise ValueError("enable_image_terms() first")
+            H, W = ln.renderer.H, ln.renderer.W
+            for name, t in (("R_hoi", hoi_targets), ("R_obj", obj_targets)):
+                if t is not None:
+                    r = ImageLossRenderer(B, H, W, V1 + cap_v, F1 + cap_f, device=self.device, tile_cap=tile_cap)
+                    r.set_targets(t)
+                    setattr(o, name, r)
+        o.terms_hoi = torch.zeros(B, 8, dtype=torch.float32, device=self.device)
+        o.terms_obj = torch.zeros(B, 8, dtype=torch.float32, device=self.device)
+        self._obj = o
+
+    def _object_eval(self, ln: _Lane, phase: float, late: bool, w, s: torch.cuda.Stream):
+        """One evaluation with the extracted object mesh in it (called after the decode); leaves dE/dSDF complete in
+        ``engine.grad_sdf``."""
+        from .engine import ObjectMeshBatch
+        o, eng = self._obj, ln.engine
+        B, Vh = self.B, ln.statics.hand_rest.shape[1]
+        ex = o.ex
+        ex.extract(self.sdf, stream=s)
+        mesh = ObjectMeshBatch(ex.verts, ex.vert_offsets, ex.edges, ex.edge_offsets)
+        g_hand = g_obj = None
+        rend = o.R_hoi if phase == 2 else o.R_obj
+        if rend is not None:
+            d0 = eng.make_desc(self.sdf, self.theta, ln.statics, late_step=late, obj_mesh=mesh, obj_moge=o.joint_verts[o.V1:])
+            d0.w = w
+            d0.stage_mask = 1 | 32                                   # leaves -> transformed hand and object vertices
+            eng.launch(d0, s)
+            set2 = (o.V1, o.F1, ex.vert_offsets, ex.face_offsets)
+            if phase == 2:
+                rend.w = (10.0, 10.0, 10.0)                          # :1580-1583
+                losses, _ = rend(o.joint_verts, o.joint_faces, ln.render_vo, ln.render_fo, stream=s, set2=set2, grad_out=o.G)
+                with torch.cuda.stream(s):
+                    o.terms_hoi.copy_(losses)
+                self._hand_image_grad(ln, 2, s, w, grad_out=o.G, prep=False)      # + 1e-3 * (10 nrm_h + 10 disp_h), :1499-1504,1588
+                g_hand = o.G[:o.V1].view(B, Vh, 3)
+            else:
+                rend.w = (10.0, 10.0, 100.0)                         # :1433-1440
+                losses, _ = rend(o.joint_verts, o.joint_faces, ln.render_vo, ln.render_fo, stream=s, set2=set2, skip_set1=True,
+                                 grad_out=o.G)
+                with torch.cuda.stream(s):
+                    o.terms_obj.copy_(losses)
+            g_obj = o.G[o.V1:]
+        elif phase == 2:
+            g_hand = self._hand_image_grad(ln, 2, s, w)
+        desc = eng.make_desc(self.sdf, self.theta, ln.statics, late_step=late, grad_hand_ext=g_hand, obj_mesh=mesh, grad_obj_ext=g_obj)
+        desc.w = w
+        eng.launch(desc, s)
+        ex.backward(eng.grad_obj_verts, eng.grad_sdf, stream=s)      # mesh gradient -> dE/dSDF (accumulated)
 
     # ------------------------------------------------------------------ one evaluation (enqueue only)
     def _enqueue_eval(self, sigma: float, late_step: bool, s: torch.cuda.Stream, phase: float = 2, lane: Optional[_Lane] = None,
@@ -520,7 +609,7 @@ class GuidanceLoop:
                     if not keep_mom:
                         w.w_mom = 0.0
                     for k in range(self.phase_iterations(phase)):
-                        g_img = self._hand_image_grad(ln, phase, s, w)
+                        g_img = None if (phase != 1 and getattr(self, "_obj", None) is not None) else self._hand_image_grad(ln, phase, s, w)
                         if phase == 1:
                             desc = eng.make_desc(self.sdf, self.theta, ln.statics, late_step=late, grad_hand_ext=g_img)
                             desc.w = w
@@ -532,9 +621,14 @@ class GuidanceLoop:
                                 self.x_t.data_ptr(), self.velocity.data_ptr(), None, self.x1.data_ptr(), self.x_t.numel(),
                                 sigma, sigma_next, sp))                                   # step_final (:1507)
                             decoder.forward(self.x1.view(B, LATENT_SHAPE[0], LATENT_SHAPE[1]), out=self.sdf.view(B, V), stream=s)
-                            desc = eng.make_desc(self.sdf, self.theta, ln.statics, late_step=late, grad_hand_ext=g_img)
-                            desc.w = w
-                            eng.launch(desc, s)
+                            if getattr(self, "_obj", None) is not None:
+                                if phase == 1.5:
+                                    w.w_dist = 0.0                       # no hand -> object distance term in the object-only step (:1433-1440)
+                                self._object_eval(ln, phase, late, w, s)
+                            else:
+                                desc = eng.make_desc(self.sdf, self.theta, ln.statics, late_step=late, grad_hand_ext=g_img)
+                                desc.w = w
+                                eng.launch(desc, s)
                             idx, val = comp(eng.grad_sdf.view(B, V), stream=s)
                             decoder.backward(idx, val, out=self.grad_velocity.view(B, LATENT_SHAPE[0], LATENT_SHAPE[1]), stream=s,
                                              out_scale=1.0 - sigma)

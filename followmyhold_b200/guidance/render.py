@@ -58,9 +58,14 @@ class ImageLossRenderer:
         self._n_valid = self.targets.gt_mask.view(B, -1).sum(1, dtype=torch.int32).contiguous()
 
     def __call__(self, verts: torch.Tensor, faces: torch.Tensor, vert_offsets: torch.Tensor, face_offsets: torch.Tensor,
-                 backward: bool = True, debug: bool = False, stream: Optional[torch.cuda.Stream] = None):
+                 backward: bool = True, debug: bool = False, stream: Optional[torch.cuda.Stream] = None, set2=None,
+                 skip_set1: bool = False, accumulate: bool = False, grad_out: Optional[torch.Tensor] = None):
         """``verts`` [Vt,3] float32 packed world-space vertices, ``faces`` [Ft,3] int32 (packed indices),
-        ``*_offsets`` [B+1] int32.  Returns (losses [B,8], grad_verts [Vt,3] or None[, debug dict])."""
+        ``*_offsets`` [B+1] int32.  Returns (losses [B,8], grad_verts [Vt,3] or None[, debug dict]).
+
+        ``set2 = (V1, F1, vert_offsets2, face_offsets2)``: the arrays hold a second per-image set behind the first V1
+        vertices / F1 faces whose counts live on the device (the extracted object mesh); Vt / Ft are then capacities.
+        ``skip_set1`` draws set 2 alone; ``accumulate`` adds into ``grad_out`` (default: the renderer's own buffer)."""
         if self.targets is None:
             raise RuntimeError("set_targets() first")
         Vt, Ft = int(verts.shape[0]), int(faces.shape[0])
@@ -78,7 +83,14 @@ class ImageLossRenderer:
         d.fov_deg, d.gt_normals, d.gt_mask = T.fov_deg.data_ptr(), T.gt_normals.data_ptr(), T.gt_mask.data_ptr()
         d.n_valid, d.gt_disp, d.gt_sil = self._n_valid.data_ptr(), T.gt_disp.data_ptr(), T.gt_sil.data_ptr()
         d.losses = self.losses.data_ptr()
-        d.grad_verts = self.grad_verts.data_ptr() if backward else None
+        gbuf = self.grad_verts if grad_out is None else grad_out
+        if backward and (gbuf.dtype != torch.float32 or not gbuf.is_contiguous() or gbuf.shape[0] < Vt):
+            raise ValueError("grad_out must be a contiguous float32 [>= Vt, 3] tensor")
+        d.grad_verts = gbuf.data_ptr() if backward else None
+        d.accumulate_grad, d.skip_set1 = int(accumulate), int(skip_set1)
+        if set2 is not None:
+            d.V1, d.F1 = int(set2[0]), int(set2[1])
+            d.vert_offsets2, d.face_offsets2 = set2[2].data_ptr(), set2[3].data_ptr()
         dbg = None
         if debug:
             dbg = {"p2f": torch.empty(self.B, self.H, self.W, dtype=torch.int32, device=self.device),
@@ -88,7 +100,7 @@ class ImageLossRenderer:
         d.workspace, d.workspace_bytes = self._ws_ptr, self._ws_bytes
         s = stream if stream is not None else torch.cuda.current_stream(self.device)
         _lib.check("foho_raster_losses_fwd_bwd", self.lib.foho_raster_losses_fwd_bwd(C.byref(d), C.c_void_p(s.cuda_stream)))
-        out = (self.losses, self.grad_verts[:Vt] if backward else None)
+        out = (self.losses, gbuf[:Vt] if backward else None)
         return out + (dbg,) if debug else out
 
 

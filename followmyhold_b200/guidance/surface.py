@@ -13,7 +13,7 @@ from .. import _lib
 
 class SurfaceExtractor:
     def __init__(self, B: int, D: int, device="cuda:0", cap_verts: int = 0, cap_faces: int = 0, cap_edges: int = 0,
-                 bound: float = 1.10, index_base: int = 0, with_edges: bool = True):
+                 bound: float = 1.10, index_base: int = 0, with_edges: bool = True, faces_out: Optional[torch.Tensor] = None):
         self.lib = _lib.load()
         self.B, self.D, self.bound, self.index_base = B, D, float(bound), int(index_base)
         dev = self.device = torch.device(device)
@@ -23,7 +23,10 @@ class SurfaceExtractor:
         self.cap_edges = int(cap_edges) or 3 * self.cap_verts + 64
         i32 = dict(dtype=torch.int32, device=dev)
         self.verts = torch.zeros(self.cap_verts, 3, dtype=torch.float32, device=dev)
-        self.faces = torch.zeros(self.cap_faces, 3, **i32)
+        # ``faces_out``: write the triangles straight into the tail of a joint face array (hand faces in front)
+        self.faces = torch.zeros(self.cap_faces, 3, **i32) if faces_out is None else faces_out
+        if self.faces.shape != (self.cap_faces, 3) or self.faces.dtype != torch.int32 or not self.faces.is_contiguous():
+            raise ValueError("faces_out must be a contiguous int32 [cap_faces, 3] tensor")
         self.edges = torch.zeros(self.cap_edges, 2, **i32) if with_edges else None
         self.vert_offsets = torch.zeros(B + 1, **i32)
         self.face_offsets = torch.zeros(B + 1, **i32)

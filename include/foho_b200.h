@@ -153,6 +153,11 @@ typedef struct foho_guidance_desc {
   /* optional: device [B] int32, OR-accumulated with every evaluation's FOHO_T_FLAGS so that an overflow in ANY
    * evaluation of a captured graph is still visible afterwards (the host layer turns bit0 into a hard error) */
   int32_t *sticky_flags;
+  /* explicit object mesh, renderer hooks (row f2): the transformed object vertices leave in absolute MoGe coordinates so
+   * that the rasteriser can draw them, and an external gradient with respect to those vertices (the joined hand + object
+   * image terms, pipelines.py:1544-1569) joins the chain rule to theta_o and to the Hunyuan-space vertices */
+  float *obj_moge;             /* device [Vo_total,3] OUT, or NULL                                      */
+  const float *grad_obj_ext;   /* device [Vo_total,3] dE_ext/d(transformed object verts), or NULL       */
 } foho_guidance_desc;
 #define FOHO_TRACE_KERNELS 11
 
@@ -404,7 +409,13 @@ typedef struct foho_raster_desc {
   int32_t B, V_total, F_total, H, W;
   int32_t tile_cap;            /* faces per 16x16-pixel tile the workspace holds (0 = 1024); overflow -> losses[b][7] = 1 */
   float w_normal, w_disp, w_sil;   /* 10, 10, 10 (pipelines.py:1580-1583) */
-  int32_t reserved;
+  int32_t accumulate_grad;     /* grad_verts += instead of = (several renders of one vertex buffer)              */
+  /* optional second set per image (the extracted object mesh, whose counts live on the device): vertices [V1, V_total)
+   * and faces [F1, F_total) of the same arrays, image b owning [V1 + vert_offsets2[b], V1 + vert_offsets2[b+1]) and
+   * [F1 + face_offsets2[b], ..); entries beyond offsets2[B] are ignored.  NULL: everything is set 1.  V_total / F_total
+   * are then CAPACITIES; skip_set1 renders set 2 alone (the object-only step). */
+  int32_t V1, F1, skip_set1, reserved;
+  const int32_t *vert_offsets2, *face_offsets2;
   const float *verts;          /* device [V_total,3] world (MoGe) space                       */
   const int32_t *faces;        /* device [F_total,3]                                          */
   const int32_t *vert_offsets; /* device [B+1]                                                */
