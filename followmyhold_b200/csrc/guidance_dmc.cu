@@ -155,7 +155,13 @@ __global__ void __launch_bounds__(DT) k_dmc_faces(foho_dmc_desc d, DmcWork w, in
   }
   if (!neg_at(s, D, q[0], q[1], q[2])) { const int t = qv[1]; qv[1] = qv[3]; qv[3] = t; }     // outside at the low end: reverse
   const long long quad = (long long)*cnt + rank;       // packed quad index
-  if (qv[0] < 0 || qv[1] < 0 || qv[2] < 0 || qv[3] < 0 || 2 * quad + 1 >= d.cap_faces) { atomicOr(d.flags, qv[0] < 0 ? 1 : 2); return; }
+  if (2 * quad + 1 >= d.cap_faces) { atomicOr(d.flags, 2); return; }
+  if (qv[0] < 0 || qv[1] < 0 || qv[2] < 0 || qv[3] < 0) {       // a corner's vertex fell beyond the capacity: a degenerate triangle pair,
+    atomicOr(d.flags, 1);                                        // never a stale slot of an earlier extraction
+    int *f0 = d.faces + 6 * quad;
+    for (int k = 0; k < 6; ++k) f0[k] = d.index_base;
+    return;
+  }
   const int vbase = d.index_base;
   int *f = d.faces + 6 * quad;
   f[0] = vbase + qv[0]; f[1] = vbase + qv[1]; f[2] = vbase + qv[2];
@@ -200,13 +206,14 @@ __global__ void __launch_bounds__(DT) k_dmc_edges(foho_dmc_desc d, DmcWork w, in
   if (!emit) { if (threadIdx.x == 0) *cnt = total; return; }
   if (!has) return;
   const long long e = (long long)*cnt + rank;
-  if (e0 < 0 || e1 < 0 || e >= d.cap_edges) { atomicOr(d.flags, 4); return; }
+  if (e >= d.cap_edges) { atomicOr(d.flags, 4); return; }
+  if (e0 < 0 || e1 < 0) { atomicOr(d.flags, 1); d.edges[2 * e] = 0; d.edges[2 * e + 1] = 0; return; }
   d.edges[2 * e] = e0 < e1 ? e0 : e1;
   d.edges[2 * e + 1] = e0 < e1 ? e1 : e0;
 }
 
 // exclusive scan of the per-block counts of all images in place (one CTA), per-image offsets out; mult = items per count
-__global__ void __launch_bounds__(1024) k_dmc_scan(int *cnt, int nb_per_img, int B, int mult, int *offsets) {
+__global__ void __launch_bounds__(1024) k_dmc_scan(int *cnt, int nb_per_img, int B, int mult, int *offsets, int cap) {
   __shared__ int ws[32];
   __shared__ int carry;
   const int t = threadIdx.x, total_blocks = nb_per_img * B;
@@ -230,13 +237,13 @@ __global__ void __launch_bounds__(1024) k_dmc_scan(int *cnt, int nb_per_img, int
     const int excl = carry + ws[t >> 5] + incl - x;
     if (i < total_blocks) {
       cnt[i] = excl;
-      if (i % nb_per_img == 0) offsets[i / nb_per_img] = excl * mult;
+      if (i % nb_per_img == 0) offsets[i / nb_per_img] = min(excl * mult, cap);      // consumers trust the offsets: never beyond capacity
     }
     __syncthreads();
     if (t == 1023) carry = excl + x;
     __syncthreads();
   }
-  if (t == 0) offsets[B] = carry * mult;
+  if (t == 0) offsets[B] = min(carry * mult, cap);
 }
 
 // ---- backward ---------------------------------------------------------------------------------------------------------
@@ -322,14 +329,14 @@ extern "C" int foho_dmc_extract(const foho_dmc_desc *dp, void *cuda_stream) {
   DmcWork w;
   dmc_carve(d, reinterpret_cast<char *>(d.workspace), &w);
   k_dmc_verts<<<dim3(w.nbv, d.B), DT, 0, st>>>(d, w, 0);
-  k_dmc_scan<<<1, 1024, 0, st>>>(w.cnt_v, w.nbv, d.B, 1, d.vert_offsets);
+  k_dmc_scan<<<1, 1024, 0, st>>>(w.cnt_v, w.nbv, d.B, 1, d.vert_offsets, d.cap_verts);
   k_dmc_verts<<<dim3(w.nbv, d.B), DT, 0, st>>>(d, w, 1);
   k_dmc_faces<<<dim3(w.nbf, d.B), DT, 0, st>>>(d, w, 0);
-  k_dmc_scan<<<1, 1024, 0, st>>>(w.cnt_f, w.nbf, d.B, 2, d.face_offsets);          // two triangles per quad
+  k_dmc_scan<<<1, 1024, 0, st>>>(w.cnt_f, w.nbf, d.B, 2, d.face_offsets, d.cap_faces & ~1);          // two triangles per quad
   k_dmc_faces<<<dim3(w.nbf, d.B), DT, 0, st>>>(d, w, 1);
   if (d.edges) {
     k_dmc_edges<<<dim3(w.nbe, d.B), DT, 0, st>>>(d, w, 0);
-    k_dmc_scan<<<1, 1024, 0, st>>>(w.cnt_e, w.nbe, d.B, 1, d.edge_offsets);
+    k_dmc_scan<<<1, 1024, 0, st>>>(w.cnt_e, w.nbe, d.B, 1, d.edge_offsets, d.cap_edges);
     k_dmc_edges<<<dim3(w.nbe, d.B), DT, 0, st>>>(d, w, 1);
   }
   FOHO_LAUNCH_CHECK();

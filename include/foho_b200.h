@@ -445,7 +445,7 @@ int foho_raster_losses_fwd_bwd(const foho_raster_desc *desc, void *cuda_stream);
  * interior sign-changing lattice edge, wound inside -> outside, split along (0, 2).  Meshes of the B images come out
  * packed: image b owns vertices [vert_offsets[b], vert_offsets[b+1]), triangles [face_offsets[b], ..) and unique edges
  * [edge_offsets[b], ..); counts stay on the device.  Orders are deterministic.  *flags: bit0 vertex capacity, bit1 face
- * capacity, bit2 edge capacity exceeded (the mesh is then truncated).
+ * capacity, bit2 edge capacity exceeded (the mesh is then truncated; the offsets never point beyond the capacities).
  * --------------------------------------------------------------------------------------------- */
 typedef struct foho_dmc_desc {
   int32_t B, D;                /* volumes [B,D,D,D], negative inside, lattice linspace(-bound, bound, D)          */

@@ -81,6 +81,9 @@ def test_capacity_overflow_is_flagged():
     ex.extract(sdf)
     with pytest.raises(_lib.FohoStatusError):
         ex.check_flags()
+    # consumers trust the offsets: they never point beyond the capacities, and no face names a dropped vertex
+    assert ex.vert_offsets.tolist() == [0, 100] and ex.face_offsets[-1] <= ex.cap_faces and ex.edge_offsets[-1] <= ex.cap_edges
+    assert int(ex.faces.max()) < 100 and int(ex.edges.max()) < 100
 
 
 # --------------------------------------------------------------------------- the extracted mesh inside the guidance evaluation
@@ -96,7 +99,7 @@ def _hoi_setup(B=1, D=25, P=512, H=96, W=96, fov=20.0, seed=40):
     samples = [make_guidance_sample(D, P, seed + i) for i in range(B)]
     sdf, theta, st = stack_samples(samples, cap=True)
     raw_faces = samples[0].hand_faces.to(torch.int64)
-    cap = B * 6 * D * D
+    cap = B * 12 * D * D                  # room for the noisy surfaces a random-weight decoder produces
     loop = GuidanceLoop(B, D, st, P, micro_batches=1, mock_decoder=False, max_obj_verts=cap)
     loop.theta.copy_(theta); loop.sdf.copy_(sdf)
     fovs = [fov + 2 * b for b in range(B)]
@@ -115,7 +118,7 @@ def _hoi_setup(B=1, D=25, P=512, H=96, W=96, fov=20.0, seed=40):
     mk = lambda tg: ImageTargets(gt_normals=torch.stack([t[0] for t in tg]), gt_mask=torch.stack([t[1] for t in tg]),
                                  gt_disp=torch.stack([t[2] for t in tg]), gt_sil=torch.stack([t[3] for t in tg]), fov_deg=torch.tensor(fovs))
     loop.enable_image_terms(mk(tg_hand), hand_faces_render=raw_faces.to(torch.int32), tile_cap=4096)
-    loop.enable_object_terms(hoi_targets=mk(tg_hoi), obj_targets=mk(tg_hoi), tile_cap=4096)
+    loop.enable_object_terms(hoi_targets=mk(tg_hoi), obj_targets=mk(tg_hoi), tile_cap=4096, cap_verts=cap)
     return loop, samples, st, raw_faces, fovs, tg_hoi, (H, W)
 
 
