@@ -116,3 +116,48 @@ def pack_meshes(meshes: Sequence, device="cuda:0"):
     dev = torch.device(device)
     return (torch.cat(vs).to(dev).contiguous(), torch.cat(fs).to(torch.int32).to(dev).contiguous(),
             torch.tensor(vo, dtype=torch.int32, device=dev), torch.tensor(fo, dtype=torch.int32, device=dev))
+
+
+def render_maps(verts, faces, fov_deg: float, H: int, W: int, device="cuda:0"):
+    """``render_normal_and_disparity(renderer, mesh)`` (pipelines.py:272-289) for ONE mesh, as maps: the min/max-normalised
+    normal colour [H,W,3] (background zeroed), the min/max-normalised disparity [H,W] and the coverage mask [H,W].
+    Set-up code (the reference renders MoGe's mesh once per image, :1247-1256): the rasterisation is the kernel's, the
+    two normalisations are a few torch reductions."""
+    v, f, vo, fo = pack_meshes([(verts, faces)], device=device)
+    r = ImageLossRenderer(1, H, W, v.shape[0], f.shape[0], device=device, tile_cap=max(1024, min(int(f.shape[0]), 8192)))
+    z = torch.zeros(1, H, W, device=device)
+    r.set_targets(ImageTargets(gt_normals=torch.zeros(1, H, W, 3), gt_mask=torch.zeros(1, H, W, dtype=torch.uint8), gt_disp=z, gt_sil=z,
+                               fov_deg=torch.tensor([float(fov_deg)])))
+    losses, _, dbg = r(v, f, vo, fo, backward=False, debug=True)
+    if float(losses[0, 7]) != 0:
+        raise _lib.FohoStatusError("foho_raster_losses_fwd_bwd", _lib.FOHO_E_WORKSPACE, "tile list overflow while rendering the targets")
+    hit = dbg["p2f"][0] >= 0
+    n = dbg["nraw"][0]
+    rn = (n - n.min()) / (n.max() - n.min() + 1e-6) * hit[..., None]
+    zb = torch.where(hit, dbg["zbuf"][0], torch.full_like(dbg["zbuf"][0], 10.0))
+    d = 1.0 / (zb + 1e-6)
+    rd = (d - d.min()) / (d.max() - d.min() + 1e-6)
+    return rn, rd, hit
+
+
+def targets_from_moge(moge_verts, moge_faces, fov_deg: float, hand_mask, obj_mask, device="cuda:0"):
+    """The three target sets of the reference for one image (pipelines.py:1229-1256 and the loss call sites):
+    ``moge_normal = render(moge_mesh) * hoi_mask``, ``moge_disp`` likewise; hand phase: valid = hand mask, disparity target
+    ``moge_disp * hand_mask``, silhouette = hand mask (:1341-1342); object phase: the same with the object mask
+    (:1421-1423); joint phase: hoi mask, ``moge_disp``, hoi silhouette (:1567-1569).  Returns a dict of tuples
+    (gt_normals, gt_mask, gt_disp, gt_sil) keyed 'hand', 'obj', 'hoi' (device tensors)."""
+    hm = torch.as_tensor(hand_mask).to(device) > 0
+    om = torch.as_tensor(obj_mask).to(device) > 0
+    H, W = hm.shape
+    rn, rd, _ = render_maps(moge_verts, moge_faces, fov_deg, H, W, device=device)
+    hoi = hm | om
+    n = rn * hoi[..., None]
+    d = rd * hoi
+    return {"hand": (n, hm, d * hm, hm.float()), "obj": (n, om, d * om, om.float()), "hoi": (n, hoi, d, hoi.float())}
+
+
+def stack_targets(per_image, key: str, fovs) -> ImageTargets:
+    t = [p[key] for p in per_image]
+    return ImageTargets(gt_normals=torch.stack([x[0] for x in t]), gt_mask=torch.stack([x[1] for x in t]),
+                        gt_disp=torch.stack([x[2] for x in t]), gt_sil=torch.stack([x[3] for x in t]),
+                        fov_deg=torch.tensor([float(f) for f in fovs]))

@@ -139,12 +139,17 @@ def load_image_inputs(p: dict, n_cloud: int, rng: np.random.Generator) -> dict:
             break
     if cloud_path is None:
         raise FileNotFoundError(f"no MoGe geometry (mesh.glb / pointcloud.ply / mesh.ply) in {p['moge_dir']}")
-    pts = np.asarray(load(cloud_path).vertices, dtype=np.float64)
+    geo = load(cloud_path)
+    pts = np.asarray(geo.vertices, dtype=np.float64)
+    # MoGe's MESH (mesh.glb in the reference, pipelines.py:1247-1250) also supplies the rendered targets of the image terms
+    moge_mesh = (pts.astype(np.float32), np.asarray(geo.faces, dtype=np.int32)) if isinstance(geo, TriMesh) and len(geo.faces) else None
     if pts.shape[0] >= n_cloud:
         pts = pts[rng.choice(pts.shape[0], n_cloud, replace=False)]
     else:                                                                           # fewer points than the batch size: repeat them cyclically
         pts = pts[np.resize(np.arange(pts.shape[0]), n_cloud)]
-    return dict(fovx=fovx, hw=(H, W), kps=kps, hand_moge=hand_moge.astype(np.float32),
+    return dict(fovx=fovx, hw=(H, W), kps=kps, hand_moge=hand_moge.astype(np.float32), moge_mesh=moge_mesh,
+                hand_mask=(hand_mask if hand_mask.ndim == 2 else hand_mask[..., 0]) > 0,
+                obj_mask=(obj_mask if obj_mask.ndim == 2 else obj_mask[..., 0]) > 0,
                 faces=np.asarray(mano.faces, dtype=np.int32), T_h2m=T.astype(np.float32), cloud=pts.astype(np.float32))
 
 
@@ -185,6 +190,7 @@ def run(
     config: Optional[OptimizationConfig] = None,
     j_regressor_path: str = J_REGRESSOR_PATH,
     seed: int = 2,
+    obj_cap_factor: int = 6,
 ) -> None:
     """Positional/keyword arguments up to ``task_list_file`` are the reference's (run.py:188-199)."""
     del project_root                      # the reference only uses it to extend sys.path (run.py:57-62)
@@ -227,7 +233,7 @@ def run(
     for chunk in batches_of_compatible_images(todo, batch_size):
         idx = [p["index"] for p, _ in chunk]
         try:
-            _run_batch(chunk, model, J, config, n_cloud, dev, seed, GuidanceLoop)
+            _run_batch(chunk, model, J, config, n_cloud, dev, seed, GuidanceLoop, obj_cap_factor)
             for i in idx:
                 print(f"Reconstructed object {i}")
         except Exception as e:
@@ -239,7 +245,7 @@ def run(
             print(f"Error in reconstruction for batch {idx} : {e}; retrying its images one by one")
             for item in chunk:
                 try:
-                    _run_batch([item], model, J, config, n_cloud, dev, seed, GuidanceLoop)
+                    _run_batch([item], model, J, config, n_cloud, dev, seed, GuidanceLoop, obj_cap_factor)
                     print(f"Reconstructed object {item[0]['index']}")
                 except Exception as e1:
                     print(f"Error in reconstruction for {item[0]['index']} : {e1}")
@@ -269,7 +275,7 @@ def batches_of_compatible_images(todo: list, batch_size: int) -> List[list]:
 
 
 def _run_batch(chunk, model: GuidanceModel, J: torch.Tensor, config: OptimizationConfig, n_cloud: int, dev, seed: int,
-               GuidanceLoop) -> None:
+               GuidanceLoop, obj_cap_factor: int = 6) -> None:
     B = len(chunk)
     inputs = [inp for _, inp in chunk]
     faces0 = inputs[0]["faces"]
@@ -297,13 +303,25 @@ def _run_batch(chunk, model: GuidanceModel, J: torch.Tensor, config: Optimizatio
     if callable(tc_decoder):
         # the reference's own decoder on the tensor cores: latent2sdf + adjoint as kernels, no autograd (row f1)
         dec = tc_decoder(B)
+        cap_obj = B * int(obj_cap_factor) * model.D * model.D      # extracted-surface capacity: a closed surface has O(D^2) cubes
         loop = GuidanceLoop(B, model.D, st, n_cloud, device=dev, config=config, latent_elems=model.latent_elems,
-                            loss_log_every=10 if debug_root else 0, mock_decoder=False)
+                            loss_log_every=10 if debug_root else 0, mock_decoder=False, max_obj_verts=cap_obj)
+        if all(inp.get("moge_mesh") is not None for inp in inputs):
+            # the reference's image terms (pipelines.py:1327-1349,1413-1440,1544-1569): targets rendered once per image from
+            # MoGe's mesh, then hand / object-only / joined renders every inner iteration, object mesh extracted from the volume
+            from .render import stack_targets, targets_from_moge
+            per = [targets_from_moge(i["moge_mesh"][0], i["moge_mesh"][1], i["fovx"], i["hand_mask"], i["obj_mask"], device=dev) for i in inputs]
+            fovs = [i["fovx"] for i in inputs]
+            loop.enable_image_terms(stack_targets(per, "hand", fovs), hand_faces_render=torch.from_numpy(faces0.astype(np.int32)).to(dev))
+            loop.enable_object_terms(hoi_targets=stack_targets(per, "hoi", fovs), obj_targets=stack_targets(per, "obj", fovs), cap_verts=cap_obj)
+        else:
+            loop.enable_object_terms(cap_verts=cap_obj)          # REF mesh terms a7 / a10 on the extracted surface, no renders
         loop.sdf.fill_(1.0)                                     # finite "outside" volume for the hand-only phase
         loop.x_t.copy_(model.initial_latents(B, gen))
         loop.reset_leaves()
         loop.run_schedule_tc_decoder(model.predict, dec)
         loop.check_overflow()
+        loop._obj.ex.check_flags()                              # a truncated surface = wrong terms: fail loudly
         x1 = (loop.x_t + (1.0 - float(loop.sigmas[last])) * loop.velocity).contiguous()      # final decode (:1641), sigma_last = 1
         sdf = dec.forward(x1.view(B, 3072, 64)).reshape(B, model.D, model.D, model.D).cpu().numpy()
     elif callable(decode):
