@@ -899,6 +899,7 @@ extern "C" const char *foho_status_string(int s) {
     case FOHO_E_SHAPE: return "size out of the supported range";
     case FOHO_E_WORKSPACE: return "workspace too small or misaligned";
     case FOHO_E_ARG: return "invalid argument";
+    case FOHO_E_DRIVER: return "CUDA driver entry point unavailable or tensor-map encode failed";
     default: return s > 0 ? cudaGetErrorString((cudaError_t)s) : "unknown foho status";
   }
 }
