@@ -23,7 +23,7 @@ NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", 
 
 FOHO_NUM_TERMS = 16
 FOHO_E_WORKSPACE = -3
-ABI_VERSION = 5
+ABI_VERSION = 6
 TERM_NAMES = ["total", "pen", "con", "int", "count", "mom", "ch", "kp", "treg_h", "treg_o", "dist", "vreg",
               "edge", "mean_d2", "ncand", "flags"]
 
@@ -33,7 +33,7 @@ EXPORTED_SYMBOLS = [
     "foho_guidance_workspace_bytes", "foho_guidance_energy_fwd_bwd", "foho_guidance_update", "foho_guidance_update_f16",
     "foho_guidance_accel_bytes", "foho_guidance_prepare_statics",
     "foho_scheduler_step", "foho_scheduler_step_f16", "foho_mock_decoder_forward", "foho_mock_decoder_backward",
-    "foho_icp_workspace_bytes", "foho_icp_run",
+    "foho_icp_workspace_bytes", "foho_icp_run", "foho_icp_run_batch",
     "foho_mesh2sdf_workspace_bytes", "foho_mesh2sdf_lattice", "foho_intersection_count", "foho_mesh_decimate",
     "foho_tc_gemm", "foho_tc_attention",
     "foho_dec_layernorm", "foho_dec_layernorm_bwd", "foho_dec_softmax", "foho_dec_softmax_bwd", "foho_dec_fourier_embed",
@@ -80,7 +80,7 @@ def build(force: bool = False, verbose: bool = False) -> Path:
     procs = []
     for src in SOURCES:
         obj = build_dir / (Path(src).stem + ".o")
-        cmd = [nvcc, *NVCC_FLAGS, "-c", str(CSRC / src), "-o", str(obj)]
+        cmd = [nvcc, *NVCC_FLAGS, *os.environ.get("FOHO_B200_EXTRA_NVCC_FLAGS", "").split(), "-c", str(CSRC / src), "-o", str(obj)]
         if verbose:
             print(" ".join(cmd))
         procs.append((src, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
@@ -186,6 +186,18 @@ class DmcDesc(C.Structure):
     ]
 
 
+class IcpProblem(C.Structure):
+    _fields_ = [
+        ("source", C.c_void_p), ("target", C.c_void_p),
+        ("Ns", C.c_int32), ("Nt", C.c_int32), ("n_iter", C.c_int32), ("n_outliers", C.c_int32), ("fixed_scale", C.c_int32),
+        ("reserved", C.c_int32),
+        ("min_scale", C.c_double), ("max_scale", C.c_double),
+        ("transform_out", C.c_void_p), ("cost_out", C.c_void_p), ("cost_history", C.c_void_p),
+        ("nn_index_last", C.c_void_p),
+        ("workspace", C.c_void_p), ("workspace_bytes", C.c_size_t),
+    ]
+
+
 _lib: Optional[C.CDLL] = None
 
 
@@ -242,6 +254,8 @@ def load(build_if_missing: bool = False) -> C.CDLL:
     lib.foho_icp_run.argtypes = [C.c_void_p, C.c_int32, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
                                  C.c_double, C.c_double, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                  C.c_void_p, C.c_size_t, C.c_void_p]
+    lib.foho_icp_run_batch.restype = C.c_int
+    lib.foho_icp_run_batch.argtypes = [C.POINTER(IcpProblem), C.c_int32, C.c_void_p]
     lib.foho_mesh2sdf_workspace_bytes.restype = C.c_size_t
     lib.foho_mesh2sdf_workspace_bytes.argtypes = [C.c_int32] * 5
     lib.foho_mesh2sdf_lattice.restype = C.c_int

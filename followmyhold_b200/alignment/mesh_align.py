@@ -168,23 +168,25 @@ def icp_points(source_points: np.ndarray, target_points: np.ndarray, n_iter: int
 
 def icp_points_many(problems, n_iter: int, n_outliers, fixed_scale: bool = False, min_scale: float = 0.5,
                     max_scale: float = 2.0, device="cuda:0"):
-    """Several independent ICP loops at once (one per image of a batch), each on its own CUDA stream.
+    """Several independent ICP loops at once (one per image of a batch) in ONE persistent launch
+    (``foho_icp_run_batch``): the SMs are divided between the problems, each problem's CTAs synchronise among
+    themselves only.
 
-    ``problems``: list of ``(source_points [Ns,3], target_points [Nt,3])``; ``n_outliers``: int or one
-    int per problem.  A single loop is latency bound (two small kernels per iteration, one of them a
-    single CTA), so the loops of different images overlap almost perfectly.  Returns a list of
-    ``(best_transform [4,4] float64, best_cost)`` -- each identical to what ``icp_points`` returns."""
+    ``problems``: list of ``(source_points [Ns,3], target_points [Nt,3])``; ``n_outliers``: int or one int per
+    problem.  Returns a list of ``(best_transform [4,4] float64, best_cost)``."""
     lib = _lib.load()
     dev = torch.device(device)
     if dev.type != "cuda":
         raise _lib.FohoLibraryError("icp needs a CUDA device; there is no CPU fallback")
     n = len(problems)
+    if n == 0:
+        return []
     outs = [n_outliers] * n if isinstance(n_outliers, int) else list(n_outliers)
     keep = []
+    descs = (_lib.IcpProblem * n)()
     with torch.cuda.device(dev):
-        cur = torch.cuda.current_stream(dev)
-        streams = [torch.cuda.Stream(device=dev) for _ in range(n)]
-        for (src_np, tgt_np), n_out, st in zip(problems, outs, streams):
+        s = torch.cuda.current_stream(dev)
+        for k, ((src_np, tgt_np), n_out) in enumerate(zip(problems, outs)):
             src = torch.as_tensor(np.ascontiguousarray(src_np, dtype=np.float64)).to(dev)
             tgt = torch.as_tensor(np.ascontiguousarray(tgt_np, dtype=np.float64)).to(dev)
             Ns, Nt = src.shape[0], tgt.shape[0]
@@ -193,14 +195,15 @@ def icp_points_many(problems, n_iter: int, n_outliers, fixed_scale: bool = False
             ws_ptr = ws.data_ptr() + ((-ws.data_ptr()) % 256)
             T = torch.zeros(16, dtype=torch.float64, device=dev)
             cost = torch.zeros(1, dtype=torch.float64, device=dev)
-            st.wait_stream(cur)
-            _lib.check("foho_icp_run", lib.foho_icp_run(
-                src.data_ptr(), Ns, tgt.data_ptr(), Nt, int(n_iter), int(n_out), int(bool(fixed_scale)),
-                float(min_scale), float(max_scale), T.data_ptr(), cost.data_ptr(), None, None,
-                C.c_void_p(ws_ptr), nbytes, C.c_void_p(st.cuda_stream)))
+            d = descs[k]
+            d.source, d.target, d.Ns, d.Nt = src.data_ptr(), tgt.data_ptr(), Ns, Nt
+            d.n_iter, d.n_outliers, d.fixed_scale = int(n_iter), int(n_out), int(bool(fixed_scale))
+            d.min_scale, d.max_scale = float(min_scale), float(max_scale)
+            d.transform_out, d.cost_out, d.cost_history, d.nn_index_last = T.data_ptr(), cost.data_ptr(), None, None
+            d.workspace, d.workspace_bytes = ws_ptr, nbytes
             keep.append((src, tgt, ws, T, cost))
-        for st in streams:
-            st.synchronize()
+        _lib.check("foho_icp_run_batch", lib.foho_icp_run_batch(descs, n, C.c_void_p(s.cuda_stream)))
+        s.synchronize()
     return [(T.cpu().numpy().reshape(4, 4), float(cost.item())) for (_, _, _, T, cost) in keep]
 
 

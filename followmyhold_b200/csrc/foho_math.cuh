@@ -219,11 +219,65 @@ FOHO_HD void jacobi_eig3(double A[3][3], double V[3][3]) {
   }
 }
 
+// Orthogonal polar factor of a 3x3 matrix with positive determinant by the scaled Newton iteration
+// X <- (g X + X^-T / g) / 2, g ~ sqrt(|X^-1|_F / |X|_F) (Higham): a handful of iterations of one reciprocal each.
+// The scaling only has to be roughly right (it is taken in single precision and switched off near the fixed point,
+// from where the plain iteration squares the error each step), so the result is the polar factor to rounding.  For
+// det(H) > 0 this IS U V^T of H = U S V^T.  Returns false (R untouched) when H is not safely orientation preserving
+// or the iteration does not settle; the caller then takes the eigen-decomposition path.
+FOHO_HD void cofactors3(const double X[3][3], double C[3][3]) {
+  C[0][0] = X[1][1] * X[2][2] - X[1][2] * X[2][1]; C[0][1] = X[1][2] * X[2][0] - X[1][0] * X[2][2]; C[0][2] = X[1][0] * X[2][1] - X[1][1] * X[2][0];
+  C[1][0] = X[0][2] * X[2][1] - X[0][1] * X[2][2]; C[1][1] = X[0][0] * X[2][2] - X[0][2] * X[2][0]; C[1][2] = X[0][1] * X[2][0] - X[0][0] * X[2][1];
+  C[2][0] = X[0][1] * X[1][2] - X[0][2] * X[1][1]; C[2][1] = X[0][2] * X[1][0] - X[0][0] * X[1][2]; C[2][2] = X[0][0] * X[1][1] - X[0][1] * X[1][0];
+}
+
+FOHO_HD bool polar_rotation3(const double H[3][3], double R[3][3]) {
+  double X[3][3], C[3][3], fro = 0.0;
+  for (int i = 0; i < 3; ++i)
+    for (int j = 0; j < 3; ++j) fro += H[i][j] * H[i][j];
+  if (!(fro > 0.0) || !(fro < 1e300)) return false;
+  const double inv = 1.0 / sqrt(fro);
+  for (int i = 0; i < 3; ++i)
+    for (int j = 0; j < 3; ++j) X[i][j] = H[i][j] * inv;
+  for (int it = 0; it < 40; ++it) {
+    cofactors3(X, C);                              // X^-T = C / det
+    const double det = X[0][0] * C[0][0] + X[0][1] * C[0][1] + X[0][2] * C[0][2];
+    if (!(det > 1e-9)) return false;               // |X|_F = 1 at the start: this small means a (nearly) flat or mirrored H
+    double nx = 0.0, nc = 0.0;
+    for (int i = 0; i < 3; ++i)
+      for (int j = 0; j < 3; ++j) { nx += X[i][j] * X[i][j]; nc += C[i][j] * C[i][j]; }
+    const double rdet = 1.0 / det;
+    // g^2 = |X^-1|_F / |X|_F = sqrt(nc / nx) / det
+    float gf = sqrtf(sqrtf((float)nc / (float)nx) * (float)rdet);
+    if (!(gf > 0.95f && gf < 1.05f)) gf = fminf(fmaxf(gf, 1e-3f), 1e3f); else gf = 1.f;
+    const double ca = 0.5 * (double)gf, cb = 0.5 * rdet * (double)(1.f / gf);
+    double change = 0.0;
+    for (int i = 0; i < 3; ++i)
+      for (int j = 0; j < 3; ++j) {
+        const double v = ca * X[i][j] + cb * C[i][j];
+        const double d = v - X[i][j];
+        change += d * d;
+        X[i][j] = v;
+      }
+    if (gf == 1.f && change <= 1e-14) {
+      // |dX| <= 1e-7 on a plain step: the error left is ~ |dX|^2 / 2 <= 1e-14; one more plain step squares it again
+      cofactors3(X, C);
+      const double d2 = X[0][0] * C[0][0] + X[0][1] * C[0][1] + X[0][2] * C[0][2];
+      const double r2 = 0.5 / d2;
+      for (int i = 0; i < 3; ++i)
+        for (int j = 0; j < 3; ++j) R[i][j] = 0.5 * X[i][j] + r2 * C[i][j];
+      return true;
+    }
+  }
+  return false;
+}
+
 // Rotation of trimesh.registration.procrustes(reflection=False): with H = U S V^T,
 // R = U diag(1,1,det(U V^T)) V^T.  Computed as R = U' V'^T where U', V' are the
 // right-handed completions of the two leading singular pairs (identical result, no
 // explicit sign logic; the smallest singular direction absorbs the flip).
 FOHO_HD void kabsch_rotation(const double H[3][3], double R[3][3]) {
+  if (polar_rotation3(H, R)) return;          // det(H) > 0 (every aligned pair of clouds): U V^T is the polar factor
   double K[3][3], V[3][3];
   for (int i = 0; i < 3; ++i)
     for (int j = 0; j < 3; ++j) K[i][j] = H[0][i] * H[0][j] + H[1][i] * H[1][j] + H[2][i] * H[2][j];   // H^T H

@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define FOHO_ABI_VERSION 5
+#define FOHO_ABI_VERSION 6
 
 #define FOHO_OK 0
 #define FOHO_E_NULL (-1)      /* required pointer is NULL            */
@@ -263,6 +263,20 @@ int foho_icp_run(const double *source, int32_t Ns, const double *target, int32_t
                  int32_t n_outliers, int32_t fixed_scale, double min_scale, double max_scale,
                  double *transform_out, double *cost_out, double *cost_history, int32_t *nn_index_last,
                  void *workspace, size_t workspace_bytes, void *cuda_stream);
+
+/* Several independent loops in ONE persistent launch (the images of a batch; `align_meshes_impl` is called once per
+ * image by h2m.py:35-54 / mano.py:24-43): the SMs are divided between the problems, each problem's CTAs synchronise
+ * among themselves only.  Every result is identical to foho_icp_run's on a grid of the same size; the fields are
+ * foho_icp_run's arguments.  `problems` is a HOST array. */
+typedef struct foho_icp_problem {
+  const double *source; const double *target;
+  int32_t Ns, Nt, n_iter, n_outliers, fixed_scale, reserved;
+  double min_scale, max_scale;
+  double *transform_out, *cost_out, *cost_history;
+  int32_t *nn_index_last;
+  void *workspace; size_t workspace_bytes;
+} foho_icp_problem;
+int foho_icp_run_batch(const foho_icp_problem *problems, int32_t n_problems, void *cuda_stream);
 
 /* Exact mesh -> signed distance on a rectilinear lattice: replaces `mesh2sdf`
  * (third_party/utilz/kaolin_sdf_ops.py:88-109: kaolin point_to_mesh_distance +

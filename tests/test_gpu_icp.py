@@ -118,6 +118,38 @@ def test_concurrent_loops_equal_single_loops():
         assert np.array_equal(T, T1) and c == c1
 
 
+@pytest.mark.gpu
+def test_one_launch_for_several_problems_equals_single_runs_at_the_stage_sizes():
+    """foho_icp_run_batch divides the SMs between the problems; block sums are formed per 32 consecutive points and
+    added in index order, so the number of CTAs a problem gets does not change a single bit."""
+    from followmyhold_b200.alignment.mesh_align import icp_points, icp_points_many
+    probs, outs = [], []
+    for k in range(3):
+        src, tgt, _ = _clouds(5000 - 37 * k, 10000 + 11 * k, seed=20 + k)
+        probs.append((src, tgt))
+        outs.append(int(0.2 * src.shape[0]))
+    many = icp_points_many(probs, 40, outs, False, 0.7, 3.0)
+    for (src, tgt), n_out, (T, c) in zip(probs, outs, many):
+        T1, c1 = icp_points(src, tgt, 40, n_out, False, 0.7, 3.0)
+        assert np.array_equal(T, T1) and c == c1
+
+
+@pytest.mark.gpu
+def test_trim_with_many_equal_distances_matches_the_oracle():
+    """Distances that tie at the trim threshold (lattice clouds, an exact offset): the lowest indices among the ties are
+    kept, like the stable argsort of the reference's loop (mesh_align.py:114-120)."""
+    from followmyhold_b200.alignment.mesh_align import icp_points
+    from oracle import icp_oracle as O
+    g = np.arange(12, dtype=np.float64)
+    tgt = np.stack(np.meshgrid(g, g, g, indexing="ij"), -1).reshape(-1, 3)          # 1728 lattice points
+    rng = np.random.default_rng(3)
+    src = tgt[rng.permutation(len(tgt))[:1200]] + np.array([0.25, 0.0, 0.0])          # every distance is exactly 0.25
+    T, cost, hist = icp_points(src, tgt, 2, 300, True, 0.5, 2.0, return_history=True)
+    To, co, ho, _ = O.icp_points(src, tgt, 2, 300, True, 0.5, 2.0, return_history=True)
+    np.testing.assert_allclose(hist[:1], ho[:1], rtol=1e-12)
+    np.testing.assert_allclose(T, To, atol=1e-9)
+
+
 def test_batched_sharded_alignment_stage_equals_one_image_at_a_time(tmp_path, monkeypatch):
     """The stages align the images of a batch with their ICP loops in flight together, and a rank only its
     share ``sorted(meshes)[r::world]`` -- transforms and meshes are bit-equal to one ``align_meshes_impl`` call
