@@ -16,7 +16,7 @@ PKG_DIR = Path(__file__).resolve().parent
 REPO_ROOT = PKG_DIR.parent
 CSRC = PKG_DIR / "csrc"
 LIB_PATH = PKG_DIR / "libfoho_b200.so"
-SOURCES = ["guidance_stream.cu", "guidance_sparse.cu", "guidance_objmesh.cu", "guidance_chamfer.cu", "guidance_voxdist.cu", "guidance_update.cu", "icp.cu",
+SOURCES = ["guidance_stream.cu", "guidance_sparse.cu", "guidance_objmesh.cu", "guidance_chamfer.cu", "guidance_voxdist.cu", "guidance_update.cu", "icp.cu", "mesh_sample.cu",
            "mesh_sdf.cu", "mesh_decimate.cu", "decoder_gemm.cu", "decoder_attn.cu", "decoder_ops.cu", "guidance_raster.cu", "guidance_dmc.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "-Xcompiler", "-fPIC", "-Xcompiler", "-O3"]
@@ -34,6 +34,7 @@ EXPORTED_SYMBOLS = [
     "foho_guidance_accel_bytes", "foho_guidance_prepare_statics",
     "foho_scheduler_step", "foho_scheduler_step_f16", "foho_mock_decoder_forward", "foho_mock_decoder_backward",
     "foho_icp_workspace_bytes", "foho_icp_run", "foho_icp_run_batch",
+    "foho_remove_close_workspace_bytes", "foho_remove_close",
     "foho_mesh2sdf_workspace_bytes", "foho_mesh2sdf_lattice", "foho_intersection_count", "foho_mesh_decimate",
     "foho_tc_gemm", "foho_tc_attention",
     "foho_dec_layernorm", "foho_dec_layernorm_bwd", "foho_dec_softmax", "foho_dec_softmax_bwd", "foho_dec_fourier_embed",
@@ -256,6 +257,10 @@ def load(build_if_missing: bool = False) -> C.CDLL:
                                  C.c_void_p, C.c_size_t, C.c_void_p]
     lib.foho_icp_run_batch.restype = C.c_int
     lib.foho_icp_run_batch.argtypes = [C.POINTER(IcpProblem), C.c_int32, C.c_void_p]
+    lib.foho_remove_close_workspace_bytes.restype = C.c_size_t
+    lib.foho_remove_close_workspace_bytes.argtypes = [C.c_int32]
+    lib.foho_remove_close.restype = C.c_int
+    lib.foho_remove_close.argtypes = [C.c_void_p, C.c_int32, C.c_double, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]
     lib.foho_mesh2sdf_workspace_bytes.restype = C.c_size_t
     lib.foho_mesh2sdf_workspace_bytes.argtypes = [C.c_int32] * 5
     lib.foho_mesh2sdf_lattice.restype = C.c_int

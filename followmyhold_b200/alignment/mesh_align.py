@@ -122,12 +122,37 @@ def remove_close(points: np.ndarray, radius: float):
     return points[mask], mask
 
 
-def sample_surface_even(mesh: TriMesh, count: int, rng: np.random.Generator):
+def remove_close_device(points: np.ndarray, radius: float, device="cuda:0"):
+    """``remove_close`` on the device (``foho_remove_close``: uniform grid + sort instead of a k-d tree); the mask
+    equals the host statement's bit for bit (tests/test_gpu_icp.py)."""
+    lib = _lib.load()
+    dev = torch.device(device)
+    if dev.type != "cuda":
+        raise _lib.FohoLibraryError("remove_close_device needs a CUDA device")
+    pts = np.ascontiguousarray(points, dtype=np.float64)
+    n = len(pts)
+    if n == 0:
+        return pts, np.ones(0, dtype=bool)
+    with torch.cuda.device(dev):
+        s = torch.cuda.current_stream(dev)
+        d_pts = torch.as_tensor(pts).to(dev)
+        keep = torch.empty(n, dtype=torch.uint8, device=dev)
+        nbytes = lib.foho_remove_close_workspace_bytes(n)
+        ws = torch.empty(nbytes + 256, dtype=torch.uint8, device=dev)
+        ws_ptr = ws.data_ptr() + ((-ws.data_ptr()) % 256)
+        _lib.check("foho_remove_close", lib.foho_remove_close(d_pts.data_ptr(), n, float(radius), keep.data_ptr(),
+                                                              C.c_void_p(ws_ptr), nbytes, C.c_void_p(s.cuda_stream)))
+        mask = keep.cpu().numpy().astype(bool)
+    return pts[mask], mask
+
+
+def sample_surface_even(mesh: TriMesh, count: int, rng: np.random.Generator, device=None):
     """``trimesh.sample.sample_surface_even``: 3x oversample, thin by min distance
-    sqrt(area/(3 count)); may return fewer than ``count`` points (mesh_align.py:79,85)."""
+    sqrt(area/(3 count)); may return fewer than ``count`` points (mesh_align.py:79,85).  With ``device`` the thinning
+    -- a k-d tree build and pair query on the host otherwise, most of the stage's wall time -- runs on the GPU."""
     radius = np.sqrt(mesh.area / (3 * count))
     points, index = sample_surface(mesh, count * 3, rng)
-    points, mask = remove_close(points, radius)
+    points, mask = remove_close(points, radius) if device is None else remove_close_device(points, radius, device)
     if len(points) >= count:
         return points[:count], index[mask][:count]
     return points, index[mask]
@@ -209,7 +234,7 @@ def icp_points_many(problems, n_iter: int, n_outliers, fixed_scale: bool = False
 
 def _icp_problem(source_mesh: Geometry, target_mesh: Geometry, count_source: int, count_target: int,
                  test_reflections: bool, test_rotations: bool, outliers: float, on_surface: bool, plot: bool,
-                 seed: Optional[int]):
+                 seed: Optional[int], device=None):
     """Host part of ``icp`` before the loop (mesh_align.py:69-102): candidate cube transforms, surface samples,
     outlier count.  Returns (cubes, source_points, target_points, n_outliers)."""
     if on_surface:
@@ -228,12 +253,12 @@ def _icp_problem(source_mesh: Geometry, target_mesh: Geometry, count_source: int
         source_points = source_mesh.vertices
         count_source = len(source_points)
     else:
-        source_points = sample_surface_even(source_mesh, count_source, rng)[0]
+        source_points = sample_surface_even(source_mesh, count_source, rng, device)[0]
     if isinstance(target_mesh, PointCloud):
         target_points = target_mesh.vertices
         count_target = len(target_points)
     else:
-        target_points = sample_surface_even(target_mesh, count_target, rng)[0]
+        target_points = sample_surface_even(target_mesh, count_target, rng, device)[0]
 
     # reference quirk kept: n_outliers from the *requested* count (mesh_align.py:87)
     n_outliers = int(outliers * count_source)
@@ -250,7 +275,7 @@ def icp(source_mesh: Geometry, target_mesh: Geometry, n_iter: int, count_source:
     """Same contract as the reference ``icp`` (mesh_align.py:56-175)."""
     cubes, source_points, target_points, n_outliers = _icp_problem(
         source_mesh, target_mesh, count_source, count_target, test_reflections, test_rotations, outliers,
-        on_surface, plot, seed)
+        on_surface, plot, seed, device)
     best_of_all_cost = np.inf
     best_of_all_transform = np.eye(4)
     for cube in cubes:
@@ -292,7 +317,7 @@ def icp_many(pairs, n_iter: int, count_source: int = 5_000, count_target: int = 
     Returns one (transform, cost) per pair, each equal to what ``icp`` returns for that pair and seed."""
     seeds = [None] * len(pairs) if seeds is None else list(seeds)
     preps = _pool_map(lambda a: _icp_problem(a[0][0], a[0][1], count_source, count_target, test_reflections,
-                                             test_rotations, outliers, on_surface, plot, a[1]),
+                                             test_rotations, outliers, on_surface, plot, a[1], device),
                       zip(pairs, seeds), workers)
     problems, n_out, owner = [], [], []
     for j, (cubes, sp, tp, no) in enumerate(preps):

@@ -278,6 +278,14 @@ typedef struct foho_icp_problem {
 } foho_icp_problem;
 int foho_icp_run_batch(const foho_icp_problem *problems, int32_t n_problems, void *cuda_stream);
 
+/* Replaces trimesh.points.remove_close inside trimesh.sample.sample_surface_even, which `icp` calls for both point
+ * sets (src/foho/alignment/mesh_align.py:79,85): keep_mask[i] = 0 for every point that some pair (a < b) with
+ * |p_a - p_b| <= radius drops -- the member that appears in more pairs, a when the counts are equal (cKDTree.query_pairs
+ * + bincount + argmax).  points [N,3] device float64, OUT keep_mask [N] device uint8. */
+size_t foho_remove_close_workspace_bytes(int32_t N);
+int foho_remove_close(const double *points, int32_t N, double radius, uint8_t *keep_mask, void *workspace,
+                      size_t workspace_bytes, void *cuda_stream);
+
 /* Exact mesh -> signed distance on a rectilinear lattice: replaces `mesh2sdf`
  * (third_party/utilz/kaolin_sdf_ops.py:88-109: kaolin point_to_mesh_distance +
  * check_sign) for the grid of get_sdf_of_meshes (:131-160), whose points are the

@@ -135,6 +135,39 @@ def test_one_launch_for_several_problems_equals_single_runs_at_the_stage_sizes()
 
 
 @pytest.mark.gpu
+def test_device_thinning_mask_equals_the_host_statement():
+    """foho_remove_close (grid + sort) against ``remove_close`` (cKDTree.query_pairs + bincount + argmax, the statement of
+    trimesh.points.remove_close): identical masks on surface samples at the stage's four sizes, on clouds with exact
+    duplicates, with fewer points than the sort's smallest size, with radius 0, and where the box is far wider than
+    16k cells of the radius."""
+    from followmyhold_b200.alignment import mesh_align as MA
+    from followmyhold_b200.meshio import TriMesh
+    from followmyhold_b200.synthetic import icosphere
+    v, f = icosphere(3, 0.4)
+    mesh = TriMesh(v.astype(np.float64) * np.array([1.0, 0.7, 0.45]), f)
+    for count in (1000, 5000, 10000):
+        rng = np.random.default_rng(count)
+        pts, _ = MA.sample_surface(mesh, 3 * count, rng)
+        radius = np.sqrt(mesh.area / (3 * count))
+        kept_h, mask_h = MA.remove_close(pts, radius)
+        kept_d, mask_d = MA.remove_close_device(pts, radius)
+        assert np.array_equal(mask_h, mask_d) and np.array_equal(kept_h, kept_d)
+        assert 0.2 * len(pts) < mask_d.sum() < len(pts)
+        a, _ = MA.sample_surface_even(mesh, count, np.random.default_rng(1))
+        b, _ = MA.sample_surface_even(mesh, count, np.random.default_rng(1), device="cuda:0")
+        assert np.array_equal(a, b)
+    rng = np.random.default_rng(0)
+    dup = rng.normal(size=(700, 3))
+    dup = np.concatenate([dup, dup[:200], dup[:50] + 1e-3])                          # exact duplicates and near ones
+    for radius in (0.0, 1e-3, 0.2, 5.0):
+        assert np.array_equal(MA.remove_close(dup, radius)[1], MA.remove_close_device(dup, radius)[1]), radius
+    wide = rng.uniform(-1e3, 1e3, size=(4000, 3))
+    wide[::7] = wide[1::7][:len(wide[::7])] + 1e-4 * rng.normal(size=(len(wide[::7]), 3))   # pairs ~1e-4 apart in a 2e3 box
+    assert np.array_equal(MA.remove_close(wide, 2e-4)[1], MA.remove_close_device(wide, 2e-4)[1])
+    assert MA.remove_close_device(np.zeros((0, 3)), 0.1)[1].shape == (0,)
+
+
+@pytest.mark.gpu
 def test_trim_with_many_equal_distances_matches_the_oracle():
     """Distances that tie at the trim threshold (lattice clouds, an exact offset): the lowest indices among the ties are
     kept, like the stable argsort of the reference's loop (mesh_align.py:114-120)."""

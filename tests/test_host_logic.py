@@ -269,6 +269,8 @@ def test_align_meshes_many_host_logic_equals_one_at_a_time(tmp_path, monkeypatch
 
     monkeypatch.setattr(MA, "icp_points", one)
     monkeypatch.setattr(MA, "icp_points_many", many)
+    # the device thinning returns the host statement's mask bit for bit (test_gpu_icp.py); no GPU here
+    monkeypatch.setattr(MA, "remove_close_device", lambda pts, radius, device=None: MA.remove_close(pts, radius))
     hv, hf = standin_hand_mesh(0.35)
     jobs = []
     for k in range(3):
@@ -305,6 +307,7 @@ def test_alignment_stage_glue_on_files_with_the_oracle_loop(tmp_path, monkeypatc
     def one(src, tgt, n_iter, n_out, fixed_scale=False, min_scale=0.5, max_scale=2.0, device=None, return_history=False):
         return IO.icp_points(src, tgt, n_iter, n_out, fixed_scale, min_scale, max_scale)
 
+    monkeypatch.setattr(MA, "remove_close_device", lambda pts, radius, device=None: MA.remove_close(pts, radius))
     monkeypatch.setattr(MA, "icp_points", one)
     monkeypatch.setattr(MA, "icp_points_many", lambda probs, n_iter, n_out, fs=False, lo=0.5, hi=2.0, device=None:
                         [one(s, t, n_iter, o, fs, lo, hi) for (s, t), o in zip(probs, n_out)])
