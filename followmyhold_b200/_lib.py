@@ -17,13 +17,13 @@ REPO_ROOT = PKG_DIR.parent
 CSRC = PKG_DIR / "csrc"
 LIB_PATH = PKG_DIR / "libfoho_b200.so"
 SOURCES = ["guidance_stream.cu", "guidance_sparse.cu", "guidance_objmesh.cu", "guidance_chamfer.cu", "guidance_voxdist.cu", "guidance_update.cu", "icp.cu", "mesh_sample.cu",
-           "mesh_sdf.cu", "mesh_decimate.cu", "decoder_gemm.cu", "decoder_attn.cu", "decoder_ops.cu", "guidance_raster.cu", "guidance_dmc.cu"]
+           "mesh_sdf.cu", "mesh_decimate.cu", "decoder_gemm.cu", "decoder_attn.cu", "decoder_attn_bwd.cu", "decoder_ops.cu", "guidance_raster.cu", "guidance_dmc.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "-Xcompiler", "-fPIC", "-Xcompiler", "-O3"]
 
 FOHO_NUM_TERMS = 16
 FOHO_E_WORKSPACE = -3
-ABI_VERSION = 6
+ABI_VERSION = 7
 TERM_NAMES = ["total", "pen", "con", "int", "count", "mom", "ch", "kp", "treg_h", "treg_o", "dist", "vreg",
               "edge", "mean_d2", "ncand", "flags"]
 
@@ -36,7 +36,7 @@ EXPORTED_SYMBOLS = [
     "foho_icp_workspace_bytes", "foho_icp_run", "foho_icp_run_batch",
     "foho_remove_close_workspace_bytes", "foho_remove_close",
     "foho_mesh2sdf_workspace_bytes", "foho_mesh2sdf_lattice", "foho_intersection_count", "foho_mesh_decimate",
-    "foho_tc_gemm", "foho_tc_attention",
+    "foho_tc_gemm", "foho_tc_attention", "foho_tc_attention_bwd",
     "foho_dec_layernorm", "foho_dec_layernorm_bwd", "foho_dec_softmax", "foho_dec_softmax_bwd", "foho_dec_fourier_embed",
     "foho_dec_head", "foho_dec_head_bwd", "foho_dec_gather_rows", "foho_dec_cast",
     "foho_dec_rowdot", "foho_dec_gather_f32", "foho_dec_compact_workspace_bytes", "foho_dec_compact_grad",
@@ -163,6 +163,21 @@ class AttnDesc(C.Structure):
     ]
 
 
+class AttnBwdDesc(C.Structure):
+    _fields_ = [
+        ("n_img", C.c_int32), ("heads", C.c_int32), ("n_q", C.c_int32), ("n_k", C.c_int32),
+        ("max_ctas", C.c_int32), ("scale", C.c_float),
+        ("q", C.c_void_p), ("ldq", C.c_int64), ("hsq", C.c_int64),
+        ("k", C.c_void_p), ("ldk", C.c_int64), ("hsk", C.c_int64),
+        ("v", C.c_void_p), ("ldv", C.c_int64), ("hsv", C.c_int64),
+        ("d_out", C.c_void_p), ("lddo", C.c_int64), ("hsdo", C.c_int64),
+        ("lse2", C.c_void_p), ("lse2_stride", C.c_int64), ("delta", C.c_void_p), ("delta_stride", C.c_int64),
+        ("dq", C.c_void_p), ("lddq", C.c_int64), ("hsdq", C.c_int64),
+        ("dk", C.c_void_p), ("lddk", C.c_int64), ("hsdk", C.c_int64),
+        ("dv", C.c_void_p), ("lddv", C.c_int64), ("hsdv", C.c_int64),
+    ]
+
+
 class RasterDesc(C.Structure):
     _fields_ = [
         ("B", C.c_int32), ("V_total", C.c_int32), ("F_total", C.c_int32), ("H", C.c_int32), ("W", C.c_int32),
@@ -276,6 +291,8 @@ def load(build_if_missing: bool = False) -> C.CDLL:
     lib.foho_tc_gemm.argtypes = [C.POINTER(GemmDesc), C.c_void_p]
     lib.foho_tc_attention.restype = C.c_int
     lib.foho_tc_attention.argtypes = [C.POINTER(AttnDesc), C.c_void_p]
+    lib.foho_tc_attention_bwd.restype = C.c_int
+    lib.foho_tc_attention_bwd.argtypes = [C.POINTER(AttnBwdDesc), C.c_void_p]
     vp, i32, i64, f32 = C.c_void_p, C.c_int32, C.c_int64, C.c_float
     lib.foho_dec_layernorm.argtypes = [vp, i32, i64, i64, vp, vp, f32, vp, i32, i64, i64, i64, i32, vp]
     lib.foho_dec_layernorm_bwd.argtypes = [vp, i32, i64, i64, vp, f32, vp, i32, i64, i64, vp, vp, i32, i64, i64, i64, i32, vp]

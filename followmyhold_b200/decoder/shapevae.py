@@ -395,9 +395,8 @@ class LatentDecoder:
                 dkn16=torch.empty(R, HEADS, HD, **f16), dkv=torch.empty(R, 2 * WIDTH, **f16),
                 g=torch.empty(R, WIDTH, **f16), g2=torch.empty(R, WIDTH, **f16), g3=torch.empty(R, WIDTH, **f16),
                 gu=torch.empty(R, 4 * WIDTH, **f16), dqkv=torch.empty(R, 3 * WIDTH, **f16),
-                tP=torch.empty(HEADS, TOKENS, TOKENS, **f16), tdelta=torch.empty(HEADS, TOKENS, **f32),
-                tdS=torch.empty(HEADS, TOKENS, TOKENS, **f16), dqn=torch.empty(TOKENS, HEADS, HD, **f16),
-                dknl=torch.empty(TOKENS, HEADS, HD, **f16))
+                tdelta=torch.empty(B, HEADS, TOKENS, **f32), dqn=torch.empty(R, HEADS, HD, **f16),
+                dknl=torch.empty(R, HEADS, HD, **f16))
         bw = self._bw
         mc = self.active_chunk
         kvv = self.kv.view(B, TOKENS, HEADS, 2 * HD)
@@ -453,17 +452,15 @@ class LatentDecoder:
             tc.gemm(bw["gu"], lw["fc_w"], out=bw["g2"], b_mn=True, stream=stream)
             g_mid = ops.layernorm_bwd(a["x_mid"], lw["ln2_w"], bw["g2"], bw["g3"], add=g, stream=stream)
             da = tc.gemm(g_mid, lw["proj_w"], out=bw["g2"], b_mn=True, stream=stream).view(B, TOKENS, HEADS, HD)
-            qn, kn = a["qn"].view(B, TOKENS, HEADS, HD), a["kn"].view(B, TOKENS, HEADS, HD)
+            # attention adjoint, fused (k_attn_bwd): P and dS live in shared memory tiles only; dV goes straight into the
+            # v third of dqkv, dQn / dKn through the per-head LayerNorm adjoints into the q and k thirds
             for b in range(B):
-                qn_b, kn_b, v_b, da_b = hv(qn[b]), hv(kn[b]), hv(qkv[b, :, :, 2 * HD:]), hv(da[b])
-                tc.gemm(qn_b, kn_b, out=bw["tP"], alpha=0.125 * LOG2E, act=tc.ACT_EXP2_ROW, row_vec=a["lse"][b], stream=stream)
-                ops.rowdot(da[b].reshape(TOKENS, WIDTH), a["o"][b], bw["tdelta"], stream=stream)
-                tc.gemm(da_b, v_b, out=bw["tdS"], alpha=0.125, act=tc.ACT_DSOFTMAX, aux_in=bw["tP"], row_vec=bw["tdelta"], stream=stream)
-                tc.gemm(bw["tP"], da_b, out=hv(dqkv[b, :, :, 2 * HD:]), a_mn=True, b_mn=True, stream=stream)     # dV
-                tc.gemm(bw["tdS"], kn_b, out=hv(bw["dqn"]), b_mn=True, stream=stream)                           # dQn = dS Kn
-                tc.gemm(bw["tdS"], qn_b, out=hv(bw["dknl"]), a_mn=True, b_mn=True, stream=stream)               # dKn = dS^T Qn
-                ops.layernorm_bwd(qkv[b, :, :, :HD], lw["qn_w"], bw["dqn"], dqkv[b, :, :, :HD], width=HD, stream=stream)
-                ops.layernorm_bwd(qkv[b, :, :, HD:2 * HD], lw["kn_w"], bw["dknl"], dqkv[b, :, :, HD:2 * HD], width=HD, stream=stream)
+                ops.rowdot(da[b].reshape(TOKENS, WIDTH), a["o"][b], bw["tdelta"][b], stream=stream)
+            qkv_r, dqkv_r = a["qkv"].view(R, HEADS, 3 * HD), bw["dqkv"].view(R, HEADS, 3 * HD)
+            tc.attention_bwd(a["qn"].view(R, HEADS, HD), a["kn"].view(R, HEADS, HD), qkv_r[:, :, 2 * HD:], da.view(R, HEADS, HD),
+                             a["lse"], bw["tdelta"], bw["dqn"], bw["dknl"], dqkv_r[:, :, 2 * HD:], B, stream=stream)
+            ops.layernorm_bwd(qkv_r[:, :, :HD], lw["qn_w"], bw["dqn"], dqkv_r[:, :, :HD], width=HD, stream=stream)
+            ops.layernorm_bwd(qkv_r[:, :, HD:2 * HD], lw["kn_w"], bw["dknl"], dqkv_r[:, :, HD:2 * HD], width=HD, stream=stream)
             tc.gemm(bw["dqkv"], lw["qkv_w"], out=bw["g2"], b_mn=True, stream=stream)
             g = ops.layernorm_bwd(a["x_in"], lw["ln1_w"], bw["g2"], bw["g"], add=g_mid, stream=stream)
         # ---- post_kl and the 1/scale_factor of the call site

@@ -120,3 +120,35 @@ def attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, n_img: int, out
         d.lse2, d.lse2_stride = lse2.data_ptr(), lse2.stride(1)
     _lib.check("foho_tc_attention", lib.foho_tc_attention(C.byref(d), _stream_ptr(stream)))
     return out
+
+
+def attention_bwd(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, d_out: torch.Tensor, lse2: torch.Tensor, delta: torch.Tensor,
+                  dq: torch.Tensor, dk: torch.Tensor, dv: torch.Tensor, n_img: int, *, scale: float = 0.125, max_ctas: int = 0,
+                  stream: Optional[torch.cuda.Stream] = None) -> None:
+    """The adjoint of ``attention`` without a score matrix in memory (``foho_tc_attention_bwd``).
+
+    ``q``, ``d_out``, ``dq``: [n_img*n_q, heads, 64]; ``k``, ``v``, ``dk``, ``dv``: [n_img*n_k, heads, 64] -- float16 views with a
+    contiguous last dimension; ``lse2``, ``delta``: float32 [n_img, heads, n_q] (``lse2`` as ``attention`` wrote it,
+    ``delta[i, h, q] = d_out[q, h] . out[q, h]``)."""
+    lib = _lib.load()
+    for t in (q, k, v, d_out, dq, dk, dv):
+        if t.dtype != torch.float16 or not t.is_cuda or t.dim() != 3 or t.shape[2] != 64 or t.stride(2) != 1:
+            raise ValueError("q, k, v, d_out, dq, dk, dv must be CUDA float16 [rows, heads, 64] views with a contiguous last dimension")
+    heads = q.shape[1]
+    n_q, n_k = q.shape[0] // n_img, k.shape[0] // n_img
+    for t in (lse2, delta):
+        if t.dtype != torch.float32 or t.shape != (n_img, heads, n_q) or t.stride(2) != 1 or \
+                (n_img > 1 and t.stride(0) != heads * t.stride(1)):
+            raise ValueError("lse2 / delta must be float32 [n_img, heads, n_q] views with uniform head stride")
+    d = _lib.AttnBwdDesc()
+    d.n_img, d.heads, d.n_q, d.n_k, d.max_ctas, d.scale = n_img, heads, n_q, n_k, max_ctas, scale
+    d.q, d.ldq, d.hsq = q.data_ptr(), q.stride(0), q.stride(1)
+    d.k, d.ldk, d.hsk = k.data_ptr(), k.stride(0), k.stride(1)
+    d.v, d.ldv, d.hsv = v.data_ptr(), v.stride(0), v.stride(1)
+    d.d_out, d.lddo, d.hsdo = d_out.data_ptr(), d_out.stride(0), d_out.stride(1)
+    d.lse2, d.lse2_stride = lse2.data_ptr(), lse2.stride(1)
+    d.delta, d.delta_stride = delta.data_ptr(), delta.stride(1)
+    d.dq, d.lddq, d.hsdq = dq.data_ptr(), dq.stride(0), dq.stride(1)
+    d.dk, d.lddk, d.hsdk = dk.data_ptr(), dk.stride(0), dk.stride(1)
+    d.dv, d.lddv, d.hsdv = dv.data_ptr(), dv.stride(0), dv.stride(1)
+    _lib.check("foho_tc_attention_bwd", lib.foho_tc_attention_bwd(C.byref(d), _stream_ptr(stream)))

@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define FOHO_ABI_VERSION 6
+#define FOHO_ABI_VERSION 7
 
 #define FOHO_OK 0
 #define FOHO_E_NULL (-1)      /* required pointer is NULL            */
@@ -370,6 +370,29 @@ typedef struct foho_attn_desc {
   int64_t lse2_stride;       /* 0 = n_q; larger when a chunk of queries writes into the rows of a longer table */
 } foho_attn_desc;
 int foho_tc_attention(const foho_attn_desc *desc, void *cuda_stream);
+
+/* The adjoint of the attention above, fused (no score matrix in memory): what autograd runs for `loss.backward()`
+ * through the transformer's self attention and the geo_decoder's cross attention (pipelines.py:1590-1600 -> :299,304).
+ *     P = exp2(scale log2(e) Q K^T - lse2)    dS = P o (dO V^T - delta)
+ *     dV = P^T dO    dK = scale dS^T Q    dQ = scale dS K
+ * q, d_out hold n_img*n_q rows, k, v hold n_img*n_k rows (fp16 row-major, leading dimension ld*, head h at column
+ * h*hs*); lse2 as written by foho_tc_attention, delta[i][h][q] = d_out[q][h] . out[q][h] (foho_dec_rowdot); dq, dk,
+ * dv are fp16 views of the same form (16-byte aligned).  n_k must be a multiple of 128.  Deterministic (no atomics). */
+typedef struct foho_attn_bwd_desc {
+  int32_t n_img, heads, n_q, n_k;
+  int32_t max_ctas;          /* 0 = one persistent CTA per SM */
+  float scale;
+  const void *q; int64_t ldq, hsq;
+  const void *k; int64_t ldk, hsk;
+  const void *v; int64_t ldv, hsv;
+  const void *d_out; int64_t lddo, hsdo;
+  const float *lse2; int64_t lse2_stride;     /* [n_img][heads][lse2_stride], 0 = n_q */
+  const float *delta; int64_t delta_stride;   /* [n_img][heads][delta_stride], 0 = n_q */
+  void *dq; int64_t lddq, hsdq;
+  void *dk; int64_t lddk, hsdk;
+  void *dv; int64_t lddv, hsdv;
+} foho_attn_bwd_desc;
+int foho_tc_attention_bwd(const foho_attn_bwd_desc *desc, void *cuda_stream);
 
 /* Row-wise kernels of the decoder (HBM-bound; fp16 activations, fp32 arithmetic; every pointer device memory).
  * A "row view" addresses row r of a [outer, inner, width] tensor at base + (r / inner)*ldo + (r % inner)*ldi
