@@ -313,7 +313,7 @@ def load(build_if_missing: bool = False) -> C.CDLL:
     lib.foho_raster_workspace_bytes.restype = C.c_size_t
     lib.foho_raster_losses_fwd_bwd.argtypes = [C.POINTER(RasterDesc), vp]
     lib.foho_raster_losses_fwd_bwd.restype = C.c_int
-    lib.foho_dec_rowdot.argtypes = [vp, i64, vp, i64, vp, i64, i32, vp]
+    lib.foho_dec_rowdot.argtypes = [vp, i64, vp, i64, vp, i64, i64, i32, vp]
     lib.foho_dec_rowdot.restype = C.c_int
     lib.foho_dec_gather_f32.argtypes = [vp, i64, vp, vp, i64, i32, vp]
     lib.foho_dec_gather_f32.restype = C.c_int

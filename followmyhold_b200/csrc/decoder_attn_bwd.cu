@@ -90,7 +90,7 @@ k_attn_bwd(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUte
   uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(y_empty + Y_STAGES);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int n_items = p.n_img * p.heads * (p.k_tiles + p.q_tiles);
+  const int n_items = p.n_img * p.heads * (p.k_tiles + (p.dq ? p.q_tiles : 0));
 
   if (warp == 0 && lane == 0) {
     tc::tma_prefetch_desc(&tmQ); tc::tma_prefetch_desc(&tmK); tc::tma_prefetch_desc(&tmV); tc::tma_prefetch_desc(&tmdO);
@@ -303,7 +303,7 @@ k_attn_bwd(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUte
 }  // namespace
 
 extern "C" int foho_tc_attention_bwd(const foho_attn_bwd_desc *d, void *cuda_stream) {
-  if (!d || !d->q || !d->k || !d->v || !d->d_out || !d->lse2 || !d->delta || !d->dq || !d->dk || !d->dv) return FOHO_E_NULL;
+  if (!d || !d->q || !d->k || !d->v || !d->d_out || !d->lse2 || !d->delta || !d->dk || !d->dv) return FOHO_E_NULL;
   if (d->n_img <= 0 || d->heads <= 0 || d->n_q <= 0 || d->n_k <= 0 || d->n_k % BT) return FOHO_E_SHAPE;
   if (d->ldq % 8 || d->ldk % 8 || d->ldv % 8 || d->lddo % 8 || d->hsq % 8 || d->hsk % 8 || d->hsv % 8 || d->hsdo % 8) return FOHO_E_ARG;
   if (d->lddq % 8 || d->lddk % 8 || d->lddv % 8 || d->hsdq % 8 || d->hsdk % 8 || d->hsdv % 8) return FOHO_E_ARG;
@@ -330,7 +330,7 @@ extern "C" int foho_tc_attention_bwd(const foho_attn_bwd_desc *d, void *cuda_str
     FOHO_CUDA_TRY(cudaGetDevice(&dev));
     FOHO_CUDA_TRY(cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev));
   }
-  const long long items = (long long)p.n_img * p.heads * (p.k_tiles + p.q_tiles);
+  const long long items = (long long)p.n_img * p.heads * (p.k_tiles + (p.dq ? p.q_tiles : 0));
   p.dbg = 0;
   int grid = (int)(items < sm_count ? items : sm_count);
   if (d->max_ctas > 0 && grid > d->max_ctas) grid = d->max_ctas;

@@ -443,7 +443,7 @@ __global__ void k_nz_scatter(const float *__restrict__ g, long long V, int nblk,
 
 // delta[h][r] = <a[r][h][:], b[r][h][:]>, 64 channels: 8 lanes per (row, head), one 16-byte load each
 __global__ void k_rowdot(const __half *__restrict__ a, long long lda, const __half *__restrict__ b, long long ldb, float *__restrict__ out,
-                         long long rows, int heads) {
+                         long long out_head_stride, long long rows, int heads) {
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   const long long pair = i >> 3;
   const int sub = (int)(i & 7);
@@ -459,7 +459,7 @@ __global__ void k_rowdot(const __half *__restrict__ a, long long lda, const __ha
     for (int t = 0; t < 4; ++t) { float2 x = __half22float2(ha[t]), y = __half22float2(hb[t]); acc += x.x * y.x + x.y * y.y; }
   }
   acc += __shfl_xor_sync(0xffffffffu, acc, 1); acc += __shfl_xor_sync(0xffffffffu, acc, 2); acc += __shfl_xor_sync(0xffffffffu, acc, 4);
-  if (live && sub == 0) out[(long long)h * rows + r] = acc;
+  if (live && sub == 0) out[(long long)h * out_head_stride + r] = acc;
 }
 __global__ void k_gather_f32(const float *__restrict__ src, long long hs, const int *__restrict__ idx, float *__restrict__ out, long long n,
                              int heads) {
@@ -602,12 +602,12 @@ extern "C" int foho_dec_compact_grad(const float *g, int32_t B, int64_t V, int32
   return 0;
 }
 
-extern "C" int foho_dec_rowdot(const void *a, int64_t lda, const void *b, int64_t ldb, float *out, int64_t rows, int32_t heads,
-                               void *cuda_stream) {
+extern "C" int foho_dec_rowdot(const void *a, int64_t lda, const void *b, int64_t ldb, float *out, int64_t out_head_stride, int64_t rows,
+                               int32_t heads, void *cuda_stream) {
   if (!a || !b || !out) return FOHO_E_NULL;
-  if (rows <= 0 || heads <= 0 || lda % 8 || ldb % 8) return FOHO_E_SHAPE;
-  k_rowdot<<<blocks_for(rows * heads * 8, 256), 256, 0, reinterpret_cast<cudaStream_t>(cuda_stream)>>>((const __half *)a, lda, (const __half *)b,
-                                                                                                        ldb, out, rows, heads);
+  if (rows <= 0 || heads <= 0 || lda % 8 || ldb % 8 || (out_head_stride != 0 && out_head_stride < rows)) return FOHO_E_SHAPE;
+  k_rowdot<<<blocks_for(rows * heads * 8, 256), 256, 0, reinterpret_cast<cudaStream_t>(cuda_stream)>>>(
+      (const __half *)a, lda, (const __half *)b, ldb, out, out_head_stride ? out_head_stride : rows, rows, heads);
   FOHO_LAUNCH_CHECK();
   return 0;
 }

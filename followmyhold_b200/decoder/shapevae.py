@@ -107,9 +107,12 @@ class _Ops:
         return out
 
     def rowdot(self, a, b, out, heads=HEADS, stream=None):
-        """out[h, r] = <a[r, h, :], b[r, h, :]> (float32 [heads, rows]): rowsum(dO o O) of the attention backward."""
+        """out[h, r] = <a[r, h, :], b[r, h, :]> (float32 [heads, rows] view, e.g. a column slice of a longer table):
+        rowsum(dO o O) of the attention backward."""
+        if out.dim() != 2 or out.shape != (heads, a.shape[0]) or out.stride(1) != 1:
+            raise ValueError("out must be a float32 [heads, rows] view with contiguous rows")
         _lib.check("foho_dec_rowdot", self.lib.foho_dec_rowdot(a.data_ptr(), a.stride(0), b.data_ptr(), b.stride(0), out.data_ptr(),
-                                                               a.shape[0], heads, _sp(stream)))
+                                                               out.stride(0), a.shape[0], heads, _sp(stream)))
         return out
 
     def gather_f32(self, src, idx, out, stream=None):
@@ -384,14 +387,10 @@ class LatentDecoder:
         if not hasattr(self, "_bw"):
             mc = self.active_chunk
             self._bw = dict(
-                qn=torch.empty(mc, HEADS, HD, **f16), x0=torch.empty(mc, WIDTH, **f16), lse=torch.empty(HEADS, mc, **f32),
-                delta=torch.empty(HEADS, mc, **f32),
-                P=torch.empty(HEADS, mc, TOKENS, **f16), dS=torch.empty(HEADS, mc, TOKENS, **f16), a=torch.empty(mc, WIDTH, **f16),
+                x0=torch.empty(mc, WIDTH, **f16), a=torch.empty(mc, WIDTH, **f16),
                 x=torch.empty(mc, WIDTH, **f16), h=torch.empty(mc, WIDTH, **f16), u=torch.empty(mc, 4 * WIDTH, **f16),
                 u_pre=torch.empty(mc, 4 * WIDTH, **f16), y=torch.empty(mc, WIDTH, **f16), dy=torch.empty(mc, WIDTH, **f16),
                 du=torch.empty(mc, 4 * WIDTH, **f16), dh=torch.empty(mc, WIDTH, **f16), dx=torch.empty(mc, WIDTH, **f16),
-                da=torch.empty(mc, WIDTH, **f16),
-                dkn32=torch.empty(B, TOKENS, WIDTH, **f32), dv32=torch.empty(B, TOKENS, WIDTH, **f32),
                 dkn16=torch.empty(R, HEADS, HD, **f16), dkv=torch.empty(R, 2 * WIDTH, **f16),
                 g=torch.empty(R, WIDTH, **f16), g2=torch.empty(R, WIDTH, **f16), g3=torch.empty(R, WIDTH, **f16),
                 gu=torch.empty(R, 4 * WIDTH, **f16), dqkv=torch.empty(R, 3 * WIDTH, **f16),
@@ -399,25 +398,26 @@ class LatentDecoder:
                 dknl=torch.empty(R, HEADS, HD, **f16))
         bw = self._bw
         mc = self.active_chunk
+        if getattr(self, "_bwq_M", None) != M:
+            # everything the fused attention adjoint needs of the M active lattice points of every image, kept over the chunks
+            self._bwq = dict(qa=torch.empty(B * M, HEADS, HD, **f16), da=torch.empty(B * M, WIDTH, **f16),
+                             lse=torch.empty(B, HEADS, M, **f32), delta=torch.empty(B, HEADS, M, **f32))
+            self._bwq_M = M
+        bq = self._bwq
         kvv = self.kv.view(B, TOKENS, HEADS, 2 * HD)
         kvn = self.kvn.view(B, TOKENS, HEADS, HD)
-        bw["dkn32"].zero_(); bw["dv32"].zero_()
-        hv = lambda t: t.permute(1, 0, 2)                                # [rows, heads, 64] -> [heads, rows, 64] view
-        # ---- query side: recompute the rows that carry a gradient, then walk back to dK, dV
+        # ---- query side: recompute the rows that carry a gradient (flash attention forward, then the MLP block), walk
+        #      back to dA; the attention adjoint of all of them runs once at the end (dK, dV only: the lattice queries
+        #      do not depend on the latents)
         for b in range(B):
-            kn_b, v_b = hv(kvn[b]), hv(kvv[b, :, :, HD:])
-            dkn_b, dv_b = hv(bw["dkn32"][b].view(TOKENS, HEADS, HD)), hv(bw["dv32"][b].view(TOKENS, HEADS, HD))
             for s in range(0, M, mc):
                 n = min(mc, M - s)
                 ix = idx[b, s:s + n]
-                qn_a = ops.gather(self.qn.view(self.Nq, WIDTH), ix, bw["qn"].view(mc, WIDTH)[:n], stream=stream).view(n, HEADS, HD)
+                r0 = b * M + s
+                qn_a = ops.gather(self.qn.view(self.Nq, WIDTH), ix, bq["qa"].view(B * M, WIDTH)[r0:r0 + n], stream=stream).view(n, HEADS, HD)
                 x0_a = ops.gather(self.x0, ix, bw["x0"][:n], stream=stream)
-                P, dS = (bw[k].view(-1)[:HEADS * n * TOKENS].view(HEADS, n, TOKENS) for k in ("P", "dS"))
-                lse_a = ops.gather_f32(self.q_lse[b], ix, bw["lse"].view(-1)[:HEADS * n].view(HEADS, n), stream=stream)
-                # P = exp2(log2(e)/8 * Qn Kn^T - lse2) straight out of the score product's epilogue: no float32 scores in HBM
-                tc.gemm(hv(qn_a), kn_b, out=P, alpha=0.125 * LOG2E, act=tc.ACT_EXP2_ROW, row_vec=lse_a, stream=stream)
                 a = bw["a"][:n]
-                tc.gemm(P, v_b, out=hv(a.view(n, HEADS, HD)), b_mn=True, stream=stream)
+                tc.attention(qn_a, kvn[b], kvv[b, :, :, HD:], 1, out=a.view(1, n, WIDTH), lse2=bq["lse"][b:b + 1, :, s:s + n], stream=stream)
                 x = tc.gemm(a, xw["proj_w"], out=bw["x"][:n], bias=xw["proj_b"], res=x0_a, stream=stream)
                 ops.layernorm(x, xw["ln3_w"], xw["ln3_b"], bw["h"][:n], stream=stream)
                 tc.gemm(bw["h"][:n], xw["fc_w"], out=bw["u"][:n], bias=xw["fc_b"], act=tc.ACT_GELU, aux_out=bw["u_pre"][:n], stream=stream)
@@ -427,20 +427,15 @@ class LatentDecoder:
                 tc.gemm(dy, xw["fc2_w"], out=bw["du"][:n], b_mn=True, act=tc.ACT_DGELU, aux_in=bw["u_pre"][:n], stream=stream)
                 tc.gemm(bw["du"][:n], xw["fc_w"], out=bw["dh"][:n], b_mn=True, stream=stream)
                 dx = ops.layernorm_bwd(x, xw["ln3_w"], bw["dh"][:n], bw["dx"][:n], add=dy, stream=stream)
-                da = tc.gemm(dx, xw["proj_w"], out=bw["da"][:n], b_mn=True, stream=stream)
-                da_h = hv(da.view(n, HEADS, HD))
-                # attention backward, heads batched: dS = P o (dA V^T - rowsum(dA o A)) / 8 in the product's epilogue;
-                # dV += P^T dA ; dKn += dS^T Qn
-                delta = ops.rowdot(da, a, bw["delta"].view(-1)[:HEADS * n].view(HEADS, n), stream=stream)
-                tc.gemm(da_h, v_b, out=dS, alpha=0.125, act=tc.ACT_DSOFTMAX, aux_in=P, row_vec=delta, stream=stream)
-                tc.gemm(P, da_h, out=dv_b, res=dv_b, a_mn=True, b_mn=True, stream=stream)
-                tc.gemm(dS, hv(qn_a), out=dkn_b, res=dkn_b, a_mn=True, b_mn=True, stream=stream)
-        # ---- K/V gradients -> token gradient d(data)
-        ops.cast(bw["dkn32"].view(R, WIDTH), bw["dkn16"].view(R, WIDTH), stream=stream)
+                da = tc.gemm(dx, xw["proj_w"], out=bq["da"][r0:r0 + n], b_mn=True, stream=stream)
+                ops.rowdot(da, a, bq["delta"][b][:, s:s + n], stream=stream)
+        # ---- attention adjoint (fused, k_attn_bwd): dV into the v half of dkv, dKn through the per-head LayerNorm adjoint
+        #      into the k half
         dkv = bw["dkv"].view(R, HEADS, 2 * HD)
-        ops.layernorm_bwd(self.kv.view(R, HEADS, 2 * HD)[:, :, :HD], xw["kn_w"], bw["dkn16"], dkv[:, :, :HD], width=HD, stream=stream)
-        for hh in range(HEADS):      # dV (fp32, [tokens, heads*64]) -> the v half of dkv
-            ops.cast(bw["dv32"].view(R, WIDTH)[:, hh * HD:(hh + 1) * HD], bw["dkv"][:, hh * 2 * HD + HD:(hh + 1) * 2 * HD], stream=stream)
+        kv_r = self.kv.view(R, HEADS, 2 * HD)
+        tc.attention_bwd(bq["qa"], self.kvn.view(R, HEADS, HD), kv_r[:, :, HD:], bq["da"].view(B * M, HEADS, HD), bq["lse"], bq["delta"],
+                         None, bw["dkn16"], dkv[:, :, HD:], B, stream=stream)
+        ops.layernorm_bwd(kv_r[:, :, :HD], xw["kn_w"], bw["dkn16"], dkv[:, :, :HD], width=HD, stream=stream)
         tc.gemm(bw["dkv"], xw["kv_w"], out=bw["g2"], b_mn=True, stream=stream)
         g = ops.layernorm_bwd(self.data, xw["ln2_w"], bw["g2"], bw["g"], stream=stream)     # d(data)
         # ---- token transformer, last layer first

@@ -123,15 +123,17 @@ def attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, n_img: int, out
 
 
 def attention_bwd(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, d_out: torch.Tensor, lse2: torch.Tensor, delta: torch.Tensor,
-                  dq: torch.Tensor, dk: torch.Tensor, dv: torch.Tensor, n_img: int, *, scale: float = 0.125, max_ctas: int = 0,
+                  dq: Optional[torch.Tensor], dk: torch.Tensor, dv: torch.Tensor, n_img: int, *, scale: float = 0.125, max_ctas: int = 0,
                   stream: Optional[torch.cuda.Stream] = None) -> None:
     """The adjoint of ``attention`` without a score matrix in memory (``foho_tc_attention_bwd``).
 
     ``q``, ``d_out``, ``dq``: [n_img*n_q, heads, 64]; ``k``, ``v``, ``dk``, ``dv``: [n_img*n_k, heads, 64] -- float16 views with a
     contiguous last dimension; ``lse2``, ``delta``: float32 [n_img, heads, n_q] (``lse2`` as ``attention`` wrote it,
-    ``delta[i, h, q] = d_out[q, h] . out[q, h]``)."""
+    ``delta[i, h, q] = d_out[q, h] . out[q, h]``).  ``dq=None`` skips the query gradient (cross attention of the lattice)."""
     lib = _lib.load()
     for t in (q, k, v, d_out, dq, dk, dv):
+        if t is None:
+            continue
         if t.dtype != torch.float16 or not t.is_cuda or t.dim() != 3 or t.shape[2] != 64 or t.stride(2) != 1:
             raise ValueError("q, k, v, d_out, dq, dk, dv must be CUDA float16 [rows, heads, 64] views with a contiguous last dimension")
     heads = q.shape[1]
@@ -148,7 +150,8 @@ def attention_bwd(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, d_out: torc
     d.d_out, d.lddo, d.hsdo = d_out.data_ptr(), d_out.stride(0), d_out.stride(1)
     d.lse2, d.lse2_stride = lse2.data_ptr(), lse2.stride(1)
     d.delta, d.delta_stride = delta.data_ptr(), delta.stride(1)
-    d.dq, d.lddq, d.hsdq = dq.data_ptr(), dq.stride(0), dq.stride(1)
+    if dq is not None:
+        d.dq, d.lddq, d.hsdq = dq.data_ptr(), dq.stride(0), dq.stride(1)
     d.dk, d.lddk, d.hsdk = dk.data_ptr(), dk.stride(0), dk.stride(1)
     d.dv, d.lddv, d.hsdv = dv.data_ptr(), dv.stride(0), dv.stride(1)
     _lib.check("foho_tc_attention_bwd", lib.foho_tc_attention_bwd(C.byref(d), _stream_ptr(stream)))

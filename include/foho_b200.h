@@ -377,7 +377,8 @@ int foho_tc_attention(const foho_attn_desc *desc, void *cuda_stream);
  *     dV = P^T dO    dK = scale dS^T Q    dQ = scale dS K
  * q, d_out hold n_img*n_q rows, k, v hold n_img*n_k rows (fp16 row-major, leading dimension ld*, head h at column
  * h*hs*); lse2 as written by foho_tc_attention, delta[i][h][q] = d_out[q][h] . out[q][h] (foho_dec_rowdot); dq, dk,
- * dv are fp16 views of the same form (16-byte aligned).  n_k must be a multiple of 128.  Deterministic (no atomics). */
+ * dv are fp16 views of the same form (16-byte aligned); dq may be NULL (the lattice queries of the cross attention do
+ * not depend on the latents: their work items are skipped).  n_k must be a multiple of 128.  Deterministic (no atomics). */
 typedef struct foho_attn_bwd_desc {
   int32_t n_img, heads, n_q, n_k;
   int32_t max_ctas;          /* 0 = one persistent CTA per SM */
@@ -424,8 +425,10 @@ int foho_dec_cast(const void *in, int64_t ld_in, void *out, int64_t ld_out, int6
                   void *cuda_stream);
 
 /* delta[h][r] = sum_d a[r][h][d] * b[r][h][d] (64 channels per head; a, b fp16 [rows, heads*64] with leading dimensions lda,
- * ldb): the rowsum(dO o O) of the attention backward.  out float32 [heads, rows]. */
-int foho_dec_rowdot(const void *a, int64_t lda, const void *b, int64_t ldb, float *out, int64_t rows, int32_t heads, void *cuda_stream);
+ * ldb): the rowsum(dO o O) of the attention backward.  out float32, head h at out + h*out_head_stride (0 = rows: a dense
+ * [heads, rows] table; larger when a chunk of rows writes into the columns of a longer table). */
+int foho_dec_rowdot(const void *a, int64_t lda, const void *b, int64_t ldb, float *out, int64_t out_head_stride, int64_t rows,
+                    int32_t heads, void *cuda_stream);
 /* out[h][i] = src[h * src_head_stride + idx[i]] (float32): per-head gather of saved log-sum-exps for the active rows */
 int foho_dec_gather_f32(const float *src, int64_t src_head_stride, const int32_t *idx, float *out, int64_t n, int32_t heads,
                         void *cuda_stream);
