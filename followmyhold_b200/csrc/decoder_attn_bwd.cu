@@ -29,10 +29,10 @@ namespace {
 
 constexpr int BT = 128;                    // rows of a tile (queries or keys)
 constexpr int HD = 64;                     // head dimension
-constexpr int Y_STAGES = 2;
 constexpr int TILE_BYTES = BT * HD * 2;    // 16 KB
 constexpr int PD_BYTES = BT * BT * 2;      // 32 KB
-constexpr int BWD_SMEM = 2 * TILE_BYTES + Y_STAGES * 2 * TILE_BYTES + 2 * 2 * PD_BYTES + 1024 + 256;
+// F1, F2 | streamed stages | P / dS buffers: 2 buffers leave room for 2 stages, 1 buffer for 4 (both 224 KB)
+constexpr int BWD_SMEM = 2 * TILE_BYTES + 2 * 2 * TILE_BYTES + 2 * 2 * PD_BYTES + 1024 + 256;
 static_assert(BWD_SMEM <= 232448, "shared memory of k_attn_bwd");
 constexpr uint32_t TB_T1 = 0, TB_T2 = 128, TB_A = 256, TB_B = 320, TB_COLS = 512;
 
@@ -74,16 +74,20 @@ __device__ __forceinline__ float ex2a(float x) {
   return y;
 }
 
-template <int NG>      // element-wise warpgroups: each takes 128 / NG columns of the tile (2: 384 threads, 4: 640 threads)
+// NG element-wise warpgroups: each takes 128 / NG columns of the tile (2: 384 threads, 4: 640 threads); PDB buffers of the
+// P / dS tiles (1: the tile is written after the products of the previous block have read it, four stages of streamed
+// operands; 2: two stages)
+template <int NG, int PDB>
 __global__ void __launch_bounds__(128 + 128 * NG, 1)
 k_attn_bwd(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK, const __grid_constant__ CUtensorMap tmV,
            const __grid_constant__ CUtensorMap tmdO, const BwdParams p) {
+  constexpr int Y_STAGES = PDB == 2 ? 2 : 4;
   extern __shared__ uint8_t smem_raw[];
   uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t *sF = smem;                                        // F1, F2
   uint8_t *sY = sF + 2 * TILE_BYTES;                         // stage s: Y1 at s*2*TILE, Y2 right after
   uint8_t *sPD = sY + Y_STAGES * 2 * TILE_BYTES;             // buffer u: P tile (kind 0) at u*2*PD, dS tile right after
-  uint64_t *bars = reinterpret_cast<uint64_t *>(sPD + 2 * 2 * PD_BYTES);
+  uint64_t *bars = reinterpret_cast<uint64_t *>(sPD + PDB * 2 * PD_BYTES);
   uint64_t *f_full = bars, *f_empty = bars + 1, *t_full = bars + 2, *t_empty = bars + 3, *acc_full = bars + 4, *acc_empty = bars + 5;
   uint64_t *pd_full = bars + 6, *pd_empty = bars + 8;
   uint64_t *y_full = bars + 10, *y_empty = y_full + Y_STAGES;
@@ -98,7 +102,7 @@ k_attn_bwd(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUte
   if (warp == 1 && lane == 0) {
     tc::mbar_init(f_full, 1); tc::mbar_init(f_empty, 1);
     tc::mbar_init(t_full, 1); tc::mbar_init(t_empty, 128 * NG);
-    for (int i = 0; i < 2; ++i) { tc::mbar_init(&pd_full[i], 128 * NG); tc::mbar_init(&pd_empty[i], 1); }
+    for (int i = 0; i < PDB; ++i) { tc::mbar_init(&pd_full[i], 128 * NG); tc::mbar_init(&pd_empty[i], 1); }
     tc::mbar_init(acc_full, 1); tc::mbar_init(acc_empty, 128 * NG);
     for (int i = 0; i < Y_STAGES; ++i) { tc::mbar_init(&y_full[i], 1); tc::mbar_init(&y_empty[i], 1); }
     tc::fence_barrier_init();
@@ -165,8 +169,8 @@ k_attn_bwd(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUte
         for (int s = 0; s < it.nsteps; ++s, ++g) {
           if (s + 1 < it.nsteps) issue_t(g + 1, it.kind);
           else tc::mma_commit(f_empty);                       // every product that reads the fixed tiles has been issued
-          const uint32_t st = g % Y_STAGES, u = g & 1;
-          tc::mbar_wait(&pd_full[u], (g >> 1) & 1);
+          const uint32_t st = g % Y_STAGES, u = PDB == 2 ? (g & 1) : 0, pph = PDB == 2 ? ((g >> 1) & 1) : (g & 1);
+          tc::mbar_wait(&pd_full[u], pph);
           if (s == 0) tc::mbar_wait(acc_empty, (w & 1) ^ 1);
           tc::tc_fence_after();
           const uint32_t y_addr = tc::smem_u32(sY + st * 2 * TILE_BYTES);
@@ -224,7 +228,7 @@ k_attn_bwd(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUte
           lse_n = INFINITY; dl_n = 0.f;
           if (s + 1 < it.nsteps && qn < p.n_q) { lse_n = __ldg(lse_p + qn); dl_n = __ldg(dl_p + qn); }
         }
-        const uint32_t u = g & 1;
+        const uint32_t u = PDB == 2 ? (g & 1) : 0, pph = PDB == 2 ? ((g >> 1) & 1) : (g & 1);
         tc::mbar_wait(t_full, g & 1);
         tc::tc_fence_after();
         uint32_t a[COLS / 32][32], b[COLS / 32][32];
@@ -233,13 +237,12 @@ k_attn_bwd(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUte
         tc::tmem_ld_wait();
         tc::tc_fence_before();
         tc::mbar_arrive(t_empty);
-        tc::mbar_wait(&pd_empty[u], ((g >> 1) & 1) ^ 1);       // the products of two blocks ago have read this buffer
         const uint32_t p_row = pd_row + u * 2 * PD_BYTES, d_row = p_row + PD_BYTES;
         const float neg_l = -lse_r;
-        if (!(p.dbg & 1))
+        // values first (in place: a <- packed P, b <- packed dS), then the wait for the buffer, then the stores: the
+        // products of the previous block run while this block's exponentials do
 #pragma unroll
         for (int cc = 0; cc < COLS / 8; ++cc) {                // 16-byte chunk: columns grp*COLS + 8cc .. +7
-          uint32_t pk[4], dk[4];
 #pragma unroll
           for (int t = 0; t < 4; ++t) {
             const int e = (cc & 3) * 8 + 2 * t;
@@ -247,13 +250,21 @@ k_attn_bwd(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUte
             const float p1 = ex2a(fmaf(__uint_as_float(a[cc >> 2][e + 1]), p.scale_log2, neg_l));
             const float s0 = p0 * (__uint_as_float(b[cc >> 2][e]) - dl_r), s1 = p1 * (__uint_as_float(b[cc >> 2][e + 1]) - dl_r);
             const __half2 hp = __floats2half2_rn(p0, p1), hs = __floats2half2_rn(s0, s1);
-            pk[t] = *reinterpret_cast<const uint32_t *>(&hp);
-            dk[t] = *reinterpret_cast<const uint32_t *>(&hs);
+            a[cc >> 2][(cc & 3) * 8 + t] = *reinterpret_cast<const uint32_t *>(&hp);      // slot 8(cc&3)+t <= e: already consumed
+            b[cc >> 2][(cc & 3) * 8 + t] = *reinterpret_cast<const uint32_t *>(&hs);
           }
+        }
+        tc::mbar_wait(&pd_empty[u], pph ^ 1);                  // the products that read this buffer are done
+        if (!(p.dbg & 1))
+#pragma unroll
+        for (int cc = 0; cc < COLS / 8; ++cc) {
+          const int o = (cc & 3) * 8;
           const uint32_t off = (uint32_t)(((chunk0 + cc) ^ (row & 7)) << 4);
-          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(d_row + off), "r"(dk[0]), "r"(dk[1]), "r"(dk[2]), "r"(dk[3]) : "memory");
+          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(d_row + off), "r"(b[cc >> 2][o]), "r"(b[cc >> 2][o + 1]),
+                       "r"(b[cc >> 2][o + 2]), "r"(b[cc >> 2][o + 3]) : "memory");
           if (it.kind == 0)
-            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(p_row + off), "r"(pk[0]), "r"(pk[1]), "r"(pk[2]), "r"(pk[3]) : "memory");
+            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(p_row + off), "r"(a[cc >> 2][o]), "r"(a[cc >> 2][o + 1]),
+                         "r"(a[cc >> 2][o + 2]), "r"(a[cc >> 2][o + 3]) : "memory");
         }
         tc::fence_proxy_async_smem();
         tc::tc_fence_before();
@@ -334,21 +345,25 @@ extern "C" int foho_tc_attention_bwd(const foho_attn_bwd_desc *d, void *cuda_str
   p.dbg = 0;
   int grid = (int)(items < sm_count ? items : sm_count);
   if (d->max_ctas > 0 && grid > d->max_ctas) grid = d->max_ctas;
-  static int ng = 0, dbg = 0;
-  if (!ng) {
+  static int mode = 0, dbg = 0;
+  if (!mode) {
     const char *db = getenv("FOHO_ATTN_BWD_DBG");
     dbg = db ? atoi(db) : 0;
-    const char *e = getenv("FOHO_ATTN_BWD_GROUPS");       // measurement switch: 2 = 256 element-wise threads, 4 = 512 (default)
-    ng = e && atoi(e) == 2 ? 2 : 4;
+    const char *e = getenv("FOHO_ATTN_BWD_VARIANT");      // measurement switch: <element-wise warpgroups><tile buffers>: 21, 22, 41 (default), 42
+    mode = e ? atoi(e) : 41;
+    if (mode != 21 && mode != 22 && mode != 42) mode = 41;
   }
   p.dbg = dbg;
-  if (ng == 2) {
-    FOHO_CUDA_TRY(cudaFuncSetAttribute(k_attn_bwd<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, BWD_SMEM));
-    k_attn_bwd<2><<<grid, 384, BWD_SMEM, st>>>(tmQ, tmK, tmV, tmdO, p);
-  } else {
-    FOHO_CUDA_TRY(cudaFuncSetAttribute(k_attn_bwd<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, BWD_SMEM));
-    k_attn_bwd<4><<<grid, 640, BWD_SMEM, st>>>(tmQ, tmK, tmV, tmdO, p);
-  }
+#define FOHO_BWD_LAUNCH(NG, PDB)                                                                                              \
+  do {                                                                                                                        \
+    FOHO_CUDA_TRY(cudaFuncSetAttribute(k_attn_bwd<NG, PDB>, cudaFuncAttributeMaxDynamicSharedMemorySize, BWD_SMEM));          \
+    k_attn_bwd<NG, PDB><<<grid, 128 + 128 * NG, BWD_SMEM, st>>>(tmQ, tmK, tmV, tmdO, p);                                      \
+  } while (0)
+  if (mode == 21) FOHO_BWD_LAUNCH(2, 1);
+  else if (mode == 22) FOHO_BWD_LAUNCH(2, 2);
+  else if (mode == 42) FOHO_BWD_LAUNCH(4, 2);
+  else FOHO_BWD_LAUNCH(4, 1);
+#undef FOHO_BWD_LAUNCH
   FOHO_LAUNCH_CHECK();
   return 0;
 }

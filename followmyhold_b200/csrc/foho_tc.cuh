@@ -149,13 +149,14 @@ __device__ __forceinline__ uint64_t smem_desc_sw128(uint32_t saddr, uint32_t lbo
   d |= 2ull << 61;
   return d;
 }
-// Instruction descriptor for kind::f16, fp16 operands, fp32 accumulation:
-//   [4,6) D format = 1 (f32), [7,10) A format = 0 (f16), [10,13) B format = 0 (f16), bit 15 A major (1 = MN),
+// Instruction descriptor for kind::f16, 16-bit operands, fp32 accumulation:
+//   [4,6) D format = 1 (f32), [7,10) A format (0 = f16, 1 = bf16), [10,13) B format (a bf16 A with an fp16 B traps: measured),
+//   bit 15 A major (1 = MN),
 //   bit 16 B major (1 = MN), [17,23) N >> 3, [24,29) M >> 4.
-__host__ __device__ constexpr uint32_t idesc_f16(uint32_t M, uint32_t N, uint32_t a_mn, uint32_t b_mn) {
-  return (1u << 4) | (a_mn << 15) | (b_mn << 16) | ((N >> 3) << 17) | ((M >> 4) << 24);
+__host__ __device__ constexpr uint32_t idesc_f16(uint32_t M, uint32_t N, uint32_t a_mn, uint32_t b_mn, uint32_t a_bf16 = 0,
+                                                 uint32_t b_bf16 = 0) {
+  return (1u << 4) | (a_bf16 << 7) | (b_bf16 << 10) | (a_mn << 15) | (b_mn << 16) | ((N >> 3) << 17) | ((M >> 4) << 24);
 }
-
 }  // namespace tc
 
 // ---------------------------------------------------------------- host side: tensor maps without linking libcuda

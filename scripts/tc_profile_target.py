@@ -20,3 +20,12 @@ for _ in range(3):
     tc.attention(q, kv[:, :, :64], kv[:, :, 64:], 1, out=o, q_shared=True)
     tc.gemm(a, w, out=u, bias=bias, act=tc.ACT_GELU)
 torch.cuda.synchronize()
+# the fused attention adjoint at the transformer's shape (3072 tokens, 16 heads)
+t = 3072
+qb = (torch.randn(t, 16, 64, device=dev) * 0.7).half(); kb = (torch.randn(t, 16, 64, device=dev) * 0.7).half()
+vb = torch.randn(t, 16, 64, device=dev).half(); dob = torch.randn(t, 16, 64, device=dev).half()
+lse = torch.full((1, 16, t), 12.0, device=dev); dl = torch.zeros(1, 16, t, device=dev)
+dq, dk, dv = torch.empty_like(qb), torch.empty_like(kb), torch.empty_like(vb)
+for _ in range(3):
+    tc.attention_bwd(qb, kb, vb, dob, lse, dl, dq, dk, dv, 1)
+torch.cuda.synchronize()
