@@ -1318,6 +1318,7 @@ extern "C" int foho_icp_run(const double *source, int32_t Ns, const double *targ
 extern "C" int foho_icp_run_batch(const foho_icp_problem *problems, int32_t n_problems, void *cuda_stream) {
   if (!problems) return FOHO_E_NULL;
   if (n_problems < 0) return FOHO_E_SHAPE;
+  if (n_problems == 0) return FOHO_OK;
   cudaStream_t st = (cudaStream_t)cuda_stream;
   IcpDevice dev;
   int rc = icp_device_info(dev);

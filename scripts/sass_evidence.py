@@ -11,7 +11,8 @@ OUT = os.path.join(ROOT, "profiles", "sass")
 KEYS = ["UTCHMMA", "UTCBAR", "UTMALDG", "UBLKCP", "LDTM", "STTM", "UTCATOMSWS", "USETMAXREG", "SYNCS", "MUFU.EX2", "HMMA", "F2FP",
         "FENCE.VIEW.ASYNC", "ELECT"]
 WANT = {"k_gemm_tc": "decoder_gemm", "k_attn_fwd2": "decoder_attn_v2", "k_attn_fwd": "decoder_attn_v1", "k_stream_tma": "guidance_stream_tma",
-        "k_chamfer_c2h_walk": "chamfer_walk", "k_voxdist_staged": "voxdist_staged", "k_icp_step": "icp_step"}
+        "k_chamfer_c2h_walk": "chamfer_walk", "k_voxdist_staged": "voxdist_staged", "k_icp_step": "icp_step", "k_icp_loop": "icp_loop",
+        "k_attn_bwd": "decoder_attn_bwd", "k_rs_raster": "raster", "k_dmc_verts": "dmc_verts", "k_rc_mask": "remove_close"}
 
 
 def main():

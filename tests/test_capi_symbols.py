@@ -37,17 +37,20 @@ def test_struct_layouts_match_header_sizes():
     prog = r'''
 #include <stdio.h>
 #include "foho_b200.h"
-int main(void){printf("%zu %zu %zu\n", sizeof(foho_weights), sizeof(foho_guidance_desc), sizeof(foho_update_desc));return 0;}
+int main(void){printf("%zu %zu %zu %zu %zu %zu %zu %zu %zu\n", sizeof(foho_weights), sizeof(foho_guidance_desc), sizeof(foho_update_desc),
+  sizeof(foho_gemm_desc), sizeof(foho_attn_desc), sizeof(foho_attn_bwd_desc), sizeof(foho_raster_desc), sizeof(foho_dmc_desc),
+  sizeof(foho_icp_problem));return 0;}
 '''
     import tempfile
     with tempfile.TemporaryDirectory() as td:
         c = os.path.join(td, "s.c"); exe = os.path.join(td, "s")
         open(c, "w").write(prog)
         subprocess.run(["gcc", "-I", os.path.join(ROOT, "include"), c, "-o", exe], check=True)
-        w, g, u = [int(x) for x in subprocess.run([exe], capture_output=True, text=True).stdout.split()]
-    assert ctypes.sizeof(_lib.Weights) == w
-    assert ctypes.sizeof(_lib.GuidanceDesc) == g
-    assert ctypes.sizeof(_lib.UpdateDesc) == u
+        sizes = [int(x) for x in subprocess.run([exe], capture_output=True, text=True).stdout.split()]
+    mirrors = (_lib.Weights, _lib.GuidanceDesc, _lib.UpdateDesc, _lib.GemmDesc, _lib.AttnDesc, _lib.AttnBwdDesc, _lib.RasterDesc,
+               _lib.DmcDesc, _lib.IcpProblem)
+    for m, n in zip(mirrors, sizes):
+        assert ctypes.sizeof(m) == n, (m.__name__, ctypes.sizeof(m), n)
 
 
 def test_argument_validation_without_gpu():
@@ -63,6 +66,12 @@ def test_argument_validation_without_gpu():
     assert lib.foho_icp_workspace_bytes(0, 10) == 0 and lib.foho_icp_workspace_bytes(5000, 10000) > 0
     assert lib.foho_icp_run(None, 1, None, 1, 1, 0, 0, 0.5, 2.0, None, None, None, None, None, 0, None) == -1
     assert lib.foho_status_string(-3).decode().startswith("workspace")
+    assert "driver" in lib.foho_status_string(-5).decode()
+    assert lib.foho_icp_run_batch(None, 1, None) == -1 and lib.foho_icp_run_batch((_lib.IcpProblem * 1)(), 0, None) == 0
+    assert lib.foho_remove_close_workspace_bytes(0) == 0 and lib.foho_remove_close_workspace_bytes(30000) > 0
+    assert lib.foho_remove_close(None, 10, 0.1, None, None, 0, None) == -1
+    assert lib.foho_tc_attention_bwd(None, None) == -1
+    assert lib.foho_tc_attention_bwd(ctypes.byref(_lib.AttnBwdDesc()), None) == -1
     w = _lib.default_weights()
     assert abs(w.w_dist - 10.0) < 1e-9 and abs(w.w_int_lo - 1e-9) < 1e-15 and abs(w.dist_margin - 0.01) < 1e-9
 
