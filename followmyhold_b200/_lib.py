@@ -32,7 +32,7 @@ EXPORTED_SYMBOLS = [
     "foho_abi_version", "foho_status_string", "foho_default_weights",
     "foho_guidance_workspace_bytes", "foho_guidance_energy_fwd_bwd", "foho_guidance_update", "foho_guidance_update_f16",
     "foho_guidance_accel_bytes", "foho_guidance_prepare_statics",
-    "foho_scheduler_step", "foho_scheduler_step_f16", "foho_mock_decoder_forward", "foho_mock_decoder_backward",
+    "foho_scheduler_step", "foho_scheduler_step_f16", "foho_mock_decoder_forward", "foho_mock_decoder_backward", "foho_mock_decoder_forward_f16", "foho_mock_decoder_backward_f16",
     "foho_icp_workspace_bytes", "foho_icp_run", "foho_icp_run_batch",
     "foho_remove_close_workspace_bytes", "foho_remove_close",
     "foho_mesh2sdf_workspace_bytes", "foho_mesh2sdf_lattice", "foho_intersection_count", "foho_mesh_decimate",
@@ -264,6 +264,10 @@ def load(build_if_missing: bool = False) -> C.CDLL:
     lib.foho_mock_decoder_backward.restype = C.c_int
     lib.foho_mock_decoder_backward.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int64, C.c_int32,
                                                C.c_float, C.c_void_p]
+    lib.foho_mock_decoder_forward_f16.restype = C.c_int
+    lib.foho_mock_decoder_forward_f16.argtypes = lib.foho_mock_decoder_forward.argtypes
+    lib.foho_mock_decoder_backward_f16.restype = C.c_int
+    lib.foho_mock_decoder_backward_f16.argtypes = lib.foho_mock_decoder_backward.argtypes
     lib.foho_icp_workspace_bytes.restype = C.c_size_t
     lib.foho_icp_workspace_bytes.argtypes = [C.c_int32, C.c_int32]
     lib.foho_icp_run.restype = C.c_int

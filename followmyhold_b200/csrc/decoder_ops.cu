@@ -326,7 +326,7 @@ __global__ void k_gather_rows(const __half *__restrict__ in, long long ld_in, co
   const int c = (int)(i - r * cpr);
   *reinterpret_cast<uint4 *>(out + r * ld_out + c * 8) = __ldg(reinterpret_cast<const uint4 *>(in + (long long)idx[r] * ld_in + c * 8));
 }
-// 2-D casts between row-major views (cols contiguous): mode 0 f32 -> f16, 1 f16 -> f32, 2 f16 -> f32 accumulate
+// 2-D casts between row-major views (cols contiguous): mode 0 f32 -> f16, 1 f16 -> f32, 2 f16 -> f32 accumulate, 4 f16 -> f16 (x scale)
 __global__ void k_cast2d(const void *__restrict__ in, long long ld_in, void *__restrict__ out, long long ld_out, long long rows, int cols,
                          float scale, int mode) {
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -335,6 +335,8 @@ __global__ void k_cast2d(const void *__restrict__ in, long long ld_in, void *__r
   const int c = (int)(i - r * cols);
   if (mode == 0) {
     reinterpret_cast<__half *>(out)[r * ld_out + c] = __float2half_rn(reinterpret_cast<const float *>(in)[r * ld_in + c] * scale);
+  } else if (mode == 4) {     // a half tensor times a python float in torch: product in float, rounded to half
+    reinterpret_cast<__half *>(out)[r * ld_out + c] = __float2half_rn(__half2float(reinterpret_cast<const __half *>(in)[r * ld_in + c]) * scale);
   } else {
     const float v = __half2float(reinterpret_cast<const __half *>(in)[r * ld_in + c]) * scale;
     float *o = reinterpret_cast<float *>(out) + r * ld_out + c;
@@ -571,7 +573,7 @@ extern "C" int foho_dec_cast(const void *in, int64_t ld_in, void *out, int64_t l
   if (rows <= 0 || cols <= 0) return FOHO_E_SHAPE;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(cuda_stream);
   const long long n = rows * cols;
-  if (mode >= 0 && mode <= 2) k_cast2d<<<blocks_for(n, 256), 256, 0, st>>>(in, ld_in, out, ld_out, rows, cols, scale, mode);
+  if ((mode >= 0 && mode <= 2) || mode == 4) k_cast2d<<<blocks_for(n, 256), 256, 0, st>>>(in, ld_in, out, ld_out, rows, cols, scale, mode);
   else if (mode == 3) {
     if (ld_in != cols || ld_out != cols) return FOHO_E_ARG;
     k_add_f16<<<blocks_for((n + 7) / 8, 256), 256, 0, st>>>((const __half *)in, (const __half *)out, (__half *)out, n);

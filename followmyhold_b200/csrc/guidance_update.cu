@@ -151,43 +151,66 @@ __global__ void __launch_bounds__(256) k_sched_step_f16(const __half *__restrict
   }
 }
 
+// LT = float | __half: the latents' dtype (the reference carries them in half, pipelines.py:1204; the decoded volume and its
+// gradient are float like `latent2sdf(...).float()`, :309)
+template <typename LT>
 __global__ void __launch_bounds__(256) k_mock_dec_fwd(float *__restrict__ sdf, const float *__restrict__ sdf0,
-                                                      const float *__restrict__ x1, const long long *__restrict__ tap,
+                                                      const LT *__restrict__ x1, const long long *__restrict__ tap,
                                                       long long vol, int L, float alpha) {
   const int b = blockIdx.y;
   for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < L; j += gridDim.x * blockDim.x) {
     const long long t = tap[j];
-    sdf[(size_t)b * vol + t] = sdf0[(size_t)b * vol + t] + alpha * x1[(size_t)b * L + j];
+    sdf[(size_t)b * vol + t] = sdf0[(size_t)b * vol + t] + alpha * (float)x1[(size_t)b * L + j];
   }
 }
 
+template <typename LT>
 __global__ void __launch_bounds__(256) k_mock_dec_bwd(const float *__restrict__ g, const long long *__restrict__ tap,
-                                                      float *__restrict__ gv, long long vol, int L, float scale) {
+                                                      LT *__restrict__ gv, long long vol, int L, float scale) {
   const int b = blockIdx.y;
   for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < L; j += gridDim.x * blockDim.x)
-    gv[(size_t)b * L + j] = scale * g[(size_t)b * vol + tap[j]];
+    gv[(size_t)b * L + j] = (LT)(scale * g[(size_t)b * vol + tap[j]]);
 }
 
 }  // namespace
 
-extern "C" int foho_mock_decoder_forward(float *sdf, const float *sdf0, const float *x1, const int64_t *tap, int32_t B,
-                                         int64_t vol, int32_t L, float alpha, void *cuda_stream) {
+template <typename LT>
+static int mock_decoder_forward(float *sdf, const float *sdf0, const LT *x1, const int64_t *tap, int32_t B, int64_t vol, int32_t L,
+                                float alpha, void *cuda_stream) {
   if (!sdf || !sdf0 || !x1 || !tap) return FOHO_E_NULL;
   if (B < 1 || vol < 1 || L < 1) return FOHO_E_SHAPE;
   int gx = (L + 255) / 256; if (gx > 296) gx = 296;
-  k_mock_dec_fwd<<<dim3(gx, B), 256, 0, (cudaStream_t)cuda_stream>>>(sdf, sdf0, x1, (const long long *)tap, vol, L, alpha);
+  k_mock_dec_fwd<LT><<<dim3(gx, B), 256, 0, (cudaStream_t)cuda_stream>>>(sdf, sdf0, x1, (const long long *)tap, vol, L, alpha);
   FOHO_LAUNCH_CHECK();
   return FOHO_OK;
 }
 
-extern "C" int foho_mock_decoder_backward(const float *grad_sdf, const int64_t *tap, float *grad_velocity, int32_t B,
-                                          int64_t vol, int32_t L, float scale, void *cuda_stream) {
+template <typename LT>
+static int mock_decoder_backward(const float *grad_sdf, const int64_t *tap, LT *grad_velocity, int32_t B, int64_t vol, int32_t L,
+                                 float scale, void *cuda_stream) {
   if (!grad_sdf || !tap || !grad_velocity) return FOHO_E_NULL;
   if (B < 1 || vol < 1 || L < 1) return FOHO_E_SHAPE;
   int gx = (L + 255) / 256; if (gx > 296) gx = 296;
-  k_mock_dec_bwd<<<dim3(gx, B), 256, 0, (cudaStream_t)cuda_stream>>>(grad_sdf, (const long long *)tap, grad_velocity, vol, L, scale);
+  k_mock_dec_bwd<LT><<<dim3(gx, B), 256, 0, (cudaStream_t)cuda_stream>>>(grad_sdf, (const long long *)tap, grad_velocity, vol, L, scale);
   FOHO_LAUNCH_CHECK();
   return FOHO_OK;
+}
+
+extern "C" int foho_mock_decoder_forward(float *sdf, const float *sdf0, const float *x1, const int64_t *tap, int32_t B,
+                                         int64_t vol, int32_t L, float alpha, void *cuda_stream) {
+  return mock_decoder_forward<float>(sdf, sdf0, x1, tap, B, vol, L, alpha, cuda_stream);
+}
+extern "C" int foho_mock_decoder_forward_f16(float *sdf, const float *sdf0, const void *x1, const int64_t *tap, int32_t B,
+                                             int64_t vol, int32_t L, float alpha, void *cuda_stream) {
+  return mock_decoder_forward<__half>(sdf, sdf0, (const __half *)x1, tap, B, vol, L, alpha, cuda_stream);
+}
+extern "C" int foho_mock_decoder_backward(const float *grad_sdf, const int64_t *tap, float *grad_velocity, int32_t B,
+                                          int64_t vol, int32_t L, float scale, void *cuda_stream) {
+  return mock_decoder_backward<float>(grad_sdf, tap, grad_velocity, B, vol, L, scale, cuda_stream);
+}
+extern "C" int foho_mock_decoder_backward_f16(const float *grad_sdf, const int64_t *tap, void *grad_velocity, int32_t B,
+                                              int64_t vol, int32_t L, float scale, void *cuda_stream) {
+  return mock_decoder_backward<__half>(grad_sdf, tap, (__half *)grad_velocity, B, vol, L, scale, cuda_stream);
 }
 
 static int update_checks(const foho_update_desc &d, int vec, int align) {

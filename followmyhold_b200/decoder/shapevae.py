@@ -122,13 +122,15 @@ class _Ops:
         return out
 
     def cast(self, src, dst, scale=1.0, accumulate=False, stream=None):
-        """2-D row-major views; f32 -> f16 or f16 -> f32 (optionally accumulating)."""
+        """2-D row-major views; f32 -> f16, f16 -> f32 (optionally accumulating) or f16 -> f16 (scaled copy)."""
         if src.dim() != 2 or dst.shape != src.shape or src.stride(1) != 1 or dst.stride(1) != 1:
             raise ValueError("cast expects matching 2-D views with contiguous columns")
         if src.dtype == torch.float32 and dst.dtype == torch.float16:
             mode = 0
         elif src.dtype == torch.float16 and dst.dtype == torch.float32:
             mode = 2 if accumulate else 1
+        elif src.dtype == torch.float16 and dst.dtype == torch.float16 and not accumulate:
+            mode = 4
         else:
             raise ValueError("unsupported cast")
         _lib.check("foho_dec_cast", self.lib.foho_dec_cast(src.data_ptr(), src.stride(0), dst.data_ptr(), dst.stride(0), src.shape[0],
@@ -269,7 +271,8 @@ class LatentDecoder:
 
     # ------------------------------------------------------------------ forward
     def forward(self, latents: torch.Tensor, out: Optional[torch.Tensor] = None, stream=None) -> torch.Tensor:
-        """``latents`` [B, 3072, 64] float32 (x1 of ``step_final``); returns sdf [B, Nq] float32, negative inside."""
+        """``latents`` [B, 3072, 64] float32 or float16 (x1 of ``step_final``; half in the reference, pipelines.py:1204);
+        returns sdf [B, Nq] float32, negative inside."""
         w, ops, B = self.w, self.ops, self.B
         if self.x0 is None:
             raise RuntimeError("set_queries() first")
@@ -461,7 +464,7 @@ class LatentDecoder:
         # ---- post_kl and the 1/scale_factor of the call site
         if out is None:
             out = torch.empty(B, TOKENS, EMBED, **f32)
-        # float32 out; the epilogue undoes the loss scale and applies the call site's 1/scale_factor (:297)
+        # float32 (or float16) out; the epilogue undoes the loss scale and applies the call site's 1/scale_factor (:297)
         tc.gemm(g, w.post_kl_w, out=out.view(R, EMBED), b_mn=True, alpha=out_scale / (w.scale_factor * ls), stream=stream)
         return out
 

@@ -59,10 +59,16 @@ class GuidanceLoop:
     def __init__(self, B: int, D: int, statics: GuidanceStatics, P: int, device="cuda:0",
                  config: Optional[OptimizationConfig] = None, weights=None, latent_elems: int = LATENT_SHAPE[0] * LATENT_SHAPE[1],
                  decoder_alpha: float = 0.05, stream_variant: int = 0, seed: int = 0, micro_batches: int = 1,
-                 loss_log_every: int = 0, mock_decoder: bool = True, max_obj_verts: int = 0):
+                 loss_log_every: int = 0, mock_decoder: bool = True, max_obj_verts: int = 0,
+                 latent_dtype: torch.dtype = torch.float32):
         """``loss_log_every`` = n > 0 keeps the loss terms of every n-th inner iteration of every step
         (``loss_history``; the reference logs every 10th when ``FOHO_DEBUG_DIR`` is set, pipelines.py:1446-1450,
         1594-1598) -- device-to-device copies inside the step graph, no host sync.
+
+        ``latent_dtype=torch.float16`` carries the latents, the model output being optimised, its gradient and ``x1`` in half,
+        as the reference does (pipelines.py:1204; the leaf is a clone of the DiT's half output, code_utils.py:43-78): the
+        update is then ``foho_guidance_update_f16`` (torch's half AdamW, rounding after every op), the scheduler
+        ``foho_scheduler_step_f16`` (pinned by the reference scheduler's golden vectors) and the decoders read half ``x1``.
 
         ``micro_batches`` = m > 1 splits the B images into m groups that advance independently inside the
         one captured graph (own engine, optimiser state, stream and library side-stream lane): while one
@@ -70,6 +76,9 @@ class GuidanceLoop:
         the other group's dense stream keeps the HBM busy.  Results are identical: images never interact."""
         self.lib = _lib.load()
         self.device = torch.device(device)
+        if latent_dtype not in (torch.float32, torch.float16):
+            raise ValueError("latent_dtype must be torch.float32 or torch.float16")
+        self.latent_dtype = latent_dtype
         self.B, self.D, self.P, self.L = B, D, P, latent_elems
         self.cfg = config or OptimizationConfig()
         self.statics = statics
@@ -95,7 +104,7 @@ class GuidanceLoop:
             eng.terms = self.terms.narrow(0, j * nb, nb)             # the lanes write straight into the
             eng.grad_theta = self.grad_theta.narrow(0, j * nb, nb)   # loop's [B, .] result buffers
             eng.prepare(st_j)
-            self.lanes.append(_Lane(j * nb, nb, eng, GuidanceOptimizer(nb, self.L, device=device, config=self.cfg), st_j,
+            self.lanes.append(_Lane(j * nb, nb, eng, GuidanceOptimizer(nb, self.L, device=device, config=self.cfg, velocity_dtype=latent_dtype), st_j,
                                     None if j == 0 else torch.cuda.Stream(device=dev)))
         self.engine = self.lanes[0].engine       # the whole batch when micro_batches == 1
         self.opt = self.lanes[0].opt
@@ -115,11 +124,16 @@ class GuidanceLoop:
         else:
             self.tap, self.sdf0 = None, None         # run_schedule_decoder / run_schedule_tc_decoder only
         self.sdf = torch.empty(B, D, D, D, dtype=f32, device=dev)      # current decode
-        self.x_t = torch.zeros(B, self.L, dtype=f32, device=dev)       # latents
-        self.velocity = torch.zeros(B, self.L, dtype=f32, device=dev)  # model output being optimised
-        self.x1 = torch.zeros(B, self.L, dtype=f32, device=dev)
-        self.grad_velocity = torch.zeros(B, self.L, dtype=f32, device=dev)
-        self.prev = torch.zeros(B, self.L, dtype=f32, device=dev)
+        lt = latent_dtype
+        self.x_t = torch.zeros(B, self.L, dtype=lt, device=dev)        # latents
+        self.velocity = torch.zeros(B, self.L, dtype=lt, device=dev)   # model output being optimised
+        self.x1 = torch.zeros(B, self.L, dtype=lt, device=dev)
+        self.grad_velocity = torch.zeros(B, self.L, dtype=lt, device=dev)
+        self.prev = torch.zeros(B, self.L, dtype=lt, device=dev)
+        half = lt == torch.float16
+        self._sched_fn = self.lib.foho_scheduler_step_f16 if half else self.lib.foho_scheduler_step
+        self._mock_fwd = self.lib.foho_mock_decoder_forward_f16 if half else self.lib.foho_mock_decoder_forward
+        self._mock_bwd = self.lib.foho_mock_decoder_backward_f16 if half else self.lib.foho_mock_decoder_backward
         self.theta = torch.zeros(B, 16, dtype=f32, device=dev)
         self.reset_leaves()
         self.sigmas = set_timesteps_sigmas(self.cfg.num_inference_steps)
@@ -335,7 +349,7 @@ class GuidanceLoop:
         vel, gvel = self.velocity.narrow(0, off, nb), self.grad_velocity.narrow(0, off, nb)
         hand_only = phase == 1
         if not hand_only:
-            _lib.check("foho_mock_decoder_forward", lib.foho_mock_decoder_forward(
+            _lib.check("foho_mock_decoder_forward", self._mock_fwd(
                 sdf.data_ptr(), sdf0.data_ptr(), x1.data_ptr(), self.tap.data_ptr(), nb, vol, self.L, self.alpha, sp))
         desc = ln.engine.make_desc(sdf, theta, ln.statics, late_step=late_step, grad_hand_ext=self._hand_image_grad(ln, phase, s))
         if phase != 2:
@@ -345,7 +359,7 @@ class GuidanceLoop:
             desc.stage_mask = 1 | 4 | 16                   # no volume term has weight: skip the stream and the voxels
         ln.engine.launch(desc, s)
         if not hand_only:
-            _lib.check("foho_mock_decoder_backward", lib.foho_mock_decoder_backward(
+            _lib.check("foho_mock_decoder_backward", self._mock_bwd(
                 ln.engine.grad_sdf.data_ptr(), self.tap.data_ptr(), gvel.data_ptr(), nb, vol, self.L,
                 self.alpha * (1.0 - sigma), sp))
         if log_slot is not None:
@@ -366,7 +380,7 @@ class GuidanceLoop:
         sigma = float(self.sigmas[step_index]); sigma_next = float(self.sigmas[step_index + 1])
         late = step_index >= cfg.num_inference_steps - 3
         if phase == 0:
-            _lib.check("foho_scheduler_step", self.lib.foho_scheduler_step(
+            _lib.check("foho_scheduler_step", self._sched_fn(
                 self.x_t.data_ptr(), self.velocity.data_ptr(), self.prev.data_ptr(), None, self.x_t.numel(), sigma,
                 sigma_next, C.c_void_p(s.cuda_stream)))
             return
@@ -382,7 +396,7 @@ class GuidanceLoop:
                 ln.opt.reset()                             # fresh optimiser state every outer step (:1318,1384,1478)
                 self.nan_flag.narrow(0, off, nb).zero_()   # the NaN `break` ends one outer step's inner loop only
                 # x1 for the first decode of this step: step_final with the incoming velocity (:1507)
-                _lib.check("foho_scheduler_step", self.lib.foho_scheduler_step(
+                _lib.check("foho_scheduler_step", self._sched_fn(
                     x_t.data_ptr(), vel.data_ptr(), None, x1.data_ptr(), x_t.numel(), sigma, sigma_next,
                     C.c_void_p(st.cuda_stream)))
                 for k in range(self.phase_iterations(phase)):
@@ -392,7 +406,7 @@ class GuidanceLoop:
                     self._enqueue_eval(sigma, late, st, phase, ln, slot)
                 self.nan_steps[step_index].narrow(0, off, nb).copy_(self.nan_flag.narrow(0, off, nb))
                 # obj_latents = scheduler.step(noise_pred_obj, t, obj_latents).prev_sample (:1612)
-                _lib.check("foho_scheduler_step", self.lib.foho_scheduler_step(
+                _lib.check("foho_scheduler_step", self._sched_fn(
                     x_t.data_ptr(), vel.data_ptr(), prev.data_ptr(), None, x_t.numel(), sigma, sigma_next,
                     C.c_void_p(st.cuda_stream)))
         for ln in self.lanes[1:]:
@@ -559,7 +573,7 @@ class GuidanceLoop:
                         opt.step(self.theta, eng.grad_theta, None if gvel is None else self.velocity, gvel,
                                  self.x_t, self.x1, sigma=sigma, stream=s, terms=eng.terms, nan_flag=self.nan_flag)
                     self.nan_steps[i].copy_(self.nan_flag)
-                _lib.check("foho_scheduler_step", self.lib.foho_scheduler_step(
+                _lib.check("foho_scheduler_step", self._sched_fn(
                     self.x_t.data_ptr(), self.velocity.data_ptr(), self.prev.data_ptr(), None, self.x_t.numel(), sigma,
                     sigma_next, sp))
                 self.x_t.copy_(self.prev)
@@ -617,7 +631,7 @@ class GuidanceLoop:
                             eng.launch(desc, s)
                             vel = gvel = None
                         else:
-                            _lib.check("foho_scheduler_step", self.lib.foho_scheduler_step(
+                            _lib.check("foho_scheduler_step", self._sched_fn(
                                 self.x_t.data_ptr(), self.velocity.data_ptr(), None, self.x1.data_ptr(), self.x_t.numel(),
                                 sigma, sigma_next, sp))                                   # step_final (:1507)
                             decoder.forward(self.x1.view(B, LATENT_SHAPE[0], LATENT_SHAPE[1]), out=self.sdf.view(B, V), stream=s)
@@ -638,7 +652,7 @@ class GuidanceLoop:
                         opt.step(self.theta, eng.grad_theta, vel, gvel, self.x_t, self.x1, sigma=sigma, stream=s,
                                  terms=eng.terms, nan_flag=self.nan_flag)
                     self.nan_steps[i].copy_(self.nan_flag)
-                _lib.check("foho_scheduler_step", self.lib.foho_scheduler_step(
+                _lib.check("foho_scheduler_step", self._sched_fn(
                     self.x_t.data_ptr(), self.velocity.data_ptr(), self.prev.data_ptr(), None, self.x_t.numel(), sigma,
                     sigma_next, sp))
                 self.x_t.copy_(self.prev)

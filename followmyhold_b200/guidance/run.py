@@ -191,8 +191,11 @@ def run(
     j_regressor_path: str = J_REGRESSOR_PATH,
     seed: int = 2,
     obj_cap_factor: int = 6,
+    latent_dtype: Optional[torch.dtype] = None,
 ) -> None:
-    """Positional/keyword arguments up to ``task_list_file`` are the reference's (run.py:188-199)."""
+    """Positional/keyword arguments up to ``task_list_file`` are the reference's (run.py:188-199).  ``latent_dtype``: the dtype
+    the latents and the model output being optimised are carried in -- default: half with the reference's own networks
+    on the tensor cores (a model with ``tc_decoder``; the reference's pipeline is half, pipelines.py:1204), float otherwise."""
     del project_root                      # the reference only uses it to extend sys.path (run.py:57-62)
     if model is None:
         model = load_model_from_env()
@@ -233,7 +236,7 @@ def run(
     for chunk in batches_of_compatible_images(todo, batch_size):
         idx = [p["index"] for p, _ in chunk]
         try:
-            _run_batch(chunk, model, J, config, n_cloud, dev, seed, GuidanceLoop, obj_cap_factor)
+            _run_batch(chunk, model, J, config, n_cloud, dev, seed, GuidanceLoop, obj_cap_factor, latent_dtype)
             for i in idx:
                 print(f"Reconstructed object {i}")
         except Exception as e:
@@ -245,7 +248,7 @@ def run(
             print(f"Error in reconstruction for batch {idx} : {e}; retrying its images one by one")
             for item in chunk:
                 try:
-                    _run_batch([item], model, J, config, n_cloud, dev, seed, GuidanceLoop, obj_cap_factor)
+                    _run_batch([item], model, J, config, n_cloud, dev, seed, GuidanceLoop, obj_cap_factor, latent_dtype)
                     print(f"Reconstructed object {item[0]['index']}")
                 except Exception as e1:
                     print(f"Error in reconstruction for {item[0]['index']} : {e1}")
@@ -275,7 +278,7 @@ def batches_of_compatible_images(todo: list, batch_size: int) -> List[list]:
 
 
 def _run_batch(chunk, model: GuidanceModel, J: torch.Tensor, config: OptimizationConfig, n_cloud: int, dev, seed: int,
-               GuidanceLoop, obj_cap_factor: int = 6) -> None:
+               GuidanceLoop, obj_cap_factor: int = 6, latent_dtype: Optional[torch.dtype] = None) -> None:
     B = len(chunk)
     inputs = [inp for _, inp in chunk]
     faces0 = inputs[0]["faces"]
@@ -305,7 +308,8 @@ def _run_batch(chunk, model: GuidanceModel, J: torch.Tensor, config: Optimizatio
         dec = tc_decoder(B)
         cap_obj = B * int(obj_cap_factor) * model.D * model.D      # extracted-surface capacity: a closed surface has O(D^2) cubes
         loop = GuidanceLoop(B, model.D, st, n_cloud, device=dev, config=config, latent_elems=model.latent_elems,
-                            loss_log_every=10 if debug_root else 0, mock_decoder=False, max_obj_verts=cap_obj)
+                            loss_log_every=10 if debug_root else 0, mock_decoder=False, max_obj_verts=cap_obj,
+                            latent_dtype=latent_dtype or torch.float16)
         if all(inp.get("moge_mesh") is not None for inp in inputs):
             # the reference's image terms (pipelines.py:1327-1349,1413-1440,1544-1569): targets rendered once per image from
             # MoGe's mesh, then hand / object-only / joined renders every inner iteration, object mesh extracted from the volume
@@ -338,7 +342,8 @@ def _run_batch(chunk, model: GuidanceModel, J: torch.Tensor, config: Optimizatio
     else:
         sdf0, tap, alpha = model.decoder_state()
         loop = GuidanceLoop(B, model.D, st, n_cloud, device=dev, config=config, latent_elems=model.latent_elems,
-                            decoder_alpha=float(alpha), loss_log_every=10 if debug_root else 0)
+                            decoder_alpha=float(alpha), loss_log_every=10 if debug_root else 0,
+                            latent_dtype=latent_dtype or torch.float32)
         loop.tap = tap.to(dev).to(torch.int64).contiguous()
         loop.sdf0.copy_(sdf0); loop.sdf.copy_(sdf0)
         loop.x_t.copy_(model.initial_latents(B, gen))

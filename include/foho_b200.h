@@ -250,6 +250,11 @@ int foho_mock_decoder_forward(float *sdf, const float *sdf0, const float *x1, co
                               int64_t vol, int32_t L, float alpha, void *cuda_stream);
 int foho_mock_decoder_backward(const float *grad_sdf, const int64_t *tap, float *grad_velocity, int32_t B,
                                int64_t vol, int32_t L, float alpha_times_one_minus_sigma, void *cuda_stream);
+/* the same with half latents / latent gradients (the reference's dtype, pipelines.py:1204); the volume stays float */
+int foho_mock_decoder_forward_f16(float *sdf, const float *sdf0, const void *x1, const int64_t *tap, int32_t B,
+                                  int64_t vol, int32_t L, float alpha, void *cuda_stream);
+int foho_mock_decoder_backward_f16(const float *grad_sdf, const int64_t *tap, void *grad_velocity, int32_t B,
+                                   int64_t vol, int32_t L, float alpha_times_one_minus_sigma, void *cuda_stream);
 
 /* Replaces `icp(...)` of src/foho/alignment/mesh_align.py:56-175 for the configuration
  * both callers use (on_surface=False, no rotation/reflection search): trimmed
@@ -420,7 +425,8 @@ int foho_dec_head_bwd(const void *x, int64_t ldx, const float *ln_w, float eps, 
 int foho_dec_gather_rows(const void *in, int64_t ld_in, const int32_t *idx, void *out, int64_t ld_out, int64_t rows, int32_t width,
                          void *cuda_stream);
 /* row-major views [rows, cols], cols contiguous, leading dimensions in elements.
- * mode 0: f32 -> f16 (x scale); 1: f16 -> f32 (x scale); 2: f16 -> f32 accumulate; 3: out += in (fp16, contiguous) */
+ * mode 0: f32 -> f16 (x scale); 1: f16 -> f32 (x scale); 2: f16 -> f32 accumulate; 3: out += in (fp16, contiguous);
+ * 4: f16 -> f16 (x scale) */
 int foho_dec_cast(const void *in, int64_t ld_in, void *out, int64_t ld_out, int64_t rows, int32_t cols, float scale, int32_t mode,
                   void *cuda_stream);
 

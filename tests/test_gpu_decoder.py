@@ -136,7 +136,7 @@ def test_reference_lattice_65_sampled_rows():
 
 
 # --------------------------------------------------------------------------- the decoder inside the guidance loop
-def _loop_setup(D=17, B=2, P=1024, layers=2):
+def _loop_setup(D=17, B=2, P=1024, layers=2, latent_dtype=torch.float32):
     from followmyhold_b200.decoder.shapevae import DecoderWeights, LatentDecoder
     from followmyhold_b200.guidance.config import OptimizationConfig
     from followmyhold_b200.guidance.loop import GuidanceLoop
@@ -147,7 +147,7 @@ def _loop_setup(D=17, B=2, P=1024, layers=2):
     cfg = OptimizationConfig()
     cfg.optimization_steps_hand, cfg.optimization_steps_scale, cfg.optimization_steps_joint = 3, 2, 2
     cfg.with_steps(6)
-    loop = GuidanceLoop(B, D, st, P, device=dev, config=cfg, micro_batches=1, mock_decoder=False)
+    loop = GuidanceLoop(B, D, st, P, device=dev, config=cfg, micro_batches=1, mock_decoder=False, latent_dtype=latent_dtype)
     loop.theta.copy_(theta0)
     vae = _vae(layers, seed=11)
     with torch.no_grad():                          # a field with an inside: shift the logits so part of the lattice is < 0
@@ -157,7 +157,7 @@ def _loop_setup(D=17, B=2, P=1024, layers=2):
     g = torch.Generator().manual_seed(7)
     loop.x_t.copy_(torch.randn(B, loop.L, generator=g))
     vel = 0.5 * torch.randn(B, loop.L, generator=g)
-    return loop, dec, vae.to(dev), vel.to(dev), st, D, B
+    return loop, dec, vae.to(dev), vel.to(dev).to(latent_dtype), st, D, B
 
 
 def test_loop_gradient_through_the_tc_decoder_matches_autograd_through_the_oracle():
@@ -209,8 +209,11 @@ def test_loop_gradient_through_the_tc_decoder_matches_autograd_through_the_oracl
     assert (got - gref).abs().max().item() <= 2e-2 * gref.abs().max().item()
 
 
-def test_schedule_with_the_tc_decoder_runs_all_phases():
-    loop, dec, vae, vel, st, D, B = _loop_setup()
+@pytest.mark.parametrize("latent_dtype", [torch.float32, torch.float16])
+def test_schedule_with_the_tc_decoder_runs_all_phases(latent_dtype):
+    """All phases with the tensor-core decoder in the loop; with half latents (the reference's dtype) the decoder reads
+    half ``x1`` and its adjoint writes the half latent gradient directly."""
+    loop, dec, vae, vel, st, D, B = _loop_setup(latent_dtype=latent_dtype)
     theta0 = loop.theta.clone()
     x0 = loop.x_t.clone()
     loop.sdf.fill_(1.0)
@@ -228,6 +231,7 @@ def test_schedule_with_the_tc_decoder_runs_all_phases():
     assert torch.isfinite(loop.x_t).all() and torch.isfinite(loop.theta).all() and torch.isfinite(loop.terms).all()
     assert not torch.equal(loop.theta, theta0) and not torch.equal(loop.x_t, x0)
     assert loop.nan_report() == {}
+    assert loop.x_t.dtype == latent_dtype and loop.grad_velocity.dtype == latent_dtype
 
 
 def test_export_lattice_decode_streams_the_query_side(small):

@@ -150,3 +150,61 @@ def test_torch_decoder_schedule_matches_the_graph_schedule():
     assert not torch.equal(th_t, theta0.cpu())
     assert torch.allclose(th_t, th_g, rtol=1e-4, atol=1e-6)
     assert torch.allclose(v_t, v_g, rtol=1e-4, atol=1e-6) and torch.allclose(x_t2, x_g, rtol=1e-4, atol=1e-6)
+
+
+def test_half_latents_through_the_loop():
+    """``latent_dtype=torch.float16`` (the reference's dtype, pipelines.py:1204).  The pieces are pinned on their own --
+    ``foho_guidance_update_f16`` bit for bit against torch's half AdamW, ``foho_scheduler_step_f16`` against the
+    reference scheduler's golden vectors -- so what is held here is the wiring: with ONE inner iteration per phase the
+    half loop's ``x1`` is the float loop's rounded once and the latent gradient agrees to half precision (same inputs,
+    same volume), the whole schedule runs in half end to end, eager and graph replay agree, and the stand-in decoder's
+    half entry points are exact.  (After many inner iterations the two dtypes legitimately part: torch's half AdamW
+    keeps its second moment in half, where g^2 underflows -- which is what the reference runs.)"""
+    import ctypes as C
+    from followmyhold_b200.guidance.config import OptimizationConfig
+    from followmyhold_b200.guidance.loop import GuidanceLoop
+    B, D, P, L = 2, 32, 512, 1024
+    samples = [make_guidance_sample(D, P, 90 + i) for i in range(B)]
+    sdf0, theta0, st = stack_samples(samples, cap=True)
+    g = torch.Generator().manual_seed(11)
+    x_t = torch.randn(B, L, generator=g).half()
+    outputs = [(0.1 * torch.randn(B, L, generator=g)).half() for _ in range(6)]
+
+    def run(dt, graphs, inner):
+        cfg = OptimizationConfig().with_steps(6)
+        cfg.optimization_steps_hand, cfg.optimization_steps_scale, cfg.optimization_steps_joint = inner
+        lp = GuidanceLoop(B, D, st, P, config=cfg, latent_elems=L, seed=4, micro_batches=2, latent_dtype=dt)
+        lp.sdf0.copy_(sdf0); lp.sdf.copy_(sdf0); lp.x_t.copy_(x_t); lp.theta.copy_(theta0)
+        # up to and including the object-only step (index 3): its single inner iteration is the first decode
+        lp.run_schedule_device([o.cuda().to(dt) for o in outputs], use_graphs=graphs, last_step=3 if inner == (1, 1, 1) else None)
+        torch.cuda.synchronize()
+        assert all(t.dtype == dt for t in (lp.x_t, lp.velocity, lp.x1, lp.grad_velocity, lp.prev))
+        return lp
+    a32, a16 = run(torch.float32, False, (1, 1, 1)), run(torch.float16, False, (1, 1, 1))
+    x1_32, x1_16 = a32.x1.cpu(), a16.x1.float().cpu()
+    assert float((x1_16 - x1_32).abs().max()) <= 2.0 ** -9 * float(x1_32.abs().max())          # rounded once (two ops in half)
+    g32, g16 = a32.grad_velocity.cpu(), a16.grad_velocity.float().cpu()
+    assert float(g32.abs().max()) > 0
+    assert float((g16 - g32).abs().max()) <= 4e-3 * float(g32.abs().max())
+    full_e, full_g = run(torch.float16, False, (5, 4, 3)), run(torch.float16, True, (5, 4, 3))
+    for lp in (full_e, full_g):
+        assert torch.isfinite(lp.x_t.float()).all() and torch.isfinite(lp.velocity.float()).all() and torch.isfinite(lp.theta).all()
+    assert not torch.equal(full_e.theta.cpu(), theta0.cpu())
+    assert torch.allclose(full_e.theta, full_g.theta, rtol=1e-3, atol=1e-4)
+    assert float((full_e.x_t.float() - full_g.x_t.float()).abs().max()) <= 8e-3
+    cfg = OptimizationConfig().with_steps(6)
+    # the stand-in decoder with half latents: sdf0 + alpha * float(x1) at the taps, gradient rounded once
+    lp = GuidanceLoop(B, D, st, P, config=cfg, latent_elems=L, seed=4, latent_dtype=torch.float16)
+    lp.sdf0.copy_(sdf0); lp.sdf.copy_(sdf0)
+    x1 = torch.randn(B, L, device="cuda").half()
+    sp = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+    vol = D ** 3
+    assert lp.lib.foho_mock_decoder_forward_f16(lp.sdf.data_ptr(), lp.sdf0.data_ptr(), x1.data_ptr(), lp.tap.data_ptr(), B, vol, L,
+                                                lp.alpha, sp) == 0
+    want = lp.sdf0.view(B, vol).clone()
+    want[:, lp.tap] = want[:, lp.tap] + lp.alpha * x1.float()
+    assert torch.allclose(lp.sdf.view(B, vol), want, rtol=0, atol=2e-7)                    # fused multiply-add vs two roundings
+    gs = torch.randn(B, vol, device="cuda")
+    gv = torch.empty(B, L, device="cuda", dtype=torch.float16)
+    assert lp.lib.foho_mock_decoder_backward_f16(gs.data_ptr(), lp.tap.data_ptr(), gv.data_ptr(), B, vol, L, 0.25, sp) == 0
+    assert torch.equal(gv, (0.25 * gs[:, lp.tap]).half())                                   # one product, rounded once
