@@ -33,9 +33,21 @@ __global__ void k_ln_fwd(const __half *__restrict__ x, int inner_x, long long ld
                          long long rows) {
   constexpr int CH = W / 8;                       // 16-byte chunks per row
   constexpr int CPL = (CH + 31) / 32;             // chunks per lane
-  const long long r = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-  if (r >= rows) return;
   const int lane = threadIdx.x & 31;
+  // W = 1024: the warps are persistent (grid-stride over the rows) and keep this lane's 32 weights and biases in registers
+  // -- read per row, the 64 scalar parameter loads per lane were most of the kernel's memory instructions
+  float wr[W == 1024 ? CPL : 1][8], br[W == 1024 ? CPL : 1][8];
+  if (W == 1024) {
+#pragma unroll
+    for (int c = 0; c < CPL; ++c)
+#pragma unroll
+      for (int t = 0; t < 8; ++t) {
+        wr[c][t] = w ? __ldg(w + (lane + 32 * c) * 8 + t) : 1.f;
+        br[c][t] = b ? __ldg(b + (lane + 32 * c) * 8 + t) : 0.f;
+      }
+  }
+  const long long warps = (long long)gridDim.x * (blockDim.x >> 5);
+  for (long long r = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); r < rows; r += warps) {
   const __half *xp = x + row_off(r, inner_x, ldo_x, ldi_x);
   float v[CPL][8];
   float s = 0.f;
@@ -69,12 +81,17 @@ __global__ void k_ln_fwd(const __half *__restrict__ x, int inner_x, long long ld
 #pragma unroll
       for (int t = 0; t < 4; ++t) {
         float a = (v[c][2 * t] - mean) * rstd, bb = (v[c][2 * t + 1] - mean) * rstd;
-        if (w) { a *= __ldg(w + ch * 8 + 2 * t); bb *= __ldg(w + ch * 8 + 2 * t + 1); }
-        if (b) { a += __ldg(b + ch * 8 + 2 * t); bb += __ldg(b + ch * 8 + 2 * t + 1); }
+        if (W == 1024) {
+          a = a * wr[c][2 * t] + br[c][2 * t]; bb = bb * wr[c][2 * t + 1] + br[c][2 * t + 1];
+        } else {
+          if (w) { a *= __ldg(w + ch * 8 + 2 * t); bb *= __ldg(w + ch * 8 + 2 * t + 1); }
+          if (b) { a += __ldg(b + ch * 8 + 2 * t); bb += __ldg(b + ch * 8 + 2 * t + 1); }
+        }
         o[t] = __floats2half2_rn(a, bb);
       }
       *reinterpret_cast<uint4 *>(yp + ch * 8) = *reinterpret_cast<uint4 *>(o);
     }
+  }
   }
 }
 
@@ -235,36 +252,43 @@ __global__ void k_fourier(const float *__restrict__ xyz, __half *__restrict__ ou
 __global__ void k_head_fwd(const __half *__restrict__ x, long long ldx, const float *__restrict__ lw, const float *__restrict__ lb, float eps,
                            const float *__restrict__ wo, float bo, const int *__restrict__ idx, float *__restrict__ out, long long rows) {
   constexpr int W = 1024, CPL = 4;
-  const long long r = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-  if (r >= rows) return;
   const int lane = threadIdx.x & 31;
-  const __half *xp = x + r * ldx;
-  float v[CPL][8];
-  float s = 0.f;
-#pragma unroll
-  for (int c = 0; c < CPL; ++c) {
-    uint4 u = *reinterpret_cast<const uint4 *>(xp + (lane + 32 * c) * 8);
-    const __half2 *h = reinterpret_cast<const __half2 *>(&u);
-#pragma unroll
-    for (int t = 0; t < 4; ++t) { float2 f = __half22float2(h[t]); v[c][2 * t] = f.x; v[c][2 * t + 1] = f.y; s += f.x + f.y; }
-  }
-  const float mean = warp_sum(s) * (1.f / W);
-  float q = 0.f;
-#pragma unroll
-  for (int c = 0; c < CPL; ++c)
-#pragma unroll
-    for (int t = 0; t < 8; ++t) { const float d = v[c][t] - mean; q += d * d; }
-  const float rstd = rsqrtf(warp_sum(q) * (1.f / W) + eps);
-  float acc = 0.f;
+  // w_out . (xhat * lw + lb) = sum_c xhat_c (lw_c wo_c) + sum_c lb_c wo_c: persistent warps keep this lane's 32 products
+  // in registers and the constant once (read per row, the 96 scalar parameter loads per lane dominated the kernel)
+  float a[CPL][8];
+  float c0 = 0.f;
 #pragma unroll
   for (int c = 0; c < CPL; ++c)
 #pragma unroll
     for (int t = 0; t < 8; ++t) {
       const int col = (lane + 32 * c) * 8 + t;
-      acc += ((v[c][t] - mean) * rstd * __ldg(lw + col) + __ldg(lb + col)) * __ldg(wo + col);
+      const float o = __ldg(wo + col);
+      a[c][t] = __ldg(lw + col) * o;
+      c0 += __ldg(lb + col) * o;
     }
-  acc = warp_sum(acc);
-  if (lane == 0) out[idx ? idx[r] : r] = -(acc + bo);
+  c0 = warp_sum(c0) + bo;
+  const long long warps = (long long)gridDim.x * (blockDim.x >> 5);
+  for (long long r = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); r < rows; r += warps) {
+    const __half *xp = x + r * ldx;
+    float v[CPL][8];
+    float s = 0.f;
+#pragma unroll
+    for (int c = 0; c < CPL; ++c) {
+      uint4 u = *reinterpret_cast<const uint4 *>(xp + (lane + 32 * c) * 8);
+      const __half2 *h = reinterpret_cast<const __half2 *>(&u);
+#pragma unroll
+      for (int t = 0; t < 4; ++t) { float2 f = __half22float2(h[t]); v[c][2 * t] = f.x; v[c][2 * t + 1] = f.y; s += f.x + f.y; }
+    }
+    const float mean = warp_sum(s) * (1.f / W);
+    float q = 0.f, acc = 0.f;
+#pragma unroll
+    for (int c = 0; c < CPL; ++c)
+#pragma unroll
+      for (int t = 0; t < 8; ++t) { const float d = v[c][t] - mean; q += d * d; acc += d * a[c][t]; }
+    const float rstd = rsqrtf(warp_sum(q) * (1.f / W) + eps);
+    acc = warp_sum(acc);
+    if (lane == 0) out[idx ? idx[r] : r] = -(acc * rstd + c0);
+  }
 }
 // backward of the head for the rows that carry a gradient: dlogit = -g_scale * dS[idx ? idx[r] : r];
 // dx = LN_bwd(dlogit * w_out)   (fp16, scaled by the caller's loss scale through g_scale)
@@ -486,7 +510,8 @@ extern "C" int foho_dec_layernorm(const void *x, int32_t inner_x, int64_t ldo_x,
   if (width == 64)
     k_ln_fwd<64><<<g, 256, 0, st>>>((const __half *)x, inner_x, ldo_x, ldi_x, w, b, eps, (__half *)y, inner_y, ldo_y, ldi_y, rows);
   else
-    k_ln_fwd<1024><<<g, 256, 0, st>>>((const __half *)x, inner_x, ldo_x, ldi_x, w, b, eps, (__half *)y, inner_y, ldo_y, ldi_y, rows);
+    k_ln_fwd<1024><<<g < 148 * 2 ? g : 148 * 2, 256, 0, st>>>((const __half *)x, inner_x, ldo_x, ldi_x, w, b, eps, (__half *)y, inner_y, ldo_y,
+                                                              ldi_y, rows);
   FOHO_LAUNCH_CHECK();
   return 0;
 }
@@ -540,8 +565,9 @@ extern "C" int foho_dec_head(const void *x, int64_t ldx, const float *ln_w, cons
                              const int32_t *idx, float *out, int64_t rows, void *cuda_stream) {
   if (!x || !ln_w || !ln_b || !w_out || !out) return FOHO_E_NULL;
   if (rows <= 0 || ldx % 8) return FOHO_E_SHAPE;
-  k_head_fwd<<<blocks_for(rows, 8), 256, 0, reinterpret_cast<cudaStream_t>(cuda_stream)>>>((const __half *)x, ldx, ln_w, ln_b, eps, w_out,
-                                                                                            b_out, idx, out, rows);
+  const int hg = blocks_for(rows, 8);
+  k_head_fwd<<<hg < 148 * 6 ? hg : 148 * 6, 256, 0, reinterpret_cast<cudaStream_t>(cuda_stream)>>>((const __half *)x, ldx, ln_w, ln_b, eps, w_out,
+                                                                                                    b_out, idx, out, rows);
   FOHO_LAUNCH_CHECK();
   return 0;
 }
