@@ -103,9 +103,14 @@ __global__ void k_ln_bwd(const __half *__restrict__ x, int inner_x, long long ld
                          __half *__restrict__ dx, int inner_dx, long long ldo_dx, long long ldi_dx, long long rows) {
   constexpr int CH = W / 8;
   constexpr int CPL = (CH + 31) / 32;
-  const long long r = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-  if (r >= rows) return;
   const int lane = threadIdx.x & 31;
+  float wr[CPL][8];                               // persistent warps: this lane's weights stay in registers
+#pragma unroll
+  for (int c = 0; c < CPL; ++c)
+#pragma unroll
+    for (int t = 0; t < 8; ++t) wr[c][t] = (w && lane + 32 * c < CH) ? __ldg(w + (lane + 32 * c) * 8 + t) : 1.f;
+  const long long warps = (long long)gridDim.x * (blockDim.x >> 5);
+  for (long long r = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); r < rows; r += warps) {
   const __half *xp = x + row_off(r, inner_x, ldo_x, ldi_x);
   const __half *gp = dy + row_off(r, inner_dy, ldo_dy, ldi_dy);
   float v[CPL][8], g[CPL][8];
@@ -122,8 +127,8 @@ __global__ void k_ln_bwd(const __half *__restrict__ x, int inner_x, long long ld
       for (int t = 0; t < 4; ++t) {
         float2 f = __half22float2(h[t]); v[c][2 * t] = f.x; v[c][2 * t + 1] = f.y; s += f.x + f.y;
         float2 fg = __half22float2(hg[t]);
-        g[c][2 * t] = fg.x * (w ? __ldg(w + ch * 8 + 2 * t) : 1.f);
-        g[c][2 * t + 1] = fg.y * (w ? __ldg(w + ch * 8 + 2 * t + 1) : 1.f);
+        g[c][2 * t] = fg.x * wr[c][2 * t];
+        g[c][2 * t + 1] = fg.y * wr[c][2 * t + 1];
       }
     } else {
 #pragma unroll
@@ -164,6 +169,105 @@ __global__ void k_ln_bwd(const __half *__restrict__ x, int inner_x, long long ld
 #pragma unroll
       for (int t = 0; t < 4; ++t) oh[t] = __floats2half2_rn(o[2 * t], o[2 * t + 1]);
       *reinterpret_cast<uint4 *>(dx + off_dx + ch * 8) = *reinterpret_cast<uint4 *>(oh);
+    }
+  }
+  }
+}
+
+// Width 64 (the per-head q_norm / k_norm): eight lanes per row, four rows per warp, persistent warps with this lane's eight
+// weights (and biases) in registers.  (The generic kernel above leaves 24 of 32 lanes idle at this width and re-reads the
+// parameters per row: 4x the warps and 16 scalar loads per lane and row.)
+__device__ __forceinline__ float group8_sum(float v) {
+  v += __shfl_xor_sync(0xffffffffu, v, 1); v += __shfl_xor_sync(0xffffffffu, v, 2); v += __shfl_xor_sync(0xffffffffu, v, 4);
+  return v;
+}
+__global__ void k_ln64_fwd(const __half *__restrict__ x, int inner_x, long long ldo_x, long long ldi_x, const float *__restrict__ w,
+                           const float *__restrict__ b, float eps, __half *__restrict__ y, int inner_y, long long ldo_y, long long ldi_y,
+                           long long rows) {
+  const int lane = threadIdx.x & 31, sub = lane & 7, grp = lane >> 3;
+  float wr[8], br[8];
+#pragma unroll
+  for (int t = 0; t < 8; ++t) { wr[t] = w ? __ldg(w + sub * 8 + t) : 1.f; br[t] = b ? __ldg(b + sub * 8 + t) : 0.f; }
+  const long long warps = (long long)gridDim.x * (blockDim.x >> 5);
+  for (long long base = ((long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * 4; base < rows; base += warps * 4) {
+    const long long r = base + grp;
+    const bool live = r < rows;
+    float v[8];
+    float s = 0.f;
+    if (live) {
+      uint4 u = *reinterpret_cast<const uint4 *>(x + row_off(r, inner_x, ldo_x, ldi_x) + sub * 8);
+      const __half2 *h = reinterpret_cast<const __half2 *>(&u);
+#pragma unroll
+      for (int t = 0; t < 4; ++t) { float2 f = __half22float2(h[t]); v[2 * t] = f.x; v[2 * t + 1] = f.y; s += f.x + f.y; }
+    } else {
+#pragma unroll
+      for (int t = 0; t < 8; ++t) v[t] = 0.f;
+    }
+    const float mean = group8_sum(s) * (1.f / 64);
+    float q = 0.f;
+#pragma unroll
+    for (int t = 0; t < 8; ++t) { const float d = v[t] - mean; q += d * d; }
+    const float rstd = rsqrtf(group8_sum(q) * (1.f / 64) + eps);
+    if (live) {
+      __align__(16) __half2 o[4];
+#pragma unroll
+      for (int t = 0; t < 4; ++t)
+        o[t] = __floats2half2_rn((v[2 * t] - mean) * rstd * wr[2 * t] + br[2 * t], (v[2 * t + 1] - mean) * rstd * wr[2 * t + 1] + br[2 * t + 1]);
+      *reinterpret_cast<uint4 *>(y + row_off(r, inner_y, ldo_y, ldi_y) + sub * 8) = *reinterpret_cast<uint4 *>(o);
+    }
+  }
+}
+__global__ void k_ln64_bwd(const __half *__restrict__ x, int inner_x, long long ldo_x, long long ldi_x, const float *__restrict__ w, float eps,
+                           const __half *__restrict__ dy, int inner_dy, long long ldo_dy, long long ldi_dy, const __half *__restrict__ add,
+                           __half *__restrict__ dx, int inner_dx, long long ldo_dx, long long ldi_dx, long long rows) {
+  const int lane = threadIdx.x & 31, sub = lane & 7, grp = lane >> 3;
+  float wr[8];
+#pragma unroll
+  for (int t = 0; t < 8; ++t) wr[t] = w ? __ldg(w + sub * 8 + t) : 1.f;
+  const long long warps = (long long)gridDim.x * (blockDim.x >> 5);
+  for (long long base = ((long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * 4; base < rows; base += warps * 4) {
+    const long long r = base + grp;
+    const bool live = r < rows;
+    float v[8], g[8];
+    float s = 0.f;
+    if (live) {
+      uint4 u = *reinterpret_cast<const uint4 *>(x + row_off(r, inner_x, ldo_x, ldi_x) + sub * 8);
+      uint4 ug = *reinterpret_cast<const uint4 *>(dy + row_off(r, inner_dy, ldo_dy, ldi_dy) + sub * 8);
+      const __half2 *h = reinterpret_cast<const __half2 *>(&u), *hg = reinterpret_cast<const __half2 *>(&ug);
+#pragma unroll
+      for (int t = 0; t < 4; ++t) {
+        float2 f = __half22float2(h[t]); v[2 * t] = f.x; v[2 * t + 1] = f.y; s += f.x + f.y;
+        float2 fg = __half22float2(hg[t]); g[2 * t] = fg.x * wr[2 * t]; g[2 * t + 1] = fg.y * wr[2 * t + 1];
+      }
+    } else {
+#pragma unroll
+      for (int t = 0; t < 8; ++t) { v[t] = 0.f; g[t] = 0.f; }
+    }
+    const float mean = group8_sum(s) * (1.f / 64);
+    float q = 0.f;
+#pragma unroll
+    for (int t = 0; t < 8; ++t) { const float d = v[t] - mean; q += d * d; }
+    const float rstd = rsqrtf(group8_sum(q) * (1.f / 64) + eps);
+    float sg = 0.f, sgx = 0.f;
+#pragma unroll
+    for (int t = 0; t < 8; ++t) { const float xh = (v[t] - mean) * rstd; sg += g[t]; sgx += g[t] * xh; }
+    sg = group8_sum(sg) * (1.f / 64);
+    sgx = group8_sum(sgx) * (1.f / 64);
+    if (live) {
+      const long long off_dx = row_off(r, inner_dx, ldo_dx, ldi_dx) + sub * 8;
+      float o[8];
+#pragma unroll
+      for (int t = 0; t < 8; ++t) { const float xh = (v[t] - mean) * rstd; o[t] = rstd * (g[t] - sg - xh * sgx); }
+      if (add) {
+        uint4 ua = *reinterpret_cast<const uint4 *>(add + off_dx);
+        const __half2 *ha = reinterpret_cast<const __half2 *>(&ua);
+#pragma unroll
+        for (int t = 0; t < 4; ++t) { float2 f = __half22float2(ha[t]); o[2 * t] += f.x; o[2 * t + 1] += f.y; }
+      }
+      __align__(16) __half2 oh[4];
+#pragma unroll
+      for (int t = 0; t < 4; ++t) oh[t] = __floats2half2_rn(o[2 * t], o[2 * t + 1]);
+      *reinterpret_cast<uint4 *>(dx + off_dx) = *reinterpret_cast<uint4 *>(oh);
     }
   }
 }
@@ -507,8 +611,11 @@ extern "C" int foho_dec_layernorm(const void *x, int32_t inner_x, int64_t ldo_x,
   if (ldo_x % 8 || ldi_x % 8 || ldo_y % 8 || ldi_y % 8) return FOHO_E_ARG;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(cuda_stream);
   const int g = blocks_for(rows, 8);
-  if (width == 64)
-    k_ln_fwd<64><<<g, 256, 0, st>>>((const __half *)x, inner_x, ldo_x, ldi_x, w, b, eps, (__half *)y, inner_y, ldo_y, ldi_y, rows);
+  if (width == 64) {
+    const int g4 = blocks_for((rows + 3) / 4, 8);
+    k_ln64_fwd<<<g4 < 148 * 8 ? g4 : 148 * 8, 256, 0, st>>>((const __half *)x, inner_x, ldo_x, ldi_x, w, b, eps, (__half *)y, inner_y, ldo_y,
+                                                            ldi_y, rows);
+  }
   else
     k_ln_fwd<1024><<<g < 148 * 2 ? g : 148 * 2, 256, 0, st>>>((const __half *)x, inner_x, ldo_x, ldi_x, w, b, eps, (__half *)y, inner_y, ldo_y,
                                                               ldi_y, rows);
@@ -524,11 +631,13 @@ extern "C" int foho_dec_layernorm_bwd(const void *x, int32_t inner_x, int64_t ld
   if (ldo_x % 8 || ldi_x % 8 || ldo_dy % 8 || ldi_dy % 8 || ldo_dx % 8 || ldi_dx % 8) return FOHO_E_ARG;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(cuda_stream);
   const int g = blocks_for(rows, 8);
-  if (width == 64)
-    k_ln_bwd<64><<<g, 256, 0, st>>>((const __half *)x, inner_x, ldo_x, ldi_x, w, eps, (const __half *)dy, inner_dy, ldo_dy, ldi_dy,
-                                     (const __half *)add, (__half *)dx, inner_dx, ldo_dx, ldi_dx, rows);
+  if (width == 64) {
+    const int g4 = blocks_for((rows + 3) / 4, 8);
+    k_ln64_bwd<<<g4 < 148 * 8 ? g4 : 148 * 8, 256, 0, st>>>((const __half *)x, inner_x, ldo_x, ldi_x, w, eps, (const __half *)dy, inner_dy,
+                                                            ldo_dy, ldi_dy, (const __half *)add, (__half *)dx, inner_dx, ldo_dx, ldi_dx, rows);
+  }
   else
-    k_ln_bwd<1024><<<g, 256, 0, st>>>((const __half *)x, inner_x, ldo_x, ldi_x, w, eps, (const __half *)dy, inner_dy, ldo_dy, ldi_dy,
+    k_ln_bwd<1024><<<g < 148 * 2 ? g : 148 * 2, 256, 0, st>>>((const __half *)x, inner_x, ldo_x, ldi_x, w, eps, (const __half *)dy, inner_dy, ldo_dy, ldi_dy,
                                        (const __half *)add, (__half *)dx, inner_dx, ldo_dx, ldi_dx, rows);
   FOHO_LAUNCH_CHECK();
   return 0;
