@@ -192,10 +192,13 @@ def run(
     seed: int = 2,
     obj_cap_factor: int = 6,
     latent_dtype: Optional[torch.dtype] = None,
+    export_resolution: Optional[int] = None,
 ) -> None:
     """Positional/keyword arguments up to ``task_list_file`` are the reference's (run.py:188-199).  ``latent_dtype``: the dtype
     the latents and the model output being optimised are carried in -- default: half with the reference's own networks
-    on the tensor cores (a model with ``tc_decoder``; the reference's pipeline is half, pipelines.py:1204), float otherwise."""
+    on the tensor cores (a model with ``tc_decoder``; the reference's pipeline is half, pipelines.py:1204), float otherwise.
+    ``export_resolution``: octree resolution of the FINAL decode with a ``tc_decoder`` model -- default 384 like the
+    reference (pipelines.py:1624-1641: a 385^3 lattice, 57 M queries, surface extracted from it); 0 = the loop's lattice."""
     del project_root                      # the reference only uses it to extend sys.path (run.py:57-62)
     if model is None:
         model = load_model_from_env()
@@ -236,7 +239,7 @@ def run(
     for chunk in batches_of_compatible_images(todo, batch_size):
         idx = [p["index"] for p, _ in chunk]
         try:
-            _run_batch(chunk, model, J, config, n_cloud, dev, seed, GuidanceLoop, obj_cap_factor, latent_dtype)
+            _run_batch(chunk, model, J, config, n_cloud, dev, seed, GuidanceLoop, obj_cap_factor, latent_dtype, export_resolution)
             for i in idx:
                 print(f"Reconstructed object {i}")
         except Exception as e:
@@ -248,7 +251,7 @@ def run(
             print(f"Error in reconstruction for batch {idx} : {e}; retrying its images one by one")
             for item in chunk:
                 try:
-                    _run_batch([item], model, J, config, n_cloud, dev, seed, GuidanceLoop, obj_cap_factor, latent_dtype)
+                    _run_batch([item], model, J, config, n_cloud, dev, seed, GuidanceLoop, obj_cap_factor, latent_dtype, export_resolution)
                     print(f"Reconstructed object {item[0]['index']}")
                 except Exception as e1:
                     print(f"Error in reconstruction for {item[0]['index']} : {e1}")
@@ -278,7 +281,8 @@ def batches_of_compatible_images(todo: list, batch_size: int) -> List[list]:
 
 
 def _run_batch(chunk, model: GuidanceModel, J: torch.Tensor, config: OptimizationConfig, n_cloud: int, dev, seed: int,
-               GuidanceLoop, obj_cap_factor: int = 6, latent_dtype: Optional[torch.dtype] = None) -> None:
+               GuidanceLoop, obj_cap_factor: int = 6, latent_dtype: Optional[torch.dtype] = None,
+               export_resolution: Optional[int] = None) -> None:
     B = len(chunk)
     inputs = [inp for _, inp in chunk]
     faces0 = inputs[0]["faces"]
@@ -300,6 +304,7 @@ def _run_batch(chunk, model: GuidanceModel, J: torch.Tensor, config: Optimizatio
     model.begin_batch([p["index"] for p, _ in chunk], [p["cropped_obj_img_path"] for p, _ in chunk], dev)
     debug_root = os.environ.get("FOHO_DEBUG_DIR")               # pipelines.py:1076-1091: debug dumps when set
     gen = torch.Generator().manual_seed(seed)                   # run.py:120 torch.manual_seed(2)
+    export_meshes = None                                        # tensor-core decoder path: surfaces of the final decode
     last = config.num_inference_steps - 1
     decode = getattr(model, "decode", None)
     tc_decoder = getattr(model, "tc_decoder", None)
@@ -327,7 +332,19 @@ def _run_batch(chunk, model: GuidanceModel, J: torch.Tensor, config: Optimizatio
         loop.check_overflow()
         loop._obj.ex.check_flags()                              # a truncated surface = wrong terms: fail loudly
         x1 = (loop.x_t + (1.0 - float(loop.sigmas[last])) * loop.velocity).contiguous()      # final decode (:1641), sigma_last = 1
-        sdf = dec.forward(x1.view(B, 3072, 64)).reshape(B, model.D, model.D, model.D).cpu().numpy()
+        # the final step re-grids to octree resolution 384 (:1624-1641) and extracts the surface from THAT volume
+        res = 384 if export_resolution is None else int(export_resolution)
+        eD = res + 1 if res > 0 else model.D
+        sdf_dev = (dec.forward(x1.view(B, 3072, 64)) if eD == model.D else dec.decode_lattice(x1.view(B, 3072, 64), eD)).view(B, eD, eD, eD)
+        from .surface import SurfaceExtractor
+        ex = SurfaceExtractor(1, eD, device=dev, cap_verts=int(obj_cap_factor) * eD * eD, with_edges=False)
+        export_meshes = []
+        for b in range(B):                                      # one image at a time: 385^3 floats and its surface per pass
+            ex.extract(sdf_dev[b:b + 1])
+            ex.check_flags()
+            v, f, _ = ex.meshes()[0]
+            export_meshes.append((v.numpy().astype(np.float64), f.numpy()))
+        sdf = None
     elif callable(decode):
         # a differentiable network decoder in the loop (eager; autograd carries dE/dSDF to the model output)
         loop = GuidanceLoop(B, model.D, st, n_cloud, device=dev, config=config, latent_elems=model.latent_elems,
@@ -368,7 +385,7 @@ def _run_batch(chunk, model: GuidanceModel, J: torch.Tensor, config: Optimizatio
             continue
         hand = inp["hand_moge"].astype(np.float64)
         ch = (hand.min(0) + hand.max(0)) / 2.0
-        verts, faces = model.extract_mesh(sdf[b])
+        verts, faces = export_meshes[b] if export_meshes is not None else model.extract_mesh(sdf[b])
         T = inp["T_h2m"].astype(np.float64)
         try:                                                               # run.py:155-167
             vm = np.asarray(verts, dtype=np.float64).reshape(-1, 3) @ T[:3, :3].T + T[:3, 3]

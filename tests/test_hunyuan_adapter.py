@@ -65,7 +65,8 @@ def test_stage_runs_with_the_tensor_core_decoder(tmp_path, capsys):
     cfg.with_steps(6)
     model = HunyuanGuidanceModel(_standin_pipe(device="cuda:0"), cfg, D=D, device="cuda:0")
     # the stand-in decoder has random weights: its volume is noise with a large surface -> generous extraction capacity
-    R.run(**_kwargs(d), model=model, batch_size=2, n_cloud=512, config=cfg, j_regressor_path=jpath, obj_cap_factor=24)
+    R.run(**_kwargs(d), model=model, batch_size=2, n_cloud=512, config=cfg, j_regressor_path=jpath, obj_cap_factor=24,
+          export_resolution=20)
     out = capsys.readouterr().out
     assert "Finished processing all images" in out and "Error" not in out, out
     produced = sorted(os.listdir(d["out"]))
@@ -95,6 +96,7 @@ def test_stage_with_moge_mesh_runs_every_image_term(tmp_path, capsys):
     cfg.optimization_steps_hand, cfg.optimization_steps_scale, cfg.optimization_steps_joint = 2, 2, 2
     cfg.with_steps(6)
     model = HunyuanGuidanceModel(_standin_pipe(device="cuda:0"), cfg, D=D, device="cuda:0")
-    R.run(**_kwargs(d), model=model, batch_size=2, n_cloud=512, config=cfg, j_regressor_path=jpath, obj_cap_factor=24)
+    R.run(**_kwargs(d), model=model, batch_size=2, n_cloud=512, config=cfg, j_regressor_path=jpath, obj_cap_factor=24,
+          export_resolution=20)
     out = capsys.readouterr().out
     assert "Finished processing all images" in out and "Error" not in out, out
