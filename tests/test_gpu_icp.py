@@ -226,3 +226,26 @@ def test_batched_sharded_alignment_stage_equals_one_image_at_a_time(tmp_path, mo
         b = meshio.load(str(tmp_path / f"one_{i}.ply")).vertices
         assert np.array_equal(a, b)
     assert np.array_equal(np.load(tmp_path / "rt_rank1" / "07_hoi_mesh.npy"), np.load(tmp_path / "rt" / "07_hoi_mesh.npy"))
+
+
+@pytest.mark.gpu
+def test_batch_launch_with_mixed_paths_and_edge_sizes():
+    """One ``foho_icp_run_batch`` call over problems that take different paths: a target below 1 024 points (launch pairs,
+    brute-force 1-NN), a large one (persistent loop), a single iteration, no trimming, and a source with fewer points than
+    one warp's worth of CTAs -- each equal to its own ``icp_points`` run and to the oracle."""
+    from followmyhold_b200.alignment.mesh_align import icp_points, icp_points_many
+    from oracle import icp_oracle as O
+    specs = [(300, 700, 0.2), (2500, 6000, 0.2), (40, 3000, 0.0), (1500, 1024, 0.1)]
+    probs, outs = [], []
+    for k, (ns, nt, frac) in enumerate(specs):
+        src, tgt, _ = _clouds(ns, nt, seed=50 + k)
+        probs.append((src, tgt)); outs.append(int(frac * ns))
+    for n_iter in (1, 12):
+        many = icp_points_many(probs, n_iter, outs, False, 0.7, 3.0)
+        for (src, tgt), n_out, (T, c) in zip(probs, outs, many):
+            T1, c1 = icp_points(src, tgt, n_iter, n_out, False, 0.7, 3.0)
+            assert np.array_equal(T, T1) and c == c1
+            To, co = O.icp_points(src, tgt, n_iter, n_out, False, 0.7, 3.0)[:2]
+            np.testing.assert_allclose(T, To, rtol=0, atol=1e-8)
+            assert abs(c - co) <= 1e-10 * max(1.0, abs(co))
+    assert icp_points_many([], 5, 0) == []
