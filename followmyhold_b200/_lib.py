@@ -17,7 +17,7 @@ REPO_ROOT = PKG_DIR.parent
 CSRC = PKG_DIR / "csrc"
 LIB_PATH = PKG_DIR / "libfoho_b200.so"
 SOURCES = ["guidance_stream.cu", "guidance_sparse.cu", "guidance_objmesh.cu", "guidance_chamfer.cu", "guidance_voxdist.cu", "guidance_update.cu", "icp.cu", "mesh_sample.cu",
-           "mesh_sdf.cu", "mesh_decimate.cu", "decoder_gemm.cu", "decoder_attn.cu", "decoder_attn_bwd.cu", "decoder_ops.cu", "guidance_raster.cu", "guidance_dmc.cu"]
+           "mesh_sdf.cu", "mesh_decimate.cpp", "decoder_gemm.cu", "decoder_attn.cu", "decoder_attn_bwd.cu", "decoder_ops.cu", "guidance_raster.cu", "guidance_dmc.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "-Xcompiler", "-fPIC", "-Xcompiler", "-O3"]
 

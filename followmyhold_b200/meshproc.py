@@ -15,7 +15,7 @@ unpinned"):
 * ``DegenerateFaceRemover`` -> a save / re-load round trip through a PLY file; here: faces with a repeated
   vertex index or zero area, and vertices no face references, are dropped;
 * ``FaceReducer`` -> ``meshing_decimation_quadric_edge_collapse(targetfacenum=40000, preserveboundary,
-  boundaryweight=3, preservenormal, preservetopology)``: ``foho_mesh_decimate`` (csrc/mesh_decimate.cu, host
+  boundaryweight=3, preservenormal, preservetopology)``: ``foho_mesh_decimate`` (csrc/mesh_decimate.cpp, host
   code in the C-ABI library).
 """
 from __future__ import annotations
