@@ -66,7 +66,7 @@ def _stale() -> bool:
     if not LIB_PATH.exists():
         return True
     t = LIB_PATH.stat().st_mtime
-    deps = list(CSRC.glob("*.cu")) + list(CSRC.glob("*.cuh")) + [REPO_ROOT / "include" / "foho_b200.h"]
+    deps = list(CSRC.glob("*.cu")) + list(CSRC.glob("*.cuh")) + list(CSRC.glob("*.cpp")) + [REPO_ROOT / "include" / "foho_b200.h"]
     return any(d.stat().st_mtime > t for d in deps)
 
 
