@@ -647,8 +647,17 @@ __device__ __forceinline__ double icp_warp_min_nonneg(double v) {
 // Exact 1-NN of one transformed source point in the box hierarchy, one warp.  Same result as k_icp_nn_tree (smallest
 // squared distance, ties -> smallest ORIGINAL index); every lane keeps the best of the points IT looked at and only
 // the pruning bound is warp-uniform, so a group costs two redux.sync instead of a three-value shuffle tree.
+#ifdef FOHO_ICP_PROFILE
+__device__ long long g_nn_prof[8];      // groups scanned, supers scanned, points, cycles: seed, supers, total
+#define NN_COUNT(k, v) do { if (threadIdx.x == 0 && blockIdx.x == 0 && blockIdx.y == 0) g_nn_prof[k] += (long long)(v); } while (0)
+#else
+#define NN_COUNT(k, v) do { } while (0)
+#endif
 __device__ __forceinline__ void icp_nn_point(const IcpWorkspace &w, int Nt, int lane, double px, double py, double pz,
                                              int seed, double &d2_out, int &idx_out, int &pos_out) {
+#ifdef FOHO_ICP_PROFILE
+  const long long tp0 = clock64();
+#endif
   double bd = INFINITY, bound = INFINITY;
   int bidx = 0x7fffffff, bpos = -1;
   auto take = [&](double d2, int idx, int s) {
@@ -662,6 +671,7 @@ __device__ __forceinline__ void icp_nn_point(const IcpWorkspace &w, int Nt, int 
       take(dx * dx + dy * dy + dz * dz, __ldg(w.tidx + s), s);
     }
     bound = icp_warp_min_nonneg(bd);
+    NN_COUNT(0, 1);
   };
   // two groups per step: their loads are in flight together and the bound is folded once
   auto scan_group2 = [&](int ga, int gb) {
@@ -674,8 +684,10 @@ __device__ __forceinline__ void icp_nn_point(const IcpWorkspace &w, int Nt, int 
     if (va) { const double dx = px - ax, dy = py - ay, dz = pz - az; take(dx * dx + dy * dy + dz * dz, ia, sa); }
     if (vb) { const double dx = px - bx, dy = py - by, dz = pz - bz; take(dx * dx + dy * dy + dz * dz, ib, sb); }
     bound = icp_warp_min_nonneg(bd);
+    NN_COUNT(0, 2);
   };
   auto scan_super = [&](int sg, int skip) {
+    NN_COUNT(1, 1);
     const int g = sg * 32 + lane;
     double lb = INFINITY;
     if (g < w.NG && g != skip) lb = icp_box_d2(w.glo + 3 * (size_t)g, w.ghi + 3 * (size_t)g, px, py, pz);
@@ -697,6 +709,9 @@ __device__ __forceinline__ void icp_nn_point(const IcpWorkspace &w, int Nt, int 
   if (seed >= 0 && seed < Nt) {
     g0 = seed >> 5;
     scan_group(g0);
+#ifdef FOHO_ICP_PROFILE
+    NN_COUNT(3, clock64() - tp0);
+#endif
   } else {
     double bl = INFINITY; int bs = 0;
     for (int s = lane; s < w.NS; s += 32) {
@@ -733,6 +748,9 @@ __device__ __forceinline__ void icp_nn_point(const IcpWorkspace &w, int Nt, int 
       mask &= __ballot_sync(0xffffffffu, lb <= bound);
     }
   }
+#ifdef FOHO_ICP_PROFILE
+  NN_COUNT(2, 1); NN_COUNT(5, clock64() - tp0);
+#endif
   const unsigned int cand = bd == bound ? (unsigned int)bidx : 0xffffffffu;
   unsigned int midx = __reduce_min_sync(0xffffffffu, cand);
   const unsigned int who = __ballot_sync(0xffffffffu, bd == bound && (unsigned int)bidx == midx);
@@ -1151,6 +1169,8 @@ __global__ void __launch_bounds__(LOOP_THREADS, 1) k_icp_loop(const IcpProblem s
   }
 #ifdef FOHO_ICP_PROFILE
   if (tid == 0 && (c == 0 || c == G - 1) && blockIdx.y == 0)
+    if (c == 0) printf("icp nn per point: groups %.2f supers %.2f cycles seed-scan %.0f total %.0f (points %lld)\n", (double)g_nn_prof[0] / g_nn_prof[2],
+                       (double)g_nn_prof[1] / g_nn_prof[2], (double)g_nn_prof[3] / g_nn_prof[2], (double)g_nn_prof[5] / g_nn_prof[2], g_nn_prof[2]);
     printf("icp profile cta %d/%d: cycles per iteration  nn %lld  bar1 %lld  select %lld  sums %lld  bar2 %lld  fit %lld | select: load %lld rest %lld passes x100 %lld\n", c, G,
            prof[0] / P.n_iter, prof[1] / P.n_iter, prof[2] / P.n_iter, prof[3] / P.n_iter, prof[4] / P.n_iter, prof[5] / P.n_iter,
            prof2[0] / P.n_iter, prof2[1] / P.n_iter, 100 * prof2[2] / P.n_iter);
