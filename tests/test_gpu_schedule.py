@@ -204,7 +204,7 @@ def test_half_latents_through_the_loop():
                                                 lp.alpha, sp) == 0
     want = lp.sdf0.view(B, vol).clone()
     want[:, lp.tap] = want[:, lp.tap] + lp.alpha * x1.float()
-    assert torch.allclose(lp.sdf.view(B, vol), want, rtol=0, atol=2e-7)                    # fused multiply-add vs two roundings
+    assert torch.allclose(lp.sdf.view(B, vol), want, rtol=1e-6, atol=1e-6)                 # fused multiply-add vs two roundings
     gs = torch.randn(B, vol, device="cuda")
     gv = torch.empty(B, L, device="cuda", dtype=torch.float16)
     assert lp.lib.foho_mock_decoder_backward_f16(gs.data_ptr(), lp.tap.data_ptr(), gv.data_ptr(), B, vol, L, 0.25, sp) == 0
