@@ -778,7 +778,12 @@ class GuidanceLoop:
                 with torch.cuda.stream(s):
                     if sdf0_h is not None:
                         self.sdf0.copy_(st["sdf0_h16"] if sdf0_h.dtype == torch.float16 else st["sdf0"])
-                    self.sdf.copy_(self.sdf0)
+                    # the stand-in decoder rewrites the tapped voxels of `sdf` from x1 at every evaluation and nothing writes
+                    # the others: `sdf` only has to be re-based when the base volume changed since the last re-base (torch's
+                    # version counters see every in-place torch op on either tensor; the kernels touch taps only)
+                    if getattr(self, "_sdf_based", None) != (self.sdf0._version, self.sdf._version):
+                        self.sdf.copy_(self.sdf0)
+                        self._sdf_based = (self.sdf0._version, self.sdf._version)
                     self.x_t.copy_(st["x_t"]); self.velocity.copy_(st["velocity"]); self.theta.copy_(st["theta"])
                     self._ev_stage_free[k & 1].record(s)
                     self._graph.replay()

@@ -329,6 +329,15 @@ def test_pipelined_host_api_matches_single_batch_calls():
     for n in ("theta", "velocity", "prev_sample", "terms"):
         assert torch.allclose(a[n], b[0][n], rtol=1e-4, atol=1e-6), n
         assert torch.allclose(b[0][n], b[1][n], rtol=1e-4, atol=1e-6), n
+    # a resident base volume changed in place between two calls is picked up (the decode volume is re-based only then)
+    b1 = {n: t.clone() for n, t in b[1].items()}
+    lp.sdf0.add_(0.05)
+    c = lp.denoise_steps_host(12, [(None,) + batches[0][1:]])[0]
+    c = {n: t.clone() for n, t in c.items()}
+    d = lp.denoise_steps_host(12, [((rounded + 0.05).pin_memory(),) + batches[0][1:]])[0]
+    for n in ("theta", "velocity", "prev_sample", "terms"):
+        assert torch.allclose(c[n], d[n], rtol=1e-4, atol=1e-6), n
+    assert not torch.allclose(c["terms"], b1["terms"], rtol=1e-4, atol=1e-6)
 
 
 @pytest.mark.parametrize("m", [2, 4])
