@@ -307,6 +307,57 @@ def decoder_leg(dev, n_images: int = 1, D_lat: int = 65, n_active: int = 8192, r
 
 
 # --------------------------------------------------------------------------- the reference's own lattices (extra keys)
+def icp_leg(dev, cpu_seconds: float = 2.0):
+    """Row a16 (iterations/s and alignments/s, no roofline claim): the reference's two ICP stages (coarse 50
+    iterations 1 000 / 5 000 points, fine 100 iterations 5 000 / 10 000, 20 % trimmed, scale clip [0.7, 3], h2m.py:35-54) on
+    synthetic clouds, point sets resident, CUDA events; the CPU oracle (scipy cKDTree + numpy, one thread like the
+    reference) on a bounded number of iterations beside it."""
+    import ctypes as C
+    import numpy as np
+    import torch
+    from followmyhold_b200 import _lib
+    from oracle import icp_oracle as IO
+    lib = _lib.load()
+    rng = np.random.default_rng(0)
+    out = {}
+    total_ms = 0.0
+    for name, n_iter, ns, nt in (("coarse", 50, 1000, 5000), ("fine", 100, 5000, 10000)):
+        tgt = rng.normal(size=(nt, 3)) * np.array([1.0, 0.6, 0.3])
+        src = (tgt[rng.choice(nt, ns, replace=False)] - 0.05) / 1.15 + 0.002 * rng.normal(size=(ns, 3))
+        d_src, d_tgt = torch.as_tensor(src).to(dev), torch.as_tensor(tgt).to(dev)
+        nbytes = lib.foho_icp_workspace_bytes(ns, nt)
+        ws = torch.empty(nbytes + 256, dtype=torch.uint8, device=dev)
+        ws_ptr = ws.data_ptr() + ((-ws.data_ptr()) % 256)
+        T = torch.zeros(16, dtype=torch.float64, device=dev)
+        cost = torch.zeros(1, dtype=torch.float64, device=dev)
+        st = torch.cuda.current_stream(dev)
+
+        def call():
+            _lib.check("foho_icp_run", lib.foho_icp_run(d_src.data_ptr(), ns, d_tgt.data_ptr(), nt, n_iter, int(0.2 * ns), 0, 0.7, 3.0,
+                                                        T.data_ptr(), cost.data_ptr(), None, None, C.c_void_p(ws_ptr), nbytes,
+                                                        C.c_void_p(st.cuda_stream)))
+        for _ in range(2):
+            call()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(10):
+            call()
+        e1.record(); torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / 10
+        total_ms += ms
+        k = max(2, min(n_iter, int(cpu_seconds / (0.004 if name == "fine" else 0.001)) // 8))
+        t0 = time.perf_counter()
+        IO.icp_points(src, tgt, k, int(0.2 * ns), False, 0.7, 3.0)
+        cpu_ms_per_iter = (time.perf_counter() - t0) / k * 1e3
+        out[name] = {"n_iter": n_iter, "Ns": ns, "Nt": nt, "ms": ms, "iterations_per_sec": n_iter / ms * 1e3,
+                     "pair_evals_per_sec": ns * nt * n_iter / ms * 1e3, "cpu_oracle_ms_per_iter": cpu_ms_per_iter,
+                     "cpu_sample": f"{k} iterations, 1 thread"}
+    out["alignments_per_sec"] = 1e3 / total_ms
+    out["note"] = "one alignment = coarse + fine run (mesh_align.py:178-217), one persistent launch each; sampling and file I/O not included"
+    return out
+
+
 def reference_lattice_leg(dev, steps: int = 10):
     """Not the headline: the same loop at the reference's real shapes -- B = 8 images on the 65^3
     lattice with the largest cloud (512^2 crop = 262 144 points), 50 evaluations per step, mock latents; and one
@@ -607,6 +658,10 @@ def run_ours(args):
             except Exception as e:
                 line["reference_lattices"] = {"error": f"{type(e).__name__}: {e}"}
             torch.cuda.empty_cache()
+            try:
+                line["icp"] = icp_leg(dev)
+            except Exception as e:
+                line["icp"] = {"error": f"{type(e).__name__}: {e}"}
         if world == 1 and not args.no_cpu:
             os.sched_setaffinity(0, orig_affinity)      # the CPU leg gets every host core back
             eps, cores, n, el = cpu_guidance_evals_per_sec(args.cpu_seconds)
