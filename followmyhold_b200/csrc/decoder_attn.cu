@@ -37,6 +37,7 @@ struct AttnParams {
   float scale_log2;                    // softmax scale * log2(e)
   float *lse2;                         // optional [n_img][heads][lse_stride]: m + log2(l) of the scaled scores (variant 0 only)
   long long lse_stride;
+  int alternate;                       // k_attn_fwd2: the two softmax groups take turns on the exponential phase
 };
 
 __global__ void __launch_bounds__(256, 1)
@@ -265,8 +266,36 @@ k_attn_fwd(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUte
 //   MMA order per key block j:  S_A(j+1), S_B(j+1) (as soon as the groups hold block j in registers), then
 //   [P_A(j) ready -> O_A += P_A V_j]  [P_B(j) ready -> O_B += P_B V_j]
 // ================================================================================================
-constexpr int ATT2_SMEM = 2 * Q_BYTES + KV_STAGES * (K_BYTES + V_BYTES) + 2 * P_BYTES + 1024 + 256;
-constexpr uint32_t T2_S = 0, T2_O = 256;          // S_g at g*128, O_g at 256 + g*64
+// PT = 1 (default since the P-in-TMEM rewrite): P never touches shared memory.  The softmax warps write the fp16
+// probabilities back into TMEM (tcgen05.st, two halves per 32-bit column: lane = query row, column c = keys 2c, 2c+1) and
+// the product O += P V takes its A operand from there (tcgen05.mma [d], [a_tmem], b_desc).  With P in shared memory
+// the P V product reads 6 KB of operands per 32-cycle instruction -- more than the 128 B/clk the shared memory
+// delivers -- while the sixteen 16-byte stores per row and block (2.4 wavefronts each: bank conflicts between the four
+// quarter-warps) compete for the same port; from TMEM the product reads only V, and the 64 KB of P buffers become two
+// more K/V stages.  TMEM: S_A | S_B | O_A | O_B | P_A | P_B = 128 + 128 + 64 + 64 + 64 + 64 = 512 columns.
+#ifdef FOHO_ATTN_TRACE
+// Debug build only (-DFOHO_ATTN_TRACE): SM-clock stamps of CTA 0's second work item, [role][block][event]; role 0 / 1 =
+// lane 0 of the first warp of softmax group A / B, role 2 = the MMA issuer.  Read back with foho_debug_attn_trace.
+__device__ long long g_attn_trace[9][32][8];   // roles 0-3: group A warps, 4-7: group B warps, 8: MMA
+#define ATT_TRACE(role, blk, ev) do { if (blockIdx.x == 0 && w == 1 && (blk) < 32) g_attn_trace[role][blk][ev] = clock64(); } while (0)
+#else
+#define ATT_TRACE(role, blk, ev) do { } while (0)
+#endif
+template <int PT> struct Att2Cfg {
+  static constexpr int STAGES = PT ? 5 : KV_STAGES;
+  static constexpr int SMEM = 2 * Q_BYTES + STAGES * (K_BYTES + V_BYTES) + (PT ? 0 : 2 * P_BYTES) + 1024 + 256;
+};
+constexpr uint32_t T2_S = 0, T2_O = 256, T2_P = 384;          // S_g at g*128, O_g at 256 + g*64, P_g at 384 + g*64
+
+// D[tmem] (+)= A[tmem] * B[smem]: A = 128 lanes x (K/2) columns of packed halves
+__device__ __forceinline__ void mma_f16_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}" ::"r"(d_tmem),
+      "r"(a_tmem), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
 
 __device__ __forceinline__ float ex2_approx(float x) {
   float y;
@@ -274,6 +303,7 @@ __device__ __forceinline__ float ex2_approx(float x) {
   return y;
 }
 
+template <int PT>
 __global__ void __launch_bounds__(384, 1)
 k_attn_fwd2(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK, const __grid_constant__ CUtensorMap tmV,
             const AttnParams p) {
@@ -281,14 +311,15 @@ k_attn_fwd2(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUt
   uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t *sQ = smem;                                           // tile A, tile B
   uint8_t *sKV = sQ + 2 * Q_BYTES;
-  uint8_t *sP = sKV + KV_STAGES * (K_BYTES + V_BYTES);          // P_A, P_B
-  uint64_t *bars = reinterpret_cast<uint64_t *>(sP + 2 * P_BYTES);
+  constexpr int KV_STAGES = Att2Cfg<PT>::STAGES;                // shadows the file-scope constant
+  uint8_t *sP = sKV + KV_STAGES * (K_BYTES + V_BYTES);          // P_A, P_B (PT = 0 only)
+  uint64_t *bars = reinterpret_cast<uint64_t *>(sP + (PT ? 0 : 2 * P_BYTES));
   uint64_t *q_full = bars, *q_empty = bars + 1;
   uint64_t *k_full = bars + 2, *v_full = k_full + KV_STAGES, *kv_empty = v_full + KV_STAGES;
   uint64_t *s_full = kv_empty + KV_STAGES, *s_empty = s_full + 2, *p_full = s_empty + 2, *p_empty = p_full + 2, *o_empty = p_empty + 2;
   uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(o_empty + 2);
 
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = tc::warp_idx_uniform(), lane = threadIdx.x & 31;
   const int nblk = p.n_k / AK;
   const int pair_tiles = (p.q_tiles + 1) / 2;
   const int items_per_img = p.heads * pair_tiles;
@@ -310,33 +341,41 @@ k_attn_fwd2(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUt
   tc::tc_fence_before();
   __syncthreads();
   tc::tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);      // provably warp-uniform
 
   if (warp < 4) {
-    asm volatile("setmaxnreg.dec.sync.aligned.u32 64;");
-    if (warp == 0 && lane == 0) {
-      // ---------------------------------------------------------- TMA producer
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 96;");
+    if (warp == 0) {
+      // ---------------------------------------------------------- TMA producer (whole warp walks the loop, one lane issues)
+      const bool leader = tc::elect_one();
       uint32_t g = 0, w = 0;
       for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++w) {
         const int img = item / items_per_img, r = item - img * items_per_img;
         const int h = r / pair_tiles, pt = r - h * pair_tiles;
         tc::mbar_wait(q_empty, (w & 1) ^ 1);
-        tc::mbar_expect_tx(q_full, 2 * Q_BYTES);
         const int qrow0 = (int)(img * p.q_rows_per_img) + pt * 2 * AQ;
-        tc::tma_load_3d(sQ, &tmQ, q_full, 0, qrow0, h);
-        tc::tma_load_3d(sQ + Q_BYTES, &tmQ, q_full, 0, qrow0 + AQ, h);      // beyond the last row: zero filled
+        if (leader) {
+          tc::mbar_expect_tx(q_full, 2 * Q_BYTES);
+          tc::tma_load_3d(sQ, &tmQ, q_full, 0, qrow0, h);
+          tc::tma_load_3d(sQ + Q_BYTES, &tmQ, q_full, 0, qrow0 + AQ, h);      // beyond the last row: zero filled
+        }
+        __syncwarp();
         for (int j = 0; j < nblk; ++j, ++g) {
           const uint32_t s = g % KV_STAGES, ph = (g / KV_STAGES) & 1;
           tc::mbar_wait(&kv_empty[s], ph ^ 1);
           uint8_t *sk = sKV + s * (K_BYTES + V_BYTES), *sv = sk + K_BYTES;
-          tc::mbar_expect_tx(&k_full[s], K_BYTES);
-          tc::tma_load_3d(sk, &tmK, &k_full[s], 0, img * p.n_k + j * AK, h);
-          tc::mbar_expect_tx(&v_full[s], V_BYTES);
-          tc::tma_load_3d(sv, &tmV, &v_full[s], 0, img * p.n_k + j * AK, h);
+          if (leader) {
+            tc::mbar_expect_tx(&k_full[s], K_BYTES);
+            tc::tma_load_3d(sk, &tmK, &k_full[s], 0, img * p.n_k + j * AK, h);
+            tc::mbar_expect_tx(&v_full[s], V_BYTES);
+            tc::tma_load_3d(sv, &tmV, &v_full[s], 0, img * p.n_k + j * AK, h);
+          }
+          __syncwarp();
         }
       }
-    } else if (warp == 1 && lane == 0) {
-      // ---------------------------------------------------------- MMA issuer
+    } else if (warp == 1) {
+      // ---------------------------------------------------------- MMA issuer (whole warp walks the loop, one lane issues)
+      const bool leader = tc::elect_one();
       constexpr uint32_t idesc_s = tc::idesc_f16(AQ, AK, 0, 0);
       constexpr uint32_t idesc_o = tc::idesc_f16(AQ, HD, 0, 1);
       uint32_t g = 0, w = 0;
@@ -347,11 +386,14 @@ k_attn_fwd2(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUt
         tc::tc_fence_after();
         const uint32_t q_addr = tc::smem_u32(sQ + grp * Q_BYTES);
         const uint32_t k_addr = tc::smem_u32(sKV + s * (K_BYTES + V_BYTES));
+        if (leader) {
 #pragma unroll
-        for (int k = 0; k < HD / 16; ++k)
-          tc::mma_f16_ss(tmem_base + T2_S + grp * 128, tc::smem_desc_sw128(q_addr + k * 32, 16, 1024),
-                         tc::smem_desc_sw128(k_addr + k * 32, 16, 1024), idesc_s, k != 0);
-        tc::mma_commit(&s_full[grp]);
+          for (int k = 0; k < HD / 16; ++k)
+            tc::mma_f16_ss(tmem_base + T2_S + grp * 128, tc::smem_desc_sw128(q_addr + k * 32, 16, 1024),
+                           tc::smem_desc_sw128(k_addr + k * 32, 16, 1024), idesc_s, k != 0);
+          tc::mma_commit(&s_full[grp]);
+        }
+        __syncwarp();
       };
       for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++w) {
         tc::mbar_wait(q_full, w & 1);
@@ -362,27 +404,41 @@ k_attn_fwd2(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUt
           const uint32_t v_addr = tc::smem_u32(sKV + s * (K_BYTES + V_BYTES) + K_BYTES);
           // the next scores first: a softmax group frees its S buffer as soon as the scores are in its registers,
           // so S(j+1) is computed while the group is still exponentiating block j
-          if (j + 1 < nblk) { issue_s(g + 1, 0); issue_s(g + 1, 1); }
-          else tc::mma_commit(q_empty);
+          ATT_TRACE(8, j, 0);
+          if (j + 1 < nblk) { issue_s(g + 1, 0); ATT_TRACE(8, j, 1); issue_s(g + 1, 1); }
+          else { if (leader) tc::mma_commit(q_empty); __syncwarp(); }
+          ATT_TRACE(8, j, 2);
 #pragma unroll
           for (int grp = 0; grp < 2; ++grp) {
             tc::mbar_wait(&p_full[grp], g & 1);
+            ATT_TRACE(8, j, 3 + 2 * grp);
             if (grp == 0) tc::mbar_wait(&v_full[s], ph);
             if (j == 0) tc::mbar_wait(&o_empty[grp], (w & 1) ^ 1);
             tc::tc_fence_after();
-            const uint32_t p_addr = tc::smem_u32(sP + grp * P_BYTES);
+            if (leader) {
+              if (PT) {
 #pragma unroll
-            for (int k = 0; k < AK / 16; ++k)
-              tc::mma_f16_ss(tmem_base + T2_O + grp * 64, tc::smem_desc_sw128(p_addr + (k >> 2) * (AQ * 128) + (k & 3) * 32, 16, 1024),
+                for (int k = 0; k < AK / 16; ++k)
+                  mma_f16_ts(tmem_base + T2_O + grp * 64, tmem_base + T2_P + grp * 64 + k * 8,
                              tc::smem_desc_sw128(v_addr + k * 2048, AK * 128, 1024), idesc_o, (j | k) != 0);
-            tc::mma_commit(&p_empty[grp]);
-            if (grp == 1) tc::mma_commit(&kv_empty[s]);
+              } else {
+                const uint32_t p_addr = tc::smem_u32(sP + grp * P_BYTES);
+#pragma unroll
+                for (int k = 0; k < AK / 16; ++k)
+                  tc::mma_f16_ss(tmem_base + T2_O + grp * 64, tc::smem_desc_sw128(p_addr + (k >> 2) * (AQ * 128) + (k & 3) * 32, 16, 1024),
+                                 tc::smem_desc_sw128(v_addr + k * 2048, AK * 128, 1024), idesc_o, (j | k) != 0);
+              }
+              tc::mma_commit(&p_empty[grp]);
+              if (grp == 1) tc::mma_commit(&kv_empty[s]);
+            }
+            __syncwarp();
+            ATT_TRACE(8, j, 4 + 2 * grp);
           }
         }
       }
     }
   } else {
-    asm volatile("setmaxnreg.inc.sync.aligned.u32 208;");
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 200;");
     // ------------------------------------------------------------ softmax group grp on its query tile
     const int grp = (warp - 4) >> 2;
     const int q = warp & 3;
@@ -390,14 +446,27 @@ k_attn_fwd2(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUt
     const uint32_t lane_off = (uint32_t)(q * 32) << 16;
     const uint32_t s_addr = tmem_base + T2_S + grp * 128 + lane_off;
     const uint32_t o_addr = tmem_base + T2_O + grp * 64 + lane_off;
-    const uint32_t pb_s = tc::smem_u32(sP + grp * P_BYTES + row * 128);
+    const uint32_t pb_s = tc::smem_u32(sP + (PT ? 0 : grp * P_BYTES) + row * 128);
+    const uint32_t p_addr = tmem_base + T2_P + grp * 64 + lane_off;
     uint32_t g = 0, w = 0;
+    // The exponential phase is bound by the MUFU pipe (128 ex2 per thread and block, 16 per clock and SM), everything
+    // else of a block (tcgen05.ld, the max pass, the barrier round trips: ~850 cycles) leaves it idle.  Left alone the
+    // two groups run in phase -- both exponentiate at half speed, then both idle the pipe (clock64 trace: 3 080 cycles
+    // per block pair, 2 200 of them in the shared exponential phase) -- and the lag between them is neutrally stable.
+    // Named barriers 1 / 2 make the phase a critical section the groups enter in strict alternation (A, B, A, ...), so
+    // that one group's loads and max pass run under the other's exponentials.  Group B's arrival on barrier 1 before
+    // the loop lets A in first; the arrival left over at the end of an item opens the next one.
+    const bool alt = p.alternate != 0;
+    if (alt && grp == 1) asm volatile("bar.arrive 1, 256;" ::: "memory");
     for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++w) {
       const int img = item / items_per_img, r = item - img * items_per_img;
       const int h = r / pair_tiles, pt = r - h * pair_tiles;
       float m_used = 0.f, l = 0.f;
       for (int j = 0; j < nblk; ++j, ++g) {
+        const bool tr = (lane == 0);
+        if (tr) ATT_TRACE(grp * 4 + q, j, 0);
         tc::mbar_wait(&s_full[grp], g & 1);
+        if (tr) ATT_TRACE(grp * 4 + q, j, 1);
         tc::tc_fence_after();
         uint32_t sv[4][32];
 #pragma unroll
@@ -405,6 +474,7 @@ k_attn_fwd2(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUt
         tc::tmem_ld_wait();
         tc::tc_fence_before();
         tc::mbar_arrive(&s_empty[grp]);
+        if (tr) ATT_TRACE(grp * 4 + q, j, 2);
         float bm0 = -INFINITY, bm1 = -INFINITY, bm2 = -INFINITY, bm3 = -INFINITY;
 #pragma unroll
         for (int i = 0; i < 32; ++i) {
@@ -422,7 +492,9 @@ k_attn_fwd2(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUt
           need = true;
         }
         // the previous product of this tile must be complete before O is rescaled or P overwritten
+        if (tr) ATT_TRACE(grp * 4 + q, j, 3);
         tc::mbar_wait(&p_empty[grp], (g & 1) ^ 1);
+        if (tr) ATT_TRACE(grp * 4 + q, j, 4);
         if (__any_sync(0xffffffffu, need)) {
           tc::tc_fence_after();
 #pragma unroll
@@ -438,6 +510,29 @@ k_attn_fwd2(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUt
         }
         float sum0 = 0.f, sum1 = 0.f;
         const float neg_m = -m_used;
+        if (alt) {
+          if (grp == 0) asm volatile("bar.sync 1, 256;" ::: "memory");
+          else asm volatile("bar.sync 2, 256;" ::: "memory");
+        }
+        if (tr) ATT_TRACE(grp * 4 + q, j, 7);
+        if (PT) {
+#pragma unroll
+          for (int c = 0; c < 2; ++c) {                              // 64 keys = 32 packed columns per store
+            uint32_t pk[32];
+#pragma unroll
+            for (int t = 0; t < 32; ++t) {
+              const int e = (c & 1) * 64 + 2 * t;
+              const float a = ex2_approx(fmaf(__uint_as_float(sv[c * 2 + (t >> 4)][e & 31]), p.scale_log2, neg_m));
+              const float b = ex2_approx(fmaf(__uint_as_float(sv[c * 2 + (t >> 4)][(e & 31) + 1]), p.scale_log2, neg_m));
+              sum0 += a; sum1 += b;
+              const __half2 hh = __floats2half2_rn(a, b);
+              pk[t] = *reinterpret_cast<const uint32_t *>(&hh);
+            }
+            tc::tmem_st32(p_addr + c * 32, pk);
+          }
+          if (tr) ATT_TRACE(grp * 4 + q, j, 5);
+          tc::tmem_st_wait();
+        } else {
 #pragma unroll
         for (int cc = 0; cc < 16; ++cc) {                          // 16-byte chunk cc = keys 8cc .. 8cc+7
           uint32_t pk[4];
@@ -454,10 +549,16 @@ k_attn_fwd2(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUt
                        "r"(pk[0]), "r"(pk[1]), "r"(pk[2]), "r"(pk[3])
                        : "memory");
         }
+        }
+        if (alt) {
+          if (grp == 0) asm volatile("bar.arrive 2, 256;" ::: "memory");
+          else asm volatile("bar.arrive 1, 256;" ::: "memory");
+        }
         l = l * corr + (sum0 + sum1);
-        tc::fence_proxy_async_smem();
+        if (!PT) tc::fence_proxy_async_smem();
         tc::tc_fence_before();
         tc::mbar_arrive(&p_full[grp]);
+        if (tr) ATT_TRACE(grp * 4 + q, j, 6);
       }
       // ---- epilogue: O / l
       tc::mbar_wait(&p_empty[grp], (g & 1) ^ 1);                    // the last product of this item (block g-1)
@@ -497,6 +598,12 @@ k_attn_fwd2(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUt
 
 }  // namespace
 
+#ifdef FOHO_ATTN_TRACE
+extern "C" int foho_debug_attn_trace(long long *host_dst) {
+  return cudaMemcpyFromSymbol(host_dst, g_attn_trace, sizeof(g_attn_trace)) == cudaSuccess ? 0 : -1;
+}
+#endif
+
 extern "C" int foho_tc_attention(const foho_attn_desc *d, void *cuda_stream) {
   if (!d || !d->q || !d->k || !d->v || !d->out) return FOHO_E_NULL;
   if (d->n_img <= 0 || d->heads <= 0 || d->n_q <= 0 || d->n_k <= 0 || d->n_k % AK) return FOHO_E_SHAPE;
@@ -519,14 +626,16 @@ extern "C" int foho_tc_attention(const foho_attn_desc *d, void *cuda_stream) {
   p.scale_log2 = d->scale * 1.4426950408889634f;
   p.lse2 = d->lse2;
   p.lse_stride = d->lse2_stride > 0 ? d->lse2_stride : d->n_q;
-  if (d->lse2 && d->variant == 1) return FOHO_E_ARG;
+  p.alternate = (d->variant & 4) ? 0 : 1;          // bit 2 of variant: free-running groups (A/B measurements)
+  const int variant = d->variant & 3;
+  if (d->lse2 && variant == 1) return FOHO_E_ARG;
   static int sm_count = 0;
   if (!sm_count) {
     int dev = 0;
     FOHO_CUDA_TRY(cudaGetDevice(&dev));
     FOHO_CUDA_TRY(cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev));
   }
-  if (d->variant == 1) {     // one query tile per CTA (the first version; kept for A/B measurements)
+  if (variant == 1) {     // one query tile per CTA (the first version; kept for A/B measurements)
     FOHO_CUDA_TRY(cudaFuncSetAttribute(k_attn_fwd, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM));
     long long items = (long long)p.n_img * p.heads * p.q_tiles;
     int grid = (int)(items < sm_count ? items : sm_count);
@@ -536,8 +645,13 @@ extern "C" int foho_tc_attention(const foho_attn_desc *d, void *cuda_stream) {
     long long items = (long long)p.n_img * p.heads * ((p.q_tiles + 1) / 2);
     int grid = (int)(items < sm_count ? items : sm_count);
     if (d->max_ctas > 0 && grid > d->max_ctas) grid = d->max_ctas;
-    FOHO_CUDA_TRY(cudaFuncSetAttribute(k_attn_fwd2, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT2_SMEM));
-    k_attn_fwd2<<<grid, 384, ATT2_SMEM, st>>>(tmQ, tmK, tmV, p);
+    if (variant == 2) {   // P through shared memory (the version before the P-in-TMEM rewrite; kept for A/B measurements)
+      FOHO_CUDA_TRY(cudaFuncSetAttribute(k_attn_fwd2<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, Att2Cfg<0>::SMEM));
+      k_attn_fwd2<0><<<grid, 384, Att2Cfg<0>::SMEM, st>>>(tmQ, tmK, tmV, p);
+    } else {
+      FOHO_CUDA_TRY(cudaFuncSetAttribute(k_attn_fwd2<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, Att2Cfg<1>::SMEM));
+      k_attn_fwd2<1><<<grid, 384, Att2Cfg<1>::SMEM, st>>>(tmQ, tmK, tmV, p);
+    }
   }
   FOHO_LAUNCH_CHECK();
   return 0;

@@ -93,7 +93,7 @@ k_attn_bwd(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUte
   uint64_t *y_full = bars + 10, *y_empty = y_full + Y_STAGES;
   uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(y_empty + Y_STAGES);
 
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = tc::warp_idx_uniform(), lane = threadIdx.x & 31;   // provably warp-uniform: see foho_tc.cuh
   const int n_items = p.n_img * p.heads * (p.k_tiles + (p.dq ? p.q_tiles : 0));
 
   if (warp == 0 && lane == 0) {
@@ -111,33 +111,41 @@ k_attn_bwd(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUte
   tc::tc_fence_before();
   __syncthreads();
   tc::tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);
 
   if (warp < 4) {
     // NG == 4: 640 threads x 96 registers is the whole file already and the element-wise code fits in 96
     if (NG == 2) asm volatile("setmaxnreg.dec.sync.aligned.u32 64;");
-    if (warp == 0 && lane == 0) {
-      // ---------------------------------------------------------- TMA producer
+    if (warp == 0) {
+      // ---------------------------------------------------------- TMA producer (whole warp walks the loop, one lane issues)
+      const bool leader = tc::elect_one();
       uint32_t g = 0, w = 0;
       for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++w) {
         const Item it = decode_item(p, item);
         const int frow = it.kind == 0 ? it.img * p.n_k + it.tile * BT : it.img * p.n_q + it.tile * BT;
         tc::mbar_wait(f_empty, (w & 1) ^ 1);
-        tc::mbar_expect_tx(f_full, 2 * TILE_BYTES);
-        tc::tma_load_3d(sF, it.kind == 0 ? &tmK : &tmQ, f_full, 0, frow, it.h);
-        tc::tma_load_3d(sF + TILE_BYTES, it.kind == 0 ? &tmV : &tmdO, f_full, 0, frow, it.h);
+        if (leader) {
+          tc::mbar_expect_tx(f_full, 2 * TILE_BYTES);
+          tc::tma_load_3d(sF, it.kind == 0 ? &tmK : &tmQ, f_full, 0, frow, it.h);
+          tc::tma_load_3d(sF + TILE_BYTES, it.kind == 0 ? &tmV : &tmdO, f_full, 0, frow, it.h);
+        }
+        __syncwarp();
         for (int s = 0; s < it.nsteps; ++s, ++g) {
           const uint32_t st = g % Y_STAGES, ph = (g / Y_STAGES) & 1;
           const int yrow = it.kind == 0 ? it.img * p.n_q + s * BT : it.img * p.n_k + s * BT;
           tc::mbar_wait(&y_empty[st], ph ^ 1);
           uint8_t *y1 = sY + st * 2 * TILE_BYTES;
-          tc::mbar_expect_tx(&y_full[st], 2 * TILE_BYTES);
-          tc::tma_load_3d(y1, it.kind == 0 ? &tmQ : &tmK, &y_full[st], 0, yrow, it.h);
-          tc::tma_load_3d(y1 + TILE_BYTES, it.kind == 0 ? &tmdO : &tmV, &y_full[st], 0, yrow, it.h);
+          if (leader) {
+            tc::mbar_expect_tx(&y_full[st], 2 * TILE_BYTES);
+            tc::tma_load_3d(y1, it.kind == 0 ? &tmQ : &tmK, &y_full[st], 0, yrow, it.h);
+            tc::tma_load_3d(y1 + TILE_BYTES, it.kind == 0 ? &tmdO : &tmV, &y_full[st], 0, yrow, it.h);
+          }
+          __syncwarp();
         }
       }
-    } else if (warp == 1 && lane == 0) {
-      // ---------------------------------------------------------- MMA issuer
+    } else if (warp == 1) {
+      // ---------------------------------------------------------- MMA issuer (whole warp walks the loop, one lane issues)
+      const bool leader = tc::elect_one();
       constexpr uint32_t idesc_t = tc::idesc_f16(BT, BT, 0, 0);      // T = A B^T        : both K-major
       constexpr uint32_t idesc_q = tc::idesc_f16(BT, HD, 0, 1);      // dQ += dS K       : dS K-major, K MN-major
       constexpr uint32_t idesc_k = tc::idesc_f16(BT, HD, 1, 1);      // dK += dS^T Q ... : the tile and Q / dO MN-major
@@ -151,16 +159,20 @@ k_attn_bwd(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUte
         const uint32_t y_addr = tc::smem_u32(sY + st * 2 * TILE_BYTES);
         // rows = queries: kind 0 streams them (A = Y), kind 1 holds them (A = F)
         const uint32_t a1 = kind == 0 ? y_addr : f_addr, b1 = kind == 0 ? f_addr : y_addr;
-        if (p.dbg & 4) { tc::mma_commit(t_full); return; }
+        if (leader) {
+          if (!(p.dbg & 4)) {
 #pragma unroll
-        for (int k = 0; k < HD / 16; ++k)
-          tc::mma_f16_ss(tmem_base + TB_T1, tc::smem_desc_sw128(a1 + k * 32, 16, 1024), tc::smem_desc_sw128(b1 + k * 32, 16, 1024),
-                         idesc_t, k != 0);
+            for (int k = 0; k < HD / 16; ++k)
+              tc::mma_f16_ss(tmem_base + TB_T1, tc::smem_desc_sw128(a1 + k * 32, 16, 1024), tc::smem_desc_sw128(b1 + k * 32, 16, 1024),
+                             idesc_t, k != 0);
 #pragma unroll
-        for (int k = 0; k < HD / 16; ++k)
-          tc::mma_f16_ss(tmem_base + TB_T2, tc::smem_desc_sw128(a1 + TILE_BYTES + k * 32, 16, 1024),
-                         tc::smem_desc_sw128(b1 + TILE_BYTES + k * 32, 16, 1024), idesc_t, k != 0);
-        tc::mma_commit(t_full);
+            for (int k = 0; k < HD / 16; ++k)
+              tc::mma_f16_ss(tmem_base + TB_T2, tc::smem_desc_sw128(a1 + TILE_BYTES + k * 32, 16, 1024),
+                             tc::smem_desc_sw128(b1 + TILE_BYTES + k * 32, 16, 1024), idesc_t, k != 0);
+          }
+          tc::mma_commit(t_full);
+        }
+        __syncwarp();
       };
       for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++w) {
         const Item it = decode_item(p, item);
@@ -168,13 +180,14 @@ k_attn_bwd(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUte
         issue_t(g, it.kind);
         for (int s = 0; s < it.nsteps; ++s, ++g) {
           if (s + 1 < it.nsteps) issue_t(g + 1, it.kind);
-          else tc::mma_commit(f_empty);                       // every product that reads the fixed tiles has been issued
+          else { if (leader) tc::mma_commit(f_empty); __syncwarp(); }   // every product that reads the fixed tiles has been issued
           const uint32_t st = g % Y_STAGES, u = PDB == 2 ? (g & 1) : 0, pph = PDB == 2 ? ((g >> 1) & 1) : (g & 1);
           tc::mbar_wait(&pd_full[u], pph);
           if (s == 0) tc::mbar_wait(acc_empty, (w & 1) ^ 1);
           tc::tc_fence_after();
           const uint32_t y_addr = tc::smem_u32(sY + st * 2 * TILE_BYTES);
           const uint32_t p_addr = pd_addr + u * 2 * PD_BYTES, d_addr = p_addr + PD_BYTES;
+          if (leader) {
           if (p.dbg & 2) {
           } else if (it.kind == 1) {
 #pragma unroll
@@ -194,6 +207,8 @@ k_attn_bwd(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUte
           tc::mma_commit(&y_empty[st]);
           tc::mma_commit(&pd_empty[u]);
           if (s + 1 == it.nsteps) tc::mma_commit(acc_full);
+          }
+          __syncwarp();
         }
       }
     }

@@ -121,7 +121,7 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
   uint64_t *full = bars, *empty = bars + C_::STAGES, *tfull = bars + 2 * C_::STAGES, *tempty = tfull + 2;
   uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(tempty + 2);
 
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = tc::warp_idx_uniform(), lane = threadIdx.x & 31;   // provably warp-uniform: see foho_tc.cuh
   const int nkb = (p.K + BK - 1) / BK;
   const int tiles_per_batch = p.tiles_m * p.tiles_n;
   const int num_tiles = tiles_per_batch * p.batch;
@@ -139,10 +139,12 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
   tc::tc_fence_before();
   __syncthreads();
   tc::tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);
 
-  if (warp == 0 && lane == 0) {
-    // ------------------------------------------------------------ TMA producer
+  if (warp == 0) {
+    // ------------------------------------------------------------ TMA producer: the whole warp walks the loop (uniform
+    // control flow keeps coordinates and barrier addresses in uniform registers), one elected lane issues
+    const bool leader = tc::elect_one();
     uint32_t it = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
       const int b = tile / tiles_per_batch, r = tile - b * tiles_per_batch;
@@ -150,25 +152,30 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
       for (int kb = 0; kb < nkb; ++kb, ++it) {
         const uint32_t s = it % C_::STAGES, ph = (it / C_::STAGES) & 1;
         tc::mbar_wait(&empty[s], ph ^ 1);
-        tc::mbar_expect_tx(&full[s], C_::STAGE_BYTES);
         uint8_t *sa = smem + s * C_::STAGE_BYTES, *sb = sa + C_::A_BYTES;
         const int k0 = kb * BK;
-        if (A_MN) {
+        if (leader) {
+          tc::mbar_expect_tx(&full[s], C_::STAGE_BYTES);
+          if (A_MN) {
 #pragma unroll
-          for (int j = 0; j < BM / 64; ++j) tc::tma_load_3d(sa + j * (BK * 128), &tmA, &full[s], m0 + 64 * j, k0, p.a_bcast ? 0 : b);
-        } else {
-          tc::tma_load_3d(sa, &tmA, &full[s], k0, m0, p.a_bcast ? 0 : b);
-        }
-        if (B_MN) {
+            for (int j = 0; j < BM / 64; ++j) tc::tma_load_3d(sa + j * (BK * 128), &tmA, &full[s], m0 + 64 * j, k0, p.a_bcast ? 0 : b);
+          } else {
+            tc::tma_load_3d(sa, &tmA, &full[s], k0, m0, p.a_bcast ? 0 : b);
+          }
+          if (B_MN) {
 #pragma unroll
-          for (int j = 0; j < BN / 64; ++j) tc::tma_load_3d(sb + j * (BK * 128), &tmB, &full[s], n0 + 64 * j, k0, p.b_bcast ? 0 : b);
-        } else {
-          tc::tma_load_3d(sb, &tmB, &full[s], k0, n0, p.b_bcast ? 0 : b);
+            for (int j = 0; j < BN / 64; ++j) tc::tma_load_3d(sb + j * (BK * 128), &tmB, &full[s], n0 + 64 * j, k0, p.b_bcast ? 0 : b);
+          } else {
+            tc::tma_load_3d(sb, &tmB, &full[s], k0, n0, p.b_bcast ? 0 : b);
+          }
         }
+        __syncwarp();
       }
     }
-  } else if (warp == 1 && lane == 0) {
-    // ------------------------------------------------------------ MMA issuer
+  } else if (warp == 1) {
+    // ------------------------------------------------------------ MMA issuer (whole warp, one elected lane issues: the
+    // descriptors are built in uniform registers and the tcgen05.mma instructions leave back to back)
+    const bool leader = tc::elect_one();
     constexpr uint32_t idesc = tc::idesc_f16(BM, BN, A_MN ? 1u : 0u, B_MN ? 1u : 0u);
     uint32_t it = 0, acc_it = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++acc_it) {
@@ -181,18 +188,21 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
         tc::mbar_wait(&full[s], ph);
         tc::tc_fence_after();
         const uint32_t sa = tc::smem_u32(smem + s * C_::STAGE_BYTES), sb = sa + C_::A_BYTES;
+        if (leader) {
 #pragma unroll
-        for (int k = 0; k < BK / UMMA_K; ++k) {
-          // K-major: 16 halves = 32 B further along the 128-B swizzled row; MN-major: 16 k-rows = 2048 B further
-          const uint64_t ad = A_MN ? tc::smem_desc_sw128(sa + k * (UMMA_K * 128), BK * 128, 1024)
-                                   : tc::smem_desc_sw128(sa + k * (UMMA_K * 2), 16, 1024);
-          const uint64_t bd = B_MN ? tc::smem_desc_sw128(sb + k * (UMMA_K * 128), BK * 128, 1024)
-                                   : tc::smem_desc_sw128(sb + k * (UMMA_K * 2), 16, 1024);
-          tc::mma_f16_ss(d_tmem, ad, bd, idesc, (kb | k) != 0);
+          for (int k = 0; k < BK / UMMA_K; ++k) {
+            // K-major: 16 halves = 32 B further along the 128-B swizzled row; MN-major: 16 k-rows = 2048 B further
+            const uint64_t ad = A_MN ? tc::smem_desc_sw128(sa + k * (UMMA_K * 128), BK * 128, 1024)
+                                     : tc::smem_desc_sw128(sa + k * (UMMA_K * 2), 16, 1024);
+            const uint64_t bd = B_MN ? tc::smem_desc_sw128(sb + k * (UMMA_K * 128), BK * 128, 1024)
+                                     : tc::smem_desc_sw128(sb + k * (UMMA_K * 2), 16, 1024);
+            tc::mma_f16_ss(d_tmem, ad, bd, idesc, (kb | k) != 0);
+          }
+          tc::mma_commit(&empty[s]);      // slot free once these MMAs have read it
+          if (kb + 1 == nkb) tc::mma_commit(&tfull[acc]);      // accumulator complete
         }
-        tc::mma_commit(&empty[s]);      // slot free once these MMAs have read it
+        __syncwarp();
       }
-      tc::mma_commit(&tfull[acc]);      // accumulator complete
     }
   } else if (warp >= 4) {
     // ------------------------------------------------------------ epilogue (256 threads: thread = one row of the tile, the two

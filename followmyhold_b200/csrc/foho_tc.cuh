@@ -17,6 +17,25 @@ namespace tc {
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ uint32_t lane_id() { return threadIdx.x & 31; }
 
+// Warp index that the compiler can prove warp-uniform (CUTLASS' canonical_warp_idx_sync): roles are chosen with it so
+// that everything a single-warp role computes (descriptors, barrier addresses, loop counters) stays in uniform
+// registers and feeds UTCHMMA / UTMALDG / UTCBAR directly.  With `if (warp == 1 && lane == 0)` around the whole role
+// the control flow is lane-dependent, every operand lives in a vector register and each tcgen05.mma is preceded by an
+// R2UR sequence inside a convergence loop: measured ~100 cycles per instruction on the issuing thread (clock64 trace of
+// the attention forward), three times the tensor pipe's own time.
+__device__ __forceinline__ int warp_idx_uniform() { return __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0); }
+// One lane of a converged warp; the predicate is warp-uniform in value but lane-dependent, so only the instructions
+// that must be issued once (tcgen05.mma / commit, TMA, expect_tx) go under it.
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "elect.sync _|p, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(pred));
+  return pred != 0;
+}
+
 // ---------------------------------------------------------------- mbarrier
 __device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
@@ -41,7 +60,9 @@ __device__ __forceinline__ uint32_t mbar_try_wait(uint64_t *bar, uint32_t parity
       : "memory");
   return ok;
 }
-// Bounded wait: a protocol bug must surface as a launch failure (trap), never as a hung GPU.
+// Bounded wait: a protocol bug must surface as a launch failure (trap), never as a hung GPU.  The message is compiled
+// in only with -DFOHO_TC_DEBUG_WAIT: a printf argument block at every wait site costs the single-thread producer / issuer
+// roles (64-96 registers after setmaxnreg) spills right in front of their tcgen05.mma instructions.
 __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
   if (mbar_try_wait(bar, parity)) return;
   unsigned long long t0 = 0;
@@ -52,8 +73,10 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
       asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
       if (t0 == 0) t0 = t;
       else if (t - t0 > 4000000000ull) {   // 4 s
+#ifdef FOHO_TC_DEBUG_WAIT
         printf("foho_tc: mbarrier wait timed out (block %d thread %d bar %u parity %u)\n", (int)blockIdx.x, (int)threadIdx.x,
                smem_u32(bar), parity);
+#endif
         __trap();
       }
     }

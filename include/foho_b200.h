@@ -365,7 +365,8 @@ typedef struct foho_attn_desc {
   int32_t q_shared;
   int32_t max_ctas;          /* 0 = one persistent CTA per SM */
   float scale;               /* 1/sqrt(64) = 0.125 */
-  int32_t variant;           /* 0 = two query tiles per CTA in ping-pong (default); 1 = one tile per CTA */
+  int32_t variant;           /* 0 = two query tiles per CTA in ping-pong, P kept in TMEM (default); 1 = one tile per CTA;
+                                2 = two tiles, P through shared memory (A/B measurements) */
   const void *q; int64_t ldq, hsq;
   const void *k; int64_t ldk, hsk;
   const void *v; int64_t ldv, hsv;
