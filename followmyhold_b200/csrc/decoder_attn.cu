@@ -37,7 +37,6 @@ struct AttnParams {
   float scale_log2;                    // softmax scale * log2(e)
   float *lse2;                         // optional [n_img][heads][lse_stride]: m + log2(l) of the scaled scores (variant 0 only)
   long long lse_stride;
-  int alternate;                       // k_attn_fwd2: the two softmax groups take turns on the exponential phase
 };
 
 __global__ void __launch_bounds__(256, 1)
@@ -281,6 +280,27 @@ __device__ long long g_attn_trace[9][32][8];   // roles 0-3: group A warps, 4-7:
 #else
 #define ATT_TRACE(role, blk, ev) do { } while (0)
 #endif
+// Packed fp32 pairs (FFMA2 / FADD2, sm_100): the scale-and-shift of the scores and the row sums cost one instruction
+// per two keys.
+__device__ __forceinline__ float2 ffma2(float2 a, float2 b, float2 c) {
+  uint64_t ra, rb, rc, rd;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(ra) : "f"(a.x), "f"(a.y));
+  asm("mov.b64 %0, {%1, %2};" : "=l"(rb) : "f"(b.x), "f"(b.y));
+  asm("mov.b64 %0, {%1, %2};" : "=l"(rc) : "f"(c.x), "f"(c.y));
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(rd) : "l"(ra), "l"(rb), "l"(rc));
+  float2 d;
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(d.x), "=f"(d.y) : "l"(rd));
+  return d;
+}
+__device__ __forceinline__ float2 fadd2(float2 a, float2 b) {
+  uint64_t ra, rb, rd;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(ra) : "f"(a.x), "f"(a.y));
+  asm("mov.b64 %0, {%1, %2};" : "=l"(rb) : "f"(b.x), "f"(b.y));
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(rd) : "l"(ra), "l"(rb));
+  float2 d;
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(d.x), "=f"(d.y) : "l"(rd));
+  return d;
+}
 template <int PT> struct Att2Cfg {
   static constexpr int STAGES = PT ? 5 : KV_STAGES;
   static constexpr int SMEM = 2 * Q_BYTES + STAGES * (K_BYTES + V_BYTES) + (PT ? 0 : 2 * P_BYTES) + 1024 + 256;
@@ -449,15 +469,13 @@ k_attn_fwd2(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUt
     const uint32_t pb_s = tc::smem_u32(sP + (PT ? 0 : grp * P_BYTES) + row * 128);
     const uint32_t p_addr = tmem_base + T2_P + grp * 64 + lane_off;
     uint32_t g = 0, w = 0;
-    // The exponential phase is bound by the MUFU pipe (128 ex2 per thread and block, 16 per clock and SM), everything
-    // else of a block (tcgen05.ld, the max pass, the barrier round trips: ~850 cycles) leaves it idle.  Left alone the
-    // two groups run in phase -- both exponentiate at half speed, then both idle the pipe (clock64 trace: 3 080 cycles
-    // per block pair, 2 200 of them in the shared exponential phase) -- and the lag between them is neutrally stable.
-    // Named barriers 1 / 2 make the phase a critical section the groups enter in strict alternation (A, B, A, ...), so
-    // that one group's loads and max pass run under the other's exponentials.  Group B's arrival on barrier 1 before
-    // the loop lets A in first; the arrival left over at the end of an item opens the next one.
-    const bool alt = p.alternate != 0;
-    if (alt && grp == 1) asm volatile("bar.arrive 1, 256;" ::: "memory");
+    // The exponential phase is bound by the MUFU pipe (128 ex2 per thread and block at 16 per clock and SM: 1 050 cycles
+    // per warp and phase with two warps on a scheduler, 1 240 with one -- scripts/ubench/exp_phase.cu), the rest of a
+    // block (tcgen05.ld, max pass, barrier round trips) takes ~550 cycles.  clock64 traces of both groups
+    // (scripts/attn_trace.py, -DFOHO_ATTN_TRACE): ~2 900 cycles per block pair with the groups in phase.  Measured and
+    // dropped on top of this version (all within +-5 % of it): named-barrier turn taking on the
+    // phase (strict, arrival at the last exponential, arrival at the middle pinned with a volatile load),
+    // FlashAttention-4's polynomial exp2 on the FMA pipe for 1-4 of every 8 key pairs.
     for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++w) {
       const int img = item / items_per_img, r = item - img * items_per_img;
       const int h = r / pair_tiles, pt = r - h * pair_tiles;
@@ -510,26 +528,27 @@ k_attn_fwd2(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUt
         }
         float sum0 = 0.f, sum1 = 0.f;
         const float neg_m = -m_used;
-        if (alt) {
-          if (grp == 0) asm volatile("bar.sync 1, 256;" ::: "memory");
-          else asm volatile("bar.sync 2, 256;" ::: "memory");
-        }
         if (tr) ATT_TRACE(grp * 4 + q, j, 7);
         if (PT) {
+          const float2 sc2 = make_float2(p.scale_log2, p.scale_log2);
+          const float2 nm2 = make_float2(neg_m, neg_m);
+          float2 acc0 = make_float2(0.f, 0.f), acc1 = make_float2(0.f, 0.f);
 #pragma unroll
           for (int c = 0; c < 2; ++c) {                              // 64 keys = 32 packed columns per store
             uint32_t pk[32];
 #pragma unroll
             for (int t = 0; t < 32; ++t) {
-              const int e = (c & 1) * 64 + 2 * t;
-              const float a = ex2_approx(fmaf(__uint_as_float(sv[c * 2 + (t >> 4)][e & 31]), p.scale_log2, neg_m));
-              const float b = ex2_approx(fmaf(__uint_as_float(sv[c * 2 + (t >> 4)][(e & 31) + 1]), p.scale_log2, neg_m));
-              sum0 += a; sum1 += b;
-              const __half2 hh = __floats2half2_rn(a, b);
+              const int e = (2 * t) & 31;
+              const float2 x = ffma2(make_float2(__uint_as_float(sv[c * 2 + (t >> 4)][e]), __uint_as_float(sv[c * 2 + (t >> 4)][e + 1])), sc2, nm2);
+              float2 ab;
+              ab.x = ex2_approx(x.x); ab.y = ex2_approx(x.y);
+              if (t & 1) acc1 = fadd2(acc1, ab); else acc0 = fadd2(acc0, ab);
+              const __half2 hh = __floats2half2_rn(ab.x, ab.y);
               pk[t] = *reinterpret_cast<const uint32_t *>(&hh);
             }
             tc::tmem_st32(p_addr + c * 32, pk);
           }
+          sum0 = acc0.x + acc0.y; sum1 = acc1.x + acc1.y;
           if (tr) ATT_TRACE(grp * 4 + q, j, 5);
           tc::tmem_st_wait();
         } else {
@@ -549,10 +568,6 @@ k_attn_fwd2(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUt
                        "r"(pk[0]), "r"(pk[1]), "r"(pk[2]), "r"(pk[3])
                        : "memory");
         }
-        }
-        if (alt) {
-          if (grp == 0) asm volatile("bar.arrive 2, 256;" ::: "memory");
-          else asm volatile("bar.arrive 1, 256;" ::: "memory");
         }
         l = l * corr + (sum0 + sum1);
         if (!PT) tc::fence_proxy_async_smem();
@@ -626,7 +641,6 @@ extern "C" int foho_tc_attention(const foho_attn_desc *d, void *cuda_stream) {
   p.scale_log2 = d->scale * 1.4426950408889634f;
   p.lse2 = d->lse2;
   p.lse_stride = d->lse2_stride > 0 ? d->lse2_stride : d->n_q;
-  p.alternate = (d->variant & 4) ? 0 : 1;          // bit 2 of variant: free-running groups (A/B measurements)
   const int variant = d->variant & 3;
   if (d->lse2 && variant == 1) return FOHO_E_ARG;
   static int sm_count = 0;
