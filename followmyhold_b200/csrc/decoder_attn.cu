@@ -280,27 +280,6 @@ __device__ long long g_attn_trace[9][32][8];   // roles 0-3: group A warps, 4-7:
 #else
 #define ATT_TRACE(role, blk, ev) do { } while (0)
 #endif
-// Packed fp32 pairs (FFMA2 / FADD2, sm_100): the scale-and-shift of the scores and the row sums cost one instruction
-// per two keys.
-__device__ __forceinline__ float2 ffma2(float2 a, float2 b, float2 c) {
-  uint64_t ra, rb, rc, rd;
-  asm("mov.b64 %0, {%1, %2};" : "=l"(ra) : "f"(a.x), "f"(a.y));
-  asm("mov.b64 %0, {%1, %2};" : "=l"(rb) : "f"(b.x), "f"(b.y));
-  asm("mov.b64 %0, {%1, %2};" : "=l"(rc) : "f"(c.x), "f"(c.y));
-  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(rd) : "l"(ra), "l"(rb), "l"(rc));
-  float2 d;
-  asm("mov.b64 {%0, %1}, %2;" : "=f"(d.x), "=f"(d.y) : "l"(rd));
-  return d;
-}
-__device__ __forceinline__ float2 fadd2(float2 a, float2 b) {
-  uint64_t ra, rb, rd;
-  asm("mov.b64 %0, {%1, %2};" : "=l"(ra) : "f"(a.x), "f"(a.y));
-  asm("mov.b64 %0, {%1, %2};" : "=l"(rb) : "f"(b.x), "f"(b.y));
-  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(rd) : "l"(ra), "l"(rb));
-  float2 d;
-  asm("mov.b64 {%0, %1}, %2;" : "=f"(d.x), "=f"(d.y) : "l"(rd));
-  return d;
-}
 template <int PT> struct Att2Cfg {
   static constexpr int STAGES = PT ? 5 : KV_STAGES;
   static constexpr int SMEM = 2 * Q_BYTES + STAGES * (K_BYTES + V_BYTES) + (PT ? 0 : 2 * P_BYTES) + 1024 + 256;
@@ -539,10 +518,10 @@ k_attn_fwd2(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUt
 #pragma unroll
             for (int t = 0; t < 32; ++t) {
               const int e = (2 * t) & 31;
-              const float2 x = ffma2(make_float2(__uint_as_float(sv[c * 2 + (t >> 4)][e]), __uint_as_float(sv[c * 2 + (t >> 4)][e + 1])), sc2, nm2);
+              const float2 x = tc::ffma2(make_float2(__uint_as_float(sv[c * 2 + (t >> 4)][e]), __uint_as_float(sv[c * 2 + (t >> 4)][e + 1])), sc2, nm2);
               float2 ab;
               ab.x = ex2_approx(x.x); ab.y = ex2_approx(x.y);
-              if (t & 1) acc1 = fadd2(acc1, ab); else acc0 = fadd2(acc0, ab);
+              if (t & 1) acc1 = tc::fadd2(acc1, ab); else acc0 = tc::fadd2(acc0, ab);
               const __half2 hh = __floats2half2_rn(ab.x, ab.y);
               pk[t] = *reinterpret_cast<const uint32_t *>(&hh);
             }

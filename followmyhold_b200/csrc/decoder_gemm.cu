@@ -62,6 +62,25 @@ __device__ __forceinline__ float erf_fast(float x) {
   asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(q));
   return copysignf(1.0f - r, x);
 }
+// The same for two elements with packed arithmetic: 20 instructions per pair against 19 per element.
+__device__ __forceinline__ float2 gelu2(float2 x) {
+  const float2 y = tc::fmul2(x, tc::splat2(0.70710678118654752f));
+  const float2 ax = make_float2(fabsf(y.x), fabsf(y.y));
+  float2 q = tc::ffma2(tc::splat2(0.0000430638f), ax, tc::splat2(0.0002765672f));
+  q = tc::ffma2(q, ax, tc::splat2(0.0001520143f));
+  q = tc::ffma2(q, ax, tc::splat2(0.0092705272f));
+  q = tc::ffma2(q, ax, tc::splat2(0.0422820123f));
+  q = tc::ffma2(q, ax, tc::splat2(0.0705230784f));
+  q = tc::ffma2(q, ax, tc::splat2(1.0f));
+  q = tc::fmul2(q, q); q = tc::fmul2(q, q); q = tc::fmul2(q, q); q = tc::fmul2(q, q);
+  float2 r;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r.x) : "f"(q.x));
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r.y) : "f"(q.y));
+  float2 e = tc::ffma2(r, tc::splat2(-1.0f), tc::splat2(1.0f));
+  e.x = copysignf(e.x, x.x); e.y = copysignf(e.y, x.y);
+  const float2 hx = tc::fmul2(x, tc::splat2(0.5f));
+  return tc::ffma2(hx, e, hx);
+}
 __device__ __forceinline__ float gelu_f(float x) { return 0.5f * x * (1.0f + erf_fast(x * 0.70710678118654752f)); }
 __device__ __forceinline__ float dgelu_f(float x) {
   float e;
@@ -233,11 +252,23 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
         float f[32];
         float pre[32];
         if (row_ok) {
+          if (p.bias && full_chunk && ((reinterpret_cast<uintptr_t>(p.bias + n) & 15) == 0)) {
+            // alpha * acc + bias in packed pairs, the bias row in 16-byte loads (the same address in every lane)
+            const float2 al = tc::splat2(p.alpha);
 #pragma unroll
-          for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]) * p.alpha;
-          if (p.bias) {
+            for (int j = 0; j < 32; j += 4) {
+              const float4 bb = __ldg(reinterpret_cast<const float4 *>(p.bias + n + j));
+              const float2 lo = tc::ffma2(make_float2(__uint_as_float(v[j]), __uint_as_float(v[j + 1])), al, make_float2(bb.x, bb.y));
+              const float2 hi = tc::ffma2(make_float2(__uint_as_float(v[j + 2]), __uint_as_float(v[j + 3])), al, make_float2(bb.z, bb.w));
+              f[j] = lo.x; f[j + 1] = lo.y; f[j + 2] = hi.x; f[j + 3] = hi.y;
+            }
+          } else {
 #pragma unroll
-            for (int j = 0; j < 32; ++j) if (full_chunk || n + j < p.N) f[j] += __ldg(p.bias + n + j);
+            for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]) * p.alpha;
+            if (p.bias) {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) if (full_chunk || n + j < p.N) f[j] += __ldg(p.bias + n + j);
+            }
           }
           if (p.aux_out) {
 #pragma unroll
@@ -245,7 +276,10 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
           }
           if (p.act == 1) {
 #pragma unroll
-            for (int j = 0; j < 32; ++j) f[j] = gelu_f(f[j]);
+            for (int j = 0; j < 32; j += 2) {
+              const float2 g2 = gelu2(make_float2(f[j], f[j + 1]));
+              f[j] = g2.x; f[j + 1] = g2.y;
+            }
           } else if (p.act == 3) {            // softmax probabilities from saved log-sum-exps: exp2(alpha acc - lse2[m])
 #pragma unroll
             for (int j = 0; j < 32; ++j) f[j] = exp2f(f[j] - rv);

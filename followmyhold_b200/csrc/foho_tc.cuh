@@ -36,6 +36,34 @@ __device__ __forceinline__ bool elect_one() {
   return pred != 0;
 }
 
+// Packed fp32 pairs (FFMA2 / FADD2 / FMUL2, sm_100): one instruction per two elements in the element-wise epilogues.
+__device__ __forceinline__ uint64_t pack2(float lo, float hi) {
+  uint64_t r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+  return r;
+}
+__device__ __forceinline__ float2 unpack2(uint64_t r) {
+  float2 d;
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(d.x), "=f"(d.y) : "l"(r));
+  return d;
+}
+__device__ __forceinline__ float2 ffma2(float2 a, float2 b, float2 c) {
+  uint64_t rd;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(rd) : "l"(pack2(a.x, a.y)), "l"(pack2(b.x, b.y)), "l"(pack2(c.x, c.y)));
+  return unpack2(rd);
+}
+__device__ __forceinline__ float2 fadd2(float2 a, float2 b) {
+  uint64_t rd;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(rd) : "l"(pack2(a.x, a.y)), "l"(pack2(b.x, b.y)));
+  return unpack2(rd);
+}
+__device__ __forceinline__ float2 fmul2(float2 a, float2 b) {
+  uint64_t rd;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(rd) : "l"(pack2(a.x, a.y)), "l"(pack2(b.x, b.y)));
+  return unpack2(rd);
+}
+__device__ __forceinline__ float2 splat2(float v) { return make_float2(v, v); }
+
 // ---------------------------------------------------------------- mbarrier
 __device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
