@@ -254,6 +254,7 @@ k_attn_bwd(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUte
         tc::mbar_arrive(t_empty);
         const uint32_t p_row = pd_row + u * 2 * PD_BYTES, d_row = p_row + PD_BYTES;
         const float neg_l = -lse_r;
+        const float2 sc2 = tc::splat2(p.scale_log2), nl2 = tc::splat2(neg_l), nd2 = tc::splat2(-dl_r);
         // values first (in place: a <- packed P, b <- packed dS), then the wait for the buffer, then the stores: the
         // products of the previous block run while this block's exponentials do
 #pragma unroll
@@ -261,10 +262,11 @@ k_attn_bwd(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUte
 #pragma unroll
           for (int t = 0; t < 4; ++t) {
             const int e = (cc & 3) * 8 + 2 * t;
-            const float p0 = ex2a(fmaf(__uint_as_float(a[cc >> 2][e]), p.scale_log2, neg_l));
-            const float p1 = ex2a(fmaf(__uint_as_float(a[cc >> 2][e + 1]), p.scale_log2, neg_l));
-            const float s0 = p0 * (__uint_as_float(b[cc >> 2][e]) - dl_r), s1 = p1 * (__uint_as_float(b[cc >> 2][e + 1]) - dl_r);
-            const __half2 hp = __floats2half2_rn(p0, p1), hs = __floats2half2_rn(s0, s1);
+            // packed pairs (FFMA2 / FADD2 / FMUL2): 3 arithmetic instructions per two elements instead of 6
+            const float2 x = tc::ffma2(make_float2(__uint_as_float(a[cc >> 2][e]), __uint_as_float(a[cc >> 2][e + 1])), sc2, nl2);
+            const float2 pp = make_float2(ex2a(x.x), ex2a(x.y));
+            const float2 ss = tc::fmul2(pp, tc::fadd2(make_float2(__uint_as_float(b[cc >> 2][e]), __uint_as_float(b[cc >> 2][e + 1])), nd2));
+            const __half2 hp = __floats2half2_rn(pp.x, pp.y), hs = __floats2half2_rn(ss.x, ss.y);
             a[cc >> 2][(cc & 3) * 8 + t] = *reinterpret_cast<const uint32_t *>(&hp);      // slot 8(cc&3)+t <= e: already consumed
             b[cc >> 2][(cc & 3) * 8 + t] = *reinterpret_cast<const uint32_t *>(&hs);
           }
