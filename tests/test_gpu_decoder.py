@@ -291,3 +291,29 @@ def test_fused_attention_adjoint_matches_autograd(n_img, heads, n_q, n_k, fused,
     dq2 = torch.empty_like(dq) if with_dq else None
     tc.attention_bwd(q, k, v, do, lse2, delta, dq2, dk2, dv2, n_img)
     assert torch.equal(dk, dk2) and torch.equal(dv, dv2) and (not with_dq or torch.equal(dq, dq2))
+
+
+@pytest.mark.parametrize("variant", [0, 1, 2])
+@pytest.mark.parametrize("n_img,heads,n_q,n_k,qscale,max_ctas", [
+    (1, 1, 128, 128, 1.0, 0), (1, 3, 200, 512, 1.0, 0), (2, 4, 1000, 1024, 1.0, 3), (1, 2, 256, 3072, 6.0, 0), (1, 2, 389, 256, 1.0, 0)])
+def test_attention_forward_variants_match_float32_softmax(variant, n_img, heads, n_q, n_k, qscale, max_ctas):
+    """``foho_tc_attention`` (cross attention of shared lattice queries, pipelines.py:304) against softmax(Q K^T / 8) V in
+    float32 for every kernel variant: 0 = two query tiles per CTA with P kept in TMEM (the product reads it as a
+    tensor-memory A operand), 2 = the same with P through shared memory, 1 = one tile per CTA.  Cases: one block, ragged
+    query counts, several work items per CTA, a peaked softmax that takes the lazy O-rescale path, an odd tile count
+    (tile B of the last pair is all padding).  fp16 operands and fp16 P: 3e-3 of the output range (measured < 6e-4)."""
+    from followmyhold_b200.decoder import tc
+    dev = "cuda:0"
+    torch.manual_seed(n_q * 7 + n_k)
+    q = (qscale * torch.randn(n_q, heads, 64, device=dev)).half()
+    kv = torch.randn(n_img * n_k, heads, 128, device=dev).half()
+    k, v = kv[:, :, :64], kv[:, :, 64:]
+    out = tc.attention(q, k, v, n_img, q_shared=True, max_ctas=max_ctas, variant=variant)
+    kk = k.float().view(n_img, n_k, heads, 64).transpose(1, 2)
+    vv = v.float().view(n_img, n_k, heads, 64).transpose(1, 2)
+    qq = q.float().unsqueeze(0).expand(n_img, -1, -1, -1).transpose(1, 2)
+    ref = torch.softmax(qq @ kk.transpose(-1, -2) * 0.125, -1) @ vv
+    ref = ref.transpose(1, 2).reshape(n_img, n_q, heads * 64)
+    assert float((out.float() - ref).abs().max()) <= TOL * float(ref.abs().max()) + 1e-4
+    out2 = tc.attention(q, k, v, n_img, q_shared=True, max_ctas=max_ctas, variant=variant)
+    assert torch.equal(out, out2)
