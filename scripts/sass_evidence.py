@@ -28,10 +28,10 @@ def main():
                 short = k
         if short is None:
             continue
-        lines = [l for l in f.split("\n") if re.search(r"/\*[0-9a-f]{4}\*/", l)]
+        lines = [l for l in f.split("\n") if re.search(r"/\*[0-9a-f]{4,6}\*/", l)]
         ops = collections.Counter()
         for l in lines:
-            m = re.search(r"/\*[0-9a-f]{4}\*/\s+(?:@!?U?P\d+\s+)?([A-Z0-9_.]+)", l)
+            m = re.search(r"/\*[0-9a-f]{4,6}\*/\s+(?:@!?U?P\d+\s+)?([A-Z0-9_.]+)", l)
             if m and any(m.group(1).startswith(k) for k in KEYS):
                 ops[m.group(1)] += 1
         summary.append((short, name, len(lines), dict(ops)))
