@@ -454,7 +454,9 @@ k_attn_fwd2(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUt
     // (scripts/attn_trace.py, -DFOHO_ATTN_TRACE): ~2 900 cycles per block pair with the groups in phase.  Measured and
     // dropped on top of this version (all within +-5 % of it): named-barrier turn taking on the
     // phase (strict, arrival at the last exponential, arrival at the middle pinned with a volatile load),
-    // FlashAttention-4's polynomial exp2 on the FMA pipe for 1-4 of every 8 key pairs.
+    // FlashAttention-4's polynomial exp2 on the FMA pipe for 1-4 of every 8 key pairs; and speculating on the running
+    // maximum (exponentials with the maximum of the blocks before, the block maximum reduced inside the pass, the pass
+    // repeated when it exceeds the lazy-rescale bound): 704 against 827 TFLOP/s.
     for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++w) {
       const int img = item / items_per_img, r = item - img * items_per_img;
       const int h = r / pair_tiles, pt = r - h * pair_tiles;
