@@ -39,7 +39,11 @@ struct Cfg {
   static constexpr int A_BYTES = BM * BK * 2, B_BYTES = BN * BK * 2, STAGE_BYTES = A_BYTES + B_BYTES;
   static constexpr int STG_ROW = 144;                       // bytes per staged output row (128 + 16: conflict-free 16-byte writes)
   static constexpr int STG_BYTES = 8 * 16 * STG_ROW;         // eight epilogue warps x 16 rows (a chunk leaves in two halves)
+#ifdef FOHO_GEMM_STAGES
+  static constexpr int STAGES = FOHO_GEMM_STAGES;
+#else
   static constexpr int STAGES = (192 * 1024 / STAGE_BYTES) > 8 ? 8 : (192 * 1024 / STAGE_BYTES);
+#endif
   static constexpr int SMEM = STAGES * STAGE_BYTES + STG_BYTES + 1024 /*align*/ + 256 /*barriers*/;
   static constexpr uint32_t TMEM_COLS = 2 * BN;
 };
