@@ -85,7 +85,6 @@ __device__ __forceinline__ float2 gelu2(float2 x) {
   const float2 hx = tc::fmul2(x, tc::splat2(0.5f));
   return tc::ffma2(hx, e, hx);
 }
-__device__ __forceinline__ float gelu_f(float x) { return 0.5f * x * (1.0f + erf_fast(x * 0.70710678118654752f)); }
 __device__ __forceinline__ float dgelu_f(float x) {
   float e;
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(-0.72134752044448170f * x * x));
@@ -242,6 +241,9 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
       const int m = m0 + q * 32 + lane;
       const bool row_ok = m < p.M;
       const float rv = (p.act >= 3 && row_ok) ? __ldg(p.row_vec + (long long)b * p.bs_rowvec + m) : 0.f;
+      // Measured and dropped: the next chunk's tcgen05.ld in flight while this one is processed, the accumulator handed back as
+      // soon as its last chunk is in registers (the MMA warp spins ~110 times per tile on `tempty` with the GELU epilogue):
+      // 32 more live registers, spills and copies -- 1 027 / 1 087 / 933 against 1 173 / 1 193 / 1 062 TFLOP/s.
 #pragma unroll 1
       for (int c = half * (BN / 64); c < (half + 1) * (BN / 64); ++c) {
         uint32_t v[32];
