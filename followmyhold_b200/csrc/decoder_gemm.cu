@@ -94,8 +94,18 @@ __device__ __forceinline__ float dgelu_f(float x) {
 // One warp's 32 x 32 chunk of outputs (lane = row) -> global memory in full 16-byte x 4 (fp16) / x 8 (fp32) row segments:
 // each lane parks its row in shared memory, then the warp writes 8 (fp16) or 4 (fp32) rows per instruction, so an
 // instruction touches 8 / 4 cache lines instead of 32 (row-per-lane stores were what bounded every K <= 1024 product).
+__device__ __forceinline__ void sts128(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+__device__ __forceinline__ uint4 lds128(uint32_t addr) {
+  uint4 v;
+  asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr) : "memory");
+  return v;
+}
+// `stg` is the stage's SHARED-space address: through a generic pointer the compiler emitted generic LD.E / ST.E for the stage
+// (address-space resolution in the load-store unit, long-scoreboard waits in the epilogue that bounds the bias + GELU tile).
 template <bool F32>
-__device__ __forceinline__ void staged_store(uint8_t *stg, int lane, const float (&f)[32], void *C, long long row0_off, long long ld,
+__device__ __forceinline__ void staged_store(uint32_t stg, int lane, const float (&f)[32], void *C, long long row0_off, long long ld,
                                              int rows_valid, int cols_valid) {
   constexpr int SEG = F32 ? 8 : 4;            // 16-byte segments per row
   constexpr int RPI = 32 / SEG;               // rows per instruction
@@ -104,17 +114,21 @@ __device__ __forceinline__ void staged_store(uint8_t *stg, int lane, const float
 #pragma unroll
   for (int hf = 0; hf < 2; ++hf) {            // rows 0..15, then 16..31: the stage holds 16 rows per warp
     if ((lane >> 4) == hf) {
-      uint8_t *mine = stg + (lane & 15) * 144;
+      const uint32_t mine = stg + (lane & 15) * 144;
       if (F32) {
 #pragma unroll
-        for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4 *>(mine + j * 4) = make_float4(f[j], f[j + 1], f[j + 2], f[j + 3]);
+        for (int j = 0; j < 32; j += 4)
+          sts128(mine + j * 4, __float_as_uint(f[j]), __float_as_uint(f[j + 1]), __float_as_uint(f[j + 2]), __float_as_uint(f[j + 3]));
       } else {
 #pragma unroll
         for (int j = 0; j < 32; j += 8) {
-          __align__(16) __half2 h[4];
+          uint32_t h[4];
 #pragma unroll
-          for (int t = 0; t < 4; ++t) h[t] = __floats2half2_rn(f[j + 2 * t], f[j + 2 * t + 1]);
-          *reinterpret_cast<uint4 *>(mine + j * 2) = *reinterpret_cast<uint4 *>(h);
+          for (int t = 0; t < 4; ++t) {
+            const __half2 hh = __floats2half2_rn(f[j + 2 * t], f[j + 2 * t + 1]);
+            h[t] = *reinterpret_cast<const uint32_t *>(&hh);
+          }
+          sts128(mine + j * 2, h[0], h[1], h[2], h[3]);
         }
       }
     }
@@ -123,7 +137,7 @@ __device__ __forceinline__ void staged_store(uint8_t *stg, int lane, const float
     for (int i = 0; i < 16 / RPI; ++i) {
       const int rl = i * RPI + rsub, r = hf * 16 + rl;
       if (r < rows_valid && seg * EPS < cols_valid) {
-        const uint4 v = *reinterpret_cast<const uint4 *>(stg + rl * 144 + seg * 16);
+        const uint4 v = lds128(stg + rl * 144 + seg * 16);
         uint8_t *dst = reinterpret_cast<uint8_t *>(C) + (row0_off + (long long)r * ld + seg * EPS) * (F32 ? 4 : 2);
         *reinterpret_cast<uint4 *>(dst) = v;
       }
@@ -253,7 +267,7 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
         if (n >= p.N) continue;                           // warp-uniform: whole chunk outside the matrix
         const bool full_chunk = (n + 32 <= p.N);
         const int rows_valid = min(32, p.M - (m0 + q * 32)), cols_valid = min(32, p.N - n);
-        uint8_t *stg = stg_base + (warp - 4) * (16 * C_::STG_ROW);
+        const uint32_t stg = tc::smem_u32(stg_base) + (warp - 4) * (16 * C_::STG_ROW);
         const long long row0 = (long long)(m0 + q * 32);
         float f[32];
         float pre[32];
