@@ -262,24 +262,31 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
       for (int c = half * (BN / 64); c < (half + 1) * (BN / 64); ++c) {
         uint32_t v[32];
         tc::tmem_ld32(tmem_base + acc * BN + c * 32 + ((uint32_t)(q * 32) << 16), v);
-        tc::tmem_ld_wait();
         const int n = n0 + c * 32;
-        if (n >= p.N) continue;                           // warp-uniform: whole chunk outside the matrix
         const bool full_chunk = (n + 32 <= p.N);
+        // the bias row of the chunk is fetched under the latency of the accumulator load
+        const bool fast_bias = p.bias && full_chunk && ((reinterpret_cast<uintptr_t>(p.bias + n) & 15) == 0);
+        float4 bb[8];
+        if (fast_bias) {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) bb[j] = __ldg(reinterpret_cast<const float4 *>(p.bias + n) + j);
+        }
+        tc::tmem_ld_wait();
+        if (n >= p.N) continue;                           // warp-uniform: whole chunk outside the matrix
         const int rows_valid = min(32, p.M - (m0 + q * 32)), cols_valid = min(32, p.N - n);
         const uint32_t stg = tc::smem_u32(stg_base) + (warp - 4) * (16 * C_::STG_ROW);
         const long long row0 = (long long)(m0 + q * 32);
         float f[32];
         float pre[32];
         if (row_ok) {
-          if (p.bias && full_chunk && ((reinterpret_cast<uintptr_t>(p.bias + n) & 15) == 0)) {
+          if (fast_bias) {
             // alpha * acc + bias in packed pairs, the bias row in 16-byte loads (the same address in every lane)
             const float2 al = tc::splat2(p.alpha);
 #pragma unroll
             for (int j = 0; j < 32; j += 4) {
-              const float4 bb = __ldg(reinterpret_cast<const float4 *>(p.bias + n + j));
-              const float2 lo = tc::ffma2(make_float2(__uint_as_float(v[j]), __uint_as_float(v[j + 1])), al, make_float2(bb.x, bb.y));
-              const float2 hi = tc::ffma2(make_float2(__uint_as_float(v[j + 2]), __uint_as_float(v[j + 3])), al, make_float2(bb.z, bb.w));
+              const float4 b4 = bb[j >> 2];
+              const float2 lo = tc::ffma2(make_float2(__uint_as_float(v[j]), __uint_as_float(v[j + 1])), al, make_float2(b4.x, b4.y));
+              const float2 hi = tc::ffma2(make_float2(__uint_as_float(v[j + 2]), __uint_as_float(v[j + 3])), al, make_float2(b4.z, b4.w));
               f[j] = lo.x; f[j + 1] = lo.y; f[j + 2] = hi.x; f[j + 3] = hi.y;
             }
           } else {
