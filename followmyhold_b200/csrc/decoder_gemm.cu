@@ -271,6 +271,15 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
 #pragma unroll
           for (int j = 0; j < 8; ++j) bb[j] = __ldg(reinterpret_cast<const float4 *>(p.bias + n) + j);
         }
+        // ... and so is this thread's 64-byte piece of a half-precision residual row (c_proj + x, fc2 + x: an L2 round trip
+        // that the chunk otherwise waits for after its arithmetic)
+        const __half *res_h = reinterpret_cast<const __half *>(p.res) + (long long)b * p.bsr + (long long)m * p.ldr + n;
+        const bool fast_res = p.res && !p.res_f32 && row_ok && full_chunk && ((reinterpret_cast<uintptr_t>(res_h) & 15) == 0);
+        uint4 rr[4];
+        if (fast_res) {
+#pragma unroll
+          for (int j = 0; j < 4; ++j) rr[j] = *(reinterpret_cast<const uint4 *>(res_h) + j);
+        }
         tc::tmem_ld_wait();
         if (n >= p.N) continue;                           // warp-uniform: whole chunk outside the matrix
         const int rows_valid = min(32, p.M - (m0 + q * 32)), cols_valid = min(32, p.N - n);
@@ -358,11 +367,11 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
                 _Pragma("unroll") for (int j = 0; j < 32; ++j) if (n + j < p.N) f[j] += rp[j];
               }
             } else {
-              const __half *rp = reinterpret_cast<const __half *>(p.res) + (long long)b * p.bsr + (long long)m * p.ldr + n;
-              if (full_chunk && ((reinterpret_cast<uintptr_t>(rp) & 15) == 0)) {
+              const __half *rp = res_h;
+              if (fast_res) {
 #pragma unroll
                 for (int j = 0; j < 32; j += 8) {
-                  uint4 u = *reinterpret_cast<const uint4 *>(rp + j);
+                  const uint4 u = rr[j >> 3];
                   const __half2 *h = reinterpret_cast<const __half2 *>(&u);
 #pragma unroll
                   for (int t = 0; t < 4; ++t) {

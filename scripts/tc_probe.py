@@ -124,6 +124,23 @@ for name, kw in (("plain", {}), ("bias", {"bias": bias}), ("bias+gelu", {"bias":
     ms = e0.elapsed_time(e1) / 20
     perf.append({"M": M, "N": N, "K": K, "epilogue": name, "ms": ms, "tflops": 2 * M * N * K / ms / 1e9})
     print(perf[-1], flush=True)
+# the 1024 -> 1024 projection with bias + half residual (c_proj + x0 of the lattice decode) and the 4096 -> 1024 one (fc2 + x)
+for (M, N, K) in ((32768, 1024, 1024), (32768, 1024, 4096)):
+    A = torch.randn(M, K, device=dev).half(); W = torch.randn(N, K, device=dev).half() * 0.03; bias = torch.randn(N, device=dev)
+    R = torch.randn(M, N, device=dev).half()
+    out = torch.empty(M, N, dtype=torch.float16, device=dev)
+    for name, kw in (("bias", {"bias": bias}), ("bias+residual", {"bias": bias, "res": R})):
+        for _ in range(3):
+            tc.gemm(A, W, out=out, **kw)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(20):
+            tc.gemm(A, W, out=out, **kw)
+        e1.record(); torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / 20
+        perf.append({"M": M, "N": N, "K": K, "epilogue": name, "ms": ms, "tflops": 2 * M * N * K / ms / 1e9})
+        print(perf[-1], flush=True)
 res["perf"] = perf
 res["all_ok"] = bool(all_ok)
 os.makedirs("gpurun_out", exist_ok=True)
