@@ -275,10 +275,16 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
         // that the chunk otherwise waits for after its arithmetic)
         const __half *res_h = reinterpret_cast<const __half *>(p.res) + (long long)b * p.bsr + (long long)m * p.ldr + n;
         const bool fast_res = p.res && !p.res_f32 && row_ok && full_chunk && ((reinterpret_cast<uintptr_t>(res_h) & 15) == 0);
+        // (the same registers serve the saved pre-activations of the GELU' epilogue: that product has no residual)
+        const __half *aux_h = p.aux_in + (long long)b * p.bsaux + (long long)m * p.ldaux + n;
+        const bool fast_aux = p.act == 2 && !p.res && row_ok && full_chunk && ((reinterpret_cast<uintptr_t>(aux_h) & 15) == 0);
         uint4 rr[4];
         if (fast_res) {
 #pragma unroll
           for (int j = 0; j < 4; ++j) rr[j] = *(reinterpret_cast<const uint4 *>(res_h) + j);
+        } else if (fast_aux) {
+#pragma unroll
+          for (int j = 0; j < 4; ++j) rr[j] = __ldg(reinterpret_cast<const uint4 *>(aux_h) + j);
         }
         tc::tmem_ld_wait();
         if (n >= p.N) continue;                           // warp-uniform: whole chunk outside the matrix
@@ -337,11 +343,11 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
               _Pragma("unroll") for (int j = 0; j < 32; ++j) if (n + j < p.N) f[j] = __half2float(ai[j]) * (f[j] - p.alpha * rv);
             }
           } else if (p.act == 2) {
-            const __half *ai = p.aux_in + (long long)b * p.bsaux + (long long)m * p.ldaux + n;
+            const __half *ai = aux_h;
             if (full_chunk && ((reinterpret_cast<uintptr_t>(ai) & 15) == 0)) {
 #pragma unroll
               for (int j = 0; j < 32; j += 8) {
-                uint4 u = __ldg(reinterpret_cast<const uint4 *>(ai + j));
+                const uint4 u = fast_aux ? rr[j >> 3] : __ldg(reinterpret_cast<const uint4 *>(ai + j));
                 const __half2 *h = reinterpret_cast<const __half2 *>(&u);
 #pragma unroll
                 for (int t = 0; t < 4; ++t) {
