@@ -372,7 +372,7 @@ typedef struct foho_attn_desc {
   const void *v; int64_t ldv, hsv;
   void *out; int64_t ldo, out_img_stride;   /* fp16 [n_img][n_q][heads*64], 16-byte aligned */
   float *lse2;               /* optional OUT float32 [n_img][heads][lse2_stride]: log2-sum-exp of the scaled scores of query
-                                row q at [..][q] (variant 0) */
+                                row q at [..][q] (variants 0 and 2) */
   int64_t lse2_stride;       /* 0 = n_q; larger when a chunk of queries writes into the rows of a longer table */
 } foho_attn_desc;
 int foho_tc_attention(const foho_attn_desc *desc, void *cuda_stream);
