@@ -468,19 +468,30 @@ k_attn_fwd2(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUt
         if (tr) ATT_TRACE(grp * 4 + q, j, 1);
         tc::tc_fence_after();
         uint32_t sv[4][32];
+        // the second half of the row is in flight while the maximum of the first half is reduced (eight chains)
+        tc::tmem_ld32(s_addr, sv[0]); tc::tmem_ld32(s_addr + 32, sv[1]);
+        tc::tmem_ld_wait();
+        tc::tmem_ld32(s_addr + 64, sv[2]); tc::tmem_ld32(s_addr + 96, sv[3]);
+        float bm0 = -INFINITY, bm1 = -INFINITY, bm2 = -INFINITY, bm3 = -INFINITY, bm4 = -INFINITY, bm5 = -INFINITY, bm6 = -INFINITY, bm7 = -INFINITY;
 #pragma unroll
-        for (int c = 0; c < 4; ++c) tc::tmem_ld32(s_addr + c * 32, sv[c]);
+        for (int i = 0; i < 32; i += 4) {
+          bm0 = fmaxf(bm0, fmaxf(__uint_as_float(sv[0][i]), __uint_as_float(sv[0][i + 1])));
+          bm1 = fmaxf(bm1, fmaxf(__uint_as_float(sv[0][i + 2]), __uint_as_float(sv[0][i + 3])));
+          bm2 = fmaxf(bm2, fmaxf(__uint_as_float(sv[1][i]), __uint_as_float(sv[1][i + 1])));
+          bm3 = fmaxf(bm3, fmaxf(__uint_as_float(sv[1][i + 2]), __uint_as_float(sv[1][i + 3])));
+        }
         tc::tmem_ld_wait();
         tc::tc_fence_before();
         tc::mbar_arrive(&s_empty[grp]);
         if (tr) ATT_TRACE(grp * 4 + q, j, 2);
-        float bm0 = -INFINITY, bm1 = -INFINITY, bm2 = -INFINITY, bm3 = -INFINITY;
 #pragma unroll
-        for (int i = 0; i < 32; ++i) {
-          bm0 = fmaxf(bm0, __uint_as_float(sv[0][i])); bm1 = fmaxf(bm1, __uint_as_float(sv[1][i]));
-          bm2 = fmaxf(bm2, __uint_as_float(sv[2][i])); bm3 = fmaxf(bm3, __uint_as_float(sv[3][i]));
+        for (int i = 0; i < 32; i += 4) {
+          bm4 = fmaxf(bm4, fmaxf(__uint_as_float(sv[2][i]), __uint_as_float(sv[2][i + 1])));
+          bm5 = fmaxf(bm5, fmaxf(__uint_as_float(sv[2][i + 2]), __uint_as_float(sv[2][i + 3])));
+          bm6 = fmaxf(bm6, fmaxf(__uint_as_float(sv[3][i]), __uint_as_float(sv[3][i + 1])));
+          bm7 = fmaxf(bm7, fmaxf(__uint_as_float(sv[3][i + 2]), __uint_as_float(sv[3][i + 3])));
         }
-        const float bm = fmaxf(fmaxf(bm0, bm1), fmaxf(bm2, bm3)) * p.scale_log2;
+        const float bm = fmaxf(fmaxf(fmaxf(bm0, bm1), fmaxf(bm2, bm3)), fmaxf(fmaxf(bm4, bm5), fmaxf(bm6, bm7))) * p.scale_log2;
         float corr = 1.f;
         bool need = false;
         if (j == 0) {
